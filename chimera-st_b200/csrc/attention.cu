@@ -1,0 +1,164 @@
+// Padding-aware attention, head_dim 64: O = softmax(Q K^T + keymask) V with an online (flash-style)
+// softmax.  All arithmetic in fp32 on the CUDA cores: this is the exact-parity kernel (fp32 mode and
+// the tiny M-query memory stage); keys >= kv_len[b] get -inf exactly like the reference's
+// key_padding_mask, every query row is computed (padded query rows are live in the reference).
+//   tile: 64 queries x 64 keys, 256 threads, 4x4 micro-tiles; Q^T/K^T kept transposed in shared memory so
+//   the inner loops are float4 broadcast/stride-1 reads; P overwrites the K^T tile.
+#include "common.cuh"
+
+namespace cst {
+
+constexpr int AT_BQ = 64, AT_BK = 64, AT_D = 64, AT_LD = 68;
+constexpr int AT_SMEM = (2 * AT_D * AT_LD + AT_BK * AT_D) * 4;
+
+template <typename T>
+__global__ void __launch_bounds__(256) attention_kernel(const T* __restrict__ q, const T* __restrict__ k,
+                                                        const T* __restrict__ v, T* __restrict__ out,
+                                                        long long ldq, long long ldkv, long long ldo,
+                                                        int n_q, int q_rows_per_seg, int n_kv, int kv_rows_per_seg,
+                                                        const int32_t* __restrict__ kv_len) {
+  extern __shared__ float sm[];
+  float* Qt = sm;                         // [d][i], pitch AT_LD
+  float* Kt = sm + AT_D * AT_LD;          // [d][j]; reused as Pt [j][i]
+  float* Vs = sm + 2 * AT_D * AT_LD;      // [j][d], pitch 64
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * AT_BQ;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  int klen = kv_len ? kv_len[b] : n_kv;
+  if (klen > n_kv) klen = n_kv;
+
+  const T* qb = q + ((long long)b * q_rows_per_seg) * ldq + h * AT_D;
+  const T* kb = k + ((long long)b * kv_rows_per_seg) * ldkv + h * AT_D;
+  const T* vb = v + ((long long)b * kv_rows_per_seg) * ldkv + h * AT_D;
+
+  // Q tile -> Qt (transposed).  loader: row = tid & 63, 4 float4 columns per thread
+  {
+    const int r = tid & 63, c4 = tid >> 6;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int d = (c4 * 4 + i) * 4;
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (q0 + r < n_q) t = load4(qb + (long long)(q0 + r) * ldq + d);
+      Qt[(d + 0) * AT_LD + r] = t.x; Qt[(d + 1) * AT_LD + r] = t.y;
+      Qt[(d + 2) * AT_LD + r] = t.z; Qt[(d + 3) * AT_LD + r] = t.w;
+    }
+  }
+  float m_run[4], l_run[4], o[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    m_run[a] = -INFINITY; l_run[a] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) o[a][c] = 0.f;
+  }
+
+  for (int k0 = 0; k0 < klen; k0 += AT_BK) {
+    __syncthreads();                      // previous PV done (and Qt visible on the first pass)
+    {
+      const int r = tid & 63, c4 = tid >> 6;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int d = (c4 * 4 + i) * 4;
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f), u = t;
+        if (k0 + r < klen) {
+          t = load4(kb + (long long)(k0 + r) * ldkv + d);
+          u = load4(vb + (long long)(k0 + r) * ldkv + d);
+        }
+        Kt[(d + 0) * AT_LD + r] = t.x; Kt[(d + 1) * AT_LD + r] = t.y;
+        Kt[(d + 2) * AT_LD + r] = t.z; Kt[(d + 3) * AT_LD + r] = t.w;
+        *reinterpret_cast<float4*>(&Vs[r * AT_D + d]) = u;
+      }
+    }
+    __syncthreads();
+    float s[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) s[a][c] = 0.f;
+#pragma unroll 8
+    for (int d = 0; d < AT_D; ++d) {
+      const float4 qa = *reinterpret_cast<const float4*>(&Qt[d * AT_LD + ty * 4]);
+      const float4 kc = *reinterpret_cast<const float4*>(&Kt[d * AT_LD + tx * 4]);
+      const float qv[4] = {qa.x, qa.y, qa.z, qa.w}, kv[4] = {kc.x, kc.y, kc.z, kc.w};
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) s[a][c] = fmaf(qv[a], kv[c], s[a][c]);
+    }
+    // mask + online softmax (row statistics shared by the 16 lanes of a row group)
+    float scale_o[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (k0 + tx * 4 + c >= klen) s[a][c] = -INFINITY;
+        mx = fmaxf(mx, s[a][c]);
+      }
+#pragma unroll
+      for (int off = 8; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+      const float m_new = fmaxf(m_run[a], mx);          // finite: every visited tile has >= 1 valid key
+      float rs = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { s[a][c] = expf(s[a][c] - m_new); rs += s[a][c]; }
+#pragma unroll
+      for (int off = 8; off > 0; off >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, off);
+      scale_o[a] = expf(m_run[a] - m_new);              // exp(-inf) = 0 on the first tile
+      l_run[a] = l_run[a] * scale_o[a] + rs;
+      m_run[a] = m_new;
+    }
+    __syncthreads();                      // all S reads of Kt done -> overwrite with P^T
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      *reinterpret_cast<float4*>(&Kt[(tx * 4 + c) * AT_LD + ty * 4]) = make_float4(s[0][c], s[1][c], s[2][c], s[3][c]);
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) o[a][c] *= scale_o[a];
+#pragma unroll 8
+    for (int j = 0; j < AT_BK; ++j) {
+      const float4 pa = *reinterpret_cast<const float4*>(&Kt[j * AT_LD + ty * 4]);
+      const float4 vc = *reinterpret_cast<const float4*>(&Vs[j * AT_D + tx * 4]);
+      const float pv[4] = {pa.x, pa.y, pa.z, pa.w}, vv[4] = {vc.x, vc.y, vc.z, vc.w};
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) o[a][c] = fmaf(pv[a], vv[c], o[a][c]);
+    }
+  }
+  T* ob = out + ((long long)b * q_rows_per_seg) * ldo + h * AT_D + tx * 4;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int r = q0 + ty * 4 + a;
+    if (r >= n_q) continue;
+    const float inv = l_run[a] > 0.f ? 1.0f / l_run[a] : 0.f;
+    store4(ob + (long long)r * ldo, make_float4(o[a][0] * inv, o[a][1] * inv, o[a][2] * inv, o[a][3] * inv));
+  }
+}
+}  // namespace cst
+
+extern "C" int cst_attention(const void* q, const void* k, const void* v, void* out, int dtype,
+                             long long ldq, long long ldkv, long long ldo,
+                             int B, int H, int n_q, int q_rows_per_seg, int n_kv, int kv_rows_per_seg,
+                             const int32_t* kv_len, void* stream) {
+  using namespace cst;
+  CST_REQUIRE(q && k && v && out && B > 0 && H > 0 && n_q > 0 && n_kv > 0, "cst_attention: bad args");
+  CST_REQUIRE(n_q <= q_rows_per_seg && n_kv <= kv_rows_per_seg, "cst_attention: n_q/n_kv exceed rows per segment");
+  CST_REQUIRE(ldq % 8 == 0 && ldkv % 8 == 0 && ldo % 8 == 0, "cst_attention: leading dims must be multiples of 8");
+  CST_REQUIRE(H <= 65535 && B <= 65535, "cst_attention: grid too large");
+  dim3 grid(cdiv(n_q, AT_BQ), H, B);
+  cudaStream_t st = (cudaStream_t)stream;
+  static bool attr[2] = {false, false};
+  if (dtype == CST_F32) {
+    if (!attr[0]) { CST_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM)); attr[0] = true; }
+    attention_kernel<float><<<grid, 256, AT_SMEM, st>>>((const float*)q, (const float*)k, (const float*)v, (float*)out,
+                                                         ldq, ldkv, ldo, n_q, q_rows_per_seg, n_kv, kv_rows_per_seg, kv_len);
+  } else if (dtype == CST_BF16) {
+    if (!attr[1]) { CST_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM)); attr[1] = true; }
+    attention_kernel<__nv_bfloat16><<<grid, 256, AT_SMEM, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v,
+                                                                 (__nv_bfloat16*)out, ldq, ldkv, ldo, n_q, q_rows_per_seg, n_kv, kv_rows_per_seg, kv_len);
+  } else {
+    CST_REQUIRE(false, "cst_attention: bad dtype %d", dtype);
+  }
+  CST_LAUNCH_CHECK();
+  return CST_OK;
+}

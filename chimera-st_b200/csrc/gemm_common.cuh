@@ -1,0 +1,93 @@
+// Epilogue shared by the FFMA (fp32) and tcgen05 (bf16) GEMM kernels: bias, activation, alpha,
+// residual, GLU on adjacent column pairs, row remap / masking, f32 or bf16 store.
+#pragma once
+#include "common.cuh"
+
+namespace cst {
+
+struct GemmDev {          // device copy of cst_gemm_params (pointers already typed by the launcher)
+  const void* A; const void* W; const float* bias; const float* residual; void* C;
+  int c_dtype;
+  int M, N, K;
+  long long lda, ldc, ldr, a_limit;     // a_limit: number of addressable A elements per batch z
+  int act; float alpha;
+  int nb_inner;
+  long long a_bs_outer, a_bs_inner, w_bs_inner, c_bs_outer, c_bs_inner, r_bs_outer, r_bs_inner;
+  int bias_bs_inner;
+  int rows_per_seg, seg_rows_valid; long long out_rows_per_seg; int out_row_off;
+  const int32_t* seg_len; int segs_per_outer;
+};
+
+struct RowInfo { long long out_row; bool store; bool zero; };
+
+__device__ __forceinline__ RowInfo row_info(const GemmDev& p, int m, int zo) {
+  RowInfo r;
+  const int seg = m / p.rows_per_seg, t = m - seg * p.rows_per_seg;
+  r.store = (m < p.M) && (t < p.seg_rows_valid);
+  r.zero = false;
+  if (p.seg_len != nullptr && r.store) r.zero = t >= p.seg_len[zo * p.segs_per_outer + seg];
+  r.out_row = (long long)seg * p.out_rows_per_seg + t + p.out_row_off;
+  return r;
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// 8 consecutive accumulator columns starting at column n (n % 8 == 0, n < N) of one output row.
+// c_off / r_off: batch offsets (elements) into C / residual; bias already offset for the batch.
+__device__ __forceinline__ void epilogue8(const GemmDev& p, const RowInfo& ri, int n, const float* bias,
+                                          long long c_off, long long r_off, const float (&acc)[8]) {
+  if (!ri.store || n >= p.N) return;
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = acc[j] + (bias ? __ldg(bias + n + j) : 0.f);
+  if (p.act == CST_ACT_GLU) {
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = v[2 * j] * sigmoidf_(v[2 * j + 1]) * p.alpha;
+    const int nc = n >> 1;
+    if (p.residual) {
+      const float4 r = load4(p.residual + r_off + ri.out_row * p.ldr + nc);
+      o[0] += r.x; o[1] += r.y; o[2] += r.z; o[3] += r.w;
+    }
+    if (ri.zero) { o[0] = o[1] = o[2] = o[3] = 0.f; }
+    const long long off = c_off + ri.out_row * p.ldc + nc;
+    if (p.c_dtype == CST_BF16) store4((__nv_bfloat16*)p.C + off, make_float4(o[0], o[1], o[2], o[3]));
+    else store4((float*)p.C + off, make_float4(o[0], o[1], o[2], o[3]));
+    return;
+  }
+  if (p.act == CST_ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
+  } else if (p.act == CST_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] *= p.alpha;
+  if (p.residual) {
+    const float* rp = p.residual + r_off + ri.out_row * p.ldr + n;
+    const float4 r0 = load4(rp), r1 = load4(rp + 4);
+    v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
+    v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+  }
+  if (ri.zero) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+  }
+  const long long off = c_off + ri.out_row * p.ldc + n;
+  if (p.c_dtype == CST_BF16) {
+    uint4 u;
+    u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+    u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>((__nv_bfloat16*)p.C + off) = u;
+  } else {
+    float* o = (float*)p.C + off;
+    store4(o, make_float4(v[0], v[1], v[2], v[3]));
+    store4(o + 4, make_float4(v[4], v[5], v[6], v[7]));
+  }
+}
+
+int launch_gemm_f32(const GemmDev& p, int nz, cudaStream_t st);
+int launch_gemm_tc(const cst_gemm_params& hp, const GemmDev& p, int nz, cudaStream_t st);
+
+}  // namespace cst

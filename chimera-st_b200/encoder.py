@@ -1,0 +1,164 @@
+"""Host-side mirror of the reference encoder module for the audio branch.
+
+`B200InterlinguaEncoder` keeps the interface of
+`S2T_W2V2_TransformerInterlinguaEncoder` (fairseq/models/chimera/w2v2_transformer_interlingua.py:155-312):
+
+    forward(src_tokens [B,L] float, src_lengths [B] long, **extra) -> EncoderOut
+    _get_w2v_feature(src_tokens, src_lengths) -> (feature [B,T',768], padding_mask [B,T'] bool, lengths [B] long)
+    reorder_encoder_out(encoder_out, new_order), max_positions() -> None, upgrade_state_dict_named(sd, name)
+
+and the SAME parameter names / shapes (state-dict layout of SURVEY.md App. D, incl. the dead
+pre-training heads and `embed_positions._float_tensor`), so a reference checkpoint loads with
+`load_state_dict(strict=True)`.  The arithmetic is done only by the CUDA kernels behind the C ABI
+(`include/chimera_st_b200.h`); without the built library or without a CUDA device `forward` raises.
+
+Not reproduced (out of scope): the text (MT) branch, training-time dropout / LayerDrop,
+`modal_embedding` debug option, `non_shared_encoder_layers`.  They raise NotImplementedError.
+"""
+from collections import OrderedDict
+from typing import List, NamedTuple, Optional
+
+import torch
+import torch.nn as nn
+
+from . import weights as _weights
+from .plan import EncoderPlan
+from .synth import encoder_param_spec, ENC_DIM
+
+
+class EncoderOut(NamedTuple):
+    """Field-for-field copy of fairseq.models.fairseq_encoder.EncoderOut (fairseq_encoder.py:13-23)."""
+    encoder_out: torch.Tensor                              # M x B x C
+    encoder_padding_mask: Optional[torch.Tensor]           # B x M, all False (not None: interlingua:301-305)
+    encoder_embedding: Optional[torch.Tensor]
+    encoder_states: Optional[List[torch.Tensor]]
+    src_tokens: Optional[torch.Tensor]
+    src_lengths: Optional[torch.Tensor]
+
+
+class _Node(nn.Module):
+    """Anonymous container: only there to give parameters the reference's dotted names."""
+
+
+def _register(root, dotted, tensor, buffer=False):
+    parts = dotted.split(".")
+    mod = root
+    for p in parts[:-1]:
+        if not hasattr(mod, p):
+            mod.add_module(p, _Node())
+        mod = getattr(mod, p)
+    if buffer:
+        mod.register_buffer(parts[-1], tensor)
+    else:
+        mod.register_parameter(parts[-1], nn.Parameter(tensor, requires_grad=False))
+
+
+class B200InterlinguaEncoder(nn.Module):
+    MAX_PLANS = 16          # cached (B, L) shapes; each plan owns its activation buffers
+
+    def __init__(self, interlingua_length=16, dtype=torch.float32, use_graph=True, dead_heads=True,
+                 text_vocab=0, encoder_out_dtype=None):
+        super().__init__()
+        if dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError("compute dtype must be float32 or bfloat16")
+        self.interlingua_length = interlingua_length
+        self.compute_dtype = dtype
+        self.use_graph = use_graph
+        self.encoder_out_dtype = encoder_out_dtype
+        self.no_interlingua = False
+        for name, shape, _, _ in encoder_param_spec(interlingua_length, dead_heads, text_vocab):
+            _register(self, name, torch.zeros(shape), buffer=name.endswith("_float_tensor"))
+        self._prepared = None
+        self._plans = OrderedDict()
+        self.last_launches = 0
+        self.register_load_state_dict_post_hook(lambda m, k: m.invalidate())
+
+    # ---- reference-compatible surface ------------------------------------------------------------
+    def max_positions(self):
+        return None                                           # interlingua:204-205
+
+    def upgrade_state_dict_named(self, state_dict, name):
+        key = name + ".text_embed_tokens.weight"              # interlingua:198-202
+        if key in state_dict and not hasattr(self, "text_embed_tokens"):
+            state_dict.pop(key)
+        return state_dict
+
+    def reorder_encoder_out(self, encoder_out, new_order):
+        """w2v2_transformer.py:388-429 (beam replication): index_select on dim 1 / dim 0."""
+        eo = encoder_out.encoder_out.index_select(1, new_order)
+        pm = encoder_out.encoder_padding_mask
+        pm = pm if pm is None else pm.index_select(0, new_order)
+        return EncoderOut(eo, pm, None, None, None, None)
+
+    def invalidate(self):
+        """Drop prepared weights and cached plans (call after mutating parameters in place)."""
+        self._prepared = None
+        self._plans.clear()
+
+    # ---- plumbing ------------------------------------------------------------------------------------
+    def _device(self):
+        dev = self.layer_norm.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("B200InterlinguaEncoder runs only on a CUDA device (no CPU fallback); call .cuda()")
+        return dev
+
+    def _plan(self, B, L):
+        dev = self._device()
+        if self._prepared is None:
+            self._prepared = _weights.prepare(self.state_dict(), dev, self.compute_dtype)
+        key = (B, L)
+        plan = self._plans.get(key)
+        if plan is None:
+            while len(self._plans) >= self.MAX_PLANS:
+                self._plans.popitem(last=False)
+            plan = EncoderPlan(self._prepared, B, L, self.interlingua_length, self.compute_dtype, dev, self.use_graph)
+            self._plans[key] = plan
+        else:
+            self._plans.move_to_end(key)
+        return plan
+
+    def _check_inputs(self, src_tokens, src_lengths):
+        if not src_tokens.dtype.is_floating_point:
+            raise NotImplementedError("text (MT) branch is out of scope for the B200 path (SURVEY.md §8(f) row 2)")
+        if self.training:
+            raise NotImplementedError("training-mode forward (dropout / LayerDrop) is not implemented; call .eval()")
+        if src_tokens.dim() != 2 or src_lengths.shape != (src_tokens.shape[0],):
+            raise ValueError("expected src_tokens [B,L], src_lengths [B]")
+
+    @torch.no_grad()
+    def _get_w2v_feature(self, src_tokens, src_lengths):
+        self._check_inputs(src_tokens, src_lengths)
+        B, L = src_tokens.shape
+        plan = self._plan(B, L)
+        plan.load_inputs(src_tokens.float(), src_lengths)
+        self.last_launches = plan.run(upto="w2v")
+        return plan.view("w2v_out").clone(), plan.view("frame_mask"), plan.w2v_len64.clone()
+
+    @torch.no_grad()
+    def forward(self, src_tokens, src_lengths, **extra_args):      # extra: the collater's stray `mask=` kwarg
+        self._check_inputs(src_tokens, src_lengths)
+        B, L = src_tokens.shape
+        plan = self._plan(B, L)
+        plan.load_inputs(src_tokens.float(), src_lengths)
+        self.last_launches = plan.run()
+        if self.no_interlingua:                                    # interlingua:260-262
+            out = plan.view("h_enc").transpose(0, 1)
+        else:
+            out = plan.memories()
+        out = out.to(self.encoder_out_dtype or src_tokens.dtype).contiguous()
+        pad = torch.zeros(B, out.shape[0], dtype=torch.bool, device=out.device)
+        return EncoderOut(out, pad, None, None, None, None)
+
+
+def build_encoder_from_state_dict(state_dict, interlingua_length=None, dtype=torch.float32, device="cuda",
+                                  use_graph=True):
+    """Convenience: infer M from the checkpoint, load strictly, move to the device."""
+    sd = state_dict
+    if any(k.startswith("encoder.") for k in sd):
+        sd = {k[len("encoder."):]: v for k, v in sd.items() if k.startswith("encoder.")}
+    M = interlingua_length or sd["interlingua_embedding.weight"].shape[0]
+    dead = "wav2vec_model.mask_emb" in sd
+    vocab = sd["text_embed_tokens.weight"].shape[0] if "text_embed_tokens.weight" in sd else 0
+    enc = B200InterlinguaEncoder(M, dtype=dtype, use_graph=use_graph, dead_heads=dead, text_vocab=vocab)
+    enc.load_state_dict(sd, strict=True)
+    return enc.to(device).eval()

@@ -1,0 +1,90 @@
+"""One-time weight preparation: reference state-dict layout -> kernel operand layout (device).
+
+Input keys are the reference encoder's, optionally prefixed "encoder.".  Both
+weight-norm forms of the pos-conv are accepted: `pos_conv.0.weight_g/_v` (checkpoint) or the folded
+`pos_conv.0.weight` left by make_generation_fast_ (fairseq/models/fairseq_model.py:175-182).
+
+Layout rules (all exact re-arrangements, no arithmetic except the folds noted):
+  * conv kernels [Cout, Cin, k] -> [Cout, k*Cin] (tap-major) so a window of channels-last frames is one
+    contiguous K run (implicit GEMM).
+  * q projection and bias are multiplied by head_dim**-0.5 = 1/8 (exact power of two; the reference
+    scales q after the bias, multihead_attention.py -> torch MHA), q|k|v concatenated.
+  * subsampler convs: output channels interleaved (value_i, gate_i) so GLU pairs are adjacent columns.
+  * pos-conv: w = g * v / ||v||_(0,1) (wav2vec2.py:785), split per group to [16, 48, 128*64] with the 48
+    input channels of a tap zero-padded to 64 lanes (one 128-byte swizzle row per tap in bf16).
+GEMM operands are stored in `act_dtype` (fp32 or bf16); biases / norm parameters stay fp32.
+"""
+import torch
+
+from .synth import CONV_LAYERS, W2V_LAYERS, ENC_LAYERS, MEM_LAYERS, POS_GROUPS, POS_K
+
+
+def _strip(sd):
+    if any(k.startswith("encoder.") for k in sd):
+        sd = {k[len("encoder."):]: v for k, v in sd.items() if k.startswith("encoder.")}
+    return sd
+
+
+def _glu_interleave(w):
+    half = w.shape[0] // 2
+    return torch.stack((w[:half], w[half:]), dim=1).reshape(w.shape)
+
+
+def prepare(state_dict, device, act_dtype):
+    sd = _strip(state_dict)
+    f32 = lambda t: t.detach().to(device=device, dtype=torch.float32).contiguous()   # noqa: E731
+    op = lambda t: t.detach().to(device=device, dtype=torch.float32).to(act_dtype).contiguous()   # noqa: E731
+    W = "wav2vec_model."
+    P = {}
+    fe = W + "feature_extractor.conv_layers."
+    P["conv0_w"] = f32(sd[fe + "0.0.weight"].reshape(512, 10))
+    P["gn_g"], P["gn_b"] = f32(sd[fe + "0.2.weight"]), f32(sd[fe + "0.2.bias"])
+    for i in range(1, len(CONV_LAYERS)):
+        w = sd[fe + f"{i}.0.weight"]                       # [512, 512, k]
+        P[f"conv{i}_w"] = op(w.permute(0, 2, 1).reshape(w.shape[0], -1))
+    P["ln_feat_g"], P["ln_feat_b"] = f32(sd[W + "layer_norm.weight"]), f32(sd[W + "layer_norm.bias"])
+    P["proj_w"], P["proj_b"] = op(sd[W + "post_extract_proj.weight"]), f32(sd[W + "post_extract_proj.bias"])
+
+    pc = W + "encoder.pos_conv.0."
+    if pc + "weight" in sd:
+        w = sd[pc + "weight"].float()
+    else:
+        v, g = sd[pc + "weight_v"].float(), sd[pc + "weight_g"].float()
+        w = v * (g / v.norm(dim=(0, 1), keepdim=True))
+    cg = w.shape[1]                                        # 48 channels per group
+    wg = w.view(POS_GROUPS, cg, cg, POS_K).permute(0, 1, 3, 2)      # [g, co, tap, ci]
+    wp = torch.zeros(POS_GROUPS, cg, POS_K, 64, dtype=torch.float32)
+    wp[..., :cg] = wg
+    P["pos_w"] = op(wp.reshape(POS_GROUPS, cg, POS_K * 64))
+    P["pos_b"] = f32(sd[pc + "bias"])
+    P["ln_enc_g"], P["ln_enc_b"] = f32(sd[W + "encoder.layer_norm.weight"]), f32(sd[W + "encoder.layer_norm.bias"])
+
+    def layer(prefix, fused_qkv=True):
+        a = prefix + "self_attn."
+        d = {}
+        wq, bq = sd[a + "q_proj.weight"].float() * 0.125, sd[a + "q_proj.bias"].float() * 0.125
+        wk, bk = sd[a + "k_proj.weight"].float(), sd[a + "k_proj.bias"].float()
+        wv, bv = sd[a + "v_proj.weight"].float(), sd[a + "v_proj.bias"].float()
+        if fused_qkv:
+            d["qkv_w"], d["qkv_b"] = op(torch.cat((wq, wk, wv), 0)), f32(torch.cat((bq, bk, bv), 0))
+        else:
+            d["q_w"], d["q_b"] = op(wq), f32(bq)
+            d["kv_w"], d["kv_b"] = op(torch.cat((wk, wv), 0)), f32(torch.cat((bk, bv), 0))
+        d["o_w"], d["o_b"] = op(sd[a + "out_proj.weight"]), f32(sd[a + "out_proj.bias"])
+        d["ln1_g"], d["ln1_b"] = f32(sd[prefix + "self_attn_layer_norm.weight"]), f32(sd[prefix + "self_attn_layer_norm.bias"])
+        d["fc1_w"], d["fc1_b"] = op(sd[prefix + "fc1.weight"]), f32(sd[prefix + "fc1.bias"])
+        d["fc2_w"], d["fc2_b"] = op(sd[prefix + "fc2.weight"]), f32(sd[prefix + "fc2.bias"])
+        d["ln2_g"], d["ln2_b"] = f32(sd[prefix + "final_layer_norm.weight"]), f32(sd[prefix + "final_layer_norm.bias"])
+        return d
+
+    P["w2v_layers"] = [layer(W + f"encoder.layers.{i}.") for i in range(W2V_LAYERS)]
+    for i in range(2):
+        w = sd[f"subsample.conv_layers.{i}.weight"].float()        # [1024, Cin, 5]
+        w = w.permute(0, 2, 1).reshape(w.shape[0], -1)
+        P[f"sub{i}_w"] = op(_glu_interleave(w))
+        P[f"sub{i}_b"] = f32(_glu_interleave(sd[f"subsample.conv_layers.{i}.bias"].float()))
+    P["enc_layers"] = [layer(f"transformer_layers.{i}.") for i in range(ENC_LAYERS)]
+    P["ln_out_g"], P["ln_out_b"] = f32(sd["layer_norm.weight"]), f32(sd["layer_norm.bias"])
+    P["mem_embed"] = f32(sd["interlingua_embedding.weight"])
+    P["mem_layers"] = [layer(f"interlingua_layers.{i}.", fused_qkv=False) for i in range(MEM_LAYERS)]
+    return P

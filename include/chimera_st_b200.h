@@ -1,0 +1,124 @@
+/* chimera_st_b200.h -- C ABI of the B200-native (sm_100a) Chimera-ST speech-encoding path.
+ *
+ * The reference (Glaciohound/Chimera-ST, a fairseq fork) has NO native seam on this path: every
+ * stage is a Python module calling torch ops.  Each entry point below therefore names the
+ * reference *Python* interface whose arithmetic it replaces (paths under the reference tree);
+ * INTEGRATION.md shows the ctypes binding and the fairseq `--user-dir` plugin that calls them.
+ *
+ * Conventions
+ *   - plain pointers + sizes only; all data pointers are DEVICE pointers unless named *_host;
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream);
+ *   - nothing allocates, nothing synchronises the stream; workspaces are caller-owned;
+ *   - every function returns 0 on success, else a CST_ERR_* code; cst_last_error() (thread-local)
+ *     gives the message.  There is no CPU fallback anywhere: no device => error.
+ *   - activations are row-major [rows, channels] ("channels-last"); a batch of B utterances is
+ *     B segments of `rows_per_seg` rows.  dtypes: CST_F32 or CST_BF16.
+ */
+#ifndef CHIMERA_ST_B200_H_
+#define CHIMERA_ST_B200_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CST_ABI_VERSION 1
+
+enum { CST_OK = 0, CST_ERR_ARG = 1, CST_ERR_CUDA = 2, CST_ERR_UNSUPPORTED = 3 };
+enum { CST_F32 = 0, CST_BF16 = 1 };
+enum { CST_ACT_NONE = 0, CST_ACT_GELU = 1, CST_ACT_RELU = 2, CST_ACT_GLU = 3 };
+
+int cst_abi_version(void);
+const char* cst_last_error(void);
+/* Fills name (<=255 chars), SM count, cc major/minor of the current device. */
+int cst_device_info(char* name, int name_cap, int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- a4: frame-level padding rule + lengths --------------------------------------------------
+ * Replaces: lengths_to_padding_mask (fairseq/data/data_utils.py:491-495), the trim/view/all frame
+ * mask of Wav2Vec2Model.forward (fairseq/models/wav2vec/wav2vec2.py:543-548), output_length of
+ * _get_w2v_feature (fairseq/models/chimera/w2v2_transformer.py:327-333) and
+ * Conv1dSubsampler.get_out_seq_lens_tensor (fairseq/models/speech_to_text/s2t_transformer.py:63-67).
+ * src_len [B] int64 (device); L = padded sample width; n_frames = T'.
+ * Outputs (device; any may be NULL): w2v_valid [B] int32 = min(T', ceil(len/(L/T'))),
+ * sub_valid [B] int32 = subsampled twice, w2v_len64 [B] int64, frame_mask [B*T'] uint8 (1 = padded). */
+int cst_frame_lengths(const int64_t* src_len, int B, int L, int n_frames,
+                      int32_t* w2v_valid, int32_t* sub_valid, int64_t* w2v_len64, uint8_t* frame_mask,
+                      void* stream);
+
+/* ---- a1: conv0 (1->512, k10, s5, no bias) + GroupNorm(512 groups, padded-time statistics) + GELU ----
+ * Replaces: ConvFeatureExtractionModel block 0 (wav2vec2.py:697-734,755-763; Fp32GroupNorm
+ * fp32_group_norm.py:17-25).  Two launches:
+ *   stats : per (b,c) mean / rstd over ALL T0 padded frames, derived from the 10x10 lag-correlation
+ *           of the waveform (reads the waveform once; no [B,512,T0] intermediate) -> scale_shift
+ *           [B,512] float2 {gamma*rstd, beta - mean*gamma*rstd};  stats_ws: B*72 doubles.
+ *   apply : recompute conv, normalise, GELU, store channels-last out[b, t, c] for t < T0, zeros for
+ *           T0 <= t < rows_per_seg.  wave [B,L] f32; w [512,10] f32. */
+int cst_conv0_stats(const float* wave, int B, int L, const float* w, const float* gamma, const float* beta,
+                    float* scale_shift, double* stats_ws, void* stream);
+int cst_conv0_apply(const float* wave, int B, int L, const float* w, const float* scale_shift,
+                    void* out, int out_dtype, int rows_per_seg, void* stream);
+
+/* ---- GEMM with fused epilogue: the conv stack (implicit GEMM), every projection and FFN ------------
+ * Replaces: nn.Conv1d of blocks 1-6 (wav2vec2.py:707,733-734), post_extract_proj (wav2vec2.py:550-551),
+ * the grouped pos_conv (wav2vec2.py:773-786,823-825), F.multi_head_attention_forward's in/out
+ * projections (fairseq/modules/multihead_attention.py:165-187), fc1/fc2 (wav2vec2.py:948-957,
+ * fairseq/modules/transformer_layer.py:148-154) and Conv1dSubsampler's convs+GLU
+ * (s2t_transformer.py:69-77).
+ *
+ *   acc[m,n] = sum_k A[zoff_a + m*lda + k] * W[zoff_w + n*K + k]          (lda < K: overlapping conv windows)
+ *   v = act(acc + bias[n]) * alpha + residual[row,n]     (GLU: v = a * sigmoid(g) on column pairs 2i,2i+1)
+ *   C[zoff_c + row*ldc + n] = v          row = seg*out_rows_per_seg + t + out_row_off, (seg,t) = divmod(m, rows_per_seg)
+ *   rows with t >= seg_rows_valid are not stored; with seg_len != NULL rows with t >= seg_len[seg]
+ *   (seg counted across batch z_outer) are stored as 0 (x[padding_mask] = 0, wav2vec2.py:820-821).
+ * Batched over z = zo*nb_inner + zi (pos-conv: zo = utterance, zi = group).
+ * CST_F32 inputs use an FFMA kernel (true-fp32 accumulate: the 1e-5 parity mode); CST_BF16 inputs use the
+ * TMA + tcgen05/TMEM kernel (fp32 accumulate in tensor memory).  A and W must share a dtype. */
+typedef struct cst_gemm_params {
+  const void* A; const void* W; const float* bias; const float* residual; void* C;
+  int ab_dtype; int c_dtype;
+  int M, N, K;
+  long long lda, ldc, ldr;
+  long long a_rows;              /* rows addressable from A (per batch z) without leaving the buffer */
+  int act; float alpha;
+  int nb_outer, nb_inner;
+  long long a_bs_outer, a_bs_inner, w_bs_inner, c_bs_outer, c_bs_inner, r_bs_outer, r_bs_inner;
+  int bias_bs_inner;
+  int rows_per_seg, seg_rows_valid; long long out_rows_per_seg; int out_row_off;
+  const int32_t* seg_len; int segs_per_outer;
+} cst_gemm_params;
+int cst_gemm(const cst_gemm_params* p, void* stream);
+
+/* ---- LayerNorm over the channel axis (eps 1e-5), one warp per row ----------------------------------
+ * Replaces: LayerNorm of wav2vec2.py:539-540, 827-828, 945/957, transformer_layer.py:129-155,
+ * w2v2_transformer_interlingua.py:254-255.  x f32 [rows, C] (C in {512,768}); writes out_f32 and/or
+ * out_lp (dtype lp_dtype) -- the fp32 residual stream and the GEMM operand copy.  Row remap as in
+ * cst_gemm; rows with t >= seg_rows_valid are written as zeros when zero_invalid != 0. */
+int cst_layernorm(const float* x, long long ldx, const float* gamma, const float* beta,
+                  float* out_f32, void* out_lp, int lp_dtype, long long ldo,
+                  int rows, int C, int rows_per_seg, int seg_rows_valid,
+                  long long out_rows_per_seg, int out_row_off, int zero_invalid, void* stream);
+
+/* Generic dtype/layout copy x[rows, C] -> y: used for (a) the pos-conv operand layout
+ * [B, 16 groups, Tpad, 64] (48 channels + 16 zero lanes, 64 zero frames each side) and (b) broadcasting
+ * the M memory embeddings over the batch (w2v2_transformer_interlingua.py:268-269). */
+int cst_posconv_pack(const float* x, int B, int rows_per_seg, int n_frames, void* xg, int xg_dtype,
+                     int t_pad_rows, void* stream);
+int cst_broadcast_rows(const float* src, int rows, int C, int B, float* dst, void* stream);
+
+/* ---- padding-aware attention: softmax(q k^T + keymask) v, head_dim 64 ---------------------------------
+ * Replaces: the attention core of F.multi_head_attention_forward as called from
+ * multihead_attention.py:165-187 (wav2vec2 layers wav2vec2.py:938-945 with a -inf key-padding mask;
+ * shared layers transformer_layer.py:131-137; memory stage w2v2_transformer_interlingua.py:289-298,
+ * where kv_len == NULL: memories attend ALL T2 frames incl. padded ones).
+ * q is pre-scaled (1/8 is folded into W_q, b_q: exact power of two).  ALL query rows are computed.
+ * q [B*q_rows_per_seg, ldq], k/v [B*kv_rows_per_seg, ldkv]; head h at columns h*64..h*64+63.
+ * kv_len [B] int32 (device) or NULL => n_kv keys for every utterance. */
+int cst_attention(const void* q, const void* k, const void* v, void* out, int dtype,
+                  long long ldq, long long ldkv, long long ldo,
+                  int B, int H, int n_q, int q_rows_per_seg, int n_kv, int kv_rows_per_seg,
+                  const int32_t* kv_len, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHIMERA_ST_B200_H_ */

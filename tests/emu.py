@@ -1,0 +1,180 @@
+"""TEST INFRASTRUCTURE: a host (numpy/torch) emulator of the C ABI in include/chimera_st_b200.h.
+
+It interprets the same argument structs / pointers as the CUDA library, on HOST memory, in fp32.
+Purpose: run the real `EncoderPlan` launch sequence on CPU tensors so that all host-side logic --
+frame geometry, buffer layouts, weight re-arrangement, row remapping, the order of launches -- is
+checked against the oracle without a GPU.  It doubles as an executable statement of each entry
+point's semantics.  Never imported by the product package.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+F32 = 0
+
+
+def _mem(ptr, n, dtype=np.float32):
+    if n <= 0:
+        return np.zeros(0, dtype)
+    buf = (C.c_char * (n * np.dtype(dtype).itemsize)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype)
+
+
+class EmuLib:
+    def __init__(self):
+        self.calls = []
+
+    # ---- a4
+    def cst_frame_lengths(self, src_len, B, L, n_frames, w2v_valid, sub_valid, w2v_len64, frame_mask, stream):
+        lens = _mem(src_len, B, np.int64)
+        r = L // n_frames
+        v = np.minimum(n_frames, -(-lens // r))
+        if w2v_valid:
+            _mem(w2v_valid, B, np.int32)[:] = v
+        if w2v_len64:
+            _mem(w2v_len64, B, np.int64)[:] = v
+        if sub_valid:
+            _mem(sub_valid, B, np.int32)[:] = ((v + 1) // 2 + 1) // 2
+        if frame_mask:
+            _mem(frame_mask, B * n_frames, np.uint8).reshape(B, n_frames)[:] = np.arange(n_frames)[None, :] >= v[:, None]
+        self.calls.append("frame_lengths")
+        return 0
+
+    # ---- a1
+    def cst_conv0_stats(self, wave, B, L, w, gamma, beta, scale_shift, ws, stream):
+        x = torch.from_numpy(_mem(wave, B * L).reshape(B, L).copy()).double()
+        wt = torch.from_numpy(_mem(w, 5120).reshape(512, 10).copy()).double()
+        T0 = (L - 10) // 5 + 1
+        win = x.unfold(1, 10, 5)[:, :T0]                              # [B,T0,10]
+        S = win.sum(1)                                               # lag sums
+        R = torch.einsum("bti,btj->bij", win, win)                   # lag correlations
+        mean = (S @ wt.T) / T0
+        ey2 = torch.einsum("ci,bij,cj->bc", wt, R, wt) / T0
+        rstd = 1.0 / torch.sqrt((ey2 - mean * mean).clamp_min(0) + 1e-5)
+        g = torch.from_numpy(_mem(gamma, 512).copy()).double()
+        bt = torch.from_numpy(_mem(beta, 512).copy()).double()
+        sc = g * rstd
+        out = torch.stack((sc, bt - mean * sc), -1).float().numpy()
+        _mem(scale_shift, B * 512 * 2).reshape(B, 512, 2)[:] = out
+        self.calls.append("conv0_stats")
+        return 0
+
+    def cst_conv0_apply(self, wave, B, L, w, scale_shift, out, out_dtype, rows_per_seg, stream):
+        assert out_dtype == F32
+        x = torch.from_numpy(_mem(wave, B * L).reshape(B, L).copy())
+        wt = torch.from_numpy(_mem(w, 5120).reshape(512, 1, 10).copy())
+        ss = torch.from_numpy(_mem(scale_shift, B * 1024).reshape(B, 512, 2).copy())
+        y = torch.nn.functional.conv1d(x.unsqueeze(1), wt, stride=5)  # [B,512,T0]
+        y = y * ss[:, :, 0:1] + ss[:, :, 1:2]
+        y = 0.5 * y * (1 + torch.erf(y / math.sqrt(2.0)))
+        T0 = y.shape[2]
+        o = _mem(out, B * rows_per_seg * 512).reshape(B, rows_per_seg, 512)
+        o[:, :T0] = y.transpose(1, 2).numpy()
+        o[:, T0:] = 0
+        self.calls.append("conv0_apply")
+        return 0
+
+    # ---- GEMM
+    def cst_gemm(self, pref, stream):
+        p = pref._obj
+        assert p.ab_dtype == F32 and p.c_dtype == F32
+        assert p.N % 8 == 0 and p.K % 64 == 0 and p.lda % 8 == 0 and p.ldc % 8 == 0
+        a_lim = p.a_rows * p.lda
+        glu = p.act == 3
+        n_out = p.N // 2 if glu else p.N
+        max_row = ((p.M - 1) // p.rows_per_seg) * p.out_rows_per_seg + p.rows_per_seg + p.out_row_off
+        for zo in range(p.nb_outer):
+            for zi in range(p.nb_inner):
+                a_off = zo * p.a_bs_outer + zi * p.a_bs_inner
+                A = np.concatenate((_mem(p.A + 4 * a_off, a_lim), np.zeros(p.K + p.lda, np.float32)))
+                At = torch.from_numpy(A.copy())
+                need = (p.M - 1) * p.lda + p.K
+                assert need <= At.numel()
+                # rows whose window leaves the addressable region read zeros from there on (guarded loads)
+                Am = At.as_strided((p.M, p.K), (p.lda, 1))
+                W = torch.from_numpy(_mem(p.W + 4 * zi * p.w_bs_inner, p.N * p.K).reshape(p.N, p.K).copy())
+                acc = Am.double() @ W.double().T
+                if p.bias:
+                    acc = acc + torch.from_numpy(_mem(p.bias + 4 * zi * p.bias_bs_inner, p.N).copy()).double()
+                if p.act == 1:
+                    acc = 0.5 * acc * (1 + torch.erf(acc / math.sqrt(2.0)))
+                elif p.act == 2:
+                    acc = torch.relu(acc)
+                elif glu:
+                    acc = acc[:, 0::2] * torch.sigmoid(acc[:, 1::2])
+                acc = (acc * p.alpha).float()
+                c_off = zo * p.c_bs_outer + zi * p.c_bs_inner
+                r_off = zo * p.r_bs_outer + zi * p.r_bs_inner
+                m = torch.arange(p.M)
+                seg, t = m // p.rows_per_seg, m % p.rows_per_seg
+                orow = seg * p.out_rows_per_seg + t + p.out_row_off
+                store = t < p.seg_rows_valid
+                Cbuf = _mem(p.C + 4 * c_off, max_row * p.ldc)
+                Cv = torch.from_numpy(Cbuf).as_strided((max_row, n_out), (p.ldc, 1))
+                if p.residual:
+                    Rv = torch.from_numpy(_mem(p.residual + 4 * r_off, max_row * p.ldr).copy()).as_strided(
+                        (max_row, n_out), (p.ldr, 1))
+                    acc = acc + Rv[orow]
+                if p.seg_len:
+                    nseg = zo * p.segs_per_outer + int(seg.max()) + 1
+                    sl = torch.from_numpy(_mem(p.seg_len, nseg, np.int32).copy()).long()
+                    acc[t >= sl[zo * p.segs_per_outer + seg]] = 0
+                Cv[orow[store]] = acc[store]
+        self.calls.append("gemm")
+        return 0
+
+    # ---- LayerNorm
+    def cst_layernorm(self, x, ldx, gamma, beta, out_f32, out_lp, lp_dtype, ldo, rows, Cd, rows_per_seg,
+                      seg_rows_valid, out_rows_per_seg, out_row_off, zero_invalid, stream):
+        assert Cd in (512, 768)
+        X = torch.from_numpy(_mem(x, rows * ldx).copy()).as_strided((rows, Cd), (ldx, 1))
+        g = torch.from_numpy(_mem(gamma, Cd).copy())
+        b = torch.from_numpy(_mem(beta, Cd).copy())
+        Y = torch.nn.functional.layer_norm(X, (Cd,), g, b, 1e-5)
+        m = torch.arange(rows)
+        seg, t = m // rows_per_seg, m % rows_per_seg
+        orow = seg * out_rows_per_seg + t + out_row_off
+        valid = t < seg_rows_valid
+        Y[~valid] = 0
+        sel = torch.ones_like(valid) if zero_invalid else valid
+        max_row = int(orow.max()) + 1
+        for o in (out_f32, out_lp):
+            if o:
+                assert o is out_f32 or lp_dtype == F32
+                Ov = torch.from_numpy(_mem(o, max_row * ldo)).as_strided((max_row, Cd), (ldo, 1))
+                Ov[orow[sel]] = Y[sel]
+        self.calls.append("layernorm")
+        return 0
+
+    def cst_posconv_pack(self, x, B, rows_per_seg, n_frames, xg, xg_dtype, t_pad_rows, stream):
+        assert xg_dtype == F32
+        X = torch.from_numpy(_mem(x, B * rows_per_seg * 768).copy()).view(B, rows_per_seg, 16, 48)
+        G = torch.zeros(B, 16, t_pad_rows, 64)
+        G[:, :, 64:64 + n_frames, :48] = X[:, :n_frames].permute(0, 2, 1, 3)
+        _mem(xg, G.numel())[:] = G.reshape(-1).numpy()
+        self.calls.append("posconv_pack")
+        return 0
+
+    def cst_broadcast_rows(self, src, rows, Cd, B, dst, stream):
+        s = _mem(src, rows * Cd)
+        _mem(dst, B * rows * Cd).reshape(B, rows * Cd)[:] = s[None, :]
+        self.calls.append("broadcast_rows")
+        return 0
+
+    # ---- attention
+    def cst_attention(self, q, k, v, out, dtype, ldq, ldkv, ldo, B, H, n_q, q_rps, n_kv, kv_rps, kv_len, stream):
+        assert dtype == F32
+        Q = torch.from_numpy(_mem(q, B * q_rps * ldq).copy()).as_strided((B, n_q, H, 64), (q_rps * ldq, ldq, 64, 1))
+        K = torch.from_numpy(_mem(k, B * kv_rps * ldkv).copy()).as_strided((B, n_kv, H, 64), (kv_rps * ldkv, ldkv, 64, 1))
+        V = torch.from_numpy(_mem(v, B * kv_rps * ldkv).copy()).as_strided((B, n_kv, H, 64), (kv_rps * ldkv, ldkv, 64, 1))
+        s = torch.einsum("bqhd,bkhd->bhqk", Q.double(), K.double())
+        if kv_len:
+            kl = torch.from_numpy(_mem(kv_len, B, np.int32).copy()).long()
+            s = s.masked_fill(torch.arange(n_kv)[None, None, None, :] >= kl[:, None, None, None], float("-inf"))
+        o = torch.einsum("bhqk,bkhd->bqhd", torch.softmax(s, -1), V.double()).float()
+        Ov = torch.from_numpy(_mem(out, B * q_rps * ldo)).as_strided((B, n_q, H, 64), (q_rps * ldo, ldo, 64, 1))
+        Ov[:] = o
+        self.calls.append("attention")
+        return 0
