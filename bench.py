@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""Benchmark of the Chimera-ST speech-encoding hot path (waveform -> M shared semantic memories).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--dtype bf16|fp32]
+
+Metric (BASELINE.json): encoded audio-seconds per second (valid audio only, padding not counted).
+Workload `c3` (BASELINE.json configs[2]): Chimera-16, `--utts` utterances of U{2..30} s per GPU, sorted by
+length, token-budget batches (max_tokens 2 000 000 samples, batch-size multiple 8: the reference's
+batch_by_size rule), every rank works on its own utterance set (weak scaling, no data-path collective).
+One "step" = one pass of the hot path over all of a rank's batches.
+
+Printed (rank 0): ONE JSON line with value (inputs resident in HBM), e2e (pinned host buffers -> H2D ->
+encoder.forward -> D2H of the memories, through the public module API), roofline of the dominant kernel
+(live CUDA-event timing of every launch of it in one instrumented pass), cpu_baseline (the oracle port of
+the reference's CPU path on this box's cores, bounded sample), clocks sampled during the timed region.
+`--impl reference`: the reference arm = the oracle port (the reference is pure Python/PyTorch and cannot
+travel to the GPU box) on the host cores, same metric/config.
+"""
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import chimera_st_b200  # noqa: E402,F401
+from chimera_st_b200 import synth, batching  # noqa: E402
+
+SR = 16000
+
+
+# --------------------------------------------------------------------------------------- workload
+def make_workload(name, rank, utts):
+    """-> list of batches, each a list of utterance lengths (samples), longest first."""
+    if name == "c3":
+        rng = np.random.RandomState(2024 + rank)
+        lens = rng.randint(32000, 480000 + 1, size=utts).astype(np.int64)
+        order = batching.ordered_indices(lens)
+        return [[int(lens[i]) for i in b] for b in batching.batch_by_size(order, lens, 2000000, 0, 8)]
+    if name == "c1":
+        return [[80000] * 4]
+    if name == "c2":
+        return [[240000] * 32]
+    if name == "c4":
+        return [[320000] * 64]
+    raise ValueError(name)
+
+
+def host_batch(lens, seed):
+    """Synthetic padded batch in pinned host memory (clamp(0.1*randn), zero tail)."""
+    L = max(lens)
+    g = torch.Generator().manual_seed(seed)
+    x = torch.empty(len(lens), L, dtype=torch.float32)
+    x.normal_(0.0, 0.1, generator=g).clamp_(-1.0, 1.0)
+    for b, n in enumerate(lens):
+        x[b, n:] = 0.0
+    if torch.cuda.is_available():
+        x = x.pin_memory()
+    return x, torch.tensor(lens, dtype=torch.int64)
+
+
+# --------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------- kernel profiler
+class LaunchProfiler:
+    """CUDA-event bracket around every C-ABI launch of one instrumented (non-graph) pass."""
+
+    def __init__(self):
+        self.rec = []
+
+    def wrap(self, plan):
+        prof = self
+        orig_gemm, orig_attn, orig_ln = plan._gemm, plan._attn, plan._ln
+
+        def ev():
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            return e
+
+        def gemm(A, W, C_, M, N, K, *a, **k):
+            nz = k.get("nb_outer", 1) * k.get("nb_inner", 1)
+            s = ev(); orig_gemm(A, W, C_, M, N, K, *a, **k); e = ev()
+            kind = "gemm_tc_bf16" if A.dtype == torch.bfloat16 else "gemm_ffma_f32"
+            prof.rec.append((kind, 2.0 * M * N * K * nz, (M * K + N * K) * A.element_size() * nz + M * N * C_.element_size() * nz, s, e,
+                             "M%d N%d K%d z%d" % (M, N, K, nz)))
+
+        def attn(q, k_, v, out, ldq, ldkv, H, n_q, q_rps, n_kv, kv_rps, kv_len):
+            s = ev(); orig_attn(q, k_, v, out, ldq, ldkv, H, n_q, q_rps, n_kv, kv_rps, kv_len); e = ev()
+            B = plan.g.B
+            prof.rec.append(("attention", 4.0 * B * H * n_q * n_kv * 64, 0, s, e, "B%d H%d q%d kv%d" % (B, H, n_q, n_kv)))
+
+        def ln(x, gb, rows, **k):
+            s = ev(); orig_ln(x, gb, rows, **k); e = ev()
+            prof.rec.append(("layernorm", 0.0, rows * x.shape[1] * 10, s, e, "rows%d C%d" % (rows, x.shape[1])))
+        plan._gemm, plan._attn, plan._ln = gemm, attn, ln
+        return (orig_gemm, orig_attn, orig_ln)
+
+    @staticmethod
+    def unwrap(plan, saved):
+        plan._gemm, plan._attn, plan._ln = saved
+
+    def summary(self):
+        torch.cuda.synchronize()
+        agg = {}
+        for kind, fl, by, s, e, _ in self.rec:
+            a = agg.setdefault(kind, [0, 0.0, 0.0, 0.0])
+            a[0] += 1; a[1] += fl; a[2] += by; a[3] += s.elapsed_time(e) * 1e-3
+        return {k: {"launches": v[0], "flops": v[1], "bytes": v[2], "seconds": v[3]} for k, v in agg.items()}
+
+
+# --------------------------------------------------------------------------------------- arms
+def cpu_reference_rate(sample_lens, steps, warmup, threads):
+    """The reference's CPU path (oracle port: same ATen CPU ops as the reference's modules) on a bounded sample."""
+    from oracle import chimera_oracle as O
+    torch.set_num_threads(threads)
+    sd = synth.make_state_dict(seed=0, interlingua_length=16)
+    wave, lens = synth.make_waveforms(sample_lens, seed=1234)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t = time.perf_counter()
+            O.encoder_forward(sd, wave, lens)
+            if i >= warmup:
+                times.append(time.perf_counter() - t)
+    audio = sum(sample_lens) / SR
+    return audio / statistics.median(times), audio / min(times), times
+
+
+def pick_cpu_sample(batches):
+    """4 utterances around the workload's median length (~10-30 s of CPU work)."""
+    allens = sorted(n for b in batches for n in b)
+    mid = len(allens) // 2
+    s = allens[max(0, mid - 2):mid + 2]
+    return sorted(s, reverse=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--workload", default="c3", choices=["c3", "c1", "c2", "c4"])
+    ap.add_argument("--utts", type=int, default=512)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-json", default="")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cores = os.cpu_count() or 1
+    M = 16
+    batches = make_workload(args.workload, rank, args.utts)
+    audio_per_step = sum(sum(b) for b in batches) / SR
+    cfg = {"workload": "%s: Chimera-16 encoder+memory, %s" % (args.workload, {
+        "c3": "%d utts/GPU U{2..30}s, length-bucketed max_tokens=2e6 bsz%%8 (%d batches)" % (args.utts, len(batches)),
+        "c1": "B=4 x 5 s", "c2": "B=32 x 15 s", "c4": "B=64 x 20 s"}[args.workload]),
+        "interlingua_length": M, "batches_per_step": len(batches), "audio_sec_per_step_per_gpu": round(audio_per_step, 2),
+        "parallelism": "utterance-sharded dp%d, no data-path collective" % world,
+        "l2": "activations per batch (>=0.4 GB) exceed the 126 MB L2; no explicit flush"}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        sample = pick_cpu_sample(batches)
+        med, best, times = cpu_reference_rate(sample, max(1, args.steps), 1, cores)
+        line = {"impl": "reference", "metric": "encoded audio-sec/sec", "value": round(med, 3), "unit": "audio-s/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": round(1e3 * statistics.median(times), 2), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+                "cpu_baseline": {"value": round(med, 3), "unit": "audio-s/s", "cores": cores, "kind": "port",
+                                 "sample": "%d utterances %s samples of the workload, fp32, torch CPU %d threads" % (len(sample), sample, cores)},
+                "e2e": {"value": round(med, 3), "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ B200 arm
+    assert torch.cuda.is_available(), "bench.py --impl b200 needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from chimera_st_b200.encoder import build_encoder_from_state_dict
+    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    sd = synth.make_state_dict(seed=0, interlingua_length=M)
+    enc = build_encoder_from_state_dict(sd, dtype=dtype, device="cuda", use_graph=not args.no_graph)
+    enc.MAX_PLANS = 4096
+
+    host = [host_batch(b, seed=1000 * rank + i) for i, b in enumerate(batches)]
+    dev = [(w.cuda(non_blocking=True), l.cuda(non_blocking=True)) for w, l in host]
+    out_host = [torch.empty(M, len(b), 512, dtype=torch.float32).pin_memory() for b in batches]
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def step_resident():
+        n = 0
+        for (w, l) in dev:
+            plan = enc._plan(*w.shape)
+            plan.load_inputs(w, l)
+            n += plan.run()
+        return n
+
+    def step_e2e():
+        for (w, l), oh in zip(host, out_host):
+            out = enc(w.cuda(non_blocking=True), l.cuda(non_blocking=True))
+            oh.copy_(out.encoder_out, non_blocking=True)
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        launches += step_resident()
+    e1.record()
+    barrier()
+    t_res = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+    clocks = sampler.stop() if rank == 0 else None
+
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    e1.record()
+    barrier()
+    t_e2e = max_over_ranks(max(e0.elapsed_time(e1) * 1e-3, 0.0))
+    t_e2e_wall = time.perf_counter() - t0
+
+    total_audio = audio_per_step
+    if world > 1:
+        t = torch.tensor([audio_per_step], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        total_audio = float(t.item())
+
+    # ---- instrumented pass: per-kernel CUDA-event timing (non-graph) for the roofline object
+    prof = LaunchProfiler()
+    for (w, l) in dev:
+        p = enc._plan(*w.shape)
+        saved = prof.wrap(p)
+        p.load_inputs(w, l)
+        p.run(eager=True)
+        prof.unwrap(p, saved)
+    ksum = prof.summary()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    dom = "gemm_tc_bf16" if "gemm_tc_bf16" in ksum else "gemm_ffma_f32"
+    kd = ksum[dom]
+    ach = kd["flops"] / kd["seconds"] / 1e12
+    if dom == "gemm_tc_bf16":
+        peak, peak_src = peaks.get("bf16_tflops_sustained", 1400.0), ("measured (sustained)" if peaks else "fallback")
+    else:
+        peak, peak_src = 72.0, "nominal fp32 FFMA 148 SM x 128 lanes x 2 x 1.9 GHz (no measured fp32 peak)"
+    step_kernel_s = sum(v["seconds"] for v in ksum.values())
+    roofline = {"bound": "tensor", "kernel": dom, "achieved": round(ach, 2), "peak": peak, "unit": "TFLOP/s",
+                "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
+                "launches_per_step": kd["launches"], "share_of_kernel_time": round(kd["seconds"] / step_kernel_s, 3),
+                "by_kernel": {k: {"launches": v["launches"], "ms": round(v["seconds"] * 1e3, 3),
+                                  "tflops": round(v["flops"] / v["seconds"] / 1e12, 2) if v["seconds"] > 0 else None}
+                              for k, v in ksum.items()}}
+    if args.profile_json:
+        with open(args.profile_json, "w") as f:
+            json.dump({"kernels": ksum, "launch_list": [(k, fl, by, s.elapsed_time(e), d) for k, fl, by, s, e, d in prof.rec]}, f)
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        sample = pick_cpu_sample(batches)
+        med, best, times = cpu_reference_rate(sample, 3, 1, cores)
+        cpu = {"value": round(med, 3), "unit": "audio-s/s", "cores": cores, "kind": "port",
+               "sample": "%d utterances %s samples of the workload, fp32, torch CPU %d threads, median of 3" % (len(sample), sample, cores)}
+
+    value = total_audio * args.steps / t_res
+    h2d = sum(w.numel() * 4 + l.numel() * 8 for w, l in host)
+    d2h = sum(o.numel() * 4 for o in out_host)
+    line = {"metric": "encoded audio-sec/sec", "value": round(value, 1), "unit": "audio-s/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": round(1e3 * t_res / args.steps, 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if dtype == torch.bfloat16 else "f32", "data": "synthetic", "config": cfg,
+            "e2e": {"value": round(total_audio * args.steps / t_e2e, 1), "unit": "audio-s/s",
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "wall_s": round(t_e2e_wall, 3)},
+            "gpu_launches": launches, "cuda_graph": not args.no_graph, "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

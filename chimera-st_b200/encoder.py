@@ -22,7 +22,7 @@ import torch
 import torch.nn as nn
 
 from . import weights as _weights
-from .plan import EncoderPlan
+from .plan import EncoderPlan, Arena
 from .synth import encoder_param_spec, ENC_DIM
 
 
@@ -54,7 +54,7 @@ def _register(root, dotted, tensor, buffer=False):
 
 
 class B200InterlinguaEncoder(nn.Module):
-    MAX_PLANS = 16          # cached (B, L) shapes; each plan owns its activation buffers
+    MAX_PLANS = 256         # cached (B, L) shapes (geometry + CUDA graph); activations overlay one shared arena
 
     def __init__(self, interlingua_length=16, dtype=torch.float32, use_graph=True, dead_heads=True,
                  text_vocab=0, encoder_out_dtype=None):
@@ -70,6 +70,7 @@ class B200InterlinguaEncoder(nn.Module):
             _register(self, name, torch.zeros(shape), buffer=name.endswith("_float_tensor"))
         self._prepared = None
         self._plans = OrderedDict()
+        self._arena = None
         self.last_launches = 0
         self.register_load_state_dict_post_hook(lambda m, k: m.invalidate())
 
@@ -94,6 +95,7 @@ class B200InterlinguaEncoder(nn.Module):
         """Drop prepared weights and cached plans (call after mutating parameters in place)."""
         self._prepared = None
         self._plans.clear()
+        self._arena = None
 
     # ---- plumbing ------------------------------------------------------------------------------------
     def _device(self):
@@ -111,7 +113,13 @@ class B200InterlinguaEncoder(nn.Module):
         if plan is None:
             while len(self._plans) >= self.MAX_PLANS:
                 self._plans.popitem(last=False)
-            plan = EncoderPlan(self._prepared, B, L, self.interlingua_length, self.compute_dtype, dev, self.use_graph)
+            if self._arena is None:
+                self._arena = Arena(dev)
+            gen = self._arena.generation
+            plan = EncoderPlan(self._prepared, B, L, self.interlingua_length, self.compute_dtype, dev, self.use_graph,
+                               arena=self._arena)
+            if self._arena.generation != gen:          # arena grew: older plans (and their graphs) point at freed memory
+                self._plans.clear()
             self._plans[key] = plan
         else:
             self._plans.move_to_end(key)

@@ -1,0 +1,111 @@
+"""Tensor-level wrappers of the C-ABI entry points (device tensors in, device tensors out).
+
+Used by the parity tests and tools; the execution plan (`plan.py`) calls the ABI directly on its
+pre-allocated buffers.  Everything here launches CUDA kernels -- no computation happens in torch.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+from .lengths import conv_out_lengths
+
+
+def _cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise L.CstError("device tensors required (no CPU fallback)")
+
+
+def frame_lengths(src_lengths, Lw):
+    _cuda(src_lengths)
+    B = src_lengths.shape[0]
+    Tp = conv_out_lengths(Lw)[-1]
+    dev = src_lengths.device
+    w2v = torch.empty(B, dtype=torch.int32, device=dev)
+    sub = torch.empty(B, dtype=torch.int32, device=dev)
+    l64 = torch.empty(B, dtype=torch.int64, device=dev)
+    mask = torch.empty(B, Tp, dtype=torch.uint8, device=dev)
+    L.check(L.load().cst_frame_lengths(src_lengths.contiguous().data_ptr(), B, Lw, Tp, w2v.data_ptr(), sub.data_ptr(),
+                                       l64.data_ptr(), mask.data_ptr(), L.stream_ptr()))
+    return w2v, sub, l64, mask.bool()
+
+
+def conv0_gn_gelu(wave, w, gamma, beta, out_dtype=torch.float32, rows_per_seg=None):
+    """wave [B,L] f32 -> channels-last [B, rows_per_seg, 512]; frames >= T0 are zero."""
+    _cuda(wave, w, gamma, beta)
+    B, Lw = wave.shape
+    T0 = (Lw - 10) // 5 + 1
+    rps = rows_per_seg or T0
+    dev = wave.device
+    ss = torch.empty(B, 512, 2, dtype=torch.float32, device=dev)
+    ws = torch.empty(B * 72, dtype=torch.float64, device=dev)
+    out = torch.empty(B, rps, 512, dtype=out_dtype, device=dev)
+    lib = L.load()
+    w = w.reshape(512, 10).contiguous()
+    L.check(lib.cst_conv0_stats(wave.data_ptr(), B, Lw, w.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                ss.data_ptr(), ws.data_ptr(), L.stream_ptr()))
+    L.check(lib.cst_conv0_apply(wave.data_ptr(), B, Lw, w.data_ptr(), ss.data_ptr(), out.data_ptr(),
+                                L.DT[out_dtype], rps, L.stream_ptr()))
+    return out, ss
+
+
+def gemm(A, W, C_, M, N, K, lda, a_rows, bias=None, residual=None, act=L.ACT_NONE, alpha=1.0,
+         rows_per_seg=None, seg_rows_valid=None, out_rows_per_seg=None, out_row_off=0, seg_len=None,
+         ldc=None, ldr=None, nb_outer=1, nb_inner=1, a_bs=(0, 0), w_bs=0, c_bs=(0, 0), r_bs=None, bias_bs=0,
+         segs_per_outer=1):
+    _cuda(A, W, C_, bias, residual, seg_len)
+    p = L.GemmParams()
+    p.A, p.W, p.bias, p.residual, p.C = A.data_ptr(), W.data_ptr(), L.ptr(bias), L.ptr(residual), C_.data_ptr()
+    p.ab_dtype, p.c_dtype = L.DT[A.dtype], L.DT[C_.dtype]
+    p.M, p.N, p.K = M, N, K
+    p.lda = lda
+    p.ldc = ldc if ldc is not None else C_.shape[-1]
+    p.ldr = ldr if ldr is not None else (residual.shape[-1] if residual is not None else 0)
+    p.a_rows = a_rows
+    p.act, p.alpha = act, alpha
+    p.nb_outer, p.nb_inner = nb_outer, nb_inner
+    p.a_bs_outer, p.a_bs_inner = a_bs
+    p.w_bs_inner = w_bs
+    p.c_bs_outer, p.c_bs_inner = c_bs
+    p.r_bs_outer, p.r_bs_inner = r_bs if r_bs is not None else c_bs
+    p.bias_bs_inner = bias_bs
+    p.rows_per_seg = rows_per_seg if rows_per_seg is not None else M
+    p.seg_rows_valid = seg_rows_valid if seg_rows_valid is not None else p.rows_per_seg
+    p.out_rows_per_seg = out_rows_per_seg if out_rows_per_seg is not None else p.rows_per_seg
+    p.out_row_off = out_row_off
+    p.seg_len = L.ptr(seg_len)
+    p.segs_per_outer = segs_per_outer
+    L.check(L.load().cst_gemm(C.byref(p), L.stream_ptr()))
+    return C_
+
+
+def linear(A, W, bias=None, act=L.ACT_NONE, residual=None, alpha=1.0, out_dtype=None):
+    """act(A W^T + b) * alpha (+ residual) for dense row-major A [M,K], W [N,K]."""
+    M, K = A.shape
+    N = W.shape[0]
+    n_out = N // 2 if act == L.ACT_GLU else N
+    out = torch.empty(M, n_out, dtype=out_dtype or A.dtype, device=A.device)
+    return gemm(A, W, out, M, N, K, lda=K, a_rows=M, bias=bias, residual=residual, act=act, alpha=alpha)
+
+
+def layernorm(x, gamma, beta, lp_dtype=None):
+    _cuda(x, gamma, beta)
+    rows, Cd = x.shape
+    o32 = torch.empty_like(x)
+    olp = torch.empty(rows, Cd, dtype=lp_dtype, device=x.device) if lp_dtype is not None else None
+    L.check(L.load().cst_layernorm(x.data_ptr(), Cd, gamma.data_ptr(), beta.data_ptr(), o32.data_ptr(), L.ptr(olp),
+                                   L.DT[lp_dtype] if lp_dtype is not None else 0, Cd, rows, Cd, rows, rows, rows, 0, 0,
+                                   L.stream_ptr()))
+    return o32, olp
+
+
+def attention(q, k, v, n_heads, kv_len=None):
+    """q [B,Tq,C], k/v [B,Tk,C] contiguous (C = n_heads*64), q pre-scaled; kv_len int32 [B] or None."""
+    _cuda(q, k, v, kv_len)
+    B, Tq, Cd = q.shape
+    Tk = k.shape[1]
+    out = torch.empty_like(q)
+    L.check(L.load().cst_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), L.DT[q.dtype],
+                                   Cd, Cd, Cd, B, n_heads, Tq, Tq, Tk, Tk, L.ptr(kv_len), L.stream_ptr()))
+    return out

@@ -47,8 +47,25 @@ class Geometry:
         assert self.T6a >= self.Tp and self.T1a >= self.T1 and self.T2a >= self.T2
 
 
+class Arena:
+    """One growable device allocation shared by all plans of an encoder: only one plan runs at a time, so
+    every (B, L) shape overlays the same HBM region instead of owning ~1 GB of activations each."""
+
+    def __init__(self, device):
+        self.device = device
+        self.buf = torch.empty(0, dtype=torch.uint8, device=device)
+        self.generation = 0
+
+    def ensure(self, nbytes):
+        if nbytes > self.buf.numel():
+            self.buf = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, device=self.device)
+            self.generation += 1          # views handed out before are stale: the owner drops its plans
+        return self.generation
+
+
 class EncoderPlan:
-    def __init__(self, params, B, Lw, M, act_dtype=torch.float32, device=None, use_graph=False, lib=None):
+    def __init__(self, params, B, Lw, M, act_dtype=torch.float32, device=None, use_graph=False, lib=None,
+                 arena=None):
         # `lib` is injectable so tests can drive the plan against a host emulator of the C ABI
         # (tests/emu.py); the product never passes it and always loads the CUDA library.
         self.lib = lib if lib is not None else L.load()
@@ -60,51 +77,43 @@ class EncoderPlan:
         self.use_graph = use_graph
         self.graph = None
         self.launches = 0
-        z = lambda rows, cols, dt: torch.zeros(rows, cols, dtype=dt, device=self.dev)   # noqa: E731
-        f32 = torch.float32
-        # ---- inputs / integer side
-        self.wave = torch.zeros(B, Lw, dtype=f32, device=self.dev)
-        self.src_len = torch.zeros(B, dtype=torch.int64, device=self.dev)
-        self.w2v_valid = torch.zeros(B, dtype=torch.int32, device=self.dev)
-        self.sub_valid = torch.zeros(B, dtype=torch.int32, device=self.dev)
-        self.w2v_len64 = torch.zeros(B, dtype=torch.int64, device=self.dev)
-        self.frame_mask = torch.zeros(B, g.Tp, dtype=torch.uint8, device=self.dev)
-        # ---- conv stack (ping-pong; level i lives in cbuf[i & 1])
-        self.scale_shift = z(B * 512, 2, f32)
-        self.stats_ws = torch.zeros(B * 72, dtype=torch.float64, device=self.dev)
-        self.cbuf = [z(B * g.Ta[0] + SLACK, 512, act_dtype), z(B * g.Ta[1] + SLACK, 512, act_dtype)]
-        self.feat = z(B * g.T6a, 512, f32)             # conv6 output (fp32 for the LN)
-        self.feat_ln = z(B * g.T6a, 512, act_dtype)
-        # ---- wav2vec2 encoder
-        R = B * g.T6a
-        self.x = z(R, W2V_DIM, f32)                   # fp32 residual stream
-        self.y = z(R, W2V_DIM, f32)                   # pre-LN sums
-        self.xa = z(R, W2V_DIM, act_dtype)            # GEMM operand copy of the stream
-        self.xg = z(B * 16 * g.Tpp + SLACK, 64, act_dtype)
-        self.qkv = z(R, 3 * W2V_DIM, act_dtype)
-        self.ctx = z(R, W2V_DIM, act_dtype)
-        self.ffn = z(R, W2V_FFN, act_dtype)
-        self.w2v_out = z(R, W2V_DIM, f32)
-        # ---- subsampler
-        self.sub_in = z(B * g.Tin1 + SLACK, W2V_DIM, act_dtype)
-        self.sub_mid = z(B * g.Tin2 + SLACK, ENC_DIM, act_dtype)
-        # ---- shared encoder
-        R2 = B * g.T2a
-        self.x2 = z(R2, ENC_DIM, f32)
-        self.x2a = z(R2, ENC_DIM, act_dtype)
-        self.qkv2 = z(R2, 3 * ENC_DIM, act_dtype)
-        self.ctx2 = z(R2, ENC_DIM, act_dtype)
-        self.ffn2 = z(R2, ENC_FFN, act_dtype)
-        self.h_enc = z(R2, ENC_DIM, f32)
-        # ---- memory stage
-        RM = B * M
-        self.kv_in = z(R2, ENC_DIM, act_dtype)
-        self.kv = z(R2, 2 * ENC_DIM, act_dtype)
-        self.mem = z(RM, ENC_DIM, f32)
-        self.mem_a = z(RM, ENC_DIM, act_dtype)
-        self.mq = z(RM, ENC_DIM, act_dtype)
-        self.mctx = z(RM, ENC_DIM, act_dtype)
-        self.mffn = z(RM, ENC_FFN, act_dtype)
+        self.arena = arena if arena is not None else Arena(self.dev)
+        f32, i32, i64, u8, f64 = torch.float32, torch.int32, torch.int64, torch.uint8, torch.float64
+        R, R2, RM = B * g.T6a, B * g.T2a, B * M
+        spec = [
+            # ---- inputs / integer side
+            ("wave", B, Lw, f32), ("src_len", 1, B, i64), ("w2v_valid", 1, B, i32), ("sub_valid", 1, B, i32),
+            ("w2v_len64", 1, B, i64), ("frame_mask", B, g.Tp, u8),
+            # ---- conv stack (ping-pong; level i lives in cbuf{i & 1}); SLACK rows absorb the last windows
+            ("scale_shift", B * 512, 2, f32), ("stats_ws", 1, B * 72, f64),
+            ("cbuf0", B * g.Ta[0] + SLACK, 512, act_dtype), ("cbuf1", B * g.Ta[1] + SLACK, 512, act_dtype),
+            ("feat", R, 512, f32), ("feat_ln", R, 512, act_dtype),
+            # ---- wav2vec2 encoder: fp32 residual stream x, pre-LN sums y, GEMM-operand copy xa
+            ("x", R, W2V_DIM, f32), ("y", R, W2V_DIM, f32), ("xa", R, W2V_DIM, act_dtype),
+            ("xg", B * 16 * g.Tpp + SLACK, 64, act_dtype), ("qkv", R, 3 * W2V_DIM, act_dtype),
+            ("ctx", R, W2V_DIM, act_dtype), ("ffn", R, W2V_FFN, act_dtype), ("w2v_out", R, W2V_DIM, f32),
+            # ---- subsampler operands (zero-padded: re-zeroed every run)
+            ("sub_in", B * g.Tin1 + SLACK, W2V_DIM, act_dtype), ("sub_mid", B * g.Tin2 + SLACK, ENC_DIM, act_dtype),
+            # ---- shared encoder
+            ("x2", R2, ENC_DIM, f32), ("x2a", R2, ENC_DIM, act_dtype), ("qkv2", R2, 3 * ENC_DIM, act_dtype),
+            ("ctx2", R2, ENC_DIM, act_dtype), ("ffn2", R2, ENC_FFN, act_dtype), ("h_enc", R2, ENC_DIM, f32),
+            # ---- memory stage
+            ("kv_in", R2, ENC_DIM, act_dtype), ("kv", R2, 2 * ENC_DIM, act_dtype), ("mem", RM, ENC_DIM, f32),
+            ("mem_a", RM, ENC_DIM, act_dtype), ("mq", RM, ENC_DIM, act_dtype), ("mctx", RM, ENC_DIM, act_dtype),
+            ("mffn", RM, ENC_FFN, act_dtype),
+        ]
+        off, table = 0, []
+        for name, rows, cols, dt in spec:
+            nbytes = rows * cols * torch.empty(0, dtype=dt).element_size()
+            table.append((name, off, nbytes, rows, cols, dt))
+            off += (nbytes + 1023) // 1024 * 1024
+        self.nbytes = off
+        self.arena_generation = self.arena.ensure(off)
+        for name, o, nbytes, rows, cols, dt in table:
+            t = self.arena.buf[o:o + nbytes].view(dt)
+            setattr(self, name, t.view(rows, cols) if rows > 1 or name in ("wave", "frame_mask") else t.view(cols))
+        self.cbuf = [self.cbuf0, self.cbuf1]
+        self.arena.buf[:off].zero_()
 
     # ------------------------------------------------------------------ launch helpers
     def _gemm(self, A, W, C_, M, N, K, lda, a_rows, bias=None, residual=None, act=L.ACT_NONE, alpha=1.0,
@@ -193,6 +202,10 @@ class EncoderPlan:
         g, P = self.g, self.P
         R = g.B * g.T6a
         D = W2V_DIM
+        # zero-padded subsampler operands share the arena with other shapes: clear them every run
+        self.sub_in.zero_()
+        self.sub_mid.zero_()
+        self.launches += 2
         es = self.qkv.element_size()
         for i, lw in enumerate(P["w2v_layers"]):
             self._linear(self.xa, lw["qkv_w"], lw["qkv_b"], self.qkv, R)
@@ -282,9 +295,11 @@ class EncoderPlan:
         self.wave.copy_(wave, non_blocking=True)
         self.src_len.copy_(src_lengths, non_blocking=True)
 
-    def run(self, upto="memory"):
+    def run(self, upto="memory", eager=False):
         """Launch the forward pass for the loaded inputs; returns the number of kernel launches issued."""
-        if self.use_graph and upto == "memory":
+        if self.arena_generation != self.arena.generation:
+            raise RuntimeError("stale plan: the arena was re-allocated after this plan was built")
+        if self.use_graph and upto == "memory" and not eager:
             if self.graph is None:
                 self._issue()                                   # warm-up: one-time attribute / descriptor setup
                 torch.cuda.current_stream().synchronize()

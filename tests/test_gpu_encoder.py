@@ -1,0 +1,122 @@
+"""End-to-end GPU parity of the B200 encoder against the golden vectors of the UNMODIFIED reference
+(tests/golden, fp32) and against the oracle on fresh seeded inputs.
+Tolerances (BASELINE.json north_star): fp32 <= 1e-5, bf16 <= 1e-2 relative (rel-L2 per tensor against
+the fp32 reference on the identical padded batch); masks / lengths bit-exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import chimera_st_b200  # noqa: F401
+from chimera_st_b200 import synth
+from oracle import chimera_oracle as O
+from conftest import rel_l2, rel_max, GOLDEN
+
+pytestmark = pytest.mark.gpu
+TOL = {torch.float32: 1e-5, torch.bfloat16: 1e-2}
+_cache = {}
+
+
+def encoder(M, dtype, use_graph=False):
+    from chimera_st_b200.encoder import build_encoder_from_state_dict
+    key = (M, dtype, use_graph)
+    if key not in _cache:
+        sd = synth.make_state_dict(seed=0, interlingua_length=M)
+        _cache[key] = build_encoder_from_state_dict(sd, dtype=dtype, device="cuda", use_graph=use_graph)
+    return _cache[key]
+
+
+def _golden(name):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    wave, lens = synth.make_waveforms(g["src_lengths"].tolist(), seed=int(g["wave_seed"]))
+    return g, wave, lens
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_tiny_all_stages(dtype):
+    g, wave, lens = _golden("tiny")
+    enc = encoder(16, dtype)
+    feat, fmask, flen = enc._get_w2v_feature(wave.cuda(), lens.cuda())
+    assert torch.equal(fmask.cpu(), torch.from_numpy(g["frame_mask"]))
+    assert torch.equal(flen.cpu(), torch.from_numpy(g["w2v_len"]))
+    assert feat.shape == (3, 49, 768)
+    tol = TOL[dtype]
+    assert rel_l2(feat.cpu(), torch.from_numpy(g["w2v_out"])) < tol
+    out = enc(wave.cuda(), lens.cuda(), mask=None)          # tolerate the collater's stray kwarg
+    plan = enc._plan(*wave.shape)
+    assert rel_l2(plan.view("conv_feats").cpu(), torch.from_numpy(g["conv_feats"])) < tol
+    assert rel_l2(plan.view("h_enc").cpu(), torch.from_numpy(g["h_enc"])) < tol
+    assert out.encoder_out.shape == (16, 3, 512) and out.encoder_out.dtype == torch.float32
+    assert rel_l2(out.encoder_out.cpu(), torch.from_numpy(g["memories"])) < tol
+    assert rel_max(out.encoder_out.cpu(), torch.from_numpy(g["memories"])) < 10 * tol
+    assert torch.equal(out.encoder_padding_mask.cpu(), torch.from_numpy(g["encoder_padding_mask"]))
+    assert plan.sub_valid.tolist() == g["sub_len"].tolist()
+    assert out.encoder_embedding is None and out.encoder_states is None
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("name", ["c1", "c1mix"])
+def test_c1_memories(name, dtype):
+    g, wave, lens = _golden(name)
+    enc = encoder(16, dtype)
+    out = enc(wave.cuda(), lens.cuda())
+    assert rel_l2(out.encoder_out.cpu(), torch.from_numpy(g["memories"])) < TOL[dtype]
+    plan = enc._plan(*wave.shape)
+    assert torch.equal(plan.view("frame_mask").cpu(), torch.from_numpy(g["frame_mask"]))
+    assert plan.w2v_len64.tolist() == g["w2v_len"].tolist()
+    assert rel_l2(plan.view("conv_feats").cpu()[:, ::37, ::11], torch.from_numpy(g["conv_feats_s"])) < TOL[dtype]
+    assert rel_l2(plan.view("w2v_out").cpu()[:, ::11, ::37], torch.from_numpy(g["w2v_out_s"])) < TOL[dtype]
+    assert rel_l2(plan.view("h_enc").cpu()[:, ::3, ::17], torch.from_numpy(g["h_enc_s"])) < TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_tiny64(dtype):
+    g, wave, lens = _golden("tiny64")
+    out = encoder(64, dtype)(wave.cuda(), lens.cuda())
+    assert out.encoder_out.shape == (64, 3, 512) and out.encoder_padding_mask.shape == (3, 64)
+    assert rel_l2(out.encoder_out.cpu(), torch.from_numpy(g["memories"])) < TOL[dtype]
+
+
+def test_cuda_graph_replay_is_bit_identical_and_reusable():
+    g, wave, lens = _golden("tiny")
+    a = encoder(16, torch.float32, use_graph=False)(wave.cuda(), lens.cuda()).encoder_out
+    eg = encoder(16, torch.float32, use_graph=True)
+    b = eg(wave.cuda(), lens.cuda()).encoder_out
+    assert torch.equal(a, b)
+    wave2, lens2 = synth.make_waveforms([16000, 3000, 9999], seed=21)      # same shape, new lengths: replay
+    c = eg(wave2.cuda(), lens2.cuda()).encoder_out
+    with torch.no_grad():
+        ref, _ = O.encoder_forward(synth.make_state_dict(seed=0), wave2, lens2)
+    assert rel_l2(c.cpu(), ref) < 1e-5
+    assert torch.equal(eg(wave.cuda(), lens.cuda()).encoder_out, a)          # and back again
+
+
+def test_batch_composition_moves_with_the_reference():
+    """the same utterance alone vs inside a padded batch gives different outputs in the
+    reference (GroupNorm over padded time, ceil-style masks, unmasked memory attention); ours must follow."""
+    sd = synth.make_state_dict(seed=0)
+    wave, lens = synth.make_waveforms([24000, 9000], seed=5)
+    enc = encoder(16, torch.float32)
+    both = enc(wave.cuda(), lens.cuda()).encoder_out.cpu()
+    alone = enc(wave[1:, :9000].contiguous().cuda(), lens[1:].cuda()).encoder_out.cpu()
+    with torch.no_grad():
+        r_both, _ = O.encoder_forward(sd, wave, lens)
+        r_alone, _ = O.encoder_forward(sd, wave[1:, :9000].contiguous(), lens[1:])
+    assert rel_l2(both, r_both) < 1e-5 and rel_l2(alone, r_alone) < 1e-5
+    assert rel_l2(both[:, 1:], alone) > 1e-3            # they really do differ
+
+
+def test_reorder_and_no_interlingua():
+    g, wave, lens = _golden("tiny")
+    enc = encoder(16, torch.float32)
+    out = enc(wave.cuda(), lens.cuda())
+    order = torch.tensor([2, 2, 0, 1], device="cuda")
+    r = enc.reorder_encoder_out(out, order)
+    assert torch.equal(r.encoder_out, out.encoder_out[:, order]) and r.encoder_padding_mask.shape == (4, 16)
+    enc.no_interlingua = True
+    try:
+        h = enc(wave.cuda(), lens.cuda()).encoder_out
+    finally:
+        enc.no_interlingua = False
+    assert rel_l2(h.cpu(), torch.from_numpy(g["h_enc"]).transpose(0, 1)) < 1e-5

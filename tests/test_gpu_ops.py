@@ -1,0 +1,194 @@
+"""GPU parity of the individual C-ABI kernels against CPU restatements (torch fp32/fp64 on host)."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import chimera_st_b200  # noqa: F401
+from chimera_st_b200 import synth, lengths
+from oracle import chimera_oracle as O
+from conftest import rel_l2, rel_max, GOLDEN
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def ops():
+    from chimera_st_b200 import ops as _ops
+    return _ops
+
+
+def L_():
+    from chimera_st_b200 import _lib
+    return _lib
+
+
+def test_device_is_blackwell():
+    name, sms, major, minor = L_().device_info()
+    assert major == 10, (name, major, minor)
+
+
+def test_frame_lengths_exhaustive_vs_reference_rows():
+    rows = np.load(os.path.join(GOLDEN, "lengths.npz"))["rows"]
+    by_L = {}
+    for Lw, n, T, v, s2 in rows.tolist():
+        by_L.setdefault(Lw, []).append((n, T, v, s2))
+    for Lw, items in by_L.items():
+        lens = torch.tensor([n for n, *_ in items], dtype=torch.int64, device=DEV)
+        w2v, sub, l64, mask = ops().frame_lengths(lens, Lw)
+        assert w2v.tolist() == [v for _, _, v, _ in items], Lw
+        assert sub.tolist() == [s for *_, s in items], Lw
+        assert l64.tolist() == w2v.tolist()
+        ref_mask = O.frame_padding_mask(lens.cpu(), items[0][1])
+        assert torch.equal(mask.cpu(), ref_mask), Lw
+
+
+@pytest.mark.parametrize("lens", [[16000, 12345, 8000], [4000], [80000, 64000, 48123, 32000]])
+def test_conv0_groupnorm_gelu(lens):
+    sd = synth.make_state_dict(seed=0)
+    wave, _ = synth.make_waveforms(lens, seed=3)
+    wave[0] += 0.05                                     # DC offset: stresses the variance-from-moments path
+    P = "wav2vec_model.feature_extractor.conv_layers."
+    ref = O.conv_feature_extractor(sd, wave, upto=1).transpose(1, 2)          # [B,T0,512]
+    T0 = ref.shape[1]
+    rps = 64 * ((T0 + 63) // 64)
+    out, _ = ops().conv0_gn_gelu(wave.to(DEV), sd[P + "0.0.weight"].to(DEV), sd[P + "0.2.weight"].to(DEV),
+                                 sd[P + "0.2.bias"].to(DEV), torch.float32, rps)
+    out = out.cpu()
+    assert rel_l2(out[:, :T0], ref) < 2e-6 and rel_max(out[:, :T0], ref) < 2e-5
+    assert float(out[:, T0:].abs().max()) == 0.0 if rps > T0 else True
+    outb, _ = ops().conv0_gn_gelu(wave.to(DEV), sd[P + "0.0.weight"].to(DEV), sd[P + "0.2.weight"].to(DEV),
+                                  sd[P + "0.2.bias"].to(DEV), torch.bfloat16, rps)
+    assert rel_l2(outb.cpu().float()[:, :T0], ref) < 4e-3      # bf16 rounding of the stored value only
+
+
+def _ref_gemm(A, W, bias, act, alpha, residual):
+    acc = A.double() @ W.double().T
+    if bias is not None:
+        acc = acc + bias.double()
+    if act == 1:
+        acc = 0.5 * acc * (1 + torch.erf(acc / math.sqrt(2.0)))
+    elif act == 2:
+        acc = torch.relu(acc)
+    elif act == 3:
+        acc = acc[:, 0::2] * torch.sigmoid(acc[:, 1::2])
+    acc = acc * alpha
+    if residual is not None:
+        acc = acc + residual.double()
+    return acc
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-6), (torch.bfloat16, 2e-5)])
+@pytest.mark.parametrize("M,N,K,act", [(300, 768, 512, 0), (257, 512, 1536, 1), (1000, 2304, 768, 0),
+                                       (128, 3072, 768, 1), (513, 768, 3072, 0), (200, 1024, 3840, 3),
+                                       (64, 2048, 512, 2), (129, 512, 2048, 0), (100, 1536, 512, 0)])
+def test_linear(dtype, tol, M, N, K, act):
+    """Both GEMM kernels (FFMA fp32 / tcgen05 bf16) on identical operand values: the bf16 run gets
+    bf16-rounded inputs, so the only difference from the fp64 reference is fp32 accumulation order."""
+    g = torch.Generator().manual_seed(M * 7 + N + K)
+    A = (torch.randn(M, K, generator=g) * 0.5).to(dtype)
+    W = (torch.randn(N, K, generator=g) * (1.0 / math.sqrt(K))).to(dtype)
+    bias = torch.randn(N, generator=g) * 0.1
+    n_out = N // 2 if act == 3 else N
+    res = torch.randn(M, n_out, generator=g)
+    ref = _ref_gemm(A.float(), W.float(), bias, act, 1.5, res)
+    out = ops().linear(A.to(DEV), W.to(DEV), bias.to(DEV), act=act, residual=res.to(DEV), alpha=1.5,
+                       out_dtype=torch.float32)
+    torch.cuda.synchronize()
+    assert rel_l2(out.cpu(), ref) < tol, rel_l2(out.cpu(), ref)
+    assert rel_max(out.cpu(), ref) < 20 * tol
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-6), (torch.bfloat16, 2e-5)])
+def test_implicit_conv_gemm_matches_conv1d(dtype, tol):
+    """stride-2 conv over channels-last rows as an overlapping-window GEMM (lda < K)."""
+    g = torch.Generator().manual_seed(5)
+    B, Tin, Cc, k = 3, 400, 512, 3
+    x = (torch.randn(B, Tin, Cc, generator=g) * 0.5).to(dtype)
+    w = (torch.randn(512, Cc, k, generator=g) * 0.03).to(dtype)
+    ref = F.gelu(F.conv1d(x.float().transpose(1, 2).double(), w.float().double(), stride=2)).transpose(1, 2)  # [B,Tout,512]
+    Tout = ref.shape[1]
+    Ta = Tin // 2
+    xb = torch.zeros(B * Tin + 8, Cc, dtype=dtype)
+    xb[:B * Tin] = x.reshape(B * Tin, Cc)
+    wk = w.permute(0, 2, 1).reshape(512, k * Cc).contiguous()
+    out = torch.zeros(B * Ta, 512, dtype=torch.float32, device=DEV)
+    ops().gemm(xb.to(DEV), wk.to(DEV), out, B * Ta, 512, k * Cc, lda=2 * Cc, a_rows=(B * Tin + 8) // 2, act=1,
+               rows_per_seg=Ta)
+    got = out.cpu().view(B, Ta, 512)[:, :Tout]
+    assert rel_l2(got, ref) < tol, rel_l2(got, ref)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-6), (torch.bfloat16, 2e-5)])
+def test_gemm_row_remap_mask_and_batches(dtype, tol):
+    """segment remap (padded destination), per-segment zeroing and the (outer, inner) batch of the pos-conv."""
+    g = torch.Generator().manual_seed(9)
+    B, G, T, Kc = 2, 16, 70, 128 * 64
+    Tpp = T + 128
+    xg = (torch.randn(B * G * Tpp + 8, 64, generator=g) * 0.3).to(dtype)
+    w = (torch.randn(G, 48, Kc, generator=g) * 0.01).to(dtype)
+    bias = torch.randn(768, generator=g) * 0.1
+    res = torch.randn(B * T, 768, generator=g)
+    out = torch.zeros(B * T, 768, dtype=torch.float32, device=DEV)
+    ops().gemm(xg.to(DEV), w.to(DEV), out, T, 48, Kc, lda=64, a_rows=Tpp, bias=bias.to(DEV), residual=res.to(DEV),
+               act=1, ldc=768, nb_outer=B, nb_inner=G, a_bs=(G * Tpp * 64, Tpp * 64), w_bs=48 * Kc,
+               c_bs=(T * 768, 48), bias_bs=48)
+    ref = torch.zeros(B, T, 768, dtype=torch.float64)
+    flat = xg.float().double().reshape(-1)
+    for b in range(B):
+        for gi in range(G):
+            base = (b * G + gi) * Tpp * 64
+            Am = flat[base:base + Tpp * 64].as_strided((T, Kc), (64, 1))
+            acc = Am @ w[gi].float().double().T + bias[gi * 48:(gi + 1) * 48].double()
+            ref[b, :, gi * 48:(gi + 1) * 48] = 0.5 * acc * (1 + torch.erf(acc / math.sqrt(2.0)))
+    ref = ref.view(B * T, 768) + res.double()
+    assert rel_l2(out.cpu(), ref) < tol, rel_l2(out.cpu(), ref)
+    # remap + mask: 3 segments of 50 rows, 45 valid, written at offset 2 into 60-row segments, zero beyond seg_len
+    M, N, K = 150, 512, 512
+    A = (torch.randn(M, K, generator=g) * 0.5).to(dtype)
+    W = (torch.randn(N, K, generator=g) * 0.05).to(dtype)
+    seg_len = torch.tensor([45, 20, 33], dtype=torch.int32)
+    out = torch.full((3 * 60, N), 7.0, dtype=torch.float32, device=DEV)
+    ops().gemm(A.to(DEV), W.to(DEV), out, M, N, K, lda=K, a_rows=M, rows_per_seg=50, seg_rows_valid=45,
+               out_rows_per_seg=60, out_row_off=2, seg_len=seg_len.to(DEV))
+    full = (A.float().double() @ W.float().double().T).view(3, 50, N)
+    exp = torch.full((3, 60, N), 7.0, dtype=torch.float64)
+    for s in range(3):
+        exp[s, 2:2 + 45] = full[s, :45]
+        exp[s, 2 + int(seg_len[s]):2 + 45] = 0
+    assert rel_l2(out.cpu().view(3, 60, N), exp) < tol
+
+
+@pytest.mark.parametrize("Cd", [512, 768])
+def test_layernorm(Cd):
+    g = torch.Generator().manual_seed(Cd)
+    x = torch.randn(301, Cd, generator=g) * 3 + 1
+    gm, bt = 1 + 0.1 * torch.randn(Cd, generator=g), 0.1 * torch.randn(Cd, generator=g)
+    ref = F.layer_norm(x.double(), (Cd,), gm.double(), bt.double(), 1e-5)
+    o32, obf = ops().layernorm(x.to(DEV), gm.to(DEV), bt.to(DEV), torch.bfloat16)
+    assert rel_l2(o32.cpu(), ref) < 1e-6
+    assert rel_l2(obf.cpu().float(), ref) < 4e-3
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-6), (torch.bfloat16, 6e-3)])
+@pytest.mark.parametrize("B,H,Tq,Tk,masked", [(3, 12, 249, 249, True), (2, 8, 63, 63, True), (2, 8, 16, 63, False),
+                                              (1, 12, 130, 130, True), (2, 8, 64, 300, False)])
+def test_attention(dtype, tol, B, H, Tq, Tk, masked):
+    g = torch.Generator().manual_seed(Tq * 3 + Tk)
+    Cd = H * 64
+    q = (torch.randn(B, Tq, Cd, generator=g) * 0.5).to(dtype)
+    k = torch.randn(B, Tk, Cd, generator=g).to(dtype)
+    v = torch.randn(B, Tk, Cd, generator=g).to(dtype)
+    kl = torch.tensor([Tk, max(1, Tk // 2), 1][:B], dtype=torch.int32) if masked else None
+    qh = q.float().double().view(B, Tq, H, 64).transpose(1, 2)
+    kh = k.float().double().view(B, Tk, H, 64).transpose(1, 2)
+    vh = v.float().double().view(B, Tk, H, 64).transpose(1, 2)
+    s = qh @ kh.transpose(-1, -2)
+    if masked:
+        s = s.masked_fill(torch.arange(Tk)[None, None, None, :] >= kl.long()[:, None, None, None], float("-inf"))
+    ref = (torch.softmax(s, -1) @ vh).transpose(1, 2).reshape(B, Tq, Cd)
+    out = ops().attention(q.to(DEV), k.to(DEV), v.to(DEV), H, kl.to(DEV) if masked else None)
+    assert rel_l2(out.cpu().float(), ref) < tol, rel_l2(out.cpu().float(), ref)
