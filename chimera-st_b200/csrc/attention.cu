@@ -134,6 +134,9 @@ __global__ void __launch_bounds__(256) attention_kernel(const T* __restrict__ q,
     store4(ob + (long long)r * ldo, make_float4(o[a][0] * inv, o[a][1] * inv, o[a][2] * inv, o[a][3] * inv));
   }
 }
+int launch_attention_tc(const void* q, const void* k, const void* v, void* out, long long ldq, long long ldkv, long long ldo,
+                        int B, int H, int n_q, int q_rows_per_seg, int n_kv, int kv_rows_per_seg,
+                        const int32_t* kv_len, cudaStream_t st);
 }  // namespace cst
 
 extern "C" int cst_attention(const void* q, const void* k, const void* v, void* out, int dtype,
@@ -145,8 +148,12 @@ extern "C" int cst_attention(const void* q, const void* k, const void* v, void* 
   CST_REQUIRE(n_q <= q_rows_per_seg && n_kv <= kv_rows_per_seg, "cst_attention: n_q/n_kv exceed rows per segment");
   CST_REQUIRE(ldq % 8 == 0 && ldkv % 8 == 0 && ldo % 8 == 0, "cst_attention: leading dims must be multiples of 8");
   CST_REQUIRE(H <= 65535 && B <= 65535, "cst_attention: grid too large");
-  dim3 grid(cdiv(n_q, AT_BQ), H, B);
   cudaStream_t st = (cudaStream_t)stream;
+  // bf16 with enough query rows to fill a 128-row MMA tile: tensor-core kernel (attention_tc.cu);
+  // fp32 (exact-parity mode) and the M-query memory stage: the CUDA-core kernel above.
+  if (dtype == CST_BF16 && n_q > 64)
+    return launch_attention_tc(q, k, v, out, ldq, ldkv, ldo, B, H, n_q, q_rows_per_seg, n_kv, kv_rows_per_seg, kv_len, st);
+  dim3 grid(cdiv(n_q, AT_BQ), H, B);
   static bool attr[2] = {false, false};
   if (dtype == CST_F32) {
     if (!attr[0]) { CST_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM)); attr[0] = true; }

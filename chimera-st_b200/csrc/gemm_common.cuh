@@ -87,6 +87,60 @@ __device__ __forceinline__ void epilogue8(const GemmDev& p, const RowInfo& ri, i
   }
 }
 
+// ---- fast exact-erf GELU for the tensor-core epilogue: Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7 on erf),
+// branch-free: 1 MUFU.RCP + 1 MUFU.EX2 + ~12 FP32 ops (erff() costs ~2x and diverges on |x|).
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  const float e = exp2f(-1.4426950408889634f * z * z);
+  const float erf_abs = fmaf(-poly, e, 1.0f);                 // erf(|x|/sqrt2)
+  const float hx = 0.5f * x;
+  return fmaf(fabsf(hx), erf_abs, hx);                        // 0.5x(1 + sign(x) erf(|x|/sqrt2))
+}
+
+struct RowDesc { long long out_row; int flags; int pad; };    // flags: 1 = store, 2 = store zeros
+
+// 4 consecutive accumulator columns n..n+3 (n % 4 == 0) of one output row, in the row-contiguous domain.
+__device__ __forceinline__ void epilogue4(const GemmDev& p, long long out_row, bool zero, int n, const float4 b4,
+                                          long long c_off, long long r_off, const float4 acc) {
+  float v[4] = {acc.x + b4.x, acc.y + b4.y, acc.z + b4.z, acc.w + b4.w};
+  if (p.act == CST_ACT_GLU) {
+    float o0 = v[0] * sigmoidf_(v[1]) * p.alpha, o1 = v[2] * sigmoidf_(v[3]) * p.alpha;
+    const int nc = n >> 1;
+    if (p.residual) {
+      const float2 r = *reinterpret_cast<const float2*>(p.residual + r_off + out_row * p.ldr + nc);
+      o0 += r.x; o1 += r.y;
+    }
+    if (zero) { o0 = 0.f; o1 = 0.f; }
+    const long long off = c_off + out_row * p.ldc + nc;
+    if (p.c_dtype == CST_BF16) *reinterpret_cast<uint32_t*>((__nv_bfloat16*)p.C + off) = pack_bf16x2(o0, o1);
+    else *reinterpret_cast<float2*>((float*)p.C + off) = make_float2(o0, o1);
+    return;
+  }
+  if (p.act == CST_ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = gelu_fast(v[j]);
+  } else if (p.act == CST_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) v[j] *= p.alpha;
+  if (p.residual) {
+    const float4 r = load4(p.residual + r_off + out_row * p.ldr + n);
+    v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
+  }
+  if (zero) { v[0] = v[1] = v[2] = v[3] = 0.f; }
+  const long long off = c_off + out_row * p.ldc + n;
+  if (p.c_dtype == CST_BF16) store4((__nv_bfloat16*)p.C + off, make_float4(v[0], v[1], v[2], v[3]));
+  else store4((float*)p.C + off, make_float4(v[0], v[1], v[2], v[3]));
+}
+
 int launch_gemm_f32(const GemmDev& p, int nz, cudaStream_t st);
 int launch_gemm_tc(const cst_gemm_params& hp, const GemmDev& p, int nz, cudaStream_t st);
 

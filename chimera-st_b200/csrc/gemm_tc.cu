@@ -2,19 +2,25 @@
 // ring -> tcgen05.mma (cta_group::1, M=128, N=BN, K=16 per instruction) accumulating fp32 in tensor
 // memory -> tcgen05.ld epilogue (bias / GELU / ReLU / GLU / alpha / residual / row masking).
 // Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc),
-// warps 2-5 = epilogue; two TMEM accumulator stages so tile i's epilogue overlaps tile i+1's MMAs.
+// warps 2-9 = epilogue (two warps per TMEM lane quarter, each owning half of the tile's columns); two TMEM
+// accumulator stages so tile i's epilogue overlaps tile i+1's MMAs.  The epilogue transposes each 32x32
+// accumulator block through a per-warp shared-memory patch so that bias/residual loads and the C stores are
+// row-contiguous (a warp instruction covers 4 rows x 128 B) instead of one row per lane.
 //
 // Implicit-GEMM convolutions need no im2col and no overlapping tensor maps: the activation is a plain
 // row-major [rows, lda] matrix and the k-th 64-wide K block of output row m lives at
 // (row m + (64k)/lda, column (64k)%lda) -- for a stride-s conv over channels-last data lda = s*C, so
 // the TMA coordinates simply walk into the following rows.
-#include <cuda.h>
 #include "gemm_common.cuh"
+#include "tc_common.cuh"
 
 namespace cst {
 
 constexpr int TC_BM = 128, TC_BK = 64;
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
+constexpr int TC_PATCH_LD = 36;                               // floats; 16B-aligned rows, conflict-free float4 access
+constexpr int TC_PATCH_BYTES = 32 * TC_PATCH_LD * 4 + 32 * 16; // 32x32 fp32 block + 32 row descriptors
 
 template <int BN> struct TcCfg {
   static constexpr int BN_PAD = (BN <= 64) ? 64 : (BN <= 128 ? 128 : 256);   // TMEM columns per stage
@@ -22,70 +28,10 @@ template <int BN> struct TcCfg {
   static constexpr int A_BYTES = TC_BM * TC_BK * 2;
   static constexpr int B_BYTES = BN * TC_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int STAGES = (BN >= 256) ? 3 : (BN >= 128 ? 5 : 7);
+  static constexpr int EPI_BYTES = TC_EPI_WARPS * TC_PATCH_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
-
-// ---- PTX wrappers ---------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok = 0;
-  const long long t0 = clock64();
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    if (ok) break;
-    if (clock64() - t0 > 4000000000LL) {   // ~2 s: a protocol bug must not hang the GPU box
-      printf("cst gemm_tc: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-  uint32_t* r = reinterpret_cast<uint32_t*>(v);
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, 128-byte swizzled operand tile (rows of 64 bf16 = 128 B, 8-row atoms of 1024 B):
-// start>>4 | LBO(ignored, 1)<<16 | SBO(1024>>4)<<32 | version 1<<46 | SWIZZLE_128B(2)<<61
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
 
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -101,13 +47,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tfull_bar = bars + 16 * STAGES, tempty_bar = tfull_bar + 16;
   const uint32_t tmem_slot = tempty_bar + 16;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  uint8_t* epi_base = smem_raw + (bars + 256 - smem_u32(smem_raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = p.K / TC_BK;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar + 8 * s, 1); mbar_init(tempty_bar + 8 * s, 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar + 8 * s, 1); mbar_init(tempty_bar + 8 * s, TC_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -169,8 +116,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     __syncwarp();
   } else {
-    // ===================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1) =====================
+    // ===================== epilogue (warps 2..9) =====================
+    // TMEM lane quarter q = warp % 4 (hardware rule); the two warps of a quarter split the BN columns.
+    const int ew = warp - 2;
     const int q = warp & 3;
+    const int chalf = ew >> 2;                                 // 0: first half of the columns, 1: second half
+    float* patch = reinterpret_cast<float*>(epi_base + ew * TC_PATCH_BYTES);
+    RowDesc* rows = reinterpret_cast<RowDesc*>(patch + 32 * TC_PATCH_LD);
+    constexpr int NCH = (BN + 31) / 32;                        // 32-column chunks in the tile
+    constexpr int CH_PER = (NCH + 1) / 2;
+    const int lr = lane >> 3, lc = (lane & 7) * 4;             // coalesced domain: 4 rows x 8 float4 per pass
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int nb = tile % n_tiles; const int r = tile / n_tiles;
@@ -180,19 +135,45 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const long long c_off = zo * p.c_bs_outer + zi * p.c_bs_inner;
       const long long r_off = zo * p.r_bs_outer + zi * p.r_bs_inner;
       const int as = it & 1; const uint32_t aph = (it >> 1) & 1;
+      {
+        const RowInfo ri = row_info(p, mb * TC_BM + q * 32 + lane, zo);
+        RowDesc d; d.out_row = ri.out_row; d.flags = (ri.store ? 1 : 0) | (ri.zero ? 2 : 0); d.pad = 0;
+        rows[lane] = d;
+      }
       mbar_wait(tfull_bar + 8 * as, aph);
       tc_fence_after();
-      const int m = mb * TC_BM + q * 32 + lane;
-      const RowInfo ri = row_info(p, m, zo);
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * Cfg::BN_PAD;
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 16) {
-        float acc[16];
-        tmem_ld16(t_row + c, acc);
+      for (int ch = chalf * CH_PER; ch < NCH && ch < (chalf + 1) * CH_PER; ++ch) {
+        const int c = ch * 32;
+        float acc[32];
+        if (BN - c >= 32) {
+          tmem_ld32(t_row + c, acc);
+        } else {                                              // BN = 48: last chunk holds 16 columns
+          tmem_ld16(t_row + c, acc);
+#pragma unroll
+          for (int i = 16; i < 32; ++i) acc[i] = 0.f;
+        }
         tmem_ld_wait();
-        const int n = nb * BN + c;
-        epilogue8(p, ri, n, bias, c_off, r_off, *reinterpret_cast<const float(*)[8]>(&acc[0]));
-        epilogue8(p, ri, n + 8, bias, c_off, r_off, *reinterpret_cast<const float(*)[8]>(&acc[8]));
+        __syncwarp();                                          // previous pass finished reading the patch
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          *reinterpret_cast<float4*>(&patch[lane * TC_PATCH_LD + 4 * i]) = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+        __syncwarp();
+        const int n = nb * BN + c + lc;
+        if (c + lc < BN && n < p.N) {
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (bias) b4 = __ldg(reinterpret_cast<const float4*>(bias + n));
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = i * 4 + lr;
+            const RowDesc d = rows[rr];
+            if (d.flags & 1) {
+              const float4 v = *reinterpret_cast<const float4*>(&patch[rr * TC_PATCH_LD + lc]);
+              epilogue4(p, d.out_row, (d.flags & 2) != 0, n, b4, c_off, r_off, v);
+            }
+          }
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -206,39 +187,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
   }
-}
-
-// ---- host side -----------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)p;
-  }
-  return fn;
-}
-
-static int make_map_2d(CUtensorMap* map, const void* base, long long inner, long long outer, long long pitch_elems,
-                       int box_inner, int box_outer) {
-  EncodeTiledFn enc = get_encode_fn();
-  CST_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
-  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
-  cuuint64_t strides[1] = {(cuuint64_t)pitch_elems * 2};
-  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  CST_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d): inner=%lld outer=%lld pitch=%lld box=%dx%d base=%p",
-              (int)r, inner, outer, pitch_elems, box_inner, box_outer, base);
-  return CST_OK;
 }
 
 template <int BN>

@@ -210,8 +210,10 @@ class EncoderPlan:
         for i, lw in enumerate(P["w2v_layers"]):
             self._linear(self.xa, lw["qkv_w"], lw["qkv_b"], self.qkv, R)
             qp = self.qkv.data_ptr()
+            # all allocated query rows are computed (rows >= T' are finite filler, never read as keys):
+            # no buffer row is ever left stale, so masked keys always meet finite V rows
             self._attn(qp, qp + D * es, qp + 2 * D * es, self.ctx, 3 * D, 3 * D, W2V_HEADS,
-                       g.Tp, g.T6a, g.Tp, g.T6a, self.w2v_valid)
+                       g.T6a, g.T6a, g.Tp, g.T6a, self.w2v_valid)
             self._linear(self.ctx, lw["o_w"], lw["o_b"], self.y, R, residual=self.x)
             self._ln(self.y, (lw["ln1_g"], lw["ln1_b"]), R, out_f32=self.x, out_lp=self.xa)
             self._linear(self.xa, lw["fc1_w"], lw["fc1_b"], self.ffn, R, act=L.ACT_GELU)
@@ -235,7 +237,7 @@ class EncoderPlan:
                    seg_rows_valid=g.T1, out_rows_per_seg=g.Tin2, out_row_off=2, ldc=ENC_DIM)
         self._gemm(self.sub_mid, w1, self.x2, B * g.T2a, w1.shape[0], w1.shape[1], lda=2 * ENC_DIM,
                    a_rows=(B * g.Tin2 + SLACK) // 2, bias=P["sub1_b"], act=L.ACT_GLU, alpha=math.sqrt(ENC_DIM),
-                   rows_per_seg=g.T2a, seg_rows_valid=g.T2, out_rows_per_seg=g.T2a, ldc=ENC_DIM)
+                   rows_per_seg=g.T2a, out_rows_per_seg=g.T2a, ldc=ENC_DIM)
 
     def _stage_shared_layers(self):
         g, P = self.g, self.P
@@ -247,7 +249,7 @@ class EncoderPlan:
             self._linear(self.x2a, lw["qkv_w"], lw["qkv_b"], self.qkv2, R2)
             qp = self.qkv2.data_ptr()
             self._attn(qp, qp + D * es, qp + 2 * D * es, self.ctx2, 3 * D, 3 * D, ENC_HEADS,
-                       g.T2, g.T2a, g.T2, g.T2a, self.sub_valid)
+                       g.T2a, g.T2a, g.T2, g.T2a, self.sub_valid)
             self._linear(self.ctx2, lw["o_w"], lw["o_b"], self.x2, R2, residual=self.x2)
             self._ln(self.x2, (lw["ln2_g"], lw["ln2_b"]), R2, out_lp=self.x2a)
             self._linear(self.x2a, lw["fc1_w"], lw["fc1_b"], self.ffn2, R2, act=L.ACT_RELU)

@@ -175,7 +175,9 @@ def test_layernorm(Cd):
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-6), (torch.bfloat16, 6e-3)])
 @pytest.mark.parametrize("B,H,Tq,Tk,masked", [(3, 12, 249, 249, True), (2, 8, 63, 63, True), (2, 8, 16, 63, False),
-                                              (1, 12, 130, 130, True), (2, 8, 64, 300, False)])
+                                              (1, 12, 130, 130, True), (2, 8, 64, 300, False),
+                                              (2, 12, 1499, 1499, True), (3, 8, 188, 188, True), (2, 12, 750, 749, False),
+                                              (1, 12, 128, 128, False), (2, 8, 129, 257, True), (3, 12, 400, 385, True)])
 def test_attention(dtype, tol, B, H, Tq, Tk, masked):
     g = torch.Generator().manual_seed(Tq * 3 + Tk)
     Cd = H * 64
