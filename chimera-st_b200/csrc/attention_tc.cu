@@ -149,9 +149,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
       }
       const float m_new = fmaxf(m_run, mx);              // finite: every visited tile holds >= 1 valid key
-      const float alpha = exp2f((m_run - m_new) * FA_LOG2E);
+      const float alpha = mufu_ex2((m_run - m_new) * FA_LOG2E);
       const float mb = m_new * FA_LOG2E;
-      // pass 2: P = exp2(s*log2e - m*log2e) -> bf16 -> swizzled shared memory; row sum of the ROUNDED values
+      // pass 2: P = exp2(s*log2e - m*log2e) -> bf16 -> swizzled shared memory (packed FFMA2 + MUFU.EX2)
       float rs = 0.f;
       const uint32_t prow = sP + sb * FA_P_BYTES + r * 128;
 #pragma unroll 1
@@ -160,17 +160,21 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tmem_ld32(srow + c, s);
         tmem_ld_wait();
         uint32_t pk[16];
+        const uint64_t l2e = pk2(FA_LOG2E, FA_LOG2E), nmb = pk2(-mb, -mb);
+        uint64_t rs2 = pk2(0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          float p0 = exp2f(fmaf(s[i], FA_LOG2E, -mb)), p1 = exp2f(fmaf(s[i + 1], FA_LOG2E, -mb));
+          float a0, a1;
+          upk2(ffma2(pk2(s[i], s[i + 1]), l2e, nmb), a0, a1);
+          float p0 = mufu_ex2(a0), p1 = mufu_ex2(a1);
           if (tail) {
             if (kbase + c + i >= klen) p0 = 0.f;
             if (kbase + c + i + 1 >= klen) p1 = 0.f;
           }
-          const __nv_bfloat162 hb = __floats2bfloat162_rn(p0, p1);
-          rs += __low2float(hb) + __high2float(hb);
-          pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&hb);
+          rs2 = fadd2(rs2, pk2(p0, p1));
+          pk[i >> 1] = pack_bf16x2(p0, p1);
         }
+        { float r0, r1; upk2(rs2, r0, r1); rs += r0 + r1; }
         const uint32_t half = prow + (c >> 6) * (FA_P_BYTES / 2);
         const int ch0 = (c & 63) >> 3;                   // first 16-byte chunk of this 32-key group
 #pragma unroll

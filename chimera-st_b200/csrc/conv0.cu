@@ -77,7 +77,9 @@ __global__ void __launch_bounds__(C0) conv0_finalize_kernel(const double* __rest
   scale_shift[(size_t)b * C0 + c] = make_float2((float)sc, (float)((double)beta[c] - mean * sc));
 }
 
-// block: 4 frame lanes x 64 channel octets; FT frames per block
+// block: 4 frame lanes x 64 channel octets; FT frames per block.  Two channels share one packed FFMA2 chain
+// (w[c][j], w[c+1][j]) * (x[j], x[j]); the bf16 path uses the branch-free packed erf GELU (gelu2), the fp32
+// path keeps erff() so the 1e-5 parity mode stays bit-comparable to torch's erf GELU.
 template <typename OutT, int FT>
 __global__ void __launch_bounds__(256) conv0_apply_kernel(const float* __restrict__ wave, int L, int T0, int rows_per_seg,
                                                           const float* __restrict__ w, const float2* __restrict__ scale_shift,
@@ -92,13 +94,13 @@ __global__ void __launch_bounds__(256) conv0_apply_kernel(const float* __restric
   }
   const int cq = threadIdx.x & 63, tq = threadIdx.x >> 6;
   const int c0 = cq * 8;
-  float wr[8][K0], sc[8], sh[8];
+  uint64_t wr[4][K0], sc[4], sh[4];                 // channel pairs (c0+2i, c0+2i+1)
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < 4; ++i) {
 #pragma unroll
-    for (int j = 0; j < K0; ++j) wr[i][j] = __ldg(w + (c0 + i) * K0 + j);
-    const float2 s = scale_shift[(size_t)b * C0 + c0 + i];
-    sc[i] = s.x; sh[i] = s.y;
+    for (int j = 0; j < K0; ++j) wr[i][j] = pk2(__ldg(w + (c0 + 2 * i) * K0 + j), __ldg(w + (c0 + 2 * i + 1) * K0 + j));
+    const float2 s0 = scale_shift[(size_t)b * C0 + c0 + 2 * i], s1 = scale_shift[(size_t)b * C0 + c0 + 2 * i + 1];
+    sc[i] = pk2(s0.x, s1.x); sh[i] = pk2(s0.y, s1.y);
   }
   __syncthreads();
   OutT* orow = out + ((size_t)b * rows_per_seg) * C0 + c0;
@@ -108,15 +110,17 @@ __global__ void __launch_bounds__(256) conv0_apply_kernel(const float* __restric
     if (t >= rows_per_seg) break;
     float y[8];
     if (t < T0) {
-      float xv[K0];
+      uint64_t xv[K0];
 #pragma unroll
-      for (int j = 0; j < K0; ++j) xv[j] = xs[tl * S0 + j];
+      for (int j = 0; j < K0; ++j) { const float v = xs[tl * S0 + j]; xv[j] = pk2(v, v); }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float a = 0.f;
+      for (int i = 0; i < 4; ++i) {
+        uint64_t a = fmul2(wr[i][0], xv[0]);
 #pragma unroll
-        for (int j = 0; j < K0; ++j) a = fmaf(wr[i][j], xv[j], a);
-        y[i] = gelu_erf(fmaf(a, sc[i], sh[i]));
+        for (int j = 1; j < K0; ++j) a = ffma2(wr[i][j], xv[j], a);
+        upk2(ffma2(a, sc[i], sh[i]), y[2 * i], y[2 * i + 1]);
+        if (sizeof(OutT) == 2) gelu2(y[2 * i], y[2 * i + 1]);
+        else { y[2 * i] = gelu_erf(y[2 * i]); y[2 * i + 1] = gelu_erf(y[2 * i + 1]); }
       }
     } else {
 #pragma unroll

@@ -20,7 +20,7 @@ constexpr int TC_BM = 128, TC_BK = 64;
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_PATCH_LD = 36;                               // floats; 16B-aligned rows, conflict-free float4 access
-constexpr int TC_PATCH_BYTES = 32 * TC_PATCH_LD * 4 + 32 * 16; // 32x32 fp32 block + 32 row descriptors
+constexpr int TC_PATCH_BYTES = 32 * TC_PATCH_LD * 4;           // one 32x32 fp32 block per epilogue warp
 
 template <int BN> struct TcCfg {
   static constexpr int BN_PAD = (BN <= 64) ? 64 : (BN <= 128 ? 128 : 256);   // TMEM columns per stage
@@ -33,7 +33,7 @@ template <int BN> struct TcCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-template <int BN>
+template <int BN, int ACT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const GemmDev p, int m_tiles, int n_tiles, int total_tiles, int a_wrap) {
@@ -122,10 +122,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int q = warp & 3;
     const int chalf = ew >> 2;                                 // 0: first half of the columns, 1: second half
     float* patch = reinterpret_cast<float*>(epi_base + ew * TC_PATCH_BYTES);
-    RowDesc* rows = reinterpret_cast<RowDesc*>(patch + 32 * TC_PATCH_LD);
     constexpr int NCH = (BN + 31) / 32;                        // 32-column chunks in the tile
     constexpr int CH_PER = (NCH + 1) / 2;
-    const int lr = lane >> 3, lc = (lane & 7) * 4;             // coalesced domain: 4 rows x 8 float4 per pass
+    const int lr = lane >> 3, lc = (lane & 7) * 4;             // row-contiguous domain: 4 rows x 8 float4 per pass
+    const bool c_bf16 = p.c_dtype == CST_BF16;
+    const uint64_t alpha2 = pk2(p.alpha, p.alpha);
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int nb = tile % n_tiles; const int r = tile / n_tiles;
@@ -135,10 +136,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const long long c_off = zo * p.c_bs_outer + zi * p.c_bs_inner;
       const long long r_off = zo * p.r_bs_outer + zi * p.r_bs_inner;
       const int as = it & 1; const uint32_t aph = (it >> 1) & 1;
-      {
-        const RowInfo ri = row_info(p, mb * TC_BM + q * 32 + lane, zo);
-        RowDesc d; d.out_row = ri.out_row; d.flags = (ri.store ? 1 : 0) | (ri.zero ? 2 : 0); d.pad = 0;
-        rows[lane] = d;
+      // this lane's 8 rows are the same for every column chunk of the tile: resolve them once
+      long long crow[8], rrow[8];
+      uint32_t st_mask = 0, z_mask = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const RowInfo ri = row_info(p, mb * TC_BM + q * 32 + i * 4 + lr, zo);
+        crow[i] = c_off + ri.out_row * p.ldc;
+        rrow[i] = r_off + ri.out_row * p.ldr;
+        st_mask |= (ri.store ? 1u : 0u) << i;
+        z_mask |= (ri.zero ? 1u : 0u) << i;
       }
       mbar_wait(tfull_bar + 8 * as, aph);
       tc_fence_after();
@@ -146,6 +153,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll 1
       for (int ch = chalf * CH_PER; ch < NCH && ch < (chalf + 1) * CH_PER; ++ch) {
         const int c = ch * 32;
+        const int n = nb * BN + c + lc;
+        const bool col_ok = (c + lc < BN) && (n < p.N);
+        const int nc = (ACT == CST_ACT_GLU) ? (n >> 1) : n;   // output column
         float acc[32];
         if (BN - c >= 32) {
           tmem_ld32(t_row + c, acc);
@@ -154,23 +164,52 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int i = 16; i < 32; ++i) acc[i] = 0.f;
         }
+        // independent global loads first (bias, residual rows): their latency overlaps the TMEM load
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bias && col_ok) b4 = __ldg(reinterpret_cast<const float4*>(bias + n));
+        float4 res[8];
+        if (p.residual) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (col_ok && ((st_mask >> i) & 1)) {
+              if (ACT == CST_ACT_GLU) { const float2 t2 = *reinterpret_cast<const float2*>(p.residual + rrow[i] + nc); res[i].x = t2.x; res[i].y = t2.y; }
+              else res[i] = *reinterpret_cast<const float4*>(p.residual + rrow[i] + nc);
+            }
+          }
+        }
         tmem_ld_wait();
         __syncwarp();                                          // previous pass finished reading the patch
 #pragma unroll
         for (int i = 0; i < 8; ++i)
           *reinterpret_cast<float4*>(&patch[lane * TC_PATCH_LD + 4 * i]) = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
         __syncwarp();
-        const int n = nb * BN + c + lc;
-        if (c + lc < BN && n < p.N) {
-          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (bias) b4 = __ldg(reinterpret_cast<const float4*>(bias + n));
+        if (col_ok) {
+          const uint64_t b01 = pk2(b4.x, b4.y), b23 = pk2(b4.z, b4.w);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const int rr = i * 4 + lr;
-            const RowDesc d = rows[rr];
-            if (d.flags & 1) {
-              const float4 v = *reinterpret_cast<const float4*>(&patch[rr * TC_PATCH_LD + lc]);
-              epilogue4(p, d.out_row, (d.flags & 2) != 0, n, b4, c_off, r_off, v);
+            if (!((st_mask >> i) & 1)) continue;
+            const float4 a4 = *reinterpret_cast<const float4*>(&patch[(i * 4 + lr) * TC_PATCH_LD + lc]);
+            float v0, v1, v2, v3;
+            upk2(fadd2(pk2(a4.x, a4.y), b01), v0, v1);
+            upk2(fadd2(pk2(a4.z, a4.w), b23), v2, v3);
+            const bool zr = (z_mask >> i) & 1;
+            if (ACT == CST_ACT_GLU) {
+              float o0 = v0 * __fdividef(1.0f, 1.0f + __expf(-v1)) * p.alpha;
+              float o1 = v2 * __fdividef(1.0f, 1.0f + __expf(-v3)) * p.alpha;
+              if (p.residual) { o0 += res[i].x; o1 += res[i].y; }
+              if (zr) { o0 = 0.f; o1 = 0.f; }
+              if (c_bf16) *reinterpret_cast<uint32_t*>((__nv_bfloat16*)p.C + crow[i] + nc) = pack_bf16x2(o0, o1);
+              else *reinterpret_cast<float2*>((float*)p.C + crow[i] + nc) = make_float2(o0, o1);
+            } else {
+              if (ACT == CST_ACT_GELU) { gelu2(v0, v1); gelu2(v2, v3); }
+              else if (ACT == CST_ACT_RELU) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
+              uint64_t o01 = fmul2(pk2(v0, v1), alpha2), o23 = fmul2(pk2(v2, v3), alpha2);
+              if (p.residual) { o01 = fadd2(o01, pk2(res[i].x, res[i].y)); o23 = fadd2(o23, pk2(res[i].z, res[i].w)); }
+              upk2(o01, v0, v1); upk2(o23, v2, v3);
+              if (zr) { v0 = v1 = v2 = v3 = 0.f; }
+              if (c_bf16) store4((__nv_bfloat16*)p.C + crow[i] + nc, make_float4(v0, v1, v2, v3));
+              else store4((float*)p.C + crow[i] + nc, make_float4(v0, v1, v2, v3));
             }
           }
         }
@@ -189,12 +228,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
-template <int BN>
-static int launch_tc(const cst_gemm_params& hp, const GemmDev& p, int nz, cudaStream_t st) {
+template <int BN, int ACT>
+static int launch_tc_act(const cst_gemm_params& hp, const GemmDev& p, int nz, cudaStream_t st) {
   using Cfg = TcCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    CST_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    CST_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   const int a_wrap = hp.K > hp.lda ? 1 : 0;
@@ -217,9 +256,19 @@ static int launch_tc(const cst_gemm_params& hp, const GemmDev& p, int nz, cudaSt
   CST_CHECK_CUDA(cudaGetDevice(&dev));
   CST_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = (int)(total < sms ? total : sms);
-  gemm_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p, m_tiles, n_tiles, (int)total, a_wrap);
+  gemm_tc_kernel<BN, ACT><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p, m_tiles, n_tiles, (int)total, a_wrap);
   CST_LAUNCH_CHECK();
   return CST_OK;
+}
+
+template <int BN>
+static int launch_tc(const cst_gemm_params& hp, const GemmDev& p, int nz, cudaStream_t st) {
+  switch (hp.act) {
+    case CST_ACT_NONE: return launch_tc_act<BN, CST_ACT_NONE>(hp, p, nz, st);
+    case CST_ACT_GELU: return launch_tc_act<BN, CST_ACT_GELU>(hp, p, nz, st);
+    case CST_ACT_RELU: return launch_tc_act<BN, CST_ACT_RELU>(hp, p, nz, st);
+    default: return launch_tc_act<BN, CST_ACT_GLU>(hp, p, nz, st);
+  }
 }
 
 int launch_gemm_tc(const cst_gemm_params& hp, const GemmDev& p, int nz, cudaStream_t st) {
