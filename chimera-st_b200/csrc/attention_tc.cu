@@ -1,45 +1,47 @@
 // Padding-aware flash attention on the 5th-gen tensor cores (bf16 operands, fp32 softmax/accumulate),
 // head_dim 64.  One CTA = 128 query rows of one (utterance, head); keys/values stream in 128-row tiles.
-//   warp 0      : TMA producer (Q once; K_j,V_j into a 3-stage ring, 128B-swizzled)
-//   warp 1      : tcgen05.mma issuer.  S_j = Q K_j^T (M128 N128 K64, both operands K-major) into one of two
-//                 TMEM S buffers; PV_j = P_j V_j (M128 N64 K128; P from shared memory K-major, V as an
-//                 MN-major B operand straight from the TMA tile -- no transpose) into one of two PV buffers.
-//                 S_{j+1} is issued before PV_j so the tensor pipe works while the softmax of tile j runs.
-//   warps 2..5  : softmax.  thread = query row: tcgen05.ld the S row, exact -inf key mask (keys >= kv_len[b]),
-//                 running max / sum in fp32, P = exp2 in bf16 -> shared memory (manual 128B swizzle), output
-//                 accumulator O kept in registers: O = O * alpha_j + PV_j (no TMEM read-modify-write).
-// Every query row of the tile is computed (padded query rows are live in the reference); keys beyond kv_len
-// contribute exactly zero probability.  V rows of masked keys must be finite (the plan guarantees it).
+// Resources are cut to HALF an SM (112 KB shared memory, 256 TMEM columns, <=170 registers) so TWO CTAs are
+// resident per SM: while one CTA's softmax warps run (MUFU/FMA bound), the other CTA's MMAs use the tensor
+// pipe -- the overlap a single CTA would need double-buffered S/P/PV for.
+//   warp 0      : TMA producer (Q once; K_j,V_j into a 2-stage ring, 128B-swizzled)
+//   warp 1      : tcgen05.mma issuer.  S_j = Q K_j^T (M128 N128 K64, both operands K-major) into TMEM cols
+//                 0..127; PV_j = P_j V_j (M128 N64 K128; P from shared memory K-major, V as an MN-major B
+//                 operand straight from the TMA tile -- no transpose) into TMEM cols 128..191.
+//   warps 2..5  : softmax.  thread = query row: tcgen05.ld the S row, exact key mask (keys >= kv_len[b] get
+//                 zero probability), running max / sum in fp32, P = exp2 in bf16 -> shared memory (manual 128B
+//                 swizzle); the output accumulator stays in registers: O = O * alpha_j + PV_j.
+// Every query row of the tile is computed (padded query rows are live in the reference).  V rows of masked
+// keys must be finite (the plan guarantees it: no activation row is ever left unwritten).
 #include "tc_common.cuh"
 
 namespace cst {
 
-constexpr int FA_BQ = 128, FA_BK = 128, FA_D = 64, FA_KS = 3;
+constexpr int FA_BQ = 128, FA_BK = 128, FA_D = 64, FA_KS = 2;
 constexpr int FA_THREADS = 192;
 constexpr int FA_Q_BYTES = FA_BQ * FA_D * 2;            // 16 KB
 constexpr int FA_KV_BYTES = FA_BK * FA_D * 2;           // 16 KB each for K and V
 constexpr int FA_P_BYTES = FA_BQ * FA_BK * 2;           // 32 KB (two 64-key halves of 16 KB)
-constexpr int FA_SMEM = FA_Q_BYTES + 2 * FA_KS * FA_KV_BYTES + 2 * FA_P_BYTES + 1024 + 256;
+constexpr int FA_SMEM = FA_Q_BYTES + 2 * FA_KS * FA_KV_BYTES + FA_P_BYTES + 256;   // 112.25 KB: two CTAs per SM
+constexpr int FA_TMEM_COLS = 256;
 constexpr float FA_LOG2E = 1.4426950408889634f;
 
-__global__ void __launch_bounds__(FA_THREADS, 1)
+__global__ void __launch_bounds__(FA_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, long long ldo,
-                    int n_q, int q_rows_per_seg, int n_kv, int kv_rows_per_seg, const int32_t* __restrict__ kv_len,
-                    int q_col0, int k_col0, int v_col0) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+                    int n_q, int q_rows_per_seg, int n_kv, int kv_rows_per_seg, const int32_t* __restrict__ kv_len) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = smem_u32(smem_raw);
   const uint32_t sQ = base;
   const uint32_t sK = sQ + FA_Q_BYTES;
   const uint32_t sV = sK + FA_KS * FA_KV_BYTES;
   const uint32_t sP = sV + FA_KS * FA_KV_BYTES;
-  const uint32_t bars = sP + 2 * FA_P_BYTES;
+  const uint32_t bars = sP + FA_P_BYTES;
   const uint32_t q_full = bars;
   const uint32_t kv_full = bars + 8, kv_empty = kv_full + 8 * FA_KS;
-  const uint32_t s_full = kv_empty + 8 * FA_KS, s_empty = s_full + 16;
-  const uint32_t p_full = s_empty + 16, pv_full = p_full + 16, pv_empty = pv_full + 16;
-  const uint32_t tmem_slot = pv_empty + 16;
-  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  const uint32_t s_full = kv_empty + 8 * FA_KS, s_empty = s_full + 8;
+  const uint32_t p_full = s_empty + 8, pv_full = p_full + 8, pv_empty = pv_full + 8;
+  const uint32_t tmem_slot = pv_empty + 8;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * FA_BQ;
@@ -48,37 +50,36 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const int n_tiles = (klen + FA_BK - 1) / FA_BK;
 
   if (warp == 0 && lane == 0) {
+    if ((base & 1023u) != 0) { printf("cst attention_tc: shared memory base not 1024-byte aligned\n"); __trap(); }
     mbar_init(q_full, 1);
     for (int s = 0; s < FA_KS; ++s) { mbar_init(kv_full + 8 * s, 1); mbar_init(kv_empty + 8 * s, 1); }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(s_full + 8 * s, 1); mbar_init(s_empty + 8 * s, 4);
-      mbar_init(p_full + 8 * s, 4); mbar_init(pv_full + 8 * s, 1); mbar_init(pv_empty + 8 * s, 4);
-    }
+    mbar_init(s_full, 1); mbar_init(s_empty, 4);
+    mbar_init(p_full, 4); mbar_init(pv_full, 1); mbar_init(pv_empty, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)FA_TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
-  const uint32_t tS = tmem_base, tPV = tmem_base + 256;        // S buffers at cols 0,128; PV at 256,320
+  const uint32_t tS = tmem_base, tPV = tmem_base + FA_BK;       // S at cols 0..127, PV at 128..191
 
   if (warp == 0) {
     if (lane == 0 && n_tiles > 0) {
       const int q_row = b * q_rows_per_seg + q0;
       mbar_expect_tx(q_full, FA_Q_BYTES);
-      tma_load_2d(sQ, &tmQ, q_full, q_col0 + h * FA_D, q_row);
+      tma_load_2d(sQ, &tmQ, q_full, h * FA_D, q_row);
       for (int j = 0; j < n_tiles; ++j) {
         const int st = j % FA_KS, u = j / FA_KS;
         mbar_wait(kv_empty + 8 * st, (u & 1) ^ 1);
         mbar_expect_tx(kv_full + 8 * st, 2 * FA_KV_BYTES);
         const int k_row = b * kv_rows_per_seg + j * FA_BK;
-        tma_load_2d(sK + st * FA_KV_BYTES, &tmK, kv_full + 8 * st, k_col0 + h * FA_D, k_row);
-        tma_load_2d(sV + st * FA_KV_BYTES, &tmV, kv_full + 8 * st, v_col0 + h * FA_D, k_row);
+        tma_load_2d(sK + st * FA_KV_BYTES, &tmK, kv_full + 8 * st, h * FA_D, k_row);
+        tma_load_2d(sV + st * FA_KV_BYTES, &tmV, kv_full + 8 * st, h * FA_D, k_row);
       }
     }
     __syncwarp();
@@ -88,35 +89,35 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       constexpr uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(FA_BK >> 3) << 17) | ((uint32_t)(FA_BQ >> 4) << 24);
       constexpr uint32_t idesc_pv = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(FA_D >> 3) << 17) | ((uint32_t)(FA_BQ >> 4) << 24);
       const uint64_t qdesc = make_sw128_desc(sQ);
-      auto issue_s = [&](int j) {
-        const int st = j % FA_KS, sb = j & 1;
-        mbar_wait(kv_full + 8 * st, (j / FA_KS) & 1);
-        mbar_wait(s_empty + 8 * sb, ((j >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint64_t kdesc = make_sw128_desc(sK + st * FA_KV_BYTES);
-#pragma unroll
-        for (int k = 0; k < FA_D / 16; ++k) tc_mma_bf16(tS + sb * FA_BK, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
-        tc_commit(s_full + 8 * sb);
-      };
-      mbar_wait(q_full, 0);
-      issue_s(0);
-      for (int j = 0; j < n_tiles; ++j) {
-        if (j + 1 < n_tiles) issue_s(j + 1);
-        const int st = j % FA_KS, pb = j & 1;
-        mbar_wait(p_full + 8 * pb, (j >> 1) & 1);
-        mbar_wait(pv_empty + 8 * pb, ((j >> 1) & 1) ^ 1);
+      auto issue_pv = [&](int j) {
+        const int st = j % FA_KS;
+        mbar_wait(p_full, j & 1);
+        mbar_wait(pv_empty, (j & 1) ^ 1);
         tc_fence_after();
         int keys = klen - j * FA_BK; keys = keys < FA_BK ? keys : FA_BK;
         const int k16 = (keys + 15) >> 4;
-        const uint32_t pbase = sP + pb * FA_P_BYTES, vbase = sV + st * FA_KV_BYTES;
+        const uint32_t vbase = sV + st * FA_KV_BYTES;
         for (int k = 0; k < k16; ++k) {
-          const uint64_t pdesc = make_sw128_desc(pbase + (k >> 2) * (FA_P_BYTES / 2) + (k & 3) * 32);
+          const uint64_t pdesc = make_sw128_desc(sP + (k >> 2) * (FA_P_BYTES / 2) + (k & 3) * 32);
           const uint64_t vdesc = make_sw128_mn_desc(vbase + k * 2048);
-          tc_mma_bf16(tPV + pb * FA_D, pdesc, vdesc, idesc_pv, k != 0);
+          tc_mma_bf16(tPV, pdesc, vdesc, idesc_pv, k != 0);
         }
-        tc_commit(pv_full + 8 * pb);
+        tc_commit(pv_full);
         tc_commit(kv_empty + 8 * st);
+      };
+      mbar_wait(q_full, 0);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j % FA_KS;
+        mbar_wait(kv_full + 8 * st, (j / FA_KS) & 1);
+        mbar_wait(s_empty, (j & 1) ^ 1);                 // softmax finished reading S_{j-1}
+        tc_fence_after();
+        const uint64_t kdesc = make_sw128_desc(sK + st * FA_KV_BYTES);
+#pragma unroll
+        for (int k = 0; k < FA_D / 16; ++k) tc_mma_bf16(tS, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
+        tc_commit(s_full);
+        if (j > 0) issue_pv(j - 1);                      // P_{j-1} was published together with s_empty
       }
+      issue_pv(n_tiles - 1);
     }
     __syncwarp();
   } else {
@@ -128,11 +129,26 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
     for (int i = 0; i < FA_D; ++i) o[i] = 0.f;
     float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
-    for (int j = 0; j < n_tiles; ++j) {
-      const int sb = j & 1;
-      mbar_wait(s_full + 8 * sb, (j >> 1) & 1);
+    const uint32_t srow = tS + lane_off;
+    const uint32_t prow = sP + r * 128;
+    auto take_pv = [&](int j) {                          // O = O * alpha_j + PV_j  (PV_j is relative to m_j)
+      mbar_wait(pv_full, j & 1);
       tc_fence_after();
-      const uint32_t srow = tS + lane_off + sb * FA_BK;
+#pragma unroll
+      for (int c = 0; c < FA_D; c += 32) {
+        float pv[32];
+        tmem_ld32(tPV + lane_off + c, pv);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[c + i] = fmaf(o[c + i], alpha_prev, pv[i]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pv_empty);
+    };
+    for (int j = 0; j < n_tiles; ++j) {
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
       const int kbase = j * FA_BK;
       const bool tail = kbase + FA_BK > klen;
       // pass 1: row maximum
@@ -151,9 +167,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const float m_new = fmaxf(m_run, mx);              // finite: every visited tile holds >= 1 valid key
       const float alpha = mufu_ex2((m_run - m_new) * FA_LOG2E);
       const float mb = m_new * FA_LOG2E;
+      if (j > 0) take_pv(j - 1);                         // also proves the P buffer is free again
       // pass 2: P = exp2(s*log2e - m*log2e) -> bf16 -> swizzled shared memory (packed FFMA2 + MUFU.EX2)
       float rs = 0.f;
-      const uint32_t prow = sP + sb * FA_P_BYTES + r * 128;
 #pragma unroll 1
       for (int c = 0; c < FA_BK; c += 32) {
         float s[32];
@@ -184,44 +200,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                        "r"(pk[4 * q4 + 2]), "r"(pk[4 * q4 + 3]) : "memory");
         }
       }
-      tc_fence_before();                                 // S buffer fully read
+      tc_fence_before();                                 // S fully read
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // P visible to the tensor-core (async) proxy
       __syncwarp();
-      if (lane == 0) { mbar_arrive(s_empty + 8 * sb); mbar_arrive(p_full + 8 * sb); }
-      // consume PV_{j-1} (relative to m_{j-1}): O = O * alpha_{j-1} + PV_{j-1}
-      if (j > 0) {
-        const int pb = (j - 1) & 1;
-        mbar_wait(pv_full + 8 * pb, ((j - 1) >> 1) & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int c = 0; c < FA_D; c += 32) {
-          float pv[32];
-          tmem_ld32(tPV + lane_off + pb * FA_D + c, pv);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[c + i] = fmaf(o[c + i], alpha_prev, pv[i]);
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(pv_empty + 8 * pb);
-      }
+      if (lane == 0) { mbar_arrive(s_empty); mbar_arrive(p_full); }
       l_run = l_run * alpha + rs;
       m_run = m_new;
       alpha_prev = alpha;
     }
-    if (n_tiles > 0) {
-      const int pb = (n_tiles - 1) & 1;
-      mbar_wait(pv_full + 8 * pb, ((n_tiles - 1) >> 1) & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < FA_D; c += 32) {
-        float pv[32];
-        tmem_ld32(tPV + lane_off + pb * FA_D + c, pv);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[c + i] = fmaf(o[c + i], alpha_prev, pv[i]);
-      }
-    }
+    if (n_tiles > 0) take_pv(n_tiles - 1);
     if (q0 + r < n_q) {
       const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
       __nv_bfloat16* op = out + ((long long)b * q_rows_per_seg + q0 + r) * ldo + h * FA_D;
@@ -239,7 +226,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)FA_TMEM_COLS) : "memory");
   }
 }
 
@@ -262,7 +249,7 @@ int launch_attention_tc(const void* q, const void* k, const void* v, void* out, 
   if (rc) return rc;
   dim3 grid(cdiv(n_q, FA_BQ), H, B);
   attention_tc_kernel<<<grid, FA_THREADS, FA_SMEM, st>>>(tmQ, tmK, tmV, (__nv_bfloat16*)out, ldo, n_q, q_rows_per_seg,
-                                                       n_kv, kv_rows_per_seg, kv_len, 0, 0, 0);
+                                                       n_kv, kv_rows_per_seg, kv_len);
   CST_LAUNCH_CHECK();
   return CST_OK;
 }
