@@ -33,19 +33,23 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 import chimera_st_b200  # noqa: E402,F401
-from chimera_st_b200 import synth, batching  # noqa: E402
+from chimera_st_b200 import synth, batching  # noqa: E402,F401
+from chimera_st_b200 import distributed as D  # noqa: E402
 
 SR = 16000
 
 
 # --------------------------------------------------------------------------------------- workload
-def make_workload(name, rank, utts):
-    """-> list of batches, each a list of utterance lengths (samples), longest first."""
+def make_workload(name, rank, world, utts):
+    """-> this rank's list of batches, each a list of utterance lengths (samples), longest first.
+    c3: ONE global set of utts*world utterances, batched globally with the reference's rule and dealt
+    round-robin to the ranks (generate.py:145-160 / ShardedIterator): per-GPU work stays ~constant as the
+    number of GPUs grows (weak scaling) and the batch -> rank map is deterministic."""
     if name == "c3":
-        rng = np.random.RandomState(2024 + rank)
-        lens = rng.randint(32000, 480000 + 1, size=utts).astype(np.int64)
-        order = batching.ordered_indices(lens)
-        return [[int(lens[i]) for i in b] for b in batching.batch_by_size(order, lens, 2000000, 0, 8)]
+        rng = np.random.RandomState(2024)
+        lens = rng.randint(32000, 480000 + 1, size=utts * world).astype(np.int64)
+        mine, _ = D.shard_utterances(lens, world, rank, 2000000, 8)
+        return [[int(lens[i]) for i in b] for b in mine]
     if name == "c1":
         return [[80000] * 4]
     if name == "c2":
@@ -199,15 +203,13 @@ def main():
     ap.add_argument("--profile-json", default="")
     args = ap.parse_args()
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    rank, world, local_rank = D.env_rank_world()
     cores = os.cpu_count() or 1
     M = 16
-    batches = make_workload(args.workload, rank, args.utts)
+    batches = make_workload(args.workload, rank, world, args.utts)
     audio_per_step = sum(sum(b) for b in batches) / SR
     cfg = {"workload": "%s: Chimera-16 encoder+memory, %s" % (args.workload, {
-        "c3": "%d utts/GPU U{2..30}s, length-bucketed max_tokens=2e6 bsz%%8 (%d batches)" % (args.utts, len(batches)),
+        "c3": "%d utts/GPU U{2..30}s (global set x%d ranks, round-robin sharded), length-bucketed max_tokens=2e6 bsz%%8 (%d batches on rank 0)" % (args.utts, world, len(batches)),
         "c1": "B=4 x 5 s", "c2": "B=32 x 15 s", "c4": "B=64 x 20 s"}[args.workload]),
         "interlingua_length": M, "batches_per_step": len(batches), "audio_sec_per_step_per_gpu": round(audio_per_step, 2),
         "parallelism": "utterance-sharded dp%d, no data-path collective" % world,
@@ -232,9 +234,7 @@ def main():
     # ------------------------------------------------------------------ B200 arm
     assert torch.cuda.is_available(), "bench.py --impl b200 needs a CUDA device (there is no CPU fallback)"
     torch.cuda.set_device(local_rank)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    D.init("nccl")
     from chimera_st_b200.encoder import build_encoder_from_state_dict
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     sd = synth.make_state_dict(seed=0, interlingua_length=M)
@@ -247,16 +247,12 @@ def main():
     torch.cuda.synchronize()
 
     def barrier():
-        if world > 1:
-            dist.barrier()
+        torch.cuda.synchronize()
+        D.barrier()
         torch.cuda.synchronize()
 
     def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return D.reduce_max(x, "cuda")
 
     def step_resident():
         n = 0
@@ -301,11 +297,7 @@ def main():
     t_e2e = max_over_ranks(max(e0.elapsed_time(e1) * 1e-3, 0.0))
     t_e2e_wall = time.perf_counter() - t0
 
-    total_audio = audio_per_step
-    if world > 1:
-        t = torch.tensor([audio_per_step], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t)
-        total_audio = float(t.item())
+    total_audio = D.reduce_sum(audio_per_step, "cuda")
 
     # ---- instrumented pass: per-kernel CUDA-event timing (non-graph) for the roofline object
     prof = LaunchProfiler()
@@ -318,8 +310,7 @@ def main():
     ksum = prof.summary()
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        D.finalize()
         return
 
     peaks = {}
@@ -364,8 +355,7 @@ def main():
             "gpu_launches": launches, "cuda_graph": not args.no_graph, "clocks": clocks,
             "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    D.finalize()
 
 
 if __name__ == "__main__":

@@ -58,7 +58,7 @@ class B200InterlinguaEncoder(nn.Module):
 
     def __init__(self, interlingua_length=16, dtype=torch.float32, use_graph=True, dead_heads=True,
                  text_vocab=0, encoder_out_dtype=None):
-        super().__init__()
+        nn.Module.__init__(self)          # explicit: the fairseq plugin mixes this class with FairseqEncoder
         if dtype not in (torch.float32, torch.bfloat16):
             raise ValueError("compute dtype must be float32 or bfloat16")
         self.interlingua_length = interlingua_length

@@ -1,0 +1,79 @@
+"""fairseq `--user-dir` plugin: drops the B200 encoder under the reference's unmodified CLIs.
+
+    fairseq-generate <data> --user-dir /path/to/repo/chimera-st_b200/fairseq_plugin --path ckpt.pt ...
+    fairseq-interactive ...   (same flag)
+
+`fairseq.utils.import_user_module` (fairseq/utils.py:431-459) imports this package before the model is
+built (generate.py:75, interactive.py:115, train.py:55).  A checkpoint stores
+`args.arch = "s2t_transformer_w2v2_interlingua_base"`; we rebind the registries
+(fairseq/models/__init__.py:31-165) so that arch resolves to a model class whose `build_encoder`
+(w2v2_transformer_interlingua.py:125-130) returns `B200InterlinguaEncoder` -- same parameter names, so
+`model.load_state_dict(checkpoint["model"])` works unchanged; the decoder / generator stay the reference's.
+
+Compute dtype: `--fp16` / `--bf16` / `--memory-efficient-*` select the bf16 tensor-core path, otherwise
+fp32; override with CHIMERA_B200_DTYPE=fp32|bf16.  Requires a CUDA device (there is no CPU fallback).
+"""
+import os
+import sys
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_REPO = os.path.dirname(os.path.dirname(_HERE))
+if _REPO not in sys.path:
+    sys.path.insert(0, _REPO)
+
+import chimera_st_b200  # noqa: E402,F401
+from chimera_st_b200.encoder import B200InterlinguaEncoder  # noqa: E402
+
+from fairseq.models import MODEL_REGISTRY, ARCH_MODEL_REGISTRY, FairseqEncoder  # noqa: E402
+from fairseq.models.chimera.w2v2_transformer_interlingua import S2TTransformerInterlinguaModelW2V2  # noqa: E402
+
+
+def _compute_dtype(args):
+    env = os.environ.get("CHIMERA_B200_DTYPE", "")
+    if env:
+        return {"fp32": torch.float32, "bf16": torch.bfloat16}[env]
+    half = any(getattr(args, k, False) for k in ("fp16", "bf16", "memory_efficient_fp16", "memory_efficient_bf16"))
+    return torch.bfloat16 if half else torch.float32
+
+
+class B200FairseqEncoder(B200InterlinguaEncoder, FairseqEncoder):
+    """B200InterlinguaEncoder with the FairseqEncoder mix-in (forward_torchscript, set_num_updates, ...)."""
+
+    def __init__(self, args, src_dict=None, embed_tokens=None):
+        if getattr(args, "non_shared_encoder_layers", 0) or getattr(args, "interlingua_debug_options", []):
+            raise NotImplementedError("non_shared_encoder_layers / interlingua_debug_options are not supported by the B200 path")
+        vocab = embed_tokens.num_embeddings if embed_tokens is not None else 0
+        B200InterlinguaEncoder.__init__(self, interlingua_length=args.interlingua_length, dtype=_compute_dtype(args),
+                                        use_graph=True, dead_heads=True, text_vocab=vocab)
+        self.dictionary = src_dict
+        self.no_interlingua = getattr(args, "no_interlingua", False)
+
+    # fairseq's model.half()/bfloat16() (generate.py:131-138) must not down-cast the fp32 master parameters:
+    # the kernels pick their own operand precision (weights.prepare).  Device moves still apply.
+    def _apply(self, fn, recurse=True):
+        return super()._apply(lambda t: fn(t).to(t.dtype) if t.is_floating_point() else fn(t), recurse)
+
+
+class B200S2TInterlinguaModel(S2TTransformerInterlinguaModelW2V2):
+    @classmethod
+    def build_encoder(cls, args, src_dict=None, encoder_embed_tokens=None):
+        return B200FairseqEncoder(args, src_dict, encoder_embed_tokens)
+
+
+def register():
+    """Rebind every registry entry of the reference interlingua model to the B200-backed class."""
+    n = 0
+    for name, klass in list(MODEL_REGISTRY.items()):
+        if klass is S2TTransformerInterlinguaModelW2V2:
+            MODEL_REGISTRY[name] = B200S2TInterlinguaModel
+            n += 1
+    for arch, klass in list(ARCH_MODEL_REGISTRY.items()):
+        if klass is S2TTransformerInterlinguaModelW2V2:
+            ARCH_MODEL_REGISTRY[arch] = B200S2TInterlinguaModel
+            n += 1
+    return n
+
+
+register()

@@ -1,0 +1,57 @@
+"""The --user-dir drop-in, exercised against the UNMODIFIED reference in the dev container (needs
+/root/reference; skipped on the GPU box).  No forward pass here (no GPU): registry rebinding, model
+construction through the reference's own build_model, and a strict state-dict exchange with a reference
+model (encoder AND decoder keys)."""
+import argparse
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree not mounted")
+
+SCRIPT = r'''
+import sys, argparse, torch
+sys.path.insert(0, %(root)r)
+from oracle import make_overlay
+make_overlay.build(); make_overlay.activate()
+import fairseq.models
+from fairseq import utils
+from fairseq.models import ARCH_MODEL_REGISTRY
+from fairseq.data import Dictionary
+ref_cls = ARCH_MODEL_REGISTRY["s2t_transformer_w2v2_interlingua_base"]
+utils.import_user_module(argparse.Namespace(user_dir=%(plugin)r))
+new_cls = ARCH_MODEL_REGISTRY["s2t_transformer_w2v2_interlingua_base"]
+assert new_cls is not ref_cls and issubclass(new_cls, ref_cls), (new_cls, ref_cls)
+d = Dictionary.load("/root/reference/chimera/resources/wmt14-en-de-spm/spm_unigram10000_wave_joint.txt")
+class Task: source_dictionary = None; target_dictionary = d
+args = argparse.Namespace(w2v2_model_path="unused", encoder_layers=6, encoder_embed_dim=512, interlingua_length=16,
+    interlingua_layers=3, interlingua_debug_options=[], dropout=0.1, share_decoder_input_output_embed=True,
+    max_source_positions=6000, max_target_positions=1024)
+model = new_cls.build_model(args, Task())
+enc = model.encoder
+import chimera_st_b200
+from chimera_st_b200.encoder import B200InterlinguaEncoder
+from chimera_st_b200 import synth
+from fairseq.models import FairseqEncoder
+assert isinstance(enc, B200InterlinguaEncoder) and isinstance(enc, FairseqEncoder)
+sd = synth.make_state_dict(seed=0, interlingua_length=16)
+full = {"encoder." + k: v for k, v in sd.items()}
+full.update({k: v for k, v in model.state_dict().items() if k.startswith("decoder.")})
+model.load_state_dict(full, strict=True)                      # fairseq_model.py:94-112 path (upgrade_state_dict runs)
+assert torch.equal(model.encoder.interlingua_embedding.weight, sd["interlingua_embedding.weight"])
+assert model.encoder.max_positions() is None
+model.half()                                                  # generate.py:131-138: must not break the fp32 masters
+assert model.encoder.layer_norm.weight.dtype == torch.float32
+print("PLUGIN_OK", type(enc).__name__, len(full))
+'''
+
+
+def test_user_dir_plugin_rebinds_arch_and_loads_reference_state_dict():
+    code = SCRIPT % {"root": ROOT, "plugin": os.path.join(ROOT, "chimera-st_b200", "fairseq_plugin")}
+    env = dict(os.environ, PYTHONDONTWRITEBYTECODE="1")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env)
+    assert "PLUGIN_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
