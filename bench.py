@@ -199,6 +199,7 @@ def main():
     ap.add_argument("--workload", default="c3", choices=["c3", "c1", "c2", "c4"])
     ap.add_argument("--utts", type=int, default=512)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--lanes", type=int, default=3, help="concurrent CUDA-stream lanes for independent batches")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-json", default="")
     args = ap.parse_args()
@@ -254,18 +255,28 @@ def main():
     def max_over_ranks(x):
         return D.reduce_max(x, "cuda")
 
+    lanes = max(1, args.lanes)
+
     def step_resident():
-        n = 0
-        for (w, l) in dev:
-            plan = enc._plan(*w.shape)
-            plan.load_inputs(w, l)
-            n += plan.run()
-        return n
+        if lanes == 1:
+            n = 0
+            for (w, l) in dev:
+                plan = enc._plan(*w.shape)
+                plan.load_inputs(w, l)
+                n += plan.run()
+            return n
+        enc.forward_many(dev, n_lanes=lanes)
+        return enc.last_launches
 
     def step_e2e():
-        for (w, l), oh in zip(host, out_host):
-            out = enc(w.cuda(non_blocking=True), l.cuda(non_blocking=True))
-            oh.copy_(out.encoder_out, non_blocking=True)
+        # public API with HOST buffers: pinned waveforms -> H2D -> encoder -> D2H of the memories
+        if lanes == 1:
+            for (w, l), oh in zip(host, out_host):
+                out = enc(w.cuda(non_blocking=True), l.cuda(non_blocking=True))
+                oh.copy_(out.encoder_out, non_blocking=True)
+        else:
+            enc.forward_many([(w.cuda(non_blocking=True), l.cuda(non_blocking=True)) for w, l in host],
+                             n_lanes=lanes, out=out_host)
         torch.cuda.synchronize()
 
     for _ in range(max(3, args.warmup)):
@@ -352,7 +363,7 @@ def main():
             "dtype": "bf16" if dtype == torch.bfloat16 else "f32", "data": "synthetic", "config": cfg,
             "e2e": {"value": round(total_audio * args.steps / t_e2e, 1), "unit": "audio-s/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "wall_s": round(t_e2e_wall, 3)},
-            "gpu_launches": launches, "cuda_graph": not args.no_graph, "clocks": clocks,
+            "gpu_launches": launches, "cuda_graph": not args.no_graph, "stream_lanes": lanes, "clocks": clocks,
             "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(line))
     D.finalize()

@@ -21,6 +21,8 @@ __global__ void __launch_bounds__(256) attention_kernel(const T* __restrict__ q,
   float* Qt = sm;                         // [d][i], pitch AT_LD
   float* Kt = sm + AT_D * AT_LD;          // [d][j]; reused as Pt [j][i]
   float* Vs = sm + 2 * AT_D * AT_LD;      // [j][d], pitch 64
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * AT_BQ;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   int klen = kv_len ? kv_len[b] : n_kv;
@@ -157,12 +159,12 @@ extern "C" int cst_attention(const void* q, const void* k, const void* v, void* 
   static bool attr[2] = {false, false};
   if (dtype == CST_F32) {
     if (!attr[0]) { CST_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM)); attr[0] = true; }
-    attention_kernel<float><<<grid, 256, AT_SMEM, st>>>((const float*)q, (const float*)k, (const float*)v, (float*)out,
-                                                         ldq, ldkv, ldo, n_q, q_rows_per_seg, n_kv, kv_rows_per_seg, kv_len);
+    CST_CHECK_CUDA(launch_k(attention_kernel<float>, grid, dim3(256), AT_SMEM, st, (const float*)q, (const float*)k, (const float*)v, (float*)out,
+                            ldq, ldkv, ldo, n_q, q_rows_per_seg, n_kv, kv_rows_per_seg, kv_len));
   } else if (dtype == CST_BF16) {
     if (!attr[1]) { CST_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM)); attr[1] = true; }
-    attention_kernel<__nv_bfloat16><<<grid, 256, AT_SMEM, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v,
-                                                                 (__nv_bfloat16*)out, ldq, ldkv, ldo, n_q, q_rows_per_seg, n_kv, kv_rows_per_seg, kv_len);
+    CST_CHECK_CUDA(launch_k(attention_kernel<__nv_bfloat16>, grid, dim3(256), AT_SMEM, st, (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v,
+                            (__nv_bfloat16*)out, ldq, ldkv, ldo, n_q, q_rows_per_seg, n_kv, kv_rows_per_seg, kv_len));
   } else {
     CST_REQUIRE(false, "cst_attention: bad dtype %d", dtype);
   }

@@ -45,9 +45,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * FA_BQ;
-  int klen = kv_len ? kv_len[b] : n_kv;
-  klen = klen < n_kv ? klen : n_kv;
-  const int n_tiles = (klen + FA_BK - 1) / FA_BK;
+  pdl_launch_dependents();
 
   if (warp == 0 && lane == 0) {
     if ((base & 1023u) != 0) { printf("cst attention_tc: shared memory base not 1024-byte aligned\n"); __trap(); }
@@ -67,6 +65,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   const uint32_t tS = tmem_base, tPV = tmem_base + FA_BK;       // S at cols 0..127, PV at 128..191
+  pdl_wait();                                                   // prologue above overlaps the previous kernel
+  int klen = kv_len ? kv_len[b] : n_kv;
+  klen = klen < n_kv ? klen : n_kv;
+  const int n_tiles = (klen + FA_BK - 1) / FA_BK;
 
   if (warp == 0) {
     if (lane == 0 && n_tiles > 0) {
@@ -248,9 +250,8 @@ int launch_attention_tc(const void* q, const void* k, const void* v, void* out, 
   rc = make_map_2d(&tmV, v, H * FA_D, (long long)B * kv_rows_per_seg, ldkv, FA_D, FA_BK);
   if (rc) return rc;
   dim3 grid(cdiv(n_q, FA_BQ), H, B);
-  attention_tc_kernel<<<grid, FA_THREADS, FA_SMEM, st>>>(tmQ, tmK, tmV, (__nv_bfloat16*)out, ldo, n_q, q_rows_per_seg,
-                                                       n_kv, kv_rows_per_seg, kv_len);
-  CST_LAUNCH_CHECK();
+  CST_CHECK_CUDA(launch_k(attention_tc_kernel, grid, dim3(FA_THREADS), FA_SMEM, st, tmQ, tmK, tmV, (__nv_bfloat16*)out, ldo, n_q,
+                          q_rows_per_seg, n_kv, kv_rows_per_seg, kv_len));
   return CST_OK;
 }
 

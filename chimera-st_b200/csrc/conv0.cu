@@ -16,6 +16,8 @@ constexpr int STAT_STRIDE = 72;
 
 __global__ void __launch_bounds__(256) conv0_stats_kernel(const float* __restrict__ wave, int L, int T0,
                                                           int frames_per_block, double* __restrict__ ws) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.y;
   const float* x = wave + (size_t)b * L;
   const int t_begin = blockIdx.x * frames_per_block;
@@ -54,6 +56,8 @@ __global__ void __launch_bounds__(256) conv0_stats_kernel(const float* __restric
 __global__ void __launch_bounds__(C0) conv0_finalize_kernel(const double* __restrict__ ws, const float* __restrict__ w,
                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
                                                              int T0, float2* __restrict__ scale_shift) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x, c = threadIdx.x;
   __shared__ double st[NSTAT];
   if (c < NSTAT) st[c] = ws[(size_t)b * STAT_STRIDE + c];
@@ -84,6 +88,8 @@ template <typename OutT, int FT>
 __global__ void __launch_bounds__(256) conv0_apply_kernel(const float* __restrict__ wave, int L, int T0, int rows_per_seg,
                                                           const float* __restrict__ w, const float2* __restrict__ scale_shift,
                                                           OutT* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * FT;
   __shared__ float xs[FT * S0 + K0];
@@ -143,10 +149,8 @@ extern "C" int cst_conv0_stats(const float* wave, int B, int L, const float* w, 
   CST_CHECK_CUDA(cudaMemsetAsync(stats_ws, 0, sizeof(double) * STAT_STRIDE * B, st));
   const int fpb = 2048;                    // 8 frames per thread: short fp32 chains, then fp64
   dim3 grid(cdiv(T0, fpb), B);
-  conv0_stats_kernel<<<grid, 256, 0, st>>>(wave, L, T0, fpb, stats_ws);
-  CST_LAUNCH_CHECK();
-  conv0_finalize_kernel<<<B, C0, 0, st>>>(stats_ws, w, gamma, beta, T0, reinterpret_cast<float2*>(scale_shift));
-  CST_LAUNCH_CHECK();
+  CST_CHECK_CUDA(launch_k(conv0_stats_kernel, grid, dim3(256), 0, st, wave, L, T0, fpb, stats_ws));
+  CST_CHECK_CUDA(launch_k(conv0_finalize_kernel, dim3(B), dim3(C0), 0, st, (const double*)stats_ws, w, gamma, beta, T0, reinterpret_cast<float2*>(scale_shift)));
   return CST_OK;
 }
 
@@ -156,14 +160,14 @@ extern "C" int cst_conv0_apply(const float* wave, int B, int L, const float* w, 
   const int T0 = (L - K0) / S0 + 1;
   CST_REQUIRE(wave && w && scale_shift && out && B > 0 && L >= K0 && rows_per_seg >= T0,
               "cst_conv0_apply: bad args B=%d L=%d rows_per_seg=%d (T0=%d)", B, L, rows_per_seg, T0);
-  constexpr int FT = 64;
+  constexpr int FT = 256;                  // frames per block: amortises the per-thread weight fetch (80 + 16 registers)
   dim3 grid(cdiv(rows_per_seg, FT), B);
   cudaStream_t st = (cudaStream_t)stream;
   const float2* ss = reinterpret_cast<const float2*>(scale_shift);
   if (out_dtype == CST_BF16)
-    conv0_apply_kernel<__nv_bfloat16, FT><<<grid, 256, 0, st>>>(wave, L, T0, rows_per_seg, w, ss, (__nv_bfloat16*)out);
+    CST_CHECK_CUDA(launch_k(conv0_apply_kernel<__nv_bfloat16, FT>, grid, dim3(256), 0, st, wave, L, T0, rows_per_seg, w, ss, (__nv_bfloat16*)out));
   else if (out_dtype == CST_F32)
-    conv0_apply_kernel<float, FT><<<grid, 256, 0, st>>>(wave, L, T0, rows_per_seg, w, ss, (float*)out);
+    CST_CHECK_CUDA(launch_k(conv0_apply_kernel<float, FT>, grid, dim3(256), 0, st, wave, L, T0, rows_per_seg, w, ss, (float*)out));
   else
     CST_REQUIRE(false, "cst_conv0_apply: bad out_dtype %d", out_dtype);
   CST_LAUNCH_CHECK();

@@ -12,6 +12,8 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmDev p) {
   constexpr int B_LD = (BN * BK / 4) / 256;            // float4 loads per thread for the W tile (2 or 1)
   __shared__ float As[2][BK][BM + 4];
   __shared__ float Bs[2][BK][BN + 4];
+  pdl_launch_dependents();
+  pdl_wait();
 
   const int z = blockIdx.z, zo = z / p.nb_inner, zi = z - zo * p.nb_inner;
   const float* A = (const float*)p.A + zo * p.a_bs_outer + zi * p.a_bs_inner;
@@ -98,12 +100,11 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmDev p) {
 int launch_gemm_f32(const GemmDev& p, int nz, cudaStream_t st) {
   if (p.N <= 64) {
     dim3 grid(cdiv(p.M, 128), cdiv(p.N, 64), nz);
-    gemm_f32_kernel<64><<<grid, 256, 0, st>>>(p);
+    CST_CHECK_CUDA(launch_k(gemm_f32_kernel<64>, grid, dim3(256), 0, st, p));
   } else {
     dim3 grid(cdiv(p.M, 128), cdiv(p.N, 128), nz);
-    gemm_f32_kernel<128><<<grid, 256, 0, st>>>(p);
+    CST_CHECK_CUDA(launch_k(gemm_f32_kernel<128>, grid, dim3(256), 0, st, p));
   }
-  CST_LAUNCH_CHECK();
   return CST_OK;
 }
 

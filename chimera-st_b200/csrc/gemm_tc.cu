@@ -51,6 +51,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = p.K / TC_BK;
+  pdl_launch_dependents();            // the next kernel may start its prologue; it still waits for our completion
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
@@ -66,6 +67,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();                         // everything above overlapped the previous kernel; global memory from here on
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -256,8 +258,7 @@ static int launch_tc_act(const cst_gemm_params& hp, const GemmDev& p, int nz, cu
   CST_CHECK_CUDA(cudaGetDevice(&dev));
   CST_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = (int)(total < sms ? total : sms);
-  gemm_tc_kernel<BN, ACT><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p, m_tiles, n_tiles, (int)total, a_wrap);
-  CST_LAUNCH_CHECK();
+  CST_CHECK_CUDA(launch_k(gemm_tc_kernel<BN, ACT>, dim3(grid), dim3(TC_THREADS), Cfg::SMEM_BYTES, st, tmA, tmB, p, m_tiles, n_tiles, (int)total, a_wrap));
   return CST_OK;
 }
 

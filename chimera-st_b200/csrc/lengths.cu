@@ -7,6 +7,8 @@ namespace cst {
 __global__ void frame_lengths_kernel(const int64_t* __restrict__ src_len, int L, int n_frames,
                                      int32_t* w2v_valid, int32_t* sub_valid, int64_t* w2v_len64,
                                      uint8_t* frame_mask) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x;
   const long long len = src_len[b];
   const int r = L / n_frames;                    // samples per frame after trimming L % T'
@@ -29,8 +31,7 @@ extern "C" int cst_frame_lengths(const int64_t* src_len, int B, int L, int n_fra
                                  uint8_t* frame_mask, void* stream) {
   CST_REQUIRE(src_len && B > 0 && L > 0 && n_frames > 0 && n_frames <= L,
               "cst_frame_lengths: bad args B=%d L=%d n_frames=%d", B, L, n_frames);
-  cst::frame_lengths_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(src_len, L, n_frames, w2v_valid,
-                                                                sub_valid, w2v_len64, frame_mask);
-  CST_LAUNCH_CHECK();
+  CST_CHECK_CUDA(cst::launch_k(cst::frame_lengths_kernel, dim3(B), dim3(128), 0, (cudaStream_t)stream, src_len, L, n_frames, w2v_valid,
+                               sub_valid, w2v_len64, frame_mask));
   return CST_OK;
 }

@@ -10,6 +10,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         float* __restrict__ out_f32, LpT* __restrict__ out_lp, long long ldo,
                                                         int rows, int rows_per_seg, int seg_rows_valid,
                                                         long long out_rows_per_seg, int out_row_off, int zero_invalid) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int C = NV * 128;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -58,6 +60,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 template <typename OutT>
 __global__ void posconv_pack_kernel(const float* __restrict__ x, int rows_per_seg, int n_frames,
                                     OutT* __restrict__ xg, int t_pad_rows, long long total_chunks) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one 8-lane chunk
   if (idx >= total_chunks) return;
   const int ch = (int)(idx & 7);
@@ -76,6 +80,8 @@ __global__ void posconv_pack_kernel(const float* __restrict__ x, int rows_per_se
 }
 
 __global__ void broadcast_rows_kernel(const float4* __restrict__ src, long long n4, float4* __restrict__ dst, int B) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   const float4 v = src[i];
@@ -95,12 +101,11 @@ extern "C" int cst_layernorm(const float* x, long long ldx, const float* gamma, 
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid(cdiv(rows, 8));
 #define CST_LN(NV, T)                                                                                   \
-  layernorm_kernel<NV, T><<<grid, 256, 0, st>>>(x, ldx, gamma, beta, out_f32, (T*)out_lp, ldo, rows,     \
-                                                rows_per_seg, seg_rows_valid, out_rows_per_seg, out_row_off, zero_invalid)
+  CST_CHECK_CUDA(launch_k(layernorm_kernel<NV, T>, grid, dim3(256), 0, st, x, ldx, gamma, beta, out_f32, (T*)out_lp, ldo, rows, \
+                          rows_per_seg, seg_rows_valid, out_rows_per_seg, out_row_off, zero_invalid))
   if (out_lp && lp_dtype == CST_BF16) { if (C == 512) CST_LN(4, __nv_bfloat16); else CST_LN(6, __nv_bfloat16); }
   else { if (C == 512) CST_LN(4, float); else CST_LN(6, float); }
 #undef CST_LN
-  CST_LAUNCH_CHECK();
   return CST_OK;
 }
 
@@ -112,10 +117,9 @@ extern "C" int cst_posconv_pack(const float* x, int B, int rows_per_seg, int n_f
   const long long chunks = (long long)B * 16 * t_pad_rows * 8;
   cudaStream_t st = (cudaStream_t)stream;
   if (xg_dtype == CST_BF16)
-    posconv_pack_kernel<__nv_bfloat16><<<cdiv(chunks, 256), 256, 0, st>>>(x, rows_per_seg, n_frames, (__nv_bfloat16*)xg, t_pad_rows, chunks);
+    CST_CHECK_CUDA(launch_k(posconv_pack_kernel<__nv_bfloat16>, dim3(cdiv(chunks, 256)), dim3(256), 0, st, x, rows_per_seg, n_frames, (__nv_bfloat16*)xg, t_pad_rows, chunks));
   else
-    posconv_pack_kernel<float><<<cdiv(chunks, 256), 256, 0, st>>>(x, rows_per_seg, n_frames, (float*)xg, t_pad_rows, chunks);
-  CST_LAUNCH_CHECK();
+    CST_CHECK_CUDA(launch_k(posconv_pack_kernel<float>, dim3(cdiv(chunks, 256)), dim3(256), 0, st, x, rows_per_seg, n_frames, (float*)xg, t_pad_rows, chunks));
   return CST_OK;
 }
 
@@ -123,7 +127,6 @@ extern "C" int cst_broadcast_rows(const float* src, int rows, int C, int B, floa
   using namespace cst;
   CST_REQUIRE(src && dst && rows > 0 && C % 4 == 0 && B > 0, "cst_broadcast_rows: bad args");
   const long long n4 = (long long)rows * C / 4;
-  broadcast_rows_kernel<<<cdiv(n4, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)src, n4, (float4*)dst, B);
-  CST_LAUNCH_CHECK();
+  CST_CHECK_CUDA(launch_k(broadcast_rows_kernel, dim3(cdiv(n4, 256)), dim3(256), 0, (cudaStream_t)stream, (const float4*)src, n4, (float4*)dst, B));
   return CST_OK;
 }

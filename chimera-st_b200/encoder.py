@@ -71,6 +71,7 @@ class B200InterlinguaEncoder(nn.Module):
         self._prepared = None
         self._plans = OrderedDict()
         self._arena = None
+        self._lanes = None          # extra (stream, arena, plans) lanes for forward_many
         self.last_launches = 0
         self.register_load_state_dict_post_hook(lambda m, k: m.invalidate())
 
@@ -96,6 +97,7 @@ class B200InterlinguaEncoder(nn.Module):
         self._prepared = None
         self._plans.clear()
         self._arena = None
+        self._lanes = None
 
     # ---- plumbing ------------------------------------------------------------------------------------
     def _device(self):
@@ -104,26 +106,68 @@ class B200InterlinguaEncoder(nn.Module):
             raise RuntimeError("B200InterlinguaEncoder runs only on a CUDA device (no CPU fallback); call .cuda()")
         return dev
 
-    def _plan(self, B, L):
+    def _plan(self, B, L, lane=None):
         dev = self._device()
         if self._prepared is None:
             self._prepared = _weights.prepare(self.state_dict(), dev, self.compute_dtype)
-        key = (B, L)
-        plan = self._plans.get(key)
-        if plan is None:
-            while len(self._plans) >= self.MAX_PLANS:
-                self._plans.popitem(last=False)
+        if lane is None:
             if self._arena is None:
                 self._arena = Arena(dev)
-            gen = self._arena.generation
-            plan = EncoderPlan(self._prepared, B, L, self.interlingua_length, self.compute_dtype, dev, self.use_graph,
-                               arena=self._arena)
-            if self._arena.generation != gen:          # arena grew: older plans (and their graphs) point at freed memory
-                self._plans.clear()
-            self._plans[key] = plan
+            plans, arena = self._plans, self._arena
         else:
-            self._plans.move_to_end(key)
+            plans, arena = lane["plans"], lane["arena"]
+        key = (B, L)
+        plan = plans.get(key)
+        if plan is None:
+            while len(plans) >= self.MAX_PLANS:
+                plans.popitem(last=False)
+            gen = arena.generation
+            plan = EncoderPlan(self._prepared, B, L, self.interlingua_length, self.compute_dtype, dev, self.use_graph,
+                               arena=arena)
+            if arena.generation != gen:                # arena grew: older plans (and their graphs) point at freed memory
+                plans.clear()
+            plans[key] = plan
+        else:
+            plans.move_to_end(key)
         return plan
+
+    def _get_lanes(self, n):
+        dev = self._device()
+        if self._lanes is None or len(self._lanes) != n:
+            self._lanes = [{"stream": torch.cuda.Stream(device=dev), "arena": Arena(dev), "plans": OrderedDict()}
+                           for _ in range(n)]
+        return self._lanes
+
+    @torch.no_grad()
+    def forward_many(self, batches, n_lanes=3, out=None):
+        """Throughput API: encode a list of independent padded batches [(src_tokens, src_lengths), ...].
+        Batches are issued round-robin on `n_lanes` CUDA streams, each lane with its own activation arena and
+        CUDA graphs, so the short kernels of one small batch (2e6-sample token budget ~ 6000 frames) overlap the
+        tails / prologues of another's instead of leaving SMs idle.  Results are identical to calling forward()
+        per batch (batches never interact).  Returns a list of EncoderOut; `out` (optional list of preallocated
+        [M,B,512] tensors, e.g. pinned host buffers) receives the memories with non_blocking copies."""
+        lanes = self._get_lanes(n_lanes)
+        cur = torch.cuda.current_stream()
+        for ln in lanes:
+            ln["stream"].wait_stream(cur)
+        results = []
+        self.last_launches = 0
+        for i, (src_tokens, src_lengths) in enumerate(batches):
+            self._check_inputs(src_tokens, src_lengths)
+            ln = lanes[i % n_lanes]
+            with torch.cuda.stream(ln["stream"]):
+                B, L = src_tokens.shape
+                plan = self._plan(B, L, ln)
+                plan.load_inputs(src_tokens if src_tokens.dtype == torch.float32 else src_tokens.float(), src_lengths)
+                self.last_launches += plan.run()
+                o = plan.memories().to(self.encoder_out_dtype or src_tokens.dtype).clone(memory_format=torch.contiguous_format)
+                if out is not None:
+                    out[i].copy_(o, non_blocking=True)
+                pad = torch.zeros(B, o.shape[0], dtype=torch.bool, device=o.device)
+                results.append(EncoderOut(o, pad, None, None, None, None))
+        for ln in lanes:
+            cur.wait_stream(ln["stream"])
+        return results
 
     def _check_inputs(self, src_tokens, src_lengths):
         if not src_tokens.dtype.is_floating_point:
@@ -153,7 +197,8 @@ class B200InterlinguaEncoder(nn.Module):
             out = plan.view("h_enc").transpose(0, 1)
         else:
             out = plan.memories()
-        out = out.to(self.encoder_out_dtype or src_tokens.dtype).contiguous()
+        # always a fresh tensor: for B == 1 `.contiguous()` would return a view of the plan's arena
+        out = out.to(self.encoder_out_dtype or src_tokens.dtype).clone(memory_format=torch.contiguous_format)
         pad = torch.zeros(B, out.shape[0], dtype=torch.bool, device=out.device)
         return EncoderOut(out, pad, None, None, None, None)
 

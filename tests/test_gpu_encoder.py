@@ -120,3 +120,32 @@ def test_reorder_and_no_interlingua():
     finally:
         enc.no_interlingua = False
     assert rel_l2(h.cpu(), torch.from_numpy(g["h_enc"]).transpose(0, 1)) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_forward_many_on_stream_lanes_equals_forward(dtype):
+    """Independent batches on concurrent CUDA-stream lanes: bit-identical to one-at-a-time forward()."""
+    enc = encoder(16, dtype, use_graph=True)
+    shapes = [[16000, 12345, 8000], [9000, 7000], [24000], [16000, 3000, 9999], [9000, 8999], [12000, 11000, 10000, 500]]
+    batches = []
+    for i, lens in enumerate(shapes * 2):
+        w, l = synth.make_waveforms(lens, seed=100 + i)
+        batches.append((w.cuda(), l.cuda()))
+    ref = [enc(w, l).encoder_out.clone() for w, l in batches]
+    for lanes in (2, 3):
+        got = enc.forward_many(batches, n_lanes=lanes)
+        torch.cuda.synchronize()
+        for a, b in zip(ref, got):
+            assert torch.equal(a, b.encoder_out)
+            assert b.encoder_padding_mask.shape == (a.shape[1], 16)
+
+
+def test_single_utterance_output_does_not_alias_the_arena():
+    """B == 1: [1,M,512].transpose(0,1) is 'contiguous' to torch, so the result must be cloned explicitly."""
+    enc = encoder(16, torch.float32, use_graph=True)
+    w, l = synth.make_waveforms([24000], seed=102)
+    a = enc(w.cuda(), l.cuda()).encoder_out
+    keep = a.clone()
+    w2, l2 = synth.make_waveforms([24000], seed=103)
+    enc(w2.cuda(), l2.cuda())
+    assert torch.equal(a, keep)
