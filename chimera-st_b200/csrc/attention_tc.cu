@@ -7,23 +7,30 @@
 //   warp 1      : tcgen05.mma issuer.  S_j = Q K_j^T (M128 N128 K64, both operands K-major) into TMEM cols
 //                 0..127; PV_j = P_j V_j (M128 N64 K128; P from shared memory K-major, V as an MN-major B
 //                 operand straight from the TMA tile -- no transpose) into TMEM cols 128..191.
-//   warps 2..5  : softmax.  thread = query row: tcgen05.ld the S row, exact key mask (keys >= kv_len[b] get
-//                 zero probability), running max / sum in fp32, P = exp2 in bf16 -> shared memory (manual 128B
-//                 swizzle); the output accumulator stays in registers: O = O * alpha_j + PV_j.
+//   warps 2..9  : softmax.  Two warps per TMEM lane quarter: a query row is shared by a thread pair, each
+//                 owning 64 of the tile's 128 keys and 32 of the 64 output columns (row max exchanged through
+//                 shared memory + a 64-thread named barrier; partial row sums are added at the end).  tcgen05.ld
+//                 the S half-row, exact key mask (keys >= kv_len[b] get zero probability), running max / sum in
+//                 fp32, P = exp2 in bf16 -> shared memory (manual 128B swizzle); the output accumulator stays
+//                 in registers: O = O * alpha_j + PV_j.
 // Every query row of the tile is computed (padded query rows are live in the reference).  V rows of masked
 // keys must be finite (the plan guarantees it: no activation row is ever left unwritten).
+#include <cuda_fp16.h>
 #include "tc_common.cuh"
 
 namespace cst {
 
 constexpr int FA_BQ = 128, FA_BK = 128, FA_D = 64, FA_KS = 2;
-constexpr int FA_THREADS = 192;
+constexpr int FA_SM_WARPS = 8;
+constexpr int FA_THREADS = 64 + 32 * FA_SM_WARPS;
 constexpr int FA_Q_BYTES = FA_BQ * FA_D * 2;            // 16 KB
 constexpr int FA_KV_BYTES = FA_BK * FA_D * 2;           // 16 KB each for K and V
 constexpr int FA_P_BYTES = FA_BQ * FA_BK * 2;           // 32 KB (two 64-key halves of 16 KB)
-constexpr int FA_SMEM = FA_Q_BYTES + 2 * FA_KS * FA_KV_BYTES + FA_P_BYTES + 256;   // 112.25 KB: two CTAs per SM
+constexpr int FA_SMEM = FA_Q_BYTES + 2 * FA_KS * FA_KV_BYTES + FA_P_BYTES + 128 + 512;   // 112.6 KB: two CTAs per SM (limit 113 KB)
 constexpr int FA_TMEM_COLS = 256;
 constexpr float FA_LOG2E = 1.4426950408889634f;
+struct TrueTag { static constexpr bool value = true; };
+struct FalseTag { static constexpr bool value = false; };
 
 __global__ void __launch_bounds__(FA_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -51,8 +58,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     if ((base & 1023u) != 0) { printf("cst attention_tc: shared memory base not 1024-byte aligned\n"); __trap(); }
     mbar_init(q_full, 1);
     for (int s = 0; s < FA_KS; ++s) { mbar_init(kv_full + 8 * s, 1); mbar_init(kv_empty + 8 * s, 1); }
-    mbar_init(s_full, 1); mbar_init(s_empty, 4);
-    mbar_init(p_full, 4); mbar_init(pv_full, 1); mbar_init(pv_empty, 4);
+    mbar_init(s_full, 1); mbar_init(s_empty, FA_SM_WARPS);
+    mbar_init(p_full, FA_SM_WARPS); mbar_init(pv_full, 1); mbar_init(pv_empty, FA_SM_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -124,84 +131,91 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     __syncwarp();
   } else {
     // ===================== softmax / output warps =====================
-    const int qd = warp & 3;
+    const int qd = warp & 3;                             // TMEM lane quarter (hardware: warp % 4)
+    const int hh = (warp - 2) >> 2;                      // 0: keys 0..63 / out cols 0..31, 1: keys 64..127 / cols 32..63
     const int r = qd * 32 + lane;                        // query row inside the tile == TMEM lane
     const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
-    float o[FA_D];
+    // row-max exchange between the two threads of a row: fp16 slots [2 halves][128 rows] (512 B is all the shared
+    // memory left under the two-CTAs-per-SM budget).  Both threads use max(fp16(own), fp16(partner)) -- any common
+    // reference point near the maximum is a valid softmax shift.  One slot set suffices: a thread cannot reach the
+    // next tile's write before its partner has read (S_{j+1} needs both warps' s_empty arrivals).
+    __half* xch = reinterpret_cast<__half*>(smem_raw + (bars + 128 - base));
+    float* lsum = reinterpret_cast<float*>(smem_raw + (sK - base));         // reused after the last MMA: partial row sums
+    float o[32];
 #pragma unroll
-    for (int i = 0; i < FA_D; ++i) o[i] = 0.f;
+    for (int i = 0; i < 32; ++i) o[i] = 0.f;
     float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
-    const uint32_t srow = tS + lane_off;
-    const uint32_t prow = sP + r * 128;
+    const uint32_t srow = tS + lane_off + hh * 64;
+    const uint32_t prow = sP + hh * (FA_P_BYTES / 2) + r * 128;
+    const uint32_t pvrow = tPV + lane_off + hh * 32;
     auto take_pv = [&](int j) {                          // O = O * alpha_j + PV_j  (PV_j is relative to m_j)
       mbar_wait(pv_full, j & 1);
       tc_fence_after();
+      float pv[32];
+      tmem_ld32(pvrow, pv);
+      tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < FA_D; c += 32) {
-        float pv[32];
-        tmem_ld32(tPV + lane_off + c, pv);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[c + i] = fmaf(o[c + i], alpha_prev, pv[i]);
-      }
+      for (int i = 0; i < 32; ++i) o[i] = fmaf(o[i], alpha_prev, pv[i]);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(pv_empty);
     };
-    for (int j = 0; j < n_tiles; ++j) {
-      mbar_wait(s_full, j & 1);
-      tc_fence_after();
-      const int kbase = j * FA_BK;
-      const bool tail = kbase + FA_BK > klen;
-      // pass 1: row maximum
+    // one key tile; TAIL is a compile-time flag so that full tiles carry no per-element masking instructions
+    auto tile_step = [&](int j, auto tail_tag) {
+      constexpr bool TAIL = decltype(tail_tag)::value;
+      const int nvalid = klen - (j * FA_BK + hh * 64);   // valid keys among this thread's 64 (TAIL only; may be <= 0)
+      // pass 1: maximum of this thread's 64 scores (two 32-column TMEM loads; registers are capped at 96/thread
+      // so that two 320-thread CTAs fit an SM, hence S is re-read in pass 2 instead of kept live)
       float mx = -INFINITY;
 #pragma unroll 1
-      for (int c = 0; c < FA_BK; c += 32) {
+      for (int c = 0; c < 64; c += 32) {
         float s[32];
         tmem_ld32(srow + c, s);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const float v = (tail && kbase + c + i >= klen) ? -INFINITY : s[i];
-          mx = fmaxf(mx, v);
+          if (TAIL) { if (c + i < nvalid) mx = fmaxf(mx, s[i]); }
+          else mx = fmaxf(mx, s[i]);
         }
       }
+      // row maximum across the thread pair
+      const __half mxh = __float2half_rn(mx);
+      xch[hh * 128 + r] = mxh;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
+      mx = fmaxf(__half2float(mxh), __half2float(xch[(hh ^ 1) * 128 + r]));
       const float m_new = fmaxf(m_run, mx);              // finite: every visited tile holds >= 1 valid key
       const float alpha = mufu_ex2((m_run - m_new) * FA_LOG2E);
       const float mb = m_new * FA_LOG2E;
       if (j > 0) take_pv(j - 1);                         // also proves the P buffer is free again
       // pass 2: P = exp2(s*log2e - m*log2e) -> bf16 -> swizzled shared memory (packed FFMA2 + MUFU.EX2)
-      float rs = 0.f;
+      const uint64_t l2e = pk2(FA_LOG2E, FA_LOG2E), nmb = pk2(-mb, -mb);
+      uint64_t rs2 = pk2(0.f, 0.f);
 #pragma unroll 1
-      for (int c = 0; c < FA_BK; c += 32) {
+      for (int c = 0; c < 64; c += 32) {
         float s[32];
         tmem_ld32(srow + c, s);
         tmem_ld_wait();
-        uint32_t pk[16];
-        const uint64_t l2e = pk2(FA_LOG2E, FA_LOG2E), nmb = pk2(-mb, -mb);
-        uint64_t rs2 = pk2(0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float a0, a1;
-          upk2(ffma2(pk2(s[i], s[i + 1]), l2e, nmb), a0, a1);
-          float p0 = mufu_ex2(a0), p1 = mufu_ex2(a1);
-          if (tail) {
-            if (kbase + c + i >= klen) p0 = 0.f;
-            if (kbase + c + i + 1 >= klen) p1 = 0.f;
+        for (int g = 0; g < 32; g += 8) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int i = 0; i < 8; i += 2) {
+            float a0, a1;
+            upk2(ffma2(pk2(s[g + i], s[g + i + 1]), l2e, nmb), a0, a1);
+            float p0 = mufu_ex2(a0), p1 = mufu_ex2(a1);
+            if (TAIL) {
+              if (c + g + i >= nvalid) p0 = 0.f;
+              if (c + g + i + 1 >= nvalid) p1 = 0.f;
+            }
+            rs2 = fadd2(rs2, pk2(p0, p1));
+            pk[i >> 1] = pack_bf16x2(p0, p1);
           }
-          rs2 = fadd2(rs2, pk2(p0, p1));
-          pk[i >> 1] = pack_bf16x2(p0, p1);
-        }
-        { float r0, r1; upk2(rs2, r0, r1); rs += r0 + r1; }
-        const uint32_t half = prow + (c >> 6) * (FA_P_BYTES / 2);
-        const int ch0 = (c & 63) >> 3;                   // first 16-byte chunk of this 32-key group
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          const uint32_t addr = half + (uint32_t)(((ch0 + q4) ^ (r & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(pk[4 * q4]), "r"(pk[4 * q4 + 1]),
-                       "r"(pk[4 * q4 + 2]), "r"(pk[4 * q4 + 3]) : "memory");
+          const uint32_t addr = prow + (uint32_t)((((c + g) >> 3) ^ (r & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
         }
       }
+      float rs;
+      { float r0, r1; upk2(rs2, r0, r1); rs = r0 + r1; }
       tc_fence_before();                                 // S fully read
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // P visible to the tensor-core (async) proxy
       __syncwarp();
@@ -209,13 +223,25 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       l_run = l_run * alpha + rs;
       m_run = m_new;
       alpha_prev = alpha;
+    };
+    for (int j = 0; j < n_tiles; ++j) {
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      if ((j + 1) * FA_BK > klen) tile_step(j, TrueTag{});
+      else tile_step(j, FalseTag{});
     }
     if (n_tiles > 0) take_pv(n_tiles - 1);
+    // combine the pair's partial row sums, normalise, store this thread's 32 output columns
+    if (hh == 1) lsum[r] = l_run;
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
+    if (hh == 0) lsum[r] = l_run + lsum[r];
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
+    const float l_tot = lsum[r];
     if (q0 + r < n_q) {
-      const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
-      __nv_bfloat16* op = out + ((long long)b * q_rows_per_seg + q0 + r) * ldo + h * FA_D;
+      const float inv = l_tot > 0.f ? 1.0f / l_tot : 0.f;
+      __nv_bfloat16* op = out + ((long long)b * q_rows_per_seg + q0 + r) * ldo + h * FA_D + hh * 32;
 #pragma unroll
-      for (int i = 0; i < FA_D; i += 8) {
+      for (int i = 0; i < 32; i += 8) {
         uint4 u;
         u.x = pack_bf16x2(o[i] * inv, o[i + 1] * inv); u.y = pack_bf16x2(o[i + 2] * inv, o[i + 3] * inv);
         u.z = pack_bf16x2(o[i + 4] * inv, o[i + 5] * inv); u.w = pack_bf16x2(o[i + 6] * inv, o[i + 7] * inv);

@@ -19,8 +19,8 @@ namespace cst {
 constexpr int TC_BM = 128, TC_BK = 64;
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
-constexpr int TC_PATCH_LD = 36;                               // floats; 16B-aligned rows, conflict-free float4 access
-constexpr int TC_PATCH_BYTES = 32 * TC_PATCH_LD * 4;           // one 32x32 fp32 block per epilogue warp
+constexpr int TC_PATCH_LD = 32;                               // floats; unpadded rows, 16-byte chunks XOR-swizzled by (row & 7)
+constexpr int TC_PATCH_BYTES = 32 * TC_PATCH_LD * 4;           // one 32x32 fp32 block per epilogue warp (4 KB)
 
 template <int BN> struct TcCfg {
   static constexpr int BN_PAD = (BN <= 64) ? 64 : (BN <= 128 ? 128 : 256);   // TMEM columns per stage
@@ -28,7 +28,7 @@ template <int BN> struct TcCfg {
   static constexpr int A_BYTES = TC_BM * TC_BK * 2;
   static constexpr int B_BYTES = BN * TC_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN >= 256) ? 3 : (BN >= 128 ? 5 : 7);
+  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);   // bytes in flight hide the ~1 us L2->smem latency
   static constexpr int EPI_BYTES = TC_EPI_WARPS * TC_PATCH_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
@@ -184,34 +184,62 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();                                          // previous pass finished reading the patch
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-          *reinterpret_cast<float4*>(&patch[lane * TC_PATCH_LD + 4 * i]) = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+          *reinterpret_cast<float4*>(&patch[lane * TC_PATCH_LD + 4 * (i ^ (lane & 7))]) = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
         __syncwarp();
         if (col_ok) {
           const uint64_t b01 = pk2(b4.x, b4.y), b23 = pk2(b4.z, b4.w);
+          // 4 rows per batch: the 16 element chains (bias, activation, alpha, residual) are independent, so the
+          // two epilogue warps of an SM sub-partition keep the FMA/MUFU pipes busy instead of waiting on one chain
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            if (!((st_mask >> i) & 1)) continue;
-            const float4 a4 = *reinterpret_cast<const float4*>(&patch[(i * 4 + lr) * TC_PATCH_LD + lc]);
-            float v0, v1, v2, v3;
-            upk2(fadd2(pk2(a4.x, a4.y), b01), v0, v1);
-            upk2(fadd2(pk2(a4.z, a4.w), b23), v2, v3);
-            const bool zr = (z_mask >> i) & 1;
+          for (int i0 = 0; i0 < 8; i0 += 4) {
+            float v[4][4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int rr = (i0 + u) * 4 + lr;
+              const float4 a4 = *reinterpret_cast<const float4*>(&patch[rr * TC_PATCH_LD + 4 * ((lc >> 2) ^ (rr & 7))]);
+              upk2(fadd2(pk2(a4.x, a4.y), b01), v[u][0], v[u][1]);
+              upk2(fadd2(pk2(a4.z, a4.w), b23), v[u][2], v[u][3]);
+            }
             if (ACT == CST_ACT_GLU) {
-              float o0 = v0 * __fdividef(1.0f, 1.0f + __expf(-v1)) * p.alpha;
-              float o1 = v2 * __fdividef(1.0f, 1.0f + __expf(-v3)) * p.alpha;
-              if (p.residual) { o0 += res[i].x; o1 += res[i].y; }
-              if (zr) { o0 = 0.f; o1 = 0.f; }
-              if (c_bf16) *reinterpret_cast<uint32_t*>((__nv_bfloat16*)p.C + crow[i] + nc) = pack_bf16x2(o0, o1);
-              else *reinterpret_cast<float2*>((float*)p.C + crow[i] + nc) = make_float2(o0, o1);
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                v[u][0] = v[u][0] * mufu_rcp(1.0f + mufu_ex2(-1.4426950408889634f * v[u][1])) * p.alpha;
+                v[u][1] = v[u][2] * mufu_rcp(1.0f + mufu_ex2(-1.4426950408889634f * v[u][3])) * p.alpha;
+                if (p.residual) { v[u][0] += res[i0 + u].x; v[u][1] += res[i0 + u].y; }
+              }
             } else {
-              if (ACT == CST_ACT_GELU) { gelu2(v0, v1); gelu2(v2, v3); }
-              else if (ACT == CST_ACT_RELU) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f); }
-              uint64_t o01 = fmul2(pk2(v0, v1), alpha2), o23 = fmul2(pk2(v2, v3), alpha2);
-              if (p.residual) { o01 = fadd2(o01, pk2(res[i].x, res[i].y)); o23 = fadd2(o23, pk2(res[i].z, res[i].w)); }
-              upk2(o01, v0, v1); upk2(o23, v2, v3);
-              if (zr) { v0 = v1 = v2 = v3 = 0.f; }
-              if (c_bf16) store4((__nv_bfloat16*)p.C + crow[i] + nc, make_float4(v0, v1, v2, v3));
-              else store4((float*)p.C + crow[i] + nc, make_float4(v0, v1, v2, v3));
+              if (ACT == CST_ACT_GELU) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { gelu2(v[u][0], v[u][1]); gelu2(v[u][2], v[u][3]); }
+              } else if (ACT == CST_ACT_RELU) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  v[u][0] = fmaxf(v[u][0], 0.f); v[u][1] = fmaxf(v[u][1], 0.f);
+                  v[u][2] = fmaxf(v[u][2], 0.f); v[u][3] = fmaxf(v[u][3], 0.f);
+                }
+              }
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                uint64_t o01 = fmul2(pk2(v[u][0], v[u][1]), alpha2), o23 = fmul2(pk2(v[u][2], v[u][3]), alpha2);
+                if (p.residual) {
+                  o01 = fadd2(o01, pk2(res[i0 + u].x, res[i0 + u].y));
+                  o23 = fadd2(o23, pk2(res[i0 + u].z, res[i0 + u].w));
+                }
+                upk2(o01, v[u][0], v[u][1]); upk2(o23, v[u][2], v[u][3]);
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int i = i0 + u;
+              if (!((st_mask >> i) & 1)) continue;
+              if ((z_mask >> i) & 1) { v[u][0] = v[u][1] = v[u][2] = v[u][3] = 0.f; }
+              if (ACT == CST_ACT_GLU) {
+                if (c_bf16) *reinterpret_cast<uint32_t*>((__nv_bfloat16*)p.C + crow[i] + nc) = pack_bf16x2(v[u][0], v[u][1]);
+                else *reinterpret_cast<float2*>((float*)p.C + crow[i] + nc) = make_float2(v[u][0], v[u][1]);
+              } else {
+                if (c_bf16) store4((__nv_bfloat16*)p.C + crow[i] + nc, make_float4(v[u][0], v[u][1], v[u][2], v[u][3]));
+                else store4((float*)p.C + crow[i] + nc, make_float4(v[u][0], v[u][1], v[u][2], v[u][3]));
+              }
             }
           }
         }
