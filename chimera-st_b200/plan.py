@@ -13,6 +13,7 @@ Stage map (reference lines in include/chimera_st_b200.h and DESIGN.md):
 """
 import ctypes as C
 import math
+import os
 
 import torch
 
@@ -77,6 +78,7 @@ class EncoderPlan:
         self.use_graph = use_graph
         self.graph = None
         self.launches = 0
+        self.use_resident_posconv = os.environ.get("CST_POSCONV_RESIDENT", "1") != "0"
         self.arena = arena if arena is not None else Arena(self.dev)
         f32, i32, i64, u8, f64 = torch.float32, torch.int32, torch.int64, torch.uint8, torch.float64
         R, R2, RM = B * g.T6a, B * g.T2a, B * M
@@ -193,9 +195,14 @@ class EncoderPlan:
         L.check(lib.cst_posconv_pack(self.x.data_ptr(), B, g.T6a, g.Tp, self.xg.data_ptr(), self.act_code, g.Tpp, self.st))
         self.launches += 1
         # grouped pos-conv: z = (utterance, group); window of frame t = rows t..t+127 of the packed operand
-        self._gemm(self.xg, P["pos_w"], self.y, g.T6a, 48, 128 * 64, lda=64, a_rows=g.Tpp, bias=P["pos_b"],
-                   residual=self.x, act=L.ACT_GELU, ldc=W2V_DIM, nb_outer=B, nb_inner=16,
-                   a_bs=(16 * g.Tpp * 64, g.Tpp * 64), w_bs=48 * 128 * 64, c_bs=(g.T6a * W2V_DIM, 48), bias_bs=48)
+        if self.act == torch.bfloat16 and self.use_resident_posconv:
+            L.check(lib.cst_posconv(self.xg.data_ptr(), P["pos_w"].data_ptr(), P["pos_b"].data_ptr(), self.x.data_ptr(),
+                                    self.y.data_ptr(), B, g.T6a, g.T6a, g.Tpp, self.st))
+            self.launches += 1
+        else:
+            self._gemm(self.xg, P["pos_w"], self.y, g.T6a, 48, 128 * 64, lda=64, a_rows=g.Tpp, bias=P["pos_b"],
+                       residual=self.x, act=L.ACT_GELU, ldc=W2V_DIM, nb_outer=B, nb_inner=16,
+                       a_bs=(16 * g.Tpp * 64, g.Tpp * 64), w_bs=48 * 128 * 64, c_bs=(g.T6a * W2V_DIM, 48), bias_bs=48)
         self._ln(self.y, (P["ln_enc_g"], P["ln_enc_b"]), R, out_f32=self.x, out_lp=self.xa)
 
     def _stage_w2v_layers(self):

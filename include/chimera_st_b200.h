@@ -105,6 +105,14 @@ int cst_posconv_pack(const float* x, int B, int rows_per_seg, int n_frames, void
                      int t_pad_rows, void* stream);
 int cst_broadcast_rows(const float* src, int rows, int C, int B, float* dst, void* stream);
 
+/* ---- a5 (bf16): grouped pos-conv + bias + GELU + residual with the activation panel resident in shared memory
+ * Replaces: `x + GELU(pos_conv(x))` of TransformerEncoder.extract_features (wav2vec2.py:773-786,823-825) for the
+ * bf16 mode (the fp32 mode runs the same arithmetic as a batched cst_gemm).  xg: packed bf16 operand of
+ * cst_posconv_pack [B,16,t_pad_rows,64]; w: bf16 [16,48,128*64] (tap-major, 64-lane padded); bias [768] f32;
+ * resid / out: f32 [B*rows_per_seg, 768]; frames t < n_rows of every utterance are written. */
+int cst_posconv(const void* xg, const void* w, const float* bias, const float* resid, float* out,
+                int B, int n_rows, int rows_per_seg, int t_pad_rows, void* stream);
+
 /* ---- padding-aware attention: softmax(q k^T + keymask) v, head_dim 64 ---------------------------------
  * Replaces: the attention core of F.multi_head_attention_forward as called from
  * multihead_attention.py:165-187 (wav2vec2 layers wav2vec2.py:938-945 with a -inf key-padding mask;

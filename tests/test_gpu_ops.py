@@ -194,3 +194,27 @@ def test_attention(dtype, tol, B, H, Tq, Tk, masked):
     ref = (torch.softmax(s, -1) @ vh).transpose(1, 2).reshape(B, Tq, Cd)
     out = ops().attention(q.to(DEV), k.to(DEV), v.to(DEV), H, kl.to(DEV) if masked else None)
     assert rel_l2(out.cpu().float(), ref) < tol, rel_l2(out.cpu().float(), ref)
+
+
+@pytest.mark.parametrize("B,T", [(2, 70), (3, 250), (1, 129)])
+def test_resident_posconv_matches_generic_gemm_path(B, T):
+    """cst_posconv (panel resident in smem, row-shifted swizzled A descriptors) vs the batched implicit GEMM."""
+    g = torch.Generator().manual_seed(B * 100 + T)
+    G, Kc = 16, 128 * 64
+    Tpp = T + 128
+    x = torch.randn(B * T, 768, generator=g)
+    w = (torch.randn(G, 48, Kc, generator=g) * 0.02).to(torch.bfloat16)
+    bias = torch.randn(768, generator=g) * 0.1
+    xd = x.to(DEV)
+    xg = torch.zeros(B * G * Tpp + 8, 64, dtype=torch.bfloat16, device=DEV)
+    L = L_()
+    L.check(L.load().cst_posconv_pack(xd.data_ptr(), B, T, T, xg.data_ptr(), L.BF16, Tpp, L.stream_ptr()))
+    ref = torch.zeros(B * T, 768, dtype=torch.float32, device=DEV)
+    ops().gemm(xg, w.to(DEV), ref, T, 48, Kc, lda=64, a_rows=Tpp, bias=bias.to(DEV), residual=xd, act=1, ldc=768,
+               nb_outer=B, nb_inner=G, a_bs=(G * Tpp * 64, Tpp * 64), w_bs=48 * Kc, c_bs=(T * 768, 48), bias_bs=48)
+    out = torch.zeros(B * T, 768, dtype=torch.float32, device=DEV)
+    wd, bd = w.to(DEV), bias.to(DEV)
+    L.check(L.load().cst_posconv(xg.data_ptr(), wd.data_ptr(), bd.data_ptr(), xd.data_ptr(), out.data_ptr(), B, T, T, Tpp,
+                                 L.stream_ptr()))
+    torch.cuda.synchronize()
+    assert rel_l2(out.cpu(), ref.cpu()) < 2e-5, rel_l2(out.cpu(), ref.cpu())

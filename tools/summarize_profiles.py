@@ -1,0 +1,86 @@
+"""Turn the ncu artefacts brought back in gpurun_out/ into the tracked summaries under profiles/.
+
+    python tools/summarize_profiles.py r01
+
+Inputs (produced by tools/gpu_ncu_full.sh on a B200):
+  gpurun_out/launches_c2.csv     ncu --metrics gpu__time_duration.sum launch list of one bench step (c2 batch)
+  gpurun_out/prof_{gemm,attn,conv0,ln}.ncu-rep   ncu --set full captures
+Outputs:
+  profiles/launches_<round>.csv          per-kernel launch count / total time / share of the step
+  profiles/ncu_<round>_<kernel>.csv      selected raw metrics per captured launch
+  (profiles/SUMMARY_<round>.md is written by hand from these + bench.py output)
+"""
+import collections
+import csv
+import os
+import re
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "profiles")
+SRC = os.path.join(ROOT, "gpurun_out")
+METRICS = [
+    "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+    "launch__occupancy_limit_shared_mem", "launch__waves_per_multiprocessor",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+]
+
+
+def launch_list(tag):
+    path = os.path.join(SRC, "launches_c2.csv")
+    if not os.path.exists(path):
+        return
+    with open(path) as f:
+        lines = [l for l in f if not l.startswith("==")]
+    r = csv.reader(lines)
+    hdr = next(r)
+    idx = {h: i for i, h in enumerate(hdr)}
+    agg = collections.OrderedDict()
+    for row in r:
+        if len(row) < len(hdr):
+            continue
+        name = re.sub(r"\(.*", "", row[idx["Kernel Name"]])
+        val = float(row[idx["Metric Value"]].replace(",", ""))
+        unit = row[idx["Metric Unit"]]
+        val *= {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(unit, 1.0)
+        a = agg.setdefault(name, [0, 0.0])
+        a[0] += 1
+        a[1] += val
+    tot = sum(v[1] for v in agg.values())
+    with open(os.path.join(OUT, "launches_%s.csv" % tag), "w") as f:
+        w = csv.writer(f)
+        w.writerow(["kernel", "launches", "total_us", "share_of_step"])
+        for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            w.writerow([k, v[0], "%.1f" % v[1], "%.4f" % (v[1] / tot)])
+        w.writerow(["TOTAL", sum(v[0] for v in agg.values()), "%.1f" % tot, "1.0"])
+    print("wrote launches_%s.csv (%d kernels, %.2f ms)" % (tag, len(agg), tot / 1e3))
+
+
+def ncu_raw(tag, name):
+    rep = os.path.join(SRC, "prof_%s.ncu-rep" % name)
+    if not os.path.exists(rep):
+        return
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    cols = [(m, hdr.index(m)) for m in ["Kernel Name"] + METRICS if m in hdr]
+    with open(os.path.join(OUT, "ncu_%s_%s.csv" % (tag, name)), "w") as f:
+        w = csv.writer(f)
+        w.writerow([m for m, _ in cols])
+        w.writerow([units[i] for _, i in cols])
+        for d in data:
+            w.writerow([re.sub(r"\(CUtensorMap.*", "", d[i]) if m == "Kernel Name" else d[i] for m, i in cols])
+    print("wrote ncu_%s_%s.csv (%d launches)" % (tag, name, len(data)))
+
+
+if __name__ == "__main__":
+    tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+    os.makedirs(OUT, exist_ok=True)
+    launch_list(tag)
+    for n in ("gemm", "attn", "conv0", "ln"):
+        ncu_raw(tag, n)
