@@ -118,46 +118,60 @@ class ClockSampler:
 
 # --------------------------------------------------------------------------------------- kernel profiler
 class LaunchProfiler:
-    """CUDA-event bracket around every C-ABI launch of one instrumented (non-graph) pass."""
+    """CUDA-event bracket around every C-ABI call of one instrumented (eager, non-graph) pass: a proxy of the
+    ctypes library records (kernel family, algorithmic flop, algorithmic bytes, start/end events)."""
 
-    def __init__(self):
-        self.rec = []
+    def __init__(self, lib):
+        self.lib, self.rec = lib, []
 
-    def wrap(self, plan):
-        prof = self
-        orig_gemm, orig_attn, orig_ln = plan._gemm, plan._attn, plan._ln
+    def __getattr__(self, name):
+        fn = getattr(self.lib, name)
+        if not name.startswith("cst_") or name in ("cst_last_error", "cst_abi_version", "cst_device_info"):
+            return fn
 
-        def ev():
-            e = torch.cuda.Event(enable_timing=True)
+        def timed(*a):
+            s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
+            s.record()
+            rc = fn(*a)
             e.record()
-            return e
-
-        def gemm(A, W, C_, M, N, K, *a, **k):
-            nz = k.get("nb_outer", 1) * k.get("nb_inner", 1)
-            s = ev(); orig_gemm(A, W, C_, M, N, K, *a, **k); e = ev()
-            kind = "gemm_tc_bf16" if A.dtype == torch.bfloat16 else "gemm_ffma_f32"
-            prof.rec.append((kind, 2.0 * M * N * K * nz, (M * K + N * K) * A.element_size() * nz + M * N * C_.element_size() * nz, s, e,
-                             "M%d N%d K%d z%d" % (M, N, K, nz)))
-
-        def attn(q, k_, v, out, ldq, ldkv, H, n_q, q_rps, n_kv, kv_rps, kv_len):
-            s = ev(); orig_attn(q, k_, v, out, ldq, ldkv, H, n_q, q_rps, n_kv, kv_rps, kv_len); e = ev()
-            B = plan.g.B
-            prof.rec.append(("attention", 4.0 * B * H * n_q * n_kv * 64, 0, s, e, "B%d H%d q%d kv%d" % (B, H, n_q, n_kv)))
-
-        def ln(x, gb, rows, **k):
-            s = ev(); orig_ln(x, gb, rows, **k); e = ev()
-            prof.rec.append(("layernorm", 0.0, rows * x.shape[1] * 10, s, e, "rows%d C%d" % (rows, x.shape[1])))
-        plan._gemm, plan._attn, plan._ln = gemm, attn, ln
-        return (orig_gemm, orig_attn, orig_ln)
+            self.rec.append(self._describe(name, a) + (s, e))
+            return rc
+        return timed
 
     @staticmethod
-    def unwrap(plan, saved):
-        plan._gemm, plan._attn, plan._ln = saved
+    def _describe(name, a):
+        if name == "cst_gemm":
+            p = a[0]._obj
+            nz = p.nb_outer * p.nb_inner
+            es = 2 if p.ab_dtype == 1 else 4
+            cs = 2 if p.c_dtype == 1 else 4
+            n_out = p.N // 2 if p.act == 3 else p.N
+            by = (p.M * min(p.K, p.lda) + p.N * p.K) * es * nz + p.M * n_out * cs * nz + (p.M * n_out * 4 * nz if p.residual else 0)
+            return ("gemm_tc_bf16" if p.ab_dtype == 1 else "gemm_ffma_f32", 2.0 * p.M * p.N * p.K * nz, by,
+                    "M%d N%d K%d z%d act%d" % (p.M, p.N, p.K, nz, p.act))
+        if name == "cst_attention":
+            dtype, B, H, n_q, n_kv = a[4], a[8], a[9], a[10], a[12]
+            kind = "attention_tc_bf16" if (dtype == 1 and n_q > 64) else "attention_simt"
+            return (kind, 4.0 * B * H * n_q * n_kv * 64, 0, "B%d H%d q%d kv%d" % (B, H, n_q, n_kv))
+        if name == "cst_layernorm":
+            rows, C = a[8], a[9]
+            by = rows * C * (4 + (4 if a[4] else 0) + ((2 if a[6] == 1 else 4) if a[5] else 0))
+            return ("layernorm", 0.0, by, "rows%d C%d" % (rows, C))
+        if name == "cst_conv0_apply":
+            B, L, odt, rps = a[1], a[2], a[6], a[7]
+            return ("conv0_gn_gelu", 2.0 * B * ((L - 10) // 5 + 1) * 512 * 10, B * rps * 512 * (2 if odt == 1 else 4) + 4 * B * L,
+                    "B%d L%d" % (B, L))
+        if name == "cst_conv0_stats":
+            return ("conv0_stats", 0.0, 4 * a[1] * a[2], "B%d L%d" % (a[1], a[2]))
+        if name == "cst_posconv":
+            B, n = a[5], a[6]
+            return ("posconv_tc_bf16", 2.0 * B * n * 768 * 48 * 128, 0, "B%d T%d" % (B, n))
+        return (name[4:], 0.0, 0, "")
 
     def summary(self):
         torch.cuda.synchronize()
         agg = {}
-        for kind, fl, by, s, e, _ in self.rec:
+        for kind, fl, by, _, s, e in self.rec:
             a = agg.setdefault(kind, [0, 0.0, 0.0, 0.0])
             a[0] += 1; a[1] += fl; a[2] += by; a[3] += s.elapsed_time(e) * 1e-3
         return {k: {"launches": v[0], "flops": v[1], "bytes": v[2], "seconds": v[3]} for k, v in agg.items()}
@@ -311,13 +325,16 @@ def main():
     total_audio = D.reduce_sum(audio_per_step, "cuda")
 
     # ---- instrumented pass: per-kernel CUDA-event timing (non-graph) for the roofline object
-    prof = LaunchProfiler()
+    prof = None
     for (w, l) in dev:
         p = enc._plan(*w.shape)
-        saved = prof.wrap(p)
+        if prof is None:
+            prof = LaunchProfiler(p.lib)
+        real = p.lib
+        p.lib = prof
         p.load_inputs(w, l)
         p.run(eager=True)
-        prof.unwrap(p, saved)
+        p.lib = real
     ksum = prof.summary()
 
     if rank != 0:
@@ -341,11 +358,20 @@ def main():
                 "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
                 "launches_per_step": kd["launches"], "share_of_kernel_time": round(kd["seconds"] / step_kernel_s, 3),
                 "by_kernel": {k: {"launches": v["launches"], "ms": round(v["seconds"] * 1e3, 3),
-                                  "tflops": round(v["flops"] / v["seconds"] / 1e12, 2) if v["seconds"] > 0 else None}
+                                  "tflops": round(v["flops"] / v["seconds"] / 1e12, 2) if v["flops"] > 0 else None,
+                                  "gbs": round(v["bytes"] / v["seconds"] / 1e9, 1) if v["bytes"] > 0 else None}
                               for k, v in ksum.items()}}
+    hbm_roof = None
+    if "conv0_gn_gelu" in ksum and ksum["conv0_gn_gelu"]["seconds"] > 0:
+        k1 = ksum["conv0_gn_gelu"]
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        gbs = k1["bytes"] / k1["seconds"] / 1e9
+        hbm_roof = {"bound": "hbm", "kernel": "conv0_gn_gelu (K1: conv0+GroupNorm+GELU, the bandwidth-bound stage)",
+                    "achieved": round(gbs, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(gbs / hbm_peak, 4),
+                    "peak_source": "measured" if peaks else "fallback", "launches_per_step": k1["launches"]}
     if args.profile_json:
         with open(args.profile_json, "w") as f:
-            json.dump({"kernels": ksum, "launch_list": [(k, fl, by, s.elapsed_time(e), d) for k, fl, by, s, e, d in prof.rec]}, f)
+            json.dump({"kernels": ksum, "launch_list": [(k, fl, by, s.elapsed_time(e), d) for k, fl, by, d, s, e in prof.rec]}, f)
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -364,7 +390,7 @@ def main():
             "e2e": {"value": round(total_audio * args.steps / t_e2e, 1), "unit": "audio-s/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "wall_s": round(t_e2e_wall, 3)},
             "gpu_launches": launches, "cuda_graph": not args.no_graph, "stream_lanes": lanes, "clocks": clocks,
-            "roofline": roofline, "cpu_baseline": cpu}
+            "roofline": roofline, "roofline_hbm_kernel": hbm_roof, "cpu_baseline": cpu}
     print(json.dumps(line))
     D.finalize()
 

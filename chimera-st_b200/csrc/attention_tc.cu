@@ -44,8 +44,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const uint32_t sP = sV + FA_KS * FA_KV_BYTES;
   const uint32_t bars = sP + FA_P_BYTES;
   const uint32_t q_full = bars;
-  const uint32_t kv_full = bars + 8, kv_empty = kv_full + 8 * FA_KS;
-  const uint32_t s_full = kv_empty + 8 * FA_KS, s_empty = s_full + 8;
+  // K and V have separate rings: a K stage is free as soon as S_j has consumed it (long before PV_j frees
+  // the V stage), so the producer can fetch K two tiles ahead although only two stages exist
+  const uint32_t k_full = bars + 8, k_empty = k_full + 8 * FA_KS;
+  const uint32_t v_full = k_empty + 8 * FA_KS, v_empty = v_full + 8 * FA_KS;
+  const uint32_t s_full = v_empty + 8 * FA_KS, s_empty = s_full + 8;
   const uint32_t p_full = s_empty + 8, pv_full = p_full + 8, pv_empty = pv_full + 8;
   const uint32_t tmem_slot = pv_empty + 8;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - base));
@@ -57,7 +60,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   if (warp == 0 && lane == 0) {
     if ((base & 1023u) != 0) { printf("cst attention_tc: shared memory base not 1024-byte aligned\n"); __trap(); }
     mbar_init(q_full, 1);
-    for (int s = 0; s < FA_KS; ++s) { mbar_init(kv_full + 8 * s, 1); mbar_init(kv_empty + 8 * s, 1); }
+    for (int s = 0; s < FA_KS; ++s) {
+      mbar_init(k_full + 8 * s, 1); mbar_init(k_empty + 8 * s, 1);
+      mbar_init(v_full + 8 * s, 1); mbar_init(v_empty + 8 * s, 1);
+    }
     mbar_init(s_full, 1); mbar_init(s_empty, FA_SM_WARPS);
     mbar_init(p_full, FA_SM_WARPS); mbar_init(pv_full, 1); mbar_init(pv_empty, FA_SM_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -84,11 +90,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       tma_load_2d(sQ, &tmQ, q_full, h * FA_D, q_row);
       for (int j = 0; j < n_tiles; ++j) {
         const int st = j % FA_KS, u = j / FA_KS;
-        mbar_wait(kv_empty + 8 * st, (u & 1) ^ 1);
-        mbar_expect_tx(kv_full + 8 * st, 2 * FA_KV_BYTES);
         const int k_row = b * kv_rows_per_seg + j * FA_BK;
-        tma_load_2d(sK + st * FA_KV_BYTES, &tmK, kv_full + 8 * st, h * FA_D, k_row);
-        tma_load_2d(sV + st * FA_KV_BYTES, &tmV, kv_full + 8 * st, h * FA_D, k_row);
+        mbar_wait(k_empty + 8 * st, (u & 1) ^ 1);        // S_{j-2} done
+        mbar_expect_tx(k_full + 8 * st, FA_KV_BYTES);
+        tma_load_2d(sK + st * FA_KV_BYTES, &tmK, k_full + 8 * st, h * FA_D, k_row);
+        mbar_wait(v_empty + 8 * st, (u & 1) ^ 1);        // PV_{j-2} done
+        mbar_expect_tx(v_full + 8 * st, FA_KV_BYTES);
+        tma_load_2d(sV + st * FA_KV_BYTES, &tmV, v_full + 8 * st, h * FA_D, k_row);
       }
     }
     __syncwarp();
@@ -100,6 +108,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const uint64_t qdesc = make_sw128_desc(sQ);
       auto issue_pv = [&](int j) {
         const int st = j % FA_KS;
+        mbar_wait(v_full + 8 * st, (j / FA_KS) & 1);
         mbar_wait(p_full, j & 1);
         mbar_wait(pv_empty, (j & 1) ^ 1);
         tc_fence_after();
@@ -112,18 +121,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           tc_mma_bf16(tPV, pdesc, vdesc, idesc_pv, k != 0);
         }
         tc_commit(pv_full);
-        tc_commit(kv_empty + 8 * st);
+        tc_commit(v_empty + 8 * st);
       };
       mbar_wait(q_full, 0);
       for (int j = 0; j < n_tiles; ++j) {
         const int st = j % FA_KS;
-        mbar_wait(kv_full + 8 * st, (j / FA_KS) & 1);
+        mbar_wait(k_full + 8 * st, (j / FA_KS) & 1);
         mbar_wait(s_empty, (j & 1) ^ 1);                 // softmax finished reading S_{j-1}
         tc_fence_after();
         const uint64_t kdesc = make_sw128_desc(sK + st * FA_KV_BYTES);
 #pragma unroll
         for (int k = 0; k < FA_D / 16; ++k) tc_mma_bf16(tS, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
         tc_commit(s_full);
+        tc_commit(k_empty + 8 * st);
         if (j > 0) issue_pv(j - 1);                      // P_{j-1} was published together with s_empty
       }
       issue_pv(n_tiles - 1);
