@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(C0) conv0_finalize_kernel(const double* __rest
 // (w[c][j], w[c+1][j]) * (x[j], x[j]); the bf16 path uses the branch-free packed erf GELU (gelu2), the fp32
 // path keeps erff() so the 1e-5 parity mode stays bit-comparable to torch's erf GELU.
 template <typename OutT, int FT>
-__global__ void __launch_bounds__(256) conv0_apply_kernel(const float* __restrict__ wave, int L, int T0, int rows_per_seg,
+__global__ void __launch_bounds__(256, 2) conv0_apply_kernel(const float* __restrict__ wave, int L, int T0, int rows_per_seg,
                                                           const float* __restrict__ w, const float2* __restrict__ scale_shift,
                                                           OutT* __restrict__ out) {
   pdl_launch_dependents();
@@ -110,31 +110,40 @@ __global__ void __launch_bounds__(256) conv0_apply_kernel(const float* __restric
   }
   __syncthreads();
   OutT* orow = out + ((size_t)b * rows_per_seg) * C0 + c0;
-#pragma unroll 2
-  for (int tl = tq; tl < FT; tl += 4) {
-    const int t = t0 + tl;
-    if (t >= rows_per_seg) break;
-    float y[8];
-    if (t < T0) {
+  // two frames (tl, tl+4) per iteration: 8 independent FFMA2 chains keep the FMA pipe fed between dependent ops
+#pragma unroll 1
+  for (int tl = tq; tl < FT; tl += 8) {
+    float y[2][8];
+#pragma unroll
+    for (int f = 0; f < 2; ++f) {
+      const int tf = tl + 4 * f;
       uint64_t xv[K0];
 #pragma unroll
-      for (int j = 0; j < K0; ++j) { const float v = xs[tl * S0 + j]; xv[j] = pk2(v, v); }
+      for (int j = 0; j < K0; ++j) { const float v = xs[tf * S0 + j]; xv[j] = pk2(v, v); }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         uint64_t a = fmul2(wr[i][0], xv[0]);
 #pragma unroll
         for (int j = 1; j < K0; ++j) a = ffma2(wr[i][j], xv[j], a);
-        upk2(ffma2(a, sc[i], sh[i]), y[2 * i], y[2 * i + 1]);
-        if (sizeof(OutT) == 2) gelu2(y[2 * i], y[2 * i + 1]);
-        else { y[2 * i] = gelu_erf(y[2 * i]); y[2 * i + 1] = gelu_erf(y[2 * i + 1]); }
+        upk2(ffma2(a, sc[i], sh[i]), y[f][2 * i], y[f][2 * i + 1]);
       }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) y[i] = 0.f;
     }
-    OutT* o = orow + (size_t)t * C0;
-    store4(o, make_float4(y[0], y[1], y[2], y[3]));
-    store4(o + 4, make_float4(y[4], y[5], y[6], y[7]));
+#pragma unroll
+    for (int f = 0; f < 2; ++f)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (sizeof(OutT) == 2) gelu2(y[f][2 * i], y[f][2 * i + 1]);
+        else { y[f][2 * i] = gelu_erf(y[f][2 * i]); y[f][2 * i + 1] = gelu_erf(y[f][2 * i + 1]); }
+      }
+#pragma unroll
+    for (int f = 0; f < 2; ++f) {
+      const int t = t0 + tl + 4 * f;
+      if (t >= rows_per_seg) continue;
+      const bool live = t < T0;
+      OutT* o = orow + (size_t)t * C0;
+      store4(o, live ? make_float4(y[f][0], y[f][1], y[f][2], y[f][3]) : make_float4(0.f, 0.f, 0.f, 0.f));
+      store4(o + 4, live ? make_float4(y[f][4], y[f][5], y[f][6], y[f][7]) : make_float4(0.f, 0.f, 0.f, 0.f));
+    }
   }
 }
 }  // namespace cst

@@ -82,5 +82,5 @@ if __name__ == "__main__":
     tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
     os.makedirs(OUT, exist_ok=True)
     launch_list(tag)
-    for n in ("gemm", "attn", "conv0", "ln"):
+    for n in ("gemm", "attn", "conv0", "posconv", "ln"):
         ncu_raw(tag, n)
