@@ -143,11 +143,11 @@ class LaunchProfiler:
         if name == "cst_gemm":
             p = a[0]._obj
             nz = p.nb_outer * p.nb_inner
-            es = 2 if p.ab_dtype == 1 else 4
-            cs = 2 if p.c_dtype == 1 else 4
+            es = 2 if p.ab_dtype in (1, 2) else 4
+            cs = 2 if p.c_dtype in (1, 2) else 4
             n_out = p.N // 2 if p.act == 3 else p.N
             by = (p.M * min(p.K, p.lda) + p.N * p.K) * es * nz + p.M * n_out * cs * nz + (p.M * n_out * 4 * nz if p.residual else 0)
-            return ("gemm_tc_bf16" if p.ab_dtype == 1 else "gemm_ffma_f32", 2.0 * p.M * p.N * p.K * nz, by,
+            return ("gemm_tc_bf16" if p.ab_dtype in (1, 2) else "gemm_ffma_f32", 2.0 * p.M * p.N * p.K * nz, by,
                     "M%d N%d K%d z%d act%d" % (p.M, p.N, p.K, nz, p.act))
         if name == "cst_attention":
             dtype, B, H, n_q, n_kv = a[4], a[8], a[9], a[10], a[12]
@@ -159,7 +159,7 @@ class LaunchProfiler:
             return ("layernorm", 0.0, by, "rows%d C%d" % (rows, C))
         if name == "cst_conv0_apply":
             B, L, odt, rps = a[1], a[2], a[6], a[7]
-            return ("conv0_gn_gelu", 2.0 * B * ((L - 10) // 5 + 1) * 512 * 10, B * rps * 512 * (2 if odt == 1 else 4) + 4 * B * L,
+            return ("conv0_gn_gelu", 2.0 * B * ((L - 10) // 5 + 1) * 512 * 10, B * rps * 512 * (2 if odt in (1, 2) else 4) + 4 * B * L,
                     "B%d L%d" % (B, L))
         if name == "cst_conv0_stats":
             return ("conv0_stats", 0.0, 4 * a[1] * a[2], "B%d L%d" % (a[1], a[2]))
@@ -228,7 +228,9 @@ def main():
         "c1": "B=4 x 5 s", "c2": "B=32 x 15 s", "c4": "B=64 x 20 s"}[args.workload]),
         "interlingua_length": M, "batches_per_step": len(batches), "audio_sec_per_step_per_gpu": round(audio_per_step, 2),
         "parallelism": "utterance-sharded dp%d, no data-path collective" % world,
-        "l2": "activations per batch (>=0.4 GB) exceed the 126 MB L2; no explicit flush"}
+        "l2": "activations per batch (>=0.4 GB) exceed the 126 MB L2; no explicit flush",
+        "precision": "bf16 operands / fp32 accumulate, residual stream, norms and softmax; conv feature extractor operands fp16 (same bytes)"
+                     if args.dtype == "bf16" else "fp32 FFMA"}
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":

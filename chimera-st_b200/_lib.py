@@ -11,9 +11,9 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libchimera_st_b200.so")
 
-F32, BF16 = 0, 1
+F32, BF16, F16 = 0, 1, 2
 ACT_NONE, ACT_GELU, ACT_RELU, ACT_GLU = 0, 1, 2, 3
-DT = {torch.float32: F32, torch.bfloat16: BF16}
+DT = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
 
 
 class GemmParams(C.Structure):

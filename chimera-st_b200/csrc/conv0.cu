@@ -173,7 +173,9 @@ extern "C" int cst_conv0_apply(const float* wave, int B, int L, const float* w, 
   dim3 grid(cdiv(rows_per_seg, FT), B);
   cudaStream_t st = (cudaStream_t)stream;
   const float2* ss = reinterpret_cast<const float2*>(scale_shift);
-  if (out_dtype == CST_BF16)
+  if (out_dtype == CST_F16)
+    CST_CHECK_CUDA(launch_k(conv0_apply_kernel<__half, FT>, grid, dim3(256), 0, st, wave, L, T0, rows_per_seg, w, ss, (__half*)out));
+  else if (out_dtype == CST_BF16)
     CST_CHECK_CUDA(launch_k(conv0_apply_kernel<__nv_bfloat16, FT>, grid, dim3(256), 0, st, wave, L, T0, rows_per_seg, w, ss, (__nv_bfloat16*)out));
   else if (out_dtype == CST_F32)
     CST_CHECK_CUDA(launch_k(conv0_apply_kernel<float, FT>, grid, dim3(256), 0, st, wave, L, T0, rows_per_seg, w, ss, (float*)out));

@@ -119,7 +119,8 @@ extern "C" int cst_gemm(const cst_gemm_params* hp, void* stream) {
   CST_REQUIRE(hp->lda % 8 == 0 && hp->ldc % 8 == 0, "cst_gemm: lda/ldc must be multiples of 8");
   CST_REQUIRE(hp->residual == nullptr || hp->ldr % 4 == 0, "cst_gemm: ldr must be a multiple of 4");
   CST_REQUIRE(hp->act >= CST_ACT_NONE && hp->act <= CST_ACT_GLU, "cst_gemm: bad act %d", hp->act);
-  CST_REQUIRE(hp->c_dtype == CST_F32 || hp->c_dtype == CST_BF16, "cst_gemm: bad c_dtype");
+  CST_REQUIRE(hp->c_dtype == CST_F32 || hp->c_dtype == CST_BF16 || hp->c_dtype == CST_F16, "cst_gemm: bad c_dtype");
+  CST_REQUIRE(hp->ab_dtype != CST_F32 || hp->c_dtype != CST_F16, "cst_gemm: the fp32 kernel has no fp16 output");
   CST_REQUIRE(hp->rows_per_seg > 0 && hp->seg_rows_valid > 0, "cst_gemm: rows_per_seg/seg_rows_valid must be > 0");
   CST_REQUIRE(hp->nb_outer >= 1 && hp->nb_inner >= 1, "cst_gemm: nb_outer/nb_inner must be >= 1");
   CST_REQUIRE(hp->a_rows > 0, "cst_gemm: a_rows must be > 0");
@@ -137,7 +138,7 @@ extern "C" int cst_gemm(const cst_gemm_params* hp, void* stream) {
   const int nz = hp->nb_outer * hp->nb_inner;
   cudaStream_t st = (cudaStream_t)stream;
   if (hp->ab_dtype == CST_F32) return launch_gemm_f32(p, nz, st);
-  if (hp->ab_dtype == CST_BF16) return launch_gemm_tc(*hp, p, nz, st);
+  if (hp->ab_dtype == CST_BF16 || hp->ab_dtype == CST_F16) return launch_gemm_tc(*hp, p, nz, st);
   CST_REQUIRE(false, "cst_gemm: bad ab_dtype %d", hp->ab_dtype);
   return CST_ERR_ARG;
 }

@@ -36,7 +36,7 @@ template <int BN> struct TcCfg {
 template <int BN, int ACT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const GemmDev p, int m_tiles, int n_tiles, int total_tiles, int a_wrap) {
+               const GemmDev p, int m_tiles, int n_tiles, int total_tiles, int a_wrap, int ab_f16) {
   using Cfg = TcCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -95,7 +95,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      // fp32 accumulate; operand formats bf16 (1) or fp16 (0) in bits 7-9 / 10-12
+      const uint32_t fmt = ab_f16 ? 0u : 1u;
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       int s = 0; uint32_t ph = 0; int it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int as = it & 1; const uint32_t aph = (it >> 1) & 1;
@@ -127,7 +129,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int NCH = (BN + 31) / 32;                        // 32-column chunks in the tile
     constexpr int CH_PER = (NCH + 1) / 2;
     const int lr = lane >> 3, lc = (lane & 7) * 4;             // row-contiguous domain: 4 rows x 8 float4 per pass
-    const bool c_bf16 = p.c_dtype == CST_BF16;
+    const bool c_16 = p.c_dtype != CST_F32, c_f16 = p.c_dtype == CST_F16;
     const uint64_t alpha2 = pk2(p.alpha, p.alpha);
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -234,10 +236,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (!((st_mask >> i) & 1)) continue;
               if ((z_mask >> i) & 1) { v[u][0] = v[u][1] = v[u][2] = v[u][3] = 0.f; }
               if (ACT == CST_ACT_GLU) {
-                if (c_bf16) *reinterpret_cast<uint32_t*>((__nv_bfloat16*)p.C + crow[i] + nc) = pack_bf16x2(v[u][0], v[u][1]);
+                if (c_16) *reinterpret_cast<uint32_t*>((__nv_bfloat16*)p.C + crow[i] + nc) = c_f16 ? pack_f16x2(v[u][0], v[u][1]) : pack_bf16x2(v[u][0], v[u][1]);
                 else *reinterpret_cast<float2*>((float*)p.C + crow[i] + nc) = make_float2(v[u][0], v[u][1]);
               } else {
-                if (c_bf16) store4((__nv_bfloat16*)p.C + crow[i] + nc, make_float4(v[u][0], v[u][1], v[u][2], v[u][3]));
+                if (c_f16) store4((__half*)p.C + crow[i] + nc, make_float4(v[u][0], v[u][1], v[u][2], v[u][3]));
+                else if (c_16) store4((__nv_bfloat16*)p.C + crow[i] + nc, make_float4(v[u][0], v[u][1], v[u][2], v[u][3]));
                 else store4((float*)p.C + crow[i] + nc, make_float4(v[u][0], v[u][1], v[u][2], v[u][3]));
               }
             }
@@ -286,7 +289,7 @@ static int launch_tc_act(const cst_gemm_params& hp, const GemmDev& p, int nz, cu
   CST_CHECK_CUDA(cudaGetDevice(&dev));
   CST_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = (int)(total < sms ? total : sms);
-  CST_CHECK_CUDA(launch_k(gemm_tc_kernel<BN, ACT>, dim3(grid), dim3(TC_THREADS), Cfg::SMEM_BYTES, st, tmA, tmB, p, m_tiles, n_tiles, (int)total, a_wrap));
+  CST_CHECK_CUDA(launch_k(gemm_tc_kernel<BN, ACT>, dim3(grid), dim3(TC_THREADS), Cfg::SMEM_BYTES, st, tmA, tmB, p, m_tiles, n_tiles, (int)total, a_wrap, hp.ab_dtype == CST_F16 ? 1 : 0));
   return CST_OK;
 }
 

@@ -15,6 +15,7 @@ pre-training heads and `embed_positions._float_tensor`), so a reference checkpoi
 Not reproduced (out of scope): the text (MT) branch, training-time dropout / LayerDrop,
 `modal_embedding` debug option, `non_shared_encoder_layers`.  They raise NotImplementedError.
 """
+import os
 from collections import OrderedDict
 from typing import List, NamedTuple, Optional
 
@@ -57,12 +58,16 @@ class B200InterlinguaEncoder(nn.Module):
     MAX_PLANS = 256         # cached (B, L) shapes (geometry + CUDA graph); activations overlay one shared arena
 
     def __init__(self, interlingua_length=16, dtype=torch.float32, use_graph=True, dead_heads=True,
-                 text_vocab=0, encoder_out_dtype=None):
+                 text_vocab=0, encoder_out_dtype=None, conv_fp16=None):
         nn.Module.__init__(self)          # explicit: the fairseq plugin mixes this class with FairseqEncoder
         if dtype not in (torch.float32, torch.bfloat16):
             raise ValueError("compute dtype must be float32 or bfloat16")
         self.interlingua_length = interlingua_length
         self.compute_dtype = dtype
+        # 16-bit mode: fp16 operands inside the normalisation-free conv feature extractor (see weights.py); bf16 elsewhere
+        if conv_fp16 is None:
+            conv_fp16 = os.environ.get("CST_CONV_FP16", "1") != "0"
+        self.conv_dtype = torch.float16 if (dtype == torch.bfloat16 and conv_fp16) else dtype
         self.use_graph = use_graph
         self.encoder_out_dtype = encoder_out_dtype
         self.no_interlingua = False
@@ -109,7 +114,7 @@ class B200InterlinguaEncoder(nn.Module):
     def _plan(self, B, L, lane=None):
         dev = self._device()
         if self._prepared is None:
-            self._prepared = _weights.prepare(self.state_dict(), dev, self.compute_dtype)
+            self._prepared = _weights.prepare(self.state_dict(), dev, self.compute_dtype, self.conv_dtype)
         if lane is None:
             if self._arena is None:
                 self._arena = Arena(dev)
@@ -123,7 +128,7 @@ class B200InterlinguaEncoder(nn.Module):
                 plans.popitem(last=False)
             gen = arena.generation
             plan = EncoderPlan(self._prepared, B, L, self.interlingua_length, self.compute_dtype, dev, self.use_graph,
-                               arena=arena)
+                               arena=arena, conv_dtype=self.conv_dtype)
             if arena.generation != gen:                # arena grew: older plans (and their graphs) point at freed memory
                 plans.clear()
             plans[key] = plan
@@ -204,7 +209,7 @@ class B200InterlinguaEncoder(nn.Module):
 
 
 def build_encoder_from_state_dict(state_dict, interlingua_length=None, dtype=torch.float32, device="cuda",
-                                  use_graph=True):
+                                  use_graph=True, conv_fp16=None):
     """Convenience: infer M from the checkpoint, load strictly, move to the device."""
     sd = state_dict
     if any(k.startswith("encoder.") for k in sd):
@@ -212,6 +217,6 @@ def build_encoder_from_state_dict(state_dict, interlingua_length=None, dtype=tor
     M = interlingua_length or sd["interlingua_embedding.weight"].shape[0]
     dead = "wav2vec_model.mask_emb" in sd
     vocab = sd["text_embed_tokens.weight"].shape[0] if "text_embed_tokens.weight" in sd else 0
-    enc = B200InterlinguaEncoder(M, dtype=dtype, use_graph=use_graph, dead_heads=dead, text_vocab=vocab)
+    enc = B200InterlinguaEncoder(M, dtype=dtype, use_graph=use_graph, dead_heads=dead, text_vocab=vocab, conv_fp16=conv_fp16)
     enc.load_state_dict(sd, strict=True)
     return enc.to(device).eval()

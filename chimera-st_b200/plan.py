@@ -66,7 +66,7 @@ class Arena:
 
 class EncoderPlan:
     def __init__(self, params, B, Lw, M, act_dtype=torch.float32, device=None, use_graph=False, lib=None,
-                 arena=None):
+                 arena=None, conv_dtype=None):
         # `lib` is injectable so tests can drive the plan against a host emulator of the C ABI
         # (tests/emu.py); the product never passes it and always loads the CUDA library.
         self.lib = lib if lib is not None else L.load()
@@ -75,6 +75,7 @@ class EncoderPlan:
         self.dev = device or torch.device("cuda", torch.cuda.current_device())
         self.act = act_dtype
         self.act_code = L.DT[act_dtype]
+        self.conv_dt = conv_dtype or act_dtype          # operand dtype of the conv feature extractor (fp16 option)
         self.use_graph = use_graph
         self.graph = None
         self.launches = 0
@@ -88,7 +89,7 @@ class EncoderPlan:
             ("w2v_len64", 1, B, i64), ("frame_mask", B, g.Tp, u8),
             # ---- conv stack (ping-pong; level i lives in cbuf{i & 1}); SLACK rows absorb the last windows
             ("scale_shift", B * 512, 2, f32), ("stats_ws", 1, B * 72, f64),
-            ("cbuf0", B * g.Ta[0] + SLACK, 512, act_dtype), ("cbuf1", B * g.Ta[1] + SLACK, 512, act_dtype),
+            ("cbuf0", B * g.Ta[0] + SLACK, 512, self.conv_dt), ("cbuf1", B * g.Ta[1] + SLACK, 512, self.conv_dt),
             ("feat", R, 512, f32), ("feat_ln", R, 512, act_dtype),
             # ---- wav2vec2 encoder: fp32 residual stream x, pre-LN sums y, GEMM-operand copy xa
             ("x", R, W2V_DIM, f32), ("y", R, W2V_DIM, f32), ("xa", R, W2V_DIM, act_dtype),
@@ -177,7 +178,7 @@ class EncoderPlan:
         L.check(lib.cst_conv0_stats(self.wave.data_ptr(), B, g.L, P["conv0_w"].data_ptr(), P["gn_g"].data_ptr(),
                                     P["gn_b"].data_ptr(), self.scale_shift.data_ptr(), self.stats_ws.data_ptr(), self.st))
         L.check(lib.cst_conv0_apply(self.wave.data_ptr(), B, g.L, P["conv0_w"].data_ptr(), self.scale_shift.data_ptr(),
-                                    self.cbuf[0].data_ptr(), self.act_code, g.Ta[0], self.st))
+                                    self.cbuf[0].data_ptr(), L.DT[self.conv_dt], g.Ta[0], self.st))
         self.launches += 4
         for i in range(1, 7):
             src = self.cbuf[(i - 1) & 1]

@@ -12,7 +12,10 @@ Layout rules (all exact re-arrangements, no arithmetic except the folds noted):
   * subsampler convs: output channels interleaved (value_i, gate_i) so GLU pairs are adjacent columns.
   * pos-conv: w = g * v / ||v||_(0,1) (wav2vec2.py:785), split per group to [16, 48, 128*64] with the 48
     input channels of a tap zero-padded to 64 lanes (one 128-byte swizzle row per tap in bf16).
-GEMM operands are stored in `act_dtype` (fp32 or bf16); biases / norm parameters stay fp32.
+GEMM operands are stored in `act_dtype` (fp32 or bf16); biases / norm parameters stay fp32.  In the 16-bit mode the
+conv feature extractor (conv1..6) may use fp16 operands (`conv_dtype`): that stack has no normalisation between its 7
+layers, so operand rounding accumulates (bf16: 6.3e-3 rel-L2 at its output, fp16: 0.8e-3) -- same bytes, same tensor
+throughput, and fp16 is the half-precision format of the reference's own recipes (`--fp16`).
 """
 import torch
 
@@ -30,8 +33,10 @@ def _glu_interleave(w):
     return torch.stack((w[:half], w[half:]), dim=1).reshape(w.shape)
 
 
-def prepare(state_dict, device, act_dtype):
+def prepare(state_dict, device, act_dtype, conv_dtype=None):
+    """conv_dtype: operand dtype of the conv feature extractor GEMMs (conv1..6); defaults to act_dtype."""
     sd = _strip(state_dict)
+    conv_dtype = conv_dtype or act_dtype
     f32 = lambda t: t.detach().to(device=device, dtype=torch.float32).contiguous()   # noqa: E731
     op = lambda t: t.detach().to(device=device, dtype=torch.float32).to(act_dtype).contiguous()   # noqa: E731
     W = "wav2vec_model."
@@ -41,7 +46,7 @@ def prepare(state_dict, device, act_dtype):
     P["gn_g"], P["gn_b"] = f32(sd[fe + "0.2.weight"]), f32(sd[fe + "0.2.bias"])
     for i in range(1, len(CONV_LAYERS)):
         w = sd[fe + f"{i}.0.weight"]                       # [512, 512, k]
-        P[f"conv{i}_w"] = op(w.permute(0, 2, 1).reshape(w.shape[0], -1))
+        P[f"conv{i}_w"] = w.detach().to(device=device, dtype=torch.float32).permute(0, 2, 1).reshape(w.shape[0], -1).to(conv_dtype).contiguous()
     P["ln_feat_g"], P["ln_feat_b"] = f32(sd[W + "layer_norm.weight"]), f32(sd[W + "layer_norm.bias"])
     P["proj_w"], P["proj_b"] = op(sd[W + "post_extract_proj.weight"]), f32(sd[W + "post_extract_proj.bias"])
 

@@ -12,7 +12,7 @@
  *   - every function returns 0 on success, else a CST_ERR_* code; cst_last_error() (thread-local)
  *     gives the message.  There is no CPU fallback anywhere: no device => error.
  *   - activations are row-major [rows, channels] ("channels-last"); a batch of B utterances is
- *     B segments of `rows_per_seg` rows.  dtypes: CST_F32 or CST_BF16.
+ *     B segments of `rows_per_seg` rows.  dtypes: CST_F32, CST_BF16 (and CST_F16 for cst_gemm / cst_conv0_apply).
  */
 #ifndef CHIMERA_ST_B200_H_
 #define CHIMERA_ST_B200_H_
@@ -25,7 +25,7 @@ extern "C" {
 #define CST_ABI_VERSION 1
 
 enum { CST_OK = 0, CST_ERR_ARG = 1, CST_ERR_CUDA = 2, CST_ERR_UNSUPPORTED = 3 };
-enum { CST_F32 = 0, CST_BF16 = 1 };
+enum { CST_F32 = 0, CST_BF16 = 1, CST_F16 = 2 };   /* F16: conv feature extractor operands of the 16-bit mode */
 enum { CST_ACT_NONE = 0, CST_ACT_GELU = 1, CST_ACT_RELU = 2, CST_ACT_GLU = 3 };
 
 int cst_abi_version(void);
@@ -72,7 +72,9 @@ int cst_conv0_apply(const float* wave, int B, int L, const float* w, const float
  *   (seg counted across batch z_outer) are stored as 0 (x[padding_mask] = 0, wav2vec2.py:820-821).
  * Batched over z = zo*nb_inner + zi (pos-conv: zo = utterance, zi = group).
  * CST_F32 inputs use an FFMA kernel (true-fp32 accumulate: the 1e-5 parity mode); CST_BF16 inputs use the
- * TMA + tcgen05/TMEM kernel (fp32 accumulate in tensor memory).  A and W must share a dtype. */
+ * TMA + tcgen05/TMEM kernel (fp32 accumulate in tensor memory); CST_F16 inputs use the same kernel with fp16 operand
+ * formats (the normalisation-free conv stack of the 16-bit mode: 3 more mantissa bits at the same bytes).
+ * A and W must share a dtype. */
 typedef struct cst_gemm_params {
   const void* A; const void* W; const float* bias; const float* residual; void* C;
   int ab_dtype; int c_dtype;

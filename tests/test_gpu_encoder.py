@@ -149,3 +149,17 @@ def test_single_utterance_output_does_not_alias_the_arena():
     w2, l2 = synth.make_waveforms([24000], seed=103)
     enc(w2.cuda(), l2.cuda())
     assert torch.equal(a, keep)
+
+
+def test_16bit_mode_margin_and_pure_bf16_option():
+    """Default 16-bit mode (bf16 + fp16 conv feature extractor) keeps a clear margin under the 1e-2 bar; the pure
+    bf16 variant (conv_fp16=False) is still inside it."""
+    from chimera_st_b200.encoder import build_encoder_from_state_dict
+    g, wave, lens = _golden("tiny")
+    sd = synth.make_state_dict(seed=0, interlingua_length=16)
+    ref = torch.from_numpy(g["memories"])
+    mixed = encoder(16, torch.bfloat16)(wave.cuda(), lens.cuda()).encoder_out.cpu()
+    pure = build_encoder_from_state_dict(sd, dtype=torch.bfloat16, device="cuda", use_graph=False, conv_fp16=False)
+    p = pure(wave.cuda(), lens.cuda()).encoder_out.cpu()
+    assert rel_l2(mixed, ref) < 8e-3, rel_l2(mixed, ref)
+    assert rel_l2(p, ref) < 1e-2, rel_l2(p, ref)

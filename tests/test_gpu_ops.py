@@ -102,7 +102,7 @@ def test_linear(dtype, tol, M, N, K, act):
     assert rel_max(out.cpu(), ref) < 20 * tol
 
 
-@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-6), (torch.bfloat16, 2e-5)])
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-6), (torch.bfloat16, 2e-5), (torch.float16, 2e-5)])
 def test_implicit_conv_gemm_matches_conv1d(dtype, tol):
     """stride-2 conv over channels-last rows as an overlapping-window GEMM (lda < K)."""
     g = torch.Generator().manual_seed(5)
@@ -120,6 +120,12 @@ def test_implicit_conv_gemm_matches_conv1d(dtype, tol):
                rows_per_seg=Ta)
     got = out.cpu().view(B, Ta, 512)[:, :Tout]
     assert rel_l2(got, ref) < tol, rel_l2(got, ref)
+    if dtype != torch.float32:          # 16-bit output of the same dtype (what the conv stack stores between layers)
+        out16 = torch.zeros(B * Ta, 512, dtype=dtype, device=DEV)
+        ops().gemm(xb.to(DEV), wk.to(DEV), out16, B * Ta, 512, k * Cc, lda=2 * Cc, a_rows=(B * Tin + 8) // 2, act=1,
+                   rows_per_seg=Ta)
+        got16 = out16.cpu().float().view(B, Ta, 512)[:, :Tout]
+        assert rel_l2(got16, ref) < (4e-3 if dtype == torch.bfloat16 else 5e-4)
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-6), (torch.bfloat16, 2e-5)])
