@@ -145,3 +145,56 @@ def make_waveforms(lengths, seed=1234, pad_to=None):
     for b, n in enumerate(lengths):
         x[b, n:] = 0.0
     return x, torch.tensor(lengths, dtype=torch.int64)
+
+
+# ---- decoder (NOT part of the B200 path: the reference's TransformerDecoder stays PyTorch).
+# Synthetic decoder weights exist only so that the parity tests can check "identical greedy-decoded token IDs"
+# downstream of the encoder (BASELINE.json north_star) with the oracle's greedy decoder.
+DEC_LAYERS, VOCAB = 6, 10000
+
+
+def decoder_param_spec(vocab=VOCAB):
+    s = [("embed_tokens.weight", (vocab, ENC_DIM), "embed_pad1", 1.0), ("embed_positions._float_tensor", (1,), "zeros", 0)]
+    for i in range(DEC_LAYERS):
+        P = f"layers.{i}."
+        for blk, gain in (("self_attn", 1.0), ("encoder_attn", 3.0)):
+            for p in ("k", "v", "q"):
+                s.append((P + f"{blk}.{p}_proj.weight", (ENC_DIM, ENC_DIM), "normal", 0.03125 * (gain if p != "v" else 1.0)))
+                s.append((P + f"{blk}.{p}_proj.bias", (ENC_DIM,), "normal", 0.02))
+            s.append((P + f"{blk}.out_proj.weight", (ENC_DIM, ENC_DIM), "normal", 0.0442 * gain))
+            s.append((P + f"{blk}.out_proj.bias", (ENC_DIM,), "normal", 0.02))
+            s.append((P + f"{blk}_layer_norm.weight", (ENC_DIM,), "gain", 0.1))
+            s.append((P + f"{blk}_layer_norm.bias", (ENC_DIM,), "normal", 0.05))
+        s.append((P + "fc1.weight", (ENC_FFN, ENC_DIM), "normal", 0.0255))
+        s.append((P + "fc1.bias", (ENC_FFN,), "normal", 0.02))
+        s.append((P + "fc2.weight", (ENC_DIM, ENC_FFN), "normal", 0.01275))
+        s.append((P + "fc2.bias", (ENC_DIM,), "normal", 0.02))
+        s.append((P + "final_layer_norm.weight", (ENC_DIM,), "gain", 0.1))
+        s.append((P + "final_layer_norm.bias", (ENC_DIM,), "normal", 0.05))
+    s.append(("layer_norm.weight", (ENC_DIM,), "gain", 0.1))
+    s.append(("layer_norm.bias", (ENC_DIM,), "normal", 0.05))
+    return s
+
+
+def make_decoder_state_dict(seed=1, vocab=VOCAB, embed_std=None, prefix="decoder."):
+    """Seeded decoder weights with the reference's keys (tied input/output embeddings: `output_projection.weight`
+    is the same tensor as `embed_tokens.weight`; `version` buffer as in fairseq)."""
+    g = torch.Generator().manual_seed(seed)
+    sd = OrderedDict()
+    embed_std = embed_std if embed_std is not None else ENC_DIM ** -0.5
+    for name, shape, kind, scale in decoder_param_spec(vocab):
+        if kind == "normal":
+            t = torch.randn(shape, generator=g) * scale
+        elif kind == "gain":
+            t = 1.0 + scale * torch.randn(shape, generator=g)
+        elif kind == "zeros":
+            t = torch.zeros(shape)
+        elif kind == "embed_pad1":     # Embedding(padding_idx=1): N(0, d^-0.5), pad row zero (transformer.py:906-910)
+            t = torch.randn(shape, generator=g) * embed_std
+            t[1].zero_()
+        else:
+            raise ValueError(kind)
+        sd[prefix + name] = t
+    sd[prefix + "output_projection.weight"] = sd[prefix + "embed_tokens.weight"]
+    sd[prefix + "version"] = torch.tensor([3.0])
+    return sd
