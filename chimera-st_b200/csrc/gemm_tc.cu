@@ -304,7 +304,12 @@ static int launch_tc(const cst_gemm_params& hp, const GemmDev& p, int nz, cudaSt
 }
 
 int launch_gemm_tc(const cst_gemm_params& hp, const GemmDev& p, int nz, cudaStream_t st) {
-  if (hp.N % 256 == 0) return launch_tc<256>(hp, p, nz, st);
+  // 128x256 tiles halve the B-operand traffic per flop.  Measured (c3, 3 stream lanes): switching problems with
+  // < 1.5 tiles per SM to 128x128 tiles raises the isolated GEMM rate (548 -> 572 TFLOP/s) but LOWERS end-to-end
+  // throughput (34.0k -> 33.0k audio-s/s): concurrent lanes already fill the tails, so 256 stays the default
+  // (CST_TC_BN=128 forces the small tile for experiments).
+  static const int force_bn = [] { const char* e = getenv("CST_TC_BN"); return e ? atoi(e) : 0; }();
+  if (hp.N % 256 == 0 && force_bn != 128) return launch_tc<256>(hp, p, nz, st);
   if (hp.N % 128 == 0) return launch_tc<128>(hp, p, nz, st);
   if (hp.N == 48) return launch_tc<48>(hp, p, nz, st);
   if (hp.N % 64 == 0) return launch_tc<64>(hp, p, nz, st);
