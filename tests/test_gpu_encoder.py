@@ -189,3 +189,31 @@ def test_full_size_batches_row_independence_and_oracle_rows(B, secs, M):
     with torch.no_grad():
         ref, _ = O.encoder_forward(sd, w0, l0)
     assert rel_l2(out[:, 0:1].cpu(), ref) < 1e-2
+
+
+@pytest.mark.parametrize("lens", [[400], [401, 400], [719, 500, 400], [960, 1], [3200, 3199, 17], [480000], [33000, 32000, 20000, 9000, 400]])
+def test_edge_shapes_fp32(lens):
+    """Ragged / extreme inputs the reference accepts: the shortest waveform the conv stack admits (L=400 -> T'=1),
+    one-sample utterances inside a longer batch, the 30 s maximum of the workload, very uneven batches."""
+    sd = synth.make_state_dict(seed=0)
+    wave, tl = synth.make_waveforms(lens, seed=len(lens) * 13 + lens[0] % 97)
+    st = {}
+    with torch.no_grad():
+        ref, _ = O.encoder_forward(sd, wave, tl, stages=st)
+    enc = encoder(16, torch.float32)
+    feat, fmask, flen = enc._get_w2v_feature(wave.cuda(), tl.cuda())
+    assert torch.equal(fmask.cpu(), st["frame_mask"]) and torch.equal(flen.cpu(), st["w2v_len"])
+    out = enc(wave.cuda(), tl.cuda())
+    assert out.encoder_out.shape == ref.shape
+    assert rel_l2(out.encoder_out.cpu(), ref) < 1e-5, rel_l2(out.encoder_out.cpu(), ref)
+    assert rel_l2(feat.cpu(), st["w2v_out"]) < 1e-5
+
+
+def test_rejects_bad_inputs():
+    enc = encoder(16, torch.float32)
+    with pytest.raises(ValueError):
+        enc(torch.zeros(2, 3, 4000).cuda(), torch.tensor([4000, 4000]).cuda())
+    with pytest.raises(ValueError):
+        enc(torch.zeros(1, 100).cuda(), torch.tensor([100]).cuda())          # shorter than the conv stack's receptive field
+    with pytest.raises(NotImplementedError):
+        enc(torch.zeros(1, 10, dtype=torch.long).cuda(), torch.tensor([10]).cuda())

@@ -1,0 +1,15 @@
+"""Tiny forward (fp32 and bf16, eager) for compute-sanitizer runs:
+   compute-sanitizer --tool memcheck python tools/sanitize.py"""
+import os, sys, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import chimera_st_b200
+from chimera_st_b200 import synth
+from chimera_st_b200.encoder import build_encoder_from_state_dict
+sd = synth.make_state_dict(seed=0)
+wave, lens = synth.make_waveforms([9000, 5000], seed=3)
+for dtype in (torch.float32, torch.bfloat16):
+    enc = build_encoder_from_state_dict(sd, dtype=dtype, device="cuda", use_graph=False)
+    out = enc(wave.cuda(), lens.cuda())
+    torch.cuda.synchronize()
+    print(dtype, float(out.encoder_out.abs().mean()))
