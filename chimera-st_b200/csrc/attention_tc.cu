@@ -29,6 +29,12 @@ constexpr int FA_P_BYTES = FA_BQ * FA_BK * 2;           // 32 KB (two 64-key hal
 constexpr int FA_SMEM = FA_Q_BYTES + 2 * FA_KS * FA_KV_BYTES + FA_P_BYTES + 128 + 512;   // 112.6 KB: two CTAs per SM (limit 113 KB)
 constexpr int FA_TMEM_COLS = 256;
 constexpr float FA_LOG2E = 1.4426950408889634f;
+#ifdef FA_PROFILE
+__device__ long long fa_prof[16];
+#define FA_T(i) do { if (prof) { const long long now_ = clock64(); atomicAdd((unsigned long long*)&fa_prof[i], (unsigned long long)(now_ - tprev)); tprev = now_; } } while (0)
+#else
+#define FA_T(i) do { } while (0)
+#endif
 struct TrueTag { static constexpr bool value = true; };
 struct FalseTag { static constexpr bool value = false; };
 
@@ -171,8 +177,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       if (lane == 0) mbar_arrive(pv_empty);
     };
     // one key tile; TAIL is a compile-time flag so that full tiles carry no per-element masking instructions
+#ifdef FA_PROFILE
+    const bool prof = (warp == 2 && lane == 0);
+    long long tprev = clock64();
+#endif
     auto tile_step = [&](int j, auto tail_tag) {
       constexpr bool TAIL = decltype(tail_tag)::value;
+      FA_T(0);                                           // waited for S_j
       const int nvalid = klen - (j * FA_BK + hh * 64);   // valid keys among this thread's 64 (TAIL only; may be <= 0)
       // pass 1: maximum of this thread's 64 scores (two 32-column TMEM loads; registers are capped at 96/thread
       // so that two 320-thread CTAs fit an SM, hence S is re-read in pass 2 instead of kept live)
@@ -188,6 +199,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           else mx = fmaxf(mx, s[i]);
         }
       }
+      FA_T(1);                                           // pass 1
       // row maximum across the thread pair
       const __half mxh = __float2half_rn(mx);
       xch[hh * 128 + r] = mxh;
@@ -196,7 +208,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const float m_new = fmaxf(m_run, mx);              // finite: every visited tile holds >= 1 valid key
       const float alpha = mufu_ex2((m_run - m_new) * FA_LOG2E);
       const float mb = m_new * FA_LOG2E;
+      FA_T(2);                                           // exchange
       if (j > 0) take_pv(j - 1);                         // also proves the P buffer is free again
+      FA_T(3);                                           // PV_{j-1} wait + accumulate
       // pass 2: P = exp2(s*log2e - m*log2e) -> bf16 -> swizzled shared memory (packed FFMA2 + MUFU.EX2)
       const uint64_t l2e = pk2(FA_LOG2E, FA_LOG2E), nmb = pk2(-mb, -mb);
       uint64_t rs2 = pk2(0.f, 0.f);
@@ -226,6 +240,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
       float rs;
       { float r0, r1; upk2(rs2, r0, r1); rs = r0 + r1; }
+      FA_T(4);                                           // pass 2
       tc_fence_before();                                 // S fully read
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // P visible to the tensor-core (async) proxy
       __syncwarp();
@@ -233,6 +248,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       l_run = l_run * alpha + rs;
       m_run = m_new;
       alpha_prev = alpha;
+      FA_T(5);                                           // fences + arrive
     };
     for (int j = 0; j < n_tiles; ++j) {
       mbar_wait(s_full, j & 1);
@@ -267,6 +283,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)FA_TMEM_COLS) : "memory");
   }
 }
+
+#ifdef FA_PROFILE
+extern "C" int cst_debug_fa_prof(long long* host16, int reset) {
+  if (reset) { long long z[16] = {0}; cudaMemcpyToSymbol(fa_prof, z, sizeof(z)); return 0; }
+  cudaDeviceSynchronize();
+  return (int)cudaMemcpyFromSymbol(host16, fa_prof, sizeof(long long) * 16);
+}
+#endif
 
 int launch_attention_tc(const void* q, const void* k, const void* v, void* out, long long ldq, long long ldkv, long long ldo,
                         int B, int H, int n_q, int q_rows_per_seg, int n_kv, int kv_rows_per_seg,
