@@ -335,6 +335,9 @@ def main():
         real = p.lib
         p.lib = prof
         p.load_inputs(w, l)
+        # keep the GPU busy while the host enqueues this batch's ~350 launches, so that the CUDA-event brackets
+        # measure kernel execution and not host launch gaps (a graph replay has none either)
+        torch.cuda._sleep(int(3.5e7))
         p.run(eager=True)
         p.lib = real
     ksum = prof.summary()

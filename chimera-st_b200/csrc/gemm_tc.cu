@@ -308,8 +308,12 @@ int launch_gemm_tc(const cst_gemm_params& hp, const GemmDev& p, int nz, cudaStre
   // < 1.5 tiles per SM to 128x128 tiles raises the isolated GEMM rate (548 -> 572 TFLOP/s) but LOWERS end-to-end
   // throughput (34.0k -> 33.0k audio-s/s): concurrent lanes already fill the tails, so 256 stays the default
   // (CST_TC_BN=128 forces the small tile for experiments).
+  // Tiny problems (shared / memory layers, M <= ~1600 rows, < 0.5 tile per SM) run 2x faster in isolation with
+  // 128x64 tiles (shorter serial K chain, 4x more CTAs), but with stream lanes they already overlap other batches'
+  // kernels on the idle SMs and the end-to-end rate does not move (34.1k vs 33.8k audio-s/s): not enabled.
   static const int force_bn = [] { const char* e = getenv("CST_TC_BN"); return e ? atoi(e) : 0; }();
-  if (hp.N % 256 == 0 && force_bn != 128) return launch_tc<256>(hp, p, nz, st);
+  if (hp.N % 256 == 0 && force_bn != 128 && force_bn != 64) return launch_tc<256>(hp, p, nz, st);
+  if (force_bn == 64 && hp.N % 64 == 0) return launch_tc<64>(hp, p, nz, st);
   if (hp.N % 128 == 0) return launch_tc<128>(hp, p, nz, st);
   if (hp.N == 48) return launch_tc<48>(hp, p, nz, st);
   if (hp.N % 64 == 0) return launch_tc<64>(hp, p, nz, st);
