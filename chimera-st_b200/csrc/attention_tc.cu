@@ -4,9 +4,12 @@
 // resident per SM: while one CTA's softmax warps run (MUFU/FMA bound), the other CTA's MMAs use the tensor
 // pipe -- the overlap a single CTA would need double-buffered S/P/PV for.
 //   warp 0      : TMA producer (Q once; K_j,V_j into a 2-stage ring, 128B-swizzled)
-//   warp 1      : tcgen05.mma issuer.  S_j = Q K_j^T (M128 N128 K64, both operands K-major) into TMEM cols
-//                 0..127; PV_j = P_j V_j (M128 N64 K128; P from shared memory K-major, V as an MN-major B
-//                 operand straight from the TMA tile -- no transpose) into TMEM cols 128..191.
+//   warp 1      : tcgen05.mma issuer.  S_j = Q K_j^T (M128 N128 K64, both operands K-major) into TMEM buffer
+//                 j&1 (two 128-column buffers); PV_j = P_j V_j (M128 N64 K128; P from shared memory K-major, V as
+//                 an MN-major B operand straight from the TMA tile -- no transpose) into the first 64 columns of
+//                 the SAME buffer, which is dead once the softmax has turned S_j into P_j.  S_{j+1} is issued as
+//                 soon as PV_{j-1} has been consumed, i.e. in the middle of softmax j, so the next S is ready
+//                 when the softmax warps come back (256 TMEM columns per CTA, still two CTAs per SM).
 //   warps 2..9  : softmax.  Two warps per TMEM lane quarter: a query row is shared by a thread pair, each
 //                 owning 64 of the tile's 128 keys and 32 of the 64 output columns (row max exchanged through
 //                 shared memory + a 64-thread named barrier; partial row sums are added at the end).  tcgen05.ld
@@ -54,8 +57,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   // the V stage), so the producer can fetch K two tiles ahead although only two stages exist
   const uint32_t k_full = bars + 8, k_empty = k_full + 8 * FA_KS;
   const uint32_t v_full = k_empty + 8 * FA_KS, v_empty = v_full + 8 * FA_KS;
-  const uint32_t s_full = v_empty + 8 * FA_KS, s_empty = s_full + 8;
-  const uint32_t p_full = s_empty + 8, pv_full = p_full + 8, pv_empty = pv_full + 8;
+  const uint32_t s_full = v_empty + 8 * FA_KS;                     // [2]: one per S buffer
+  const uint32_t p_full = s_full + 16, pv_full = p_full + 8, pv_empty = pv_full + 8;
   const uint32_t tmem_slot = pv_empty + 8;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - base));
 
@@ -70,7 +73,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_init(k_full + 8 * s, 1); mbar_init(k_empty + 8 * s, 1);
       mbar_init(v_full + 8 * s, 1); mbar_init(v_empty + 8 * s, 1);
     }
-    mbar_init(s_full, 1); mbar_init(s_empty, FA_SM_WARPS);
+    mbar_init(s_full, 1); mbar_init(s_full + 8, 1);
     mbar_init(p_full, FA_SM_WARPS); mbar_init(pv_full, 1); mbar_init(pv_empty, FA_SM_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -83,7 +86,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
-  const uint32_t tS = tmem_base, tPV = tmem_base + FA_BK;       // S at cols 0..127, PV at 128..191
+  const uint32_t tS = tmem_base;                                // S_j (128 cols) then PV_j (64 cols) in buffer j&1 at col (j&1)*128
   pdl_wait();                                                   // prologue above overlaps the previous kernel
   int klen = kv_len ? kv_len[b] : n_kv;
   klen = klen < n_kv ? klen : n_kv;
@@ -115,8 +118,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       auto issue_pv = [&](int j) {
         const int st = j % FA_KS;
         mbar_wait(v_full + 8 * st, (j / FA_KS) & 1);
-        mbar_wait(p_full, j & 1);
-        mbar_wait(pv_empty, (j & 1) ^ 1);
+        mbar_wait(p_full, j & 1);                        // P_j published => S_j fully read: its buffer may take PV_j
         tc_fence_after();
         int keys = klen - j * FA_BK; keys = keys < FA_BK ? keys : FA_BK;
         const int k16 = (keys + 15) >> 4;
@@ -124,25 +126,28 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         for (int k = 0; k < k16; ++k) {
           const uint64_t pdesc = make_sw128_desc(sP + (k >> 2) * (FA_P_BYTES / 2) + (k & 3) * 32);
           const uint64_t vdesc = make_sw128_mn_desc(vbase + k * 2048);
-          tc_mma_bf16(tPV, pdesc, vdesc, idesc_pv, k != 0);
+          tc_mma_bf16(tS + (j & 1) * FA_BK, pdesc, vdesc, idesc_pv, k != 0);
         }
         tc_commit(pv_full);
         tc_commit(v_empty + 8 * st);
       };
-      mbar_wait(q_full, 0);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int st = j % FA_KS;
-        mbar_wait(k_full + 8 * st, (j / FA_KS) & 1);
-        mbar_wait(s_empty, (j & 1) ^ 1);                 // softmax finished reading S_{j-1}
+      auto issue_s = [&](int i) {
+        const int st = i % FA_KS;
+        mbar_wait(k_full + 8 * st, (i / FA_KS) & 1);
+        if (i >= 2) mbar_wait(pv_empty, i & 1);          // PV_{i-2} (same buffer) consumed: completion index i-2
         tc_fence_after();
         const uint64_t kdesc = make_sw128_desc(sK + st * FA_KV_BYTES);
 #pragma unroll
-        for (int k = 0; k < FA_D / 16; ++k) tc_mma_bf16(tS, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
-        tc_commit(s_full);
+        for (int k = 0; k < FA_D / 16; ++k) tc_mma_bf16(tS + (i & 1) * FA_BK, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
+        tc_commit(s_full + 8 * (i & 1));
         tc_commit(k_empty + 8 * st);
-        if (j > 0) issue_pv(j - 1);                      // P_{j-1} was published together with s_empty
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int j = 0; j < n_tiles; ++j) {
+        if (j + 1 < n_tiles) issue_s(j + 1);             // runs while the softmax warps are still on tile j
+        issue_pv(j);
       }
-      issue_pv(n_tiles - 1);
     }
     __syncwarp();
   } else {
@@ -153,22 +158,22 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
     // row-max exchange between the two threads of a row: fp16 slots [2 halves][128 rows] (512 B is all the shared
     // memory left under the two-CTAs-per-SM budget).  Both threads use max(fp16(own), fp16(partner)) -- any common
-    // reference point near the maximum is a valid softmax shift.  One slot set suffices: a thread cannot reach the
-    // next tile's write before its partner has read (S_{j+1} needs both warps' s_empty arrivals).
+    // reference point near the maximum is a valid softmax shift.  One slot set suffices: a second 64-thread barrier
+    // after the read keeps a fast thread from rewriting its slot before the partner has read it.
     __half* xch = reinterpret_cast<__half*>(smem_raw + (bars + 128 - base));
     float* lsum = reinterpret_cast<float*>(smem_raw + (sK - base));         // reused after the last MMA: partial row sums
     float o[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) o[i] = 0.f;
     float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
-    const uint32_t srow = tS + lane_off + hh * 64;
+    const uint32_t srow0 = tS + lane_off + hh * 64;
     const uint32_t prow = sP + hh * (FA_P_BYTES / 2) + r * 128;
-    const uint32_t pvrow = tPV + lane_off + hh * 32;
+    const uint32_t pvrow0 = tS + lane_off + hh * 32;
     auto take_pv = [&](int j) {                          // O = O * alpha_j + PV_j  (PV_j is relative to m_j)
       mbar_wait(pv_full, j & 1);
       tc_fence_after();
       float pv[32];
-      tmem_ld32(pvrow, pv);
+      tmem_ld32(pvrow0 + (j & 1) * FA_BK, pv);
       tmem_ld_wait();
 #pragma unroll
       for (int i = 0; i < 32; ++i) o[i] = fmaf(o[i], alpha_prev, pv[i]);
@@ -183,6 +188,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #endif
     auto tile_step = [&](int j, auto tail_tag) {
       constexpr bool TAIL = decltype(tail_tag)::value;
+      const uint32_t srow = srow0 + (j & 1) * FA_BK;
       FA_T(0);                                           // waited for S_j
       const int nvalid = klen - (j * FA_BK + hh * 64);   // valid keys among this thread's 64 (TAIL only; may be <= 0)
       // pass 1: maximum of this thread's 64 scores (two 32-column TMEM loads; registers are capped at 96/thread
@@ -205,6 +211,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       xch[hh * 128 + r] = mxh;
       asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
       mx = fmaxf(__half2float(mxh), __half2float(xch[(hh ^ 1) * 128 + r]));
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");   // partner has read: the slot may be rewritten next tile
       const float m_new = fmaxf(m_run, mx);              // finite: every visited tile holds >= 1 valid key
       const float alpha = mufu_ex2((m_run - m_new) * FA_LOG2E);
       const float mb = m_new * FA_LOG2E;
@@ -244,14 +251,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       tc_fence_before();                                 // S fully read
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // P visible to the tensor-core (async) proxy
       __syncwarp();
-      if (lane == 0) { mbar_arrive(s_empty); mbar_arrive(p_full); }
+      if (lane == 0) mbar_arrive(p_full);
       l_run = l_run * alpha + rs;
       m_run = m_new;
       alpha_prev = alpha;
       FA_T(5);                                           // fences + arrive
     };
     for (int j = 0; j < n_tiles; ++j) {
-      mbar_wait(s_full, j & 1);
+      mbar_wait(s_full + 8 * (j & 1), (j >> 1) & 1);
       tc_fence_after();
       if ((j + 1) * FA_BK > klen) tile_step(j, TrueTag{});
       else tile_step(j, FalseTag{});
