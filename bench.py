@@ -359,8 +359,20 @@ def main():
     else:
         peak, peak_src = 72.0, "nominal fp32 FFMA 148 SM x 128 lanes x 2 x 1.9 GHz (no measured fp32 peak)"
     step_kernel_s = sum(v["seconds"] for v in ksum.values())
+    # DRAM traffic per launch of the dominant kernel from the committed ncu capture (profiles/traffic_r01.json,
+    # same workload family: c3 batches); null for other workloads
+    traffic, traffic_src = None, None
+    try:
+        if args.workload == "c3":
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01.json")))
+            traffic = round(tj["kernels"][dom]["traffic_bytes_per_launch"])
+            traffic_src = "profiles/traffic_r01.json: " + tj["workload"]
+    except Exception:
+        pass
     roofline = {"bound": "tensor", "kernel": dom, "achieved": round(ach, 2), "peak": peak, "unit": "TFLOP/s",
-                "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
+                "frac": round(ach / peak, 4), "traffic": traffic, "traffic_unit": "bytes per launch (dram read+write, ncu)",
+                "traffic_source": traffic_src, "algorithmic_bytes_per_launch": round(kd["bytes"] / max(1, kd["launches"])),
+                "peak_source": peak_src,
                 "launches_per_step": kd["launches"], "share_of_kernel_time": round(kd["seconds"] / step_kernel_s, 3),
                 "by_kernel": {k: {"launches": v["launches"], "ms": round(v["seconds"] * 1e3, 3),
                                   "tflops": round(v["flops"] / v["seconds"] / 1e12, 2) if v["flops"] > 0 else None,
