@@ -33,6 +33,90 @@ template <int BN> struct TcCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
+// ---- lean tile epilogue: compile-time output dtype (0 f32, 1 bf16, 2 f16) and residual flag, alpha == 1, no
+// per-segment zeroing.  Everything that does not depend on the column chunk (row pointers, store predicates) is
+// resolved once per tile by the caller, so the inner loop is TMEM -> smem transpose -> packed math -> 128-bit stores
+// with no address arithmetic, dtype branches or mask tests per element.
+template <int BN, int ACT, int CD, bool RES>
+__device__ __forceinline__ void epi_tile_fast(const GemmDev& p, float* patch, uint32_t t_row, int nb, int lane, int chalf,
+                                              const float* bias, uint8_t* const (&cp)[8], const float* const (&rp)[8],
+                                              uint32_t st_mask) {
+  constexpr int NCH = (BN + 31) / 32, CH_PER = (NCH + 1) / 2;
+  constexpr int ES = CD == 0 ? 4 : 2;
+  const int lr = lane >> 3, lc = (lane & 7) * 4;
+#pragma unroll 1
+  for (int ch = chalf * CH_PER; ch < NCH && ch < (chalf + 1) * CH_PER; ++ch) {
+    const int c = ch * 32;
+    const int n = nb * BN + c + lc;
+    const bool col_ok = (c + lc < BN) && (n < p.N);
+    float acc[32];
+    if (BN - c >= 32) {
+      tmem_ld32(t_row + c, acc);
+    } else {
+      tmem_ld16(t_row + c, acc);
+#pragma unroll
+      for (int i = 16; i < 32; ++i) acc[i] = 0.f;
+    }
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias && col_ok) b4 = __ldg(reinterpret_cast<const float4*>(bias + n));
+    float4 res[RES ? 8 : 1];
+    if (RES) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (col_ok && ((st_mask >> i) & 1)) res[i] = *reinterpret_cast<const float4*>(rp[i] + n);
+      }
+    }
+    tmem_ld_wait();
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      *reinterpret_cast<float4*>(&patch[lane * TC_PATCH_LD + 4 * (i ^ (lane & 7))]) = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+    __syncwarp();
+    if (col_ok) {
+      const uint64_t b01 = pk2(b4.x, b4.y), b23 = pk2(b4.z, b4.w);
+#pragma unroll
+      for (int i0 = 0; i0 < 8; i0 += 4) {
+        float v[4][4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int rr = (i0 + u) * 4 + lr;
+          const float4 a4 = *reinterpret_cast<const float4*>(&patch[rr * TC_PATCH_LD + 4 * ((lc >> 2) ^ (rr & 7))]);
+          upk2(fadd2(pk2(a4.x, a4.y), b01), v[u][0], v[u][1]);
+          upk2(fadd2(pk2(a4.z, a4.w), b23), v[u][2], v[u][3]);
+        }
+        if (ACT == CST_ACT_GELU) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) { gelu2(v[u][0], v[u][1]); gelu2(v[u][2], v[u][3]); }
+        } else if (ACT == CST_ACT_RELU) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            v[u][0] = fmaxf(v[u][0], 0.f); v[u][1] = fmaxf(v[u][1], 0.f);
+            v[u][2] = fmaxf(v[u][2], 0.f); v[u][3] = fmaxf(v[u][3], 0.f);
+          }
+        }
+        if (RES) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            upk2(fadd2(pk2(v[u][0], v[u][1]), pk2(res[i0 + u].x, res[i0 + u].y)), v[u][0], v[u][1]);
+            upk2(fadd2(pk2(v[u][2], v[u][3]), pk2(res[i0 + u].z, res[i0 + u].w)), v[u][2], v[u][3]);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u;
+          if ((st_mask >> i) & 1) {
+            uint8_t* o = cp[i] + (size_t)n * ES;
+            if (CD == 0) *reinterpret_cast<float4*>(o) = make_float4(v[u][0], v[u][1], v[u][2], v[u][3]);
+            else if (CD == 1) *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16x2(v[u][0], v[u][1]), pack_bf16x2(v[u][2], v[u][3]));
+            else *reinterpret_cast<uint2*>(o) = make_uint2(pack_f16x2(v[u][0], v[u][1]), pack_f16x2(v[u][2], v[u][3]));
+          }
+        }
+      }
+    }
+  }
+}
+
 template <int BN, int ACT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -131,6 +215,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int lr = lane >> 3, lc = (lane & 7) * 4;             // row-contiguous domain: 4 rows x 8 float4 per pass
     const bool c_16 = p.c_dtype != CST_F32, c_f16 = p.c_dtype == CST_F16;
     const uint64_t alpha2 = pk2(p.alpha, p.alpha);
+    const bool fast = (ACT != CST_ACT_GLU) && p.alpha == 1.0f && p.seg_len == nullptr;
+    const int esz = c_16 ? 2 : 4;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int nb = tile % n_tiles; const int r = tile / n_tiles;
@@ -154,6 +240,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(tfull_bar + 8 * as, aph);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * Cfg::BN_PAD;
+      if (fast) {
+        uint8_t* cp[8];
+        const float* rp[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          cp[i] = reinterpret_cast<uint8_t*>(p.C) + crow[i] * esz;
+          rp[i] = p.residual + rrow[i];
+        }
+        if (p.residual) {
+          if (!c_16) epi_tile_fast<BN, ACT, 0, true>(p, patch, t_row, nb, lane, chalf, bias, cp, rp, st_mask);
+          else if (!c_f16) epi_tile_fast<BN, ACT, 1, true>(p, patch, t_row, nb, lane, chalf, bias, cp, rp, st_mask);
+          else epi_tile_fast<BN, ACT, 2, true>(p, patch, t_row, nb, lane, chalf, bias, cp, rp, st_mask);
+        } else {
+          if (!c_16) epi_tile_fast<BN, ACT, 0, false>(p, patch, t_row, nb, lane, chalf, bias, cp, rp, st_mask);
+          else if (!c_f16) epi_tile_fast<BN, ACT, 1, false>(p, patch, t_row, nb, lane, chalf, bias, cp, rp, st_mask);
+          else epi_tile_fast<BN, ACT, 2, false>(p, patch, t_row, nb, lane, chalf, bias, cp, rp, st_mask);
+        }
+      } else
 #pragma unroll 1
       for (int ch = chalf * CH_PER; ch < NCH && ch < (chalf + 1) * CH_PER; ++ch) {
         const int c = ch * 32;
