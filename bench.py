@@ -157,7 +157,7 @@ class LaunchProfiler:
             rows, C = a[8], a[9]
             by = rows * C * (4 + (4 if a[4] else 0) + ((2 if a[6] == 1 else 4) if a[5] else 0))
             return ("layernorm", 0.0, by, "rows%d C%d" % (rows, C))
-        if name == "cst_conv0_apply":
+        if name in ("cst_conv0_apply", "cst_conv0_apply_tc"):
             B, L, odt, rps = a[1], a[2], a[6], a[7]
             return ("conv0_gn_gelu", 2.0 * B * ((L - 10) // 5 + 1) * 512 * 10, B * rps * 512 * (2 if odt in (1, 2) else 4) + 4 * B * L,
                     "B%d L%d" % (B, L))

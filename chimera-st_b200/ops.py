@@ -31,8 +31,9 @@ def frame_lengths(src_lengths, Lw):
     return w2v, sub, l64, mask.bool()
 
 
-def conv0_gn_gelu(wave, w, gamma, beta, out_dtype=torch.float32, rows_per_seg=None):
-    """wave [B,L] f32 -> channels-last [B, rows_per_seg, 512]; frames >= T0 are zero."""
+def conv0_gn_gelu(wave, w, gamma, beta, out_dtype=torch.float32, rows_per_seg=None, tensor_core=False):
+    """wave [B,L] f32 -> channels-last [B, rows_per_seg, 512]; frames >= T0 are zero.
+    tensor_core: run the convolution on tcgen05 (16-bit outputs only; 3-term fp16 split of x and w)."""
     _cuda(wave, w, gamma, beta)
     B, Lw = wave.shape
     T0 = (Lw - 10) // 5 + 1
@@ -45,6 +46,13 @@ def conv0_gn_gelu(wave, w, gamma, beta, out_dtype=torch.float32, rows_per_seg=No
     w = w.reshape(512, 10).contiguous()
     L.check(lib.cst_conv0_stats(wave.data_ptr(), B, Lw, w.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
                                 ss.data_ptr(), ws.data_ptr(), L.stream_ptr()))
+    if tensor_core:
+        hi = w.to(torch.float16)
+        w16 = torch.zeros(512, 64, dtype=torch.float16, device=dev)
+        w16[:, 0:10], w16[:, 10:20], w16[:, 20:30] = hi, hi, (w - hi.float()).to(torch.float16)
+        L.check(lib.cst_conv0_apply_tc(wave.data_ptr(), B, Lw, w16.data_ptr(), ss.data_ptr(), out.data_ptr(),
+                                       L.DT[out_dtype], rps, L.stream_ptr()))
+        return out, ss
     L.check(lib.cst_conv0_apply(wave.data_ptr(), B, Lw, w.data_ptr(), ss.data_ptr(), out.data_ptr(),
                                 L.DT[out_dtype], rps, L.stream_ptr()))
     return out, ss

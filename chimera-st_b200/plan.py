@@ -80,6 +80,7 @@ class EncoderPlan:
         self.graph = None
         self.launches = 0
         self.use_resident_posconv = os.environ.get("CST_POSCONV_RESIDENT", "1") != "0"
+        self.use_conv0_tc = os.environ.get("CST_CONV0_TC", "1") != "0"
         self.arena = arena if arena is not None else Arena(self.dev)
         f32, i32, i64, u8, f64 = torch.float32, torch.int32, torch.int64, torch.uint8, torch.float64
         R, R2, RM = B * g.T6a, B * g.T2a, B * M
@@ -177,8 +178,12 @@ class EncoderPlan:
                                       self.frame_mask.data_ptr(), self.st))
         L.check(lib.cst_conv0_stats(self.wave.data_ptr(), B, g.L, P["conv0_w"].data_ptr(), P["gn_g"].data_ptr(),
                                     P["gn_b"].data_ptr(), self.scale_shift.data_ptr(), self.stats_ws.data_ptr(), self.st))
-        L.check(lib.cst_conv0_apply(self.wave.data_ptr(), B, g.L, P["conv0_w"].data_ptr(), self.scale_shift.data_ptr(),
-                                    self.cbuf[0].data_ptr(), L.DT[self.conv_dt], g.Ta[0], self.st))
+        if self.conv_dt != torch.float32 and self.use_conv0_tc:
+            L.check(lib.cst_conv0_apply_tc(self.wave.data_ptr(), B, g.L, P["conv0_w16"].data_ptr(), self.scale_shift.data_ptr(),
+                                           self.cbuf[0].data_ptr(), L.DT[self.conv_dt], g.Ta[0], self.st))
+        else:
+            L.check(lib.cst_conv0_apply(self.wave.data_ptr(), B, g.L, P["conv0_w"].data_ptr(), self.scale_shift.data_ptr(),
+                                        self.cbuf[0].data_ptr(), L.DT[self.conv_dt], g.Ta[0], self.st))
         self.launches += 4
         for i in range(1, 7):
             src = self.cbuf[(i - 1) & 1]

@@ -5,6 +5,7 @@ weight-norm forms of the pos-conv are accepted: `pos_conv.0.weight_g/_v` (checkp
 `pos_conv.0.weight` left by make_generation_fast_ (fairseq/models/fairseq_model.py:175-182).
 
 Layout rules (all exact re-arrangements, no arithmetic except the folds noted):
+  * conv0 (16-bit mode): 3-term fp16 split of the [512,10] kernel for the tensor-core conv0 (see cst_conv0_apply_tc).
   * conv kernels [Cout, Cin, k] -> [Cout, k*Cin] (tap-major) so a window of channels-last frames is one
     contiguous K run (implicit GEMM).
   * q projection and bias are multiplied by head_dim**-0.5 = 1/8 (exact power of two; the reference
@@ -43,6 +44,14 @@ def prepare(state_dict, device, act_dtype, conv_dtype=None):
     P = {}
     fe = W + "feature_extractor.conv_layers."
     P["conv0_w"] = f32(sd[fe + "0.0.weight"].reshape(512, 10))
+    if act_dtype != torch.float32:
+        # tcgen05 conv0 (cst_conv0_apply_tc): fp16 [512, 64] rows [hi | hi | lo | 0...], hi = fp16(w), lo = fp16(w - hi)
+        w0 = P["conv0_w"]
+        hi = w0.to(torch.float16)
+        lo = (w0 - hi.float()).to(torch.float16)
+        w16 = torch.zeros(512, 64, dtype=torch.float16, device=device)
+        w16[:, 0:10], w16[:, 10:20], w16[:, 20:30] = hi, hi, lo
+        P["conv0_w16"] = w16.contiguous()
     P["gn_g"], P["gn_b"] = f32(sd[fe + "0.2.weight"]), f32(sd[fe + "0.2.bias"])
     for i in range(1, len(CONV_LAYERS)):
         w = sd[fe + f"{i}.0.weight"]                       # [512, 512, k]

@@ -58,6 +58,14 @@ int cst_conv0_stats(const float* wave, int B, int L, const float* w, const float
 int cst_conv0_apply(const float* wave, int B, int L, const float* w, const float* scale_shift,
                     void* out, int out_dtype, int rows_per_seg, void* stream);
 
+/* ---- a1 (16-bit mode): the same stage with the convolution on tcgen05 (3-term fp16 split: fp32-level accuracy)
+ * Replaces: as cst_conv0_apply, for out_dtype CST_F16 / CST_BF16.  w16: fp16 [512, 64], row c =
+ * [ hi(w[c,0..9]) | hi(w[c,0..9]) | lo(w[c,0..9]) | 0 ... ] with hi = fp16(w), lo = fp16(w - hi); the kernel builds
+ * the matching activation rows [ hi(x) | lo(x) | hi(x) | 0 0 ] so that x.w ~= xh.wh + xl.wh + xh.wl.  The epilogue
+ * (scale/shift, exact-erf GELU, pack) runs in the accumulator layout and is written by bulk tensor stores. */
+int cst_conv0_apply_tc(const float* wave, int B, int L, const void* w16, const float* scale_shift,
+                       void* out, int out_dtype, int rows_per_seg, void* stream);
+
 /* ---- GEMM with fused epilogue: the conv stack (implicit GEMM), every projection and FFN ------------
  * Replaces: nn.Conv1d of blocks 1-6 (wav2vec2.py:707,733-734), post_extract_proj (wav2vec2.py:550-551),
  * the grouped pos_conv (wav2vec2.py:773-786,823-825), F.multi_head_attention_forward's in/out

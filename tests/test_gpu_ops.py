@@ -63,6 +63,19 @@ def test_conv0_groupnorm_gelu(lens):
     outb, _ = ops().conv0_gn_gelu(wave.to(DEV), sd[P + "0.0.weight"].to(DEV), sd[P + "0.2.weight"].to(DEV),
                                   sd[P + "0.2.bias"].to(DEV), torch.bfloat16, rps)
     assert rel_l2(outb.cpu().float()[:, :T0], ref) < 4e-3      # bf16 rounding of the stored value only
+    # tensor-core conv0 (3-term fp16 split): must agree with the CUDA-core kernel to the output rounding, zero the tail
+    for dt, tol in ((torch.float16, 5e-4), (torch.bfloat16, 4e-3)):
+        outc, _ = ops().conv0_gn_gelu(wave.to(DEV), sd[P + "0.0.weight"].to(DEV), sd[P + "0.2.weight"].to(DEV),
+                                      sd[P + "0.2.bias"].to(DEV), dt, rps)
+        outt, _ = ops().conv0_gn_gelu(wave.to(DEV), sd[P + "0.0.weight"].to(DEV), sd[P + "0.2.weight"].to(DEV),
+                                      sd[P + "0.2.bias"].to(DEV), dt, rps, tensor_core=True)
+        outt = outt.cpu().float()
+        assert rel_l2(outt[:, :T0], ref) < tol
+        assert float(outt[:, T0:].abs().max()) == 0.0 if rps > T0 else True
+        # same value before rounding up to ~1e-6: at most a 1-ulp flip on a tiny fraction of the outputs
+        diff = (outt - outc.cpu().float()).abs()
+        assert float((diff > 0).float().mean()) < 0.02
+        assert rel_l2(outt[:, :T0], outc.cpu().float()[:, :T0]) < (2e-4 if dt == torch.float16 else 1.5e-3)
 
 
 def _ref_gemm(A, W, bias, act, alpha, residual):
