@@ -59,10 +59,13 @@ __device__ int tc_dbg_flags;      // timing experiments: 1 skip global stores, 2
 // through TMEM load -> smem transpose -> math -> store.  So everything with a long latency is issued one chunk ahead:
 // the tcgen05.ld of chunk c+1 goes out as soon as chunk c's registers are parked in the patch, and the bias / residual
 // loads of chunk c+1 are in flight while chunk c's math runs.
-template <int BN, int ACT, int CD, bool RES, typename WaitF>
+// BST (fp32 output, identity row mapping): the finished values go back into the patch -- whose XOR layout IS the
+// 128-byte TMA swizzle -- and one lane bulk-stores the 32x32 block, instead of eight STG per lane and chunk.
+template <int BN, int ACT, int CD, bool RES, bool BST, typename WaitF>
 __device__ __forceinline__ void epi_tile_fast(const GemmDev& p, float* patch, uint32_t t_row, int nb, int lane, int chalf,
                                               const float* bias, uint8_t* c_base, const float* r_base, const int (&orow)[8],
-                                              uint32_t st_mask, WaitF wait_acc) {
+                                              uint32_t st_mask, WaitF wait_acc, const CUtensorMap* tmC = nullptr, int row0 = 0) {
+  static_assert(!BST || CD == 0, "in-place bulk store: fp32 output only");
   constexpr int NCH = (BN + 31) / 32, CH_PER = (NCH + 1) / 2;
   constexpr int ES = CD == 0 ? 4 : 2;
   const int lr = lane >> 3, lc = (lane & 7) * 4;
@@ -108,6 +111,7 @@ __device__ __forceinline__ void epi_tile_fast(const GemmDev& p, float* patch, ui
     const int n = col_of(ch);
     const bool col_ok = col_ok_of(ch);
     tmem_ld_wait();
+    if (BST) { if (lane == 0) bulk_wait_read<0>(); }           // the previous chunk's bulk store has read the patch
     __syncwarp();                                              // previous chunk's readers are done with the patch
     if (!TC_DBG(4)) {
 #pragma unroll
@@ -153,13 +157,24 @@ __device__ __forceinline__ void epi_tile_fast(const GemmDev& p, float* patch, ui
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int i = i0 + u;
-          if (((st_mask >> i) & 1) && !TC_DBG(1)) {
+          if (BST) {
+            const int rr = i * 4 + lr;
+            *reinterpret_cast<float4*>(&patch[rr * TC_PATCH_LD + 4 * ((lc >> 2) ^ (rr & 7))]) = make_float4(v[u][0], v[u][1], v[u][2], v[u][3]);
+          } else if (((st_mask >> i) & 1) && !TC_DBG(1)) {
             uint8_t* o = c_base + ((long long)orow[i] * p.ldc + n) * ES;
             if (CD == 0) *reinterpret_cast<float4*>(o) = make_float4(v[u][0], v[u][1], v[u][2], v[u][3]);
             else if (CD == 1) *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16x2(v[u][0], v[u][1]), pack_bf16x2(v[u][2], v[u][3]));
             else *reinterpret_cast<uint2*>(o) = make_uint2(pack_f16x2(v[u][0], v[u][1]), pack_f16x2(v[u][2], v[u][3]));
           }
         }
+      }
+    }
+    if (BST) {                                                 // (all columns of a BN % 64 == 0 tile are valid)
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(tmC, smem_u32(patch), nb * BN + ch * 32, row0);
+        bulk_commit();
       }
     }
     b_cur = b_nxt;
@@ -240,9 +255,13 @@ __device__ __forceinline__ void epi_tile_bulk(const GemmDev& p, const CUtensorMa
 // accumulator stage is complete (called after the row bookkeeping so that work overlaps the wait).
 template <int BN, int ACT, typename WaitF, typename ReleaseF>
 __device__ __forceinline__ void epi_tile(const GemmDev& p, const CUtensorMap* tmC, int bulk, uint32_t& seq, float* patch, uint32_t t_row,
-                                         int row_base, int nb, int zo, int zi, int lane, int chalf, WaitF wait_acc, ReleaseF release_acc) {
+                                         int row_base, int nb, int zo, int zi, int lane, int chalf, WaitF wait_acc, ReleaseF release_acc,
+                                         int next_row_base = -1, int next_nb = 0) {
+  // (Tried: prefetch.global.L2 of the NEXT tile's residual rows from here -- out-proj 61.4 -> 63.5 us, fc2 103 -> 109 us
+  // isolated; the residual fetch is not what holds these two GEMMs back, so the hook is unused.)
+  (void)next_row_base; (void)next_nb;
   if constexpr (BN % 64 == 0 && ACT != CST_ACT_GLU) {
-    if (bulk) {
+    if (bulk == 1) {
       const uint32_t stage_s = smem_u32(patch);
       if (p.c_dtype == CST_F32) epi_tile_bulk<BN, ACT, 0>(p, tmC, stage_s, seq, t_row, row_base, nb, lane, chalf, p.bias, wait_acc, release_acc);
       else if (p.c_dtype == CST_BF16) epi_tile_bulk<BN, ACT, 1>(p, tmC, stage_s, seq, t_row, row_base, nb, lane, chalf, p.bias, wait_acc, release_acc);
@@ -286,13 +305,20 @@ __device__ __forceinline__ void epi_tile(const GemmDev& p, const CUtensorMap* tm
     uint8_t* c_base = reinterpret_cast<uint8_t*>(p.C) + c_off * esz;
     const float* r_base = p.residual + r_off;
     if (p.residual) {
-      if (!c_16) epi_tile_fast<BN, ACT, 0, true>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc);
-      else if (!c_f16) epi_tile_fast<BN, ACT, 1, true>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc);
-      else epi_tile_fast<BN, ACT, 2, true>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc);
+      if (!c_16) {
+        if constexpr (BN % 64 == 0) {
+          if (bulk == 2) epi_tile_fast<BN, ACT, 0, true, true>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc, tmC, row_base);
+          else epi_tile_fast<BN, ACT, 0, true, false>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc);
+        } else {
+          epi_tile_fast<BN, ACT, 0, true, false>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc);
+        }
+      }
+      else if (!c_f16) epi_tile_fast<BN, ACT, 1, true, false>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc);
+      else epi_tile_fast<BN, ACT, 2, true, false>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc);
     } else {
-      if (!c_16) epi_tile_fast<BN, ACT, 0, false>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc);
-      else if (!c_f16) epi_tile_fast<BN, ACT, 1, false>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc);
-      else epi_tile_fast<BN, ACT, 2, false>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc);
+      if (!c_16) epi_tile_fast<BN, ACT, 0, false, false>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc);
+      else if (!c_f16) epi_tile_fast<BN, ACT, 1, false, false>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc);
+      else epi_tile_fast<BN, ACT, 2, false, false>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc);
     }
   } else {
   wait_acc();
@@ -496,9 +522,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int zo = z / p.nb_inner, zi = z - zo * p.nb_inner;
       const int as = it & 1; const uint32_t aph = (it >> 1) & 1;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * Cfg::BN_PAD;
+      const int nxt = tile + gridDim.x;
+      int nrow = -1, nnb = 0;
+      if (nxt < total_tiles) { nnb = nxt % n_tiles; nrow = ((nxt / n_tiles) % m_tiles) * TC_BM + q * 32; }
       epi_tile<BN, ACT>(p, &tmC, bulk, seq, patch, t_row, mb * TC_BM + q * 32, nb, zo, zi, lane, chalf,
                         [&] { mbar_wait(tfull_bar + 8 * as, aph); tc_fence_after(); },
-                        [&] { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(tempty_bar + 8 * as); });
+                        [&] { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(tempty_bar + 8 * as); }, nrow, nnb);
     }
     if (bulk && lane == 0) bulk_wait_all<0>();     // staging buffers are read, and the stores complete, before exit
   }
@@ -514,14 +543,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // The bulk-store epilogue applies when output row == GEMM row (no segment remap / padding rows / zeroing), there is no
 // residual, GLU or alpha, and the problem is not batched; C rows beyond M are clipped by the tensor map.
 // CST_TC_BULK=0 keeps the register-path epilogue (A/B experiments).
-static bool bulk_store_ok(const cst_gemm_params& hp, int nz, int bn) {
-  static const int enabled = [] { const char* e = getenv("CST_TC_BULK"); return e ? atoi(e) : 1; }();
+// Returns 0 (register-path stores), 1 (bulk epilogue) or 2 (fp32 + residual: register path, in-place staging, bulk store;
+// the residual must not alias a different row of C, which the identity mapping guarantees).  CST_TC_BULK: bit 0 enables
+// mode 1, bit 1 mode 2 (default 3).
+static int bulk_store_ok(const cst_gemm_params& hp, int nz, int bn) {
+  static const int enabled = [] { const char* e = getenv("CST_TC_BULK"); return e ? atoi(e) : 3; }();
   const int esz = hp.c_dtype == CST_F32 ? 4 : 2;
-  return enabled && nz == 1 && bn % 64 == 0 && hp.act != CST_ACT_GLU && hp.alpha == 1.0f && hp.residual == nullptr &&
+  const bool ident = nz == 1 && bn % 64 == 0 && hp.act != CST_ACT_GLU && hp.alpha == 1.0f &&
          hp.seg_len == nullptr && hp.out_row_off == 0 && hp.out_rows_per_seg == hp.rows_per_seg &&
          hp.seg_rows_valid >= hp.rows_per_seg && hp.N % bn == 0 && ((uintptr_t)hp.C % 16) == 0 && (hp.ldc * esz) % 16 == 0;
+  if (!ident) return 0;
+  if (hp.residual == nullptr) return (enabled & 1) ? 1 : 0;
+  return ((enabled & 2) && hp.c_dtype == CST_F32) ? 2 : 0;
 }
-static int make_c_map(CUtensorMap* tmC, const cst_gemm_params& hp, bool bulk) {
+static int make_c_map(CUtensorMap* tmC, const cst_gemm_params& hp, int bulk) {
   if (!bulk) { memset(tmC, 0, sizeof(*tmC)); return CST_OK; }
   const int esz = hp.c_dtype == CST_F32 ? 4 : 2;
   return make_map_2d(tmC, hp.C, hp.N, hp.M, hp.ldc, 32, 32, esz, esz == 4 ? 128 : 64);
@@ -548,7 +583,7 @@ static int launch_tc_act(const cst_gemm_params& hp, const GemmDev& p, int nz, cu
   if (rc) return rc;
   rc = make_map_2d(&tmB, hp.W, hp.K, (long long)hp.nb_inner * hp.N, hp.K, TC_BK, BN);
   if (rc) return rc;
-  const bool bulk = bulk_store_ok(hp, nz, BN);
+  const int bulk = bulk_store_ok(hp, nz, BN);
   CUtensorMap tmC;
   rc = make_c_map(&tmC, hp, bulk);
   if (rc) return rc;
@@ -559,7 +594,7 @@ static int launch_tc_act(const cst_gemm_params& hp, const GemmDev& p, int nz, cu
   CST_CHECK_CUDA(cudaGetDevice(&dev));
   CST_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = (int)(total < sms ? total : sms);
-  CST_CHECK_CUDA(launch_k(gemm_tc_kernel<BN, ACT>, dim3(grid), dim3(TC_THREADS), Cfg::SMEM_BYTES, st, tmA, tmB, tmC, p, m_tiles, n_tiles, (int)total, a_wrap, hp.ab_dtype == CST_F16 ? 1 : 0, bulk ? 1 : 0));
+  CST_CHECK_CUDA(launch_k(gemm_tc_kernel<BN, ACT>, dim3(grid), dim3(TC_THREADS), Cfg::SMEM_BYTES, st, tmA, tmB, tmC, p, m_tiles, n_tiles, (int)total, a_wrap, hp.ab_dtype == CST_F16 ? 1 : 0, bulk));
   return CST_OK;
 }
 
@@ -773,7 +808,7 @@ static int launch_tc_pair_act(const cst_gemm_params& hp, const GemmDev& p, int n
   if (rc) return rc;
   rc = make_map_2d(&tmB, hp.W, hp.K, (long long)hp.nb_inner * hp.N, hp.K, TC_BK, 128);
   if (rc) return rc;
-  const bool bulk = bulk_store_ok(hp, nz, 256);
+  const int bulk = bulk_store_ok(hp, nz, 256);
   CUtensorMap tmC;
   rc = make_c_map(&tmC, hp, bulk);
   if (rc) return rc;
@@ -786,7 +821,7 @@ static int launch_tc_pair_act(const cst_gemm_params& hp, const GemmDev& p, int n
   if (const char* e = getenv("CST_TC_SKIP")) a_wrap |= atoi(e) & 12;
 #endif
   CST_CHECK_CUDA(launch_k(gemm_tc_pair_kernel<ACT>, dim3(2 * pairs), dim3(TC_THREADS), TC2_SMEM_BYTES, st, tmA, tmB, tmC, p, m_tiles, n_tiles,
-                          (int)total, a_wrap, hp.ab_dtype == CST_F16 ? 1 : 0, bulk ? 1 : 0));
+                          (int)total, a_wrap, hp.ab_dtype == CST_F16 ? 1 : 0, bulk));
   return CST_OK;
 }
 

@@ -11,8 +11,8 @@ from chimera_st_b200 import ops, _lib as L  # noqa: E402
 SHAPES = [  # M, N, K, act, out dtype, note
     (24000, 2304, 768, L.ACT_NONE, torch.bfloat16, "qkv"),
     (24000, 3072, 768, L.ACT_GELU, torch.bfloat16, "fc1"),
-    (24000, 768, 3072, L.ACT_NONE, torch.float32, "fc2"),
-    (24000, 768, 768, L.ACT_NONE, torch.float32, "out-proj"),
+    (24000, 768, 3072, L.ACT_NONE, torch.float32, "fc2 +res"),
+    (24000, 768, 768, L.ACT_NONE, torch.float32, "out-proj +res"),
     (383000, 512, 1536, L.ACT_GELU, torch.bfloat16, "conv2-like (dense A)"),
     (6000, 2304, 768, L.ACT_NONE, torch.bfloat16, "qkv small batch"),
 ]
@@ -27,14 +27,15 @@ def main():
         A = (torch.randn(M, K, generator=g) * 0.5).to(torch.bfloat16).cuda()
         W = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(torch.bfloat16).cuda()
         b = torch.randn(N, generator=g).cuda()
+        R = torch.randn(M, N, generator=g).cuda() if "+res" in note else None
         for _ in range(3):
-            out = ops.linear(A, W, b, act=act, out_dtype=od)
+            out = ops.linear(A, W, b, act=act, residual=R, out_dtype=od)
         ts = []
         for _ in range(10):
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            out = ops.linear(A, W, b, act=act, out_dtype=od)
+            out = ops.linear(A, W, b, act=act, residual=R, out_dtype=od)
             e1.record()
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
@@ -44,6 +45,8 @@ def main():
         ref = A[idx].float() @ W.float().T + b
         if act == L.ACT_GELU:
             ref = torch.nn.functional.gelu(ref)
+        if R is not None:
+            ref = ref + R[idx]
         err = float((out[idx].float() - ref).norm() / ref.norm())
         print(f"{note:24s} M={M} N={N} K={K}: {ms*1e3:8.1f} us  {2.0*M*N*K/ms/1e9:7.1f} TFLOP/s  rel_err={err:.2e}", flush=True)
 
