@@ -7,7 +7,7 @@
 // (the dropped xl.wl term is ~2^-22 relative).  K = 32 -> two K=16 MMAs per 256 output channels; the 128 x 512 fp32
 // accumulator fills tensor memory as two 256-column stages, so the MMAs of frame tile i+1 / stage h start as soon as
 // stage h of tile i is drained.  What is left on the CUDA cores is the part that bounds the kernel: y*scale+shift,
-// exact-erf GELU (2 MUFU per output) and the fp16/bf16 pack -- done in the accumulator's layout (lane = frame), staged
+// erf GELU (one MUFU per output, common.cuh gelu2) and the fp16/bf16 pack -- done in the accumulator's layout (lane = frame), staged
 // through swizzled shared memory and written by the TMA engine (3-D map [B, rows_per_seg, 512]: the frame axis clips
 // the last tile, frames T0 <= t < rows_per_seg are written as zeros, like conv0.cu).
 //
@@ -146,6 +146,7 @@ conv0_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         cur_b = b;
       }
       const bool live = t0 + q * 32 + lane < T0;
+      const bool all_live = __all_sync(0xffffffffu, live);       // only an utterance's last tile has dead frames
 #pragma unroll 1
       for (int h = 0; h < 2; ++h) {
         mbar_wait(t_full + 8 * h, (uint32_t)(i & 1));
@@ -174,14 +175,16 @@ conv0_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
           const uint32_t buf = stage_s + (seq & 1u) * 2048u;
           if (lane == 0) bulk_wait_read<1>();
           __syncwarp();
+          if (!all_live && !live) {                              // warp-divergent only in an utterance's last tile
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = 0.f;
+          }
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             uint32_t wv[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float lo = live ? v[8 * c + 2 * k] : 0.f, hi = live ? v[8 * c + 2 * k + 1] : 0.f;
-              wv[k] = OUT_F16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi);
-            }
+            for (int k = 0; k < 4; ++k)
+              wv[k] = OUT_F16 ? pack_f16x2(v[8 * c + 2 * k], v[8 * c + 2 * k + 1]) : pack_bf16x2(v[8 * c + 2 * k], v[8 * c + 2 * k + 1]);
             sts128(buf + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4), wv[0], wv[1], wv[2], wv[3]);
           }
           fence_async_smem();
