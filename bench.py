@@ -151,7 +151,7 @@ class LaunchProfiler:
                     "M%d N%d K%d z%d act%d" % (p.M, p.N, p.K, nz, p.act))
         if name == "cst_attention":
             dtype, B, H, n_q, n_kv = a[4], a[8], a[9], a[10], a[12]
-            kind = "attention_tc_bf16" if (dtype == 1 and n_q > 64) else "attention_simt"
+            kind = "attention_tc_bf16" if (dtype == 1 and n_q > 64) else ("memory_attention" if (n_q <= 64 and n_kv <= 2048) else "attention_simt")
             return (kind, 4.0 * B * H * n_q * n_kv * 64, 0, "B%d H%d q%d kv%d" % (B, H, n_q, n_kv))
         if name == "cst_layernorm":
             rows, C = a[8], a[9]

@@ -136,6 +136,141 @@ __global__ void __launch_bounds__(256) attention_kernel(const T* __restrict__ q,
     store4(ob + (long long)r * ldo, make_float4(o[a][0] * inv, o[a][1] * inv, o[a][2] * inv, o[a][3] * inv));
   }
 }
+// ---- memory cross-attention: M learned queries (M = 16 / 64, w2v2_transformer_interlingua.py:262-274) over ALL key rows ----
+// The generic kernel above tiles 64 queries x 64 keys; with 16 queries three quarters of every tile is padding and
+// the key loop is a serial chain of small tiles (35-45 us per call, measured).  Here one CTA owns (utterance, head,
+// block of 16 queries) and the whole key axis at once:
+//   1. thread = key row: its 64-dim K row goes to registers once and meets the 16 queries (shared memory, broadcast)
+//      -> 16 scores per thread, written to S[16][n_kv] in shared memory;
+//   2. warp = query row (2 rows per warp): max / exp / sum over the key axis with shuffles (fp32, expf);
+//   3. thread = (query, 4 output dims): P[m][:] . V[:, d] with V rows read once per CTA through L1.
+// Keys beyond kv_len[b] are masked (the memory stage passes no mask: the reference hands its layers an all-False
+// key-padding mask there).  Scores live in dynamic shared memory: n_kv <= MA_MAX_KV, else the generic kernel runs.
+constexpr int MA_Q = 16, MA_THREADS = 256, MA_MAX_KV = 2048, MA_VCH = 64;
+
+template <typename T>
+__global__ void __launch_bounds__(MA_THREADS) memory_attention_kernel(const T* __restrict__ q, const T* __restrict__ k,
+                                                                      const T* __restrict__ v, T* __restrict__ out,
+                                                                      long long ldq, long long ldkv, long long ldo,
+                                                                      int n_q, int q_rows_per_seg, int n_kv, int kv_rows_per_seg,
+                                                                      const int32_t* __restrict__ kv_len) {
+  extern __shared__ float sm[];
+  float* Qs = sm;                          // [16][64]
+  float* inv_l = sm + MA_Q * AT_D;         // [16]
+  float* Vs = inv_l + MA_Q;                // [64 key rows][64] staging for step 3
+  float* S = Vs + MA_VCH * AT_D;           // [16][n_kv_pad]
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * MA_Q;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ldS = (n_kv + 3) & ~3;
+  int klen = kv_len ? kv_len[b] : n_kv;
+  if (klen > n_kv) klen = n_kv;
+  const T* qb = q + ((long long)b * q_rows_per_seg) * ldq + h * AT_D;
+  const T* kb = k + ((long long)b * kv_rows_per_seg) * ldkv + h * AT_D;
+  const T* vb = v + ((long long)b * kv_rows_per_seg) * ldkv + h * AT_D;
+  {
+    const int m = tid >> 4, d = (tid & 15) * 4;                  // 256 threads = 16 rows x 16 float4
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q0 + m < n_q) t = load4(qb + (long long)(q0 + m) * ldq + d);
+    *reinterpret_cast<float4*>(&Qs[m * AT_D + d]) = t;
+  }
+  __syncthreads();
+  // 1. scores
+  for (int j = tid; j < n_kv; j += MA_THREADS) {
+    float sc[MA_Q];
+#pragma unroll
+    for (int m = 0; m < MA_Q; ++m) sc[m] = 0.f;
+    if (j < klen) {
+      const T* kr = kb + (long long)j * ldkv;
+#pragma unroll
+      for (int d0 = 0; d0 < AT_D; d0 += 16) {                    // 16 dims of the key row at a time (register budget)
+        float4 kk[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) kk[i] = load4(kr + d0 + 4 * i);
+#pragma unroll
+        for (int m = 0; m < MA_Q; ++m) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 qq = *reinterpret_cast<const float4*>(&Qs[m * AT_D + d0 + 4 * i]);   // same address in every lane
+            sc[m] = fmaf(qq.x, kk[i].x, fmaf(qq.y, kk[i].y, fmaf(qq.z, kk[i].z, fmaf(qq.w, kk[i].w, sc[m]))));
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int m = 0; m < MA_Q; ++m) sc[m] = -INFINITY;
+    }
+#pragma unroll
+    for (int m = 0; m < MA_Q; ++m) S[m * ldS + j] = sc[m];
+  }
+  __syncthreads();
+  // 2. softmax over the key axis, two query rows per warp
+#pragma unroll
+  for (int mm = 0; mm < 2; ++mm) {
+    const int m = warp * 2 + mm;
+    float* row = S + m * ldS;
+    float mx = -INFINITY;
+    for (int j = lane; j < n_kv; j += 32) mx = fmaxf(mx, row[j]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < n_kv; j += 32) {
+      const float e = (mx == -INFINITY) ? 0.f : expf(row[j] - mx);
+      row[j] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) inv_l[m] = sum > 0.f ? 1.0f / sum : 0.f;
+  }
+  __syncthreads();
+  // 3. P V: thread = (query m, dims d..d+3).  V is staged 64 key rows at a time through shared memory: four independent
+  //    row loads per thread in flight (a serial load -> FMA loop over the keys was latency-bound: 15 us of a 29 us call)
+  {
+    const int m = tid >> 4, d = (tid & 15) * 4;
+    const float* row = S + m * ldS;
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j0 = 0; j0 < klen; j0 += MA_VCH) {
+      float4 vv[MA_VCH / 16];
+#pragma unroll
+      for (int i = 0; i < MA_VCH / 16; ++i) {
+        const int j = j0 + m + 16 * i;
+        vv[i] = (j < klen) ? load4(vb + (long long)j * ldkv + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      __syncthreads();                                            // previous chunk consumed
+#pragma unroll
+      for (int i = 0; i < MA_VCH / 16; ++i) *reinterpret_cast<float4*>(&Vs[(m + 16 * i) * AT_D + d]) = vv[i];
+      __syncthreads();
+      const int n = min(MA_VCH, klen - j0);
+#pragma unroll 8
+      for (int jj = 0; jj < n; ++jj) {
+        const float pj = row[j0 + jj];
+        const float4 v4 = *reinterpret_cast<const float4*>(&Vs[jj * AT_D + d]);
+        o.x = fmaf(pj, v4.x, o.x); o.y = fmaf(pj, v4.y, o.y); o.z = fmaf(pj, v4.z, o.z); o.w = fmaf(pj, v4.w, o.w);
+      }
+    }
+    if (q0 + m < n_q) {
+      const float inv = inv_l[m];
+      store4(out + ((long long)b * q_rows_per_seg + q0 + m) * ldo + h * AT_D + d, make_float4(o.x * inv, o.y * inv, o.z * inv, o.w * inv));
+    }
+  }
+}
+
+template <typename T>
+static int launch_memory_attention(const T* q, const T* k, const T* v, T* out, long long ldq, long long ldkv, long long ldo,
+                                   int B, int H, int n_q, int q_rows_per_seg, int n_kv, int kv_rows_per_seg,
+                                   const int32_t* kv_len, cudaStream_t st) {
+  const int smem = (MA_Q * AT_D + MA_Q + MA_VCH * AT_D + MA_Q * ((n_kv + 3) & ~3)) * 4;
+  static int attr_bytes = 0;
+  if (smem > attr_bytes) {
+    CST_CHECK_CUDA(cudaFuncSetAttribute(memory_attention_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (MA_Q * AT_D + MA_Q + MA_VCH * AT_D + MA_Q * MA_MAX_KV) * 4));
+    attr_bytes = (MA_Q * AT_D + MA_Q + MA_VCH * AT_D + MA_Q * MA_MAX_KV) * 4;
+  }
+  dim3 grid(cdiv(n_q, MA_Q), H, B);
+  CST_CHECK_CUDA(launch_k(memory_attention_kernel<T>, grid, dim3(MA_THREADS), smem, st, q, k, v, out, ldq, ldkv, ldo, n_q, q_rows_per_seg,
+                          n_kv, kv_rows_per_seg, kv_len));
+  return CST_OK;
+}
+
 int launch_attention_tc(const void* q, const void* k, const void* v, void* out, long long ldq, long long ldkv, long long ldo,
                         int B, int H, int n_q, int q_rows_per_seg, int n_kv, int kv_rows_per_seg,
                         const int32_t* kv_len, cudaStream_t st);
@@ -155,6 +290,15 @@ extern "C" int cst_attention(const void* q, const void* k, const void* v, void* 
   // fp32 (exact-parity mode) and the M-query memory stage: the CUDA-core kernel above.
   if (dtype == CST_BF16 && n_q > 64)
     return launch_attention_tc(q, k, v, out, ldq, ldkv, ldo, B, H, n_q, q_rows_per_seg, n_kv, kv_rows_per_seg, kv_len, st);
+  // few queries over a whole key axis (the memory stage): dedicated kernel; CST_MEMATTN=0 keeps the generic one
+  static const int mem_attn = [] { const char* e = getenv("CST_MEMATTN"); return e ? atoi(e) : 1; }();
+  if (mem_attn && n_q <= 64 && n_kv <= MA_MAX_KV && (dtype == CST_BF16 || dtype == CST_F32)) {
+    if (dtype == CST_F32)
+      return launch_memory_attention((const float*)q, (const float*)k, (const float*)v, (float*)out, ldq, ldkv, ldo, B, H, n_q, q_rows_per_seg,
+                                     n_kv, kv_rows_per_seg, kv_len, st);
+    return launch_memory_attention((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, (__nv_bfloat16*)out, ldq, ldkv, ldo,
+                                   B, H, n_q, q_rows_per_seg, n_kv, kv_rows_per_seg, kv_len, st);
+  }
   dim3 grid(cdiv(n_q, AT_BQ), H, B);
   static bool attr[2] = {false, false};
   if (dtype == CST_F32) {

@@ -196,7 +196,9 @@ def test_layernorm(Cd):
 @pytest.mark.parametrize("B,H,Tq,Tk,masked", [(3, 12, 249, 249, True), (2, 8, 63, 63, True), (2, 8, 16, 63, False),
                                               (1, 12, 130, 130, True), (2, 8, 64, 300, False),
                                               (2, 12, 1499, 1499, True), (3, 8, 188, 188, True), (2, 12, 750, 749, False),
-                                              (1, 12, 128, 128, False), (2, 8, 129, 257, True), (3, 12, 400, 385, True)])
+                                              (1, 12, 128, 128, False), (2, 8, 129, 257, True), (3, 12, 400, 385, True),
+                                              (3, 8, 16, 375, True), (3, 8, 40, 701, True), (2, 8, 64, 1500, False),
+                                              (2, 8, 16, 3100, False)])
 def test_attention(dtype, tol, B, H, Tq, Tk, masked):
     g = torch.Generator().manual_seed(Tq * 3 + Tk)
     Cd = H * 64
