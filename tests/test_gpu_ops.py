@@ -217,7 +217,7 @@ def test_attention(dtype, tol, B, H, Tq, Tk, masked):
     assert rel_l2(out.cpu().float(), ref) < tol, rel_l2(out.cpu().float(), ref)
 
 
-@pytest.mark.parametrize("B,T", [(2, 70), (3, 250), (1, 129)])
+@pytest.mark.parametrize("B,T", [(2, 70), (3, 250), (1, 129), (2, 750), (1, 1000), (1, 385)])
 def test_resident_posconv_matches_generic_gemm_path(B, T):
     """cst_posconv (panel resident in smem, row-shifted swizzled A descriptors) vs the batched implicit GEMM."""
     g = torch.Generator().manual_seed(B * 100 + T)
