@@ -78,9 +78,53 @@ def ncu_raw(tag, name):
     print("wrote ncu_%s_%s.csv (%d launches)" % (tag, name, len(data)))
 
 
+CLASSES = [("gemm_tc", "gemm_tc_bf16"), ("layernorm_kernel", "layernorm"), ("conv0_tc", "conv0_gn_gelu"), ("conv0_apply", "conv0_gn_gelu"),
+           ("attention_tc", "attention_tc_bf16"), ("posconv_tc", "posconv_tc_bf16"), ("memory_attention", "memory_attention")]
+
+
+def traffic(tag):
+    """gpurun_out/traffic_c3.csv (tools/gpu_traffic.sh) -> profiles/traffic_<tag>.json: DRAM bytes per launch per kernel class."""
+    import json
+    path = os.path.join(SRC, "traffic_c3.csv")
+    if not os.path.exists(path):
+        return
+    with open(path) as f:
+        lines = [l for l in f if not l.startswith("==")]
+    r = csv.reader(lines)
+    hdr = next(r)
+    idx = {h: i for i, h in enumerate(hdr)}
+    per = collections.OrderedDict()
+    for row in r:
+        if len(row) < len(hdr):
+            continue
+        name = row[idx["Kernel Name"]]
+        cls = next((c for key, c in CLASSES if key in name), None)
+        if cls is None:
+            continue
+        metric, unit = row[idx["Metric Name"]], row[idx["Metric Unit"]]
+        val = float(row[idx["Metric Value"]].replace(",", ""))
+        val *= {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1.0)
+        a = per.setdefault(cls, {"ids": set(), "read": 0.0, "write": 0.0})
+        a["ids"].add(row[idx["ID"]])
+        if metric == "dram__bytes_read.sum":
+            a["read"] += val
+        elif metric == "dram__bytes_write.sum":
+            a["write"] += val
+    out = {"workload": "c3, 24 utterances (4 batches), bf16, eager launches, ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum "
+                       "--clock-control none", "kernels": {}}
+    for cls, a in per.items():
+        n = len(a["ids"])
+        out["kernels"][cls] = {"launches": n, "dram_read_bytes_per_launch": a["read"] / n, "dram_write_bytes_per_launch": a["write"] / n,
+                               "traffic_bytes_per_launch": (a["read"] + a["write"]) / n}
+    with open(os.path.join(OUT, "traffic_%s.json" % tag), "w") as f:
+        json.dump(out, f, indent=1)
+    print("wrote traffic_%s.json (%s)" % (tag, ", ".join("%s x%d" % (k, v["launches"]) for k, v in out["kernels"].items())))
+
+
 if __name__ == "__main__":
     tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
     os.makedirs(OUT, exist_ok=True)
     launch_list(tag)
     for n in ("gemm", "attn", "conv0", "posconv", "ln"):
         ncu_raw(tag, n)
+    traffic(tag)
