@@ -85,7 +85,11 @@ __device__ __forceinline__ void epi_tile_fast(const GemmDev& p, float* patch, ui
       for (int u = 0; u < 4; ++u) {
         const int i = i0 + u;
         r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ok && ((st_mask >> i) & 1)) r[i] = *reinterpret_cast<const float4*>(r_base + (long long)orow[i] * p.ldr + n);
+        if (ok && ((st_mask >> i) & 1)) {
+          // 256-byte L2 fill granularity: the neighbouring 128 B of the row is this warp's next chunk
+          const float* ra = r_base + (long long)orow[i] * p.ldr + n;
+          asm volatile("ld.global.L2::256B.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r[i].x), "=f"(r[i].y), "=f"(r[i].z), "=f"(r[i].w) : "l"(ra));
+        }
       }
     }
   };
