@@ -23,6 +23,10 @@
 
 namespace cst {
 
+#ifndef FA_POLY_EXP
+#define FA_POLY_EXP 0      // 1: half of the softmax exponentials on the FMA pipe. Measured: 1.84 -> 1.95 ms (c2), the pass is issue-bound, not MUFU-bound
+#endif
+
 constexpr int FA_BQ = 128, FA_BK = 128, FA_D = 64, FA_KS = 2;
 constexpr int FA_SM_WARPS = 8;
 constexpr int FA_THREADS = 64 + 32 * FA_SM_WARPS;
@@ -231,9 +235,26 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           uint32_t pk[4];
 #pragma unroll
           for (int i = 0; i < 8; i += 2) {
-            float a0, a1;
+            float a0, a1, p0, p1;
             upk2(ffma2(pk2(s[g + i], s[g + i + 1]), l2e, nmb), a0, a1);
-            float p0 = mufu_ex2(a0), p1 = mufu_ex2(a1);
+            if (FA_POLY_EXP && (i & 2)) {
+              // every other pair: 2^a on the FMA / integer pipes (Cody-Waite split + degree-3 minimax on [-0.5, 0.5], relative
+              // error 7.7e-5, far below the bf16 rounding of P).  The 16 MUFU lanes per SM are what bounds this pass with
+              // 16 softmax warps resident; half of the exponentials leave that pipe.
+              const uint64_t ac = pk2(fmaxf(a0, -125.f), fmaxf(a1, -125.f));
+              const uint64_t magic = pk2(12582912.f, 12582912.f);                  // 1.5 * 2^23: low mantissa bits = round(a)
+              const uint64_t t = fadd2(ac, magic);
+              const uint64_t f = ffma2(fadd2(t, pk2(-12582912.f, -12582912.f)), pk2(-1.f, -1.f), ac);   // a - round(a)
+              uint64_t q = ffma2(f, pk2(5.508868381e-02f, 5.508868381e-02f), pk2(2.426040515e-01f, 2.426040515e-01f));
+              q = ffma2(q, f, pk2(6.932762417e-01f, 6.932762417e-01f));
+              q = ffma2(q, f, pk2(9.999289404e-01f, 9.999289404e-01f));
+              float q0, q1, t0, t1;
+              upk2(q, q0, q1); upk2(t, t0, t1);
+              p0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(t0) << 23));
+              p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(t1) << 23));
+            } else {
+              p0 = mufu_ex2(a0); p1 = mufu_ex2(a1);
+            }
             if (TAIL) {
               if (c + g + i >= nvalid) p0 = 0.f;
               if (c + g + i + 1 >= nvalid) p1 = 0.f;
