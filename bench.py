@@ -286,13 +286,14 @@ def main():
 
     def step_e2e():
         # public API with HOST buffers: pinned waveforms -> H2D -> encoder -> D2H of the memories
+        # (the encoder copies host tensors straight into its input buffers on the stream that runs the batch, so
+        # with stream lanes one batch's H2D copy overlaps another batch's kernels)
         if lanes == 1:
             for (w, l), oh in zip(host, out_host):
-                out = enc(w.cuda(non_blocking=True), l.cuda(non_blocking=True))
+                out = enc(w, l)
                 oh.copy_(out.encoder_out, non_blocking=True)
         else:
-            enc.forward_many([(w.cuda(non_blocking=True), l.cuda(non_blocking=True)) for w, l in host],
-                             n_lanes=lanes, out=out_host)
+            enc.forward_many(host, n_lanes=lanes, out=out_host)
         torch.cuda.synchronize()
 
     for _ in range(max(3, args.warmup)):

@@ -150,7 +150,9 @@ class B200InterlinguaEncoder(nn.Module):
         CUDA graphs, so the short kernels of one small batch (2e6-sample token budget ~ 6000 frames) overlap the
         tails / prologues of another's instead of leaving SMs idle.  Results are identical to calling forward()
         per batch (batches never interact).  Returns a list of EncoderOut; `out` (optional list of preallocated
-        [M,B,512] tensors, e.g. pinned host buffers) receives the memories with non_blocking copies."""
+        [M,B,512] tensors, e.g. pinned host buffers) receives the memories with non_blocking copies.
+        src_tokens / src_lengths may be (pinned) HOST tensors: they are copied straight into the lane's input buffers
+        on the lane's stream, so one batch's H2D transfer overlaps the other lanes' kernels."""
         lanes = self._get_lanes(n_lanes)
         cur = torch.cuda.current_stream()
         for ln in lanes:

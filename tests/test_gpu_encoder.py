@@ -138,6 +138,15 @@ def test_forward_many_on_stream_lanes_equals_forward(dtype):
         for a, b in zip(ref, got):
             assert torch.equal(a, b.encoder_out)
             assert b.encoder_padding_mask.shape == (a.shape[1], 16)
+    # pinned HOST inputs / outputs (the end-to-end form bench.py times): copied on the lanes' own streams, same bits
+    host = [(w.cpu().pin_memory(), l.cpu().pin_memory()) for w, l in batches]
+    out_host = [torch.empty_like(r, device="cpu").pin_memory() for r in ref]
+    enc.forward_many(host, n_lanes=3, out=out_host)
+    torch.cuda.synchronize()
+    for oh, r in zip(out_host, ref):
+        assert torch.equal(oh, r.cpu())
+    one = enc(host[0][0], host[0][1])
+    assert one.encoder_out.is_cuda and torch.equal(one.encoder_out, ref[0])
 
 
 def test_single_utterance_output_does_not_alias_the_arena():
