@@ -40,7 +40,7 @@ SR = 16000
 
 
 # --------------------------------------------------------------------------------------- workload
-def make_workload(name, rank, world, utts):
+def make_workload(name, rank, world, utts, max_tokens=2000000):
     """-> this rank's list of batches, each a list of utterance lengths (samples), longest first.
     c3: ONE global set of utts*world utterances, batched globally with the reference's rule and dealt
     round-robin to the ranks (generate.py:145-160 / ShardedIterator): per-GPU work stays ~constant as the
@@ -48,7 +48,7 @@ def make_workload(name, rank, world, utts):
     if name == "c3":
         rng = np.random.RandomState(2024)
         lens = rng.randint(32000, 480000 + 1, size=utts * world).astype(np.int64)
-        mine, _ = D.shard_utterances(lens, world, rank, 2000000, 8)
+        mine, _ = D.shard_utterances(lens, world, rank, max_tokens, 8)
         return [[int(lens[i]) for i in b] for b in mine]
     if name == "c1":
         return [[80000] * 4]
@@ -212,6 +212,9 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--workload", default="c3", choices=["c3", "c1", "c2", "c4"])
     ap.add_argument("--utts", type=int, default=512)
+    ap.add_argument("--max-tokens", type=int, default=2000000,
+                    help="c3 token budget per batch in samples (default: the reference's --max-tokens 2000000, "
+                         "chimera/scripts/interactive-en2any-ST.sh:21)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--lanes", type=int, default=3, help="concurrent CUDA-stream lanes for independent batches")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -221,10 +224,10 @@ def main():
     rank, world, local_rank = D.env_rank_world()
     cores = os.cpu_count() or 1
     M = 16
-    batches = make_workload(args.workload, rank, world, args.utts)
+    batches = make_workload(args.workload, rank, world, args.utts, args.max_tokens)
     audio_per_step = sum(sum(b) for b in batches) / SR
     cfg = {"workload": "%s: Chimera-16 encoder+memory, %s" % (args.workload, {
-        "c3": "%d utts/GPU U{2..30}s (global set x%d ranks, round-robin sharded), length-bucketed max_tokens=2e6 bsz%%8 (%d batches on rank 0)" % (args.utts, world, len(batches)),
+        "c3": "%d utts/GPU U{2..30}s (global set x%d ranks, round-robin sharded), length-bucketed max_tokens=%.0e bsz%%8 (%d batches on rank 0)" % (args.utts, world, args.max_tokens, len(batches)),
         "c1": "B=4 x 5 s", "c2": "B=32 x 15 s", "c4": "B=64 x 20 s"}[args.workload]),
         "interlingua_length": M, "batches_per_step": len(batches), "audio_sec_per_step_per_gpu": round(audio_per_step, 2),
         "parallelism": "utterance-sharded dp%d, no data-path collective" % world,

@@ -203,10 +203,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         float s[32];
         tmem_ld32(srow + c, s);
         tmem_ld_wait();
+        if (TAIL) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if (TAIL) { if (c + i < nvalid) mx = fmaxf(mx, s[i]); }
-          else mx = fmaxf(mx, s[i]);
+          for (int i = 0; i < 32; ++i) { if (c + i < nvalid) mx = fmaxf(mx, s[i]); }
+        } else {
+          // three-input max (FMNMX3, sm_100): half the instructions of the row-maximum pass
+          float mx2 = mx;                                  // two independent chains
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            asm("max.f32 %0, %0, %1, %2;" : "+f"(mx) : "f"(s[i]), "f"(s[i + 1]));
+            asm("max.f32 %0, %0, %1, %2;" : "+f"(mx2) : "f"(s[i + 2]), "f"(s[i + 3]));
+          }
+          mx = fmaxf(mx, mx2);
         }
       }
       FA_T(1);                                           // pass 1
