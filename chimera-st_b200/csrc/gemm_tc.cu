@@ -857,14 +857,20 @@ int launch_gemm_tc(const cst_gemm_params& hp, const GemmDev& p, int nz, cudaStre
   // 128x64 tiles (shorter serial K chain, 4x more CTAs), but with stream lanes they already overlap other batches'
   // kernels on the idle SMs and the end-to-end rate does not move (34.1k vs 33.8k audio-s/s): not enabled.
   static const int force_bn = [] { const char* e = getenv("CST_TC_BN"); return e ? atoi(e) : 0; }();
-  // CTA pairs (256x256 tiles): CST_TC_PAIR = 0 off (default), 1 when the problem has at least `pair_min` pair tiles,
-  // 2 always when the shape allows it.  Measured on B200 the pair kernel is at parity with the single-CTA kernel
-  // (the loads are not what limits either; see profiles/SUMMARY), so the simpler kernel stays the default.
-  static const int pair_mode = [] { const char* e = getenv("CST_TC_PAIR"); return e ? atoi(e) : 0; }();
+  // CTA pairs (256x256 tiles): CST_TC_PAIR = 0 off, 1 when the problem has at least `pair_min` pair tiles, 2 always when
+  // the shape allows it, 3 selective (default, below).  Measured on B200: before the bulk-store epilogue the pair kernel
+  // was at parity with the single-CTA kernel (the epilogue, not the loads, paced both); with it the pair kernel is ahead
+  // on the big-M MMA-paced shapes and the selective policy gains 1.4-1.7 % of the c2 step (3 A/B repetitions).
+  static const int pair_mode = [] { const char* e = getenv("CST_TC_PAIR"); return e ? atoi(e) : 3; }();
   static const int pair_min = [] { const char* e = getenv("CST_TC_PAIR_MIN"); return e ? atoi(e) : 74; }();
   if (pair_mode && hp.N % 256 == 0 && force_bn == 0) {
     const long long pair_tiles = (long long)cdiv(hp.M, 256) * (hp.N / 256) * nz;
-    if (pair_mode == 2 || pair_tiles >= pair_min) return launch_tc_pair(hp, p, nz, st);
+    // mode 3: only where the pair kernel measured ahead in isolation (tools/gemm_rate.py): big-M problems whose tile is
+    // MMA- or load-paced (QKV 1121 -> 1220, fc2 1107 -> 1217, conv 1252 -> 1279 TFLOP/s), not the GELU epilogue-paced
+    // K = 768 fc1 (1192 -> 1143)
+    const bool selective = hp.M >= 16384 && !(hp.act == CST_ACT_GELU && hp.K <= 768);
+    if (pair_mode == 2 || (pair_mode == 1 && pair_tiles >= pair_min) || (pair_mode == 3 && selective && pair_tiles >= pair_min))
+      return launch_tc_pair(hp, p, nz, st);
   }
   if (hp.N % 256 == 0 && force_bn != 128 && force_bn != 64) return launch_tc<256>(hp, p, nz, st);
   if (force_bn == 64 && hp.N % 64 == 0) return launch_tc<64>(hp, p, nz, st);
