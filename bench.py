@@ -389,7 +389,15 @@ def main():
         gbs = k1["bytes"] / k1["seconds"] / 1e9
         hbm_roof = {"bound": "hbm", "kernel": "conv0_gn_gelu (K1: conv0+GroupNorm+GELU, the bandwidth-bound stage)",
                     "achieved": round(gbs, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(gbs / hbm_peak, 4),
-                    "peak_source": "measured" if peaks else "fallback", "launches_per_step": k1["launches"]}
+                    "peak_source": "measured" if peaks else "fallback", "launches_per_step": k1["launches"],
+                    "algorithmic_bytes_per_launch": round(k1["bytes"] / max(1, k1["launches"])), "traffic": None}
+        try:
+            if args.workload == "c3":
+                tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01.json")))
+                hbm_roof["traffic"] = round(tj["kernels"]["conv0_gn_gelu"]["traffic_bytes_per_launch"])
+                hbm_roof["traffic_source"] = "profiles/traffic_r01.json: " + tj["workload"]
+        except Exception:
+            pass
     if args.profile_json:
         with open(args.profile_json, "w") as f:
             json.dump({"kernels": ksum, "launch_list": [(k, fl, by, s.elapsed_time(e), d) for k, fl, by, d, s, e in prof.rec]}, f)

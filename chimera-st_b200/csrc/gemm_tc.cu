@@ -259,11 +259,7 @@ __device__ __forceinline__ void epi_tile_bulk(const GemmDev& p, const CUtensorMa
 // accumulator stage is complete (called after the row bookkeeping so that work overlaps the wait).
 template <int BN, int ACT, typename WaitF, typename ReleaseF>
 __device__ __forceinline__ void epi_tile(const GemmDev& p, const CUtensorMap* tmC, int bulk, uint32_t& seq, float* patch, uint32_t t_row,
-                                         int row_base, int nb, int zo, int zi, int lane, int chalf, WaitF wait_acc, ReleaseF release_acc,
-                                         int next_row_base = -1, int next_nb = 0) {
-  // (Tried: prefetch.global.L2 of the NEXT tile's residual rows from here -- out-proj 61.4 -> 63.5 us, fc2 103 -> 109 us
-  // isolated; the residual fetch is not what holds these two GEMMs back, so the hook is unused.)
-  (void)next_row_base; (void)next_nb;
+                                         int row_base, int nb, int zo, int zi, int lane, int chalf, WaitF wait_acc, ReleaseF release_acc) {
   if constexpr (BN % 64 == 0 && ACT != CST_ACT_GLU) {
     if (bulk == 1) {
       const uint32_t stage_s = smem_u32(patch);
@@ -526,12 +522,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int zo = z / p.nb_inner, zi = z - zo * p.nb_inner;
       const int as = it & 1; const uint32_t aph = (it >> 1) & 1;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * Cfg::BN_PAD;
-      const int nxt = tile + gridDim.x;
-      int nrow = -1, nnb = 0;
-      if (nxt < total_tiles) { nnb = nxt % n_tiles; nrow = ((nxt / n_tiles) % m_tiles) * TC_BM + q * 32; }
       epi_tile<BN, ACT>(p, &tmC, bulk, seq, patch, t_row, mb * TC_BM + q * 32, nb, zo, zi, lane, chalf,
                         [&] { mbar_wait(tfull_bar + 8 * as, aph); tc_fence_after(); },
-                        [&] { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(tempty_bar + 8 * as); }, nrow, nnb);
+                        [&] { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(tempty_bar + 8 * as); });
     }
     if (bulk && lane == 0) bulk_wait_all<0>();     // staging buffers are read, and the stores complete, before exit
   }
