@@ -19,7 +19,7 @@ import torch
 
 from . import _lib as L
 from .lengths import conv_out_lengths
-from .synth import W2V_DIM, W2V_FFN, W2V_HEADS, ENC_DIM, ENC_FFN, ENC_HEADS
+from .synth import W2V_DIM, W2V_FFN, W2V_HEADS, ENC_DIM, ENC_FFN, ENC_HEADS, MEM_LAYERS
 
 SLACK = 8          # zero rows appended to activation buffers read by overlapping conv windows
 
@@ -102,7 +102,7 @@ class EncoderPlan:
             ("x2", R2, ENC_DIM, f32), ("x2a", R2, ENC_DIM, act_dtype), ("qkv2", R2, 3 * ENC_DIM, act_dtype),
             ("ctx2", R2, ENC_DIM, act_dtype), ("ffn2", R2, ENC_FFN, act_dtype), ("h_enc", R2, ENC_DIM, f32),
             # ---- memory stage
-            ("kv_in", R2, ENC_DIM, act_dtype), ("kv", R2, 2 * ENC_DIM, act_dtype), ("mem", RM, ENC_DIM, f32),
+            ("kv_in", R2, ENC_DIM, act_dtype), ("kv", R2, 2 * ENC_DIM * MEM_LAYERS, act_dtype), ("mem", RM, ENC_DIM, f32),
             ("mem_a", RM, ENC_DIM, act_dtype), ("mq", RM, ENC_DIM, act_dtype), ("mctx", RM, ENC_DIM, act_dtype),
             ("mffn", RM, ENC_FFN, act_dtype),
         ]
@@ -276,15 +276,18 @@ class EncoderPlan:
         es = self.kv.element_size()
         L.check(self.lib.cst_broadcast_rows(P["mem_embed"].data_ptr(), M, D, B, self.mem.data_ptr(), self.st))
         self.launches += 1
-        for lw in P["mem_layers"]:
+        # K/V side of all memory layers at once: unit LayerNorm of h_enc, then one GEMM whose weights carry each layer's
+        # LN1 affine (weights.py) -> kv[:, i*1024 : (i+1)*1024] = [K_i | V_i]
+        nl = len(P["mem_layers"])
+        self._ln(self.h_enc, (P["unit_g"], P["unit_b"]), R2, out_lp=self.kv_in)
+        self._linear(self.kv_in, P["mem_kv_w"], P["mem_kv_b"], self.kv, R2)
+        for i, lw in enumerate(P["mem_layers"]):
             ln1 = (lw["ln1_g"], lw["ln1_b"])
-            self._ln(self.h_enc, ln1, R2, out_lp=self.kv_in)            # shared pre-LN on the K/V side
-            self._linear(self.kv_in, lw["kv_w"], lw["kv_b"], self.kv, R2)
-            self._ln(self.mem, ln1, RM, out_lp=self.mem_a)              # ... and on the M queries
+            self._ln(self.mem, ln1, RM, out_lp=self.mem_a)              # the layer's pre-LN on the M queries
             self._linear(self.mem_a, lw["q_w"], lw["q_b"], self.mq, RM)
-            kp = self.kv.data_ptr()
+            kp = self.kv.data_ptr() + i * 2 * D * es
             # memories attend ALL T2 frames: the reference passes an all-False key-padding mask here
-            self._attn(self.mq.data_ptr(), kp, kp + D * es, self.mctx, D, 2 * D, ENC_HEADS, M, M, g.T2, g.T2a, None)
+            self._attn(self.mq.data_ptr(), kp, kp + D * es, self.mctx, D, 2 * D * nl, ENC_HEADS, M, M, g.T2, g.T2a, None)
             self._linear(self.mctx, lw["o_w"], lw["o_b"], self.mem, RM, residual=self.mem)
             self._ln(self.mem, (lw["ln2_g"], lw["ln2_b"]), RM, out_lp=self.mem_a)
             self._linear(self.mem_a, lw["fc1_w"], lw["fc1_b"], self.mffn, RM, act=L.ACT_RELU)

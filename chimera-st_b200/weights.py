@@ -101,4 +101,19 @@ def prepare(state_dict, device, act_dtype, conv_dtype=None):
     P["ln_out_g"], P["ln_out_b"] = f32(sd["layer_norm.weight"]), f32(sd["layer_norm.bias"])
     P["mem_embed"] = f32(sd["interlingua_embedding.weight"])
     P["mem_layers"] = [layer(f"interlingua_layers.{i}.", fused_qkv=False) for i in range(MEM_LAYERS)]
+    # K/V side of the memory stage: every layer i normalises the SAME h_enc with its own affine LN1 and projects it
+    # (w2v2_transformer_interlingua.py:262-274 -> transformer_layer.py:129-139).  LN(x; g, b) W^T + c =
+    # xhat (W diag g)^T + (W b + c), so the affine part folds into the projection exactly: one unit LayerNorm of h_enc
+    # and ONE [MEM_LAYERS*1024, 512] GEMM replace MEM_LAYERS LayerNorms and MEM_LAYERS small GEMMs.
+    ws, bs = [], []
+    for i in range(MEM_LAYERS):
+        pre = f"interlingua_layers.{i}."
+        g_, b_ = sd[pre + "self_attn_layer_norm.weight"].double(), sd[pre + "self_attn_layer_norm.bias"].double()
+        a = pre + "self_attn."
+        w = torch.cat((sd[a + "k_proj.weight"], sd[a + "v_proj.weight"]), 0).double()
+        c = torch.cat((sd[a + "k_proj.bias"], sd[a + "v_proj.bias"]), 0).double()
+        ws.append(w * g_[None, :])
+        bs.append(c + w @ b_)
+    P["mem_kv_w"], P["mem_kv_b"] = op(torch.cat(ws, 0).float()), f32(torch.cat(bs, 0).float())
+    P["unit_g"], P["unit_b"] = f32(torch.ones(sd["layer_norm.weight"].shape[0])), f32(torch.zeros(sd["layer_norm.weight"].shape[0]))
     return P
