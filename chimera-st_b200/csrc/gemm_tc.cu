@@ -114,15 +114,19 @@ __device__ __forceinline__ void epi_tile_fast(const GemmDev& p, float* patch, ui
   for (int ch = ch0; ch < ch1; ++ch) {
     const int n = col_of(ch);
     const bool col_ok = col_ok_of(ch);
+    TC_EPI_T(q0);
     tmem_ld_wait();
+    TC_EPI_T(q1);
     if (BST) { if (lane == 0) bulk_wait_read<0>(); }           // the previous chunk's bulk store has read the patch
     __syncwarp();                                              // previous chunk's readers are done with the patch
+    TC_EPI_T(q2);
     if (!TC_DBG(4)) {
 #pragma unroll
     for (int i = 0; i < 8; ++i)
       *reinterpret_cast<float4*>(&patch[lane * TC_PATCH_LD + 4 * (i ^ (lane & 7))]) = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
     }
     __syncwarp();
+    TC_EPI_T(q3);
     const bool has_next = ch + 1 < ch1;
     if (has_next) {                                            // next chunk: TMEM and bias loads in flight during the math
       load_acc(ch + 1, acc);
@@ -173,6 +177,8 @@ __device__ __forceinline__ void epi_tile_fast(const GemmDev& p, float* patch, ui
         }
       }
     }
+    TC_EPI_T(q4);
+    TC_EPI_ADD(4, q0, q1); TC_EPI_ADD(5, q1, q2); TC_EPI_ADD(6, q2, q3); TC_EPI_ADD(7, q3, q4);
     if (BST) {                                                 // (all columns of a BN % 64 == 0 tile are valid)
       fence_async_smem();
       __syncwarp();

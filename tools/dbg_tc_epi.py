@@ -33,3 +33,5 @@ for M, N, K, act, od, res, note in SHAPES:
     n = max(buf[3], 1)
     print("%-22s %7.1f us %7.1f TF | per tile (warp 2, block 0, %d tiles): rows %5.0f  wait %6.0f  chunks %6.0f cycles; MMA floor %d" % (
         note, e0.elapsed_time(e1) * 1e3, 2.0 * M * N * K / e0.elapsed_time(e1) / 1e9, n, buf[0] / n, buf[1] / n, buf[2] / n, K // 64 * 512))
+    print("      register-path chunk phases per tile: tmem wait %5.0f  store-read wait + sync %5.0f  transpose STS %5.0f  math + residual + stores %6.0f"
+          % (buf[4] / n, buf[5] / n, buf[6] / n, buf[7] / n))
