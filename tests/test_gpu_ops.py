@@ -239,3 +239,22 @@ def test_resident_posconv_matches_generic_gemm_path(B, T):
                                  L.stream_ptr()))
     torch.cuda.synchronize()
     assert rel_l2(out.cpu(), ref.cpu()) < 2e-5, rel_l2(out.cpu(), ref.cpu())
+
+
+def test_conv0_tensor_core_full_c2_size_matches_cuda_core_kernel():
+    """B = 32 x 15 s (BASELINE configs[1] size): 12 000 frame tiles over the persistent grid, utterance changes inside a CTA's
+    tile range, dead frames in each utterance's last tile -- against the CUDA-core kernel on the same inputs."""
+    sd = synth.make_state_dict(seed=0)
+    lens = [240000 - 997 * i for i in range(32)]
+    wave, _ = synth.make_waveforms(lens, seed=11)
+    P = "wav2vec_model.feature_extractor.conv_layers."
+    T0 = (wave.shape[1] - 10) // 5 + 1
+    rps = 64 * ((T0 + 63) // 64)
+    args = (wave.to(DEV), sd[P + "0.0.weight"].to(DEV), sd[P + "0.2.weight"].to(DEV), sd[P + "0.2.bias"].to(DEV), torch.float16, rps)
+    a, _ = ops().conv0_gn_gelu(*args)
+    b, _ = ops().conv0_gn_gelu(*args, tensor_core=True)
+    assert float(b[:, T0:].abs().max()) == 0.0 if rps > T0 else True
+    diff = (a.float() - b.float()).abs()
+    assert float((diff > 0).float().mean()) < 0.02                      # 1-ulp flips only
+    assert float(diff.max()) <= 2.0 ** -9 * float(a.float().abs().max())
+    assert rel_l2(b.float().cpu(), a.float().cpu()) < 2e-4
