@@ -163,7 +163,7 @@ class LaunchProfiler:
                     "B%d L%d" % (B, L))
         if name == "cst_conv0_stats":
             return ("conv0_stats", 0.0, 4 * a[1] * a[2], "B%d L%d" % (a[1], a[2]))
-        if name == "cst_posconv":
+        if name in ("cst_posconv", "cst_posconv_stacked"):
             B, n = a[5], a[6]
             return ("posconv_tc_bf16", 2.0 * B * n * 768 * 48 * 128, 0, "B%d T%d" % (B, n))
         return (name[4:], 0.0, 0, "")

@@ -81,6 +81,7 @@ class EncoderPlan:
         self.launches = 0
         self.use_resident_posconv = os.environ.get("CST_POSCONV_RESIDENT", "1") != "0"
         self.use_conv0_tc = os.environ.get("CST_CONV0_TC", "1") != "0"
+        self.use_stacked_posconv = os.environ.get("CST_POSCONV_STACKED", "1") != "0"
         self.arena = arena if arena is not None else Arena(self.dev)
         f32, i32, i64, u8, f64 = torch.float32, torch.int32, torch.int64, torch.uint8, torch.float64
         R, R2, RM = B * g.T6a, B * g.T2a, B * M
@@ -201,7 +202,11 @@ class EncoderPlan:
         L.check(lib.cst_posconv_pack(self.x.data_ptr(), B, g.T6a, g.Tp, self.xg.data_ptr(), self.act_code, g.Tpp, self.st))
         self.launches += 1
         # grouped pos-conv: z = (utterance, group); window of frame t = rows t..t+127 of the packed operand
-        if self.act == torch.bfloat16 and self.use_resident_posconv:
+        if self.act == torch.bfloat16 and self.use_resident_posconv and self.use_stacked_posconv:
+            L.check(lib.cst_posconv_stacked(self.xg.data_ptr(), P["pos_w2"].data_ptr(), P["pos_b"].data_ptr(), self.x.data_ptr(),
+                                            self.y.data_ptr(), B, g.T6a, g.T6a, g.Tpp, self.st))
+            self.launches += 1
+        elif self.act == torch.bfloat16 and self.use_resident_posconv:
             L.check(lib.cst_posconv(self.xg.data_ptr(), P["pos_w"].data_ptr(), P["pos_b"].data_ptr(), self.x.data_ptr(),
                                     self.y.data_ptr(), B, g.T6a, g.T6a, g.Tpp, self.st))
             self.launches += 1

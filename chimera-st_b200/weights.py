@@ -70,6 +70,12 @@ def prepare(state_dict, device, act_dtype, conv_dtype=None):
     wp = torch.zeros(POS_GROUPS, cg, POS_K, 64, dtype=torch.float32)
     wp[..., :cg] = wg
     P["pos_w"] = op(wp.reshape(POS_GROUPS, cg, POS_K * 64))
+    if act_dtype != torch.float32:
+        # cst_posconv_stacked: [group, tap pair, 128 rows, 64 lanes]; rows 0..47 even tap, rows 64..111 odd tap
+        w2 = torch.zeros(POS_GROUPS, POS_K // 2, 128, 64, dtype=torch.float32)
+        w2[:, :, 0:cg, :] = wp[:, :, 0::2, :].permute(0, 2, 1, 3)
+        w2[:, :, 64:64 + cg, :] = wp[:, :, 1::2, :].permute(0, 2, 1, 3)
+        P["pos_w2"] = op(w2)
     P["pos_b"] = f32(sd[pc + "bias"])
     P["ln_enc_g"], P["ln_enc_b"] = f32(sd[W + "encoder.layer_norm.weight"]), f32(sd[W + "encoder.layer_norm.bias"])
 

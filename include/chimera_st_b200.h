@@ -123,6 +123,12 @@ int cst_broadcast_rows(const float* src, int rows, int C, int B, float* dst, voi
 int cst_posconv(const void* xg, const void* w, const float* bias, const float* resid, float* out,
                 int B, int n_rows, int rows_per_seg, int t_pad_rows, void* stream);
 
+/* Same stage, "taps stacked in M" formulation (default for bf16): weights are the A operand, two taps per instruction,
+ * frames are N = 256.  w2: bf16 [16 groups, 64 tap pairs, 128 rows, 64 lanes]; rows 0..47 = W[g, co, tap 2p, ci],
+ * rows 64..111 = W[g, co, tap 2p+1, ci], other rows and lanes 48..63 zero.  Other arguments as cst_posconv. */
+int cst_posconv_stacked(const void* xg, const void* w2, const float* bias, const float* resid, float* out,
+                        int B, int n_rows, int rows_per_seg, int t_pad_rows, void* stream);
+
 /* ---- padding-aware attention: softmax(q k^T + keymask) v, head_dim 64 ---------------------------------
  * Replaces: the attention core of F.multi_head_attention_forward as called from
  * multihead_attention.py:165-187 (wav2vec2 layers wav2vec2.py:938-945 with a -inf key-padding mask;

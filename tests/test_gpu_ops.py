@@ -239,6 +239,17 @@ def test_resident_posconv_matches_generic_gemm_path(B, T):
                                  L.stream_ptr()))
     torch.cuda.synchronize()
     assert rel_l2(out.cpu(), ref.cpu()) < 2e-5, rel_l2(out.cpu(), ref.cpu())
+    # "taps stacked in M" formulation: weights as the A operand, two taps per instruction (cst_posconv_stacked)
+    w4 = w.view(G, 48, 128, 64)                                        # [g, co, tap, lane]
+    w2 = torch.zeros(G, 64, 128, 64, dtype=torch.bfloat16)
+    w2[:, :, 0:48, :] = w4[:, :, 0::2, :].permute(0, 2, 1, 3)
+    w2[:, :, 64:112, :] = w4[:, :, 1::2, :].permute(0, 2, 1, 3)
+    out2 = torch.zeros(B * T, 768, dtype=torch.float32, device=DEV)
+    w2d = w2.to(DEV).contiguous()
+    L.check(L.load().cst_posconv_stacked(xg.data_ptr(), w2d.data_ptr(), bd.data_ptr(), xd.data_ptr(), out2.data_ptr(), B, T, T, Tpp,
+                                         L.stream_ptr()))
+    torch.cuda.synchronize()
+    assert rel_l2(out2.cpu(), ref.cpu()) < 2e-5, rel_l2(out2.cpu(), ref.cpu())
 
 
 def test_conv0_tensor_core_full_c2_size_matches_cuda_core_kernel():
