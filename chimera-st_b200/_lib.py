@@ -35,6 +35,17 @@ class GemmParams(C.Structure):
     ]
 
 
+class DecLinearParams(C.Structure):
+    _fields_ = [
+        ("A", C.c_void_p), ("W", C.c_void_p), ("bias", C.c_void_p), ("ln_gamma", C.c_void_p), ("ln_beta", C.c_void_p),
+        ("residual", C.c_void_p), ("out", C.c_void_p * 3),
+        ("lda", C.c_longlong), ("ldr", C.c_longlong), ("ldo", C.c_longlong * 3), ("step_stride", C.c_longlong * 3),
+        ("step", C.c_void_p),
+        ("a_dtype", C.c_int), ("w_dtype", C.c_int), ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
+        ("n_seg", C.c_int), ("act", C.c_int),
+    ]
+
+
 _SIGS = {
     "cst_abi_version": (C.c_int, []),
     "cst_last_error": (C.c_char_p, []),
@@ -60,6 +71,13 @@ _SIGS = {
     "cst_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_longlong,
                                 C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                 C.c_void_p]),
+    "cst_dec_embed": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_int,
+                                C.c_int, C.c_void_p, C.c_void_p]),
+    "cst_dec_linear": (C.c_int, [C.POINTER(DecLinearParams), C.c_void_p]),
+    "cst_dec_attention": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong,
+                                    C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "cst_dec_select": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
 }
 EXPORTS = tuple(_SIGS)
 

@@ -1,0 +1,308 @@
+"""Greedy target-token decoding from the M memories on the B200 (BASELINE configs[3]).
+
+Host-side mirror of the reference's generation stack for `beam_size = 1`:
+
+    SequenceGenerator(models, tgt_dict, beam_size=1, max_len_a, max_len_b, min_len).generate(models, sample)
+        fairseq/sequence_generator.py:17-540      -> B200GreedyGenerator.generate(models, sample)
+    TransformerDecoder (incremental)  fairseq/models/transformer.py:640-838     -> B200GreedyDecoder
+    TransformerDecoderLayer           fairseq/modules/transformer_layer.py:158-412
+
+`B200GreedyDecoder` takes the reference's `decoder.*` state dict (same keys and shapes: q/k/v/out projections,
+three LayerNorms and fc1/fc2 per layer, tied `embed_tokens` / `output_projection`), and produces, for every
+utterance, the reference's hypothesis: token IDs ending in EOS, per-token log-probabilities and the
+length-normalised score.  All arithmetic runs in the CUDA kernels behind `cst_dec_*` (csrc/decoder.cu); a decoding
+step is 51 launches captured once into a CUDA graph and replayed -- the step index lives on the device, and the
+host only polls the number of finished hypotheses every few steps.  No CPU fallback: a non-CUDA memory tensor raises
+(the `lib` argument exists so that tests can drive the launch sequence against a host emulator of the C ABI).
+
+Not reproduced: beam_size > 1, sampling, prefix tokens, n-gram blocking, temperature, LM fusion, alignment output.
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib as L
+
+PAD, EOS = 1, 2          # Dictionary defaults (fairseq/data/dictionary.py:26-31): bos 0, pad 1, eos 2, unk 3
+DIM, FFN, HEADS, LAYERS = 512, 2048, 8, 6
+
+
+def sinusoidal_positions(n_steps, dim=DIM, padding_idx=PAD):
+    """Rows t = 0..n_steps-1 of SinusoidalPositionalEmbedding.get_embedding (sinusoidal_positional_embedding.py:38-59)
+    at positions padding_idx + 1 + t (incremental decoding: `pos = padding_idx + seq_len`, :80-88)."""
+    half = dim // 2
+    e = math.log(10000) / (half - 1)
+    e = torch.exp(torch.arange(half, dtype=torch.float) * -e)
+    pos = torch.arange(padding_idx + 1, padding_idx + 1 + n_steps, dtype=torch.float)
+    e = pos.unsqueeze(1) * e.unsqueeze(0)
+    return torch.cat([torch.sin(e), torch.cos(e)], dim=1).contiguous()
+
+
+def prepare_decoder_weights(sd, device, dtype, prefix="decoder."):
+    """Reference `decoder.*` state dict -> fused device tensors.  Matrices in `dtype` (fp32 / bf16), biases and LayerNorm
+    parameters fp32.  Only exact folds: the 1/8 query scaling (a power of two) into W_q, b_q; q|k|v concatenation."""
+    if dtype not in (torch.float32, torch.bfloat16):
+        raise ValueError("decoder weight dtype must be float32 or bfloat16")
+
+    def g(name):
+        return sd[prefix + name].detach().float()
+
+    def w(t):
+        return t.to(device=device, dtype=dtype).contiguous()
+
+    def f(t):
+        return t.to(device=device, dtype=torch.float32).contiguous()
+
+    P = {"layers": []}
+    E = g("output_projection.weight") if prefix + "output_projection.weight" in sd else g("embed_tokens.weight")
+    if not torch.equal(E, g("embed_tokens.weight")):
+        raise NotImplementedError("untied decoder input/output embeddings")     # share_decoder_input_output_embed
+    P["embed"] = w(E)
+    P["vocab"] = E.shape[0]
+    P["ln_g"], P["ln_b"] = f(g("layer_norm.weight")), f(g("layer_norm.bias"))
+    n = 0
+    while prefix + "layers.%d.fc1.weight" % n in sd:
+        n += 1
+    scale = (DIM // HEADS) ** -0.5
+    for i in range(n):
+        p = "layers.%d." % i
+        sa, ea = p + "self_attn.", p + "encoder_attn."
+        lay = {
+            "ln1_g": f(g(p + "self_attn_layer_norm.weight")), "ln1_b": f(g(p + "self_attn_layer_norm.bias")),
+            "qkv_w": w(torch.cat([g(sa + "q_proj.weight") * scale, g(sa + "k_proj.weight"), g(sa + "v_proj.weight")], 0)),
+            "qkv_b": f(torch.cat([g(sa + "q_proj.bias") * scale, g(sa + "k_proj.bias"), g(sa + "v_proj.bias")], 0)),
+            "so_w": w(g(sa + "out_proj.weight")), "so_b": f(g(sa + "out_proj.bias")),
+            "ln2_g": f(g(p + "encoder_attn_layer_norm.weight")), "ln2_b": f(g(p + "encoder_attn_layer_norm.bias")),
+            "xq_w": w(g(ea + "q_proj.weight") * scale), "xq_b": f(g(ea + "q_proj.bias") * scale),
+            "xkv_w": w(torch.cat([g(ea + "k_proj.weight"), g(ea + "v_proj.weight")], 0)),
+            "xkv_b": f(torch.cat([g(ea + "k_proj.bias"), g(ea + "v_proj.bias")], 0)),
+            "xo_w": w(g(ea + "out_proj.weight")), "xo_b": f(g(ea + "out_proj.bias")),
+            "ln3_g": f(g(p + "final_layer_norm.weight")), "ln3_b": f(g(p + "final_layer_norm.bias")),
+            "fc1_w": w(g(p + "fc1.weight")), "fc1_b": f(g(p + "fc1.bias")),
+            "fc2_w": w(g(p + "fc2.weight")), "fc2_b": f(g(p + "fc2.bias")),
+        }
+        P["layers"].append(lay)
+    return P
+
+
+class _DecodePlan:
+    """Buffers + launch sequence (+ CUDA graph of one step) for a fixed (B hypotheses, M memories, max_len)."""
+
+    def __init__(self, P, B, M, max_len, mem_dtype, device, lib, use_graph):
+        self.P, self.B, self.M, self.max_len, self.lib = P, B, M, max_len, lib
+        self.device = device
+        self.use_graph = use_graph and device.type == "cuda"
+        self.T = max_len + 2                                  # cache rows / token columns (EOS start + max_len + 1 picks)
+        nl = len(P["layers"])
+        z = dict(device=device, dtype=torch.float32)
+        self.mem = torch.zeros(M * B, DIM, device=device, dtype=mem_dtype)       # row m*B + b  (= encoder_out [M,B,C])
+        self.xk = torch.zeros(nl, M * B, DIM, **z)            # cross-attention keys / values of the memories, per layer
+        self.xv = torch.zeros(nl, M * B, DIM, **z)
+        self.kc = torch.zeros(nl, B, self.T, DIM, **z)        # self-attention cache
+        self.vc = torch.zeros(nl, B, self.T, DIM, **z)
+        self.x = torch.zeros(B, DIM, **z)
+        self.q = torch.zeros(B, DIM, **z)
+        self.a = torch.zeros(B, DIM, **z)
+        self.h = torch.zeros(B, FFN, **z)
+        self.logits = torch.zeros(B, P["vocab"], **z)
+        self.pos = sinusoidal_positions(self.T).to(device)
+        self.tokens = torch.zeros(B, self.T, device=device, dtype=torch.int32)
+        self.pos_scores = torch.zeros(B, self.T, **z)
+        self.done = torch.zeros(B, device=device, dtype=torch.int32)
+        self.out_len = torch.zeros(B, device=device, dtype=torch.int32)
+        self.counters = torch.zeros(4, device=device, dtype=torch.int32)
+        self.graph = None
+        self.min_len = 1
+        self.launches_per_step = 0
+        self.total_launches = 0
+
+    # ---- launches -------------------------------------------------------------------------------------
+    def _st(self):
+        return L.stream_ptr() if self.device.type == "cuda" else 0
+
+    def _linear(self, A, W, bias, outs, M, N, K, ln=None, residual=None, act=L.ACT_NONE, ldo=None, step_stride=None,
+                use_step=False):
+        p = L.DecLinearParams()
+        p.A, p.W, p.bias = A.data_ptr(), W.data_ptr(), L.ptr(bias)
+        p.ln_gamma, p.ln_beta = (ln[0].data_ptr(), ln[1].data_ptr()) if ln is not None else (0, 0)
+        p.residual = L.ptr(residual)
+        p.lda, p.ldr = K, N
+        n_seg = len(outs)
+        for s in range(3):
+            p.out[s] = outs[s].data_ptr() if s < n_seg else 0
+            p.ldo[s] = (ldo[s] if ldo is not None else N // n_seg) if s < n_seg else 0
+            p.step_stride[s] = step_stride[s] if (step_stride is not None and s < n_seg) else 0
+        p.step = self.counters.data_ptr() if use_step else 0
+        p.a_dtype, p.w_dtype = L.DT[A.dtype], L.DT[W.dtype]
+        p.M, p.N, p.K, p.n_seg, p.act = M, N, K, n_seg, act
+        L.check(self.lib.cst_dec_linear(C.byref(p), self._st()))
+        self.n_launch += 1
+
+    def _attention(self, k, v, kv_bs, kv_rs, n_keys, n_max, use_step):
+        L.check(self.lib.cst_dec_attention(self.q.data_ptr(), DIM, k.data_ptr(), v.data_ptr(), kv_bs, kv_rs,
+                                           self.a.data_ptr(), DIM, self.B, HEADS, n_keys, n_max,
+                                           self.counters.data_ptr() if use_step else 0, self._st()))
+        self.n_launch += 1
+
+    def begin(self, memories):
+        """memories [M,B,512] -> cross-attention K/V of every layer (static_kv, multihead_attention.py:213-221);
+        reset tokens / counters."""
+        B, M, P = self.B, self.M, self.P
+        self.n_launch = 0
+        self.mem.copy_(memories.reshape(M * B, DIM))
+        self.tokens.fill_(EOS)                               # tokens[:, 0] = EOS (sequence_generator.py:247-252)
+        self.pos_scores.zero_()
+        self.done.zero_()
+        self.out_len.zero_()
+        self.counters.zero_()
+        for i, lay in enumerate(P["layers"]):
+            self._linear(self.mem, lay["xkv_w"], lay["xkv_b"], [self.xk[i], self.xv[i]], M * B, 2 * DIM, DIM)
+
+    def _step(self):
+        B, M, P, T = self.B, self.M, self.P, self.T
+        self.n_launch = 0
+        L.check(self.lib.cst_dec_embed(self.tokens.data_ptr(), T, P["embed"].data_ptr(), L.DT[P["embed"].dtype],
+                                       self.pos.data_ptr(), math.sqrt(DIM), self.x.data_ptr(), B, DIM,
+                                       self.counters.data_ptr(), self._st()))
+        self.n_launch += 1
+        for i, lay in enumerate(P["layers"]):
+            # self-attention block: x += Out(attn(LN1 x)); K/V rows of this step appended to the cache by the projection
+            self._linear(self.x, lay["qkv_w"], lay["qkv_b"], [self.q, self.kc[i], self.vc[i]], B, 3 * DIM, DIM,
+                         ln=(lay["ln1_g"], lay["ln1_b"]), ldo=[DIM, T * DIM, T * DIM], step_stride=[0, DIM, DIM],
+                         use_step=True)
+            self._attention(self.kc[i], self.vc[i], T * DIM, DIM, 0, T, True)
+            self._linear(self.a, lay["so_w"], lay["so_b"], [self.x], B, DIM, DIM, residual=self.x)
+            # encoder-decoder attention over the M memories
+            self._linear(self.x, lay["xq_w"], lay["xq_b"], [self.q], B, DIM, DIM, ln=(lay["ln2_g"], lay["ln2_b"]))
+            self._attention(self.xk[i], self.xv[i], DIM, B * DIM, M, M, False)
+            self._linear(self.a, lay["xo_w"], lay["xo_b"], [self.x], B, DIM, DIM, residual=self.x)
+            # feed-forward
+            self._linear(self.x, lay["fc1_w"], lay["fc1_b"], [self.h], B, FFN, DIM, ln=(lay["ln3_g"], lay["ln3_b"]),
+                         act=L.ACT_RELU)
+            self._linear(self.h, lay["fc2_w"], lay["fc2_b"], [self.x], B, DIM, FFN, residual=self.x)
+        self._linear(self.x, P["embed"], None, [self.logits], B, P["vocab"], DIM, ln=(P["ln_g"], P["ln_b"]))
+        L.check(self.lib.cst_dec_select(self.logits.data_ptr(), P["vocab"], B, self.tokens.data_ptr(), T,
+                                        self.pos_scores.data_ptr(), T, self.done.data_ptr(), self.out_len.data_ptr(),
+                                        self.counters.data_ptr(), self.max_len, self.min_len, PAD, EOS, self._st()))
+        self.n_launch += 1
+        self.launches_per_step = self.n_launch
+
+    def step(self):
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._step()
+
+    def run(self, memories, min_len=1, poll=8):
+        """-> number of steps issued."""
+        if self.graph is not None and min_len != self.min_len:
+            self.graph = None                                  # min_len is a kernel argument baked into the graph
+        self.min_len = min_len
+        self.begin(memories)
+        if self.use_graph and self.graph is None:
+            # warm-up step (module loading, function attributes), then capture; the step index and token state are
+            # device state, so rewind them afterwards (capturing does not execute anything)
+            self._step()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._step()
+            self.graph = g
+            self.begin(memories)
+        n_begin = self.n_launch
+        steps = 0
+        for s in range(self.max_len + 1):
+            self.step()
+            steps += 1
+            if s == self.max_len or (s % poll) == poll - 1:
+                if int(self.counters[2].item()) >= self.B:     # the only host synchronisation of the loop
+                    break
+        self.total_launches = n_begin + steps * self.launches_per_step
+        return steps
+
+
+class B200GreedyDecoder:
+    """decoder.* state dict + memories -> greedy hypotheses (see module docstring)."""
+
+    def __init__(self, state_dict, dtype=torch.float32, device="cuda", prefix="decoder.", use_graph=True, lib=None):
+        self.device = torch.device(device)
+        if lib is None:
+            if self.device.type != "cuda":
+                raise L.CstError("B200GreedyDecoder needs a CUDA device (there is no CPU fallback)")
+            lib = L.load()
+        self.lib = lib
+        self.P = prepare_decoder_weights(state_dict, self.device, dtype, prefix)
+        self.use_graph = use_graph
+        self._plans = {}
+        self.last_steps = 0
+        self.last_launches = 0
+
+    def _plan(self, B, M, max_len, mem_dtype):
+        key = (B, M, max_len, mem_dtype)
+        if key not in self._plans:
+            if len(self._plans) >= 8:
+                self._plans.pop(next(iter(self._plans)))
+            self._plans[key] = _DecodePlan(self.P, B, M, max_len, mem_dtype, self.device, self.lib, self.use_graph)
+        return self._plans[key]
+
+    @torch.no_grad()
+    def generate(self, memories, max_len=200, min_len=1):
+        """memories: encoder_out [M,B,512] (fp32 or bf16, on the decoder's device).
+        max_len = int(max_len_a * src_len + max_len_b) as in sequence_generator.py:222-230.
+        -> list over utterances of {"tokens": LongTensor [n] ending in EOS, "score": float (sum of log-probs / n),
+           "positional_scores": FloatTensor [n]} -- the reference's hypothesis dict (sequence_generator.py:636-648)."""
+        if memories.device.type != self.device.type:
+            raise L.CstError("memories must live on %s (no CPU fallback)" % self.device)
+        if memories.dim() != 3 or memories.shape[2] != DIM:
+            raise ValueError("memories must be [M, B, %d]" % DIM)
+        if memories.dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError("memories must be float32 or bfloat16")
+        M, B = memories.shape[0], memories.shape[1]
+        plan = self._plan(B, M, int(max_len), memories.dtype)
+        self.last_steps = plan.run(memories.contiguous(), min_len=min_len)
+        self.last_launches = plan.total_launches
+        toks, lens, ps = plan.tokens.cpu(), plan.out_len.cpu(), plan.pos_scores.cpu()
+        out = []
+        for b in range(B):
+            n = int(lens[b])
+            sc = ps[b, :n].clone()
+            out.append({"tokens": toks[b, 1:n + 1].long(), "score": float(sc.sum() / max(n, 1)), "attention": None,
+                        "alignment": torch.empty(0), "positional_scores": sc})
+        return out
+
+
+class B200GreedyGenerator:
+    """Drop-in for `SequenceGenerator(models, tgt_dict, beam_size=1, ...)` (fairseq/sequence_generator.py:17-100):
+    `generate(models, sample)` runs the model's own encoder (the B200 encoder when the plugin is active) and decodes
+    greedily on the GPU.  Returns the reference structure: per sentence a list (beam) of hypothesis dicts."""
+
+    def __init__(self, models, tgt_dict=None, beam_size=1, max_len_a=0.0, max_len_b=200, min_len=1, dtype=None, **unsupported):
+        models = list(models) if isinstance(models, (list, tuple)) else [models]
+        if len(models) != 1:
+            raise NotImplementedError("model ensembles")
+        if beam_size != 1:
+            raise NotImplementedError("beam_size > 1 (greedy only)")
+        for k, v in unsupported.items():
+            if v not in (None, False, 0, 0.0, 1.0) and k not in ("normalize_scores", "len_penalty", "unk_penalty", "temperature",
+                                                                  "match_source_len", "no_repeat_ngram_size"):
+                raise NotImplementedError("SequenceGenerator option %s=%r" % (k, v))
+        self.model = models[0]
+        if tgt_dict is not None and (tgt_dict.pad(), tgt_dict.eos()) != (PAD, EOS):
+            raise NotImplementedError("non-default pad/eos indices")
+        self.max_len_a, self.max_len_b, self.min_len = max_len_a, max_len_b, min_len
+        dec_sd = {k: v for k, v in self.model.state_dict().items() if k.startswith("decoder.")}
+        p = next(self.model.decoder.parameters())
+        self.decoder = B200GreedyDecoder(dec_sd, dtype=dtype or (p.dtype if p.dtype == torch.bfloat16 else torch.float32),
+                                         device=p.device)
+
+    @torch.no_grad()
+    def generate(self, models, sample, prefix_tokens=None, constraints=None, bos_token=None, **kwargs):
+        if prefix_tokens is not None or constraints is not None:
+            raise NotImplementedError("prefix tokens / constraints")
+        net_input = sample["net_input"]
+        enc = self.model.encoder(**{k: v for k, v in net_input.items() if k != "prev_output_tokens"})
+        mem = enc.encoder_out
+        src_len = net_input["src_tokens"].shape[1]
+        max_len = min(int(self.max_len_a * src_len + self.max_len_b), self.model.max_decoder_positions() - 1)
+        return [[h] for h in self.decoder.generate(mem, max_len=max_len, min_len=self.min_len)]

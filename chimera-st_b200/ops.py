@@ -117,3 +117,45 @@ def attention(q, k, v, n_heads, kv_len=None):
     L.check(L.load().cst_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), L.DT[q.dtype],
                                    Cd, Cd, Cd, B, n_heads, Tq, Tq, Tk, Tk, L.ptr(kv_len), L.stream_ptr()))
     return out
+
+
+# ---- greedy decoding kernels (cst_dec_*) ------------------------------------------------------------------------------
+def dec_linear(A, W, bias=None, ln=None, residual=None, act=L.ACT_NONE, outs=None, ldo=None, step_stride=None, step=None):
+    """act(LN?(A) W^T + b) (+ residual) -> f32.  outs: list of 1-3 output tensors (N split evenly); default one [M,N]."""
+    _cuda(A, W, bias, residual, step)
+    M, K = A.shape
+    N = W.shape[0]
+    if outs is None:
+        outs = [torch.empty(M, N, dtype=torch.float32, device=A.device)]
+    p = L.DecLinearParams()
+    p.A, p.W, p.bias, p.residual = A.data_ptr(), W.data_ptr(), L.ptr(bias), L.ptr(residual)
+    p.ln_gamma, p.ln_beta = (ln[0].data_ptr(), ln[1].data_ptr()) if ln is not None else (0, 0)
+    p.lda, p.ldr = A.stride(0), (residual.stride(0) if residual is not None else 0)
+    for s in range(3):
+        p.out[s] = outs[s].data_ptr() if s < len(outs) else 0
+        p.ldo[s] = (ldo[s] if ldo is not None else N // len(outs)) if s < len(outs) else 0
+        p.step_stride[s] = step_stride[s] if (step_stride is not None and s < len(outs)) else 0
+    p.step = L.ptr(step)
+    p.a_dtype, p.w_dtype = L.DT[A.dtype], L.DT[W.dtype]
+    p.M, p.N, p.K, p.n_seg, p.act = M, N, K, len(outs), act
+    L.check(L.load().cst_dec_linear(C.byref(p), L.stream_ptr()))
+    return outs[0] if len(outs) == 1 else outs
+
+
+def dec_attention(q, k, v, kv_batch_stride, kv_row_stride, n_heads, n_keys, n_keys_max, step=None):
+    """q [B, H*64] f32 (pre-scaled); key j of row b at k + b*kv_batch_stride + j*kv_row_stride (elements)."""
+    _cuda(q, k, v, step)
+    B = q.shape[0]
+    out = torch.empty_like(q)
+    L.check(L.load().cst_dec_attention(q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), kv_batch_stride, kv_row_stride,
+                                       out.data_ptr(), out.stride(0), B, n_heads, n_keys, n_keys_max, L.ptr(step),
+                                       L.stream_ptr()))
+    return out
+
+
+def dec_select(logits, tokens, pos_scores, done, out_len, counters, max_len, min_len=1, pad=1, eos=2):
+    _cuda(logits, tokens, pos_scores, done, out_len, counters)
+    B, V = logits.shape
+    L.check(L.load().cst_dec_select(logits.data_ptr(), V, B, tokens.data_ptr(), tokens.stride(0), pos_scores.data_ptr(),
+                                    pos_scores.stride(0), done.data_ptr(), out_len.data_ptr(), counters.data_ptr(),
+                                    max_len, min_len, pad, eos, L.stream_ptr()))

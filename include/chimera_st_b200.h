@@ -142,6 +142,52 @@ int cst_attention(const void* q, const void* k, const void* v, void* out, int dt
                   int B, int H, int n_q, int q_rows_per_seg, int n_kv, int kv_rows_per_seg,
                   const int32_t* kv_len, void* stream);
 
+/* ==== greedy incremental decoding from the memories (BASELINE configs[3] "encode + greedy decode")
+ * All four entry points read the current step from a DEVICE counter, so one captured CUDA graph of a decoding step is
+ * replayed for every step without a host round trip.  Activations of the decoder are fp32; weights fp32 or bf16
+ * (fp32 accumulation).  head_dim is 64. */
+
+/* x[b,:] = scale * embed[tokens[b, *step], :] + pos_table[*step, :]
+ * Replaces: embed_scale * embed_tokens(prev_output_tokens[:, -1:]) + embed_positions(...) of
+ * TransformerDecoder.extract_features_scriptable (fairseq/models/transformer.py:761-778);  pos_table row t is the
+ * sinusoidal embedding of position padding_idx + 1 + t (fairseq/modules/sinusoidal_positional_embedding.py:71-93).
+ * tokens int32 [B, ld_tok]; embed [V, C] (w_dtype); pos_table f32 [>= max steps, C]; x f32 [B, C]. */
+int cst_dec_embed(const int32_t* tokens, int ld_tok, const void* embed, int w_dtype, const float* pos_table,
+                  float scale, float* x, int B, int C, const int32_t* step, void* stream);
+
+/* out = act(LN?(A) W^T + bias) (+ residual) for M <= a few hundred rows (weight-streaming "skinny" linear).
+ * Replaces: the q/k/v/out projections of the incremental MultiheadAttention (fairseq/modules/multihead_attention.py:
+ * 189-379), fc1/fc2 and the three pre-LayerNorms of TransformerDecoderLayer.forward (fairseq/modules/
+ * transformer_layer.py:300-412), the final layer_norm + output_projection (fairseq/models/transformer.py:816-838).
+ *   A [M, K] (a_dtype, row stride lda), W [N, K] (w_dtype), K a multiple of 512; ln_gamma/ln_beta (K == 512): LayerNorm
+ *   (eps 1e-5) of each A row is applied before the product.  The N outputs are split into n_seg equal segments;
+ *   segment s is written to out[s][m*ldo[s] + (*step)*step_stride[s] + col]  (q | K-cache row | V-cache row).
+ *   residual [M, N] (row stride ldr, may alias out[0]) only with n_seg == 1.  step may be NULL (= 0). */
+typedef struct cst_dec_linear_params {
+  const void* A; const void* W; const float* bias; const float* ln_gamma; const float* ln_beta;
+  const float* residual; float* out[3];
+  long long lda, ldr, ldo[3], step_stride[3];
+  const int32_t* step;
+  int a_dtype, w_dtype, M, N, K, n_seg, act;
+} cst_dec_linear_params;
+int cst_dec_linear(const cst_dec_linear_params* p, void* stream);
+
+/* out[b, h*64:(h+1)*64] = softmax(q[b,h] . K[b, 0..n, h]^T) V[b, 0..n, h];  key row j of hypothesis b starts at
+ * k + b*kv_batch_stride + j*kv_row_stride.  n = *step + 1 when step != NULL (self-attention over the cache: the
+ * reference's saved_state prev_key/prev_value, multihead_attention.py:249-296), else n_keys (encoder-decoder attention
+ * over the M memories with the all-False padding mask, transformer_layer.py:371-392).  q is pre-scaled. */
+int cst_dec_attention(const float* q, long long ldq, const float* k, const float* v, long long kv_batch_stride,
+                      long long kv_row_stride, float* out, long long ldo, int B, int H, int n_keys, int n_keys_max,
+                      const int32_t* step, void* stream);
+
+/* One step of SequenceGenerator._generate for beam_size = 1 (fairseq/sequence_generator.py:294-540):
+ * lp = log_softmax(logits[b]); lp[pad] = -inf; step >= max_len: only EOS; step < min_len: no EOS; next = argmax.
+ * Unfinished rows: tokens[b, step+1] = next, pos_scores[b, step] = lp[next]; next == EOS => done[b] = 1,
+ * out_len[b] = step + 1.  counters int32[3]: [0] step (incremented by this call), [1] scratch, [2] rows finished. */
+int cst_dec_select(const float* logits, int V, int B, int32_t* tokens, int ld_tok, float* pos_scores, int ld_ps,
+                   int32_t* done, int32_t* out_len, int32_t* counters, int max_len, int min_len, int pad, int eos,
+                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -178,3 +178,92 @@ class EmuLib:
         Ov[:] = o
         self.calls.append("attention")
         return 0
+
+
+# ---- greedy decoding (cst_dec_*): same pointer-level semantics on host memory, fp32 -----------------------------------
+def _dec_embed(self, tokens, ld_tok, embed, w_dtype, pos_table, scale, x, B, Cd, step, stream):
+    assert w_dtype == F32
+    t = int(_mem(step, 1, np.int32)[0])
+    for b in range(B):
+        tok = int(_mem(tokens + 4 * (b * ld_tok + t), 1, np.int32)[0])
+        _mem(x + 4 * b * Cd, Cd)[:] = np.float32(scale) * _mem(embed + 4 * tok * Cd, Cd) + _mem(pos_table + 4 * t * Cd, Cd)
+    self.calls.append("dec_embed")
+    return 0
+
+
+def _dec_linear(self, pref, stream):
+    p = pref._obj
+    assert p.a_dtype == F32 and p.w_dtype == F32 and p.K % 512 == 0 and 1 <= p.n_seg <= 3 and p.N % p.n_seg == 0
+    step = int(_mem(p.step, 1, np.int32)[0]) if p.step else 0
+    A = torch.from_numpy(np.stack([_mem(p.A + 4 * m * p.lda, p.K).copy() for m in range(p.M)]))
+    W = torch.from_numpy(_mem(p.W, p.N * p.K).reshape(p.N, p.K).copy())
+    if p.ln_gamma:
+        assert p.K == 512
+        A = torch.nn.functional.layer_norm(A, (p.K,), torch.from_numpy(_mem(p.ln_gamma, p.K).copy()),
+                                           torch.from_numpy(_mem(p.ln_beta, p.K).copy()), 1e-5)
+    acc = A.double() @ W.double().T
+    if p.bias:
+        acc = acc + torch.from_numpy(_mem(p.bias, p.N).copy()).double()
+    if p.act == 2:
+        acc = torch.relu(acc)
+    else:
+        assert p.act == 0
+    acc = acc.float().numpy()
+    if p.residual:
+        assert p.n_seg == 1
+        acc = acc + np.stack([_mem(p.residual + 4 * m * p.ldr, p.N).copy() for m in range(p.M)])
+    sn = p.N // p.n_seg
+    for s in range(p.n_seg):
+        for m in range(p.M):
+            _mem(p.out[s] + 4 * (m * p.ldo[s] + step * p.step_stride[s]), sn)[:] = acc[m, s * sn:(s + 1) * sn]
+    self.calls.append("dec_linear")
+    return 0
+
+
+def _dec_attention(self, q, ldq, k, v, kv_bs, kv_rs, out, ldo, B, H, n_keys, n_max, step, stream):
+    n = min(int(_mem(step, 1, np.int32)[0]) + 1, n_max) if step else n_keys
+    for b in range(B):
+        qb = torch.from_numpy(_mem(q + 4 * b * ldq, H * 64).copy()).view(H, 64).double()
+        K = torch.from_numpy(np.stack([_mem(k + 4 * (b * kv_bs + j * kv_rs), H * 64).copy() for j in range(n)])).view(n, H, 64).double()
+        Vv = torch.from_numpy(np.stack([_mem(v + 4 * (b * kv_bs + j * kv_rs), H * 64).copy() for j in range(n)])).view(n, H, 64).double()
+        s = torch.einsum("hd,nhd->hn", qb, K)
+        o = torch.einsum("hn,nhd->hd", torch.softmax(s, -1), Vv)
+        _mem(out + 4 * b * ldo, H * 64)[:] = o.reshape(-1).float().numpy()
+    self.calls.append("dec_attention")
+    return 0
+
+
+def _dec_select(self, logits, V, B, tokens, ld_tok, pos_scores, ld_ps, done, out_len, counters, max_len, min_len, pad, eos,
+                stream):
+    cnt = _mem(counters, 3, np.int32)
+    step = int(cnt[0])
+    if step > max_len:
+        return 0
+    dn, ol = _mem(done, B, np.int32), _mem(out_len, B, np.int32)
+    for b in range(B):
+        lp = torch.log_softmax(torch.from_numpy(_mem(logits + 4 * b * V, V).copy()), -1)
+        lp[pad] = -math.inf
+        if step >= max_len:
+            lp[:eos] = -math.inf
+            lp[eos + 1:] = -math.inf
+        elif step < min_len:
+            lp[eos] = -math.inf
+        nxt = int(lp.argmax())
+        trow = _mem(tokens + 4 * b * ld_tok, ld_tok, np.int32)
+        if not dn[b]:
+            trow[step + 1] = nxt
+            _mem(pos_scores + 4 * b * ld_ps, ld_ps)[step] = float(lp[nxt])
+            if nxt == eos:
+                dn[b], ol[b] = 1, step + 1
+                cnt[2] += 1
+        else:
+            trow[step + 1] = eos
+    cnt[0] = step + 1
+    self.calls.append("dec_select")
+    return 0
+
+
+EmuLib.cst_dec_embed = _dec_embed
+EmuLib.cst_dec_linear = _dec_linear
+EmuLib.cst_dec_attention = _dec_attention
+EmuLib.cst_dec_select = _dec_select

@@ -1,0 +1,195 @@
+"""GPU parity of the greedy-decoding path (cst_dec_*, chimera-st_b200/decoder.py) -- BASELINE configs[3] "encode + greedy
+decode", north-star bar "identical greedy-decoded token IDs on a fixed synthetic set".
+
+Checkers: torch fp64 restatements per kernel; `oracle/decoder_oracle.py` (pinned to the reference's SequenceGenerator)
+for whole hypotheses; `tests/golden/greedy.npz` = tokens written by the UNMODIFIED reference model + generator."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import chimera_st_b200  # noqa: F401
+from chimera_st_b200 import synth, _lib as L
+from conftest import GOLDEN, rel_l2
+
+pytestmark = pytest.mark.gpu
+CASES = {"tiny": ([16000, 12345, 8000], 7), "c1mix": ([80000, 64000, 48123, 32000], 1234)}
+
+
+def _r(*shape, seed=0, scale=1.0):
+    return (torch.randn(*shape, generator=torch.Generator().manual_seed(seed)) * scale)
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 8, 512), (3, 512, 512), (64, 1536, 512), (37, 2048, 512), (64, 512, 2048),
+                                   (61, 10, 512), (130, 24, 1024), (64, 10000, 512)])
+@pytest.mark.parametrize("wdt", [torch.float32, torch.bfloat16])
+def test_dec_linear_plain_ln_relu_residual(M, N, K, wdt):
+    from chimera_st_b200 import ops
+    A, W, b = _r(M, K, seed=1), _r(N, K, seed=2, scale=K ** -0.5).to(wdt), _r(N, seed=3)
+    g, be, res = 1 + 0.1 * _r(K, seed=4), 0.1 * _r(K, seed=5), _r(M, N, seed=6)
+    Wd = W.double()
+    out = ops.dec_linear(A.cuda(), W.cuda(), b.cuda()).cpu()
+    assert rel_l2(out, A.double() @ Wd.T + b.double()) < 2e-6
+    out = ops.dec_linear(A.cuda(), W.cuda(), None, act=L.ACT_RELU, residual=res.cuda()).cpu()
+    assert rel_l2(out, torch.relu(A.double() @ Wd.T) + res.double()) < 2e-6
+    if K == 512:
+        ref = F.layer_norm(A.double(), (K,), g.double(), be.double(), 1e-5) @ Wd.T + b.double()
+        out = ops.dec_linear(A.cuda(), W.cuda(), b.cuda(), ln=(g.cuda(), be.cuda())).cpu()
+        assert rel_l2(out, ref) < 2e-6
+    # bf16 activations (bf16 memories feeding the cross-attention K/V projection)
+    Ab = A.to(torch.bfloat16)
+    out = ops.dec_linear(Ab.cuda(), W.cuda(), b.cuda()).cpu()
+    assert rel_l2(out, Ab.double() @ Wd.T + b.double()) < 2e-6
+
+
+def test_dec_linear_residual_in_place_and_segments_at_step():
+    from chimera_st_b200 import ops
+    B, T, step = 5, 9, 4
+    A, W, b = _r(B, 512, seed=1), _r(1536, 512, seed=2, scale=0.05), _r(1536, seed=3)
+    ref = A.double() @ W.double().T + b.double()
+    q = torch.zeros(B, 512, device="cuda")
+    kc, vc = torch.full((B, T, 512), 7.0, device="cuda"), torch.full((B, T, 512), 7.0, device="cuda")
+    st = torch.tensor([step, 0, 0, 0], dtype=torch.int32, device="cuda")
+    ops.dec_linear(A.cuda(), W.cuda(), b.cuda(), outs=[q, kc, vc], ldo=[512, T * 512, T * 512], step_stride=[0, 512, 512], step=st)
+    assert rel_l2(q.cpu(), ref[:, :512]) < 2e-6
+    assert rel_l2(kc[:, step].cpu(), ref[:, 512:1024]) < 2e-6 and rel_l2(vc[:, step].cpu(), ref[:, 1024:]) < 2e-6
+    keep = [t for t in range(T) if t != step]
+    assert bool((kc[:, keep] == 7.0).all()) and bool((vc[:, keep] == 7.0).all())       # only row `step` is written
+    x = _r(B, 512, seed=9).cuda()
+    x0 = x.clone()
+    ops.dec_linear(A.cuda(), W[:512].cuda(), b[:512].cuda(), residual=x, outs=[x])
+    assert rel_l2(x.cpu(), ref[:, :512] + x0.cpu().double()) < 2e-6
+
+
+@pytest.mark.parametrize("B,n", [(1, 1), (3, 5), (64, 33), (7, 202), (64, 64)])
+def test_dec_attention_self_cache_and_memory_layouts(B, n):
+    from chimera_st_b200 import ops
+    H, T = 8, max(n, 2) + 3
+    q, K, V = _r(B, 512, seed=1, scale=0.3), _r(B, T, 512, seed=2), _r(B, T, 512, seed=3)
+
+    def ref(K, V, n):
+        s = torch.einsum("bhd,bnhd->bhn", q.double().view(B, H, 64), K[:, :n].double().view(B, n, H, 64))
+        return torch.einsum("bhn,bnhd->bhd", torch.softmax(s, -1), V[:, :n].double().view(B, n, H, 64)).reshape(B, 512)
+    # self-attention over the cache: n = step + 1 keys, [B, T, 512] layout
+    st = torch.tensor([n - 1], dtype=torch.int32, device="cuda")
+    out = ops.dec_attention(q.cuda(), K.cuda(), V.cuda(), T * 512, 512, H, 0, T, step=st).cpu()
+    assert rel_l2(out, ref(K, V, n)) < 2e-6
+    # cross-attention over memories: key-major [n, B, 512] layout, explicit n
+    Km, Vm = K[:, :n].transpose(0, 1).contiguous(), V[:, :n].transpose(0, 1).contiguous()
+    out = ops.dec_attention(q.cuda(), Km.cuda(), Vm.cuda(), 512, B * 512, H, n, n).cpu()
+    assert rel_l2(out, ref(K, V, n)) < 2e-6
+
+
+def test_dec_select_rules_and_step_protocol():
+    from chimera_st_b200 import ops
+    B, V, max_len = 6, 10000, 3
+    T = max_len + 2
+    tokens = torch.full((B, T), 2, dtype=torch.int32, device="cuda")
+    ps = torch.zeros(B, T, device="cuda")
+    done, out_len = torch.zeros(B, dtype=torch.int32, device="cuda"), torch.zeros(B, dtype=torch.int32, device="cuda")
+    cnt = torch.zeros(4, dtype=torch.int32, device="cuda")
+    exp_tokens = [[] for _ in range(B)]
+    fin = [False] * B
+    for step in range(max_len + 1):
+        lg = _r(B, V, seed=100 + step)
+        lg[0, 1] = 50.0                       # pad is the raw arg-max of row 0: never selected
+        lg[1, 2] = 40.0                       # EOS is the arg-max of row 1: forbidden at step 0 (min_len = 1), ends it at step 1
+        if step == 2:
+            lg[2, 2] = 60.0                   # row 2 ends at step 2
+        ops.dec_select(lg.cuda(), tokens, ps, done, out_len, cnt, max_len, min_len=1)
+        lp = torch.log_softmax(lg.double(), -1)
+        lp[:, 1] = -math.inf
+        if step >= max_len:
+            lp[:, :2] = -math.inf
+            lp[:, 3:] = -math.inf
+        elif step < 1:
+            lp[:, 2] = -math.inf
+        nxt = lp.argmax(-1)
+        for b in range(B):
+            if not fin[b]:
+                exp_tokens[b].append(int(nxt[b]))
+                assert abs(float(ps[b, step]) - float(lp[b, nxt[b]])) < 1e-4
+                fin[b] = int(nxt[b]) == 2
+        assert int(cnt[0]) == step + 1 and int(cnt[1]) == 0 and int(cnt[2]) == sum(fin)
+    assert all(fin)
+    tk, ol = tokens.cpu(), out_len.cpu()
+    for b in range(B):
+        assert tk[b, 1:int(ol[b]) + 1].tolist() == exp_tokens[b]
+    assert int(ol[1]) == 2 and int(ol[2]) == 3 and int(ol[3]) == max_len + 1
+    ops.dec_select(lg.cuda(), tokens, ps, done, out_len, cnt, max_len)              # past the end: no-op
+    assert int(cnt[0]) == max_len + 1 and torch.equal(tokens.cpu(), tk)
+
+
+@pytest.mark.parametrize("name", ["tiny", "c1mix"])
+def test_greedy_decode_of_reference_memories_matches_oracle_and_golden(name):
+    """fp32 decoder on the reference's own memories: the reference generator's tokens, oracle log-probs; CUDA-graph
+    replay identical to plain launches."""
+    from chimera_st_b200.decoder import B200GreedyDecoder
+    from oracle import decoder_oracle as Dm
+    g, gg = np.load(os.path.join(GOLDEN, name + ".npz")), np.load(os.path.join(GOLDEN, "greedy.npz"))
+    mem = torch.from_numpy(g["memories"])
+    dsd = synth.make_decoder_state_dict(seed=int(gg["decoder_seed"]))
+    max_len = int(gg["max_len_b"])
+    gold = [[x for x in row.tolist() if x >= 0] for row in gg[name + "_tokens"]]
+    outs = []
+    for use_graph in (False, True):
+        dec = B200GreedyDecoder(dsd, dtype=torch.float32, device="cuda", use_graph=use_graph)
+        hyp = dec.generate(mem.cuda(), max_len=max_len)
+        assert [h["tokens"].tolist() for h in hyp] == gold
+        assert dec.last_launches == 6 + dec.last_steps * 51
+        hyp2 = dec.generate(mem.cuda(), max_len=max_len)                 # plan / graph reuse
+        assert [h["tokens"].tolist() for h in hyp2] == gold
+        outs.append(hyp)
+    for a, b in zip(*outs):
+        assert torch.equal(a["positional_scores"], b["positional_scores"])
+    # per-token log-probs against the oracle decoder, teacher-forced on the same tokens
+    with torch.no_grad():
+        for b, h in enumerate(outs[0]):
+            prev = torch.tensor([[2] + h["tokens"].tolist()[:-1]])
+            for t in range(0, prev.shape[1], 7):
+                lp = torch.log_softmax(Dm.decoder_logits(dsd, prev[:, :t + 1], mem[:, b:b + 1]).float(), -1)
+                assert abs(float(lp[0, h["tokens"][t]]) - float(h["positional_scores"][t])) < 2e-4
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("name", ["tiny", "c1mix"])
+def test_encode_then_decode_on_gpu_gives_reference_token_ids(name, dtype):
+    """waveform -> B200 encoder -> B200 greedy decoder == tokens of the unmodified reference model + SequenceGenerator."""
+    from chimera_st_b200.encoder import build_encoder_from_state_dict
+    from chimera_st_b200.decoder import B200GreedyDecoder
+    gg = np.load(os.path.join(GOLDEN, "greedy.npz"))
+    lens, seed = CASES[name]
+    wave, tl = synth.make_waveforms(lens, seed=seed)
+    enc = build_encoder_from_state_dict(synth.make_state_dict(seed=0), dtype=dtype, device="cuda", use_graph=False)
+    dec = B200GreedyDecoder(synth.make_decoder_state_dict(seed=int(gg["decoder_seed"])), dtype=dtype, device="cuda")
+    mem = enc(wave.cuda(), tl.cuda()).encoder_out
+    hyp = dec.generate(mem, max_len=int(gg["max_len_b"]))
+    gold = [[x for x in row.tolist() if x >= 0] for row in gg[name + "_tokens"]]
+    assert [h["tokens"].tolist() for h in hyp] == gold
+
+
+def test_c4_shape_batch64_m64_matches_oracle():
+    """BASELINE configs[3] decode shape: 64 hypotheses over M = 64 memories (synthetic memories), short max_len so
+    that the CPU oracle finishes in seconds; every hypothesis runs into the forced EOS or ends earlier."""
+    from chimera_st_b200.decoder import B200GreedyDecoder
+    from oracle import decoder_oracle as Dm
+    mem = _r(64, 64, 512, seed=5)
+    dsd = synth.make_decoder_state_dict(seed=1)
+    dec = B200GreedyDecoder(dsd, dtype=torch.float32, device="cuda")
+    hyp = dec.generate(mem.cuda(), max_len=12)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    ref, margins = Dm.greedy_decode(dsd, mem, max_len=12, return_margins=True)
+    for b, h in enumerate(hyp):
+        if margins[b] > 1e-3:                 # an arg-max closer than that to a tie may legitimately flip in fp32
+            assert h["tokens"].tolist() == ref[b], b
+    assert sum(m > 1e-3 for m in margins) >= 60
+
+
+def test_decoder_rejects_host_tensors():
+    from chimera_st_b200.decoder import B200GreedyDecoder
+    dec = B200GreedyDecoder(synth.make_decoder_state_dict(seed=1), device="cuda")
+    with pytest.raises(L.CstError):
+        dec.generate(torch.zeros(16, 2, 512))
