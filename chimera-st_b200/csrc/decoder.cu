@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(128) dec_attention_kernel(const float* __restr
   const int wid = blockIdx.x * 4 + warp;
   if (wid >= B * H) return;
   const int b = wid / H, h = wid - b * H;
-  float* sq = da_smem + (size_t)warp * (64 + n_max);
+  float* sq = da_smem + (size_t)warp * (64 + ((n_max + 3) & ~3));   // 16-byte aligned per warp
   float* ss = sq + 64;
   const int n = step ? min(*step + 1, n_max) : n_keys;
   sq[lane] = q[(size_t)b * ldq + h * 64 + lane];
@@ -352,7 +352,7 @@ extern "C" int cst_dec_attention(const float* q, long long ldq, const float* k, 
   CST_REQUIRE(q && k && v && out, "cst_dec_attention: null pointer");
   CST_REQUIRE(B > 0 && H > 0 && n_keys_max > 0 && (step || (n_keys > 0 && n_keys <= n_keys_max)), "cst_dec_attention: bad sizes");
   CST_REQUIRE(kv_row_stride % 4 == 0 && kv_batch_stride % 4 == 0 && ldo % 2 == 0, "cst_dec_attention: strides must keep 16-byte rows");
-  const size_t smem = 4 * (size_t)(64 + n_keys_max) * sizeof(float);
+  const size_t smem = 4 * (size_t)(64 + ((n_keys_max + 3) & ~3)) * sizeof(float);
   CST_REQUIRE(smem <= 48 * 1024, "cst_dec_attention: n_keys_max=%d too large", n_keys_max);
   CST_CHECK_CUDA(launch_k(dec_attention_kernel, dim3(cdiv((long long)B * H, 4)), dim3(128), smem, (cudaStream_t)stream, q, ldq, k, v,
                           kv_batch_stride, kv_row_stride, out, ldo, B, H, n_keys, n_keys_max, step));
