@@ -19,16 +19,27 @@
 
 namespace cst {
 
-constexpr int DL_ROWS = 64;                 // hypotheses per CTA (8 warps x 8 rows)
-constexpr int DL_COLS = 8;                  // output features per CTA
-constexpr int DL_KC = 512;                  // K chunk resident in shared memory
-constexpr int DL_THREADS = 256;
-constexpr int DL_SMEM = (DL_ROWS * DL_KC + DL_COLS * DL_KC) * 4;
+constexpr int DL_COLS = 8;                  // output features per column tile
+constexpr int DL_THREADS = 256;             // 8 warps
+constexpr int DL_A_BYTES = 8 * 4096 * 4;    // every warp keeps RPW rows x K = 4096 fp32 activations resident (128 KB per CTA)
 
-// exchange-and-add step of the 64 -> 2 transposing warp reduction: afterwards v[0..N/2) hold the sums of the index
-// half selected by lane bit `off`
-template <int N>
-__device__ __forceinline__ void bfly(float (&v)[64], int off, int lane) {
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 lds4(const __nv_bfloat16* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16),
+                     __uint_as_float(u.y & 0xffff0000u));
+}
+
+// exchange-and-add step of the transposing warp reduction: afterwards v[0..N/2) hold the sums of the index half
+// selected by lane bit `off`
+template <int N, int NV>
+__device__ __forceinline__ void bfly(float (&v)[NV], int off, int lane) {
   const bool up = (lane & off) != 0;
 #pragma unroll
   for (int i = 0; i < N / 2; ++i) {
@@ -36,6 +47,18 @@ __device__ __forceinline__ void bfly(float (&v)[64], int off, int lane) {
     const float send = up ? v[i] : v[i + N / 2];
     v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
   }
+}
+// NV per-lane partial sums -> full sums: NV >= 32: lane holds indices lane*(NV/32) + j in v[j]; NV < 32: index lane / (32/NV) in v[0]
+template <int NV>
+__device__ __forceinline__ void warp_transpose_reduce(float (&v)[NV], int lane) {
+  if constexpr (NV >= 2) bfly<NV, NV>(v, 16, lane);
+  if constexpr (NV >= 4) bfly<NV / 2, NV>(v, 8, lane);
+  if constexpr (NV >= 8) bfly<NV / 4, NV>(v, 4, lane);
+  if constexpr (NV >= 16) bfly<NV / 8, NV>(v, 2, lane);
+  if constexpr (NV >= 32) bfly<NV / 16, NV>(v, 1, lane);
+  if constexpr (NV < 32) v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+  if constexpr (NV < 16) v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
+  if constexpr (NV < 8) v[0] += __shfl_xor_sync(0xffffffffu, v[0], 4);
 }
 
 struct DecLinearArgs {
@@ -45,111 +68,164 @@ struct DecLinearArgs {
   float* out0; float* out1; float* out2;
   long long ldo0, ldo1, ldo2, ss0, ss1, ss2;
   const int* step;
-  int M, N, K, seg_n, act;
+  int M, N, seg_n, act;
 };
 
-// Warp w of a CTA owns rows 8w..8w+7 of the CTA's 64-row block and all 8 output columns; a lane owns the K positions
-// 4*lane + 128*j.  Per K chunk a lane does 8 + 8 LDS.128 for 256 FMAs; the 64 partial sums per lane are reduced
-// across the warp with 62 shuffles (bfly) and land as outputs (row = lane/4, col = 2*(lane%4) + {0,1}).
-// The A rows of a warp are private to it (loaded, optionally LayerNorm-ed, and read back by the same warp).
-template <typename AT, typename WT>
+// K = 4096 / RPW is a compile-time constant (512, 1024, 2048).  A CTA owns 8*RPW rows (warp w: rows w*RPW ...), keeps
+// them resident in shared memory for its whole life (cp.async, all rows in flight at once; optionally LayerNorm-ed in
+// place by the owning warp) and walks over 8-column weight tiles t = blockIdx.x, += gridDim.x (K = 512: the next
+// tile's weights are prefetched with cp.async into the other buffer while this one is multiplied).  A lane owns the
+// K positions 4*lane + 128*j; per 128-wide K step it does 8 + RPW LDS.128 for 32*RPW FMAs; the RPW*8 partial sums per
+// lane are reduced across the warp by a transposing butterfly (62 shuffles for 64 values).
+template <typename AT, typename WT, int RPW>
 __global__ void __launch_bounds__(DL_THREADS, 1) dec_linear_kernel(const DecLinearArgs a) {
-  extern __shared__ __align__(16) float dl_smem[];
-  float* sW = dl_smem + DL_ROWS * DL_KC;
+  constexpr int K = 4096 / RPW, NV = RPW * 8, NBUF = (K == 512) ? 2 : 1;
+  constexpr int W_UNITS_PER_COL = K * (int)sizeof(WT) / 16, W_ELEMS_PER_UNIT = 16 / (int)sizeof(WT);
+  extern __shared__ __align__(16) unsigned char dl_smem[];
+  float* sA = reinterpret_cast<float*>(dl_smem);
+  WT* sW = reinterpret_cast<WT*>(dl_smem + DL_A_BYTES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * DL_COLS;
-  const int m0 = blockIdx.y * DL_ROWS + warp * 8;
-  const int rows_here = min(8, a.M - m0);                     // warp-uniform; may be <= 0
-  float* myA = dl_smem + warp * 8 * DL_KC;
+  const int m0 = blockIdx.y * 8 * RPW + warp * RPW;
+  const int rows_here = min(RPW, a.M - m0);                    // warp-uniform; may be <= 0
+  float* myA = sA + warp * RPW * K;
   const AT* A = reinterpret_cast<const AT*>(a.A);
   const WT* W = reinterpret_cast<const WT*>(a.W);
-  const bool ln = a.ln_g != nullptr;
+  const int ntiles = (a.N + DL_COLS - 1) / DL_COLS;
   pdl_launch_dependents();
-  pdl_wait();
 
-  float acc[64];
-#pragma unroll
-  for (int i = 0; i < 64; ++i) acc[i] = 0.f;
-
-  for (int k0 = 0; k0 < a.K; k0 += DL_KC) {
-    if (k0) __syncthreads();                                  // previous chunk's sW is still being read
-    for (int i = threadIdx.x; i < DL_COLS * DL_KC / 4; i += DL_THREADS) {
-      const int c = i / (DL_KC / 4), kk = (i % (DL_KC / 4)) * 4;
-      const int n = n0 + c;
-      float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (n < a.N) w = load4(W + (size_t)n * a.K + k0 + kk);
-      *reinterpret_cast<float4*>(sW + c * DL_KC + kk) = w;
+  auto load_w = [&](int tile, int buf) {
+    WT* dst = sW + (size_t)buf * DL_COLS * K;
+    for (int u = threadIdx.x; u < DL_COLS * W_UNITS_PER_COL; u += DL_THREADS) {
+      const int c = u / W_UNITS_PER_COL, e = (u - c * W_UNITS_PER_COL) * W_ELEMS_PER_UNIT;
+      const int n = tile * DL_COLS + c;
+      if (n < a.N) cp_async16(dst + c * K + e, W + (size_t)n * K + e);
+      else *reinterpret_cast<uint4*>(dst + c * K + e) = make_uint4(0u, 0u, 0u, 0u);
     }
-    for (int r = 0; r < 8; ++r) {
-      float4 v[4];
+  };
+
+  int t = blockIdx.x;
+  if (NBUF == 2 && t < ntiles) load_w(t, 0);                   // weights do not depend on the previous kernel
+  pdl_wait();
 #pragma unroll
-      for (int j = 0; j < 4; ++j) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int r = 0; r < RPW; ++r) {
+#pragma unroll
+    for (int j = 0; j < K / 128; ++j) {
+      float* dst = myA + r * K + 4 * lane + 128 * j;
       if (r < rows_here) {
-        const AT* row = A + (size_t)(m0 + r) * a.lda + k0 + 4 * lane;
+        const AT* src = A + (size_t)(m0 + r) * a.lda + 4 * lane + 128 * j;
+        if constexpr (sizeof(AT) == 4) cp_async16(dst, src);
+        else *reinterpret_cast<float4*>(dst) = load4(src);
+      } else {
+        *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  }
+  cp_async_commit();
+
+  const long long step = a.step ? (long long)*a.step : 0;
+  for (int it = 0; t < ntiles; t += gridDim.x, ++it) {
+    const int buf = NBUF == 2 ? (it & 1) : 0;
+    if (NBUF == 1) load_w(t, 0);
+    else if (t + (int)gridDim.x < ntiles) load_w(t + gridDim.x, buf ^ 1);
+    cp_async_commit();
+    cp_async_wait<NBUF - 1>();
+    __syncthreads();
+    if constexpr (K == 512) if (it == 0 && a.ln_g != nullptr) {   // K == 512: LayerNorm of this warp's own rows, in place
+      // three sweeps over the warp's rows so that the RPW shuffle reductions of a sweep are independent chains
+      float mean[RPW], rstd[RPW];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = load4(row + 128 * j);
-        if (ln) {                                             // K == 512: the whole row is in this warp's registers
-          float s = 0.f;
+      for (int r = 0; r < RPW; ++r) {
+        float s = 0.f;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
-          const float mean = warp_sum(s) * (1.0f / DL_KC);
-          float q = 0.f;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            v[j].x -= mean; v[j].y -= mean; v[j].z -= mean; v[j].w -= mean;
-            q += (v[j].x * v[j].x + v[j].y * v[j].y) + (v[j].z * v[j].z + v[j].w * v[j].w);
-          }
-          const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / DL_KC) + 1e-5f);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 g = load4(a.ln_g + 4 * lane + 128 * j), b = load4(a.ln_b + 4 * lane + 128 * j);
-            v[j].x = v[j].x * rstd * g.x + b.x; v[j].y = v[j].y * rstd * g.y + b.y;
-            v[j].z = v[j].z * rstd * g.z + b.z; v[j].w = v[j].w * rstd * g.w + b.w;
-          }
+        for (int j = 0; j < K / 128; ++j) {
+          const float4 v = *reinterpret_cast<const float4*>(myA + r * K + 4 * lane + 128 * j);
+          s += (v.x + v.y) + (v.z + v.w);
         }
+        mean[r] = s;
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(myA + r * DL_KC + 4 * lane + 128 * j) = v[j];
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int r = 0; r < RPW; ++r) mean[r] += __shfl_xor_sync(0xffffffffu, mean[r], o);
+      }
+#pragma unroll
+      for (int r = 0; r < RPW; ++r) {
+        mean[r] *= (1.0f / K);
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < K / 128; ++j) {
+          float4 v = *reinterpret_cast<const float4*>(myA + r * K + 4 * lane + 128 * j);
+          v.x -= mean[r]; v.y -= mean[r]; v.z -= mean[r]; v.w -= mean[r];
+          q += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+        }
+        rstd[r] = q;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int r = 0; r < RPW; ++r) rstd[r] += __shfl_xor_sync(0xffffffffu, rstd[r], o);
+      }
+#pragma unroll
+      for (int r = 0; r < RPW; ++r) rstd[r] = 1.0f / sqrtf(rstd[r] * (1.0f / K) + 1e-5f);
+#pragma unroll
+      for (int j = 0; j < K / 128; ++j) {
+        const float4 g = load4(a.ln_g + 4 * lane + 128 * j), b = load4(a.ln_b + 4 * lane + 128 * j);
+#pragma unroll
+        for (int r = 0; r < RPW; ++r) {
+          float4 v = *reinterpret_cast<const float4*>(myA + r * K + 4 * lane + 128 * j);
+          v.x = (v.x - mean[r]) * rstd[r] * g.x + b.x; v.y = (v.y - mean[r]) * rstd[r] * g.y + b.y;
+          v.z = (v.z - mean[r]) * rstd[r] * g.z + b.z; v.w = (v.w - mean[r]) * rstd[r] * g.w + b.w;
+          *reinterpret_cast<float4*>(myA + r * K + 4 * lane + 128 * j) = v;
+        }
+      }
+      __syncwarp();
     }
-    __syncthreads();
     if (rows_here > 0) {
+      const WT* wt = sW + (size_t)buf * DL_COLS * K;
+      float acc[NV];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) acc[i] = 0.f;
 #pragma unroll 1
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < K / 128; ++j) {
         float4 w[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) w[c] = *reinterpret_cast<const float4*>(sW + c * DL_KC + 4 * lane + 128 * j);
+        for (int c = 0; c < 8; ++c) w[c] = lds4(wt + c * K + 4 * lane + 128 * j);
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          const float4 x = *reinterpret_cast<const float4*>(myA + r * DL_KC + 4 * lane + 128 * j);
+        for (int r = 0; r < RPW; ++r) {
+          const float4 x = *reinterpret_cast<const float4*>(myA + r * K + 4 * lane + 128 * j);
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
-            float t = acc[r * 8 + c];
-            t = fmaf(x.x, w[c].x, t); t = fmaf(x.y, w[c].y, t); t = fmaf(x.z, w[c].z, t); t = fmaf(x.w, w[c].w, t);
-            acc[r * 8 + c] = t;
+            float v = acc[r * 8 + c];
+            v = fmaf(x.x, w[c].x, v); v = fmaf(x.y, w[c].y, v); v = fmaf(x.z, w[c].z, v); v = fmaf(x.w, w[c].w, v);
+            acc[r * 8 + c] = v;
+          }
+        }
+      }
+      warp_transpose_reduce<NV>(acc, lane);
+      constexpr int VPL = NV >= 32 ? NV / 32 : 1;              // outputs per lane
+      constexpr int LPV = NV >= 32 ? 1 : 32 / NV;              // lanes holding the same output
+      if (lane % LPV == 0) {
+#pragma unroll
+        for (int j = 0; j < VPL; ++j) {
+          const int idx = NV >= 32 ? lane * VPL + j : lane / LPV;
+          const int m = m0 + idx / 8, n = t * DL_COLS + (idx & 7);
+          if (m < a.M && n < a.N) {
+            float v = acc[j];
+            if (a.bias) v += a.bias[n];
+            if (a.act == CST_ACT_RELU) v = fmaxf(v, 0.f);
+            const int seg = n / a.seg_n, col = n - seg * a.seg_n;
+            if (a.residual) v += a.residual[(size_t)m * a.ldr + n];
+            float* o = seg == 0 ? a.out0 : (seg == 1 ? a.out1 : a.out2);
+            const long long ldo = seg == 0 ? a.ldo0 : (seg == 1 ? a.ldo1 : a.ldo2);
+            const long long ss = seg == 0 ? a.ss0 : (seg == 1 ? a.ss1 : a.ss2);
+            o[(size_t)m * ldo + step * ss + col] = v;
           }
         }
       }
     }
+    __syncthreads();                                           // the weight buffer just read is the next prefetch target
   }
-  if (rows_here <= 0) return;
-  bfly<64>(acc, 16, lane); bfly<32>(acc, 8, lane); bfly<16>(acc, 4, lane); bfly<8>(acc, 2, lane); bfly<4>(acc, 1, lane);
-  const int m = m0 + (lane >> 2);
-  if (m >= a.M) return;
-  const long long step = a.step ? (long long)*a.step : 0;
-#pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    const int n = n0 + 2 * (lane & 3) + j;
-    if (n >= a.N) continue;
-    float v = acc[j];
-    if (a.bias) v += a.bias[n];
-    if (a.act == CST_ACT_RELU) v = fmaxf(v, 0.f);
-    const int seg = n / a.seg_n, col = n - seg * a.seg_n;
-    if (a.residual) v += a.residual[(size_t)m * a.ldr + n];
-    float* o = seg == 0 ? a.out0 : (seg == 1 ? a.out1 : a.out2);
-    const long long ldo = seg == 0 ? a.ldo0 : (seg == 1 ? a.ldo1 : a.ldo2);
-    const long long ss = seg == 0 ? a.ss0 : (seg == 1 ? a.ss1 : a.ss2);
-    o[(size_t)m * ldo + step * ss + col] = v;
-  }
+  cp_async_wait<0>();
 }
 
 // x[b,:] = scale * E[tokens[b, step], :] + pos[step, :]
@@ -167,80 +243,125 @@ __global__ void dec_embed_kernel(const int* __restrict__ tokens, int ld_tok, con
   }
 }
 
-// one warp per (hypothesis, head); head_dim 64; q pre-scaled.  n keys = *step + 1 (self-attention over the cache) or
-// n_keys (cross-attention over the memories; the reference passes an all-False key-padding mask).
-__global__ void __launch_bounds__(128) dec_attention_kernel(const float* __restrict__ q, long long ldq,
-                                                            const float* __restrict__ k, const float* __restrict__ v,
-                                                            long long kv_bs, long long kv_rs, float* __restrict__ out,
-                                                            long long ldo, int B, int H, int n_keys, int n_max,
-                                                            const int* __restrict__ step) {
-  extern __shared__ __align__(16) float da_smem[];
+// one CTA (8 warps) per (hypothesis, head); head_dim 64; q pre-scaled.  n keys = *step + 1 (self-attention over the
+// cache) or n_keys (cross-attention over the memories; the reference passes an all-False key-padding mask).
+// Scores: 4 lanes per key (16 dims each, 4 independent LDG.128 per lane), 8 keys per warp pass, 64 keys per CTA pass;
+// fp32 softmax over the score row in shared memory; PV: warp w accumulates keys w, w+8, ... (lane = 2 output dims,
+// coalesced 256-byte V rows), the 8 partial rows are summed through shared memory.
+constexpr int DA_THREADS = 256;
+__global__ void __launch_bounds__(DA_THREADS) dec_attention_kernel(const float* __restrict__ q, long long ldq,
+                                                                   const float* __restrict__ k, const float* __restrict__ v,
+                                                                   long long kv_bs, long long kv_rs, float* __restrict__ out,
+                                                                   long long ldo, int H, int n_keys, int n_max,
+                                                                   const int* __restrict__ step) {
+  extern __shared__ __align__(16) float da_smem[];            // [64 q][8*64 partial o][16 red][n_max scores]
+  float* sq = da_smem;
+  float* po = da_smem + 64;
+  float* red = po + 8 * 64;
+  float* ss = red + 16;
   pdl_launch_dependents();
   pdl_wait();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int wid = blockIdx.x * 4 + warp;
-  if (wid >= B * H) return;
-  const int b = wid / H, h = wid - b * H;
-  float* sq = da_smem + (size_t)warp * (64 + ((n_max + 3) & ~3));   // 16-byte aligned per warp
-  float* ss = sq + 64;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.x / H, h = blockIdx.x - b * H;
   const int n = step ? min(*step + 1, n_max) : n_keys;
-  sq[lane] = q[(size_t)b * ldq + h * 64 + lane];
-  sq[lane + 32] = q[(size_t)b * ldq + h * 64 + lane + 32];
-  __syncwarp();
+  if (tid < 64) sq[tid] = q[(size_t)b * ldq + h * 64 + tid];
+  __syncthreads();
   const float* kb = k + (size_t)b * kv_bs + h * 64;
   const float* vb = v + (size_t)b * kv_bs + h * 64;
-  float mx = -INFINITY;
-  for (int key = lane; key < n; key += 32) {
-    const float* kr = kb + (size_t)key * kv_rs;
-    float s = 0.f;
+  const int sub = lane & 3;                                    // which 16-dim quarter of the head this lane covers
+  float4 qq[4];
 #pragma unroll
-    for (int d = 0; d < 16; ++d) {
-      const float4 kk = load4(kr + 4 * d), qq = *reinterpret_cast<const float4*>(sq + 4 * d);
-      s = fmaf(kk.x, qq.x, s); s = fmaf(kk.y, qq.y, s); s = fmaf(kk.z, qq.z, s); s = fmaf(kk.w, qq.w, s);
+  for (int d = 0; d < 4; ++d) qq[d] = *reinterpret_cast<const float4*>(sq + 16 * sub + 4 * d);
+  float mx = -INFINITY;
+  for (int key0 = 0; key0 < n; key0 += 64) {
+    const int key = key0 + warp * 8 + (lane >> 2);
+    float s = 0.f;
+    if (key < n) {
+      const float* kr = kb + (size_t)key * kv_rs + 16 * sub;
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        const float4 kk = load4(kr + 4 * d);
+        s = fmaf(kk.x, qq[d].x, s); s = fmaf(kk.y, qq[d].y, s); s = fmaf(kk.z, qq[d].z, s); s = fmaf(kk.w, qq[d].w, s);
+      }
     }
-    ss[key] = s;
-    mx = fmaxf(mx, s);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    if (key < n) {
+      if (sub == 0) ss[key] = s;
+      mx = fmaxf(mx, s);
+    }
   }
   mx = warp_max(mx);
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = red[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
   float sum = 0.f;
-  for (int key = lane; key < n; key += 32) {
+  for (int key = tid; key < n; key += DA_THREADS) {
     const float p = expf(ss[key] - mx);
     ss[key] = p;
     sum += p;
   }
   sum = warp_sum(sum);
-  __syncwarp();
+  if (lane == 0) red[8 + warp] = sum;
+  __syncthreads();
   float o0 = 0.f, o1 = 0.f;
-  for (int key = 0; key < n; ++key) {
+  for (int key = warp; key < n; key += 8) {
     const float p = ss[key];
     const float2 vv = *reinterpret_cast<const float2*>(vb + (size_t)key * kv_rs + 2 * lane);
     o0 = fmaf(p, vv.x, o0);
     o1 = fmaf(p, vv.y, o1);
   }
-  const float inv = 1.0f / sum;
-  *reinterpret_cast<float2*>(out + (size_t)b * ldo + h * 64 + 2 * lane) = make_float2(o0 * inv, o1 * inv);
+  *reinterpret_cast<float2*>(po + warp * 64 + 2 * lane) = make_float2(o0, o1);
+  __syncthreads();
+  if (tid < 64) {
+    float tot = 0.f, o = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { tot += red[8 + w]; o += po[w * 64 + tid]; }
+    out[(size_t)b * ldo + h * 64 + tid] = o / tot;
+  }
 }
 
 // counters: [0] step, [1] CTAs finished (scratch), [2] hypotheses finished
-__global__ void __launch_bounds__(256) dec_select_kernel(const float* __restrict__ logits, int V, int* __restrict__ tokens,
-                                                         int ld_tok, float* __restrict__ pos_scores, int ld_ps,
-                                                         int* __restrict__ done, int* __restrict__ out_len,
-                                                         int* counters, int max_len, int min_len, int pad, int eos) {
-  __shared__ float s_f[8];
-  __shared__ float s_b[8];
-  __shared__ int s_i[8];
+constexpr int DS_THREADS = 1024;
+__global__ void __launch_bounds__(DS_THREADS) dec_select_kernel(const float* __restrict__ logits, int V, int* __restrict__ tokens,
+                                                                int ld_tok, float* __restrict__ pos_scores, int ld_ps,
+                                                                int* __restrict__ done, int* __restrict__ out_len,
+                                                                int* counters, int max_len, int min_len, int pad, int eos) {
+  __shared__ float s_f[32];
+  __shared__ float s_b[32];
+  __shared__ int s_i[32];
   pdl_launch_dependents();
   pdl_wait();
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int step = *reinterpret_cast<volatile int*>(counters);
   const float* row = logits + (size_t)b * V;
+  const bool only_eos = step >= max_len, no_eos = step < min_len;
+  // the row stays in registers for both sweeps: V <= 3 * 4 * 1024 elements take the vector path (V % 4 == 0)
+  constexpr int NV4 = 3;
+  float4 x[NV4];
+  const bool vec = (V % 4 == 0) && (V <= NV4 * 4 * DS_THREADS);
   float m_all = -INFINITY, best = -INFINITY;
   int bi = 0x7fffffff;
-  for (int i = tid; i < V; i += 256) {
-    const float x = row[i];
-    m_all = fmaxf(m_all, x);
-    const bool allowed = (i != pad) && (step >= max_len ? (i == eos) : (step < min_len ? (i != eos) : true));
-    if (allowed && x > best) { best = x; bi = i; }             // ascending i per thread: first maximum wins
+  auto consider = [&](float v, int i) {
+    m_all = fmaxf(m_all, v);
+    const bool allowed = (i != pad) && (only_eos ? (i == eos) : (no_eos ? (i != eos) : true));
+    if (allowed && (v > best || (v == best && i < bi))) { best = v; bi = i; }
+  };
+  if (vec) {
+#pragma unroll
+    for (int u = 0; u < NV4; ++u) {
+      const int i = 4 * (tid + u * DS_THREADS);
+      x[u] = i < V ? load4(row + i) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    }
+#pragma unroll
+    for (int u = 0; u < NV4; ++u) {
+      const int i = 4 * (tid + u * DS_THREADS);
+      if (i < V) { consider(x[u].x, i); consider(x[u].y, i + 1); consider(x[u].z, i + 2); consider(x[u].w, i + 3); }
+    }
+  } else {
+    for (int i = tid; i < V; i += DS_THREADS) consider(row[i], i);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -253,20 +374,26 @@ __global__ void __launch_bounds__(256) dec_select_kernel(const float* __restrict
   __syncthreads();
   m_all = s_f[0]; best = s_b[0]; bi = s_i[0];
 #pragma unroll
-  for (int w = 1; w < 8; ++w) {
+  for (int w = 1; w < DS_THREADS / 32; ++w) {
     m_all = fmaxf(m_all, s_f[w]);
     if (s_b[w] > best || (s_b[w] == best && s_i[w] < bi)) { best = s_b[w]; bi = s_i[w]; }
   }
   __syncthreads();
   float sum = 0.f;
-  for (int i = tid; i < V; i += 256) sum += expf(row[i] - m_all);
+  if (vec) {
+#pragma unroll
+    for (int u = 0; u < NV4; ++u)     // padding lanes hold -inf: expf(-inf) = 0
+      sum += (expf(x[u].x - m_all) + expf(x[u].y - m_all)) + (expf(x[u].z - m_all) + expf(x[u].w - m_all));
+  } else {
+    for (int i = tid; i < V; i += DS_THREADS) sum += expf(row[i] - m_all);
+  }
   sum = warp_sum(sum);
   if (lane == 0) s_f[warp] = sum;
   __syncthreads();
   if (tid == 0) {
     sum = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) sum += s_f[w];
+    for (int w = 0; w < DS_THREADS / 32; ++w) sum += s_f[w];
     if (bi < 0 || bi >= V) { bi = eos; best = row[eos]; }      // nothing selectable (non-finite logits): stop the hypothesis
     const float lp = best - (m_all + logf(sum));
     if (step > max_len) return;                                // replayed past the last step: nothing to do
@@ -285,6 +412,23 @@ __global__ void __launch_bounds__(256) dec_select_kernel(const float* __restrict
   }
 }
 
+// decoder kernels are launched with programmatic dependent launch by default (CST_DEC_PDL=0 turns it off): a step is a
+// chain of 51 short dependent kernels, and the linear kernel prefetches its first weight tile before griddepcontrol.wait
+inline bool dec_pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("CST_DEC_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_dec(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = dec_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 }  // namespace cst
 
 using namespace cst;
@@ -295,37 +439,64 @@ extern "C" int cst_dec_embed(const int32_t* tokens, int ld_tok, const void* embe
   CST_REQUIRE(B > 0 && C > 0 && C % 4 == 0, "cst_dec_embed: bad B=%d C=%d", B, C);
   cudaStream_t st = (cudaStream_t)stream;
   if (w_dtype == CST_F32)
-    CST_CHECK_CUDA(launch_k(dec_embed_kernel<float>, dim3(B), dim3(128), 0, st, tokens, ld_tok, (const float*)embed, pos_table, scale, x, C, step));
+    CST_CHECK_CUDA(launch_dec(dec_embed_kernel<float>, dim3(B), dim3(128), 0, st, tokens, ld_tok, (const float*)embed, pos_table, scale, x, C, step));
   else if (w_dtype == CST_BF16)
-    CST_CHECK_CUDA(launch_k(dec_embed_kernel<__nv_bfloat16>, dim3(B), dim3(128), 0, st, tokens, ld_tok, (const __nv_bfloat16*)embed, pos_table, scale, x, C, step));
+    CST_CHECK_CUDA(launch_dec(dec_embed_kernel<__nv_bfloat16>, dim3(B), dim3(128), 0, st, tokens, ld_tok, (const __nv_bfloat16*)embed, pos_table, scale, x, C, step));
   else
     CST_REQUIRE(false, "cst_dec_embed: unsupported dtype %d", w_dtype);
   return CST_OK;
 }
 
+template <int RPW>
+static constexpr int dl_smem_bytes(int wsize) { return DL_A_BYTES + ((4096 / RPW) == 512 ? 2 : 1) * DL_COLS * (4096 / RPW) * wsize; }
+
+template <typename AT, typename WT, int RPW>
+static cudaError_t dl_set_attr() {
+  return cudaFuncSetAttribute(dec_linear_kernel<AT, WT, RPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, dl_smem_bytes<RPW>((int)sizeof(WT)));
+}
+template <typename AT, typename WT>
+static cudaError_t dl_set_attr_all() {
+  cudaError_t e = dl_set_attr<AT, WT, 8>();
+  if (e == cudaSuccess) e = dl_set_attr<AT, WT, 4>();
+  if (e == cudaSuccess) e = dl_set_attr<AT, WT, 2>();
+  return e;
+}
+static int g_dl_sms = 148;
 static int dec_linear_init() {
-  // all four instantiations up front: the first launch of one of them may happen inside a stream capture
-  CST_CHECK_CUDA(cudaFuncSetAttribute(dec_linear_kernel<float, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, DL_SMEM));
-  CST_CHECK_CUDA(cudaFuncSetAttribute(dec_linear_kernel<float, __nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, DL_SMEM));
-  CST_CHECK_CUDA(cudaFuncSetAttribute(dec_linear_kernel<__nv_bfloat16, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, DL_SMEM));
-  CST_CHECK_CUDA(cudaFuncSetAttribute(dec_linear_kernel<__nv_bfloat16, __nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, DL_SMEM));
+  // every instantiation up front: the first launch of one of them may happen inside a stream capture
+  CST_CHECK_CUDA((dl_set_attr_all<float, float>()));
+  CST_CHECK_CUDA((dl_set_attr_all<float, __nv_bfloat16>()));
+  CST_CHECK_CUDA((dl_set_attr_all<__nv_bfloat16, float>()));
+  CST_CHECK_CUDA((dl_set_attr_all<__nv_bfloat16, __nv_bfloat16>()));
+  int dev = 0;
+  CST_CHECK_CUDA(cudaGetDevice(&dev));
+  CST_CHECK_CUDA(cudaDeviceGetAttribute(&g_dl_sms, cudaDevAttrMultiProcessorCount, dev));
+  return CST_OK;
+}
+
+template <typename AT, typename WT, int RPW>
+static int launch_dec_linear_rpw(const DecLinearArgs& a, cudaStream_t st) {
+  const int ntiles = cdiv(a.N, DL_COLS), gy = cdiv(a.M, 8 * RPW);
+  // K = 512: persistent over column tiles (double-buffered weights), one CTA per SM; larger K: one tile per CTA
+  const int gx = (4096 / RPW == 512) ? min(ntiles, max(1, g_dl_sms / gy)) : ntiles;
+  CST_CHECK_CUDA(launch_dec(dec_linear_kernel<AT, WT, RPW>, dim3(gx, gy), dim3(DL_THREADS), (size_t)dl_smem_bytes<RPW>((int)sizeof(WT)), st, a));
   return CST_OK;
 }
 
 template <typename AT, typename WT>
-static int launch_dec_linear(const DecLinearArgs& a, cudaStream_t st) {
+static int launch_dec_linear(const DecLinearArgs& a, int K, cudaStream_t st) {
   static int init_rc = dec_linear_init();
   if (init_rc != CST_OK) return init_rc;
-  dim3 grid(cdiv(a.N, DL_COLS), cdiv(a.M, DL_ROWS));
-  CST_CHECK_CUDA(launch_k(dec_linear_kernel<AT, WT>, grid, dim3(DL_THREADS), (size_t)DL_SMEM, st, a));
-  return CST_OK;
+  if (K == 512) return launch_dec_linear_rpw<AT, WT, 8>(a, st);
+  if (K == 1024) return launch_dec_linear_rpw<AT, WT, 4>(a, st);
+  return launch_dec_linear_rpw<AT, WT, 2>(a, st);
 }
 
 extern "C" int cst_dec_linear(const cst_dec_linear_params* p, void* stream) {
   CST_REQUIRE(p && p->A && p->W && p->out[0], "cst_dec_linear: null pointer");
-  CST_REQUIRE(p->M > 0 && p->N > 0 && p->K > 0 && p->K % DL_KC == 0, "cst_dec_linear: K=%d must be a multiple of %d", p->K, DL_KC);
+  CST_REQUIRE(p->M > 0 && p->N > 0 && (p->K == 512 || p->K == 1024 || p->K == 2048), "cst_dec_linear: K=%d must be 512, 1024 or 2048", p->K);
   CST_REQUIRE(p->n_seg >= 1 && p->n_seg <= 3 && p->N % p->n_seg == 0, "cst_dec_linear: bad n_seg=%d for N=%d", p->n_seg, p->N);
-  CST_REQUIRE(!(p->ln_gamma || p->ln_beta) || (p->ln_gamma && p->ln_beta && p->K == DL_KC), "cst_dec_linear: fused LayerNorm needs K == %d", DL_KC);
+  CST_REQUIRE(!(p->ln_gamma || p->ln_beta) || (p->ln_gamma && p->ln_beta && p->K == 512), "cst_dec_linear: fused LayerNorm needs K == 512");
   CST_REQUIRE(!p->residual || p->n_seg == 1, "cst_dec_linear: residual only with one output segment");
   CST_REQUIRE(p->act == CST_ACT_NONE || p->act == CST_ACT_RELU, "cst_dec_linear: act %d unsupported", p->act);
   CST_REQUIRE(p->lda % 4 == 0, "cst_dec_linear: lda must be a multiple of 4");
@@ -336,12 +507,12 @@ extern "C" int cst_dec_linear(const cst_dec_linear_params* p, void* stream) {
   a.out0 = p->out[0]; a.out1 = p->out[1]; a.out2 = p->out[2];
   a.ldo0 = p->ldo[0]; a.ldo1 = p->ldo[1]; a.ldo2 = p->ldo[2];
   a.ss0 = p->step_stride[0]; a.ss1 = p->step_stride[1]; a.ss2 = p->step_stride[2];
-  a.step = p->step; a.M = p->M; a.N = p->N; a.K = p->K; a.seg_n = p->N / p->n_seg; a.act = p->act;
+  a.step = p->step; a.M = p->M; a.N = p->N; a.seg_n = p->N / p->n_seg; a.act = p->act;
   cudaStream_t st = (cudaStream_t)stream;
-  if (p->a_dtype == CST_F32 && p->w_dtype == CST_F32) return launch_dec_linear<float, float>(a, st);
-  if (p->a_dtype == CST_F32 && p->w_dtype == CST_BF16) return launch_dec_linear<float, __nv_bfloat16>(a, st);
-  if (p->a_dtype == CST_BF16 && p->w_dtype == CST_F32) return launch_dec_linear<__nv_bfloat16, float>(a, st);
-  if (p->a_dtype == CST_BF16 && p->w_dtype == CST_BF16) return launch_dec_linear<__nv_bfloat16, __nv_bfloat16>(a, st);
+  if (p->a_dtype == CST_F32 && p->w_dtype == CST_F32) return launch_dec_linear<float, float>(a, p->K, st);
+  if (p->a_dtype == CST_F32 && p->w_dtype == CST_BF16) return launch_dec_linear<float, __nv_bfloat16>(a, p->K, st);
+  if (p->a_dtype == CST_BF16 && p->w_dtype == CST_F32) return launch_dec_linear<__nv_bfloat16, float>(a, p->K, st);
+  if (p->a_dtype == CST_BF16 && p->w_dtype == CST_BF16) return launch_dec_linear<__nv_bfloat16, __nv_bfloat16>(a, p->K, st);
   CST_REQUIRE(false, "cst_dec_linear: unsupported dtypes a=%d w=%d", p->a_dtype, p->w_dtype);
   return CST_OK;
 }
@@ -352,10 +523,10 @@ extern "C" int cst_dec_attention(const float* q, long long ldq, const float* k, 
   CST_REQUIRE(q && k && v && out, "cst_dec_attention: null pointer");
   CST_REQUIRE(B > 0 && H > 0 && n_keys_max > 0 && (step || (n_keys > 0 && n_keys <= n_keys_max)), "cst_dec_attention: bad sizes");
   CST_REQUIRE(kv_row_stride % 4 == 0 && kv_batch_stride % 4 == 0 && ldo % 2 == 0, "cst_dec_attention: strides must keep 16-byte rows");
-  const size_t smem = 4 * (size_t)(64 + ((n_keys_max + 3) & ~3)) * sizeof(float);
+  const size_t smem = (size_t)(64 + 8 * 64 + 16 + n_keys_max) * sizeof(float);
   CST_REQUIRE(smem <= 48 * 1024, "cst_dec_attention: n_keys_max=%d too large", n_keys_max);
-  CST_CHECK_CUDA(launch_k(dec_attention_kernel, dim3(cdiv((long long)B * H, 4)), dim3(128), smem, (cudaStream_t)stream, q, ldq, k, v,
-                          kv_batch_stride, kv_row_stride, out, ldo, B, H, n_keys, n_keys_max, step));
+  CST_CHECK_CUDA(launch_dec(dec_attention_kernel, dim3(B * H), dim3(DA_THREADS), smem, (cudaStream_t)stream, q, ldq, k, v,
+                          kv_batch_stride, kv_row_stride, out, ldo, H, n_keys, n_keys_max, step));
   return CST_OK;
 }
 
@@ -365,7 +536,7 @@ extern "C" int cst_dec_select(const float* logits, int V, int B, int32_t* tokens
   CST_REQUIRE(logits && tokens && pos_scores && done && out_len && counters, "cst_dec_select: null pointer");
   CST_REQUIRE(V > 0 && B > 0 && eos >= 0 && eos < V && max_len >= 0 && ld_tok >= max_len + 2 && ld_ps >= max_len + 1,
               "cst_dec_select: bad sizes (V=%d B=%d max_len=%d ld_tok=%d ld_ps=%d)", V, B, max_len, ld_tok, ld_ps);
-  CST_CHECK_CUDA(launch_k(dec_select_kernel, dim3(B), dim3(256), 0, (cudaStream_t)stream, logits, V, tokens, ld_tok, pos_scores,
+  CST_CHECK_CUDA(launch_dec(dec_select_kernel, dim3(B), dim3(DS_THREADS), 0, (cudaStream_t)stream, logits, V, tokens, ld_tok, pos_scores,
                           ld_ps, done, out_len, counters, max_len, min_len, pad, eos));
   return CST_OK;
 }

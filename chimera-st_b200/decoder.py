@@ -275,34 +275,39 @@ class B200GreedyDecoder:
 class B200GreedyGenerator:
     """Drop-in for `SequenceGenerator(models, tgt_dict, beam_size=1, ...)` (fairseq/sequence_generator.py:17-100):
     `generate(models, sample)` runs the model's own encoder (the B200 encoder when the plugin is active) and decodes
-    greedily on the GPU.  Returns the reference structure: per sentence a list (beam) of hypothesis dicts."""
+    greedily on the GPU.  Returns the reference structure: per sentence a list (beam) of hypothesis dicts.  Options that
+    change the search (beam > 1, sampling, penalties, temperature, n-gram blocking, prefixes ...) raise."""
 
-    def __init__(self, models, tgt_dict=None, beam_size=1, max_len_a=0.0, max_len_b=200, min_len=1, dtype=None, **unsupported):
+    def __init__(self, models, tgt_dict=None, beam_size=1, max_len_a=0.0, max_len_b=200, min_len=1, normalize_scores=True,
+                 len_penalty=1.0, unk_penalty=0.0, temperature=1.0, match_source_len=False, no_repeat_ngram_size=0,
+                 symbols_to_strip_from_output=None, dtype=None):
         models = list(models) if isinstance(models, (list, tuple)) else [models]
         if len(models) != 1:
             raise NotImplementedError("model ensembles")
-        if beam_size != 1:
-            raise NotImplementedError("beam_size > 1 (greedy only)")
-        for k, v in unsupported.items():
-            if v not in (None, False, 0, 0.0, 1.0) and k not in ("normalize_scores", "len_penalty", "unk_penalty", "temperature",
-                                                                  "match_source_len", "no_repeat_ngram_size"):
-                raise NotImplementedError("SequenceGenerator option %s=%r" % (k, v))
+        if (beam_size != 1 or not normalize_scores or len_penalty != 1 or unk_penalty != 0 or temperature != 1.0
+                or match_source_len or no_repeat_ngram_size):
+            raise NotImplementedError("only plain greedy search (beam 1, default penalties) runs on the B200 decoder")
         self.model = models[0]
+        self.pad, self.eos = PAD, EOS
         if tgt_dict is not None and (tgt_dict.pad(), tgt_dict.eos()) != (PAD, EOS):
             raise NotImplementedError("non-default pad/eos indices")
-        self.max_len_a, self.max_len_b, self.min_len = max_len_a, max_len_b, min_len
+        self.symbols_to_strip_from_output = (set(symbols_to_strip_from_output) | {EOS}
+                                             if symbols_to_strip_from_output is not None else {EOS})
+        self.beam_size, self.max_len_a, self.max_len_b, self.min_len = 1, max_len_a, max_len_b, min_len
         dec_sd = {k: v for k, v in self.model.state_dict().items() if k.startswith("decoder.")}
         p = next(self.model.decoder.parameters())
-        self.decoder = B200GreedyDecoder(dec_sd, dtype=dtype or (p.dtype if p.dtype == torch.bfloat16 else torch.float32),
-                                         device=p.device)
+        half = p.dtype in (torch.bfloat16, torch.float16)
+        self.decoder = B200GreedyDecoder(dec_sd, dtype=dtype or (torch.bfloat16 if half else torch.float32), device=p.device)
+
+    def cuda(self):
+        return self
 
     @torch.no_grad()
     def generate(self, models, sample, prefix_tokens=None, constraints=None, bos_token=None, **kwargs):
-        if prefix_tokens is not None or constraints is not None:
-            raise NotImplementedError("prefix tokens / constraints")
+        if prefix_tokens is not None or constraints is not None or bos_token is not None:
+            raise NotImplementedError("prefix tokens / constraints / bos override")
         net_input = sample["net_input"]
         enc = self.model.encoder(**{k: v for k, v in net_input.items() if k != "prev_output_tokens"})
-        mem = enc.encoder_out
         src_len = net_input["src_tokens"].shape[1]
         max_len = min(int(self.max_len_a * src_len + self.max_len_b), self.model.max_decoder_positions() - 1)
-        return [[h] for h in self.decoder.generate(mem, max_len=max_len, min_len=self.min_len)]
+        return [[h] for h in self.decoder.generate(enc.encoder_out, max_len=max_len, min_len=self.min_len)]

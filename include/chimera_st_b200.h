@@ -159,7 +159,7 @@ int cst_dec_embed(const int32_t* tokens, int ld_tok, const void* embed, int w_dt
  * Replaces: the q/k/v/out projections of the incremental MultiheadAttention (fairseq/modules/multihead_attention.py:
  * 189-379), fc1/fc2 and the three pre-LayerNorms of TransformerDecoderLayer.forward (fairseq/modules/
  * transformer_layer.py:300-412), the final layer_norm + output_projection (fairseq/models/transformer.py:816-838).
- *   A [M, K] (a_dtype, row stride lda), W [N, K] (w_dtype), K a multiple of 512; ln_gamma/ln_beta (K == 512): LayerNorm
+ *   A [M, K] (a_dtype, row stride lda), W [N, K] (w_dtype), K in {512, 1024, 2048}; ln_gamma/ln_beta (K == 512): LayerNorm
  *   (eps 1e-5) of each A row is applied before the product.  The N outputs are split into n_seg equal segments;
  *   segment s is written to out[s][m*ldo[s] + (*step)*step_stride[s] + col]  (q | K-cache row | V-cache row).
  *   residual [M, N] (row stride ldr, may alias out[0]) only with n_seg == 1.  step may be NULL (= 0). */
