@@ -219,14 +219,18 @@ def main():
     ap.add_argument("--lanes", type=int, default=3, help="concurrent CUDA-stream lanes for independent batches")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-json", default="")
+    ap.add_argument("--decode", action="store_true",
+                    help="also time greedy decoding (max_len_b 200) of the first batch's memories on the GPU decoder and "
+                         "report it in a `decode` object (BASELINE configs[3]: encode + greedy decode); the headline "
+                         "value / e2e stay the encoder path")
     args = ap.parse_args()
 
     rank, world, local_rank = D.env_rank_world()
     cores = os.cpu_count() or 1
-    M = 16
+    M = 64 if args.workload == "c4" else 16          # configs[3] is Chimera-64
     batches = make_workload(args.workload, rank, world, args.utts, args.max_tokens)
     audio_per_step = sum(sum(b) for b in batches) / SR
-    cfg = {"workload": "%s: Chimera-16 encoder+memory, %s" % (args.workload, {
+    cfg = {"workload": "%s: Chimera-%d encoder+memory, %s" % (args.workload, M, {
         "c3": "%d utts/GPU U{2..30}s (global set x%d ranks, round-robin sharded), length-bucketed max_tokens=%.0e bsz%%8 (%d batches on rank 0)" % (args.utts, world, args.max_tokens, len(batches)),
         "c1": "B=4 x 5 s", "c2": "B=32 x 15 s", "c4": "B=64 x 20 s"}[args.workload]),
         "interlingua_length": M, "batches_per_step": len(batches), "audio_sec_per_step_per_gpu": round(audio_per_step, 2),
@@ -409,6 +413,31 @@ def main():
         cpu = {"value": round(med, 3), "unit": "audio-s/s", "cores": cores, "kind": "port",
                "sample": "%d utterances %s samples of the workload, fp32, torch CPU %d threads, median of 3" % (len(sample), sample, cores)}
 
+    decode = None
+    if args.decode:
+        # encode + greedy decode of the first batch (reference: SequenceGenerator beam 1, max_len_a 0, max_len_b 200);
+        # random-init hypotheses run into the forced EOS, i.e. the full 201 steps
+        from chimera_st_b200.decoder import B200GreedyDecoder
+        dec = B200GreedyDecoder(synth.make_decoder_state_dict(seed=1), dtype=dtype, device="cuda")
+        w0, l0 = dev[0]
+        for _ in range(2):
+            dec.generate(enc(w0, l0).encoder_out, max_len=200)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record()
+        mem0 = enc(w0, l0).encoder_out
+        ev[1].record()
+        hyp = dec.generate(mem0, max_len=200)
+        ev[2].record()
+        torch.cuda.synchronize()
+        t_enc, t_dec = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
+        a0 = sum(batches[0]) / SR
+        decode = {"batch": "%d utterances x %.1f s, M=%d" % (len(batches[0]), max(batches[0]) / SR, M),
+                  "encode_ms": round(t_enc, 3), "decode_ms": round(t_dec, 3), "steps": dec.last_steps,
+                  "us_per_step": round(1e3 * t_dec / max(1, dec.last_steps), 1), "gpu_launches": dec.last_launches,
+                  "tokens": sum(len(h["tokens"]) for h in hyp),
+                  "encode_decode_audio_s_per_s": round(a0 / ((t_enc + t_dec) * 1e-3), 1),
+                  "encode_only_audio_s_per_s": round(a0 / (t_enc * 1e-3), 1)}
+
     value = total_audio * args.steps / t_res
     h2d = sum(w.numel() * 4 + l.numel() * 8 for w, l in host)
     d2h = sum(o.numel() * 4 for o in out_host)
@@ -420,6 +449,8 @@ def main():
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "wall_s": round(t_e2e_wall, 3)},
             "gpu_launches": launches, "cuda_graph": not args.no_graph, "stream_lanes": lanes, "clocks": clocks,
             "roofline": roofline, "roofline_hbm_kernel": hbm_roof, "cpu_baseline": cpu}
+    if decode is not None:
+        line["decode"] = decode
     print(json.dumps(line))
     D.finalize()
 
