@@ -228,6 +228,178 @@ __global__ void __launch_bounds__(DL_THREADS, 1) dec_linear_kernel(const DecLine
   cp_async_wait<0>();
 }
 
+// ---- bf16 weights: the same linear on the tensor cores (warp-level mma.sync m16n8k16, fp32 accumulate) -----------------
+// A decoding step is latency-bound (51 dependent launches, <= 64 rows), so the point of the tensor-core form is not
+// FLOP/s but a short CTA life and a small footprint: activations are LayerNorm-ed in registers and kept as bf16
+// (64 KB instead of 128 KB), 100 KB of shared memory and <= 128 registers let two CTAs share an SM, so with PDL the next
+// kernel's CTAs are resident and have their weight tile in flight while this kernel drains.  tcgen05 needs >= 64
+// accumulator rows per instruction and a TMEM round trip per 8-column tile; at M <= 64, N-tile 8 that buys nothing.
+// CTA = RB rows (K * RB = 32768: K 512 / 1024 / 2048 -> 64 / 32 / 16 rows) x 8-column weight tiles; the 8 warps split K
+// (16 MMAs per warp per tile), partial tiles are summed through shared memory.  Row padding of 8 bf16 makes the row
+// stride 4 banks mod 32: every fragment load (lane -> row lane/4, k pair lane%4) is conflict-free.
+constexpr int DM_PAD = 8;
+
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+template <int RB> struct DmCfg {
+  static constexpr int K = 32768 / RB, LD = K + DM_PAD, NBUF = (K == 512) ? 2 : 1;
+  static constexpr int A_BYTES = RB * LD * 2, W_BYTES = NBUF * DL_COLS * LD * 2, RED_BYTES = 8 * RB * DL_COLS * 4;
+  static constexpr int SMEM = A_BYTES + W_BYTES + RED_BYTES;
+};
+
+template <typename AT, int RB>
+__global__ void __launch_bounds__(DL_THREADS, 2) dec_linear_mma_kernel(const DecLinearArgs a) {
+  using Cfg = DmCfg<RB>;
+  constexpr int K = Cfg::K, LD = Cfg::LD, NBUF = Cfg::NBUF;
+  constexpr int MT = RB / 16, KW = K / 8, KS = KW / 16, RW = RB / 8, V4 = K / 128, HR = RW / 2;
+  static_assert(HR * V4 == 16, "half of a warp's rows = 16 float4 per lane");
+  extern __shared__ __align__(16) unsigned char dm_smem[];
+  __nv_bfloat16* sA = reinterpret_cast<__nv_bfloat16*>(dm_smem);
+  __nv_bfloat16* sW = reinterpret_cast<__nv_bfloat16*>(dm_smem + Cfg::A_BYTES);
+  float* red = reinterpret_cast<float*>(dm_smem + Cfg::A_BYTES + Cfg::W_BYTES);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tq = lane & 3;
+  const int row0 = blockIdx.y * RB;
+  const AT* A = reinterpret_cast<const AT*>(a.A);
+  const __nv_bfloat16* W = reinterpret_cast<const __nv_bfloat16*>(a.W);
+  const int ntiles = (a.N + DL_COLS - 1) / DL_COLS;
+  pdl_launch_dependents();
+
+  auto load_w = [&](int tile, int buf) {
+    __nv_bfloat16* dst = sW + (size_t)buf * DL_COLS * LD;
+    for (int u = tid; u < DL_COLS * (K / 8); u += DL_THREADS) {
+      const int c = u / (K / 8), e = (u - c * (K / 8)) * 8;
+      const int n = tile * DL_COLS + c;
+      if (n < a.N) cp_async16(dst + c * LD + e, W + (size_t)n * K + e);
+      else *reinterpret_cast<uint4*>(dst + c * LD + e) = make_uint4(0u, 0u, 0u, 0u);
+    }
+  };
+
+  int t = blockIdx.x;
+  if (NBUF == 2 && t < ntiles) load_w(t, 0);                   // weights do not depend on the previous kernel
+  cp_async_commit();
+  pdl_wait();
+  // activations: this warp's RW rows, two halves of 16 float4 per lane in flight; LayerNorm in registers; bf16 to smem
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    float4 v[HR][V4];
+#pragma unroll
+    for (int r = 0; r < HR; ++r) {
+      const int m = row0 + warp * RW + half * HR + r;
+#pragma unroll
+      for (int j = 0; j < V4; ++j)
+        v[r][j] = m < a.M ? load4(A + (size_t)m * a.lda + 4 * lane + 128 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if constexpr (K == 512) if (a.ln_g != nullptr) {
+      float mean[HR], rstd[HR];
+#pragma unroll
+      for (int r = 0; r < HR; ++r) {
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < V4; ++j) s += (v[r][j].x + v[r][j].y) + (v[r][j].z + v[r][j].w);
+        mean[r] = s;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int r = 0; r < HR; ++r) mean[r] += __shfl_xor_sync(0xffffffffu, mean[r], o);
+      }
+#pragma unroll
+      for (int r = 0; r < HR; ++r) {
+        mean[r] *= (1.0f / K);
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < V4; ++j) {
+          v[r][j].x -= mean[r]; v[r][j].y -= mean[r]; v[r][j].z -= mean[r]; v[r][j].w -= mean[r];
+          q += (v[r][j].x * v[r][j].x + v[r][j].y * v[r][j].y) + (v[r][j].z * v[r][j].z + v[r][j].w * v[r][j].w);
+        }
+        rstd[r] = q;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int r = 0; r < HR; ++r) rstd[r] += __shfl_xor_sync(0xffffffffu, rstd[r], o);
+      }
+#pragma unroll
+      for (int j = 0; j < V4; ++j) {
+        const float4 gm = load4(a.ln_g + 4 * lane + 128 * j), bt = load4(a.ln_b + 4 * lane + 128 * j);
+#pragma unroll
+        for (int r = 0; r < HR; ++r) {
+          const float rs = 1.0f / sqrtf(rstd[r] * (1.0f / K) + 1e-5f);
+          v[r][j].x = v[r][j].x * rs * gm.x + bt.x; v[r][j].y = v[r][j].y * rs * gm.y + bt.y;
+          v[r][j].z = v[r][j].z * rs * gm.z + bt.z; v[r][j].w = v[r][j].w * rs * gm.w + bt.w;
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < HR; ++r) {
+      __nv_bfloat16* dst = sA + (size_t)(warp * RW + half * HR + r) * LD + 4 * lane;
+#pragma unroll
+      for (int j = 0; j < V4; ++j)
+        *reinterpret_cast<uint2*>(dst + 128 * j) = make_uint2(pack_bf16x2(v[r][j].x, v[r][j].y), pack_bf16x2(v[r][j].z, v[r][j].w));
+    }
+  }
+
+  const long long step = a.step ? (long long)*a.step : 0;
+  for (int it = 0; t < ntiles; t += gridDim.x, ++it) {
+    const int buf = NBUF == 2 ? (it & 1) : 0;
+    if (NBUF == 1) load_w(t, 0);
+    else if (t + (int)gridDim.x < ntiles) load_w(t + gridDim.x, buf ^ 1);
+    cp_async_commit();
+    cp_async_wait<NBUF - 1>();
+    __syncthreads();                                           // weight tile + (first iteration) all activation rows visible
+    const __nv_bfloat16* wt = sW + (size_t)buf * DL_COLS * LD;
+    float c[MT][4];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) { c[mt][0] = 0.f; c[mt][1] = 0.f; c[mt][2] = 0.f; c[mt][3] = 0.f; }
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      const int k0 = warp * KW + ks * 16 + 2 * tq;
+      uint32_t bfr[2];
+      bfr[0] = *reinterpret_cast<const uint32_t*>(wt + g * LD + k0);
+      bfr[1] = *reinterpret_cast<const uint32_t*>(wt + g * LD + k0 + 8);
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        const __nv_bfloat16* ap = sA + (size_t)(mt * 16 + g) * LD + k0;
+        uint32_t afr[4];
+        afr[0] = *reinterpret_cast<const uint32_t*>(ap);
+        afr[1] = *reinterpret_cast<const uint32_t*>(ap + 8 * LD);
+        afr[2] = *reinterpret_cast<const uint32_t*>(ap + 8);
+        afr[3] = *reinterpret_cast<const uint32_t*>(ap + 8 * LD + 8);
+        mma_bf16_16816(c[mt], afr, bfr);
+      }
+    }
+    float* myred = red + warp * RB * DL_COLS;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      *reinterpret_cast<float2*>(myred + (mt * 16 + g) * DL_COLS + 2 * tq) = make_float2(c[mt][0], c[mt][1]);
+      *reinterpret_cast<float2*>(myred + (mt * 16 + g + 8) * DL_COLS + 2 * tq) = make_float2(c[mt][2], c[mt][3]);
+    }
+    __syncthreads();
+    for (int idx = tid; idx < RB * DL_COLS; idx += DL_THREADS) {
+      const int m = row0 + idx / DL_COLS, n = t * DL_COLS + (idx & (DL_COLS - 1));
+      if (m < a.M && n < a.N) {
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) v += red[w * RB * DL_COLS + idx];
+        if (a.bias) v += a.bias[n];
+        if (a.act == CST_ACT_RELU) v = fmaxf(v, 0.f);
+        const int seg = n / a.seg_n, col = n - seg * a.seg_n;
+        if (a.residual) v += a.residual[(size_t)m * a.ldr + n];
+        float* o = seg == 0 ? a.out0 : (seg == 1 ? a.out1 : a.out2);
+        const long long ldo = seg == 0 ? a.ldo0 : (seg == 1 ? a.ldo1 : a.ldo2);
+        const long long ss = seg == 0 ? a.ss0 : (seg == 1 ? a.ss1 : a.ss2);
+        o[(size_t)m * ldo + step * ss + col] = v;
+      }
+    }
+    __syncthreads();                                           // `red` and the weight buffer just read are reused next
+  }
+  cp_async_wait<0>();
+}
+
 // x[b,:] = scale * E[tokens[b, step], :] + pos[step, :]
 template <typename WT>
 __global__ void dec_embed_kernel(const int* __restrict__ tokens, int ld_tok, const WT* __restrict__ E,
@@ -468,10 +640,34 @@ static int dec_linear_init() {
   CST_CHECK_CUDA((dl_set_attr_all<float, __nv_bfloat16>()));
   CST_CHECK_CUDA((dl_set_attr_all<__nv_bfloat16, float>()));
   CST_CHECK_CUDA((dl_set_attr_all<__nv_bfloat16, __nv_bfloat16>()));
+  CST_CHECK_CUDA(cudaFuncSetAttribute(dec_linear_mma_kernel<float, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, DmCfg<64>::SMEM));
+  CST_CHECK_CUDA(cudaFuncSetAttribute(dec_linear_mma_kernel<float, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, DmCfg<32>::SMEM));
+  CST_CHECK_CUDA(cudaFuncSetAttribute(dec_linear_mma_kernel<float, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, DmCfg<16>::SMEM));
+  CST_CHECK_CUDA(cudaFuncSetAttribute(dec_linear_mma_kernel<__nv_bfloat16, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, DmCfg<64>::SMEM));
+  CST_CHECK_CUDA(cudaFuncSetAttribute(dec_linear_mma_kernel<__nv_bfloat16, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, DmCfg<32>::SMEM));
+  CST_CHECK_CUDA(cudaFuncSetAttribute(dec_linear_mma_kernel<__nv_bfloat16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, DmCfg<16>::SMEM));
   int dev = 0;
   CST_CHECK_CUDA(cudaGetDevice(&dev));
   CST_CHECK_CUDA(cudaDeviceGetAttribute(&g_dl_sms, cudaDevAttrMultiProcessorCount, dev));
   return CST_OK;
+}
+
+// bf16 weights: tensor-core kernel unless CST_DEC_MMA=0 (then the exact-fp32-activation FFMA kernel; read per call so
+// that tests can exercise both)
+static bool dec_mma_enabled() { const char* e = getenv("CST_DEC_MMA"); return !(e && e[0] == '0'); }
+
+template <typename AT, int RB>
+static int launch_dec_linear_mma_rb(const DecLinearArgs& a, cudaStream_t st) {
+  const int ntiles = cdiv(a.N, DL_COLS), gy = cdiv(a.M, RB);
+  const int gx = (DmCfg<RB>::K == 512) ? min(ntiles, max(1, 2 * g_dl_sms / gy)) : ntiles;     // two CTAs per SM
+  CST_CHECK_CUDA(launch_dec(dec_linear_mma_kernel<AT, RB>, dim3(gx, gy), dim3(DL_THREADS), (size_t)DmCfg<RB>::SMEM, st, a));
+  return CST_OK;
+}
+template <typename AT>
+static int launch_dec_linear_mma(const DecLinearArgs& a, int K, cudaStream_t st) {
+  if (K == 512) return launch_dec_linear_mma_rb<AT, 64>(a, st);
+  if (K == 1024) return launch_dec_linear_mma_rb<AT, 32>(a, st);
+  return launch_dec_linear_mma_rb<AT, 16>(a, st);
 }
 
 template <typename AT, typename WT, int RPW>
@@ -487,6 +683,9 @@ template <typename AT, typename WT>
 static int launch_dec_linear(const DecLinearArgs& a, int K, cudaStream_t st) {
   static int init_rc = dec_linear_init();
   if (init_rc != CST_OK) return init_rc;
+  if constexpr (sizeof(WT) == 2) {
+    if (dec_mma_enabled()) return launch_dec_linear_mma<AT>(a, K, st);
+  }
   if (K == 512) return launch_dec_linear_rpw<AT, WT, 8>(a, st);
   if (K == 1024) return launch_dec_linear_rpw<AT, WT, 4>(a, st);
   return launch_dec_linear_rpw<AT, WT, 2>(a, st);

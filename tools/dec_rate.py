@@ -50,6 +50,7 @@ def main():
     ap.add_argument("--M", type=int, default=64)
     ap.add_argument("--max-len", type=int, default=200)
     ap.add_argument("--encode", action="store_true")
+    ap.add_argument("--lanes", default="1,2,4,8")
     ap.add_argument("--json", default="")
     a = ap.parse_args()
     out = {"B": a.B, "M": a.M, "max_len": a.max_len}
@@ -59,18 +60,21 @@ def main():
         name = str(dt).replace("torch.", "")
         dec = B200GreedyDecoder(dsd, dtype=dt, device="cuda")
         mem = mem32.to(dt)
-        dec.generate(mem, max_len=a.max_len)                       # warm-up + graph capture
-        ts = []
-        for _ in range(3):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            hyp = dec.generate(mem, max_len=a.max_len)
-            e1.record()
-            torch.cuda.synchronize()
-            ts.append(e0.elapsed_time(e1))
-        ms = sorted(ts)[1]
+        by_lanes = {}
+        for nl in [int(x) for x in a.lanes.split(",")][::-1]:
+            dec.generate(mem, max_len=a.max_len, n_lanes=nl)       # warm-up + graph capture
+            ts = []
+            for _ in range(3):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                hyp = dec.generate(mem, max_len=a.max_len, n_lanes=nl)
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            by_lanes[nl] = round(sorted(ts)[1], 3)
+        ms = by_lanes[1] if 1 in by_lanes else sorted(ts)[1]
         steps = dec.last_steps
-        plan = next(iter(dec._plans.values()))
+        plan = dec._plan(a.B, a.M, a.max_len, mem.dtype)
         # instrumented eager step at a late step index (long self-attention cache)
         plan.begin(mem)
         plan.counters[0] = a.max_len - 1
@@ -85,7 +89,7 @@ def main():
             d = fam.setdefault(tag, [0, 0.0])
             d[0] += 1
             d[1] += s.elapsed_time(e) * 1e3
-        out[name] = {"decode_ms": round(ms, 3), "steps": steps, "us_per_step": round(1e3 * ms / steps, 1),
+        out[name] = {"decode_ms_by_lanes": by_lanes, "decode_ms": round(ms, 3), "steps": steps, "us_per_step": round(1e3 * ms / steps, 1),
                      "launches": dec.last_launches, "tokens_per_s": round(sum(len(h["tokens"]) for h in hyp) / (ms * 1e-3)),
                      "eager_step_us_by_kernel": {k: {"launches": v[0], "us": round(v[1], 1)} for k, v in fam.items()},
                      "eager_step_us": round(sum(v[1] for v in fam.values()), 1)}
