@@ -341,7 +341,7 @@ class B200GreedyGenerator:
 
     def __init__(self, models, tgt_dict=None, beam_size=1, max_len_a=0.0, max_len_b=200, min_len=1, normalize_scores=True,
                  len_penalty=1.0, unk_penalty=0.0, temperature=1.0, match_source_len=False, no_repeat_ngram_size=0,
-                 symbols_to_strip_from_output=None, dtype=None):
+                 symbols_to_strip_from_output=None, dtype=None, lib=None):
         models = list(models) if isinstance(models, (list, tuple)) else [models]
         if len(models) != 1:
             raise NotImplementedError("model ensembles")
@@ -358,7 +358,8 @@ class B200GreedyGenerator:
         dec_sd = {k: v for k, v in self.model.state_dict().items() if k.startswith("decoder.")}
         p = next(self.model.decoder.parameters())
         half = p.dtype in (torch.bfloat16, torch.float16)
-        self.decoder = B200GreedyDecoder(dec_sd, dtype=dtype or (torch.bfloat16 if half else torch.float32), device=p.device)
+        self.decoder = B200GreedyDecoder(dec_sd, dtype=dtype or (torch.bfloat16 if half else torch.float32), device=p.device,
+                                         lib=lib)
 
     def cuda(self):
         return self

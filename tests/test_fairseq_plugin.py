@@ -55,3 +55,58 @@ def test_user_dir_plugin_rebinds_arch_and_loads_reference_state_dict():
     env = dict(os.environ, PYTHONDONTWRITEBYTECODE="1")
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env)
     assert "PLUGIN_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+GEN_SCRIPT = r'''
+import sys, argparse, tempfile, os, torch
+sys.path.insert(0, %(root)r); sys.path.insert(0, os.path.join(%(root)r, "tests"))
+from oracle import make_overlay
+make_overlay.build(); make_overlay.activate()
+import fairseq.models
+from fairseq.data import Dictionary
+from fairseq.models.wav2vec import wav2vec2 as W
+from fairseq.models.chimera.w2v2_transformer_interlingua import S2TTransformerInterlinguaModelW2V2
+from fairseq.sequence_generator import SequenceGenerator
+from oracle.ref_model import W2V_CONV_SPEC
+import chimera_st_b200
+from chimera_st_b200 import synth
+from chimera_st_b200.decoder import B200GreedyGenerator
+from emu import EmuLib
+torch.set_num_threads(8)
+d = Dictionary.load("/root/reference/chimera/resources/wmt14-en-de-spm/spm_unigram10000_wave_joint.txt")
+class Task: source_dictionary = None; target_dictionary = d
+w2v_args = argparse.Namespace(conv_feature_layers=W2V_CONV_SPEC, quantize_targets=True, final_dim=256, encoder_layerdrop=0.05,
+                              dropout_input=0.1, dropout_features=0.1, feature_grad_mult=0.1)
+W.base_architecture(w2v_args)
+tmp = tempfile.NamedTemporaryFile(suffix=".pt", delete=False); tmp.close()
+torch.save({"args": w2v_args, "model": W.Wav2Vec2Model.build_model(w2v_args, task=None).state_dict()}, tmp.name)
+args = argparse.Namespace(w2v2_model_path=tmp.name, encoder_layers=6, encoder_embed_dim=512, interlingua_length=16,
+    interlingua_layers=3, interlingua_debug_options=[], dropout=0.1, share_decoder_input_output_embed=True,
+    max_source_positions=6000, max_target_positions=1024)
+model = S2TTransformerInterlinguaModelW2V2.build_model(args, Task()); os.unlink(tmp.name)
+sd = {"encoder." + k: v for k, v in synth.make_state_dict(seed=0, interlingua_length=16).items()}
+sd.update(synth.make_decoder_state_dict(seed=1))
+sd["encoder.text_embed_tokens.weight"] = torch.zeros(synth.VOCAB, 512)
+model.load_state_dict(sd, strict=True); model.eval()
+wave, lens = synth.make_waveforms([9000, 6000], seed=5)
+sample = {"net_input": {"src_tokens": wave, "src_lengths": lens}}
+kw = dict(beam_size=1, max_len_a=0, max_len_b=7)
+ref = SequenceGenerator([model], d, **kw).generate([model], sample)
+new = B200GreedyGenerator([model], d, lib=EmuLib(), **kw).generate([model], sample)     # reference encoder (CPU) + B200 greedy search on the ABI emulator
+assert len(ref) == len(new) == 2
+for r, n in zip(ref, new):
+    assert len(n) == 1 and set(n[0]) >= {"tokens", "score", "attention", "alignment", "positional_scores"}
+    assert r[0]["tokens"].tolist() == n[0]["tokens"].tolist(), (r[0]["tokens"], n[0]["tokens"])
+    assert abs(float(r[0]["score"]) - n[0]["score"]) < 1e-4
+    assert (r[0]["positional_scores"] - n[0]["positional_scores"]).abs().max() < 1e-4
+print("GEN_OK", [h[0]["tokens"].tolist() for h in new])
+'''
+
+
+def test_greedy_generator_matches_reference_sequence_generator_structure_and_scores():
+    """B200GreedyGenerator (decode logic on the host emulator of the C ABI) against the UNMODIFIED reference
+    SequenceGenerator(beam_size=1) on the same reference model and sample: tokens, normalised score, positional scores."""
+    code = GEN_SCRIPT % {"root": ROOT}
+    env = dict(os.environ, PYTHONDONTWRITEBYTECODE="1")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900, env=env)
+    assert "GEN_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
