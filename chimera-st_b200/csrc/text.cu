@@ -1,0 +1,44 @@
+// Text (MT) input of the shared encoder: token embedding + sinusoidal positions, written in the shared stage's layout.
+// Replaces: the text branch of S2T_W2V2_TransformerInterlinguaEncoder.forward
+// (fairseq/models/chimera/w2v2_transformer_interlingua.py:212-217,230-236): x = sqrt(d) * text_embed_tokens(tokens) +
+// embed_positions(padding_mask), positions 2, 3, ... on the valid tokens (t < len_b) and the zeroed padding row elsewhere
+// (SinusoidalPositionalEmbedding, fairseq/modules/sinusoidal_positional_embedding.py:71-93; make_positions, utils.py:235-245).
+#include "common.cuh"
+
+namespace cst {
+
+__global__ void __launch_bounds__(128) text_embed_kernel(const long long* __restrict__ tokens, const long long* __restrict__ lens,
+                                                         const float* __restrict__ E, const float* __restrict__ pos, float scale,
+                                                         float* __restrict__ x, int* __restrict__ valid, int T, int rows_per_seg,
+                                                         int C, int V) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.x / rows_per_seg, t = blockIdx.x - b * rows_per_seg;
+  const long long len = lens[b];
+  if (t == 0 && threadIdx.x == 0 && valid) valid[b] = (int)min((long long)T, max(0ll, len));
+  float* dst = x + (size_t)blockIdx.x * C;
+  if (t >= T) {                                                // filler rows of the segment
+    for (int c = 4 * threadIdx.x; c < C; c += 4 * blockDim.x) store4(dst + c, make_float4(0.f, 0.f, 0.f, 0.f));
+    return;
+  }
+  long long tok = tokens[(size_t)b * T + t];
+  tok = min((long long)V - 1, max(0ll, tok));                  // the reference would raise on an out-of-range id
+  const int p = t < len ? t + 2 : 1;                           // row 1 (padding_idx) of the table is zero
+  for (int c = 4 * threadIdx.x; c < C; c += 4 * blockDim.x) {
+    const float4 e = load4(E + (size_t)tok * C + c), q = load4(pos + (size_t)p * C + c);
+    store4(dst + c, make_float4(fmaf(scale, e.x, q.x), fmaf(scale, e.y, q.y), fmaf(scale, e.z, q.z), fmaf(scale, e.w, q.w)));
+  }
+}
+
+}  // namespace cst
+
+extern "C" int cst_text_embed(const int64_t* tokens, const int64_t* lengths, const float* embed, const float* pos_table,
+                              float scale, float* x, int32_t* valid, int B, int T, int rows_per_seg, int C, int V,
+                              void* stream) {
+  CST_REQUIRE(tokens && lengths && embed && pos_table && x, "cst_text_embed: null pointer");
+  CST_REQUIRE(B > 0 && T > 0 && rows_per_seg >= T && C > 0 && C % 4 == 0 && V > 0, "cst_text_embed: bad sizes");
+  CST_CHECK_CUDA(cst::launch_k(cst::text_embed_kernel, dim3(B * rows_per_seg), dim3(128), 0, (cudaStream_t)stream,
+                               (const long long*)tokens, (const long long*)lengths, embed, pos_table, scale, x, valid, T,
+                               rows_per_seg, C, V));
+  return CST_OK;
+}

@@ -12,7 +12,8 @@ pre-training heads and `embed_positions._float_tensor`), so a reference checkpoi
 `load_state_dict(strict=True)`.  The arithmetic is done only by the CUDA kernels behind the C ABI
 (`include/chimera_st_b200.h`); without the built library or without a CUDA device `forward` raises.
 
-Not reproduced (out of scope): the text (MT) branch, training-time dropout / LayerDrop,
+Integer `src_tokens` take the text (MT) branch (embedding + sinusoidal positions -> the same shared layers and memory stage).
+Not reproduced (out of scope): training-time dropout / LayerDrop,
 `modal_embedding` debug option, `non_shared_encoder_layers`.  They raise NotImplementedError.
 """
 import os
@@ -23,7 +24,7 @@ import torch
 import torch.nn as nn
 
 from . import weights as _weights
-from .plan import EncoderPlan, Arena
+from .plan import EncoderPlan, TextPlan, Arena
 from .synth import encoder_param_spec, ENC_DIM
 
 
@@ -111,7 +112,7 @@ class B200InterlinguaEncoder(nn.Module):
             raise RuntimeError("B200InterlinguaEncoder runs only on a CUDA device (no CPU fallback); call .cuda()")
         return dev
 
-    def _plan(self, B, L, lane=None):
+    def _plan(self, B, L, lane=None, text=False):
         dev = self._device()
         if self._prepared is None:
             self._prepared = _weights.prepare(self.state_dict(), dev, self.compute_dtype, self.conv_dtype)
@@ -121,14 +122,18 @@ class B200InterlinguaEncoder(nn.Module):
             plans, arena = self._plans, self._arena
         else:
             plans, arena = lane["plans"], lane["arena"]
-        key = (B, L)
+        key = (B, L, text)
         plan = plans.get(key)
         if plan is None:
             while len(plans) >= self.MAX_PLANS:
                 plans.popitem(last=False)
             gen = arena.generation
-            plan = EncoderPlan(self._prepared, B, L, self.interlingua_length, self.compute_dtype, dev, self.use_graph,
-                               arena=arena, conv_dtype=self.conv_dtype)
+            if text:
+                plan = TextPlan(self._prepared, B, L, self.interlingua_length, self.compute_dtype, dev, self.use_graph,
+                                arena=arena)
+            else:
+                plan = EncoderPlan(self._prepared, B, L, self.interlingua_length, self.compute_dtype, dev, self.use_graph,
+                                   arena=arena, conv_dtype=self.conv_dtype)
             if arena.generation != gen:                # arena grew: older plans (and their graphs) point at freed memory
                 plans.clear()
             plans[key] = plan
@@ -176,9 +181,9 @@ class B200InterlinguaEncoder(nn.Module):
             cur.wait_stream(ln["stream"])
         return results
 
-    def _check_inputs(self, src_tokens, src_lengths):
-        if not src_tokens.dtype.is_floating_point:
-            raise NotImplementedError("text (MT) branch is out of scope for the B200 path (SURVEY.md §8(f) row 2)")
+    def _check_inputs(self, src_tokens, src_lengths, allow_text=False):
+        if not src_tokens.dtype.is_floating_point and not allow_text:
+            raise NotImplementedError("integer (text) tokens are only accepted by forward()")
         if self.training:
             raise NotImplementedError("training-mode forward (dropout / LayerDrop) is not implemented; call .eval()")
         if src_tokens.dim() != 2 or src_lengths.shape != (src_tokens.shape[0],):
@@ -195,8 +200,16 @@ class B200InterlinguaEncoder(nn.Module):
 
     @torch.no_grad()
     def forward(self, src_tokens, src_lengths, **extra_args):      # extra: the collater's stray `mask=` kwarg
-        self._check_inputs(src_tokens, src_lengths)
+        self._check_inputs(src_tokens, src_lengths, allow_text=True)
         B, L = src_tokens.shape
+        if not src_tokens.dtype.is_floating_point:                 # text (MT) branch, interlingua:212-217
+            if self.no_interlingua:
+                raise NotImplementedError("no_interlingua with text input")
+            plan = self._plan(B, L, text=True)
+            plan.load_inputs(src_tokens.long(), src_lengths)
+            self.last_launches = plan.run()
+            out = plan.memories().to(self.encoder_out_dtype or torch.float32).clone(memory_format=torch.contiguous_format)
+            return EncoderOut(out, torch.zeros(B, out.shape[0], dtype=torch.bool, device=out.device), None, None, None, None)
         plan = self._plan(B, L)
         plan.load_inputs(src_tokens.float(), src_lengths)
         self.last_launches = plan.run()

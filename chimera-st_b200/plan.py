@@ -353,3 +353,89 @@ class EncoderPlan:
         if name == "frame_mask":
             return self.frame_mask.bool()
         raise KeyError(name)
+
+
+class TextGeometry:
+    """Shared-stage geometry of a text batch: T tokens per utterance, no subsampling (T2 = T2a = T)."""
+
+    def __init__(self, B, T, M):
+        if T < 1:
+            raise ValueError("empty token batch")
+        self.B, self.L, self.M = B, T, M
+        self.T2 = self.T2a = T
+
+
+def sinusoidal_table(n, dim=ENC_DIM, padding_idx=1):
+    """SinusoidalPositionalEmbedding.get_embedding (fairseq/modules/sinusoidal_positional_embedding.py:38-59), computed
+    with the reference's own float32 torch expressions."""
+    half = dim // 2
+    e = math.log(10000) / (half - 1)
+    e = torch.exp(torch.arange(half, dtype=torch.float) * -e)
+    e = torch.arange(n, dtype=torch.float).unsqueeze(1) * e.unsqueeze(0)
+    t = torch.cat([torch.sin(e), torch.cos(e)], dim=1)
+    t[padding_idx] = 0
+    return t.contiguous()
+
+
+class TextPlan(EncoderPlan):
+    """Text (MT) branch of the encoder (w2v2_transformer_interlingua.py:212-217,230-236): `cst_text_embed` feeds the
+    SAME shared-layer and memory stages as the audio branch (`_stage_shared_layers`, `_stage_memory`)."""
+
+    def __init__(self, params, B, T, M, act_dtype=torch.float32, device=None, use_graph=False, lib=None, arena=None):
+        if "text_embed" not in params:
+            raise RuntimeError("the checkpoint has no text_embed_tokens.weight: the text branch is unavailable")
+        self.lib = lib if lib is not None else L.load()
+        self.P = params
+        self.g = g = TextGeometry(B, T, M)
+        self.dev = device or torch.device("cuda", torch.cuda.current_device())
+        self.act = act_dtype
+        self.act_code = L.DT[act_dtype]
+        self.use_graph = use_graph
+        self.graph = None
+        self.launches = 0
+        self.arena = arena if arena is not None else Arena(self.dev)
+        f32, i32, i64 = torch.float32, torch.int32, torch.int64
+        R2, RM = B * g.T2a, B * M
+        spec = [
+            ("tokens", B, T, i64), ("src_len", 1, B, i64), ("sub_valid", 1, B, i32), ("pos_table", T + 2, ENC_DIM, f32),
+            ("x2", R2, ENC_DIM, f32), ("x2a", R2, ENC_DIM, act_dtype), ("qkv2", R2, 3 * ENC_DIM, act_dtype),
+            ("ctx2", R2, ENC_DIM, act_dtype), ("ffn2", R2, ENC_FFN, act_dtype), ("h_enc", R2, ENC_DIM, f32),
+            ("kv_in", R2, ENC_DIM, act_dtype), ("kv", R2, 2 * ENC_DIM * MEM_LAYERS, act_dtype), ("mem", RM, ENC_DIM, f32),
+            ("mem_a", RM, ENC_DIM, act_dtype), ("mq", RM, ENC_DIM, act_dtype), ("mctx", RM, ENC_DIM, act_dtype),
+            ("mffn", RM, ENC_FFN, act_dtype),
+        ]
+        off, table = 0, []
+        for name, rows, cols, dt in spec:
+            nbytes = rows * cols * torch.empty(0, dtype=dt).element_size()
+            table.append((name, off, nbytes, rows, cols, dt))
+            off += (nbytes + 1023) // 1024 * 1024
+        self.nbytes = off
+        self.arena_generation = self.arena.ensure(off)
+        for name, o, nbytes, rows, cols, dt in table:
+            t = self.arena.buf[o:o + nbytes].view(dt)
+            setattr(self, name, t.view(rows, cols) if (rows > 1 or name == "tokens") else t.view(cols))
+        self.arena.buf[:off].zero_()
+        self._pos_host = sinusoidal_table(T + 2)
+
+    def load_inputs(self, tokens, src_lengths):
+        assert tuple(tokens.shape) == (self.g.B, self.g.L), (tuple(tokens.shape), (self.g.B, self.g.L))
+        self.tokens.copy_(tokens, non_blocking=True)
+        self.src_len.copy_(src_lengths, non_blocking=True)
+        self.pos_table.copy_(self._pos_host, non_blocking=True)      # the arena is shared with other shapes
+
+    def _issue(self, upto="memory"):
+        g, P = self.g, self.P
+        self.st = L.stream_ptr() if self.dev.type == "cuda" else 0
+        self.launches = 0
+        E = P["text_embed"]
+        L.check(self.lib.cst_text_embed(self.tokens.data_ptr(), self.src_len.data_ptr(), E.data_ptr(), self.pos_table.data_ptr(),
+                                        math.sqrt(ENC_DIM), self.x2.data_ptr(), self.sub_valid.data_ptr(), g.B, g.L, g.T2a,
+                                        ENC_DIM, E.shape[0], self.st))
+        self.launches += 1
+        self._stage_shared_layers()
+        self._stage_memory()
+
+    def view(self, name):
+        if name == "h_enc":
+            return self.h_enc.view(self.g.B, self.g.T2a, ENC_DIM)[:, :self.g.T2]
+        raise KeyError(name)

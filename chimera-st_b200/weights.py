@@ -106,6 +106,8 @@ def prepare(state_dict, device, act_dtype, conv_dtype=None):
     P["enc_layers"] = [layer(f"transformer_layers.{i}.") for i in range(ENC_LAYERS)]
     P["ln_out_g"], P["ln_out_b"] = f32(sd["layer_norm.weight"]), f32(sd["layer_norm.bias"])
     P["mem_embed"] = f32(sd["interlingua_embedding.weight"])
+    if "text_embed_tokens.weight" in sd:                       # text (MT) branch input, interlingua:216
+        P["text_embed"] = f32(sd["text_embed_tokens.weight"])
     P["mem_layers"] = [layer(f"interlingua_layers.{i}.", fused_qkv=False) for i in range(MEM_LAYERS)]
     # K/V side of the memory stage: every layer i normalises the SAME h_enc with its own affine LN1 and projects it
     # (w2v2_transformer_interlingua.py:262-274 -> transformer_layer.py:129-139).  LN(x; g, b) W^T + c =

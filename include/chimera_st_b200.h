@@ -142,6 +142,15 @@ int cst_attention(const void* q, const void* k, const void* v, void* out, int dt
                   int B, int H, int n_q, int q_rows_per_seg, int n_kv, int kv_rows_per_seg,
                   const int32_t* kv_len, void* stream);
 
+/* ---- text (MT) input of the shared encoder ------------------------------------------------------
+ * Replaces: the text branch of S2T_W2V2_TransformerInterlinguaEncoder.forward (fairseq/models/chimera/
+ * w2v2_transformer_interlingua.py:212-217,230-236): x = scale * text_embed_tokens(tokens) + embed_positions(padding mask).
+ * tokens int64 [B,T], lengths int64 [B] (device); embed f32 [V,C]; pos_table f32 [T+2, C] = SinusoidalPositionalEmbedding
+ * table with row 1 (padding_idx) zero: token t of utterance b gets row t+2 if t < lengths[b], else row 1.
+ * x f32 [B*rows_per_seg, C] (rows t >= T of a segment are zero-filled); valid int32 [B] = lengths (may be NULL). */
+int cst_text_embed(const int64_t* tokens, const int64_t* lengths, const float* embed, const float* pos_table,
+                   float scale, float* x, int32_t* valid, int B, int T, int rows_per_seg, int C, int V, void* stream);
+
 /* ==== greedy incremental decoding from the memories (BASELINE configs[3] "encode + greedy decode")
  * All four entry points read the current step from a DEVICE counter, so one captured CUDA graph of a decoding step is
  * replayed for every step without a host round trip.  Activations of the decoder are fp32; weights fp32 or bf16

@@ -240,5 +240,39 @@ def encoder_forward(sd, wave, src_lengths, stages=None, literal_memory=False):
     return out, torch.zeros(wave.shape[0], out.shape[0], dtype=torch.bool)        # :301-312
 
 
+def sinusoidal_table(n, dim=512, padding_idx=1):
+    """SinusoidalPositionalEmbedding.get_embedding, fairseq/modules/sinusoidal_positional_embedding.py:38-59."""
+    half = dim // 2
+    e = math.log(10000) / (half - 1)
+    e = torch.exp(torch.arange(half, dtype=torch.float) * -e)
+    e = torch.arange(n, dtype=torch.float).unsqueeze(1) * e.unsqueeze(0)
+    t = torch.cat([torch.sin(e), torch.cos(e)], dim=1)
+    t[padding_idx] = 0
+    return t
+
+
+def encoder_forward_text(sd, src_tokens, src_lengths, stages=None):
+    """S2T_W2V2_TransformerInterlinguaEncoder.forward, TEXT branch (w2v2_transformer_interlingua.py:212-217,230-236):
+    x = sqrt(512) * text_embed_tokens(tokens) + embed_positions(padding_mask).  The reference hands the *padding mask*
+    (bool) to SinusoidalPositionalEmbedding, whose make_positions (fairseq/utils.py:235-245) then computes
+    cumsum(mask != padding_idx) * (mask != padding_idx) + padding_idx with padding_idx = 1, i.e. positions 2, 3, ... on
+    the valid tokens and the zeroed padding row elsewhere.  src_tokens [B,T] int64 (max(src_lengths) == T)."""
+    B, T = src_tokens.shape
+    assert int(src_lengths.max()) == T
+    pad = lengths_to_padding_mask(src_lengths)
+    valid = ~pad
+    positions = torch.cumsum(valid.long(), dim=1) * valid.long() + 1
+    x = math.sqrt(512) * sd["text_embed_tokens.weight"][src_tokens] + sinusoidal_table(T + 2)[positions]
+    if stages is not None:
+        stages["text_in"] = x
+    for i in range(6):
+        x = encoder_layer(sd, f"transformer_layers.{i}.", x, pad)
+    h_enc = _ln(x, sd, "layer_norm")
+    if stages is not None:
+        stages["h_enc"] = h_enc
+    out = memory_stage(sd, h_enc).transpose(0, 1).contiguous()
+    return out, torch.zeros(B, out.shape[0], dtype=torch.bool)
+
+
 def cast_state_dict(sd, dtype):
     return {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in sd.items()}

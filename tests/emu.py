@@ -267,3 +267,23 @@ EmuLib.cst_dec_embed = _dec_embed
 EmuLib.cst_dec_linear = _dec_linear
 EmuLib.cst_dec_attention = _dec_attention
 EmuLib.cst_dec_select = _dec_select
+
+
+def _text_embed(self, tokens, lengths, embed, pos_table, scale, x, valid, B, T, rows_per_seg, Cd, V, stream):
+    tok = _mem(tokens, B * T, np.int64).reshape(B, T)
+    lens = _mem(lengths, B, np.int64)
+    E = _mem(embed, V * Cd).reshape(V, Cd)
+    pos = _mem(pos_table, (T + 2) * Cd).reshape(T + 2, Cd)
+    out = _mem(x, B * rows_per_seg * Cd).reshape(B, rows_per_seg, Cd)
+    out[:] = 0
+    for b in range(B):
+        for t in range(T):
+            p = t + 2 if t < lens[b] else 1
+            out[b, t] = np.float32(scale) * E[min(V - 1, max(0, int(tok[b, t])))] + pos[p]
+    if valid:
+        _mem(valid, B, np.int32)[:] = np.minimum(T, np.maximum(0, lens))
+    self.calls.append("text_embed")
+    return 0
+
+
+EmuLib.cst_text_embed = _text_embed

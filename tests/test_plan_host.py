@@ -81,8 +81,10 @@ def test_state_dict_layout_and_strict_load():
     assert enc2.max_positions() is None
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         enc2(torch.zeros(1, 16000), torch.tensor([16000]))           # product path refuses to run on CPU
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match="no CPU fallback"):         # text branch: same rule
         enc2(torch.zeros(1, 10, dtype=torch.long), torch.tensor([10]))
+    with pytest.raises(NotImplementedError):
+        enc2._get_w2v_feature(torch.zeros(1, 10, dtype=torch.long), torch.tensor([10]))
 
 
 def test_posconv_weight_folding_accepts_both_forms():
