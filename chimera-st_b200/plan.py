@@ -413,7 +413,7 @@ class TextPlan(EncoderPlan):
         self.arena_generation = self.arena.ensure(off)
         for name, o, nbytes, rows, cols, dt in table:
             t = self.arena.buf[o:o + nbytes].view(dt)
-            setattr(self, name, t.view(rows, cols) if (rows > 1 or name == "tokens") else t.view(cols))
+            setattr(self, name, t.view(cols) if name in ("src_len", "sub_valid") else t.view(rows, cols))
         self.arena.buf[:off].zero_()
         self._pos_host = sinusoidal_table(T + 2)
 
