@@ -248,7 +248,8 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
 template <int RB> struct DmCfg {
   static constexpr int K = 32768 / RB, LD = K + DM_PAD, NBUF = (K == 512) ? 2 : 1;
   static constexpr int A_BYTES = RB * LD * 2, W_BYTES = NBUF * DL_COLS * LD * 2, RED_BYTES = 8 * RB * DL_COLS * 4;
-  static constexpr int SMEM = A_BYTES + W_BYTES + RED_BYTES;
+  static constexpr int LN_BYTES = (K == 512) ? 2 * K * 4 : 0;          // gamma | beta staged before griddepcontrol.wait
+  static constexpr int SMEM = A_BYTES + W_BYTES + RED_BYTES + LN_BYTES;
 };
 
 template <typename AT, int RB>
@@ -261,6 +262,7 @@ __global__ void __launch_bounds__(DL_THREADS, 2) dec_linear_mma_kernel(const Dec
   __nv_bfloat16* sA = reinterpret_cast<__nv_bfloat16*>(dm_smem);
   __nv_bfloat16* sW = reinterpret_cast<__nv_bfloat16*>(dm_smem + Cfg::A_BYTES);
   float* red = reinterpret_cast<float*>(dm_smem + Cfg::A_BYTES + Cfg::W_BYTES);
+  float* sln = reinterpret_cast<float*>(dm_smem + Cfg::A_BYTES + Cfg::W_BYTES + Cfg::RED_BYTES);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tq = lane & 3;
   const int row0 = blockIdx.y * RB;
   const AT* A = reinterpret_cast<const AT*>(a.A);
@@ -280,6 +282,13 @@ __global__ void __launch_bounds__(DL_THREADS, 2) dec_linear_mma_kernel(const Dec
 
   int t = blockIdx.x;
   if (NBUF == 2 && t < ntiles) load_w(t, 0);                   // weights do not depend on the previous kernel
+  if constexpr (K == 512) if (a.ln_g != nullptr) {             // nor do the LayerNorm parameters: each lane stages exactly
+#pragma unroll                                                 // the 32 values it will read back itself
+    for (int j = 0; j < V4; ++j) {
+      cp_async16(sln + 4 * lane + 128 * j, a.ln_g + 4 * lane + 128 * j);
+      cp_async16(sln + K + 4 * lane + 128 * j, a.ln_b + 4 * lane + 128 * j);
+    }
+  }
   cp_async_commit();
   pdl_wait();
   // activations: this warp's RW rows, two halves of 16 float4 per lane in flight; LayerNorm in registers; bf16 to smem
@@ -323,9 +332,11 @@ __global__ void __launch_bounds__(DL_THREADS, 2) dec_linear_mma_kernel(const Dec
 #pragma unroll
         for (int r = 0; r < HR; ++r) rstd[r] += __shfl_xor_sync(0xffffffffu, rstd[r], o);
       }
+      cp_async_wait<0>();                                        // this lane's own gamma / beta copies (and weight tile 0)
 #pragma unroll
       for (int j = 0; j < V4; ++j) {
-        const float4 gm = load4(a.ln_g + 4 * lane + 128 * j), bt = load4(a.ln_b + 4 * lane + 128 * j);
+        const float4 gm = *reinterpret_cast<const float4*>(sln + 4 * lane + 128 * j);
+        const float4 bt = *reinterpret_cast<const float4*>(sln + K + 4 * lane + 128 * j);
 #pragma unroll
         for (int r = 0; r < HR; ++r) {
           const float rs = 1.0f / sqrtf(rstd[r] * (1.0f / K) + 1e-5f);

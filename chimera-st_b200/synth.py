@@ -147,9 +147,8 @@ def make_waveforms(lengths, seed=1234, pad_to=None):
     return x, torch.tensor(lengths, dtype=torch.int64)
 
 
-# ---- decoder (NOT part of the B200 path: the reference's TransformerDecoder stays PyTorch).
-# Synthetic decoder weights exist only so that the parity tests can check "identical greedy-decoded token IDs"
-# downstream of the encoder (BASELINE.json north_star) with the oracle's greedy decoder.
+# ---- decoder: seeded weights with the reference's keys, for the greedy-decoding path (decoder.py),
+# the "identical greedy-decoded token IDs" parity tests (BASELINE.json north_star) and `bench.py --decode`.
 DEC_LAYERS, VOCAB = 6, 10000
 
 

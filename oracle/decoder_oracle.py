@@ -1,9 +1,9 @@
 """ORACLE -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
 
 CPU restatement of the reference's decoder forward and of greedy search (beam 1), used only to check the
-north-star bar "identical greedy-decoded token IDs on a fixed synthetic set" DOWNSTREAM of the encoder: the
-same oracle decoder is run on the reference/oracle memories and on the B200 memories.  The decoder itself is
-outside the B200 path.  Pinned against the reference's own `SequenceGenerator`
+north-star bar "identical greedy-decoded token IDs on a fixed synthetic set": (a) downstream of the encoder (the
+same oracle decoder is run on the reference/oracle memories and on the B200 memories) and (b) as the checker of the
+B200 greedy decoder (chimera-st_b200/decoder.py).  Pinned against the reference's own `SequenceGenerator`
 (tests/golden/greedy.npz, written by oracle/gen_golden.py).
 
 Reference lines restated:

@@ -224,5 +224,7 @@ def test_rejects_bad_inputs():
         enc(torch.zeros(2, 3, 4000).cuda(), torch.tensor([4000, 4000]).cuda())
     with pytest.raises(ValueError):
         enc(torch.zeros(1, 100).cuda(), torch.tensor([100]).cuda())          # shorter than the conv stack's receptive field
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match="text_embed_tokens"):          # text input needs the text embedding in the checkpoint
         enc(torch.zeros(1, 10, dtype=torch.long).cuda(), torch.tensor([10]).cuda())
+    with pytest.raises(NotImplementedError):
+        enc._get_w2v_feature(torch.zeros(1, 10, dtype=torch.long).cuda(), torch.tensor([10]).cuda())

@@ -1,7 +1,7 @@
 """North-star bar "identical greedy-decoded token IDs on a fixed synthetic set", checked downstream of the encoder.
 
 Goldens: the UNMODIFIED reference model + its own SequenceGenerator(beam_size=1) (oracle/gen_golden_greedy.py).
-The decoder is outside the B200 path, so the oracle's greedy decoder (oracle/decoder_oracle.py, pinned here against
+Here the decoder is the ORACLE's (the B200 decoder has its own tests in test_gpu_decoder.py): the oracle's greedy decoder (oracle/decoder_oracle.py, pinned here against
 the goldens on CPU) is run on the memories produced by the B200 encoder; a teacher-forced log-probability probe on a
 fixed random target is compared as well, because random-init greedy output is nearly constant per utterance."""
 import os
