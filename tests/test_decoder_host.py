@@ -47,6 +47,32 @@ def test_golden_reference_tokens_via_emulator():
         assert h["tokens"].tolist() == [x for x in gold[b].tolist() if x >= 0]
 
 
+def eos_happy_decoder(scale=4.0):
+    """Decoder weights whose EOS output row is scaled up: hypotheses end at scattered steps instead of running into max_len."""
+    dsd = synth.make_decoder_state_dict(seed=1)
+    E = dsd["decoder.embed_tokens.weight"].clone()
+    E[EOS] *= scale
+    dsd["decoder.embed_tokens.weight"] = E
+    dsd["decoder.output_projection.weight"] = E
+    return dsd
+
+
+def test_rows_finish_independently_and_the_loop_stops_early():
+    dsd = eos_happy_decoder(8.0)
+    mem = torch.randn(16, 6, 512, generator=torch.Generator().manual_seed(21))
+    dec = B200GreedyDecoder(dsd, dtype=torch.float32, device="cpu", lib=EmuLib(), use_graph=False)
+    hyp = dec.generate(mem, max_len=40, poll=4)
+    ref = Dm.greedy_decode(dsd, mem, max_len=40)
+    assert [h["tokens"].tolist() for h in hyp] == ref
+    lens = [len(r) for r in ref]
+    assert min(lens) < 5 and any(5 < n < 41 for n in lens) and max(lens) == 41, lens     # early, middle and forced endings in one batch
+    # only the early rows: the loop stops at the first poll after the last EOS instead of running to max_len
+    early = [b for b, n in enumerate(lens) if n < 5]
+    hyp = dec.generate(mem[:, early].contiguous(), max_len=40, poll=4)
+    assert [h["tokens"].tolist() for h in hyp] == [ref[b] for b in early]
+    assert dec.last_steps == 4
+
+
 def test_cpu_device_without_emulator_raises():
     from chimera_st_b200._lib import CstError
     with pytest.raises(CstError):

@@ -199,6 +199,33 @@ def test_c4_shape_batch64_m64_matches_oracle():
     assert sum(m > 1e-3 for m in margins) >= 60
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_rows_finish_independently_and_the_loop_stops_early(dtype):
+    """EOS-happy weights: hypotheses end at scattered steps; finished rows keep stepping but their output is frozen."""
+    from chimera_st_b200.decoder import B200GreedyDecoder
+    from oracle import decoder_oracle as Dm
+    from test_decoder_host import eos_happy_decoder
+    dsd = eos_happy_decoder(8.0)
+    mem = _r(16, 24, 512, seed=21)
+    dec = B200GreedyDecoder(dsd, dtype=dtype, device="cuda")
+    hyp = dec.generate(mem.cuda(), max_len=60)
+    ref, margins = Dm.greedy_decode(dsd, mem, max_len=60, return_margins=True)
+    tol = 1e-3 if dtype == torch.float32 else 0.15
+    same = 0
+    for b, h in enumerate(hyp):
+        assert h["tokens"][-1] == 2 and len(h["positional_scores"]) == len(h["tokens"])
+        if margins[b] > tol:
+            assert h["tokens"].tolist() == ref[b], (b, margins[b])
+            same += 1
+    assert same >= (20 if dtype == torch.float32 else 8)
+    lens = [len(r) for r in ref]
+    assert min(lens) < 6 and max(lens) > 20, lens               # early and late endings in one batch
+    early = [b for b, n in enumerate(lens) if n < 6 and margins[b] > tol]
+    hyp = dec.generate(mem[:, early].contiguous().cuda(), max_len=60)
+    assert [h["tokens"].tolist() for h in hyp] == [ref[b] for b in early]
+    assert dec.last_steps == 8                                  # first poll after the last EOS, not max_len + 1
+
+
 def test_stream_lanes_are_bit_identical_to_one_lane():
     from chimera_st_b200.decoder import B200GreedyDecoder
     mem = _r(16, 40, 512, seed=8).cuda()
