@@ -42,7 +42,7 @@ class DecLinearParams(C.Structure):
         ("lda", C.c_longlong), ("ldr", C.c_longlong), ("ldo", C.c_longlong * 3), ("step_stride", C.c_longlong * 3),
         ("step", C.c_void_p),
         ("a_dtype", C.c_int), ("w_dtype", C.c_int), ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
-        ("n_seg", C.c_int), ("act", C.c_int),
+        ("n_seg", C.c_int), ("act", C.c_int), ("out_dtype", C.c_int * 3),
     ]
 
 
@@ -76,7 +76,7 @@ _SIGS = {
     "cst_dec_embed": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_int,
                                 C.c_int, C.c_void_p, C.c_void_p]),
     "cst_dec_linear": (C.c_int, [C.POINTER(DecLinearParams), C.c_void_p]),
-    "cst_dec_attention": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong,
+    "cst_dec_attention": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_longlong,
                                     C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "cst_dec_select": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),

@@ -65,11 +65,18 @@ struct DecLinearArgs {
   const void* A; long long lda;
   const void* W; const float* bias; const float* ln_g; const float* ln_b;
   const float* residual; long long ldr;
-  float* out0; float* out1; float* out2;
+  void* out0; void* out1; void* out2;
   long long ldo0, ldo1, ldo2, ss0, ss1, ss2;
   const int* step;
   int M, N, seg_n, act;
+  int bf16_mask;                 // bit s: output segment s is bf16 (K / V cache rows of the 16-bit mode)
 };
+
+__device__ __forceinline__ void dec_store_out(const DecLinearArgs& a, int seg, size_t idx, float v) {
+  void* o = seg == 0 ? (void*)a.out0 : (seg == 1 ? (void*)a.out1 : (void*)a.out2);
+  if ((a.bf16_mask >> seg) & 1) reinterpret_cast<__nv_bfloat16*>(o)[idx] = __float2bfloat16_rn(v);
+  else reinterpret_cast<float*>(o)[idx] = v;
+}
 
 // K = 4096 / RPW is a compile-time constant (512, 1024, 2048).  A CTA owns 8*RPW rows (warp w: rows w*RPW ...), keeps
 // them resident in shared memory for its whole life (cp.async, all rows in flight at once; optionally LayerNorm-ed in
@@ -215,10 +222,9 @@ __global__ void __launch_bounds__(DL_THREADS, 1) dec_linear_kernel(const DecLine
             if (a.act == CST_ACT_RELU) v = fmaxf(v, 0.f);
             const int seg = n / a.seg_n, col = n - seg * a.seg_n;
             if (a.residual) v += a.residual[(size_t)m * a.ldr + n];
-            float* o = seg == 0 ? a.out0 : (seg == 1 ? a.out1 : a.out2);
             const long long ldo = seg == 0 ? a.ldo0 : (seg == 1 ? a.ldo1 : a.ldo2);
             const long long ss = seg == 0 ? a.ss0 : (seg == 1 ? a.ss1 : a.ss2);
-            o[(size_t)m * ldo + step * ss + col] = v;
+            dec_store_out(a, seg, (size_t)m * ldo + step * ss + col, v);
           }
         }
       }
@@ -400,10 +406,9 @@ __global__ void __launch_bounds__(DL_THREADS, 2) dec_linear_mma_kernel(const Dec
         if (a.act == CST_ACT_RELU) v = fmaxf(v, 0.f);
         const int seg = n / a.seg_n, col = n - seg * a.seg_n;
         if (a.residual) v += a.residual[(size_t)m * a.ldr + n];
-        float* o = seg == 0 ? a.out0 : (seg == 1 ? a.out1 : a.out2);
         const long long ldo = seg == 0 ? a.ldo0 : (seg == 1 ? a.ldo1 : a.ldo2);
         const long long ss = seg == 0 ? a.ss0 : (seg == 1 ? a.ss1 : a.ss2);
-        o[(size_t)m * ldo + step * ss + col] = v;
+        dec_store_out(a, seg, (size_t)m * ldo + step * ss + col, v);
       }
     }
     __syncthreads();                                           // `red` and the weight buffer just read are reused next
@@ -432,8 +437,14 @@ __global__ void dec_embed_kernel(const int* __restrict__ tokens, int ld_tok, con
 // fp32 softmax over the score row in shared memory; PV: warp w accumulates keys w, w+8, ... (lane = 2 output dims,
 // coalesced 256-byte V rows), the 8 partial rows are summed through shared memory.
 constexpr int DA_THREADS = 256;
+__device__ __forceinline__ float2 load2(const float* p) { return *reinterpret_cast<const float2*>(p); }
+__device__ __forceinline__ float2 load2(const __nv_bfloat16* p) {
+  const uint32_t u = *reinterpret_cast<const uint32_t*>(p);
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+template <typename KVT>
 __global__ void __launch_bounds__(DA_THREADS) dec_attention_kernel(const float* __restrict__ q, long long ldq,
-                                                                   const float* __restrict__ k, const float* __restrict__ v,
+                                                                   const KVT* __restrict__ k, const KVT* __restrict__ v,
                                                                    long long kv_bs, long long kv_rs, float* __restrict__ out,
                                                                    long long ldo, int H, int n_keys, int n_max,
                                                                    const int* __restrict__ step) {
@@ -449,8 +460,8 @@ __global__ void __launch_bounds__(DA_THREADS) dec_attention_kernel(const float* 
   const int n = step ? min(*step + 1, n_max) : n_keys;
   if (tid < 64) sq[tid] = q[(size_t)b * ldq + h * 64 + tid];
   __syncthreads();
-  const float* kb = k + (size_t)b * kv_bs + h * 64;
-  const float* vb = v + (size_t)b * kv_bs + h * 64;
+  const KVT* kb = k + (size_t)b * kv_bs + h * 64;
+  const KVT* vb = v + (size_t)b * kv_bs + h * 64;
   const int sub = lane & 3;                                    // which 16-dim quarter of the head this lane covers
   float4 qq[4];
 #pragma unroll
@@ -460,7 +471,7 @@ __global__ void __launch_bounds__(DA_THREADS) dec_attention_kernel(const float* 
     const int key = key0 + warp * 8 + (lane >> 2);
     float s = 0.f;
     if (key < n) {
-      const float* kr = kb + (size_t)key * kv_rs + 16 * sub;
+      const KVT* kr = kb + (size_t)key * kv_rs + 16 * sub;
 #pragma unroll
       for (int d = 0; d < 4; ++d) {
         const float4 kk = load4(kr + 4 * d);
@@ -492,7 +503,7 @@ __global__ void __launch_bounds__(DA_THREADS) dec_attention_kernel(const float* 
   float o0 = 0.f, o1 = 0.f;
   for (int key = warp; key < n; key += 8) {
     const float p = ss[key];
-    const float2 vv = *reinterpret_cast<const float2*>(vb + (size_t)key * kv_rs + 2 * lane);
+    const float2 vv = load2(vb + (size_t)key * kv_rs + 2 * lane);
     o0 = fmaf(p, vv.x, o0);
     o1 = fmaf(p, vv.y, o1);
   }
@@ -715,6 +726,12 @@ extern "C" int cst_dec_linear(const cst_dec_linear_params* p, void* stream) {
   a.A = p->A; a.lda = p->lda; a.W = p->W; a.bias = p->bias; a.ln_g = p->ln_gamma; a.ln_b = p->ln_beta;
   a.residual = p->residual; a.ldr = p->ldr;
   a.out0 = p->out[0]; a.out1 = p->out[1]; a.out2 = p->out[2];
+  a.bf16_mask = 0;
+  for (int s = 0; s < p->n_seg; ++s) {
+    CST_REQUIRE(p->out_dtype[s] == CST_F32 || p->out_dtype[s] == CST_BF16, "cst_dec_linear: out_dtype[%d]=%d unsupported", s, p->out_dtype[s]);
+    if (p->out_dtype[s] == CST_BF16) a.bf16_mask |= 1 << s;
+  }
+  CST_REQUIRE(!(p->residual && a.bf16_mask), "cst_dec_linear: residual needs an f32 output");
   a.ldo0 = p->ldo[0]; a.ldo1 = p->ldo[1]; a.ldo2 = p->ldo[2];
   a.ss0 = p->step_stride[0]; a.ss1 = p->step_stride[1]; a.ss2 = p->step_stride[2];
   a.step = p->step; a.M = p->M; a.N = p->N; a.seg_n = p->N / p->n_seg; a.act = p->act;
@@ -727,16 +744,23 @@ extern "C" int cst_dec_linear(const cst_dec_linear_params* p, void* stream) {
   return CST_OK;
 }
 
-extern "C" int cst_dec_attention(const float* q, long long ldq, const float* k, const float* v, long long kv_batch_stride,
-                                 long long kv_row_stride, float* out, long long ldo, int B, int H, int n_keys,
-                                 int n_keys_max, const int32_t* step, void* stream) {
+extern "C" int cst_dec_attention(const float* q, long long ldq, const void* k, const void* v, int kv_dtype,
+                                 long long kv_batch_stride, long long kv_row_stride, float* out, long long ldo, int B, int H,
+                                 int n_keys, int n_keys_max, const int32_t* step, void* stream) {
   CST_REQUIRE(q && k && v && out, "cst_dec_attention: null pointer");
   CST_REQUIRE(B > 0 && H > 0 && n_keys_max > 0 && (step || (n_keys > 0 && n_keys <= n_keys_max)), "cst_dec_attention: bad sizes");
-  CST_REQUIRE(kv_row_stride % 4 == 0 && kv_batch_stride % 4 == 0 && ldo % 2 == 0, "cst_dec_attention: strides must keep 16-byte rows");
+  CST_REQUIRE(kv_row_stride % 8 == 0 && kv_batch_stride % 8 == 0 && ldo % 2 == 0, "cst_dec_attention: strides must keep 16-byte rows");
   const size_t smem = (size_t)(64 + 8 * 64 + 16 + n_keys_max) * sizeof(float);
   CST_REQUIRE(smem <= 48 * 1024, "cst_dec_attention: n_keys_max=%d too large", n_keys_max);
-  CST_CHECK_CUDA(launch_dec(dec_attention_kernel, dim3(B * H), dim3(DA_THREADS), smem, (cudaStream_t)stream, q, ldq, k, v,
-                          kv_batch_stride, kv_row_stride, out, ldo, H, n_keys, n_keys_max, step));
+  if (kv_dtype == CST_F32)
+    CST_CHECK_CUDA(launch_dec(dec_attention_kernel<float>, dim3(B * H), dim3(DA_THREADS), smem, (cudaStream_t)stream, q, ldq,
+                              (const float*)k, (const float*)v, kv_batch_stride, kv_row_stride, out, ldo, H, n_keys, n_keys_max, step));
+  else if (kv_dtype == CST_BF16)
+    CST_CHECK_CUDA(launch_dec(dec_attention_kernel<__nv_bfloat16>, dim3(B * H), dim3(DA_THREADS), smem, (cudaStream_t)stream, q, ldq,
+                              (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, kv_batch_stride, kv_row_stride, out, ldo, H, n_keys,
+                              n_keys_max, step));
+  else
+    CST_REQUIRE(false, "cst_dec_attention: kv_dtype %d unsupported", kv_dtype);
   return CST_OK;
 }
 

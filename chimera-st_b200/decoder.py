@@ -98,10 +98,13 @@ class _DecodePlan:
         nl = len(P["layers"])
         z = dict(device=device, dtype=torch.float32)
         self.mem = torch.zeros(M * B, DIM, device=device, dtype=mem_dtype)       # row m*B + b  (= encoder_out [M,B,C])
-        self.xk = torch.zeros(nl, M * B, DIM, **z)            # cross-attention keys / values of the memories, per layer
-        self.xv = torch.zeros(nl, M * B, DIM, **z)
-        self.kc = torch.zeros(nl, B, self.T, DIM, **z)        # self-attention cache
-        self.vc = torch.zeros(nl, B, self.T, DIM, **z)
+        # K / V of the memories (per layer) and the self-attention cache: bf16 in the 16-bit mode (half the HBM bytes of
+        # the only tensors a step streams from DRAM), fp32 in the fp32 parity mode
+        kv = dict(device=device, dtype=P["embed"].dtype)
+        self.xk = torch.zeros(nl, M * B, DIM, **kv)
+        self.xv = torch.zeros(nl, M * B, DIM, **kv)
+        self.kc = torch.zeros(nl, B, self.T, DIM, **kv)
+        self.vc = torch.zeros(nl, B, self.T, DIM, **kv)
         self.x = torch.zeros(B, DIM, **z)
         self.q = torch.zeros(B, DIM, **z)
         self.a = torch.zeros(B, DIM, **z)
@@ -133,6 +136,7 @@ class _DecodePlan:
         n_seg = len(outs)
         for s in range(3):
             p.out[s] = outs[s].data_ptr() if s < n_seg else 0
+            p.out_dtype[s] = L.DT[outs[s].dtype] if s < n_seg else L.F32
             p.ldo[s] = (ldo[s] if ldo is not None else N // n_seg) if s < n_seg else 0
             p.step_stride[s] = step_stride[s] if (step_stride is not None and s < n_seg) else 0
         p.step = self.counters.data_ptr() if use_step else 0
@@ -142,7 +146,7 @@ class _DecodePlan:
         self.n_launch += 1
 
     def _attention(self, k, v, kv_bs, kv_rs, n_keys, n_max, use_step):
-        L.check(self.lib.cst_dec_attention(self.q.data_ptr(), DIM, k.data_ptr(), v.data_ptr(), kv_bs, kv_rs,
+        L.check(self.lib.cst_dec_attention(self.q.data_ptr(), DIM, k.data_ptr(), v.data_ptr(), L.DT[k.dtype], kv_bs, kv_rs,
                                            self.a.data_ptr(), DIM, self.B, HEADS, n_keys, n_max,
                                            self.counters.data_ptr() if use_step else 0, self._st()))
         self.n_launch += 1

@@ -133,6 +133,7 @@ def dec_linear(A, W, bias=None, ln=None, residual=None, act=L.ACT_NONE, outs=Non
     p.lda, p.ldr = A.stride(0), (residual.stride(0) if residual is not None else 0)
     for s in range(3):
         p.out[s] = outs[s].data_ptr() if s < len(outs) else 0
+        p.out_dtype[s] = L.DT[outs[s].dtype] if s < len(outs) else L.F32
         p.ldo[s] = (ldo[s] if ldo is not None else N // len(outs)) if s < len(outs) else 0
         p.step_stride[s] = step_stride[s] if (step_stride is not None and s < len(outs)) else 0
     p.step = L.ptr(step)
@@ -143,11 +144,11 @@ def dec_linear(A, W, bias=None, ln=None, residual=None, act=L.ACT_NONE, outs=Non
 
 
 def dec_attention(q, k, v, kv_batch_stride, kv_row_stride, n_heads, n_keys, n_keys_max, step=None):
-    """q [B, H*64] f32 (pre-scaled); key j of row b at k + b*kv_batch_stride + j*kv_row_stride (elements)."""
+    """q [B, H*64] f32 (pre-scaled); k / v f32 or bf16; key j of row b at k + b*kv_batch_stride + j*kv_row_stride (elements)."""
     _cuda(q, k, v, step)
     B = q.shape[0]
     out = torch.empty_like(q)
-    L.check(L.load().cst_dec_attention(q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), kv_batch_stride, kv_row_stride,
+    L.check(L.load().cst_dec_attention(q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), L.DT[k.dtype], kv_batch_stride, kv_row_stride,
                                        out.data_ptr(), out.stride(0), B, n_heads, n_keys, n_keys_max, L.ptr(step),
                                        L.stream_ptr()))
     return out

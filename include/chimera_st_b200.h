@@ -174,20 +174,22 @@ int cst_dec_embed(const int32_t* tokens, int ld_tok, const void* embed, int w_dt
  *   residual [M, N] (row stride ldr, may alias out[0]) only with n_seg == 1.  step may be NULL (= 0). */
 typedef struct cst_dec_linear_params {
   const void* A; const void* W; const float* bias; const float* ln_gamma; const float* ln_beta;
-  const float* residual; float* out[3];
+  const float* residual; void* out[3];
   long long lda, ldr, ldo[3], step_stride[3];
   const int32_t* step;
   int a_dtype, w_dtype, M, N, K, n_seg, act;
+  int out_dtype[3];              /* CST_F32 or CST_BF16 per segment (bf16: the K / V cache rows of the 16-bit mode) */
 } cst_dec_linear_params;
 int cst_dec_linear(const cst_dec_linear_params* p, void* stream);
 
 /* out[b, h*64:(h+1)*64] = softmax(q[b,h] . K[b, 0..n, h]^T) V[b, 0..n, h];  key row j of hypothesis b starts at
  * k + b*kv_batch_stride + j*kv_row_stride.  n = *step + 1 when step != NULL (self-attention over the cache: the
  * reference's saved_state prev_key/prev_value, multihead_attention.py:249-296), else n_keys (encoder-decoder attention
- * over the M memories with the all-False padding mask, transformer_layer.py:371-392).  q is pre-scaled. */
-int cst_dec_attention(const float* q, long long ldq, const float* k, const float* v, long long kv_batch_stride,
-                      long long kv_row_stride, float* out, long long ldo, int B, int H, int n_keys, int n_keys_max,
-                      const int32_t* step, void* stream);
+ * over the M memories with the all-False padding mask, transformer_layer.py:371-392).  q (f32) is pre-scaled; k / v are
+ * kv_dtype CST_F32 or CST_BF16 (strides in elements, multiples of 8). */
+int cst_dec_attention(const float* q, long long ldq, const void* k, const void* v, int kv_dtype,
+                      long long kv_batch_stride, long long kv_row_stride, float* out, long long ldo, int B, int H,
+                      int n_keys, int n_keys_max, const int32_t* step, void* stream);
 
 /* One step of SequenceGenerator._generate for beam_size = 1 (fairseq/sequence_generator.py:294-540):
  * lp = log_softmax(logits[b]); lp[pad] = -inf; step >= max_len: only EOS; step < min_len: no EOS; next = argmax.

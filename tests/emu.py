@@ -194,6 +194,7 @@ def _dec_embed(self, tokens, ld_tok, embed, w_dtype, pos_table, scale, x, B, Cd,
 def _dec_linear(self, pref, stream):
     p = pref._obj
     assert p.a_dtype == F32 and p.w_dtype == F32 and p.K % 512 == 0 and 1 <= p.n_seg <= 3 and p.N % p.n_seg == 0
+    assert all(p.out_dtype[s] == F32 for s in range(p.n_seg))
     step = int(_mem(p.step, 1, np.int32)[0]) if p.step else 0
     A = torch.from_numpy(np.stack([_mem(p.A + 4 * m * p.lda, p.K).copy() for m in range(p.M)]))
     W = torch.from_numpy(_mem(p.W, p.N * p.K).reshape(p.N, p.K).copy())
@@ -220,7 +221,8 @@ def _dec_linear(self, pref, stream):
     return 0
 
 
-def _dec_attention(self, q, ldq, k, v, kv_bs, kv_rs, out, ldo, B, H, n_keys, n_max, step, stream):
+def _dec_attention(self, q, ldq, k, v, kv_dtype, kv_bs, kv_rs, out, ldo, B, H, n_keys, n_max, step, stream):
+    assert kv_dtype == F32
     n = min(int(_mem(step, 1, np.int32)[0]) + 1, n_max) if step else n_keys
     for b in range(B):
         qb = torch.from_numpy(_mem(q + 4 * b * ldq, H * 64).copy()).view(H, 64).double()

@@ -69,6 +69,12 @@ def test_dec_linear_residual_in_place_and_segments_at_step():
     assert rel_l2(kc[:, step].cpu(), ref[:, 512:1024]) < 2e-6 and rel_l2(vc[:, step].cpu(), ref[:, 1024:]) < 2e-6
     keep = [t for t in range(T) if t != step]
     assert bool((kc[:, keep] == 7.0).all()) and bool((vc[:, keep] == 7.0).all())       # only row `step` is written
+    # bf16 cache rows (16-bit mode): q stays f32, the K / V segments are rounded once on the way into the cache
+    kb, vb = torch.zeros(B, T, 512, device="cuda", dtype=torch.bfloat16), torch.zeros(B, T, 512, device="cuda", dtype=torch.bfloat16)
+    ops.dec_linear(A.cuda(), W.cuda(), b.cuda(), outs=[q, kb, vb], ldo=[512, T * 512, T * 512], step_stride=[0, 512, 512], step=st)
+    assert rel_l2(q.cpu(), ref[:, :512]) < 2e-6
+    assert torch.equal(kb[:, step].cpu(), kc[:, step].to(torch.bfloat16).cpu()) and torch.equal(vb[:, step].cpu(), vc[:, step].to(torch.bfloat16).cpu())
+    assert int((kb != 0).sum()) == int((kb[:, step] != 0).sum())
     x = _r(B, 512, seed=9).cuda()
     x0 = x.clone()
     ops.dec_linear(A.cuda(), W[:512].cuda(), b[:512].cuda(), residual=x, outs=[x])
@@ -76,22 +82,24 @@ def test_dec_linear_residual_in_place_and_segments_at_step():
 
 
 @pytest.mark.parametrize("B,n", [(1, 1), (3, 5), (64, 33), (7, 202), (64, 64)])
-def test_dec_attention_self_cache_and_memory_layouts(B, n):
+@pytest.mark.parametrize("kvdt", [torch.float32, torch.bfloat16])
+def test_dec_attention_self_cache_and_memory_layouts(B, n, kvdt):
     from chimera_st_b200 import ops
-    H, T = 8, max(n, 2) + 3
-    q, K, V = _r(B, 512, seed=1, scale=0.3), _r(B, T, 512, seed=2), _r(B, T, 512, seed=3)
+    H, T = 8, 8 * ((max(n, 2) + 3 + 7) // 8)
+    q = _r(B, 512, seed=1, scale=0.3)
+    K, V = _r(B, T, 512, seed=2).to(kvdt), _r(B, T, 512, seed=3).to(kvdt)        # the 16-bit mode keeps K / V in bf16
 
-    def ref(K, V, n):
+    def ref(n):
         s = torch.einsum("bhd,bnhd->bhn", q.double().view(B, H, 64), K[:, :n].double().view(B, n, H, 64))
         return torch.einsum("bhn,bnhd->bhd", torch.softmax(s, -1), V[:, :n].double().view(B, n, H, 64)).reshape(B, 512)
     # self-attention over the cache: n = step + 1 keys, [B, T, 512] layout
     st = torch.tensor([n - 1], dtype=torch.int32, device="cuda")
     out = ops.dec_attention(q.cuda(), K.cuda(), V.cuda(), T * 512, 512, H, 0, T, step=st).cpu()
-    assert rel_l2(out, ref(K, V, n)) < 2e-6
+    assert rel_l2(out, ref(n)) < 2e-6
     # cross-attention over memories: key-major [n, B, 512] layout, explicit n
     Km, Vm = K[:, :n].transpose(0, 1).contiguous(), V[:, :n].transpose(0, 1).contiguous()
     out = ops.dec_attention(q.cuda(), Km.cuda(), Vm.cuda(), 512, B * 512, H, n, n).cpu()
-    assert rel_l2(out, ref(K, V, n)) < 2e-6
+    assert rel_l2(out, ref(n)) < 2e-6
 
 
 def test_dec_select_rules_and_step_protocol():

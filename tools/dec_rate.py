@@ -38,7 +38,7 @@ class Prof:
                 p = a[0]._obj
                 tag = "linear N=%d K=%d%s" % (p.N, p.K, " +LN" if p.ln_gamma else "")
             elif name == "cst_dec_attention":
-                tag = "attention " + ("self" if a[12] else "memory")
+                tag = "attention " + ("self" if a[13] else "memory")
             self.rec.append((tag, s, e))
             return rc
         return timed
