@@ -288,12 +288,9 @@ __global__ void __launch_bounds__(DL_THREADS, 2) dec_linear_mma_kernel(const Dec
 
   int t = blockIdx.x;
   if (NBUF == 2 && t < ntiles) load_w(t, 0);                   // weights do not depend on the previous kernel
-  if constexpr (K == 512) if (a.ln_g != nullptr) {             // nor do the LayerNorm parameters: each lane stages exactly
-#pragma unroll                                                 // the 32 values it will read back itself
-    for (int j = 0; j < V4; ++j) {
-      cp_async16(sln + 4 * lane + 128 * j, a.ln_g + 4 * lane + 128 * j);
-      cp_async16(sln + K + 4 * lane + 128 * j, a.ln_b + 4 * lane + 128 * j);
-    }
+  if constexpr (K == 512) if (a.ln_g != nullptr) {             // nor do the LayerNorm parameters: 256 threads x 16 bytes =
+    const float* src = tid < 128 ? a.ln_g + 4 * tid : a.ln_b + 4 * (tid - 128);   // gamma[512] | beta[512], staged once per CTA
+    cp_async16(sln + 4 * tid, src);
   }
   cp_async_commit();
   pdl_wait();
@@ -338,7 +335,10 @@ __global__ void __launch_bounds__(DL_THREADS, 2) dec_linear_mma_kernel(const Dec
 #pragma unroll
         for (int r = 0; r < HR; ++r) rstd[r] += __shfl_xor_sync(0xffffffffu, rstd[r], o);
       }
-      cp_async_wait<0>();                                        // this lane's own gamma / beta copies (and weight tile 0)
+      if (half == 0) {                                           // gamma / beta (and weight tile 0) staged by all threads
+        cp_async_wait<0>();
+        __syncthreads();                                         // CTA-uniform branch: ln_g is a kernel argument
+      }
 #pragma unroll
       for (int j = 0; j < V4; ++j) {
         const float4 gm = *reinterpret_cast<const float4*>(sln + 4 * lane + 128 * j);
