@@ -47,3 +47,48 @@ def shard_batches(batches, num_shards, shard_id):
     sharded_len = int(math.ceil(len(batches) / float(num_shards)))
     mine = list(batches[shard_id::num_shards])
     return mine + [[] for _ in range(sharded_len - len(mine))]
+
+
+# ---- collation (the caller side of the encoder: SURVEY.md §8(f) row 3) ------------------------------------------------
+def collate_waveforms(waves, ids=None, pin=False):
+    """Padded batch of 1-D float waveforms as the reference's collater builds it: zero-padded to the longest
+    (`_collate_frames(..., is_audio_input=True)`, fairseq/data/audio/speech_to_text_dataset.py:207-225), then rows
+    re-ordered by descending length with torch's own sort (triplet_dataset.py:165-179).
+    -> (ids [B] int64 in batch order, src_tokens [B, L] float32, src_lengths [B] int64); `pin` puts src_tokens in
+    pinned host memory (the form `encoder.forward_many` copies on its lanes' own streams)."""
+    import torch
+    if len(waves) == 0:
+        raise ValueError("empty batch")
+    waves = [torch.as_tensor(w, dtype=torch.float32).reshape(-1) for w in waves]
+    n = torch.tensor([w.numel() for w in waves], dtype=torch.long)
+    out = torch.zeros(len(waves), int(n.max()), dtype=torch.float32)
+    for i, w in enumerate(waves):
+        out[i, :w.numel()] = w
+    n_sorted, order = n.sort(descending=True)
+    idx = torch.arange(len(waves)) if ids is None else torch.as_tensor(ids, dtype=torch.long)
+    out = out.index_select(0, order)
+    if pin and torch.cuda.is_available():
+        out = out.pin_memory()
+    return idx.index_select(0, order), out, n_sorted
+
+
+def plan_batches(lengths, max_tokens=2000000, max_sentences=0, bsz_mult=8, num_shards=1, shard_id=0):
+    """Utterance indices of this rank's batches: longest-first order, the reference's token-budget packing, round-robin
+    sharding (generate.py:145-160)."""
+    batches = batch_by_size(ordered_indices(lengths), lengths, max_tokens, max_sentences, bsz_mult)
+    return [b for b in shard_batches(batches, num_shards, shard_id) if b]
+
+
+def encode_utterances(encoder, waves, max_tokens=2000000, bsz_mult=8, n_lanes=3, num_shards=1, shard_id=0):
+    """waveform list -> {utterance index: memories [M, 512]} for this rank's share, through the public module API:
+    reference batching + collation on the host, pinned batches, `encoder.forward_many` on stream lanes."""
+    lengths = [len(w) for w in waves]
+    todo = plan_batches(lengths, max_tokens, 0, bsz_mult, num_shards, shard_id)
+    coll = [collate_waveforms([waves[i] for i in b], ids=b, pin=True) for b in todo]
+    outs = encoder.forward_many([(w, n) for _, w, n in coll], n_lanes=n_lanes)
+    result = {}
+    for (ids, _, _), o in zip(coll, outs):
+        mem = o.encoder_out                                     # [M, B, 512]
+        for j, i in enumerate(ids.tolist()):
+            result[i] = mem[:, j]
+    return result
