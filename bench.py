@@ -195,6 +195,28 @@ def cpu_reference_rate(sample_lens, steps, warmup, threads):
     return audio / statistics.median(times), audio / min(times), times
 
 
+def eager_gpu_rate(lens, steps, warmup, autocast):
+    """BASELINE.md §5 comparison point: the reference's PyTorch-eager arithmetic (the oracle port: cuDNN conv1d, cuBLAS,
+    ATen norms / GELU / softmax) on the SAME GPU, one padded batch, CUDA events.  Not the reference arm the driver times
+    (that is the CPU path); reported by `--impl reference --ref-device cuda`."""
+    from oracle import chimera_oracle as O
+    sd = {k: v.cuda() for k, v in synth.make_state_dict(seed=0, interlingua_length=16).items()}
+    wave, tl = synth.make_waveforms(lens, seed=1234)
+    wave, tl = wave.cuda(), tl.cuda()
+    times = []
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+        for i in range(warmup + steps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out, _ = O.encoder_forward(sd, wave, tl)
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= warmup:
+                times.append(e0.elapsed_time(e1) * 1e-3)
+    audio = sum(lens) / SR
+    return audio / statistics.median(times), times
+
+
 def pick_cpu_sample(batches):
     """4 utterances around the workload's median length (~10-30 s of CPU work)."""
     allens = sorted(n for b in batches for n in b)
@@ -219,6 +241,9 @@ def main():
     ap.add_argument("--lanes", type=int, default=3, help="concurrent CUDA-stream lanes for independent batches")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-json", default="")
+    ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
+                    help="--impl reference only: cpu = the reference arm (host cores); cuda = the same oracle port as "
+                         "PyTorch-eager kernels on the GPU (BASELINE.md §5 comparison point), first batch of the workload")
     ap.add_argument("--decode", action="store_true",
                     help="also time greedy decoding (max_len_b 200) of the first batch's memories on the GPU decoder and "
                          "report it in a `decode` object (BASELINE configs[3]: encode + greedy decode); the headline "
@@ -242,6 +267,16 @@ def main():
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
         if rank != 0:
+            return
+        if args.ref_device == "cuda":
+            res = {}
+            for name, ac in (("fp32", False), ("bf16_autocast", True)):
+                med, times = eager_gpu_rate(batches[0], max(1, args.steps), 2, ac)
+                res[name] = {"audio_s_per_s": round(med, 1), "ms_per_batch": round(1e3 * statistics.median(times), 2)}
+            print(json.dumps({"impl": "reference", "variant": "pytorch-eager oracle port on cuda (not the driver's reference arm)",
+                              "metric": "encoded audio-sec/sec", "unit": "audio-s/s", "value": res["bf16_autocast"]["audio_s_per_s"],
+                              "config": cfg, "batch": "first batch of the workload: %d utterances, L=%d" % (len(batches[0]), max(batches[0])),
+                              "eager_gpu": res, "device": torch.cuda.get_device_name(0)}))
             return
         sample = pick_cpu_sample(batches)
         med, best, times = cpu_reference_rate(sample, max(1, args.steps), 1, cores)

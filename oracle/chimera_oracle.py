@@ -37,7 +37,7 @@ def conv_out_lengths(L):
 def lengths_to_padding_mask(lens):
     """fairseq/data/data_utils.py:491-495."""
     bsz, max_len = lens.size(0), int(lens.max())
-    mask = torch.arange(max_len).view(1, max_len).expand(bsz, -1)
+    mask = torch.arange(max_len, device=lens.device).view(1, max_len).expand(bsz, -1)      # `.to(lengths.device)` in the reference
     return mask >= lens.view(bsz, 1)
 
 
