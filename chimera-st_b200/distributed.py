@@ -28,9 +28,8 @@ def init(backend=None):
 
 def shard_utterances(lengths, world, rank, max_tokens=2000000, bsz_mult=8):
     """Global length-sorted token-budget batches, dealt round-robin: -> this rank's batches (index lists)."""
-    order = batching.ordered_indices(lengths)
-    batches = batching.batch_by_size(order, lengths, max_tokens, 0, bsz_mult)
-    return [b for b in batching.shard_batches(batches, world, rank) if b], len(batches)
+    n_total = len(batching.batch_by_size(batching.ordered_indices(lengths), lengths, max_tokens, 0, bsz_mult))
+    return batching.plan_batches(lengths, max_tokens, 0, bsz_mult, world, rank), n_total
 
 
 def _scalar(x, device):
