@@ -80,7 +80,8 @@ def register():
 
 
 def _plain_greedy(args, seq_gen_cls):
-    flags = ("score_reference", "sampling", "constraints", "print_alignment", "match_source_len", "unnormalized")
+    flags = ("score_reference", "sampling", "constraints", "print_alignment", "match_source_len", "unnormalized",
+             "controlled_generator")                 # the Chimera fork's own generator switch (fairseq_task.py:392)
     return (seq_gen_cls is None and getattr(args, "beam", 5) == 1 and not any(getattr(args, k, False) for k in flags)
             and getattr(args, "diverse_beam_groups", -1) <= 0 and getattr(args, "diversity_rate", -1) <= 0
             and getattr(args, "no_repeat_ngram_size", 0) == 0 and getattr(args, "temperature", 1.0) == 1.0

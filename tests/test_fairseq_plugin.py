@@ -46,6 +46,28 @@ assert torch.equal(model.encoder.interlingua_embedding.weight, sd["interlingua_e
 assert model.encoder.max_positions() is None
 model.half()                                                  # generate.py:131-138: must not break the fp32 masters
 assert model.encoder.layer_norm.weight.dtype == torch.float32
+# generator routing (fairseq_task.py:309-412 hook): beam 5 -> the reference SequenceGenerator; plain greedy -> the B200
+# generator, which refuses to be built on a CPU-resident model (no CPU fallback)
+from fairseq.tasks.fairseq_task import FairseqTask
+from fairseq.sequence_generator import SequenceGenerator
+from chimera_st_b200._lib import CstError
+class T(FairseqTask):
+    target_dictionary = d
+    source_dictionary = None
+task = T(argparse.Namespace())
+model.float()
+g5 = task.build_generator([model], argparse.Namespace(beam=5, controlled_generator=False))
+assert type(g5) is SequenceGenerator, type(g5)
+gs = task.build_generator([model], argparse.Namespace(beam=1, sampling=True, sampling_topk=3, controlled_generator=False))
+assert type(gs) is SequenceGenerator, type(gs)
+try:
+    task.build_generator([model], argparse.Namespace(beam=1, controlled_generator=False))
+    raise SystemExit("greedy generator was built on CPU")
+except CstError as e:
+    assert "CUDA" in str(e)
+import os
+os.environ["CHIMERA_B200_GREEDY"] = "0"
+assert type(task.build_generator([model], argparse.Namespace(beam=1, controlled_generator=False))) is SequenceGenerator
 print("PLUGIN_OK", type(enc).__name__, len(full))
 '''
 
