@@ -46,6 +46,17 @@ class DecLinearParams(C.Structure):
     ]
 
 
+class DecBeamParams(C.Structure):
+    _fields_ = [
+        ("logits", C.c_void_p), ("tok_in", C.c_void_p), ("tok_out", C.c_void_p), ("sc_in", C.c_void_p), ("sc_out", C.c_void_p),
+        ("hist_in", C.c_void_p), ("hist_out", C.c_void_p), ("ignore", C.c_void_p),
+        ("fin_tokens", C.c_void_p), ("fin_pos", C.c_void_p), ("fin_score", C.c_void_p), ("fin_len", C.c_void_p),
+        ("n_final", C.c_void_p), ("finished", C.c_void_p), ("counters", C.c_void_p),
+        ("B", C.c_int), ("K", C.c_int), ("V", C.c_int), ("T", C.c_int), ("max_len", C.c_int), ("min_len", C.c_int),
+        ("pad", C.c_int), ("eos", C.c_int), ("len_penalty", C.c_float),
+    ]
+
+
 _SIGS = {
     "cst_abi_version": (C.c_int, []),
     "cst_last_error": (C.c_char_p, []),
@@ -78,6 +89,10 @@ _SIGS = {
     "cst_dec_linear": (C.c_int, [C.POINTER(DecLinearParams), C.c_void_p]),
     "cst_dec_attention": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_longlong,
                                     C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "cst_dec_attention_beam": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_longlong,
+                                         C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                         C.c_void_p]),
+    "cst_dec_beam_select": (C.c_int, [C.POINTER(DecBeamParams), C.c_void_p]),
     "cst_dec_select": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
 }

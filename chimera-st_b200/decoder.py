@@ -337,6 +337,146 @@ class B200GreedyDecoder:
         return plans
 
 
+class _BeamPlan(_DecodePlan):
+    """Buffers + launch sequence of beam search for B sentences x K beams (R = B*K decoder rows).  Tokens, cumulative scores
+    and the cache-history table are double-buffered (the select kernel permutes rows from one set into the other), so the
+    replayed CUDA graph holds TWO steps (parity 0 then 1)."""
+
+    def __init__(self, P, B, K, M, max_len, mem_dtype, device, lib, use_graph):
+        super().__init__(P, B * K, M, max_len, mem_dtype, device, lib, use_graph)
+        self.nsent, self.K, self.R = B, K, B * K
+        R, T = self.R, self.T
+        zi = dict(device=device, dtype=torch.int32)
+        zf = dict(device=device, dtype=torch.float32)
+        self.tok = [torch.zeros(R, T, **zi) for _ in range(2)]
+        self.sc = [torch.zeros(R, T, **zf) for _ in range(2)]
+        self.hist = [torch.zeros(R, T, **zi) for _ in range(2)]
+        self.ignore = torch.zeros(R, **zi)
+        self.fin_tokens = torch.zeros(B, K, T, **zi)
+        self.fin_pos = torch.zeros(B, K, T, **zf)
+        self.fin_score = torch.zeros(B, K, **zf)
+        self.fin_len = torch.zeros(B, K, **zi)
+        self.n_final = torch.zeros(B, **zi)
+        self.finished = torch.zeros(B, **zi)
+        self.len_penalty = 1.0
+
+    def begin_beam(self, memories):
+        """memories [M, B, 512]: every sentence's memories are repeated for its K beams (reorder_encoder_out with
+        new_order = arange(B).repeat_interleave(K), sequence_generator.py:239-243)."""
+        M, B, K = self.M, self.nsent, self.K
+        self.begin(memories.reshape(M, B, 1, DIM).expand(M, B, K, DIM).reshape(M * B * K, DIM))
+        for t in self.tok:
+            t.fill_(PAD)
+            t[:, 0] = EOS
+        for t in self.sc + self.hist + [self.ignore, self.fin_tokens, self.fin_pos, self.fin_score, self.fin_len, self.n_final,
+                                        self.finished]:
+            t.zero_()
+
+    def _step_beam(self, parity):
+        R, M, P, T = self.R, self.M, self.P, self.T
+        tok_in, tok_out = self.tok[parity], self.tok[1 - parity]
+        n0 = self.n_launch
+        L.check(self.lib.cst_dec_embed(tok_in.data_ptr(), T, P["embed"].data_ptr(), L.DT[P["embed"].dtype],
+                                       self.pos.data_ptr(), math.sqrt(DIM), self.x.data_ptr(), R, DIM,
+                                       self.counters.data_ptr(), self._st()))
+        self.n_launch += 1
+        for i, lay in enumerate(P["layers"]):
+            self._linear(self.x, lay["qkv_w"], lay["qkv_b"], [self.q, self.kc[i], self.vc[i]], R, 3 * DIM, DIM,
+                         ln=(lay["ln1_g"], lay["ln1_b"]), ldo=[DIM, T * DIM, T * DIM], step_stride=[0, DIM, DIM],
+                         use_step=True)
+            L.check(self.lib.cst_dec_attention_beam(self.q.data_ptr(), DIM, self.kc[i].data_ptr(), self.vc[i].data_ptr(),
+                                                    L.DT[self.kc.dtype], T * DIM, DIM, self.a.data_ptr(), DIM, R, HEADS, T,
+                                                    self.hist[parity].data_ptr(), T, self.counters.data_ptr(), self._st()))
+            self.n_launch += 1
+            self._linear(self.a, lay["so_w"], lay["so_b"], [self.x], R, DIM, DIM, residual=self.x)
+            self._linear(self.x, lay["xq_w"], lay["xq_b"], [self.q], R, DIM, DIM, ln=(lay["ln2_g"], lay["ln2_b"]))
+            self._attention(self.xk[i], self.xv[i], DIM, R * DIM, M, M, False)
+            self._linear(self.a, lay["xo_w"], lay["xo_b"], [self.x], R, DIM, DIM, residual=self.x)
+            self._linear(self.x, lay["fc1_w"], lay["fc1_b"], [self.h], R, FFN, DIM, ln=(lay["ln3_g"], lay["ln3_b"]),
+                         act=L.ACT_RELU)
+            self._linear(self.h, lay["fc2_w"], lay["fc2_b"], [self.x], R, DIM, FFN, residual=self.x)
+        self._linear(self.x, P["embed"], None, [self.logits], R, P["vocab"], DIM, ln=(P["ln_g"], P["ln_b"]))
+        p = L.DecBeamParams()
+        p.logits = self.logits.data_ptr()
+        p.tok_in, p.tok_out = tok_in.data_ptr(), tok_out.data_ptr()
+        p.sc_in, p.sc_out = self.sc[parity].data_ptr(), self.sc[1 - parity].data_ptr()
+        p.hist_in, p.hist_out = self.hist[parity].data_ptr(), self.hist[1 - parity].data_ptr()
+        p.ignore = self.ignore.data_ptr()
+        p.fin_tokens, p.fin_pos, p.fin_score = self.fin_tokens.data_ptr(), self.fin_pos.data_ptr(), self.fin_score.data_ptr()
+        p.fin_len, p.n_final, p.finished = self.fin_len.data_ptr(), self.n_final.data_ptr(), self.finished.data_ptr()
+        p.counters = self.counters.data_ptr()
+        p.B, p.K, p.V, p.T = self.nsent, self.K, P["vocab"], T
+        p.max_len, p.min_len, p.pad, p.eos, p.len_penalty = self.max_len, self.min_len, PAD, EOS, self.len_penalty
+        L.check(self.lib.cst_dec_beam_select(C.byref(p), self._st()))
+        self.n_launch += 1
+        self.launches_per_step = self.n_launch - n0
+
+    def run_beam(self, memories, min_len=1, poll=4):
+        if self.graph is not None and min_len != self.min_len:
+            self.graph = None
+        self.min_len = min_len
+        self.begin_beam(memories)
+        if self.use_graph and self.graph is None:
+            self._step_beam(0)
+            self._step_beam(1)
+            torch.cuda.current_stream().synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._step_beam(0)
+                self._step_beam(1)
+            self.graph = g
+            self.begin_beam(memories)
+        steps = 0
+        while steps <= self.max_len:
+            if self.graph is not None:
+                self.graph.replay()                            # two steps; a step past max_len is a no-op in the select kernel
+                steps += 2
+            else:
+                self._step_beam(steps & 1)
+                steps += 1
+            if steps > self.max_len or (steps // 2) % poll == 0:
+                if int(self.counters[2].item()) >= self.nsent:
+                    break
+        return steps
+
+
+class B200BeamDecoder(B200GreedyDecoder):
+    """Beam search (SequenceGenerator with beam_size K <= 8, default options) on the cst_dec_* kernels plus
+    `cst_dec_attention_beam` / `cst_dec_beam_select`.  EXPERIMENTAL: the launch sequence and the ABI semantics are verified
+    on the host emulator against the oracle's beam search (pinned to the reference generator, tests/golden/beam.npz); the two
+    beam kernels have not been run on hardware yet, so on a CUDA device this class needs CST_EXPERIMENTAL_BEAM=1."""
+
+    def __init__(self, state_dict, beam=5, **kw):
+        super().__init__(state_dict, **kw)
+        if not 1 <= beam <= 8:
+            raise ValueError("beam must be in 1..8")
+        if self.device.type == "cuda" and os.environ.get("CST_EXPERIMENTAL_BEAM", "0") != "1":
+            raise NotImplementedError("GPU beam search is not validated on hardware yet (set CST_EXPERIMENTAL_BEAM=1 to try it); "
+                                      "beam > 1 otherwise stays with the reference's SequenceGenerator")
+        self.beam = beam
+
+    @torch.no_grad()
+    def generate(self, memories, max_len=200, min_len=1, len_penalty=1.0):
+        """-> per sentence a list (best first) of hypothesis dicts, as SequenceGenerator.generate returns them."""
+        if memories.device.type != self.device.type:
+            raise L.CstError("memories must live on %s (no CPU fallback)" % self.device)
+        M, B = memories.shape[0], memories.shape[1]
+        key = ("beam", B, self.beam, M, int(max_len), memories.dtype)
+        if key not in self._plans:
+            self._plans[key] = _BeamPlan(self.P, B, self.beam, M, int(max_len), memories.dtype, self.device, self.lib, self.use_graph)
+        plan = self._plans[key]
+        plan.len_penalty = float(len_penalty)
+        self.last_steps = plan.run_beam(memories.contiguous(), min_len=min_len)
+        ft, fp, fs, fl, nf = (t.cpu() for t in (plan.fin_tokens, plan.fin_pos, plan.fin_score, plan.fin_len, plan.n_final))
+        out = []
+        for b in range(B):
+            n = int(nf[b])
+            order = torch.sort(fs[b, :n], descending=True).indices.tolist()      # "sort by score descending", :533-540
+            out.append([{"tokens": ft[b, k, :int(fl[b, k])].long(), "score": float(fs[b, k]), "attention": None,
+                         "alignment": torch.empty(0), "positional_scores": fp[b, k, :int(fl[b, k])].clone()} for k in order])
+        return out
+
+
 class B200GreedyGenerator:
     """Drop-in for `SequenceGenerator(models, tgt_dict, beam_size=1, ...)` (fairseq/sequence_generator.py:17-100):
     `generate(models, sample)` runs the model's own encoder (the B200 encoder when the plugin is active) and decodes

@@ -199,6 +199,31 @@ int cst_dec_select(const float* logits, int V, int B, int32_t* tokens, int ld_to
                    int32_t* done, int32_t* out_len, int32_t* counters, int max_len, int min_len, int pad, int eos,
                    void* stream);
 
+/* ==== beam search from the memories (EXPERIMENTAL: semantics verified on the host emulator against the oracle's beam search,
+ * which is pinned to the reference's SequenceGenerator(beam_size=5); the kernels have not yet been run on hardware) ========
+ * Self-attention over the cache with a per-row history table instead of a cache re-order: position j of logical row r lives
+ * in physical cache row hist[r*ld_hist + j] for j < *step and in row r for j == *step.
+ * Replaces: reorder_incremental_state + attention over saved_state (fairseq/modules/multihead_attention.py:249-296,381-395). */
+int cst_dec_attention_beam(const float* q, long long ldq, const void* k, const void* v, int kv_dtype,
+                           long long kv_batch_stride, long long kv_row_stride, float* out, long long ldo, int R, int H,
+                           int n_keys_max, const int32_t* hist, int ld_hist, const int32_t* step, void* stream);
+
+/* One step of SequenceGenerator._generate for beam_size K <= 8 (fairseq/sequence_generator.py:294-540, finalize_hypos
+ * :590-712, BeamSearch.step fairseq/search.py:109-160), one CTA per sentence: lprobs = log_softmax(logits) with the pad /
+ * min_len / max_len rules + cumulative scores (step 0: first beam only); top-2K candidates; EOS candidates among the top K
+ * are finalised (tokens, per-position scores, score / (step+1)^len_penalty) until K hypotheses exist; the K best remaining
+ * candidates continue: tokens / cumulative scores / history rows are permuted from the *_in into the *_out buffers
+ * ([B*K, T], T >= max_len + 2).  counters int32[3]: [0] step (incremented), [1] scratch, [2] sentences finished. */
+typedef struct cst_dec_beam_params {
+  const float* logits; const int32_t* tok_in; int32_t* tok_out; const float* sc_in; float* sc_out;
+  const int32_t* hist_in; int32_t* hist_out; int32_t* ignore;
+  int32_t* fin_tokens; float* fin_pos; float* fin_score; int32_t* fin_len; int32_t* n_final; int32_t* finished;
+  int32_t* counters;
+  int B, K, V, T, max_len, min_len, pad, eos;
+  float len_penalty;
+} cst_dec_beam_params;
+int cst_dec_beam_select(const cst_dec_beam_params* p, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -83,3 +83,65 @@ def greedy_decode(sd, memories, max_len=200, min_len=1, return_margins=False):
                 break
             tokens = torch.cat((tokens, nxt.unsqueeze(1)), dim=1)
     return (out, margins) if return_margins else out
+
+
+def beam_search(sd, memories, beam=5, max_len=200, min_len=1, len_penalty=1.0):
+    """SequenceGenerator._generate + BeamSearch.step + finalize_hypos restated per sentence (sentences never interact;
+    the reference's removal of finished sentences from the batch is an optimisation), fairseq/sequence_generator.py:
+    179-540,590-712 and fairseq/search.py:109-160.  Default options only (normalize_scores, no unk penalty, no prefix,
+    no n-gram blocking, temperature 1).
+    -> per sentence a list (best first) of dicts {tokens (ends in EOS), score, positional_scores}."""
+    results = []
+    V = sd["decoder.embed_tokens.weight"].shape[0]
+    K, cand_size = beam, 2 * beam
+    with torch.no_grad():
+        for b in range(memories.shape[1]):
+            mem = memories[:, b:b + 1].expand(-1, K, -1).contiguous()
+            tokens = torch.full((K, max_len + 2), PAD, dtype=torch.long)
+            tokens[:, 0] = EOS
+            scores = torch.zeros(K, max_len + 1)
+            ignore = torch.zeros(K, dtype=torch.bool)                          # cands_to_ignore
+            finalized = []
+            for step in range(max_len + 1):
+                lp = torch.log_softmax(decoder_logits(sd, tokens[:, :step + 1], mem).float(), dim=-1)
+                lp[lp != lp] = -math.inf
+                lp[:, PAD] = -math.inf
+                if step >= max_len:
+                    lp[:, :EOS] = -math.inf
+                    lp[:, EOS + 1:] = -math.inf
+                elif step < min_len:
+                    lp[:, EOS] = -math.inf
+                # BeamSearch.step: first step uses only the first beam (all hypotheses are identical)
+                cand = lp[:1] if step == 0 else lp + scores[:, step - 1:step]
+                top = torch.topk(cand.reshape(-1), k=min(cand_size, cand.numel() - 1))
+                cand_scores, idx = top.values, top.indices
+                cand_beams, cand_tok = idx // V, idx.fmod(V)
+                eos_mask = cand_tok.eq(EOS) & cand_scores.ne(-math.inf)
+                eos_mask[:K][ignore] = False
+                # finalize_hypos: EOS among the top `beam` candidates ends that hypothesis
+                for i in range(K):
+                    if eos_mask[i] and len(finalized) < K:
+                        src = int(cand_beams[i])
+                        toks = tokens[src, 1:step + 2].clone()
+                        toks[step] = EOS
+                        pos = scores[src, :step + 1].clone()
+                        pos[step] = cand_scores[i]
+                        pos[1:] = pos[1:] - pos[:-1]
+                        finalized.append({"tokens": toks, "score": float(cand_scores[i]) / (step + 1) ** len_penalty,
+                                          "positional_scores": pos})
+                if len(finalized) == K or step == max_len:                      # is_finished
+                    break
+                # the `beam` best candidates that are not EOS (and not ignored) continue
+                eos_mask[:K] = ~((~ignore) & (~eos_mask[:K]))
+                active_mask = eos_mask.long() * cand_size + torch.arange(cand_size)[:eos_mask.numel()]
+                new_ignore, active = torch.topk(active_mask, k=K, largest=False)
+                ignore = new_ignore.ge(cand_size)
+                src = cand_beams[active]
+                tokens[:, :step + 1] = tokens[src, :step + 1]
+                tokens[:, step + 1] = cand_tok[active]
+                if step > 0:
+                    scores[:, :step] = scores[src, :step]
+                scores[:, step] = cand_scores[active]
+            order = torch.sort(torch.tensor([h["score"] for h in finalized]), descending=True).indices.tolist()
+            results.append([finalized[i] for i in order])
+    return results

@@ -23,7 +23,8 @@ CASES = {"tiny": ([16000, 12345, 8000], 7), "c1mix": ([80000, 64000, 48123, 3200
 MAX_LEN_B = 50
 
 
-def main():
+def build_reference_model():
+    """-> (unmodified reference model with the seeded synthetic weights, eval mode; target dictionary)"""
     make_overlay.build()
     make_overlay.activate()
     import tempfile
@@ -56,6 +57,12 @@ def main():
     sd["encoder.text_embed_tokens.weight"] = torch.zeros(synth.VOCAB, 512)
     print("load:", model.load_state_dict(sd, strict=True))
     model.eval()
+    return model, d
+
+
+def main():
+    model, d = build_reference_model()                          # activates the import overlay
+    from fairseq.sequence_generator import SequenceGenerator
     gen = SequenceGenerator([model], d, beam_size=1, max_len_a=0, max_len_b=MAX_LEN_B)
     out = {"max_len_b": MAX_LEN_B, "decoder_seed": 1}
     g = torch.Generator().manual_seed(99)

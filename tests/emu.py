@@ -289,3 +289,93 @@ def _text_embed(self, tokens, lengths, embed, pos_table, scale, x, valid, B, T, 
 
 
 EmuLib.cst_text_embed = _text_embed
+
+
+# ---- beam search (experimental ABI): cst_dec_attention_beam / cst_dec_beam_select --------------------------------------
+def _dec_attention_beam(self, q, ldq, k, v, kv_dtype, kv_bs, kv_rs, out, ldo, R, H, n_max, hist, ld_hist, step, stream):
+    assert kv_dtype == F32
+    cur = min(int(_mem(step, 1, np.int32)[0]), n_max - 1)
+    n = cur + 1
+    for r in range(R):
+        rows = [r if j == cur else int(_mem(hist + 4 * (r * ld_hist + j), 1, np.int32)[0]) for j in range(n)]
+        qb = torch.from_numpy(_mem(q + 4 * r * ldq, H * 64).copy()).view(H, 64).double()
+        K = torch.from_numpy(np.stack([_mem(k + 4 * (rows[j] * kv_bs + j * kv_rs), H * 64).copy() for j in range(n)])).view(n, H, 64).double()
+        Vv = torch.from_numpy(np.stack([_mem(v + 4 * (rows[j] * kv_bs + j * kv_rs), H * 64).copy() for j in range(n)])).view(n, H, 64).double()
+        o = torch.einsum("hn,nhd->hd", torch.softmax(torch.einsum("hd,nhd->hn", qb, K), -1), Vv)
+        _mem(out + 4 * r * ldo, H * 64)[:] = o.reshape(-1).float().numpy()
+    self.calls.append("dec_attention_beam")
+    return 0
+
+
+def _dec_beam_select(self, pref, stream):
+    p = pref._obj
+    B, K, V, T, C = p.B, p.K, p.V, p.T, 2 * p.K
+    cnt = _mem(p.counters, 3, np.int32)
+    step = int(cnt[0])
+    logits = _mem(p.logits, B * K * V).reshape(B, K, V)
+    tin, tout = _mem(p.tok_in, B * K * T, np.int32).reshape(B, K, T), _mem(p.tok_out, B * K * T, np.int32).reshape(B, K, T)
+    sin, sout = _mem(p.sc_in, B * K * T).reshape(B, K, T), _mem(p.sc_out, B * K * T).reshape(B, K, T)
+    hin, hout = _mem(p.hist_in, B * K * T, np.int32).reshape(B, K, T), _mem(p.hist_out, B * K * T, np.int32).reshape(B, K, T)
+    ign = _mem(p.ignore, B * K, np.int32).reshape(B, K)
+    ft, fp = _mem(p.fin_tokens, B * K * T, np.int32).reshape(B, K, T), _mem(p.fin_pos, B * K * T).reshape(B, K, T)
+    fs, fl = _mem(p.fin_score, B * K).reshape(B, K), _mem(p.fin_len, B * K, np.int32).reshape(B, K)
+    nfin, finished = _mem(p.n_final, B, np.int32), _mem(p.finished, B, np.int32)
+    for b in range(B):
+        if step > p.max_len or finished[b]:
+            continue
+        nb = 1 if step == 0 else K
+        lp = torch.log_softmax(torch.from_numpy(logits[b, :nb].copy()), -1)
+        lp[lp != lp] = -math.inf
+        lp[:, p.pad] = -math.inf
+        if step >= p.max_len:
+            lp[:, :p.eos] = -math.inf
+            lp[:, p.eos + 1:] = -math.inf
+        elif step < p.min_len:
+            lp[:, p.eos] = -math.inf
+        if step > 0:
+            lp = lp + torch.from_numpy(sin[b, :, step - 1].copy()).unsqueeze(1)
+        flat = lp.reshape(-1)
+        ncand = min(C, flat.numel() - 1)
+        # top candidates, ties by lowest flat index (stable sort of the negated values)
+        order = torch.sort(-flat, stable=True).indices[:ncand]
+        cv, cbeam, ctok = flat[order], (order // V).tolist(), (order % V).tolist()
+        eos = [ctok[c] == p.eos and float(cv[c]) != -math.inf and not (c < K and ign[b, c]) for c in range(ncand)]
+        nf = int(nfin[b])
+        for c in range(min(K, ncand)):
+            if not eos[c] or nf >= K:
+                continue
+            src = cbeam[c]
+            cum = np.concatenate((sin[b, src, :step], [float(cv[c])])).astype(np.float32)
+            ft[b, nf, :step] = tin[b, src, 1:step + 1]
+            ft[b, nf, step] = p.eos
+            fp[b, nf, :step + 1] = np.diff(np.concatenate(([np.float32(0)], cum))).astype(np.float32)
+            fl[b, nf] = step + 1
+            fs[b, nf] = np.float32(float(cv[c]) / (step + 1) ** p.len_penalty)
+            nf += 1
+        nfin[b] = nf
+        if nf == K or step == p.max_len:
+            finished[b] = 1
+            cnt[2] += 1
+            continue
+        flag = [bool(ign[b, c]) or eos[c] if c < K else eos[c] for c in range(ncand)]
+        active = [c for c in range(ncand) if not flag[c]][:K]
+        n_clean = len(active)
+        active += [c for c in range(ncand) if flag[c]][:K - n_clean]
+        new_tok, new_sc, new_h = tin[b].copy(), sin[b].copy(), hin[b].copy()
+        for i, c in enumerate(active):
+            src = cbeam[c]
+            ign[b, i] = int(i >= n_clean)
+            tout[b, i, :step + 1] = new_tok[src, :step + 1]
+            tout[b, i, step + 1] = ctok[c]
+            sout[b, i, :step] = new_sc[src, :step]
+            sout[b, i, step] = float(cv[c])
+            hout[b, i, :step] = new_h[src, :step]
+            hout[b, i, step] = b * K + src
+    if step <= p.max_len:
+        cnt[0] = step + 1
+    self.calls.append("dec_beam_select")
+    return 0
+
+
+EmuLib.cst_dec_attention_beam = _dec_attention_beam
+EmuLib.cst_dec_beam_select = _dec_beam_select
