@@ -1,6 +1,6 @@
-// Beam search on the device (EXPERIMENTAL in round 1: host logic and ABI semantics are verified against the oracle's beam
-// search -- itself pinned to the reference's SequenceGenerator -- on the host emulator; the two kernels below have been
-// compiled for sm_100a but not yet run on hardware, so `B200BeamDecoder` refuses to use them unless CST_EXPERIMENTAL_BEAM=1).
+// Beam search on the device (decoder.py: B200BeamDecoder).  Host logic and ABI semantics are verified against the oracle's
+// beam search -- itself pinned to the reference's SequenceGenerator -- on the host emulator, the kernels against the same
+// goldens on the B200 (tests/test_gpu_beam.py).
 //
 //   dec_attention_beam_kernel  self-attention over the cache with a per-row history table: position j of logical row r
 //                              lives in physical cache row hist[r][j] (j < step) or r (j == step), so that re-ordering the

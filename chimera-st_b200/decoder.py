@@ -442,17 +442,14 @@ class _BeamPlan(_DecodePlan):
 
 class B200BeamDecoder(B200GreedyDecoder):
     """Beam search (SequenceGenerator with beam_size K <= 8, default options) on the cst_dec_* kernels plus
-    `cst_dec_attention_beam` / `cst_dec_beam_select`.  EXPERIMENTAL: the launch sequence and the ABI semantics are verified
-    on the host emulator against the oracle's beam search (pinned to the reference generator, tests/golden/beam.npz); the two
-    beam kernels have not been run on hardware yet, so on a CUDA device this class needs CST_EXPERIMENTAL_BEAM=1."""
+    `cst_dec_attention_beam` / `cst_dec_beam_select`.  The K/V cache is never re-ordered: a per-row history table says
+    which physical cache row holds each past position of a beam.  Checked against the reference generator's beam-5
+    hypotheses (tests/golden/beam.npz) on the ABI emulator (CPU) and on the B200 (tests/test_gpu_beam.py)."""
 
     def __init__(self, state_dict, beam=5, **kw):
         super().__init__(state_dict, **kw)
         if not 1 <= beam <= 8:
             raise ValueError("beam must be in 1..8")
-        if self.device.type == "cuda" and os.environ.get("CST_EXPERIMENTAL_BEAM", "0") != "1":
-            raise NotImplementedError("GPU beam search is not validated on hardware yet (set CST_EXPERIMENTAL_BEAM=1 to try it); "
-                                      "beam > 1 otherwise stays with the reference's SequenceGenerator")
         self.beam = beam
 
     @torch.no_grad()
@@ -478,10 +475,11 @@ class B200BeamDecoder(B200GreedyDecoder):
 
 
 class B200GreedyGenerator:
-    """Drop-in for `SequenceGenerator(models, tgt_dict, beam_size=1, ...)` (fairseq/sequence_generator.py:17-100):
-    `generate(models, sample)` runs the model's own encoder (the B200 encoder when the plugin is active) and decodes
-    greedily on the GPU.  Returns the reference structure: per sentence a list (beam) of hypothesis dicts.  Options that
-    change the search (beam > 1, sampling, penalties, temperature, n-gram blocking, prefixes ...) raise."""
+    """Drop-in for `SequenceGenerator(models, tgt_dict, beam_size<=8, ...)` (fairseq/sequence_generator.py:17-100):
+    `generate(models, sample)` runs the model's own encoder (the B200 encoder when the plugin is active) and decodes on
+    the GPU -- greedily for beam_size 1, with `B200BeamDecoder` for 2..8.  Returns the reference structure: per sentence a
+    list (best first) of hypothesis dicts.  Options that change the search beyond that (sampling, unk penalty, temperature,
+    n-gram blocking, prefixes, unnormalised scores ...) raise."""
 
     def __init__(self, models, tgt_dict=None, beam_size=1, max_len_a=0.0, max_len_b=200, min_len=1, normalize_scores=True,
                  len_penalty=1.0, unk_penalty=0.0, temperature=1.0, match_source_len=False, no_repeat_ngram_size=0,
@@ -489,21 +487,25 @@ class B200GreedyGenerator:
         models = list(models) if isinstance(models, (list, tuple)) else [models]
         if len(models) != 1:
             raise NotImplementedError("model ensembles")
-        if (beam_size != 1 or not normalize_scores or len_penalty != 1 or unk_penalty != 0 or temperature != 1.0
+        if (not 1 <= beam_size <= 8 or not normalize_scores or unk_penalty != 0 or temperature != 1.0
                 or match_source_len or no_repeat_ngram_size):
-            raise NotImplementedError("only plain greedy search (beam 1, default penalties) runs on the B200 decoder")
+            raise NotImplementedError("only plain beam search (beam <= 8, default options) runs on the B200 decoder")
         self.model = models[0]
         self.pad, self.eos = PAD, EOS
         if tgt_dict is not None and (tgt_dict.pad(), tgt_dict.eos()) != (PAD, EOS):
             raise NotImplementedError("non-default pad/eos indices")
         self.symbols_to_strip_from_output = (set(symbols_to_strip_from_output) | {EOS}
                                              if symbols_to_strip_from_output is not None else {EOS})
-        self.beam_size, self.max_len_a, self.max_len_b, self.min_len = 1, max_len_a, max_len_b, min_len
+        self.beam_size, self.max_len_a, self.max_len_b, self.min_len = beam_size, max_len_a, max_len_b, min_len
+        self.len_penalty = float(len_penalty)
         dec_sd = {k: v for k, v in self.model.state_dict().items() if k.startswith("decoder.")}
         p = next(self.model.decoder.parameters())
         half = p.dtype in (torch.bfloat16, torch.float16)
-        self.decoder = B200GreedyDecoder(dec_sd, dtype=dtype or (torch.bfloat16 if half else torch.float32), device=p.device,
-                                         lib=lib)
+        wdt = dtype or (torch.bfloat16 if half else torch.float32)
+        if beam_size == 1:
+            self.decoder = B200GreedyDecoder(dec_sd, dtype=wdt, device=p.device, lib=lib)
+        else:
+            self.decoder = B200BeamDecoder(dec_sd, beam=beam_size, dtype=wdt, device=p.device, lib=lib)
 
     def cuda(self):
         return self
@@ -516,4 +518,10 @@ class B200GreedyGenerator:
         enc = self.model.encoder(**{k: v for k, v in net_input.items() if k != "prev_output_tokens"})
         src_len = net_input["src_tokens"].shape[1]
         max_len = min(int(self.max_len_a * src_len + self.max_len_b), self.model.max_decoder_positions() - 1)
-        return [[h] for h in self.decoder.generate(enc.encoder_out, max_len=max_len, min_len=self.min_len)]
+        if self.beam_size > 1:
+            return self.decoder.generate(enc.encoder_out, max_len=max_len, min_len=self.min_len, len_penalty=self.len_penalty)
+        hyps = self.decoder.generate(enc.encoder_out, max_len=max_len, min_len=self.min_len)
+        for h in hyps:                                             # greedy: the normalised score with the requested length penalty
+            n = len(h["tokens"])
+            h["score"] = float(h["positional_scores"].sum()) / max(n, 1) ** self.len_penalty
+        return [[h] for h in hyps]

@@ -9,9 +9,10 @@ built (generate.py:75, interactive.py:115, train.py:55).  A checkpoint stores
 (fairseq/models/__init__.py:31-165) so that arch resolves to a model class whose `build_encoder`
 (w2v2_transformer_interlingua.py:125-130) returns `B200InterlinguaEncoder` -- same parameter names, so
 `model.load_state_dict(checkpoint["model"])` works unchanged.  The decoder module stays the reference's (it owns the
-`decoder.*` parameters); with `--beam 1` and default search options `task.build_generator` returns the B200 greedy
-generator (chimera_st_b200/decoder.py), which decodes from those parameters on the GPU -- any other search setting,
-or CHIMERA_B200_GREEDY=0, keeps the reference's SequenceGenerator.
+`decoder.*` parameters); with `--beam` <= 8 (fairseq's default is 5) and otherwise default search options
+`task.build_generator` returns the B200 generator (chimera_st_b200/decoder.py: greedy for beam 1, beam search for 2..8),
+which decodes from those parameters on the GPU -- any other search setting, or CHIMERA_B200_GREEDY=0, keeps the
+reference's SequenceGenerator.
 
 Compute dtype: `--fp16` / `--bf16` / `--memory-efficient-*` select the bf16 tensor-core path, otherwise
 fp32; override with CHIMERA_B200_DTYPE=fp32|bf16.  Requires a CUDA device (there is no CPU fallback).
@@ -82,15 +83,15 @@ def register():
 def _plain_greedy(args, seq_gen_cls):
     flags = ("score_reference", "sampling", "constraints", "print_alignment", "match_source_len", "unnormalized",
              "controlled_generator")                 # the Chimera fork's own generator switch (fairseq_task.py:392)
-    return (seq_gen_cls is None and getattr(args, "beam", 5) == 1 and not any(getattr(args, k, False) for k in flags)
+    return (seq_gen_cls is None and 1 <= getattr(args, "beam", 5) <= 8 and not any(getattr(args, k, False) for k in flags)
             and getattr(args, "diverse_beam_groups", -1) <= 0 and getattr(args, "diversity_rate", -1) <= 0
             and getattr(args, "no_repeat_ngram_size", 0) == 0 and getattr(args, "temperature", 1.0) == 1.0
-            and getattr(args, "lenpen", 1) == 1 and getattr(args, "unkpen", 0) == 0 and getattr(args, "prefix_size", 0) == 0
+            and getattr(args, "unkpen", 0) == 0 and getattr(args, "prefix_size", 0) == 0
             and getattr(args, "prefix_allowed_tokens_fn", None) is None)
 
 
 def patch_build_generator():
-    """`--beam 1` with default search options -> B200GreedyGenerator (FairseqTask.build_generator,
+    """`--beam` <= 8 with default search options -> B200GreedyGenerator (FairseqTask.build_generator,
     fairseq/tasks/fairseq_task.py:309-412, is what every task's override ends in)."""
     from fairseq.tasks.fairseq_task import FairseqTask
     from chimera_st_b200.decoder import B200GreedyGenerator
@@ -102,8 +103,9 @@ def patch_build_generator():
         if (os.environ.get("CHIMERA_B200_GREEDY", "1") != "0" and _plain_greedy(args, seq_gen_cls) and len(models) == 1
                 and isinstance(models[0], B200S2TInterlinguaModel)):
             extra = extra_gen_cls_kwargs or {}
-            return B200GreedyGenerator(models, self.target_dictionary, beam_size=1, max_len_a=getattr(args, "max_len_a", 0),
-                                       max_len_b=getattr(args, "max_len_b", 200), min_len=getattr(args, "min_len", 1),
+            return B200GreedyGenerator(models, self.target_dictionary, beam_size=getattr(args, "beam", 5),
+                                       max_len_a=getattr(args, "max_len_a", 0), max_len_b=getattr(args, "max_len_b", 200),
+                                       min_len=getattr(args, "min_len", 1), len_penalty=getattr(args, "lenpen", 1),
                                        symbols_to_strip_from_output=extra.get("symbols_to_strip_from_output"))
         return orig(self, models, args, seq_gen_cls=seq_gen_cls, extra_gen_cls_kwargs=extra_gen_cls_kwargs)
     build_generator._b200 = True

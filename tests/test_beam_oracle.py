@@ -58,10 +58,3 @@ def test_beam_decoder_launch_sequence_on_the_emulator_reproduces_the_reference(n
             assert h["tokens"].tolist() == want, (name, b, k)
             assert abs(h["score"] - sc[b, k]) < 2e-4
             assert np.abs(h["positional_scores"].numpy() - ps[b, k, :len(want)]).max() < 2e-4
-
-
-def test_beam_decoder_is_gated_on_hardware():
-    from chimera_st_b200.decoder import B200BeamDecoder
-    if torch.cuda.is_available() and os.environ.get("CST_EXPERIMENTAL_BEAM", "0") != "1":
-        with pytest.raises(NotImplementedError):
-            B200BeamDecoder(synth.make_decoder_state_dict(seed=1), beam=5, device="cuda")

@@ -46,8 +46,8 @@ assert torch.equal(model.encoder.interlingua_embedding.weight, sd["interlingua_e
 assert model.encoder.max_positions() is None
 model.half()                                                  # generate.py:131-138: must not break the fp32 masters
 assert model.encoder.layer_norm.weight.dtype == torch.float32
-# generator routing (fairseq_task.py:309-412 hook): beam 5 -> the reference SequenceGenerator; plain greedy -> the B200
-# generator, which refuses to be built on a CPU-resident model (no CPU fallback)
+# generator routing (fairseq_task.py:309-412 hook): beam > 8 / sampling -> the reference SequenceGenerator; plain beam
+# search with beam <= 8 (greedy included) -> the B200 generator, which refuses to be built on a CPU-resident model
 from fairseq.tasks.fairseq_task import FairseqTask
 from fairseq.sequence_generator import SequenceGenerator
 from chimera_st_b200._lib import CstError
@@ -56,8 +56,13 @@ class T(FairseqTask):
     source_dictionary = None
 task = T(argparse.Namespace())
 model.float()
-g5 = task.build_generator([model], argparse.Namespace(beam=5, controlled_generator=False))
-assert type(g5) is SequenceGenerator, type(g5)
+g16 = task.build_generator([model], argparse.Namespace(beam=16, controlled_generator=False))
+assert type(g16) is SequenceGenerator, type(g16)
+try:
+    task.build_generator([model], argparse.Namespace(beam=5, controlled_generator=False))
+    raise SystemExit("beam-5 generator was built on CPU")
+except CstError as e:
+    assert "CUDA" in str(e)
 gs = task.build_generator([model], argparse.Namespace(beam=1, sampling=True, sampling_topk=3, controlled_generator=False))
 assert type(gs) is SequenceGenerator, type(gs)
 try:
@@ -112,15 +117,17 @@ sd["encoder.text_embed_tokens.weight"] = torch.zeros(synth.VOCAB, 512)
 model.load_state_dict(sd, strict=True); model.eval()
 wave, lens = synth.make_waveforms([9000, 6000], seed=5)
 sample = {"net_input": {"src_tokens": wave, "src_lengths": lens}}
-kw = dict(beam_size=1, max_len_a=0, max_len_b=7)
-ref = SequenceGenerator([model], d, **kw).generate([model], sample)
-new = B200GreedyGenerator([model], d, lib=EmuLib(), **kw).generate([model], sample)     # reference encoder (CPU) + B200 greedy search on the ABI emulator
-assert len(ref) == len(new) == 2
-for r, n in zip(ref, new):
-    assert len(n) == 1 and set(n[0]) >= {"tokens", "score", "attention", "alignment", "positional_scores"}
-    assert r[0]["tokens"].tolist() == n[0]["tokens"].tolist(), (r[0]["tokens"], n[0]["tokens"])
-    assert abs(float(r[0]["score"]) - n[0]["score"]) < 1e-4
-    assert (r[0]["positional_scores"] - n[0]["positional_scores"]).abs().max() < 1e-4
+for beam, lenpen in ((1, 1.0), (4, 0.6)):
+    kw = dict(beam_size=beam, max_len_a=0, max_len_b=7, len_penalty=lenpen)
+    ref = SequenceGenerator([model], d, **kw).generate([model], sample)
+    new = B200GreedyGenerator([model], d, lib=EmuLib(), **kw).generate([model], sample)     # reference encoder (CPU) + B200 search on the ABI emulator
+    assert len(ref) == len(new) == 2
+    for r, n in zip(ref, new):
+        assert len(n) == len(r) == beam and set(n[0]) >= {"tokens", "score", "attention", "alignment", "positional_scores"}
+        for rh, nh in zip(r, n):
+            assert rh["tokens"].tolist() == nh["tokens"].tolist(), (beam, rh["tokens"], nh["tokens"])
+            assert abs(float(rh["score"]) - nh["score"]) < 1e-4
+            assert (rh["positional_scores"] - nh["positional_scores"]).abs().max() < 1e-4
 print("GEN_OK", [h[0]["tokens"].tolist() for h in new])
 '''
 

@@ -1,9 +1,5 @@
-"""GPU validation of the EXPERIMENTAL beam-search kernels (cst_dec_attention_beam, cst_dec_beam_select).  Skipped unless
-CST_EXPERIMENTAL_BEAM=1: the kernels were written when the round's GPU budget was spent and have only been compiled; the
-first thing to run next round is
-
-    CST_EXPERIMENTAL_BEAM=1 python -m pytest tests/test_gpu_beam.py -m gpu -x -q
-"""
+"""GPU parity of the beam-search kernels (cst_dec_attention_beam, cst_dec_beam_select) and of B200BeamDecoder against the
+UNMODIFIED reference generator's beam-5 hypotheses (tests/golden/beam.npz, oracle/gen_golden_beam.py)."""
 import os
 
 import numpy as np
@@ -14,8 +10,7 @@ import chimera_st_b200  # noqa: F401
 from chimera_st_b200 import synth, _lib as L
 from conftest import GOLDEN, rel_l2
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("CST_EXPERIMENTAL_BEAM", "0") != "1", reason="experimental beam kernels are gated")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("kvdt", [torch.float32, torch.bfloat16])
