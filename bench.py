@@ -241,6 +241,7 @@ def main():
     ap.add_argument("--lanes", type=int, default=3, help="concurrent CUDA-stream lanes for independent batches")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-json", default="")
+    ap.add_argument("--beam", type=int, default=1, help="--decode only: beam width (1 = greedy, 2..8 = B200BeamDecoder)")
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
                     help="--impl reference only: cpu = the reference arm (host cores); cuda = the same oracle port as "
                          "PyTorch-eager kernels on the GPU (BASELINE.md §5 comparison point), first batch of the workload")
@@ -452,8 +453,10 @@ def main():
     if args.decode:
         # encode + greedy decode of the first batch (reference: SequenceGenerator beam 1, max_len_a 0, max_len_b 200);
         # random-init hypotheses run into the forced EOS, i.e. the full 201 steps
-        from chimera_st_b200.decoder import B200GreedyDecoder
-        dec = B200GreedyDecoder(synth.make_decoder_state_dict(seed=1), dtype=dtype, device="cuda")
+        from chimera_st_b200.decoder import B200GreedyDecoder, B200BeamDecoder
+        dsd = synth.make_decoder_state_dict(seed=1)
+        dec = (B200GreedyDecoder(dsd, dtype=dtype, device="cuda") if args.beam == 1
+               else B200BeamDecoder(dsd, beam=args.beam, dtype=dtype, device="cuda"))
         w0, l0 = dev[0]
         for _ in range(2):
             dec.generate(enc(w0, l0).encoder_out, max_len=200)
@@ -468,8 +471,10 @@ def main():
         a0 = sum(batches[0]) / SR
         decode = {"batch": "%d utterances x %.1f s, M=%d" % (len(batches[0]), max(batches[0]) / SR, M),
                   "encode_ms": round(t_enc, 3), "decode_ms": round(t_dec, 3), "steps": dec.last_steps,
-                  "us_per_step": round(1e3 * t_dec / max(1, dec.last_steps), 1), "gpu_launches": dec.last_launches,
-                  "tokens": sum(len(h["tokens"]) for h in hyp),
+                  "us_per_step": round(1e3 * t_dec / max(1, dec.last_steps), 1),
+                  "gpu_launches": dec.last_launches if args.beam == 1 else None,
+                  "beam": args.beam,
+                  "tokens": sum(len(h["tokens"]) for h in hyp) if args.beam == 1 else sum(len(hs[0]["tokens"]) for hs in hyp),
                   "encode_decode_audio_s_per_s": round(a0 / ((t_enc + t_dec) * 1e-3), 1),
                   "encode_only_audio_s_per_s": round(a0 / (t_enc * 1e-3), 1)}
 
