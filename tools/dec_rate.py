@@ -51,6 +51,7 @@ def main():
     ap.add_argument("--max-len", type=int, default=200)
     ap.add_argument("--encode", action="store_true")
     ap.add_argument("--lanes", default="1,2,4,8")
+    ap.add_argument("--beam", type=int, default=0, help="also time B200BeamDecoder with this beam width (2..8)")
     ap.add_argument("--json", default="")
     a = ap.parse_args()
     out = {"B": a.B, "M": a.M, "max_len": a.max_len}
@@ -94,6 +95,24 @@ def main():
                      "eager_step_us_by_kernel": {k: {"launches": v[0], "us": round(v[1], 1)} for k, v in fam.items()},
                      "eager_step_us": round(sum(v[1] for v in fam.values()), 1)}
         print(name, json.dumps(out[name]))
+    if a.beam > 1:
+        from chimera_st_b200.decoder import B200BeamDecoder
+        for dt in (torch.float32, torch.bfloat16):
+            bd = B200BeamDecoder(dsd, beam=a.beam, dtype=dt, device="cuda")
+            mem = mem32.to(dt)
+            bd.generate(mem, max_len=a.max_len)
+            ts = []
+            for _ in range(3):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                bd.generate(mem, max_len=a.max_len)
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            key = "beam%d_%s" % (a.beam, str(dt).replace("torch.", ""))
+            out[key] = {"decode_ms": round(sorted(ts)[1], 3), "steps": bd.last_steps,
+                        "us_per_step": round(1e3 * sorted(ts)[1] / max(1, bd.last_steps), 1), "rows": a.B * a.beam}
+            print(key, json.dumps(out[key]))
     if a.encode:
         from chimera_st_b200.encoder import build_encoder_from_state_dict
         L = 320000
