@@ -525,3 +525,6 @@ class B200GreedyGenerator:
             n = len(h["tokens"])
             h["score"] = float(h["positional_scores"].sum()) / max(n, 1) ** self.len_penalty
         return [[h] for h in hyps]
+
+
+B200Generator = B200GreedyGenerator        # the class serves beam widths 1..8; the first name is kept for callers

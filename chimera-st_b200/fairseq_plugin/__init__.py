@@ -11,7 +11,7 @@ built (generate.py:75, interactive.py:115, train.py:55).  A checkpoint stores
 `model.load_state_dict(checkpoint["model"])` works unchanged.  The decoder module stays the reference's (it owns the
 `decoder.*` parameters); with `--beam` <= 8 (fairseq's default is 5) and otherwise default search options
 `task.build_generator` returns the B200 generator (chimera_st_b200/decoder.py: greedy for beam 1, beam search for 2..8),
-which decodes from those parameters on the GPU -- any other search setting, or CHIMERA_B200_GREEDY=0, keeps the
+which decodes from those parameters on the GPU -- any other search setting, or CHIMERA_B200_SEARCH=0 (alias CHIMERA_B200_GREEDY=0), keeps the
 reference's SequenceGenerator.
 
 Compute dtype: `--fp16` / `--bf16` / `--memory-efficient-*` select the bf16 tensor-core path, otherwise
@@ -100,7 +100,8 @@ def patch_build_generator():
     orig = FairseqTask.build_generator
 
     def build_generator(self, models, args, seq_gen_cls=None, extra_gen_cls_kwargs=None):
-        if (os.environ.get("CHIMERA_B200_GREEDY", "1") != "0" and _plain_greedy(args, seq_gen_cls) and len(models) == 1
+        on = os.environ.get("CHIMERA_B200_SEARCH", os.environ.get("CHIMERA_B200_GREEDY", "1")) != "0"
+        if (on and _plain_greedy(args, seq_gen_cls) and len(models) == 1
                 and isinstance(models[0], B200S2TInterlinguaModel)):
             extra = extra_gen_cls_kwargs or {}
             return B200GreedyGenerator(models, self.target_dictionary, beam_size=getattr(args, "beam", 5),
