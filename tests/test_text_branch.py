@@ -98,3 +98,21 @@ def test_b200_text_branch_other_shapes_against_oracle(lens):
     assert rel_l2(enc(tok.cuda(), tl.cuda()).encoder_out.cpu(), ref) < 1e-5
     encb = build_encoder_from_state_dict(sd, dtype=torch.bfloat16, device="cuda", use_graph=False)
     assert rel_l2(encb(tok.cuda(), tl.cuda()).encoder_out.cpu(), ref) < 1e-2
+
+
+def test_text_to_tokens_on_the_emulator():
+    """MT path end to end on the ABI emulator: integer tokens -> TextPlan -> memories -> greedy decoder == oracle text
+    forward + oracle greedy search (both pinned to the reference)."""
+    from chimera_st_b200.decoder import B200GreedyDecoder
+    from oracle import decoder_oracle as Dm
+    _, sd, tok, lens = _gold()
+    P = weights.prepare(sd, torch.device("cpu"), torch.float32)
+    plan = TextPlan(P, tok.shape[0], tok.shape[1], 16, torch.float32, torch.device("cpu"), lib=EmuLib())
+    plan.load_inputs(tok, lens)
+    plan.run()
+    mem = plan.memories().contiguous()
+    dsd = synth.make_decoder_state_dict(seed=1)
+    hyp = B200GreedyDecoder(dsd, dtype=torch.float32, device="cpu", lib=EmuLib(), use_graph=False).generate(mem, max_len=5)
+    with torch.no_grad():
+        ref_mem, _ = O.encoder_forward_text(sd, tok, lens)
+    assert [h["tokens"].tolist() for h in hyp] == Dm.greedy_decode(dsd, ref_mem, max_len=5)
