@@ -11,10 +11,12 @@ One "step" = one pass of the hot path over all of a rank's batches.
 
 Printed (rank 0): ONE JSON line with value (inputs resident in HBM), e2e (pinned host buffers -> H2D ->
 encoder.forward -> D2H of the memories, through the public module API), roofline of the dominant kernel
-(live CUDA-event timing of every launch of it in one instrumented pass), cpu_baseline (the oracle port of
-the reference's CPU path on this box's cores, bounded sample), clocks sampled during the timed region.
-`--impl reference`: the reference arm = the oracle port (the reference is pure Python/PyTorch and cannot
-travel to the GPU box) on the host cores, same metric/config.
+(live CUDA-event timing of every launch of it in one instrumented pass), cpu_baseline (the UNMODIFIED reference
+encoder -- `oracle/_ref/src`, the bundle `oracle/make_ref_bundle.py` ships -- on this box's cores, one batch per length
+decile of the workload), parity (the B200 memories of those same batches against the reference's, every row), clocks
+sampled during the timed region.
+`--impl reference`: the reference arm = the reference's own modules (kind "reference"; only if the bundle is missing the
+oracle port, kind "port", with a warning) on the host cores, same metric/config; step i times decile batch i mod 10.
 """
 import argparse
 import json
@@ -40,14 +42,15 @@ SR = 16000
 
 
 # --------------------------------------------------------------------------------------- workload
-def make_workload(name, rank, world, utts, max_tokens=2000000):
+def make_workload(name, rank, world, utts, max_tokens=2000000, strong=False):
     """-> this rank's list of batches, each a list of utterance lengths (samples), longest first.
     c3: ONE global set of utts*world utterances, batched globally with the reference's rule and dealt
     round-robin to the ranks (generate.py:145-160 / ShardedIterator): per-GPU work stays ~constant as the
     number of GPUs grows (weak scaling) and the batch -> rank map is deterministic."""
     if name == "c3":
         rng = np.random.RandomState(2024)
-        lens = rng.randint(32000, 480000 + 1, size=utts * world).astype(np.int64)
+        # weak scaling: utts per GPU (set grows with the ranks); strong scaling: a FIXED global set of `utts` utterances
+        lens = rng.randint(32000, 480000 + 1, size=utts if strong else utts * world).astype(np.int64)
         mine, _ = D.shard_utterances(lens, world, rank, max_tokens, 8)
         return [[int(lens[i]) for i in b] for b in mine]
     if name == "c1":
@@ -178,51 +181,62 @@ class LaunchProfiler:
 
 
 # --------------------------------------------------------------------------------------- arms
-def cpu_reference_rate(sample_lens, steps, warmup, threads):
-    """The reference's CPU path (oracle port: same ATen CPU ops as the reference's modules) on a bounded sample."""
+def reference_forward(M, device="cpu", dtype=torch.float32):
+    """-> (fn(wave, lens) -> memories [M,B,512], kind).  kind "reference": the UNMODIFIED reference encoder
+    (S2T_W2V2_TransformerInterlinguaEncoder, fairseq/models/chimera/w2v2_transformer_interlingua.py:155-312) imported
+    from /root/reference or from the bundle oracle/_ref/src; kind "port": the oracle restatement (only when no
+    reference tree is available -- says so on stderr)."""
+    from oracle import make_overlay
+    sd = synth.make_state_dict(seed=0, interlingua_length=M)
+    if make_overlay.available():
+        import warnings
+        warnings.filterwarnings("ignore")
+        from oracle.ref_model import build_reference_encoder
+        enc, _ = build_reference_encoder(M)
+        enc.load_state_dict(sd, strict=True)
+        enc = enc.to(device=device, dtype=dtype).eval()
+
+        def fn(wave, lens):
+            return enc(wave.to(dtype), lens).encoder_out
+        return fn, "reference"
+    print("WARNING: no reference tree (/root/reference or oracle/_ref/src): timing the oracle PORT instead "
+          "(run `python -m oracle.make_ref_bundle` in the dev container)", file=sys.stderr)
     from oracle import chimera_oracle as O
-    torch.set_num_threads(threads)
-    sd = synth.make_state_dict(seed=0, interlingua_length=16)
-    wave, lens = synth.make_waveforms(sample_lens, seed=1234)
-    times = []
-    with torch.no_grad():
-        for i in range(warmup + steps):
-            t = time.perf_counter()
-            O.encoder_forward(sd, wave, lens)
-            if i >= warmup:
-                times.append(time.perf_counter() - t)
-    audio = sum(sample_lens) / SR
-    return audio / statistics.median(times), audio / min(times), times
+    sd = {k: v.to(device) for k, v in sd.items()}
+
+    def fn(wave, lens):
+        return O.encoder_forward(sd, wave, lens)[0]
+    return fn, "port"
 
 
-def eager_gpu_rate(lens, steps, warmup, autocast):
-    """BASELINE.md §5 comparison point: the reference's PyTorch-eager arithmetic (the oracle port: cuDNN conv1d, cuBLAS,
-    ATen norms / GELU / softmax) on the SAME GPU, one padded batch, CUDA events.  Not the reference arm the driver times
-    (that is the CPU path); reported by `--impl reference --ref-device cuda`."""
-    from oracle import chimera_oracle as O
-    sd = {k: v.cuda() for k, v in synth.make_state_dict(seed=0, interlingua_length=16).items()}
-    wave, tl = synth.make_waveforms(lens, seed=1234)
-    wave, tl = wave.cuda(), tl.cuda()
+def decile_sample(batches, workload):
+    """Bounded sample of the workload for the CPU arm: indices of one WHOLE bucketed batch per length decile (c3), or an
+    8-utterance slice of the single fixed batch (c1/c2/c4).  -> ([(batch index, row count)], description)"""
+    if workload != "c3" or len(batches) <= 10:
+        rows = min(8, len(batches[0]))
+        return [(0, rows)], "rows 0..%d of the %d x %d-sample batch" % (rows - 1, len(batches[0]), max(batches[0]))
+    order = sorted(range(len(batches)), key=lambda i: max(batches[i]))
+    pick = [order[min(len(order) - 1, (2 * d + 1) * len(order) // 20)] for d in range(10)]
+    desc = "one whole bucketed batch per length decile: " + ", ".join(
+        "%dx%d" % (len(batches[i]), max(batches[i])) for i in pick)
+    return [(i, len(batches[i])) for i in pick], desc
+
+
+def eager_gpu_rate(fn, wave, tl, steps, warmup, autocast=False):
+    """BASELINE.md §5 comparison point: the reference's own modules as PyTorch-eager kernels (cuDNN conv1d, cuBLAS, SDPA,
+    ATen norms / GELU) on the SAME GPU, one padded batch, CUDA events.  Not the reference arm the driver times (that is
+    the CPU path); reported by `--impl reference --ref-device cuda`."""
     times = []
     with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
         for i in range(warmup + steps):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            out, _ = O.encoder_forward(sd, wave, tl)
+            fn(wave, tl)
             e1.record()
             torch.cuda.synchronize()
             if i >= warmup:
                 times.append(e0.elapsed_time(e1) * 1e-3)
-    audio = sum(lens) / SR
-    return audio / statistics.median(times), times
-
-
-def pick_cpu_sample(batches):
-    """4 utterances around the workload's median length (~10-30 s of CPU work)."""
-    allens = sorted(n for b in batches for n in b)
-    mid = len(allens) // 2
-    s = allens[max(0, mid - 2):mid + 2]
-    return sorted(s, reverse=True)
+    return times
 
 
 def main():
@@ -237,6 +251,9 @@ def main():
     ap.add_argument("--max-tokens", type=int, default=2000000,
                     help="c3 token budget per batch in samples (default: the reference's --max-tokens 2000000, "
                          "chimera/scripts/interactive-en2any-ST.sh:21)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="c3 only: weak = --utts utterances per GPU (default, the driver's 1->8 run); strong = a fixed global set "
+                         "of --utts utterances dealt over the ranks (exposes graph warm-up and tail imbalance)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--lanes", type=int, default=3, help="concurrent CUDA-stream lanes for independent batches")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -254,10 +271,13 @@ def main():
     rank, world, local_rank = D.env_rank_world()
     cores = os.cpu_count() or 1
     M = 64 if args.workload == "c4" else 16          # configs[3] is Chimera-64
-    batches = make_workload(args.workload, rank, world, args.utts, args.max_tokens)
+    scaling = args.scaling if args.workload == "c3" else "weak"
+    batches = make_workload(args.workload, rank, world, args.utts, args.max_tokens, strong=scaling == "strong")
     audio_per_step = sum(sum(b) for b in batches) / SR
     cfg = {"workload": "%s: Chimera-%d encoder+memory, %s" % (args.workload, M, {
-        "c3": "%d utts/GPU U{2..30}s (global set x%d ranks, round-robin sharded), length-bucketed max_tokens=%.0e bsz%%8 (%d batches on rank 0)" % (args.utts, world, args.max_tokens, len(batches)),
+        "c3": ("%d utts/GPU U{2..30}s (global set x%d ranks, round-robin sharded)" % (args.utts, world) if scaling == "weak" else
+               "FIXED global set of %d utts U{2..30}s dealt round-robin over %d ranks" % (args.utts, world)) +
+              ", length-bucketed max_tokens=%.0e bsz%%8 (%d batches on rank 0)" % (args.max_tokens, len(batches)),
         "c1": "B=4 x 5 s", "c2": "B=32 x 15 s", "c4": "B=64 x 20 s"}[args.workload]),
         "interlingua_length": M, "batches_per_step": len(batches), "audio_sec_per_step_per_gpu": round(audio_per_step, 2),
         "parallelism": "utterance-sharded dp%d, no data-path collective" % world,
@@ -270,24 +290,47 @@ def main():
         if rank != 0:
             return
         if args.ref_device == "cuda":
-            res = {}
-            for name, ac in (("fp32", False), ("bf16_autocast", True)):
-                med, times = eager_gpu_rate(batches[0], max(1, args.steps), 2, ac)
-                res[name] = {"audio_s_per_s": round(med, 1), "ms_per_batch": round(1e3 * statistics.median(times), 2)}
-            print(json.dumps({"impl": "reference", "variant": "pytorch-eager oracle port on cuda (not the driver's reference arm)",
-                              "metric": "encoded audio-sec/sec", "unit": "audio-s/s", "value": res["bf16_autocast"]["audio_s_per_s"],
-                              "config": cfg, "batch": "first batch of the workload: %d utterances, L=%d" % (len(batches[0]), max(batches[0])),
+            lens0 = batches[0]
+            wave, tl = host_batch(lens0, seed=0)
+            wave, tl = wave.cuda(), tl.cuda()
+            res, kind = {}, None
+            for name, dt, ac in (("fp32", torch.float32, False), ("fp16", torch.float16, False), ("bf16_autocast", torch.float32, True)):
+                fn, kind = reference_forward(M, "cuda", dt)
+                times = eager_gpu_rate(fn, wave, tl, max(1, args.steps), 2, ac)
+                res[name] = {"audio_s_per_s": round(sum(lens0) / SR / statistics.median(times), 1),
+                             "ms_per_batch": round(1e3 * statistics.median(times), 2)}
+                del fn
+                torch.cuda.empty_cache()
+            print(json.dumps({"impl": "reference", "variant": "the reference's own modules as PyTorch-eager kernels on cuda "
+                              "(kind %s; not the driver's reference arm)" % kind,
+                              "metric": "encoded audio-sec/sec", "unit": "audio-s/s", "value": res["fp16"]["audio_s_per_s"],
+                              "config": cfg, "batch": "first batch of the workload: %d utterances, L=%d" % (len(lens0), max(lens0)),
                               "eager_gpu": res, "device": torch.cuda.get_device_name(0)}))
             return
-        sample = pick_cpu_sample(batches)
-        med, best, times = cpu_reference_rate(sample, max(1, args.steps), 1, cores)
-        line = {"impl": "reference", "metric": "encoded audio-sec/sec", "value": round(med, 3), "unit": "audio-s/s",
+        torch.set_num_threads(cores)
+        fn, kind = reference_forward(M)
+        picks, desc = decile_sample(batches, args.workload)
+        host = {i: host_batch(batches[i][:rows], seed=1000 * rank + i) for i, rows in picks}
+        times, audio = [], []
+        with torch.no_grad():
+            for it in range(args.warmup + args.steps):
+                i, rows = picks[it % len(picks)]
+                w, l = host[i]
+                t = time.perf_counter()
+                fn(w, l)
+                dt = time.perf_counter() - t
+                if it >= args.warmup:
+                    times.append(dt)
+                    audio.append(sum(batches[i][:rows]) / SR)
+        rate = sum(audio) / sum(times)
+        sample = "%s; step i runs batch i mod %d (%d timed steps = %.0f audio-s), fp32, torch CPU %d threads" % (
+            desc, len(picks), len(times), sum(audio), cores)
+        line = {"impl": "reference", "metric": "encoded audio-sec/sec", "value": round(rate, 3), "unit": "audio-s/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": round(1e3 * statistics.median(times), 2), "higher_is_better": True, "scaling": "weak",
+                "ms_per_step": round(1e3 * sum(times) / len(times), 2), "higher_is_better": True, "scaling": scaling,
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
-                "cpu_baseline": {"value": round(med, 3), "unit": "audio-s/s", "cores": cores, "kind": "port",
-                                 "sample": "%d utterances %s samples of the workload, fp32, torch CPU %d threads" % (len(sample), sample, cores)},
-                "e2e": {"value": round(med, 3), "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+                "cpu_baseline": {"value": round(rate, 3), "unit": "audio-s/s", "cores": cores, "kind": kind, "sample": sample},
+                "e2e": {"value": round(rate, 3), "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
 
@@ -442,12 +485,40 @@ def main():
         with open(args.profile_json, "w") as f:
             json.dump({"kernels": ksum, "launch_list": [(k, fl, by, s.elapsed_time(e), d) for k, fl, by, d, s, e in prof.rec]}, f)
 
-    cpu = None
+    # ---- CPU baseline + in-bench parity: the UNMODIFIED reference (fp32, host cores) on one whole batch per length decile;
+    # the B200 memories of the SAME host batches (every row) are compared with the reference's
+    cpu, parity = None, None
     if world == 1 and not args.no_cpu_baseline:
-        sample = pick_cpu_sample(batches)
-        med, best, times = cpu_reference_rate(sample, 3, 1, cores)
-        cpu = {"value": round(med, 3), "unit": "audio-s/s", "cores": cores, "kind": "port",
-               "sample": "%d utterances %s samples of the workload, fp32, torch CPU %d threads, median of 3" % (len(sample), sample, cores)}
+        torch.set_num_threads(cores)
+        fn, kind = reference_forward(M)
+        picks, desc = decile_sample(batches, args.workload)
+        t_cpu, a_cpu, checks = 0.0, 0.0, []
+        with torch.no_grad():
+            w0, l0 = host_batch([16000, 12000], seed=1)
+            fn(w0, l0)                                               # warm-up (thread pool, allocator)
+            for i, rows in picks:
+                w, l = host[i]
+                w, l = w[:rows], l[:rows]
+                t = time.perf_counter()
+                ref = fn(w, l)
+                t_cpu += time.perf_counter() - t
+                a_cpu += sum(batches[i][:rows]) / SR
+                if rows == len(batches[i]):
+                    got = enc(w.cuda(), l.cuda()).encoder_out.float().cpu()      # [M, B, 512]
+                    d = (got.double() - ref.double())
+                    per_row = (d.pow(2).sum((0, 2)).sqrt() / ref.double().pow(2).sum((0, 2)).sqrt())
+                    checks.append({"batch": "%dx%d" % (len(batches[i]), max(batches[i])),
+                                   "ragged_min_len": min(batches[i]),
+                                   "rel_l2": round(float(d.norm() / ref.double().norm()), 6),
+                                   "worst_row_rel_l2": round(float(per_row.max()), 6)})
+        cpu = {"value": round(a_cpu / t_cpu, 3), "unit": "audio-s/s", "cores": cores, "kind": kind,
+               "sample": "%s (%.0f audio-s, one pass), fp32, torch CPU %d threads" % (desc, a_cpu, cores)}
+        if checks:
+            tol = 1e-2 if dtype == torch.bfloat16 else 1e-5
+            worst = max(c["worst_row_rel_l2"] for c in checks)
+            parity = {"against": kind, "dtype": args.dtype, "tolerance_rel_l2": tol, "rows_checked": "every row of every batch",
+                      "rel_l2": max(c["rel_l2"] for c in checks), "worst_row_rel_l2": worst, "ok": bool(worst <= tol),
+                      "batches": checks}
 
     decode = None
     if args.decode:
@@ -483,12 +554,12 @@ def main():
     d2h = sum(o.numel() * 4 for o in out_host)
     line = {"metric": "encoded audio-sec/sec", "value": round(value, 1), "unit": "audio-s/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": round(1e3 * t_res / args.steps, 3),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
             "dtype": "bf16" if dtype == torch.bfloat16 else "f32", "data": "synthetic", "config": cfg,
             "e2e": {"value": round(total_audio * args.steps / t_e2e, 1), "unit": "audio-s/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "wall_s": round(t_e2e_wall, 3)},
             "gpu_launches": launches, "cuda_graph": not args.no_graph, "stream_lanes": lanes, "clocks": clocks,
-            "roofline": roofline, "roofline_hbm_kernel": hbm_roof, "cpu_baseline": cpu}
+            "roofline": roofline, "roofline_hbm_kernel": hbm_roof, "cpu_baseline": cpu, "parity": parity}
     if decode is not None:
         line["decode"] = decode
     print(json.dumps(line))

@@ -40,6 +40,8 @@ __global__ void __launch_bounds__(DB_THREADS) dec_attention_beam_kernel(const fl
   int* srow = reinterpret_cast<int*>(ss + n_max);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int r = blockIdx.x / H, h = blockIdx.x - r * H;
+  pdl_launch_dependents();
+  pdl_wait();                        // q / the cache rows of this step are written by the preceding dec_linear launch
   const int cur = min(*step, n_max - 1), n = cur + 1;
   if (tid < 64) sq[tid] = q[(size_t)r * ldq + h * 64 + tid];
   for (int j = tid; j < n; j += DB_THREADS) srow[j] = j == cur ? r : hist[(size_t)r * ld_hist + j];
@@ -129,6 +131,8 @@ __global__ void __launch_bounds__(DB_THREADS) dec_beam_select_kernel(const DecBe
   __shared__ int s_ci[2 * DB_MAXK];
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int K = a.K, V = a.V, T = a.T, C = 2 * K;
+  pdl_launch_dependents();
+  pdl_wait();                        // the logits come from the preceding dec_linear launch
   const int step = *reinterpret_cast<volatile int*>(a.counters);
   const bool live = step <= a.max_len && !a.finished[b];
   if (live) {

@@ -55,6 +55,18 @@ def prepare_decoder_weights(sd, device, dtype, prefix="decoder."):
     def f(t):
         return t.to(device=device, dtype=torch.float32).contiguous()
 
+    # only the decoder variant the Chimera recipes train (pre-LN layers, sinusoidal positions, sqrt(d)-scaled tied
+    # embeddings, no layernorm_embedding / project_in / project_out): anything else in the checkpoint is refused here so
+    # that callers (the fairseq plugin) keep the reference SequenceGenerator instead of decoding wrong tokens silently
+    import re
+    known = re.compile(r"^(embed_tokens\.weight|output_projection\.weight|embed_positions\._float_tensor|version|"
+                       r"layer_norm\.(weight|bias)|layers\.\d+\.((self_attn|encoder_attn)\.(q|k|v|out)_proj\.(weight|bias)|"
+                       r"(self_attn_layer_norm|encoder_attn_layer_norm|final_layer_norm)\.(weight|bias)|fc[12]\.(weight|bias)))$")
+    extra = [k[len(prefix):] for k in sd if k.startswith(prefix) and not known.match(k[len(prefix):])]
+    if extra:
+        raise NotImplementedError("unsupported decoder variant: unexpected checkpoint keys %s" % extra[:4])
+    if prefix + "layer_norm.weight" not in sd:
+        raise NotImplementedError("unsupported decoder variant: no final layer_norm (decoder_normalize_before=False)")
     P = {"layers": []}
     E = g("output_projection.weight") if prefix + "output_projection.weight" in sd else g("embed_tokens.weight")
     if not torch.equal(E, g("embed_tokens.weight")):
@@ -446,6 +458,8 @@ class B200BeamDecoder(B200GreedyDecoder):
     which physical cache row holds each past position of a beam.  Checked against the reference generator's beam-5
     hypotheses (tests/golden/beam.npz) on the ABI emulator (CPU) and on the B200 (tests/test_gpu_beam.py)."""
 
+    MAX_BEAM_PLANS = 4
+
     def __init__(self, state_dict, beam=5, **kw):
         super().__init__(state_dict, **kw)
         if not 1 <= beam <= 8:
@@ -460,8 +474,14 @@ class B200BeamDecoder(B200GreedyDecoder):
         M, B = memories.shape[0], memories.shape[1]
         key = ("beam", B, self.beam, M, int(max_len), memories.dtype)
         if key not in self._plans:
+            # bounded LRU: a beam plan owns 2*6*(B*K)*(max_len+2)*512 cache elements + a CUDA graph, and fairseq-generate
+            # presents a new (B, max_len) for most batches of a real test set
+            while len(self._plans) >= self.MAX_BEAM_PLANS:
+                self._plans.pop(next(iter(self._plans)))
             self._plans[key] = _BeamPlan(self.P, B, self.beam, M, int(max_len), memories.dtype, self.device, self.lib, self.use_graph)
-        plan = self._plans[key]
+        plan = self._plans[key] = self._plans.pop(key)              # most recently used last
+        if plan.graph is not None and float(len_penalty) != plan.len_penalty:
+            plan.graph = None          # len_penalty is a by-value argument of cst_dec_beam_select: baked into the captured graph
         plan.len_penalty = float(len_penalty)
         self.last_steps = plan.run_beam(memories.contiguous(), min_len=min_len)
         ft, fp, fs, fl, nf = (t.cpu() for t in (plan.fin_tokens, plan.fin_pos, plan.fin_score, plan.fin_len, plan.n_final))
@@ -491,6 +511,15 @@ class B200GreedyGenerator:
                 or match_source_len or no_repeat_ngram_size):
             raise NotImplementedError("only plain beam search (beam <= 8, default options) runs on the B200 decoder")
         self.model = models[0]
+        margs = getattr(self.model, "args", None)
+        if margs is not None:
+            bad = [k for k, want in (("decoder_learned_pos", False), ("no_scale_embedding", False), ("layernorm_embedding", False),
+                                     ("decoder_normalize_before", True), ("no_token_positional_embeddings", False),
+                                     ("decoder_embed_dim", DIM), ("decoder_ffn_embed_dim", FFN), ("decoder_attention_heads", HEADS),
+                                     ("adaptive_softmax_cutoff", None), ("cross_self_attention", False))
+                   if getattr(margs, k, want) != want]
+            if bad:
+                raise NotImplementedError("decoder options not supported by the B200 decoder: %s" % bad)
         self.pad, self.eos = PAD, EOS
         if tgt_dict is not None and (tgt_dict.pad(), tgt_dict.eos()) != (PAD, EOS):
             raise NotImplementedError("non-default pad/eos indices")

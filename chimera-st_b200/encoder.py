@@ -188,6 +188,14 @@ class B200InterlinguaEncoder(nn.Module):
             raise NotImplementedError("training-mode forward (dropout / LayerDrop) is not implemented; call .eval()")
         if src_tokens.dim() != 2 or src_lengths.shape != (src_tokens.shape[0],):
             raise ValueError("expected src_tokens [B,L], src_lengths [B]")
+        # Precondition of the frame-mask rule (a4): the batch is padded exactly to its longest utterance, as the
+        # reference's collater guarantees (speech_to_text_dataset.py:218).  The reference derives the mask width from
+        # max(src_lengths) (w2v2_transformer.py:327) and breaks on an over-padded batch; we use L = src_tokens.shape[1].
+        # Checked only for host-resident lengths (a device tensor would need a sync).
+        if src_tokens.dtype.is_floating_point and src_lengths.device.type == "cpu" and src_lengths.numel():
+            if int(src_lengths.max()) != src_tokens.shape[1]:
+                raise ValueError("src_tokens must be padded to max(src_lengths) exactly (got L=%d, max length %d)"
+                                 % (src_tokens.shape[1], int(src_lengths.max())))
 
     @torch.no_grad()
     def _get_w2v_feature(self, src_tokens, src_lengths):

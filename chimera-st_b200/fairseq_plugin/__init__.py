@@ -84,7 +84,7 @@ def _plain_greedy(args, seq_gen_cls):
     flags = ("score_reference", "sampling", "constraints", "print_alignment", "match_source_len", "unnormalized",
              "controlled_generator")                 # the Chimera fork's own generator switch (fairseq_task.py:392)
     return (seq_gen_cls is None and 1 <= getattr(args, "beam", 5) <= 8 and not any(getattr(args, k, False) for k in flags)
-            and getattr(args, "diverse_beam_groups", -1) <= 0 and getattr(args, "diversity_rate", -1) <= 0
+            and getattr(args, "diverse_beam_groups", -1) <= 0 and getattr(args, "diversity_rate", -1) <= -1      # > -1 selects DiverseSiblingsSearch (fairseq_task.py:349)
             and getattr(args, "no_repeat_ngram_size", 0) == 0 and getattr(args, "temperature", 1.0) == 1.0
             and getattr(args, "unkpen", 0) == 0 and getattr(args, "prefix_size", 0) == 0
             and getattr(args, "prefix_allowed_tokens_fn", None) is None)
@@ -104,10 +104,13 @@ def patch_build_generator():
         if (on and _plain_greedy(args, seq_gen_cls) and len(models) == 1
                 and isinstance(models[0], B200S2TInterlinguaModel)):
             extra = extra_gen_cls_kwargs or {}
-            return B200GreedyGenerator(models, self.target_dictionary, beam_size=getattr(args, "beam", 5),
-                                       max_len_a=getattr(args, "max_len_a", 0), max_len_b=getattr(args, "max_len_b", 200),
-                                       min_len=getattr(args, "min_len", 1), len_penalty=getattr(args, "lenpen", 1),
-                                       symbols_to_strip_from_output=extra.get("symbols_to_strip_from_output"))
+            try:
+                return B200GreedyGenerator(models, self.target_dictionary, beam_size=getattr(args, "beam", 5),
+                                           max_len_a=getattr(args, "max_len_a", 0), max_len_b=getattr(args, "max_len_b", 200),
+                                           min_len=getattr(args, "min_len", 1), len_penalty=getattr(args, "lenpen", 1),
+                                           symbols_to_strip_from_output=extra.get("symbols_to_strip_from_output"))
+            except NotImplementedError as e:       # a decoder variant / option the B200 decoder does not cover
+                print("chimera_st_b200: keeping the reference SequenceGenerator (%s)" % e, file=sys.stderr)
         return orig(self, models, args, seq_gen_cls=seq_gen_cls, extra_gen_cls_kwargs=extra_gen_cls_kwargs)
     build_generator._b200 = True
     FairseqTask.build_generator = build_generator

@@ -38,7 +38,9 @@ int cst_device_info(char* name, int name_cap, int* sm_count, int* cc_major, int*
  * mask of Wav2Vec2Model.forward (fairseq/models/wav2vec/wav2vec2.py:543-548), output_length of
  * _get_w2v_feature (fairseq/models/chimera/w2v2_transformer.py:327-333) and
  * Conv1dSubsampler.get_out_seq_lens_tensor (fairseq/models/speech_to_text/s2t_transformer.py:63-67).
- * src_len [B] int64 (device); L = padded sample width; n_frames = T'.
+ * src_len [B] int64 (device); L = padded sample width; n_frames = T'.  Precondition: L == max(src_len) (the collater
+ * pads to the longest utterance, speech_to_text_dataset.py:218; the reference takes the mask width from max(src_lengths)
+ * and is undefined for an over-padded batch).
  * Outputs (device; any may be NULL): w2v_valid [B] int32 = min(T', ceil(len/(L/T'))),
  * sub_valid [B] int32 = subsampled twice, w2v_len64 [B] int64, frame_mask [B*T'] uint8 (1 = padded). */
 int cst_frame_lengths(const int64_t* src_len, int B, int L, int n_frames,

@@ -34,7 +34,7 @@ def build_reference_model():
     from fairseq.models.chimera.w2v2_transformer_interlingua import S2TTransformerInterlinguaModelW2V2
     from fairseq.sequence_generator import SequenceGenerator
     torch.set_num_threads(8)
-    d = Dictionary.load("/root/reference/chimera/resources/wmt14-en-de-spm/spm_unigram10000_wave_joint.txt")
+    d = Dictionary.load(os.path.join(make_overlay.ref_root(), "chimera/resources/wmt14-en-de-spm/spm_unigram10000_wave_joint.txt"))
     assert len(d) == synth.VOCAB and (d.bos(), d.pad(), d.eos(), d.unk()) == (0, 1, 2, 3)
 
     class Task:

@@ -6,8 +6,11 @@ one file that is regex-patched on the fly into the git-ignored `oracle/_ref/`
 configs.py:880-889).  All arithmetic files (wav2vec2.py, multihead_attention.py,
 transformer_layer.py, s2t_transformer.py, chimera/*.py) execute unmodified.
 
-The overlay cannot travel to the GPU box (/root/reference does not exist there):
-it is used only by `oracle/gen_golden.py` to pin the oracle restatement.
+Where the reference comes from (`ref_root()`): /root/reference when it is mounted (dev
+container), else the bundle `oracle/_ref/src/` that `oracle/make_ref_bundle.py` wrote -- verbatim
+copies of the reference files this path imports, git-ignored, shipped to the GPU box with the
+snapshot like a built .so.  The overlay resolves the reference root when it is IMPORTED (no absolute
+path is baked in), so the same `oracle/_ref/` works here and on the box.  CST_REF_ROOT overrides.
 
 usage: python oracle/make_overlay.py   ->  oracle/_ref/{ovl,shim}
 """
@@ -18,6 +21,34 @@ import sys
 REF = "/root/reference"
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, "_ref")
+BUNDLE = os.path.join(OUT, "src")
+
+
+def ref_root():
+    """Root of the reference tree to import: CST_REF_ROOT, the mounted tree, or the bundle; None if there is none."""
+    env = os.environ.get("CST_REF_ROOT")
+    for cand in ([env] if env else [REF, BUNDLE]):
+        if cand and os.path.isdir(os.path.join(cand, "fairseq")):
+            return cand
+    return None
+
+
+def available():
+    return ref_root() is not None
+
+
+# evaluated inside the overlay package when it is imported
+_RESOLVE = (
+    "import os, sys\n"
+    "def _ref_root():\n"
+    "    here = os.path.dirname(os.path.abspath(__file__))\n"
+    "    while os.path.basename(here) != 'ovl':\n"
+    "        here = os.path.dirname(here)\n"
+    "    env = os.environ.get('CST_REF_ROOT')\n"
+    "    for cand in ([env] if env else ['/root/reference', os.path.join(os.path.dirname(here), 'src')]):\n"
+    "        if cand and os.path.isdir(os.path.join(cand, 'fairseq')):\n"
+    "            return cand\n"
+    "    raise ImportError('no reference tree: neither /root/reference nor oracle/_ref/src')\n")
 
 
 def _w(path, text):
@@ -26,9 +57,11 @@ def _w(path, text):
         f.write(text)
 
 
-def build(out=OUT, ref=REF):
-    if not os.path.isdir(ref):
-        raise RuntimeError("reference tree %s not present (GPU box?)" % ref)
+def build(out=OUT, ref=None):
+    ref = ref or ref_root()
+    if ref is None:
+        raise RuntimeError("no reference tree: neither %s nor the bundle %s (run oracle/make_ref_bundle.py in the "
+                           "dev container)" % (REF, BUNDLE))
     shim, ovl = os.path.join(out, "shim"), os.path.join(out, "ovl")
     # --- stubs for packages the container lacks -------------------------------
     _w(os.path.join(shim, "omegaconf", "__init__.py"),
@@ -67,18 +100,18 @@ def build(out=OUT, ref=REF):
         _w(os.path.join(shim, m, "__init__.py"), "")
     # --- overlay package: search overlay dir first, then the reference ---------
     _w(os.path.join(ovl, "fairseq", "__init__.py"),
-       "import os, sys\n"
-       "__path__ = [os.path.dirname(__file__), %r]\n"
+       _RESOLVE +
+       "__path__ = [os.path.dirname(__file__), os.path.join(_ref_root(), 'fairseq')]\n"
        "__version__ = '1.0.0a0'\n"
        "from fairseq.logging import meters, metrics, progress_bar\n"
        "sys.modules['fairseq.meters'] = meters\n"
        "sys.modules['fairseq.metrics'] = metrics\n"
-       "sys.modules['fairseq.progress_bar'] = progress_bar\n" % os.path.join(ref, "fairseq"))
+       "sys.modules['fairseq.progress_bar'] = progress_bar\n")
     _w(os.path.join(ovl, "fairseq", "dataclass", "__init__.py"),
-       "import os\n"
-       "__path__ = [os.path.dirname(__file__), %r]\n"
+       _RESOLVE +
+       "__path__ = [os.path.dirname(__file__), os.path.join(_ref_root(), 'fairseq', 'dataclass')]\n"
        "from .configs import FairseqDataclass\n"
-       "from .constants import ChoiceEnum\n" % os.path.join(ref, "fairseq", "dataclass"))
+       "from .constants import ChoiceEnum\n")
     src = open(os.path.join(ref, "fairseq", "dataclass", "configs.py")).read()
     src = re.sub(r"^(    [a-z_]+: ([A-Za-z]+Config)) = \2\(\)$",
                  r"\1 = field(default_factory=\2)", src, flags=re.M)
