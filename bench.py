@@ -156,6 +156,11 @@ class LaunchProfiler:
             dtype, B, H, n_q, n_kv = a[4], a[8], a[9], a[10], a[12]
             kind = "attention_tc_bf16" if (dtype == 1 and n_q > 64) else ("memory_attention" if (n_q <= 64 and n_kv <= 2048) else "attention_simt")
             return (kind, 4.0 * B * H * n_q * n_kv * 64, 0, "B%d H%d q%d kv%d" % (B, H, n_q, n_kv))
+        if name == "cst_attention_segs":
+            from chimera_st_b200 import plan as _plan_mod
+            dtype, B, H, n_q, n_kv = a[4], a[8], a[9], a[11], a[12]
+            kind = "attention_tc_bf16" if (dtype == 1 and n_q > 64) else ("memory_attention" if (n_q <= 64 and n_kv <= 2048) else "attention_simt")
+            return (kind, 4.0 * H * _plan_mod.SEG_WORK.get(a[10], B * n_q * n_kv) * 64, 0, "B%d H%d q<=%d kv<=%d" % (B, H, n_q, n_kv))
         if name == "cst_layernorm":
             rows, C = a[8], a[9]
             by = rows * C * (4 + (4 if a[4] else 0) + ((2 if a[6] == 1 else 4) if a[5] else 0))
@@ -255,7 +260,10 @@ def main():
                     help="c3 only: weak = --utts utterances per GPU (default, the driver's 1->8 run); strong = a fixed global set "
                          "of --utts utterances dealt over the ranks (exposes graph warm-up and tail imbalance)")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--lanes", type=int, default=3, help="concurrent CUDA-stream lanes for independent batches")
+    ap.add_argument("--lanes", type=int, default=2, help="concurrent CUDA-stream lanes for independent super-batches")
+    ap.add_argument("--super-rows", type=int, default=-1,
+                    help="wav2vec2 frame rows per super-batch (several reference batches, each with its own padded width, in one "
+                         "row space / one CUDA graph); -1 = the encoder's default (24576), 0 = one plan per reference batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-json", default="")
     ap.add_argument("--beam", type=int, default=1, help="--decode only: beam width (1 = greedy, 2..8 = B200BeamDecoder)")
@@ -342,7 +350,7 @@ def main():
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     sd = synth.make_state_dict(seed=0, interlingua_length=M)
     enc = build_encoder_from_state_dict(sd, dtype=dtype, device="cuda", use_graph=not args.no_graph)
-    enc.MAX_PLANS = 4096
+    enc.MAX_PLANS = 64          # bounded LRU of cached plans / CUDA graphs (c3: 19 super-batch compositions per lane set)
 
     host = [host_batch(b, seed=1000 * rank + i) for i, b in enumerate(batches)]
     dev = [(w.cuda(non_blocking=True), l.cuda(non_blocking=True)) for w, l in host]
@@ -358,28 +366,18 @@ def main():
         return D.reduce_max(x, "cuda")
 
     lanes = max(1, args.lanes)
+    super_rows = None if args.super_rows < 0 else args.super_rows
+    supers = enc.plan_super_batches([tuple(w.shape) for w, _ in dev], super_rows)
 
     def step_resident():
-        if lanes == 1:
-            n = 0
-            for (w, l) in dev:
-                plan = enc._plan(*w.shape)
-                plan.load_inputs(w, l)
-                n += plan.run()
-            return n
-        enc.forward_many(dev, n_lanes=lanes)
+        enc.forward_many(dev, n_lanes=lanes, super_rows=super_rows)
         return enc.last_launches
 
     def step_e2e():
         # public API with HOST buffers: pinned waveforms -> H2D -> encoder -> D2H of the memories
         # (the encoder copies host tensors straight into its input buffers on the stream that runs the batch, so
         # with stream lanes one batch's H2D copy overlaps another batch's kernels)
-        if lanes == 1:
-            for (w, l), oh in zip(host, out_host):
-                out = enc(w, l)
-                oh.copy_(out.encoder_out, non_blocking=True)
-        else:
-            enc.forward_many(host, n_lanes=lanes, out=out_host)
+        enc.forward_many(host, n_lanes=lanes, out=out_host, super_rows=super_rows)
         torch.cuda.synchronize()
 
     for _ in range(max(3, args.warmup)):
@@ -413,16 +411,18 @@ def main():
 
     total_audio = D.reduce_sum(audio_per_step, "cuda")
 
-    # ---- instrumented pass: per-kernel CUDA-event timing (non-graph) for the roofline object
+    # ---- instrumented pass: per-kernel CUDA-event timing (non-graph) for the roofline object, same super-batches
     prof = None
-    for (w, l) in dev:
-        p = enc._plan(*w.shape)
+    for idx in supers:
+        groups = [tuple(dev[i][0].shape) for i in idx]
+        p = enc._plan(groups[0][0], groups[0][1]) if len(groups) == 1 else enc._plan(None, None, groups=groups)
         if prof is None:
             prof = LaunchProfiler(p.lib)
         real = p.lib
         p.lib = prof
-        p.load_inputs(w, l)
-        # keep the GPU busy while the host enqueues this batch's ~350 launches, so that the CUDA-event brackets
+        for k, i in enumerate(idx):
+            p.load_inputs(dev[i][0], dev[i][1], group=k)
+        # keep the GPU busy while the host enqueues this super-batch's launches, so that the CUDA-event brackets
         # measure kernel execution and not host launch gaps (a graph replay has none either)
         torch.cuda._sleep(int(3.5e7))
         p.run(eager=True)
@@ -558,7 +558,10 @@ def main():
             "dtype": "bf16" if dtype == torch.bfloat16 else "f32", "data": "synthetic", "config": cfg,
             "e2e": {"value": round(total_audio * args.steps / t_e2e, 1), "unit": "audio-s/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "wall_s": round(t_e2e_wall, 3)},
-            "gpu_launches": launches, "cuda_graph": not args.no_graph, "stream_lanes": lanes, "clocks": clocks,
+            "gpu_launches": launches, "cuda_graph": not args.no_graph, "stream_lanes": lanes,
+            "super_batches": {"count": len(supers), "frame_rows_target": enc.SUPER_ROWS if super_rows is None else super_rows,
+                              "reference_batches_per_super_batch": round(len(dev) / max(1, len(supers)), 2)},
+            "clocks": clocks,
             "roofline": roofline, "roofline_hbm_kernel": hbm_roof, "cpu_baseline": cpu, "parity": parity}
     if decode is not None:
         line["decode"] = decode

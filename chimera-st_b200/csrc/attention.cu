@@ -16,21 +16,25 @@ __global__ void __launch_bounds__(256) attention_kernel(const T* __restrict__ q,
                                                         const T* __restrict__ v, T* __restrict__ out,
                                                         long long ldq, long long ldkv, long long ldo,
                                                         int n_q, int q_rows_per_seg, int n_kv, int kv_rows_per_seg,
-                                                        const int32_t* __restrict__ kv_len) {
+                                                        const int32_t* __restrict__ kv_len, const int4* __restrict__ seg) {
   extern __shared__ float sm[];
   float* Qt = sm;                         // [d][i], pitch AT_LD
   float* Kt = sm + AT_D * AT_LD;          // [d][j]; reused as Pt [j][i]
   float* Vs = sm + 2 * AT_D * AT_LD;      // [j][d], pitch 64
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * AT_BQ;
+  // ragged batches: seg[b] = {first q row, q rows, first kv row, kv rows} (static plan data)
+  long long q_row0 = (long long)b * q_rows_per_seg, kv_row0 = (long long)b * kv_rows_per_seg;
+  if (seg != nullptr) { const int4 sg = seg[b]; q_row0 = sg.x; n_q = sg.y; kv_row0 = sg.z; n_kv = sg.w; }
+  if (q0 >= n_q) return;
   pdl_launch_dependents();
   pdl_wait();
-  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * AT_BQ;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   int klen = kv_len ? kv_len[b] : n_kv;
   if (klen > n_kv) klen = n_kv;
 
-  const T* qb = q + ((long long)b * q_rows_per_seg) * ldq + h * AT_D;
-  const T* kb = k + ((long long)b * kv_rows_per_seg) * ldkv + h * AT_D;
-  const T* vb = v + ((long long)b * kv_rows_per_seg) * ldkv + h * AT_D;
+  const T* qb = q + q_row0 * ldq + h * AT_D;
+  const T* kb = k + kv_row0 * ldkv + h * AT_D;
+  const T* vb = v + kv_row0 * ldkv + h * AT_D;
 
   // Q tile -> Qt (transposed).  loader: row = tid & 63, 4 float4 columns per thread
   {
@@ -127,7 +131,7 @@ __global__ void __launch_bounds__(256) attention_kernel(const T* __restrict__ q,
         for (int c = 0; c < 4; ++c) o[a][c] = fmaf(pv[a], vv[c], o[a][c]);
     }
   }
-  T* ob = out + ((long long)b * q_rows_per_seg) * ldo + h * AT_D + tx * 4;
+  T* ob = out + q_row0 * ldo + h * AT_D + tx * 4;
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
     const int r = q0 + ty * 4 + a;
@@ -153,22 +157,25 @@ __global__ void __launch_bounds__(MA_THREADS) memory_attention_kernel(const T* _
                                                                       const T* __restrict__ v, T* __restrict__ out,
                                                                       long long ldq, long long ldkv, long long ldo,
                                                                       int n_q, int q_rows_per_seg, int n_kv, int kv_rows_per_seg,
-                                                                      const int32_t* __restrict__ kv_len) {
+                                                                      const int32_t* __restrict__ kv_len, const int4* __restrict__ seg) {
   extern __shared__ float sm[];
   float* Qs = sm;                          // [16][64]
   float* inv_l = sm + MA_Q * AT_D;         // [16]
   float* Vs = inv_l + MA_Q;                // [64 key rows][64] staging for step 3
   float* S = Vs + MA_VCH * AT_D;           // [16][n_kv_pad]
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * MA_Q;
+  long long q_row0 = (long long)b * q_rows_per_seg, kv_row0 = (long long)b * kv_rows_per_seg;
+  if (seg != nullptr) { const int4 sg = seg[b]; q_row0 = sg.x; n_q = sg.y; kv_row0 = sg.z; n_kv = sg.w; }   // n_kv <= launch maximum
+  if (q0 >= n_q) return;
   pdl_launch_dependents();
   pdl_wait();
-  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * MA_Q;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ldS = (n_kv + 3) & ~3;
   int klen = kv_len ? kv_len[b] : n_kv;
   if (klen > n_kv) klen = n_kv;
-  const T* qb = q + ((long long)b * q_rows_per_seg) * ldq + h * AT_D;
-  const T* kb = k + ((long long)b * kv_rows_per_seg) * ldkv + h * AT_D;
-  const T* vb = v + ((long long)b * kv_rows_per_seg) * ldkv + h * AT_D;
+  const T* qb = q + q_row0 * ldq + h * AT_D;
+  const T* kb = k + kv_row0 * ldkv + h * AT_D;
+  const T* vb = v + kv_row0 * ldkv + h * AT_D;
   {
     const int m = tid >> 4, d = (tid & 15) * 4;                  // 256 threads = 16 rows x 16 float4
     float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -250,7 +257,7 @@ __global__ void __launch_bounds__(MA_THREADS) memory_attention_kernel(const T* _
     }
     if (q0 + m < n_q) {
       const float inv = inv_l[m];
-      store4(out + ((long long)b * q_rows_per_seg + q0 + m) * ldo + h * AT_D + d, make_float4(o.x * inv, o.y * inv, o.z * inv, o.w * inv));
+      store4(out + (q_row0 + q0 + m) * ldo + h * AT_D + d, make_float4(o.x * inv, o.y * inv, o.z * inv, o.w * inv));
     }
   }
 }
@@ -258,7 +265,7 @@ __global__ void __launch_bounds__(MA_THREADS) memory_attention_kernel(const T* _
 template <typename T>
 static int launch_memory_attention(const T* q, const T* k, const T* v, T* out, long long ldq, long long ldkv, long long ldo,
                                    int B, int H, int n_q, int q_rows_per_seg, int n_kv, int kv_rows_per_seg,
-                                   const int32_t* kv_len, cudaStream_t st) {
+                                   const int32_t* kv_len, const int32_t* seg, cudaStream_t st) {
   const int smem = (MA_Q * AT_D + MA_Q + MA_VCH * AT_D + MA_Q * ((n_kv + 3) & ~3)) * 4;
   static int attr_bytes = 0;
   if (smem > attr_bytes) {
@@ -267,13 +274,50 @@ static int launch_memory_attention(const T* q, const T* k, const T* v, T* out, l
   }
   dim3 grid(cdiv(n_q, MA_Q), H, B);
   CST_CHECK_CUDA(launch_k(memory_attention_kernel<T>, grid, dim3(MA_THREADS), smem, st, q, k, v, out, ldq, ldkv, ldo, n_q, q_rows_per_seg,
-                          n_kv, kv_rows_per_seg, kv_len));
+                          n_kv, kv_rows_per_seg, kv_len, reinterpret_cast<const int4*>(seg)));
   return CST_OK;
 }
 
 int launch_attention_tc(const void* q, const void* k, const void* v, void* out, long long ldq, long long ldkv, long long ldo,
                         int B, int H, int n_q, int q_rows_per_seg, int n_kv, int kv_rows_per_seg,
-                        const int32_t* kv_len, cudaStream_t st);
+                        const int32_t* kv_len, const int32_t* seg, cudaStream_t st);
+
+// seg == nullptr: B uniform segments.  seg != nullptr (int32 [B][4] = {first q row, q rows, first kv row, kv rows}):
+// n_q / n_kv are the maxima over the table and q_rows_per_seg / kv_rows_per_seg the total rows of the q / kv buffers.
+static int attention_dispatch(const void* q, const void* k, const void* v, void* out, int dtype,
+                              long long ldq, long long ldkv, long long ldo,
+                              int B, int H, int n_q, int q_rows_per_seg, int n_kv, int kv_rows_per_seg,
+                              const int32_t* kv_len, const int32_t* seg, cudaStream_t st) {
+  const int4* seg4 = reinterpret_cast<const int4*>(seg);
+  // bf16 with enough query rows to fill a 128-row MMA tile: tensor-core kernel (attention_tc.cu);
+  // fp32 (exact-parity mode) and the M-query memory stage: the CUDA-core kernel above.
+  if (dtype == CST_BF16 && n_q > 64)
+    return launch_attention_tc(q, k, v, out, ldq, ldkv, ldo, B, H, n_q, q_rows_per_seg, n_kv, kv_rows_per_seg, kv_len, seg, st);
+  // few queries over a whole key axis (the memory stage): dedicated kernel; CST_MEMATTN=0 keeps the generic one
+  static const int mem_attn = [] { const char* e = getenv("CST_MEMATTN"); return e ? atoi(e) : 1; }();
+  if (mem_attn && n_q <= 64 && n_kv <= MA_MAX_KV && (dtype == CST_BF16 || dtype == CST_F32)) {
+    if (dtype == CST_F32)
+      return launch_memory_attention((const float*)q, (const float*)k, (const float*)v, (float*)out, ldq, ldkv, ldo, B, H, n_q, q_rows_per_seg,
+                                     n_kv, kv_rows_per_seg, kv_len, seg, st);
+    return launch_memory_attention((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, (__nv_bfloat16*)out, ldq, ldkv, ldo,
+                                   B, H, n_q, q_rows_per_seg, n_kv, kv_rows_per_seg, kv_len, seg, st);
+  }
+  dim3 grid(cdiv(n_q, AT_BQ), H, B);
+  static bool attr[2] = {false, false};
+  if (dtype == CST_F32) {
+    if (!attr[0]) { CST_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM)); attr[0] = true; }
+    CST_CHECK_CUDA(launch_k(attention_kernel<float>, grid, dim3(256), AT_SMEM, st, (const float*)q, (const float*)k, (const float*)v, (float*)out,
+                            ldq, ldkv, ldo, n_q, q_rows_per_seg, n_kv, kv_rows_per_seg, kv_len, seg4));
+  } else if (dtype == CST_BF16) {
+    if (!attr[1]) { CST_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM)); attr[1] = true; }
+    CST_CHECK_CUDA(launch_k(attention_kernel<__nv_bfloat16>, grid, dim3(256), AT_SMEM, st, (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v,
+                            (__nv_bfloat16*)out, ldq, ldkv, ldo, n_q, q_rows_per_seg, n_kv, kv_rows_per_seg, kv_len, seg4));
+  } else {
+    CST_REQUIRE(false, "cst_attention: bad dtype %d", dtype);
+  }
+  CST_LAUNCH_CHECK();
+  return CST_OK;
+}
 }  // namespace cst
 
 extern "C" int cst_attention(const void* q, const void* k, const void* v, void* out, int dtype,
@@ -285,33 +329,21 @@ extern "C" int cst_attention(const void* q, const void* k, const void* v, void* 
   CST_REQUIRE(n_q <= q_rows_per_seg && n_kv <= kv_rows_per_seg, "cst_attention: n_q/n_kv exceed rows per segment");
   CST_REQUIRE(ldq % 8 == 0 && ldkv % 8 == 0 && ldo % 8 == 0, "cst_attention: leading dims must be multiples of 8");
   CST_REQUIRE(H <= 65535 && B <= 65535, "cst_attention: grid too large");
-  cudaStream_t st = (cudaStream_t)stream;
-  // bf16 with enough query rows to fill a 128-row MMA tile: tensor-core kernel (attention_tc.cu);
-  // fp32 (exact-parity mode) and the M-query memory stage: the CUDA-core kernel above.
-  if (dtype == CST_BF16 && n_q > 64)
-    return launch_attention_tc(q, k, v, out, ldq, ldkv, ldo, B, H, n_q, q_rows_per_seg, n_kv, kv_rows_per_seg, kv_len, st);
-  // few queries over a whole key axis (the memory stage): dedicated kernel; CST_MEMATTN=0 keeps the generic one
-  static const int mem_attn = [] { const char* e = getenv("CST_MEMATTN"); return e ? atoi(e) : 1; }();
-  if (mem_attn && n_q <= 64 && n_kv <= MA_MAX_KV && (dtype == CST_BF16 || dtype == CST_F32)) {
-    if (dtype == CST_F32)
-      return launch_memory_attention((const float*)q, (const float*)k, (const float*)v, (float*)out, ldq, ldkv, ldo, B, H, n_q, q_rows_per_seg,
-                                     n_kv, kv_rows_per_seg, kv_len, st);
-    return launch_memory_attention((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, (__nv_bfloat16*)out, ldq, ldkv, ldo,
-                                   B, H, n_q, q_rows_per_seg, n_kv, kv_rows_per_seg, kv_len, st);
-  }
-  dim3 grid(cdiv(n_q, AT_BQ), H, B);
-  static bool attr[2] = {false, false};
-  if (dtype == CST_F32) {
-    if (!attr[0]) { CST_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM)); attr[0] = true; }
-    CST_CHECK_CUDA(launch_k(attention_kernel<float>, grid, dim3(256), AT_SMEM, st, (const float*)q, (const float*)k, (const float*)v, (float*)out,
-                            ldq, ldkv, ldo, n_q, q_rows_per_seg, n_kv, kv_rows_per_seg, kv_len));
-  } else if (dtype == CST_BF16) {
-    if (!attr[1]) { CST_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM)); attr[1] = true; }
-    CST_CHECK_CUDA(launch_k(attention_kernel<__nv_bfloat16>, grid, dim3(256), AT_SMEM, st, (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v,
-                            (__nv_bfloat16*)out, ldq, ldkv, ldo, n_q, q_rows_per_seg, n_kv, kv_rows_per_seg, kv_len));
-  } else {
-    CST_REQUIRE(false, "cst_attention: bad dtype %d", dtype);
-  }
-  CST_LAUNCH_CHECK();
-  return CST_OK;
+  return attention_dispatch(q, k, v, out, dtype, ldq, ldkv, ldo, B, H, n_q, q_rows_per_seg, n_kv, kv_rows_per_seg, kv_len, nullptr,
+                            (cudaStream_t)stream);
+}
+
+extern "C" int cst_attention_segs(const void* q, const void* k, const void* v, void* out, int dtype,
+                                  long long ldq, long long ldkv, long long ldo, int B, int H,
+                                  const int32_t* seg, int max_n_q, int max_n_kv, long long q_rows_total, long long kv_rows_total,
+                                  const int32_t* kv_len, void* stream) {
+  using namespace cst;
+  CST_REQUIRE(q && k && v && out && seg && B > 0 && H > 0 && max_n_q > 0 && max_n_kv > 0, "cst_attention_segs: bad args");
+  CST_REQUIRE(q_rows_total > 0 && kv_rows_total > 0 && q_rows_total < (1ll << 31) && kv_rows_total < (1ll << 31),
+              "cst_attention_segs: bad buffer extents");
+  CST_REQUIRE(ldq % 8 == 0 && ldkv % 8 == 0 && ldo % 8 == 0, "cst_attention_segs: leading dims must be multiples of 8");
+  CST_REQUIRE(((uintptr_t)seg % 16) == 0, "cst_attention_segs: the segment table must be 16-byte aligned");
+  CST_REQUIRE(H <= 65535 && B <= 65535, "cst_attention_segs: grid too large");
+  return attention_dispatch(q, k, v, out, dtype, ldq, ldkv, ldo, B, H, max_n_q, (int)q_rows_total, max_n_kv, (int)kv_rows_total, kv_len,
+                            seg, (cudaStream_t)stream);
 }

@@ -48,7 +48,8 @@ struct FalseTag { static constexpr bool value = false; };
 __global__ void __launch_bounds__(FA_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, long long ldo,
-                    int n_q, int q_rows_per_seg, int n_kv, int kv_rows_per_seg, const int32_t* __restrict__ kv_len) {
+                    int n_q, int q_rows_per_seg, int n_kv, int kv_rows_per_seg, const int32_t* __restrict__ kv_len,
+                    const int4* __restrict__ seg) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
   const uint32_t sQ = base;
@@ -68,6 +69,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * FA_BQ;
+  // ragged batches: seg[b] = {first q row, q rows, first kv row, kv rows} of utterance b (static plan data, not produced
+  // by the preceding kernel); the grid covers the longest utterance and the surplus CTAs of shorter ones leave at once
+  int q_row0 = b * q_rows_per_seg, kv_row0 = b * kv_rows_per_seg;
+  if (seg != nullptr) {
+    const int4 sg = seg[b];
+    q_row0 = sg.x; n_q = sg.y; kv_row0 = sg.z; n_kv = sg.w;
+  }
+  if (q0 >= n_q) return;
   pdl_launch_dependents();
 
   if (warp == 0 && lane == 0) {
@@ -98,12 +107,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
   if (warp == 0) {
     if (lane == 0 && n_tiles > 0) {
-      const int q_row = b * q_rows_per_seg + q0;
+      const int q_row = q_row0 + q0;
       mbar_expect_tx(q_full, FA_Q_BYTES);
       tma_load_2d(sQ, &tmQ, q_full, h * FA_D, q_row);
       for (int j = 0; j < n_tiles; ++j) {
         const int st = j % FA_KS, u = j / FA_KS;
-        const int k_row = b * kv_rows_per_seg + j * FA_BK;
+        const int k_row = kv_row0 + j * FA_BK;
         mbar_wait(k_empty + 8 * st, (u & 1) ^ 1);        // S_{j-2} done
         mbar_expect_tx(k_full + 8 * st, FA_KV_BYTES);
         tma_load_2d(sK + st * FA_KV_BYTES, &tmK, k_full + 8 * st, h * FA_D, k_row);
@@ -301,7 +310,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const float l_tot = lsum[r];
     if (q0 + r < n_q) {
       const float inv = l_tot > 0.f ? 1.0f / l_tot : 0.f;
-      __nv_bfloat16* op = out + ((long long)b * q_rows_per_seg + q0 + r) * ldo + h * FA_D + hh * 32;
+      __nv_bfloat16* op = out + ((long long)q_row0 + q0 + r) * ldo + h * FA_D + hh * 32;
 #pragma unroll
       for (int i = 0; i < 32; i += 8) {
         uint4 u;
@@ -328,9 +337,11 @@ extern "C" int cst_debug_fa_prof(long long* host16, int reset) {
 }
 #endif
 
+// seg == nullptr: B uniform segments.  seg != nullptr: n_q / n_kv are the maxima over the table, q_rows_per_seg /
+// kv_rows_per_seg the TOTAL rows of the q / kv buffers (tensor-map extents).
 int launch_attention_tc(const void* q, const void* k, const void* v, void* out, long long ldq, long long ldkv, long long ldo,
                         int B, int H, int n_q, int q_rows_per_seg, int n_kv, int kv_rows_per_seg,
-                        const int32_t* kv_len, cudaStream_t st) {
+                        const int32_t* kv_len, const int32_t* seg, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
     CST_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
@@ -339,15 +350,17 @@ int launch_attention_tc(const void* q, const void* k, const void* v, void* out, 
   CST_REQUIRE(((uintptr_t)q % 16) == 0 && ((uintptr_t)k % 16) == 0 && ((uintptr_t)v % 16) == 0, "cst_attention(bf16): q/k/v must be 16-byte aligned");
   // tensor maps over the full row-major buffers: inner = one head's 64 columns are addressed by coordinate
   CUtensorMap tmQ, tmK, tmV;
-  int rc = make_map_2d(&tmQ, q, H * FA_D, (long long)B * q_rows_per_seg, ldq, FA_D, FA_BQ);
+  const long long q_total = seg ? q_rows_per_seg : (long long)B * q_rows_per_seg;
+  const long long kv_total = seg ? kv_rows_per_seg : (long long)B * kv_rows_per_seg;
+  int rc = make_map_2d(&tmQ, q, H * FA_D, q_total, ldq, FA_D, FA_BQ);
   if (rc) return rc;
-  rc = make_map_2d(&tmK, k, H * FA_D, (long long)B * kv_rows_per_seg, ldkv, FA_D, FA_BK);
+  rc = make_map_2d(&tmK, k, H * FA_D, kv_total, ldkv, FA_D, FA_BK);
   if (rc) return rc;
-  rc = make_map_2d(&tmV, v, H * FA_D, (long long)B * kv_rows_per_seg, ldkv, FA_D, FA_BK);
+  rc = make_map_2d(&tmV, v, H * FA_D, kv_total, ldkv, FA_D, FA_BK);
   if (rc) return rc;
   dim3 grid(cdiv(n_q, FA_BQ), H, B);
   CST_CHECK_CUDA(launch_k(attention_tc_kernel, grid, dim3(FA_THREADS), FA_SMEM, st, tmQ, tmK, tmV, (__nv_bfloat16*)out, ldo, n_q,
-                          q_rows_per_seg, n_kv, kv_rows_per_seg, kv_len));
+                          q_rows_per_seg, n_kv, kv_rows_per_seg, kv_len, reinterpret_cast<const int4*>(seg)));
   return CST_OK;
 }
 

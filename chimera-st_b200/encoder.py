@@ -112,7 +112,7 @@ class B200InterlinguaEncoder(nn.Module):
             raise RuntimeError("B200InterlinguaEncoder runs only on a CUDA device (no CPU fallback); call .cuda()")
         return dev
 
-    def _plan(self, B, L, lane=None, text=False):
+    def _plan(self, B, L, lane=None, text=False, groups=None):
         dev = self._device()
         if self._prepared is None:
             self._prepared = _weights.prepare(self.state_dict(), dev, self.compute_dtype, self.conv_dtype)
@@ -122,7 +122,7 @@ class B200InterlinguaEncoder(nn.Module):
             plans, arena = self._plans, self._arena
         else:
             plans, arena = lane["plans"], lane["arena"]
-        key = (B, L, text)
+        key = (B, L, text) if groups is None else tuple(groups)
         plan = plans.get(key)
         if plan is None:
             while len(plans) >= self.MAX_PLANS:
@@ -133,7 +133,7 @@ class B200InterlinguaEncoder(nn.Module):
                                 arena=arena)
             else:
                 plan = EncoderPlan(self._prepared, B, L, self.interlingua_length, self.compute_dtype, dev, self.use_graph,
-                                   arena=arena, conv_dtype=self.conv_dtype)
+                                   arena=arena, conv_dtype=self.conv_dtype, groups=groups)
             if arena.generation != gen:                # arena grew: older plans (and their graphs) point at freed memory
                 plans.clear()
             plans[key] = plan
@@ -148,35 +148,67 @@ class B200InterlinguaEncoder(nn.Module):
                            for _ in range(n)]
         return self._lanes
 
+    SUPER_ROWS = 24576      # forward_many: wav2vec2 frame rows per super-batch; 0 = one plan per batch
+    SUPER_MAX_GROUPS = 16
+
+    @staticmethod
+    def frame_rows(B, L):
+        """Rows a padded [B, L] batch occupies in the wav2vec2 stage (allocation grid of plan.Geometry)."""
+        t0 = (L - 10) // 5 + 1
+        return B * ((t0 + 63) // 64)
+
+    def plan_super_batches(self, shapes, super_rows=None):
+        """Consecutive batches [(B, L), ...] -> index lists, each closed once it holds >= super_rows frame rows."""
+        super_rows = self.SUPER_ROWS if super_rows is None else super_rows
+        out, cur, rows = [], [], 0
+        for i, (B, L) in enumerate(shapes):
+            cur.append(i)
+            rows += self.frame_rows(B, L)
+            if super_rows <= 0 or rows >= super_rows or len(cur) >= self.SUPER_MAX_GROUPS:
+                out.append(cur)
+                cur, rows = [], 0
+        if cur:
+            out.append(cur)
+        return out
+
     @torch.no_grad()
-    def forward_many(self, batches, n_lanes=3, out=None):
+    def forward_many(self, batches, n_lanes=2, out=None, super_rows=None):
         """Throughput API: encode a list of independent padded batches [(src_tokens, src_lengths), ...].
-        Batches are issued round-robin on `n_lanes` CUDA streams, each lane with its own activation arena and
-        CUDA graphs, so the short kernels of one small batch (2e6-sample token budget ~ 6000 frames) overlap the
-        tails / prologues of another's instead of leaving SMs idle.  Results are identical to calling forward()
-        per batch (batches never interact).  Returns a list of EncoderOut; `out` (optional list of preallocated
-        [M,B,512] tensors, e.g. pinned host buffers) receives the memories with non_blocking copies.
-        src_tokens / src_lengths may be (pinned) HOST tensors: they are copied straight into the lane's input buffers
-        on the lane's stream, so one batch's H2D transfer overlaps the other lanes' kernels."""
+        Consecutive batches are packed into SUPER-BATCHES of >= `super_rows` wav2vec2 frame rows: each reference batch
+        keeps its own padded width, GroupNorm extent and frame mask (results are those of calling forward() per batch),
+        but all of them share one row space, so the row-wise GEMM / LayerNorm launches see >= 24k rows instead of the
+        ~6k of one 2e6-sample batch, and one CUDA graph covers the whole super-batch.  Super-batches are issued
+        round-robin on `n_lanes` CUDA streams, each lane with its own activation arena and graphs.
+        Returns a list of EncoderOut; `out` (optional list of preallocated [M,B,512] tensors, e.g. pinned host
+        buffers) receives the memories with non_blocking copies.  src_tokens / src_lengths may be (pinned) HOST
+        tensors: they are copied straight into the lane's input buffers on the lane's stream, so one super-batch's H2D
+        transfer overlaps the other lanes' kernels."""
         lanes = self._get_lanes(n_lanes)
         cur = torch.cuda.current_stream()
         for ln in lanes:
             ln["stream"].wait_stream(cur)
-        results = []
-        self.last_launches = 0
-        for i, (src_tokens, src_lengths) in enumerate(batches):
+        for src_tokens, src_lengths in batches:
             self._check_inputs(src_tokens, src_lengths)
-            ln = lanes[i % n_lanes]
+        results = [None] * len(batches)
+        self.last_launches = 0
+        supers = self.plan_super_batches([tuple(b[0].shape) for b in batches], super_rows)
+        for si, idx in enumerate(supers):
+            ln = lanes[si % n_lanes]
             with torch.cuda.stream(ln["stream"]):
-                B, L = src_tokens.shape
-                plan = self._plan(B, L, ln)
-                plan.load_inputs(src_tokens if src_tokens.dtype == torch.float32 else src_tokens.float(), src_lengths)
+                groups = [tuple(batches[i][0].shape) for i in idx]
+                plan = (self._plan(groups[0][0], groups[0][1], ln) if len(groups) == 1
+                        else self._plan(None, None, ln, groups=groups))
+                for k, i in enumerate(idx):
+                    src_tokens, src_lengths = batches[i]
+                    plan.load_inputs(src_tokens if src_tokens.dtype == torch.float32 else src_tokens.float(), src_lengths, group=k)
                 self.last_launches += plan.run()
-                o = plan.memories().to(self.encoder_out_dtype or src_tokens.dtype).clone(memory_format=torch.contiguous_format)
-                if out is not None:
-                    out[i].copy_(o, non_blocking=True)
-                pad = torch.zeros(B, o.shape[0], dtype=torch.bool, device=o.device)
-                results.append(EncoderOut(o, pad, None, None, None, None))
+                for k, i in enumerate(idx):
+                    src_tokens = batches[i][0]
+                    o = plan.memories(k).to(self.encoder_out_dtype or src_tokens.dtype).clone(memory_format=torch.contiguous_format)
+                    if out is not None:
+                        out[i].copy_(o, non_blocking=True)
+                    pad = torch.zeros(src_tokens.shape[0], o.shape[0], dtype=torch.bool, device=o.device)
+                    results[i] = EncoderOut(o, pad, None, None, None, None)
         for ln in lanes:
             cur.wait_stream(ln["stream"])
         return results

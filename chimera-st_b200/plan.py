@@ -21,6 +21,7 @@ from . import _lib as L
 from .lengths import conv_out_lengths
 from .synth import W2V_DIM, W2V_FFN, W2V_HEADS, ENC_DIM, ENC_FFN, ENC_HEADS, MEM_LAYERS
 
+SEG_WORK = {}      # seg-table device pointer -> sum over utterances of (q rows x kv rows): flop accounting of profilers
 SLACK = 8          # zero rows appended to activation buffers read by overlapping conv windows
 
 
@@ -65,13 +66,24 @@ class Arena:
 
 
 class EncoderPlan:
+    """Launch sequence + buffers for ONE reference batch (B, Lw) or for a SUPER-BATCH: several reference batches
+    `groups = [(B_k, L_k), ...]` that keep their own padded width, GroupNorm extent and frame mask (outputs depend on
+    batch composition) but share one row space, so that every row-wise launch (conv / projection / FFN
+    GEMMs, LayerNorms) runs once over all groups' rows (M >= 24k rows instead of ~6k under the reference's 2e6-sample
+    token budget).  Attention runs once per layer over a per-utterance segment table (cst_attention_segs); the few
+    segment-aware launches (lengths, conv0, masked projection, pos-conv, subsampler) are issued per group with pointer
+    offsets.  Results are those of running each group alone (tests/test_gpu_encoder.py::test_super_batch_*)."""
+
     def __init__(self, params, B, Lw, M, act_dtype=torch.float32, device=None, use_graph=False, lib=None,
-                 arena=None, conv_dtype=None):
+                 arena=None, conv_dtype=None, groups=None):
         # `lib` is injectable so tests can drive the plan against a host emulator of the C ABI
         # (tests/emu.py); the product never passes it and always loads the CUDA library.
         self.lib = lib if lib is not None else L.load()
         self.P = params
-        self.g = g = Geometry(B, Lw, M)
+        self.groups = [(int(b), int(l)) for b, l in groups] if groups is not None else [(int(B), int(Lw))]
+        self.gs = gs = [Geometry(b, l, M) for b, l in self.groups]
+        self.g = gs[0]                                  # single-batch plans: the geometry (kept for callers / tests)
+        self.M = M
         self.dev = device or torch.device("cuda", torch.cuda.current_device())
         self.act = act_dtype
         self.act_code = L.DT[act_dtype]
@@ -84,21 +96,38 @@ class EncoderPlan:
         self.use_stacked_posconv = os.environ.get("CST_POSCONV_STACKED", "1") != "0"
         self.arena = arena if arena is not None else Arena(self.dev)
         f32, i32, i64, u8, f64 = torch.float32, torch.int32, torch.int64, torch.uint8, torch.float64
-        R, R2, RM = B * g.T6a, B * g.T2a, B * M
+
+        def offsets(per_group):
+            o, acc = [], 0
+            for n in per_group:
+                o.append(acc)
+                acc += n
+            return o, acc
+        self.utt0, self.Bt = offsets([g.B for g in gs])                                    # first utterance of a group
+        self.crow0, self.crows = zip(*[offsets([g.B * g.Ta[i] for g in gs]) for i in range(7)])   # conv level i rows
+        self.r0, R = offsets([g.B * g.T6a for g in gs])                                    # wav2vec2 frame rows
+        self.xg0, XG = offsets([g.B * 16 * g.Tpp for g in gs])
+        self.s1_0, S1 = offsets([g.B * g.Tin1 for g in gs])                                # subsampler operands
+        self.s2_0, S2 = offsets([g.B * g.Tin2 for g in gs])
+        self.r2_0, R2 = offsets([g.B * g.T2a for g in gs])                                 # shared-encoder rows
+        self.w0, W = offsets([g.B * g.L for g in gs])
+        self.fm0, FM = offsets([g.B * g.Tp for g in gs])
+        self.R, self.R2 = R, R2
+        Bt, RM = self.Bt, self.Bt * M
         spec = [
             # ---- inputs / integer side
-            ("wave", B, Lw, f32), ("src_len", 1, B, i64), ("w2v_valid", 1, B, i32), ("sub_valid", 1, B, i32),
-            ("w2v_len64", 1, B, i64), ("frame_mask", B, g.Tp, u8),
+            ("wave_flat", 1, W, f32), ("src_len", 1, Bt, i64), ("w2v_valid", 1, Bt, i32), ("sub_valid", 1, Bt, i32),
+            ("w2v_len64", 1, Bt, i64), ("frame_mask_flat", 1, FM, u8),
             # ---- conv stack (ping-pong; level i lives in cbuf{i & 1}); SLACK rows absorb the last windows
-            ("scale_shift", B * 512, 2, f32), ("stats_ws", 1, B * 72, f64),
-            ("cbuf0", B * g.Ta[0] + SLACK, 512, self.conv_dt), ("cbuf1", B * g.Ta[1] + SLACK, 512, self.conv_dt),
+            ("scale_shift", Bt * 512, 2, f32), ("stats_ws", 1, Bt * 72, f64),
+            ("cbuf0", self.crows[0] + SLACK, 512, self.conv_dt), ("cbuf1", self.crows[1] + SLACK, 512, self.conv_dt),
             ("feat", R, 512, f32), ("feat_ln", R, 512, act_dtype),
             # ---- wav2vec2 encoder: fp32 residual stream x, pre-LN sums y, GEMM-operand copy xa
             ("x", R, W2V_DIM, f32), ("y", R, W2V_DIM, f32), ("xa", R, W2V_DIM, act_dtype),
-            ("xg", B * 16 * g.Tpp + SLACK, 64, act_dtype), ("qkv", R, 3 * W2V_DIM, act_dtype),
+            ("xg", XG + SLACK, 64, act_dtype), ("qkv", R, 3 * W2V_DIM, act_dtype),
             ("ctx", R, W2V_DIM, act_dtype), ("ffn", R, W2V_FFN, act_dtype), ("w2v_out", R, W2V_DIM, f32),
             # ---- subsampler operands (zero-padded: re-zeroed every run)
-            ("sub_in", B * g.Tin1 + SLACK, W2V_DIM, act_dtype), ("sub_mid", B * g.Tin2 + SLACK, ENC_DIM, act_dtype),
+            ("sub_in", S1 + SLACK, W2V_DIM, act_dtype), ("sub_mid", S2 + SLACK, ENC_DIM, act_dtype),
             # ---- shared encoder
             ("x2", R2, ENC_DIM, f32), ("x2a", R2, ENC_DIM, act_dtype), ("qkv2", R2, 3 * ENC_DIM, act_dtype),
             ("ctx2", R2, ENC_DIM, act_dtype), ("ffn2", R2, ENC_FFN, act_dtype), ("h_enc", R2, ENC_DIM, f32),
@@ -116,9 +145,27 @@ class EncoderPlan:
         self.arena_generation = self.arena.ensure(off)
         for name, o, nbytes, rows, cols, dt in table:
             t = self.arena.buf[o:o + nbytes].view(dt)
-            setattr(self, name, t.view(rows, cols) if rows > 1 or name in ("wave", "frame_mask") else t.view(cols))
+            setattr(self, name, t.view(rows, cols) if rows > 1 else t.view(cols))
         self.cbuf = [self.cbuf0, self.cbuf1]
+        self.waves = [self.wave_flat[o:o + g.B * g.L].view(g.B, g.L) for o, g in zip(self.w0, gs)]
+        self.frame_masks = [self.frame_mask_flat[o:o + g.B * g.Tp].view(g.B, g.Tp) for o, g in zip(self.fm0, gs)]
+        self.wave, self.frame_mask = self.waves[0], self.frame_masks[0]
         self.arena.buf[:off].zero_()
+        # per-utterance attention segments {first q row, q rows, first kv row, kv rows}: static plan data, kept OUTSIDE
+        # the arena (other plans overlay it).  Only super-batches need them; a single batch uses the uniform entry point.
+        self.seg_w2v = self.seg_enc = self.seg_mem = None
+        if len(gs) > 1:
+            tw, te, tm = [], [], []
+            for k, g in enumerate(gs):
+                for b in range(g.B):
+                    rw, re = self.r0[k] + b * g.T6a, self.r2_0[k] + b * g.T2a
+                    tw.append([rw, g.T6a, rw, g.Tp])
+                    te.append([re, g.T2a, re, g.T2])
+                    tm.append([(self.utt0[k] + b) * M, M, re, g.T2])
+            mk = lambda t: torch.tensor(t, dtype=i32).to(self.dev)        # noqa: E731
+            self.seg_w2v, self.seg_enc, self.seg_mem = mk(tw), mk(te), mk(tm)
+            for t, host in ((self.seg_w2v, tw), (self.seg_enc, te), (self.seg_mem, tm)):
+                SEG_WORK[t.data_ptr()] = sum(r[1] * r[3] for r in host)
 
     # ------------------------------------------------------------------ launch helpers
     def _gemm(self, A, W, C_, M, N, K, lda, a_rows, bias=None, residual=None, act=L.ACT_NONE, alpha=1.0,
@@ -165,61 +212,80 @@ class EncoderPlan:
             out_rows_per_seg if out_rows_per_seg is not None else rps, out_row_off, zero_invalid, self.st))
         self.launches += 1
 
-    def _attn(self, q, k, v, out, ldq, ldkv, H, n_q, q_rps, n_kv, kv_rps, kv_len):
-        L.check(self.lib.cst_attention(q, k, v, out.data_ptr(), L.DT[out.dtype], ldq, ldkv, out.shape[1],
-                                       self.g.B, H, n_q, q_rps, n_kv, kv_rps, L.ptr(kv_len), self.st))
+    def _attn(self, q, k, v, out, ldq, ldkv, H, n_q, q_rps, n_kv, kv_rps, kv_len, seg=None, totals=None):
+        """Uniform segments (single batch), or `seg` = per-utterance table with n_q / n_kv the maxima over it and
+        `totals` = (q rows, kv rows) of the buffers."""
+        if seg is None:
+            L.check(self.lib.cst_attention(q, k, v, out.data_ptr(), L.DT[out.dtype], ldq, ldkv, out.shape[1],
+                                           self.Bt, H, n_q, q_rps, n_kv, kv_rps, L.ptr(kv_len), self.st))
+        else:
+            L.check(self.lib.cst_attention_segs(q, k, v, out.data_ptr(), L.DT[out.dtype], ldq, ldkv, out.shape[1],
+                                                self.Bt, H, seg.data_ptr(), n_q, n_kv, totals[0], totals[1],
+                                                L.ptr(kv_len), self.st))
         self.launches += 1
 
     # ------------------------------------------------------------------ stages
     def _stage_frontend(self):
-        g, P, lib = self.g, self.P, self.lib
-        B = g.B
-        L.check(lib.cst_frame_lengths(self.src_len.data_ptr(), B, g.L, g.Tp, self.w2v_valid.data_ptr(),
-                                      self.sub_valid.data_ptr(), self.w2v_len64.data_ptr(),
-                                      self.frame_mask.data_ptr(), self.st))
-        L.check(lib.cst_conv0_stats(self.wave.data_ptr(), B, g.L, P["conv0_w"].data_ptr(), P["gn_g"].data_ptr(),
-                                    P["gn_b"].data_ptr(), self.scale_shift.data_ptr(), self.stats_ws.data_ptr(), self.st))
-        if self.conv_dt != torch.float32 and self.use_conv0_tc:
-            L.check(lib.cst_conv0_apply_tc(self.wave.data_ptr(), B, g.L, P["conv0_w16"].data_ptr(), self.scale_shift.data_ptr(),
-                                           self.cbuf[0].data_ptr(), L.DT[self.conv_dt], g.Ta[0], self.st))
-        else:
-            L.check(lib.cst_conv0_apply(self.wave.data_ptr(), B, g.L, P["conv0_w"].data_ptr(), self.scale_shift.data_ptr(),
-                                        self.cbuf[0].data_ptr(), L.DT[self.conv_dt], g.Ta[0], self.st))
-        self.launches += 4
+        P, lib = self.P, self.lib
+        tc0 = self.conv_dt != torch.float32 and self.use_conv0_tc
+        for k, g in enumerate(self.gs):
+            u0, B = self.utt0[k], g.B
+            wave = self.waves[k]
+            ss = self.scale_shift[u0 * 512:]
+            L.check(lib.cst_frame_lengths(self.src_len[u0:].data_ptr(), B, g.L, g.Tp, self.w2v_valid[u0:].data_ptr(),
+                                          self.sub_valid[u0:].data_ptr(), self.w2v_len64[u0:].data_ptr(),
+                                          self.frame_masks[k].data_ptr(), self.st))
+            L.check(lib.cst_conv0_stats(wave.data_ptr(), B, g.L, P["conv0_w"].data_ptr(), P["gn_g"].data_ptr(),
+                                        P["gn_b"].data_ptr(), ss.data_ptr(), self.stats_ws[u0 * 72:].data_ptr(), self.st))
+            out0 = self.cbuf[0][self.crow0[0][k]:]
+            if tc0:
+                L.check(lib.cst_conv0_apply_tc(wave.data_ptr(), B, g.L, P["conv0_w16"].data_ptr(), ss.data_ptr(),
+                                               out0.data_ptr(), L.DT[self.conv_dt], g.Ta[0], self.st))
+            else:
+                L.check(lib.cst_conv0_apply(wave.data_ptr(), B, g.L, P["conv0_w"].data_ptr(), ss.data_ptr(),
+                                            out0.data_ptr(), L.DT[self.conv_dt], g.Ta[0], self.st))
+            self.launches += 4
         for i in range(1, 7):
             src = self.cbuf[(i - 1) & 1]
             dst = self.feat if i == 6 else self.cbuf[i & 1]
             w = P[f"conv{i}_w"]
-            rows = B * g.Ta[i]
-            # stride-2 conv over channels-last rows: window of output row m = K contiguous elements at 1024*m
-            self._gemm(src, w, dst, rows, 512, w.shape[1], lda=1024, a_rows=(B * g.Ta[i - 1] + SLACK) // 2,
-                       act=L.ACT_GELU, rows_per_seg=g.Ta[i], ldc=512)
-        R = B * g.T6a
+            # stride-2 conv over channels-last rows: window of output row m = K contiguous elements at 1024*m of the
+            # FLATTENED previous level (every group's rows halve exactly, so group boundaries stay aligned)
+            self._gemm(src, w, dst, self.crows[i], 512, w.shape[1], lda=1024, a_rows=(self.crows[i - 1] + SLACK) // 2,
+                       act=L.ACT_GELU, ldc=512)
+        R = self.R
         self._ln(self.feat, (P["ln_feat_g"], P["ln_feat_b"]), R, out_lp=self.feat_ln)
-        # post_extract_proj + x[padding_mask] = 0 (rows t >= valid_b, incl. the allocation tail t >= T')
-        self._gemm(self.feat_ln, P["proj_w"], self.x, R, W2V_DIM, 512, lda=512, a_rows=R, bias=P["proj_b"],
-                   rows_per_seg=g.T6a, seg_len=self.w2v_valid)
-        L.check(lib.cst_posconv_pack(self.x.data_ptr(), B, g.T6a, g.Tp, self.xg.data_ptr(), self.act_code, g.Tpp, self.st))
-        self.launches += 1
-        # grouped pos-conv: z = (utterance, group); window of frame t = rows t..t+127 of the packed operand
-        if self.act == torch.bfloat16 and self.use_resident_posconv and self.use_stacked_posconv:
-            L.check(lib.cst_posconv_stacked(self.xg.data_ptr(), P["pos_w2"].data_ptr(), P["pos_b"].data_ptr(), self.x.data_ptr(),
-                                            self.y.data_ptr(), B, g.T6a, g.T6a, g.Tpp, self.st))
+        stacked = self.act == torch.bfloat16 and self.use_resident_posconv and self.use_stacked_posconv
+        resident = self.act == torch.bfloat16 and self.use_resident_posconv
+        for k, g in enumerate(self.gs):
+            r0, rows, B = self.r0[k], g.B * g.T6a, g.B
+            x, y, xg = self.x[r0:r0 + rows], self.y[r0:r0 + rows], self.xg[self.xg0[k]:]
+            # post_extract_proj + x[padding_mask] = 0 (rows t >= valid_b, incl. the allocation tail t >= T')
+            self._gemm(self.feat_ln[r0:r0 + rows], P["proj_w"], x, rows, W2V_DIM, 512, lda=512, a_rows=rows, bias=P["proj_b"],
+                       rows_per_seg=g.T6a, seg_len=self.w2v_valid[self.utt0[k]:])
+            L.check(lib.cst_posconv_pack(x.data_ptr(), B, g.T6a, g.Tp, xg.data_ptr(), self.act_code, g.Tpp, self.st))
             self.launches += 1
-        elif self.act == torch.bfloat16 and self.use_resident_posconv:
-            L.check(lib.cst_posconv(self.xg.data_ptr(), P["pos_w"].data_ptr(), P["pos_b"].data_ptr(), self.x.data_ptr(),
-                                    self.y.data_ptr(), B, g.T6a, g.T6a, g.Tpp, self.st))
-            self.launches += 1
-        else:
-            self._gemm(self.xg, P["pos_w"], self.y, g.T6a, 48, 128 * 64, lda=64, a_rows=g.Tpp, bias=P["pos_b"],
-                       residual=self.x, act=L.ACT_GELU, ldc=W2V_DIM, nb_outer=B, nb_inner=16,
-                       a_bs=(16 * g.Tpp * 64, g.Tpp * 64), w_bs=48 * 128 * 64, c_bs=(g.T6a * W2V_DIM, 48), bias_bs=48)
+            # grouped pos-conv: z = (utterance, group); window of frame t = rows t..t+127 of the packed operand
+            if stacked:
+                L.check(lib.cst_posconv_stacked(xg.data_ptr(), P["pos_w2"].data_ptr(), P["pos_b"].data_ptr(), x.data_ptr(),
+                                                y.data_ptr(), B, g.T6a, g.T6a, g.Tpp, self.st))
+                self.launches += 1
+            elif resident:
+                L.check(lib.cst_posconv(xg.data_ptr(), P["pos_w"].data_ptr(), P["pos_b"].data_ptr(), x.data_ptr(),
+                                        y.data_ptr(), B, g.T6a, g.T6a, g.Tpp, self.st))
+                self.launches += 1
+            else:
+                self._gemm(xg, P["pos_w"], y, g.T6a, 48, 128 * 64, lda=64, a_rows=g.Tpp, bias=P["pos_b"],
+                           residual=x, act=L.ACT_GELU, ldc=W2V_DIM, nb_outer=B, nb_inner=16,
+                           a_bs=(16 * g.Tpp * 64, g.Tpp * 64), w_bs=48 * 128 * 64, c_bs=(g.T6a * W2V_DIM, 48), bias_bs=48)
         self._ln(self.y, (P["ln_enc_g"], P["ln_enc_b"]), R, out_f32=self.x, out_lp=self.xa)
 
     def _stage_w2v_layers(self):
-        g, P = self.g, self.P
-        R = g.B * g.T6a
+        P = self.P
+        R = self.R
         D = W2V_DIM
+        g0 = self.gs[0]
+        max_q, max_kv = max(g.T6a for g in self.gs), max(g.Tp for g in self.gs)
         # zero-padded subsampler operands share the arena with other shapes: clear them every run
         self.sub_in.zero_()
         self.sub_mid.zero_()
@@ -230,8 +296,12 @@ class EncoderPlan:
             qp = self.qkv.data_ptr()
             # all allocated query rows are computed (rows >= T' are finite filler, never read as keys):
             # no buffer row is ever left stale, so masked keys always meet finite V rows
-            self._attn(qp, qp + D * es, qp + 2 * D * es, self.ctx, 3 * D, 3 * D, W2V_HEADS,
-                       g.T6a, g.T6a, g.Tp, g.T6a, self.w2v_valid)
+            if self.seg_w2v is None:
+                self._attn(qp, qp + D * es, qp + 2 * D * es, self.ctx, 3 * D, 3 * D, W2V_HEADS,
+                           g0.T6a, g0.T6a, g0.Tp, g0.T6a, self.w2v_valid)
+            else:
+                self._attn(qp, qp + D * es, qp + 2 * D * es, self.ctx, 3 * D, 3 * D, W2V_HEADS,
+                           max_q, None, max_kv, None, self.w2v_valid, seg=self.seg_w2v, totals=(R, R))
             self._linear(self.ctx, lw["o_w"], lw["o_b"], self.y, R, residual=self.x)
             self._ln(self.y, (lw["ln1_g"], lw["ln1_b"]), R, out_f32=self.x, out_lp=self.xa)
             self._linear(self.xa, lw["fc1_w"], lw["fc1_b"], self.ffn, R, act=L.ACT_GELU)
@@ -242,32 +312,48 @@ class EncoderPlan:
                 # last layer: the LN output is (a) the wav2vec2 feature [B,T',768] and (b) the subsampler's
                 # zero-padded operand (2 leading zero frames, zeros from frame T' on)
                 self._ln(self.y, (lw["ln2_g"], lw["ln2_b"]), R, out_f32=self.w2v_out)
-                self._ln(self.y, (lw["ln2_g"], lw["ln2_b"]), R, out_lp=self.sub_in, rows_per_seg=g.T6a,
-                         seg_rows_valid=g.Tp, out_rows_per_seg=g.Tin1, out_row_off=2, zero_invalid=0)
+                for k, g in enumerate(self.gs):
+                    r0, rows = self.r0[k], g.B * g.T6a
+                    self._ln(self.y[r0:r0 + rows], (lw["ln2_g"], lw["ln2_b"]), rows, out_lp=self.sub_in[self.s1_0[k]:],
+                             rows_per_seg=g.T6a, seg_rows_valid=g.Tp, out_rows_per_seg=g.Tin1, out_row_off=2, zero_invalid=0)
 
     def _stage_subsample(self):
-        g, P = self.g, self.P
-        B = g.B
+        P = self.P
         w0, w1 = P["sub0_w"], P["sub1_w"]
         # Conv1d(k5,s2,p2)+GLU twice; operands are zero-padded so the window of frame t1 starts at padded row 2*t1
-        self._gemm(self.sub_in, w0, self.sub_mid, B * g.T1a, w0.shape[0], w0.shape[1], lda=2 * W2V_DIM,
-                   a_rows=(B * g.Tin1 + SLACK) // 2, bias=P["sub0_b"], act=L.ACT_GLU, rows_per_seg=g.T1a,
-                   seg_rows_valid=g.T1, out_rows_per_seg=g.Tin2, out_row_off=2, ldc=ENC_DIM)
-        self._gemm(self.sub_mid, w1, self.x2, B * g.T2a, w1.shape[0], w1.shape[1], lda=2 * ENC_DIM,
-                   a_rows=(B * g.Tin2 + SLACK) // 2, bias=P["sub1_b"], act=L.ACT_GLU, alpha=math.sqrt(ENC_DIM),
-                   rows_per_seg=g.T2a, out_rows_per_seg=g.T2a, ldc=ENC_DIM)
+        for k, g in enumerate(self.gs):
+            B = g.B
+            a0 = self.sub_in[self.s1_0[k]:]
+            mid = self.sub_mid[self.s2_0[k]:]
+            last = k + 1 == len(self.gs)
+            self._gemm(a0, w0, mid, B * g.T1a, w0.shape[0], w0.shape[1], lda=2 * W2V_DIM,
+                       a_rows=(B * g.Tin1 + (SLACK if last else 0)) // 2, bias=P["sub0_b"], act=L.ACT_GLU, rows_per_seg=g.T1a,
+                       seg_rows_valid=g.T1, out_rows_per_seg=g.Tin2, out_row_off=2, ldc=ENC_DIM)
+        for k, g in enumerate(self.gs):
+            B = g.B
+            mid = self.sub_mid[self.s2_0[k]:]
+            last = k + 1 == len(self.gs)
+            self._gemm(mid, w1, self.x2[self.r2_0[k]:], B * g.T2a, w1.shape[0], w1.shape[1], lda=2 * ENC_DIM,
+                       a_rows=(B * g.Tin2 + (SLACK if last else 0)) // 2, bias=P["sub1_b"], act=L.ACT_GLU, alpha=math.sqrt(ENC_DIM),
+                       rows_per_seg=g.T2a, out_rows_per_seg=g.T2a, ldc=ENC_DIM)
 
     def _stage_shared_layers(self):
-        g, P = self.g, self.P
-        R2 = g.B * g.T2a
+        P = self.P
+        R2 = self.R2
         D = ENC_DIM
+        g0 = self.gs[0]
+        max_q, max_kv = max(g.T2a for g in self.gs), max(g.T2 for g in self.gs)
         es = self.qkv2.element_size()
         for lw in P["enc_layers"]:
             self._ln(self.x2, (lw["ln1_g"], lw["ln1_b"]), R2, out_lp=self.x2a)
             self._linear(self.x2a, lw["qkv_w"], lw["qkv_b"], self.qkv2, R2)
             qp = self.qkv2.data_ptr()
-            self._attn(qp, qp + D * es, qp + 2 * D * es, self.ctx2, 3 * D, 3 * D, ENC_HEADS,
-                       g.T2a, g.T2a, g.T2, g.T2a, self.sub_valid)
+            if self.seg_enc is None:
+                self._attn(qp, qp + D * es, qp + 2 * D * es, self.ctx2, 3 * D, 3 * D, ENC_HEADS,
+                           g0.T2a, g0.T2a, g0.T2, g0.T2a, self.sub_valid)
+            else:
+                self._attn(qp, qp + D * es, qp + 2 * D * es, self.ctx2, 3 * D, 3 * D, ENC_HEADS,
+                           max_q, None, max_kv, None, self.sub_valid, seg=self.seg_enc, totals=(R2, R2))
             self._linear(self.ctx2, lw["o_w"], lw["o_b"], self.x2, R2, residual=self.x2)
             self._ln(self.x2, (lw["ln2_g"], lw["ln2_b"]), R2, out_lp=self.x2a)
             self._linear(self.x2a, lw["fc1_w"], lw["fc1_b"], self.ffn2, R2, act=L.ACT_RELU)
@@ -275,9 +361,10 @@ class EncoderPlan:
         self._ln(self.x2, (P["ln_out_g"], P["ln_out_b"]), R2, out_f32=self.h_enc)
 
     def _stage_memory(self):
-        g, P = self.g, self.P
-        B, M = g.B, g.M
-        R2, RM, D = B * g.T2a, B * M, ENC_DIM
+        P = self.P
+        B, M = self.Bt, self.M
+        R2, RM, D = self.R2, B * M, ENC_DIM
+        g0 = self.gs[0]
         es = self.kv.element_size()
         L.check(self.lib.cst_broadcast_rows(P["mem_embed"].data_ptr(), M, D, B, self.mem.data_ptr(), self.st))
         self.launches += 1
@@ -292,7 +379,11 @@ class EncoderPlan:
             self._linear(self.mem_a, lw["q_w"], lw["q_b"], self.mq, RM)
             kp = self.kv.data_ptr() + i * 2 * D * es
             # memories attend ALL T2 frames: the reference passes an all-False key-padding mask here
-            self._attn(self.mq.data_ptr(), kp, kp + D * es, self.mctx, D, 2 * D * nl, ENC_HEADS, M, M, g.T2, g.T2a, None)
+            if self.seg_mem is None:
+                self._attn(self.mq.data_ptr(), kp, kp + D * es, self.mctx, D, 2 * D * nl, ENC_HEADS, M, M, g0.T2, g0.T2a, None)
+            else:
+                self._attn(self.mq.data_ptr(), kp, kp + D * es, self.mctx, D, 2 * D * nl, ENC_HEADS, M, None,
+                           max(g.T2 for g in self.gs), None, None, seg=self.seg_mem, totals=(RM, R2))
             self._linear(self.mctx, lw["o_w"], lw["o_b"], self.mem, RM, residual=self.mem)
             self._ln(self.mem, (lw["ln2_g"], lw["ln2_b"]), RM, out_lp=self.mem_a)
             self._linear(self.mem_a, lw["fc1_w"], lw["fc1_b"], self.mffn, RM, act=L.ACT_RELU)
@@ -312,11 +403,13 @@ class EncoderPlan:
         self._stage_memory()
 
     # ------------------------------------------------------------------ public
-    def load_inputs(self, wave, src_lengths):
-        """Copy one padded batch into the plan's static input buffers (async on the current stream)."""
-        assert tuple(wave.shape) == (self.g.B, self.g.L), (tuple(wave.shape), (self.g.B, self.g.L))
-        self.wave.copy_(wave, non_blocking=True)
-        self.src_len.copy_(src_lengths, non_blocking=True)
+    def load_inputs(self, wave, src_lengths, group=0):
+        """Copy one padded batch into the plan's static input buffers (async on the current stream); `group` selects the
+        reference batch of a super-batch."""
+        g = self.gs[group]
+        assert tuple(wave.shape) == (g.B, g.L), (tuple(wave.shape), (g.B, g.L))
+        self.waves[group].copy_(wave, non_blocking=True)
+        self.src_len[self.utt0[group]:self.utt0[group] + g.B].copy_(src_lengths, non_blocking=True)
 
     def run(self, upto="memory", eager=False):
         """Launch the forward pass for the loaded inputs; returns the number of kernel launches issued."""
@@ -336,22 +429,25 @@ class EncoderPlan:
         return self.launches
 
     # views of the results (valid until the next run)
-    def memories(self):
-        """[M, B, 512] fp32, the reference's `encoder_out` layout (time-major)."""
-        return self.mem.view(self.g.B, self.g.M, ENC_DIM).transpose(0, 1)
+    def memories(self, group=0):
+        """[M, B, 512] fp32, the reference's `encoder_out` layout (time-major), of one reference batch."""
+        g, u0 = self.gs[group], self.utt0[group]
+        return self.mem.view(self.Bt, self.M, ENC_DIM)[u0:u0 + g.B].transpose(0, 1)
 
-    def view(self, name):
-        g = self.g
+    def view(self, name, group=0):
+        g, k = self.gs[group], group
         if name == "conv_feats":     # [B, 512, T'] like ConvFeatureExtractionModel's output
-            return self.feat.view(g.B, g.T6a, 512)[:, :g.Tp].transpose(1, 2)
+            return self.feat[self.r0[k]:self.r0[k] + g.B * g.T6a].view(g.B, g.T6a, 512)[:, :g.Tp].transpose(1, 2)
         if name == "w2v_in":
             return None
         if name == "w2v_out":
-            return self.w2v_out.view(g.B, g.T6a, W2V_DIM)[:, :g.Tp]
+            return self.w2v_out[self.r0[k]:self.r0[k] + g.B * g.T6a].view(g.B, g.T6a, W2V_DIM)[:, :g.Tp]
         if name == "h_enc":
-            return self.h_enc.view(g.B, g.T2a, ENC_DIM)[:, :g.T2]
+            return self.h_enc[self.r2_0[k]:self.r2_0[k] + g.B * g.T2a].view(g.B, g.T2a, ENC_DIM)[:, :g.T2]
         if name == "frame_mask":
-            return self.frame_mask.bool()
+            return self.frame_masks[k].bool()
+        if name == "w2v_len64":
+            return self.w2v_len64[self.utt0[k]:self.utt0[k] + g.B]
         raise KeyError(name)
 
 
@@ -387,6 +483,9 @@ class TextPlan(EncoderPlan):
         self.lib = lib if lib is not None else L.load()
         self.P = params
         self.g = g = TextGeometry(B, T, M)
+        self.gs, self.groups, self.Bt, self.M = [g], [(B, T)], B, M
+        self.utt0, self.r2_0, self.R2 = [0], [0], B * g.T2a
+        self.seg_w2v = self.seg_enc = self.seg_mem = None
         self.dev = device or torch.device("cuda", torch.cuda.current_device())
         self.act = act_dtype
         self.act_code = L.DT[act_dtype]
@@ -435,7 +534,7 @@ class TextPlan(EncoderPlan):
         self._stage_shared_layers()
         self._stage_memory()
 
-    def view(self, name):
+    def view(self, name, group=0):
         if name == "h_enc":
             return self.h_enc.view(self.g.B, self.g.T2a, ENC_DIM)[:, :self.g.T2]
         raise KeyError(name)

@@ -144,6 +144,16 @@ int cst_attention(const void* q, const void* k, const void* v, void* out, int dt
                   int B, int H, int n_q, int q_rows_per_seg, int n_kv, int kv_rows_per_seg,
                   const int32_t* kv_len, void* stream);
 
+/* The same attention over a RAGGED set of utterances (several reference batches of different padded widths sharing one
+ * row space, so that the row-wise GEMM / LayerNorm launches around it see M >= 24k rows -- DESIGN.md §3a).
+ * seg: int32 [B][4] (device, 16-byte aligned) = {first q row, q rows, first kv row, kv rows} of utterance b;
+ * max_n_q / max_n_kv = maxima over the table (grid / shared-memory sizing); q_rows_total / kv_rows_total = rows of the
+ * q / kv buffers (tensor-map extents).  Everything else as cst_attention (same reference lines). */
+int cst_attention_segs(const void* q, const void* k, const void* v, void* out, int dtype,
+                       long long ldq, long long ldkv, long long ldo, int B, int H,
+                       const int32_t* seg, int max_n_q, int max_n_kv, long long q_rows_total, long long kv_rows_total,
+                       const int32_t* kv_len, void* stream);
+
 /* ---- text (MT) input of the shared encoder ------------------------------------------------------
  * Replaces: the text branch of S2T_W2V2_TransformerInterlinguaEncoder.forward (fairseq/models/chimera/
  * w2v2_transformer_interlingua.py:212-217,230-236): x = scale * text_embed_tokens(tokens) + embed_positions(padding mask).

@@ -179,6 +179,26 @@ class EmuLib:
         self.calls.append("attention")
         return 0
 
+    def cst_attention_segs(self, q, k, v, out, dtype, ldq, ldkv, ldo, B, H, seg, max_n_q, max_n_kv, q_total, kv_total, kv_len,
+                           stream):
+        assert dtype == F32
+        tbl = _mem(seg, 4 * B, np.int32).reshape(B, 4)
+        kl = _mem(kv_len, B, np.int32) if kv_len else None
+        for b in range(B):
+            q0, nq, k0, nk = (int(t) for t in tbl[b])
+            assert nq <= max_n_q and nk <= max_n_kv and q0 + nq <= q_total and k0 + nk <= kv_total
+            Q = torch.from_numpy(_mem(q + 4 * q0 * ldq, nq * ldq).copy()).as_strided((nq, H, 64), (ldq, 64, 1))
+            K = torch.from_numpy(_mem(k + 4 * k0 * ldkv, nk * ldkv).copy()).as_strided((nk, H, 64), (ldkv, 64, 1))
+            V = torch.from_numpy(_mem(v + 4 * k0 * ldkv, nk * ldkv).copy()).as_strided((nk, H, 64), (ldkv, 64, 1))
+            s_ = torch.einsum("qhd,khd->hqk", Q.double(), K.double())
+            if kl is not None:
+                s_ = s_.masked_fill(torch.arange(nk)[None, None, :] >= int(kl[b]), float("-inf"))
+            o = torch.einsum("hqk,khd->qhd", torch.softmax(s_, -1), V.double()).float()
+            Ov = torch.from_numpy(_mem(out + 4 * q0 * ldo, nq * ldo)).as_strided((nq, H, 64), (ldo, 64, 1))
+            Ov[:] = o
+        self.calls.append("attention_segs")
+        return 0
+
 
 # ---- greedy decoding (cst_dec_*): same pointer-level semantics on host memory, fp32 -----------------------------------
 def _dec_embed(self, tokens, ld_tok, embed, w_dtype, pos_table, scale, x, B, Cd, step, stream):

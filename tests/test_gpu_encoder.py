@@ -149,6 +149,42 @@ def test_forward_many_on_stream_lanes_equals_forward(dtype):
     assert one.encoder_out.is_cuda and torch.equal(one.encoder_out, ref[0])
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_super_batch_small_groups_equal_forward(dtype):
+    """Several reference batches of different padded widths in one row space (one launch sequence / one graph):
+    bit-identical to forward() per batch, with and without lanes, for every grouping size."""
+    enc = encoder(16, dtype, use_graph=True)
+    shapes = [[16000, 12345, 8000], [9000, 7000], [24000], [16000, 3000, 9999], [9000, 8999], [12000, 11000, 10000, 500], [400]]
+    batches = []
+    for i, lens in enumerate(shapes):
+        w, l = synth.make_waveforms(lens, seed=200 + i)
+        batches.append((w.cuda(), l.cuda()))
+    ref = [enc(w, l).encoder_out.clone() for w, l in batches]
+    for rows, lanes in ((1 << 30, 1), (150, 2), (0, 2)):          # one super-batch of 7 groups; several; none
+        got = enc.forward_many(batches, n_lanes=lanes, super_rows=rows)
+        torch.cuda.synchronize()
+        for a, b in zip(ref, got):
+            assert torch.equal(a, b.encoder_out), (rows, lanes, rel_l2(b.encoder_out, a))
+
+
+def test_super_batch_c3_shapes_equal_forward_bf16():
+    """Real c3 shapes (2e6-sample token budget): four reference batches -> one super-batch of ~25k frame rows, where the
+    GEMMs switch to the CTA-pair kernel (M >= 16384).  Memories must be those of forward() per batch."""
+    enc = encoder(16, torch.bfloat16, use_graph=True)
+    shapes = [[262960 - 777 * i for i in range(7)], [255000 - 500 * i for i in range(7)], [250000 - 300 * i for i in range(8)],
+              [247000 - 311 * i for i in range(8)]]
+    batches = []
+    for i, lens in enumerate(shapes):
+        w, l = synth.make_waveforms(lens, seed=300 + i)
+        batches.append((w.cuda(), l.cuda()))
+    ref = [enc(w, l).encoder_out.clone() for w, l in batches]
+    got = enc.forward_many(batches, n_lanes=1)
+    torch.cuda.synchronize()
+    assert len(enc.plan_super_batches([tuple(w.shape) for w, _ in batches])) == 1
+    for a, b in zip(ref, got):
+        assert torch.equal(a, b.encoder_out), rel_l2(b.encoder_out, a)
+
+
 def test_single_utterance_output_does_not_alias_the_arena():
     """B == 1: [1,M,512].transpose(0,1) is 'contiguous' to torch, so the result must be cloned explicitly."""
     enc = encoder(16, torch.float32, use_graph=True)
@@ -198,6 +234,42 @@ def test_full_size_batches_row_independence_and_oracle_rows(B, secs, M):
     with torch.no_grad():
         ref, _ = O.encoder_forward(sd, w0, l0)
     assert rel_l2(out[:, 0:1].cpu(), ref) < 1e-2
+
+
+def _cpu_reference(M):
+    """The UNMODIFIED reference encoder when its tree or the shipped bundle (oracle/_ref/src) is there, else the oracle."""
+    from oracle import make_overlay
+    sd = synth.make_state_dict(seed=0, interlingua_length=M)
+    if make_overlay.available():
+        from oracle.ref_model import build_reference_encoder
+        enc, _ = build_reference_encoder(M)
+        enc.load_state_dict(sd, strict=True)
+        return (lambda w, l: enc(w, l).encoder_out), "reference"
+    return (lambda w, l: O.encoder_forward(sd, w, l)[0]), "oracle"
+
+
+@pytest.mark.parametrize("case", ["c3_ragged_30s", "c3_ragged_short", "c2_full"])
+def test_every_row_of_real_batch_shapes_bf16(case):
+    """The benched configurations, EVERY row (incl. partially padded rows at T' = 1499 / 749): a c3 batch of 8 ragged
+    utterances up to L = 480 000, a short-utterance c3 bucket, and the whole C2 batch (32 x 15 s, ragged) -- bf16 memories
+    within 1e-2 rel-L2 per utterance of the fp32 reference on the identical padded batch."""
+    torch.set_num_threads(os.cpu_count() or 8)
+    if case == "c3_ragged_30s":
+        lens = [480000, 479000, 471234, 455000, 430001, 401000, 377777, 350000]
+    elif case == "c3_ragged_short":
+        lens = [60000 - 1111 * i for i in range(24)]
+    else:
+        L = 240000
+        lens = [L] + [int(L * (0.55 + 0.45 * ((7 * i) % 11) / 11.0)) for i in range(1, 32)]
+    wave, tl = synth.make_waveforms(lens, seed=77)
+    ref_fn, kind = _cpu_reference(16)
+    with torch.no_grad():
+        ref = ref_fn(wave, tl).double()                                  # [M, B, 512]
+    enc = encoder(16, torch.bfloat16, use_graph=True)
+    out = enc(wave.cuda(), tl.cuda()).encoder_out.cpu().double()
+    per_row = (out - ref).pow(2).sum((0, 2)).sqrt() / ref.pow(2).sum((0, 2)).sqrt()
+    assert float(per_row.max()) < 1e-2, (kind, per_row.tolist())
+    assert rel_l2(out, ref) < 1e-2
 
 
 @pytest.mark.parametrize("lens", [[400], [401, 400], [719, 500, 400], [960, 1], [3200, 3199, 17], [480000], [33000, 32000, 20000, 9000, 400]])

@@ -53,6 +53,34 @@ def test_plan_is_reusable_with_other_lengths(tiny_plan):
     assert rel_l2(plan.memories(), ref) < 5e-6
 
 
+def test_super_batch_equals_each_batch_alone_on_the_emulator():
+    """Three reference batches of different padded widths in ONE row space (shared row-wise launches, segment-table
+    attention, per-group segment-aware launches): every group's stages, masks, lengths and memories equal the group run
+    alone, and the oracle."""
+    sd = synth.make_state_dict(seed=0, interlingua_length=16)
+    P = weights.prepare(sd, torch.device("cpu"), torch.float32)
+    batches = [[9000, 7000], [5000], [3300, 3000, 400]]
+    data = [synth.make_waveforms(b, seed=21 + i) for i, b in enumerate(batches)]
+    sup = EncoderPlan(P, None, None, 16, torch.float32, torch.device("cpu"), lib=EmuLib(),
+                      groups=[tuple(w.shape) for w, _ in data])
+    for k, (w, l) in enumerate(data):
+        sup.load_inputs(w, l, group=k)
+    sup.run()
+    assert "attention_segs" in sup.lib.calls and "attention" not in sup.lib.calls
+    for k, (w, l) in enumerate(data):
+        one = EncoderPlan(P, w.shape[0], w.shape[1], 16, torch.float32, torch.device("cpu"), lib=EmuLib())
+        one.load_inputs(w, l)
+        one.run()
+        for name in ("conv_feats", "w2v_out", "h_enc"):
+            assert rel_l2(sup.view(name, k), one.view(name)) < 2e-6, (k, name)
+        assert torch.equal(sup.view("frame_mask", k), one.view("frame_mask"))
+        assert torch.equal(sup.view("w2v_len64", k), one.w2v_len64)
+        assert rel_l2(sup.memories(k), one.memories()) < 2e-6
+        with torch.no_grad():
+            ref, _ = O.encoder_forward(sd, w, l)
+        assert rel_l2(sup.memories(k), ref) < 5e-6
+
+
 @pytest.mark.parametrize("L", [400, 401, 719, 720, 16000, 80000, 240000, 480000])
 def test_geometry_invariants(L):
     g = Geometry(3, L, 16)
