@@ -10,43 +10,41 @@ Restates the reference's rule so that a batch -> rank assignment is identical to
   * ordering: longest first (descending length, stable), the order the bench / tests use
     (the collater itself re-sorts each batch by length descending, triplet_dataset.py:174-179).
 """
-import math
-
-
 def ordered_indices(lengths):
     return sorted(range(len(lengths)), key=lambda i: -int(lengths[i]))
 
 
 def batch_by_size(indices, lengths, max_tokens=2000000, max_sentences=0, bsz_mult=8):
-    batches, batch, sample_lens = [], [], []
-    sample_len = 0
-    for idx in indices:
-        n_tok = int(lengths[idx])
-        sample_lens.append(n_tok)
-        sample_len = max(sample_len, n_tok)
-        if max_tokens > 0 and sample_len > max_tokens:
-            raise ValueError("utterance %d of %d samples exceeds max_tokens=%d" % (idx, sample_len, max_tokens))
-        num_tokens = (len(batch) + 1) * sample_len
-        full = len(batch) > 0 and ((max_sentences > 0 and len(batch) == max_sentences)
-                                   or (max_tokens > 0 and num_tokens > max_tokens))
-        if full:
-            mod_len = max(bsz_mult * (len(batch) // bsz_mult), len(batch) % bsz_mult)
-            batches.append(batch[:mod_len])
-            batch = batch[mod_len:]
-            sample_lens = sample_lens[mod_len:]
-            sample_len = max(sample_lens) if sample_lens else 0
-        batch.append(idx)
-    if batch:
-        batches.append(batch)
-    return batches
+    """Token-budget packing with the reference's outcome (fairseq/data/data_utils_fast.pyx:28-69; pinned to the
+    reference's compiled Cython by tests/test_batching.py).  Batches are consecutive slices of the ordered index list, so
+    only cut positions are tracked: the open slice order[lo:pos] is closed when taking utterance `pos` as well would
+    exceed the budget ((count + 1) * widest > max_tokens) or the sentence cap; a closed slice keeps a whole multiple of
+    `bsz_mult` utterances (all of them when it has fewer than one multiple) and the rest stay open for the next batch."""
+    order = [int(i) for i in indices]
+    width = [int(lengths[i]) for i in order]
+    cuts, lo, widest = [], 0, 0
+    for pos, w in enumerate(width):
+        widest = max(widest, w)
+        if 0 < max_tokens < widest:
+            raise ValueError("utterance %d of %d samples exceeds max_tokens=%d" % (order[pos], widest, max_tokens))
+        count = pos - lo
+        if count and ((0 < max_sentences == count) or (max_tokens > 0 and (count + 1) * widest > max_tokens)):
+            keep = count if count < bsz_mult else count - count % bsz_mult
+            cuts.append((lo, lo + keep))
+            lo += keep
+            widest = max(width[lo:pos + 1])
+    if lo < len(order):
+        cuts.append((lo, len(order)))
+    return [order[a:b] for a, b in cuts]
 
 
 def shard_batches(batches, num_shards, shard_id):
+    """Every num_shards-th batch starting at shard_id; all shards report the same number of batches, the short ones
+    padded with empty batches (ShardedIterator, fairseq/data/iterators.py:470-500)."""
     if not 0 <= shard_id < num_shards:
         raise ValueError("shard_id must be between 0 and num_shards")
-    sharded_len = int(math.ceil(len(batches) / float(num_shards)))
-    mine = list(batches[shard_id::num_shards])
-    return mine + [[] for _ in range(sharded_len - len(mine))]
+    per_shard = -(-len(batches) // num_shards)
+    return [list(batches[j]) if j < len(batches) else [] for j in range(shard_id, per_shard * num_shards, num_shards)]
 
 
 # ---- collation (the caller side of the encoder: SURVEY.md §8(f) row 3) ------------------------------------------------
@@ -56,12 +54,16 @@ def collate_waveforms(waves, ids=None, pin=False):
     re-ordered by descending length with torch's own sort (triplet_dataset.py:165-179).
     -> (ids [B] int64 in batch order, src_tokens [B, L] float32, src_lengths [B] int64); `pin` puts src_tokens in
     pinned host memory (the form `encoder.forward_many` copies on its lanes' own streams)."""
+    import numpy as np
     import torch
     if len(waves) == 0:
         raise ValueError("empty batch")
-    waves = [torch.as_tensor(w, dtype=torch.float32).reshape(-1) for w in waves]
+    # int16 inputs (16-bit PCM, `audio_io.read_pcm16`) stay int16: the wire format the encoder de-quantises on the GPU
+    pcm = all(getattr(w, "dtype", None) in (torch.int16, np.dtype("int16")) for w in waves)
+    dt = torch.int16 if pcm else torch.float32
+    waves = [torch.as_tensor(w, dtype=dt).reshape(-1) for w in waves]
     n = torch.tensor([w.numel() for w in waves], dtype=torch.long)
-    out = torch.zeros(len(waves), int(n.max()), dtype=torch.float32)
+    out = torch.zeros(len(waves), int(n.max()), dtype=dt)
     for i, w in enumerate(waves):
         out[i, :w.numel()] = w
     n_sorted, order = n.sort(descending=True)

@@ -282,6 +282,10 @@ int launch_attention_tc(const void* q, const void* k, const void* v, void* out, 
                         int B, int H, int n_q, int q_rows_per_seg, int n_kv, int kv_rows_per_seg,
                         const int32_t* kv_len, const int32_t* seg, cudaStream_t st);
 
+int launch_attention_tc2(const void* q, const void* k, const void* v, void* out, long long ldq, long long ldkv, long long ldo,
+                         int B, int H, int n_q, int q_rows_per_seg, int n_kv, int kv_rows_per_seg,
+                         const int32_t* kv_len, const int32_t* seg, cudaStream_t st);
+
 // seg == nullptr: B uniform segments.  seg != nullptr (int32 [B][4] = {first q row, q rows, first kv row, kv rows}):
 // n_q / n_kv are the maxima over the table and q_rows_per_seg / kv_rows_per_seg the total rows of the q / kv buffers.
 static int attention_dispatch(const void* q, const void* k, const void* v, void* out, int dtype,
@@ -291,8 +295,17 @@ static int attention_dispatch(const void* q, const void* k, const void* v, void*
   const int4* seg4 = reinterpret_cast<const int4*>(seg);
   // bf16 with enough query rows to fill a 128-row MMA tile: tensor-core kernel (attention_tc.cu);
   // fp32 (exact-parity mode) and the M-query memory stage: the CUDA-core kernel above.
-  if (dtype == CST_BF16 && n_q > 64)
+  // CST_ATTN_V2=1 selects the second-generation kernel (attention_tc2.cu: P in tensor memory, persistent CTAs, two query
+  // tiles per CTA).  Measured on B200 (profiles/SUMMARY_r02.md): both kernels are bound by the per-instruction floor of
+  // the small MMAs attention issues at head_dim 64 (tools/micro/mma_attn_rate.cu), and v2 is not ahead yet -> default 0.
+  if (dtype == CST_BF16 && n_q > 64) {
+    static const int v2 = [] { const char* e = getenv("CST_ATTN_V2"); return e ? atoi(e) : 0; }();
+    if (v2) {
+      const int rc = launch_attention_tc2(q, k, v, out, ldq, ldkv, ldo, B, H, n_q, q_rows_per_seg, n_kv, kv_rows_per_seg, kv_len, seg, st);
+      if (rc != CST_ERR_UNSUPPORTED) return rc;
+    }
     return launch_attention_tc(q, k, v, out, ldq, ldkv, ldo, B, H, n_q, q_rows_per_seg, n_kv, kv_rows_per_seg, kv_len, seg, st);
+  }
   // few queries over a whole key axis (the memory stage): dedicated kernel; CST_MEMATTN=0 keeps the generic one
   static const int mem_attn = [] { const char* e = getenv("CST_MEMATTN"); return e ? atoi(e) : 1; }();
   if (mem_attn && n_q <= 64 && n_kv <= MA_MAX_KV && (dtype == CST_BF16 || dtype == CST_F32)) {

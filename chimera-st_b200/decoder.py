@@ -296,8 +296,10 @@ class B200GreedyDecoder:
             raise L.CstError("memories must live on %s (no CPU fallback)" % self.device)
         if memories.dim() != 3 or memories.shape[2] != DIM:
             raise ValueError("memories must be [M, B, %d]" % DIM)
+        if memories.dtype == torch.float16:          # fairseq --fp16 models hand over half memories; the kernels take fp32 / bf16
+            memories = memories.float()
         if memories.dtype not in (torch.float32, torch.bfloat16):
-            raise ValueError("memories must be float32 or bfloat16")
+            raise ValueError("memories must be float32, bfloat16 or float16")
         M, B = memories.shape[0], memories.shape[1]
         max_len = int(max_len)
         split = self._lane_split(B, self.n_lanes if n_lanes is None else n_lanes)
@@ -471,6 +473,8 @@ class B200BeamDecoder(B200GreedyDecoder):
         """-> per sentence a list (best first) of hypothesis dicts, as SequenceGenerator.generate returns them."""
         if memories.device.type != self.device.type:
             raise L.CstError("memories must live on %s (no CPU fallback)" % self.device)
+        if memories.dtype == torch.float16:          # fairseq --fp16 models hand over half memories; the kernels take fp32 / bf16
+            memories = memories.float()
         M, B = memories.shape[0], memories.shape[1]
         key = ("beam", B, self.beam, M, int(max_len), memories.dtype)
         if key not in self._plans:

@@ -12,7 +12,9 @@ pre-training heads and `embed_positions._float_tensor`), so a reference checkpoi
 `load_state_dict(strict=True)`.  The arithmetic is done only by the CUDA kernels behind the C ABI
 (`include/chimera_st_b200.h`); without the built library or without a CUDA device `forward` raises.
 
-Integer `src_tokens` take the text (MT) branch (embedding + sinusoidal positions -> the same shared layers and memory stage).
+Integer (int32 / int64) `src_tokens` take the text (MT) branch (embedding + sinusoidal positions -> the same shared layers
+and memory stage).  `torch.int16` src_tokens are 16-bit PCM samples "on the wire" (SURVEY §8 f.3): copied as int16 and
+scaled by 2^-15 on the device, bit-identical to the reference's float32 waveform read at half the PCIe bytes.
 Not reproduced (out of scope): training-time dropout / LayerDrop,
 `modal_embedding` debug option, `non_shared_encoder_layers`.  They raise NotImplementedError.
 """
@@ -200,11 +202,12 @@ class B200InterlinguaEncoder(nn.Module):
                         else self._plan(None, None, ln, groups=groups))
                 for k, i in enumerate(idx):
                     src_tokens, src_lengths = batches[i]
-                    plan.load_inputs(src_tokens if src_tokens.dtype == torch.float32 else src_tokens.float(), src_lengths, group=k)
+                    plan.load_inputs(src_tokens if src_tokens.dtype in (torch.float32, torch.int16) else src_tokens.float(),
+                                     src_lengths, group=k)
                 self.last_launches += plan.run()
                 for k, i in enumerate(idx):
                     src_tokens = batches[i][0]
-                    o = plan.memories(k).to(self.encoder_out_dtype or src_tokens.dtype).clone(memory_format=torch.contiguous_format)
+                    o = plan.memories(k).to(self.encoder_out_dtype or self._out_dtype(src_tokens)).clone(memory_format=torch.contiguous_format)
                     if out is not None:
                         out[i].copy_(o, non_blocking=True)
                     pad = torch.zeros(src_tokens.shape[0], o.shape[0], dtype=torch.bool, device=o.device)
@@ -213,8 +216,13 @@ class B200InterlinguaEncoder(nn.Module):
             cur.wait_stream(ln["stream"])
         return results
 
+    @staticmethod
+    def _out_dtype(src_tokens):
+        """The reference returns the model dtype, which equals the waveform dtype; int16 PCM input -> float32."""
+        return src_tokens.dtype if src_tokens.dtype.is_floating_point else torch.float32
+
     def _check_inputs(self, src_tokens, src_lengths, allow_text=False):
-        if not src_tokens.dtype.is_floating_point and not allow_text:
+        if not src_tokens.dtype.is_floating_point and src_tokens.dtype != torch.int16 and not allow_text:
             raise NotImplementedError("integer (text) tokens are only accepted by forward()")
         if self.training:
             raise NotImplementedError("training-mode forward (dropout / LayerDrop) is not implemented; call .eval()")
@@ -224,7 +232,8 @@ class B200InterlinguaEncoder(nn.Module):
         # reference's collater guarantees (speech_to_text_dataset.py:218).  The reference derives the mask width from
         # max(src_lengths) (w2v2_transformer.py:327) and breaks on an over-padded batch; we use L = src_tokens.shape[1].
         # Checked only for host-resident lengths (a device tensor would need a sync).
-        if src_tokens.dtype.is_floating_point and src_lengths.device.type == "cpu" and src_lengths.numel():
+        if (src_tokens.dtype.is_floating_point or src_tokens.dtype == torch.int16) and src_lengths.device.type == "cpu" \
+                and src_lengths.numel():
             if int(src_lengths.max()) != src_tokens.shape[1]:
                 raise ValueError("src_tokens must be padded to max(src_lengths) exactly (got L=%d, max length %d)"
                                  % (src_tokens.shape[1], int(src_lengths.max())))
@@ -234,7 +243,7 @@ class B200InterlinguaEncoder(nn.Module):
         self._check_inputs(src_tokens, src_lengths)
         B, L = src_tokens.shape
         plan = self._plan(B, L)
-        plan.load_inputs(src_tokens.float(), src_lengths)
+        plan.load_inputs(src_tokens if src_tokens.dtype == torch.int16 else src_tokens.float(), src_lengths)
         self.last_launches = plan.run(upto="w2v")
         return plan.view("w2v_out").clone(), plan.view("frame_mask"), plan.w2v_len64.clone()
 
@@ -242,7 +251,7 @@ class B200InterlinguaEncoder(nn.Module):
     def forward(self, src_tokens, src_lengths, **extra_args):      # extra: the collater's stray `mask=` kwarg
         self._check_inputs(src_tokens, src_lengths, allow_text=True)
         B, L = src_tokens.shape
-        if not src_tokens.dtype.is_floating_point:                 # text (MT) branch, interlingua:212-217
+        if not src_tokens.dtype.is_floating_point and src_tokens.dtype != torch.int16:     # text (MT) branch, interlingua:212-217
             if self.no_interlingua:
                 raise NotImplementedError("no_interlingua with text input")
             plan = self._plan(B, L, text=True)
@@ -251,14 +260,14 @@ class B200InterlinguaEncoder(nn.Module):
             out = plan.memories().to(self.encoder_out_dtype or torch.float32).clone(memory_format=torch.contiguous_format)
             return EncoderOut(out, torch.zeros(B, out.shape[0], dtype=torch.bool, device=out.device), None, None, None, None)
         plan = self._plan(B, L)
-        plan.load_inputs(src_tokens.float(), src_lengths)
+        plan.load_inputs(src_tokens if src_tokens.dtype == torch.int16 else src_tokens.float(), src_lengths)
         self.last_launches = plan.run()
         if self.no_interlingua:                                    # interlingua:260-262
             out = plan.view("h_enc").transpose(0, 1)
         else:
             out = plan.memories()
         # always a fresh tensor: for B == 1 `.contiguous()` would return a view of the plan's arena
-        out = out.to(self.encoder_out_dtype or src_tokens.dtype).clone(memory_format=torch.contiguous_format)
+        out = out.to(self.encoder_out_dtype or self._out_dtype(src_tokens)).clone(memory_format=torch.contiguous_format)
         pad = torch.zeros(B, out.shape[0], dtype=torch.bool, device=out.device)
         return EncoderOut(out, pad, None, None, None, None)
 

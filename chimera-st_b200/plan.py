@@ -110,13 +110,13 @@ class EncoderPlan:
         self.s1_0, S1 = offsets([g.B * g.Tin1 for g in gs])                                # subsampler operands
         self.s2_0, S2 = offsets([g.B * g.Tin2 for g in gs])
         self.r2_0, R2 = offsets([g.B * g.T2a for g in gs])                                 # shared-encoder rows
-        self.w0, W = offsets([g.B * g.L for g in gs])
+        self.w0, W = offsets([(g.B * g.L + 7) // 8 * 8 for g in gs])                       # 16-byte aligned int16 / fp32 groups
         self.fm0, FM = offsets([g.B * g.Tp for g in gs])
         self.R, self.R2 = R, R2
         Bt, RM = self.Bt, self.Bt * M
         spec = [
             # ---- inputs / integer side
-            ("wave_flat", 1, W, f32), ("src_len", 1, Bt, i64), ("w2v_valid", 1, Bt, i32), ("sub_valid", 1, Bt, i32),
+            ("wave_flat", 1, W, f32), ("wave_i16", 1, W, torch.int16), ("src_len", 1, Bt, i64), ("w2v_valid", 1, Bt, i32), ("sub_valid", 1, Bt, i32),
             ("w2v_len64", 1, Bt, i64), ("frame_mask_flat", 1, FM, u8),
             # ---- conv stack (ping-pong; level i lives in cbuf{i & 1}); SLACK rows absorb the last windows
             ("scale_shift", Bt * 512, 2, f32), ("stats_ws", 1, Bt * 72, f64),
@@ -408,7 +408,16 @@ class EncoderPlan:
         reference batch of a super-batch."""
         g = self.gs[group]
         assert tuple(wave.shape) == (g.B, g.L), (tuple(wave.shape), (g.B, g.L))
-        self.waves[group].copy_(wave, non_blocking=True)
+        if wave.dtype == torch.int16:
+            # 16-bit PCM on the wire (what a .wav holds): half the host->device bytes, scaled by 2^-15 on the device --
+            # bit-identical to the reference's float32 read (audio_utils.py:33-55)
+            n, o = g.B * g.L, self.w0[group]
+            stage = self.wave_i16[o:o + n]
+            stage.view(g.B, g.L).copy_(wave, non_blocking=True)
+            L.check(self.lib.cst_wave_i16_to_f32(stage.data_ptr(), self.waves[group].data_ptr(), n,
+                                                 L.stream_ptr() if self.dev.type == "cuda" else 0))
+        else:
+            self.waves[group].copy_(wave, non_blocking=True)
         self.src_len[self.utt0[group]:self.utt0[group] + g.B].copy_(src_lengths, non_blocking=True)
 
     def run(self, upto="memory", eager=False):

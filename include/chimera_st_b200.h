@@ -47,6 +47,13 @@ int cst_frame_lengths(const int64_t* src_len, int B, int L, int n_frames,
                       int32_t* w2v_valid, int32_t* sub_valid, int64_t* w2v_len64, uint8_t* frame_mask,
                       void* stream);
 
+/* ---- f.3 input pipeline: 16-bit PCM on the wire ------------------------------------------------------------------------
+ * Replaces: the host-side int16 -> float32 normalisation of get_waveform (fairseq/data/audio/audio_utils.py:33-55, soundfile
+ * dtype="float32": sample / 32768) followed by an fp32 host->device copy (fairseq/utils.py move_to_cuda).  The padded batch is
+ * sent as int16 (half the PCIe bytes) and scaled on the device: out[i] = in[i] * 2^-15, bit-identical (exact power of two).
+ * in / out: n contiguous samples, both 16-byte aligned. */
+int cst_wave_i16_to_f32(const int16_t* in, float* out, long long n, void* stream);
+
 /* ---- a1: conv0 (1->512, k10, s5, no bias) + GroupNorm(512 groups, padded-time statistics) + GELU ----
  * Replaces: ConvFeatureExtractionModel block 0 (wav2vec2.py:697-734,755-763; Fp32GroupNorm
  * fp32_group_norm.py:17-25).  Two launches:
@@ -162,6 +169,28 @@ int cst_attention_segs(const void* q, const void* k, const void* v, void* out, i
  * x f32 [B*rows_per_seg, C] (rows t >= T of a segment are zero-filled); valid int32 [B] = lengths (may be NULL). */
 int cst_text_embed(const int64_t* tokens, const int64_t* lengths, const float* embed, const float* pos_table,
                    float scale, float* x, int32_t* valid, int B, int T, int rows_per_seg, int C, int V, void* stream);
+
+/* ==== training heads over the path's outputs =====================================================
+ * Contrastive (InfoNCE) loss over the M shared semantic memories of the audio and the text pass.
+ * Replaces: TripletSTMTContrastiveCriterion.compute_contrastive (fairseq/criterions/triplet_st_mt_contrastive.py:154-169):
+ *   logits[b,i,j] = cosine_similarity(audio[b,i,:], text[b,j,:]) / temp   (cosine in fp32, eps 1e-8)
+ *   loss_rows[b*M + j] = cross_entropy over the AUDIO index i of logits[b,:,j], target = j  (the reference hands the 3-D
+ *   [b,i,j] tensor to F.cross_entropy, whose class axis is dim 1; reduce=False form -- sum the rows for reduce=True)
+ * audio / text: [M, B, C] (encoder_out layout), dtype CST_F32 or CST_BF16; M <= 64, C <= 1024.  lse_ws: B*M floats.
+ * d_audio / d_text (both or neither, f32 [M,B,C]): dscale * d(sum of loss_rows)/d(input). */
+int cst_contrastive_loss(const void* audio, const void* text, int dtype, int M, int B, int C, float temp,
+                         float* loss_rows, float* lse_ws, float* d_audio, float* d_text, float dscale, void* stream);
+
+/* Label-smoothed cross entropy of N target positions over V classes.
+ * Replaces: label_smoothed_nll_loss (fairseq/criterions/label_smoothed_cross_entropy.py:13-30) applied to
+ * log_softmax(logits): nll_rows[r] = -lprobs[r, target[r]], loss_rows[r] = (1-eps)*nll + eps/V * (-sum_v lprobs[r,v]);
+ * rows with target == ignore_index give 0.  dlogits (optional, [N, ldd]) = dscale * d(sum of loss_rows)/d(logits). */
+int cst_label_smoothed_ce(const float* logits, long long ld, const int64_t* target, int N, int V, float eps,
+                          long long ignore_index, float* loss_rows, float* nll_rows, float* dlogits, long long ldd,
+                          float dscale, void* stream);
+
+/* out[0] = sum of n floats, fixed summation order (deterministic): the reduce=True form of the two criteria. */
+int cst_sum(const float* x, long long n, float* out, void* stream);
 
 /* ==== greedy incremental decoding from the memories (BASELINE configs[3] "encode + greedy decode")
  * All four entry points read the current step from a DEVICE counter, so one captured CUDA graph of a decoding step is

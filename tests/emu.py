@@ -26,6 +26,11 @@ class EmuLib:
     def __init__(self):
         self.calls = []
 
+    def cst_wave_i16_to_f32(self, src, dst, n, stream):
+        _mem(dst, n)[:] = _mem(src, n, np.int16).astype(np.float32) * np.float32(1.0 / 32768.0)
+        self.calls.append("wave_i16_to_f32")
+        return 0
+
     # ---- a4
     def cst_frame_lengths(self, src_len, B, L, n_frames, w2v_valid, sub_valid, w2v_len64, frame_mask, stream):
         lens = _mem(src_len, B, np.int64)

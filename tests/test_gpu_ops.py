@@ -217,6 +217,50 @@ def test_attention(dtype, tol, B, H, Tq, Tk, masked):
     assert rel_l2(out.cpu().float(), ref) < tol, rel_l2(out.cpu().float(), ref)
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-6), (torch.bfloat16, 6e-3)])
+@pytest.mark.parametrize("H,segs,masked", [
+    (12, [(749, 749), (300, 290), (1499, 1499), (128, 100), (257, 256)], True),      # wav2vec2 stage: q rows >= kv rows
+    (8, [(188, 188), (63, 63), (375, 375), (1, 1), (26, 25)], True),                 # shared layers
+    (8, [(16, 188), (16, 63), (16, 375), (16, 25)], False),                          # memory stage: M queries, no mask
+    (8, [(64, 250), (64, 1000)], False)])
+def test_attention_segment_table(dtype, tol, H, segs, masked):
+    """cst_attention_segs: utterances of different lengths in one row space (the super-batch form), q / kv rows of
+    utterance b anywhere in their buffers; must equal per-utterance softmax attention in fp64."""
+    g = torch.Generator().manual_seed(len(segs) * 7 + H)
+    Cd = H * 64
+    gap = 3                                                         # junk rows between segments: must never be read as valid
+    tbl, qo, ko = [], 0, 0
+    for nq, nk in segs:
+        tbl.append([qo, nq, ko, nk])
+        qo += nq + gap
+        ko += nk + gap
+    q = (torch.randn(qo, Cd, generator=g) * 0.5).to(dtype)
+    k = torch.randn(ko, Cd, generator=g).to(dtype)
+    v = torch.randn(ko, Cd, generator=g).to(dtype)
+    kl = torch.tensor([max(1, (nk * (3 + i)) // (4 + i)) for i, (_, nk) in enumerate(segs)], dtype=torch.int32) if masked else None
+    out = torch.full((qo, Cd), 7.0, dtype=dtype, device=DEV)
+    L = L_()
+    seg = torch.tensor(tbl, dtype=torch.int32, device=DEV)
+    qd, kd, vd = q.to(DEV), k.to(DEV), v.to(DEV)
+    kld = kl.to(DEV) if masked else None
+    L.check(L.load().cst_attention_segs(qd.data_ptr(), kd.data_ptr(), vd.data_ptr(), out.data_ptr(), L.DT[dtype], Cd, Cd, Cd,
+                                        len(segs), H, seg.data_ptr(), max(s[0] for s in segs), max(s[1] for s in segs), qo, ko,
+                                        L.ptr(kld), L.stream_ptr()))
+    torch.cuda.synchronize()
+    out = out.cpu().float()
+    for i, (q0, nq, k0, nk) in enumerate(tbl):
+        qh = q[q0:q0 + nq].float().double().view(nq, H, 64).transpose(0, 1)
+        kh = k[k0:k0 + nk].float().double().view(nk, H, 64).transpose(0, 1)
+        vh = v[k0:k0 + nk].float().double().view(nk, H, 64).transpose(0, 1)
+        sc = qh @ kh.transpose(-1, -2)
+        if masked:
+            sc = sc.masked_fill(torch.arange(nk)[None, None, :] >= int(kl[i]), float("-inf"))
+        ref = (torch.softmax(sc, -1) @ vh).transpose(0, 1).reshape(nq, Cd)
+        assert rel_l2(out[q0:q0 + nq], ref) < tol, (i, rel_l2(out[q0:q0 + nq], ref))
+        if i + 1 < len(tbl):
+            assert bool((out[q0 + nq:q0 + nq + gap] == 7.0).all()), "rows outside the segment were written"
+
+
 @pytest.mark.parametrize("B,T", [(2, 70), (3, 250), (1, 129), (2, 750), (1, 1000), (1, 385)])
 def test_resident_posconv_matches_generic_gemm_path(B, T):
     """cst_posconv (panel resident in smem, row-shifted swizzled A descriptors) vs the batched implicit GEMM."""
