@@ -32,6 +32,10 @@ class GemmParams(C.Structure):
         ("rows_per_seg", C.c_int), ("seg_rows_valid", C.c_int),
         ("out_rows_per_seg", C.c_longlong), ("out_row_off", C.c_int),
         ("seg_len", C.c_void_p), ("segs_per_outer", C.c_int),
+        ("ln_in_stats", C.c_void_p), ("ln_colsum", C.c_void_p), ("ln_in_slots", C.c_int),
+        ("res_stats", C.c_void_p), ("res_slots", C.c_int), ("res_gamma", C.c_void_p), ("res_beta", C.c_void_p),
+        ("C2", C.c_void_p), ("c2_dtype", C.c_int), ("ldc2", C.c_longlong),
+        ("out_stats", C.c_void_p), ("ln_dim", C.c_int),
     ]
 
 
@@ -74,6 +78,8 @@ _SIGS = {
     "cst_layernorm": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                 C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_int,
                                 C.c_void_p]),
+    "cst_layernorm_ab": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p,
+                                   C.c_int, C.c_int, C.c_void_p]),
     "cst_posconv_pack": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "cst_broadcast_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "cst_posconv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,

@@ -16,7 +16,25 @@ struct GemmDev {          // device copy of cst_gemm_params (pointers already ty
   int bias_bs_inner;
   int rows_per_seg, seg_rows_valid; long long out_rows_per_seg; int out_row_off;
   const int32_t* seg_len; int segs_per_outer;
+  // LayerNorm fused around the GEMM (tensor-core path; see cst_gemm_params)
+  const float2* ln_in_stats; const float* ln_colsum; int ln_in_slots;
+  const float2* res_stats; int res_slots; const float* res_gamma; const float* res_beta;
+  __nv_bfloat16* C2; long long ldc2;
+  float2* out_stats;
+  float ln_inv_dim;
 };
+
+// {rstd, -mean * rstd} of one row from its partial sums (sum, sum of squares per 128-column slice), eps 1e-5
+__device__ __forceinline__ float2 ln_ab_from_partials(const float2* stats, long long row, int slots, float inv_dim) {
+  if (slots == 0) return __ldg(stats + row);       // already {rstd, -mean*rstd} (cst_layernorm_ab)
+  float s = 0.f, q = 0.f;
+  const float2* sp = stats + row * 8;
+  for (int i = 0; i < slots; ++i) { const float2 t = __ldg(sp + i); s += t.x; q += t.y; }
+  const float mean = s * inv_dim;
+  const float var = fmaxf(q * inv_dim - mean * mean, 0.f);
+  const float rstd = rsqrtf(var + 1e-5f);
+  return make_float2(rstd, -mean * rstd);
+}
 
 struct RowInfo { long long out_row; bool store; bool zero; };
 

@@ -135,6 +135,24 @@ extern "C" int cst_gemm(const cst_gemm_params* hp, void* stream) {
   p.rows_per_seg = hp->rows_per_seg; p.seg_rows_valid = hp->seg_rows_valid;
   p.out_rows_per_seg = hp->out_rows_per_seg; p.out_row_off = hp->out_row_off;
   p.seg_len = hp->seg_len; p.segs_per_outer = hp->segs_per_outer;
+  p.ln_in_stats = reinterpret_cast<const float2*>(hp->ln_in_stats); p.ln_colsum = hp->ln_colsum; p.ln_in_slots = hp->ln_in_slots;
+  p.res_stats = reinterpret_cast<const float2*>(hp->res_stats); p.res_slots = hp->res_slots;
+  p.res_gamma = hp->res_gamma; p.res_beta = hp->res_beta;
+  p.C2 = reinterpret_cast<__nv_bfloat16*>(hp->C2); p.ldc2 = hp->ldc2;
+  p.out_stats = reinterpret_cast<float2*>(hp->out_stats);
+  p.ln_inv_dim = hp->ln_dim > 0 ? 1.0f / (float)hp->ln_dim : 0.f;
+  const bool ln_fused = hp->ln_in_stats || hp->res_stats || hp->C2 || hp->out_stats;
+  if (ln_fused) {
+    CST_REQUIRE(hp->ab_dtype == CST_BF16 || hp->ab_dtype == CST_F16, "cst_gemm: fused LayerNorm needs the tensor-core path (16-bit operands)");
+    CST_REQUIRE(hp->ln_dim > 0, "cst_gemm: fused LayerNorm needs ln_dim");
+    CST_REQUIRE(!hp->ln_in_stats || (hp->ln_colsum && hp->ln_in_slots > 0 && hp->ln_in_slots <= 8 && !hp->residual),
+                "cst_gemm: ln_in_stats needs ln_colsum, 1..8 slots and no residual");
+    CST_REQUIRE(!hp->res_stats || (hp->res_gamma && hp->res_beta && hp->res_slots >= 0 && hp->res_slots <= 8 && hp->residual),
+                "cst_gemm: res_stats needs res_gamma / res_beta, 0..8 slots and a residual");
+    CST_REQUIRE(!(hp->C2 || hp->out_stats || hp->res_stats) || (hp->residual && hp->c_dtype == CST_F32),
+                "cst_gemm: C2 / out_stats / res_stats need an fp32 C with a residual");
+    CST_REQUIRE(!hp->C2 || (hp->c2_dtype == CST_BF16 && hp->ldc2 % 8 == 0), "cst_gemm: C2 must be bf16 with ldc2 %% 8 == 0");
+  }
   const int nz = hp->nb_outer * hp->nb_inner;
   cudaStream_t st = (cudaStream_t)stream;
   if (hp->ab_dtype == CST_F32) return launch_gemm_f32(p, nz, st);

@@ -61,11 +61,15 @@ __device__ int tc_dbg_flags;      // timing experiments: 1 skip global stores, 2
 // loads of chunk c+1 are in flight while chunk c's math runs.
 // BST (fp32 output, identity row mapping): the finished values go back into the patch -- whose XOR layout IS the
 // 128-byte TMA swizzle -- and one lane bulk-stores the 32x32 block, instead of eight STG per lane and chunk.
-template <int BN, int ACT, int CD, bool RES, bool BST, typename WaitF>
+// LNF (fp32 output with residual): LayerNorm fused around the GEMM (cst_gemm_params: res_stats / C2 / out_stats) -- the
+// residual rows are normalised on the fly from their partial statistics, a bf16 copy of the output is stored next to the
+// fp32 one, and this warp's partial statistics of the output rows (its 128-column slice) are written for the consumers.
+template <int BN, int ACT, int CD, bool RES, bool BST, bool LNF, typename WaitF>
 __device__ __forceinline__ void epi_tile_fast(const GemmDev& p, float* patch, uint32_t t_row, int nb, int lane, int chalf,
                                               const float* bias, uint8_t* c_base, const float* r_base, const int (&orow)[8],
                                               uint32_t st_mask, WaitF wait_acc, const CUtensorMap* tmC = nullptr, int row0 = 0) {
   static_assert(!BST || CD == 0, "in-place bulk store: fp32 output only");
+  static_assert(!LNF || (RES && CD == 0), "fused LayerNorm epilogue: fp32 output with residual");
   constexpr int NCH = (BN + 31) / 32, CH_PER = (NCH + 1) / 2;
   constexpr int ES = CD == 0 ? 4 : 2;
   const int lr = lane >> 3, lc = (lane & 7) * 4;
@@ -108,6 +112,28 @@ __device__ __forceinline__ void epi_tile_fast(const GemmDev& p, float* patch, ui
   float4 r_cur[RES ? 8 : 1];
   load_res(ch0, 0, r_cur);
   load_res(ch0, 4, r_cur);
+  // fused LayerNorm state: per-row {rstd, -mean*rstd} of the lazily normalised residual, gamma / beta of the current and
+  // next chunk, running partial statistics of the output rows
+  const bool lazy_res = LNF && p.res_stats != nullptr;
+  float ra[LNF ? 8 : 1], rb[LNF ? 8 : 1], s1[LNF ? 8 : 1], s2[LNF ? 8 : 1];
+  float4 g_cur = make_float4(1.f, 1.f, 1.f, 1.f), t_cur = make_float4(0.f, 0.f, 0.f, 0.f), g_nxt = g_cur, t_nxt = t_cur;
+  auto load_gamma = [&](int ch) {
+    return (lazy_res && col_ok_of(ch)) ? __ldg(reinterpret_cast<const float4*>(p.res_gamma + col_of(ch))) : make_float4(1.f, 1.f, 1.f, 1.f);
+  };
+  auto load_beta = [&](int ch) {
+    return (lazy_res && col_ok_of(ch)) ? __ldg(reinterpret_cast<const float4*>(p.res_beta + col_of(ch))) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  if (LNF) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      ra[i] = 1.f; rb[i] = 0.f; s1[i] = 0.f; s2[i] = 0.f;
+      if (lazy_res && ((st_mask >> i) & 1)) {
+        const float2 ab = ln_ab_from_partials(p.res_stats, orow[i], p.res_slots, p.ln_inv_dim);
+        ra[i] = ab.x; rb[i] = ab.y;
+      }
+    }
+    g_cur = load_gamma(ch0); t_cur = load_beta(ch0);
+  }
   wait_acc();
   load_acc(ch0, acc);
 #pragma unroll 1
@@ -131,6 +157,7 @@ __device__ __forceinline__ void epi_tile_fast(const GemmDev& p, float* patch, ui
     if (has_next) {                                            // next chunk: TMEM and bias loads in flight during the math
       load_acc(ch + 1, acc);
       b_nxt = load_bias(ch + 1);
+      if (LNF) { g_nxt = load_gamma(ch + 1); t_nxt = load_beta(ch + 1); }
     }
     if (col_ok && !TC_DBG(2)) {
       const uint64_t b01 = pk2(b_cur.x, b_cur.y), b23 = pk2(b_cur.z, b_cur.w);
@@ -157,10 +184,29 @@ __device__ __forceinline__ void epi_tile_fast(const GemmDev& p, float* patch, ui
         if (RES) {
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            upk2(fadd2(pk2(v[u][0], v[u][1]), pk2(r_cur[i0 + u].x, r_cur[i0 + u].y)), v[u][0], v[u][1]);
-            upk2(fadd2(pk2(v[u][2], v[u][3]), pk2(r_cur[i0 + u].z, r_cur[i0 + u].w)), v[u][2], v[u][3]);
+            float4 r4 = r_cur[i0 + u];
+            if (LNF) {                                         // LayerNorm of the residual row, applied on the fly
+              const float a = ra[i0 + u], b = rb[i0 + u];
+              r4.x = fmaf(fmaf(r4.x, a, b), g_cur.x, t_cur.x); r4.y = fmaf(fmaf(r4.y, a, b), g_cur.y, t_cur.y);
+              r4.z = fmaf(fmaf(r4.z, a, b), g_cur.z, t_cur.z); r4.w = fmaf(fmaf(r4.w, a, b), g_cur.w, t_cur.w);
+            }
+            upk2(fadd2(pk2(v[u][0], v[u][1]), pk2(r4.x, r4.y)), v[u][0], v[u][1]);
+            upk2(fadd2(pk2(v[u][2], v[u][3]), pk2(r4.z, r4.w)), v[u][2], v[u][3]);
           }
           if (has_next) load_res(ch + 1, i0, r_cur);           // these four registers are free again: refill for chunk c+1
+        }
+        if (LNF) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u;
+            if ((st_mask >> i) & 1) {
+              s1[i] += (v[u][0] + v[u][1]) + (v[u][2] + v[u][3]);
+              s2[i] += fmaf(v[u][0], v[u][0], v[u][1] * v[u][1]) + fmaf(v[u][2], v[u][2], v[u][3] * v[u][3]);
+              if (p.C2 != nullptr)
+                *reinterpret_cast<uint2*>(p.C2 + (long long)orow[i] * p.ldc2 + n) =
+                    make_uint2(pack_bf16x2(v[u][0], v[u][1]), pack_bf16x2(v[u][2], v[u][3]));
+            }
+          }
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -188,6 +234,21 @@ __device__ __forceinline__ void epi_tile_fast(const GemmDev& p, float* patch, ui
       }
     }
     b_cur = b_nxt;
+    if (LNF) { g_cur = g_nxt; t_cur = t_nxt; }
+  }
+  if (LNF) {
+    if (p.out_stats != nullptr) {                              // the 8 lanes of a row group hold 4 columns each of the row's chunks
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+#pragma unroll
+        for (int off = 1; off < 8; off <<= 1) {
+          s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], off);
+          s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], off);
+        }
+        if ((lane & 7) == 0 && ((st_mask >> i) & 1))
+          p.out_stats[(long long)orow[i] * 8 + nb * 2 + chalf] = make_float2(s1[i], s2[i]);
+      }
+    }
   }
 }
 
@@ -199,7 +260,9 @@ __device__ __forceinline__ void epi_tile_fast(const GemmDev& p, float* patch, ui
 // writes it (clipping rows >= M) while the warp moves on: no STG, no read-back, no per-row address arithmetic.
 // Two register buffers alternate so that the tcgen05.ld of chunk c+1 is in flight during chunk c's math, and the
 // accumulator stage is released as soon as its last chunk is in registers.
-template <int BN, int ACT, int CD, typename WaitF, typename ReleaseF>
+// LNI: the A operand was the bf16 copy of UN-normalised rows; their LayerNorm is applied after the product (lane = row, so
+// mean / rstd are per-lane scalars): v = rstd*acc + (-mean*rstd)*colsum[n] + bias[n]  (cst_gemm_params: ln_in_stats).
+template <int BN, int ACT, int CD, bool LNI, typename WaitF, typename ReleaseF>
 __device__ __forceinline__ void epi_tile_bulk(const GemmDev& p, const CUtensorMap* tmC, uint32_t stage_s, uint32_t& seq, uint32_t t_row,
                                               int row0, int nb, int lane, int chalf, const float* bias, WaitF wait_acc, ReleaseF release_acc) {
   static_assert(BN % 64 == 0, "bulk epilogue: whole 32-column chunks per warp half");
@@ -207,6 +270,12 @@ __device__ __forceinline__ void epi_tile_bulk(const GemmDev& p, const CUtensorMa
   constexpr int NBUF = CD == 0 ? 1 : 2;                        // 4 KB per warp: one fp32 block or two 16-bit blocks
   const int ch0 = chalf * CH_PER;
   float acc[2][32];
+  uint64_t ln_a2 = 0, ln_b2 = 0;
+  if (LNI) {
+    float2 ab = make_float2(0.f, 0.f);
+    if (row0 + lane < p.M) ab = ln_ab_from_partials(p.ln_in_stats, row0 + lane, p.ln_in_slots, p.ln_inv_dim);
+    ln_a2 = pk2(ab.x, ab.x); ln_b2 = pk2(ab.y, ab.y);
+  }
   wait_acc();
   tmem_ld32(t_row + ch0 * 32, acc[0]);
 #pragma unroll
@@ -216,7 +285,15 @@ __device__ __forceinline__ void epi_tile_bulk(const GemmDev& p, const CUtensorMa
     tmem_ld_wait();
     if (j + 1 < CH_PER) tmem_ld32(t_row + (ch0 + j + 1) * 32, acc[(j + 1) & 1]);
     else release_acc();                                        // whole accumulator stage is in registers now
-    if (bias) {                                                // same address in every lane: one broadcast transaction each
+    if (LNI) {                                                 // rstd*acc + (-mean*rstd)*colsum + bias
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 bv = bias ? __ldg(reinterpret_cast<const float4*>(bias + n0) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 cs = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + n0) + i);
+        upk2(ffma2(pk2(v[4 * i], v[4 * i + 1]), ln_a2, ffma2(ln_b2, pk2(cs.x, cs.y), pk2(bv.x, bv.y))), v[4 * i], v[4 * i + 1]);
+        upk2(ffma2(pk2(v[4 * i + 2], v[4 * i + 3]), ln_a2, ffma2(ln_b2, pk2(cs.z, cs.w), pk2(bv.z, bv.w))), v[4 * i + 2], v[4 * i + 3]);
+      }
+    } else if (bias) {                                         // same address in every lane: one broadcast transaction each
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + n0) + i);
@@ -269,9 +346,14 @@ __device__ __forceinline__ void epi_tile(const GemmDev& p, const CUtensorMap* tm
   if constexpr (BN % 64 == 0 && ACT != CST_ACT_GLU) {
     if (bulk == 1) {
       const uint32_t stage_s = smem_u32(patch);
-      if (p.c_dtype == CST_F32) epi_tile_bulk<BN, ACT, 0>(p, tmC, stage_s, seq, t_row, row_base, nb, lane, chalf, p.bias, wait_acc, release_acc);
-      else if (p.c_dtype == CST_BF16) epi_tile_bulk<BN, ACT, 1>(p, tmC, stage_s, seq, t_row, row_base, nb, lane, chalf, p.bias, wait_acc, release_acc);
-      else epi_tile_bulk<BN, ACT, 2>(p, tmC, stage_s, seq, t_row, row_base, nb, lane, chalf, p.bias, wait_acc, release_acc);
+      if (p.ln_in_stats != nullptr) {                            // LayerNorm of the input applied after the product (bf16 outputs)
+        if constexpr (ACT == CST_ACT_NONE || ACT == CST_ACT_GELU || ACT == CST_ACT_RELU)
+          epi_tile_bulk<BN, ACT, 1, true>(p, tmC, stage_s, seq, t_row, row_base, nb, lane, chalf, p.bias, wait_acc, release_acc);
+        return;
+      }
+      if (p.c_dtype == CST_F32) epi_tile_bulk<BN, ACT, 0, false>(p, tmC, stage_s, seq, t_row, row_base, nb, lane, chalf, p.bias, wait_acc, release_acc);
+      else if (p.c_dtype == CST_BF16) epi_tile_bulk<BN, ACT, 1, false>(p, tmC, stage_s, seq, t_row, row_base, nb, lane, chalf, p.bias, wait_acc, release_acc);
+      else epi_tile_bulk<BN, ACT, 2, false>(p, tmC, stage_s, seq, t_row, row_base, nb, lane, chalf, p.bias, wait_acc, release_acc);
       return;
     }
   }
@@ -310,21 +392,28 @@ __device__ __forceinline__ void epi_tile(const GemmDev& p, const CUtensorMap* tm
   if (fast) {
     uint8_t* c_base = reinterpret_cast<uint8_t*>(p.C) + c_off * esz;
     const float* r_base = p.residual + r_off;
+    const bool lnf = p.res_stats != nullptr || p.C2 != nullptr || p.out_stats != nullptr;
     if (p.residual) {
       if (!c_16) {
         if constexpr (BN % 64 == 0) {
-          if (bulk == 2) epi_tile_fast<BN, ACT, 0, true, true>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc, tmC, row_base);
-          else epi_tile_fast<BN, ACT, 0, true, false>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc);
+          if (lnf) {
+            if constexpr (ACT == CST_ACT_NONE) {               // out-proj / fc2: the only users of the fused LayerNorm epilogue
+              if (bulk == 2) epi_tile_fast<BN, ACT, 0, true, true, true>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc, tmC, row_base);
+              else epi_tile_fast<BN, ACT, 0, true, false, true>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc);
+            }
+          }
+          else if (bulk == 2) epi_tile_fast<BN, ACT, 0, true, true, false>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc, tmC, row_base);
+          else epi_tile_fast<BN, ACT, 0, true, false, false>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc);
         } else {
-          epi_tile_fast<BN, ACT, 0, true, false>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc);
+          epi_tile_fast<BN, ACT, 0, true, false, false>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc);
         }
       }
-      else if (!c_f16) epi_tile_fast<BN, ACT, 1, true, false>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc);
-      else epi_tile_fast<BN, ACT, 2, true, false>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc);
+      else if (!c_f16) epi_tile_fast<BN, ACT, 1, true, false, false>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc);
+      else epi_tile_fast<BN, ACT, 2, true, false, false>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc);
     } else {
-      if (!c_16) epi_tile_fast<BN, ACT, 0, false, false>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc);
-      else if (!c_f16) epi_tile_fast<BN, ACT, 1, false, false>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc);
-      else epi_tile_fast<BN, ACT, 2, false, false>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc);
+      if (!c_16) epi_tile_fast<BN, ACT, 0, false, false, false>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc);
+      else if (!c_f16) epi_tile_fast<BN, ACT, 1, false, false, false>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc);
+      else epi_tile_fast<BN, ACT, 2, false, false, false>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc);
     }
   } else {
   wait_acc();
@@ -559,6 +648,21 @@ static int bulk_store_ok(const cst_gemm_params& hp, int nz, int bn) {
   if (hp.residual == nullptr) return (enabled & 1) ? 1 : 0;
   return ((enabled & 2) && hp.c_dtype == CST_F32) ? 2 : 0;
 }
+// fused LayerNorm modes exist only where the plan uses them: identity-mapped, unbatched GEMMs with 256-column tiles
+static int check_ln_fused(const cst_gemm_params& hp, int nz, int bn, int bulk) {
+  if (hp.ln_in_stats) {
+    CST_REQUIRE(bulk == 1 && hp.c_dtype == CST_BF16 && hp.act != CST_ACT_GLU, "cst_gemm: ln_in_stats needs the bulk-store epilogue with a bf16 output (identity "
+                "row mapping, N %% %d == 0, no residual / GLU / alpha)", bn);
+    CST_REQUIRE(((uintptr_t)hp.ln_colsum % 16) == 0 && ((uintptr_t)hp.ln_in_stats % 8) == 0, "cst_gemm: ln_colsum / ln_in_stats alignment");
+  }
+  if (hp.res_stats || hp.C2 || hp.out_stats) {
+    const bool ident = nz == 1 && bn % 64 == 0 && hp.act == CST_ACT_NONE && hp.alpha == 1.0f && hp.seg_len == nullptr && hp.out_row_off == 0 &&
+                       hp.out_rows_per_seg == hp.rows_per_seg && hp.seg_rows_valid >= hp.rows_per_seg && hp.N % bn == 0;
+    CST_REQUIRE(ident && hp.N / bn * 2 <= 8, "cst_gemm: res_stats / C2 / out_stats need an identity-mapped, unbatched GEMM without "
+                "activation (N %% %d == 0, at most 8 statistics slots)", bn);
+  }
+  return CST_OK;
+}
 static int make_c_map(CUtensorMap* tmC, const cst_gemm_params& hp, int bulk) {
   if (!bulk) { memset(tmC, 0, sizeof(*tmC)); return CST_OK; }
   const int esz = hp.c_dtype == CST_F32 ? 4 : 2;
@@ -587,6 +691,8 @@ static int launch_tc_act(const cst_gemm_params& hp, const GemmDev& p, int nz, cu
   rc = make_map_2d(&tmB, hp.W, hp.K, (long long)hp.nb_inner * hp.N, hp.K, TC_BK, BN);
   if (rc) return rc;
   const int bulk = bulk_store_ok(hp, nz, BN);
+  rc = check_ln_fused(hp, nz, BN, bulk);
+  if (rc) return rc;
   CUtensorMap tmC;
   rc = make_c_map(&tmC, hp, bulk);
   if (rc) return rc;
@@ -812,6 +918,8 @@ static int launch_tc_pair_act(const cst_gemm_params& hp, const GemmDev& p, int n
   rc = make_map_2d(&tmB, hp.W, hp.K, (long long)hp.nb_inner * hp.N, hp.K, TC_BK, 128);
   if (rc) return rc;
   const int bulk = bulk_store_ok(hp, nz, 256);
+  rc = check_ln_fused(hp, nz, 256, bulk);
+  if (rc) return rc;
   CUtensorMap tmC;
   rc = make_c_map(&tmC, hp, bulk);
   if (rc) return rc;

@@ -56,6 +56,46 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   }
 }
 
+// "Light" LayerNorm for the post-LN wav2vec2 layers (16-bit mode): writes ONLY the 16-bit GEMM operand copy of the normalised
+// row and the row's {rstd, -mean*rstd}; the fp32 normalised row is never stored -- the next residual GEMM re-creates it in its
+// epilogue from the un-normalised row and these two numbers (cst_gemm_params.res_stats with res_slots == 0).
+template <int NV, typename LpT>
+__global__ void __launch_bounds__(256) layernorm_ab_kernel(const float* __restrict__ x, long long ldx,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           LpT* __restrict__ out_lp, long long ldo, float2* __restrict__ ab_out, int rows) {
+  pdl_launch_dependents();
+  pdl_wait();
+  constexpr int C = NV * 128;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float4 v[NV];
+  const float* xr = x + (long long)row * ldx;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = load4(xr + (lane + 32 * i) * 4);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  const float mean = warp_sum(s) * (1.0f / C);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / C) + 1e-5f);
+  if (lane == 0) ab_out[row] = make_float2(rstd, -mean * rstd);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 g = load4(gamma + (lane + 32 * i) * 4), bb = load4(beta + (lane + 32 * i) * 4);
+    v[i].x = (v[i].x - mean) * rstd * g.x + bb.x;
+    v[i].y = (v[i].y - mean) * rstd * g.y + bb.y;
+    v[i].z = (v[i].z - mean) * rstd * g.z + bb.z;
+    v[i].w = (v[i].w - mean) * rstd * g.w + bb.w;
+    store4(out_lp + (long long)row * ldo + (lane + 32 * i) * 4, v[i]);
+  }
+}
+
 // xg[b][g][row][64]: frame t at row t+64, lanes 0..47 = x[b, t, g*48 .. g*48+47], rest zero.
 template <typename OutT>
 __global__ void posconv_pack_kernel(const float* __restrict__ x, int rows_per_seg, int n_frames,
@@ -106,6 +146,20 @@ extern "C" int cst_layernorm(const float* x, long long ldx, const float* gamma, 
   if (out_lp && lp_dtype == CST_BF16) { if (C == 512) CST_LN(4, __nv_bfloat16); else CST_LN(6, __nv_bfloat16); }
   else { if (C == 512) CST_LN(4, float); else CST_LN(6, float); }
 #undef CST_LN
+  return CST_OK;
+}
+
+extern "C" int cst_layernorm_ab(const float* x, long long ldx, const float* gamma, const float* beta, void* out_lp, int lp_dtype,
+                                long long ldo, float* ab_out, int rows, int C, void* stream) {
+  using namespace cst;
+  CST_REQUIRE(x && gamma && beta && out_lp && ab_out && rows > 0, "cst_layernorm_ab: bad args rows=%d", rows);
+  CST_REQUIRE(C == 512 || C == 768, "cst_layernorm_ab: C=%d unsupported (512 or 768)", C);
+  CST_REQUIRE(lp_dtype == CST_BF16, "cst_layernorm_ab: bf16 operand copy only");
+  CST_REQUIRE(ldx % 4 == 0 && ldo % 4 == 0, "cst_layernorm_ab: ldx/ldo must be multiples of 4");
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid(cdiv(rows, 8));
+  if (C == 512) CST_CHECK_CUDA(launch_k(layernorm_ab_kernel<4, __nv_bfloat16>, grid, dim3(256), 0, st, x, ldx, gamma, beta, (__nv_bfloat16*)out_lp, ldo, (float2*)ab_out, rows));
+  else CST_CHECK_CUDA(launch_k(layernorm_ab_kernel<6, __nv_bfloat16>, grid, dim3(256), 0, st, x, ldx, gamma, beta, (__nv_bfloat16*)out_lp, ldo, (float2*)ab_out, rows));
   return CST_OK;
 }
 

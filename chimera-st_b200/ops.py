@@ -61,7 +61,7 @@ def conv0_gn_gelu(wave, w, gamma, beta, out_dtype=torch.float32, rows_per_seg=No
 def gemm(A, W, C_, M, N, K, lda, a_rows, bias=None, residual=None, act=L.ACT_NONE, alpha=1.0,
          rows_per_seg=None, seg_rows_valid=None, out_rows_per_seg=None, out_row_off=0, seg_len=None,
          ldc=None, ldr=None, nb_outer=1, nb_inner=1, a_bs=(0, 0), w_bs=0, c_bs=(0, 0), r_bs=None, bias_bs=0,
-         segs_per_outer=1):
+         segs_per_outer=1, ln_in=None, res_ln=None, c2=None, out_stats=None, ln_dim=0):
     _cuda(A, W, C_, bias, residual, seg_len)
     p = L.GemmParams()
     p.A, p.W, p.bias, p.residual, p.C = A.data_ptr(), W.data_ptr(), L.ptr(bias), L.ptr(residual), C_.data_ptr()
@@ -84,6 +84,15 @@ def gemm(A, W, C_, M, N, K, lda, a_rows, bias=None, residual=None, act=L.ACT_NON
     p.out_row_off = out_row_off
     p.seg_len = L.ptr(seg_len)
     p.segs_per_outer = segs_per_outer
+    if ln_in is not None:            # (stats [rows,8,2] f32, colsum [N] f32, slots)
+        p.ln_in_stats, p.ln_colsum, p.ln_in_slots = ln_in[0].data_ptr(), ln_in[1].data_ptr(), ln_in[2]
+    if res_ln is not None:           # (stats, slots, gamma, beta)
+        p.res_stats, p.res_slots, p.res_gamma, p.res_beta = res_ln[0].data_ptr(), res_ln[1], res_ln[2].data_ptr(), res_ln[3].data_ptr()
+    if c2 is not None:
+        p.C2, p.c2_dtype, p.ldc2 = c2.data_ptr(), L.DT[c2.dtype], c2.shape[-1]
+    if out_stats is not None:
+        p.out_stats = out_stats.data_ptr()
+    p.ln_dim = ln_dim
     L.check(L.load().cst_gemm(C.byref(p), L.stream_ptr()))
     return C_
 

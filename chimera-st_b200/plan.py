@@ -94,6 +94,19 @@ class EncoderPlan:
         self.use_resident_posconv = os.environ.get("CST_POSCONV_RESIDENT", "1") != "0"
         self.use_conv0_tc = os.environ.get("CST_CONV0_TC", "1") != "0"
         self.use_stacked_posconv = os.environ.get("CST_POSCONV_STACKED", "1") != "0"
+        # LayerNorm fused around the GEMMs of the transformer layers (16-bit mode): CST_LN_FUSE=0 keeps the
+        # separate LayerNorm passes (A/B lever)
+        # CST_LN_FUSE: 0 = separate LayerNorm passes writing the fp32 row + the bf16 operand copy (round 1);
+        #   1 = "light" LayerNorm (default, 16-bit mode): the pass writes only the bf16 operand copy + {rstd, -mean*rstd} per row
+        #       and the next residual GEMM re-creates the fp32 normalised row in its epilogue (6 instead of 10 bytes per
+        #       element through HBM);  2 = LayerNorm fully fused around the GEMMs (statistics emitted by the producing
+        #       epilogue, normalisation applied after the consuming product): measured SLOWER than 0 on B200 -- the register-path
+        #       epilogue of the residual GEMMs has no headroom for a second output (profiles/SUMMARY_r02.md) -- kept as a lever.
+        mode = int(os.environ.get("CST_LN_FUSE", "1")) if act_dtype == torch.bfloat16 else 0
+        self.ln_fuse, self.ln_light = mode == 2, mode == 1
+        # memory stage (B*M rows): LayerNorm fused into weight-streaming linears (cst_dec_linear); CST_MEM_FUSED=0 keeps
+        # LayerNorm + tensor-core / FFMA GEMM launches
+        self.mem_fused = os.environ.get("CST_MEM_FUSED", "1") != "0"
         self.arena = arena if arena is not None else Arena(self.dev)
         f32, i32, i64, u8, f64 = torch.float32, torch.int32, torch.int64, torch.uint8, torch.float64
 
@@ -124,6 +137,7 @@ class EncoderPlan:
             ("feat", R, 512, f32), ("feat_ln", R, 512, act_dtype),
             # ---- wav2vec2 encoder: fp32 residual stream x, pre-LN sums y, GEMM-operand copy xa
             ("x", R, W2V_DIM, f32), ("y", R, W2V_DIM, f32), ("xa", R, W2V_DIM, act_dtype),
+            ("ln_stats0", R, 16, f32), ("ln_stats1", R, 16, f32),      # partial row statistics [row][8 slots]{sum, sum sq}
             ("xg", XG + SLACK, 64, act_dtype), ("qkv", R, 3 * W2V_DIM, act_dtype),
             ("ctx", R, W2V_DIM, act_dtype), ("ffn", R, W2V_FFN, act_dtype), ("w2v_out", R, W2V_DIM, f32),
             # ---- subsampler operands (zero-padded: re-zeroed every run)
@@ -170,7 +184,11 @@ class EncoderPlan:
     # ------------------------------------------------------------------ launch helpers
     def _gemm(self, A, W, C_, M, N, K, lda, a_rows, bias=None, residual=None, act=L.ACT_NONE, alpha=1.0,
               rows_per_seg=None, seg_rows_valid=None, out_rows_per_seg=None, out_row_off=0, seg_len=None,
-              ldc=None, nb_outer=1, nb_inner=1, a_bs=(0, 0), w_bs=0, c_bs=(0, 0), bias_bs=0):
+              ldc=None, nb_outer=1, nb_inner=1, a_bs=(0, 0), w_bs=0, c_bs=(0, 0), bias_bs=0,
+              ln_in=None, res_ln=None, c2=None, out_stats=None, ln_dim=0):
+        """ln_in = (stats, colsum, slots): LayerNorm of the A rows applied after the product; res_ln = (stats, slots, gamma,
+        beta): the residual rows are normalised on the fly; c2: bf16 copy of the output; out_stats: partial statistics of the
+        output rows (cst_gemm_params, "LayerNorm fused around the GEMM")."""
         p = L.GemmParams()
         p.A, p.W, p.bias, p.residual, p.C = A.data_ptr(), W.data_ptr(), L.ptr(bias), L.ptr(residual), C_.data_ptr()
         p.ab_dtype, p.c_dtype = L.DT[A.dtype], L.DT[C_.dtype]
@@ -193,13 +211,23 @@ class EncoderPlan:
         p.out_row_off = out_row_off
         p.seg_len = L.ptr(seg_len)
         p.segs_per_outer = 1
+        if ln_in is not None:
+            p.ln_in_stats, p.ln_colsum, p.ln_in_slots = ln_in[0].data_ptr(), ln_in[1].data_ptr(), ln_in[2]
+        if res_ln is not None:
+            p.res_stats, p.res_slots = res_ln[0].data_ptr(), res_ln[1]
+            p.res_gamma, p.res_beta = res_ln[2].data_ptr(), res_ln[3].data_ptr()
+        if c2 is not None:
+            p.C2, p.c2_dtype, p.ldc2 = c2.data_ptr(), L.DT[c2.dtype], c2.shape[1]
+        if out_stats is not None:
+            p.out_stats = out_stats.data_ptr()
+        p.ln_dim = ln_dim
         L.check(self.lib.cst_gemm(C.byref(p), self.st))
         self.launches += 1
 
-    def _linear(self, A, W, b, C_, rows, act=L.ACT_NONE, residual=None, alpha=1.0):
+    def _linear(self, A, W, b, C_, rows, act=L.ACT_NONE, residual=None, alpha=1.0, **ln):
         """C[rows, N] = act(A[rows, K] W^T + b) * alpha (+ residual); dense row-major operands."""
         N, K = W.shape
-        self._gemm(A, W, C_, rows, N, K, lda=A.shape[1], a_rows=A.shape[0], bias=b, residual=residual, act=act, alpha=alpha)
+        self._gemm(A, W, C_, rows, N, K, lda=A.shape[1], a_rows=A.shape[0], bias=b, residual=residual, act=act, alpha=alpha, **ln)
 
     def _ln(self, x, gb, rows, out_f32=None, out_lp=None, rows_per_seg=None, seg_rows_valid=None,
             out_rows_per_seg=None, out_row_off=0, zero_invalid=0):
@@ -210,6 +238,27 @@ class EncoderPlan:
             x.data_ptr(), Cdim, gb[0].data_ptr(), gb[1].data_ptr(), L.ptr(out_f32), L.ptr(out_lp), lp_dt, Cdim,
             rows, Cdim, rps, seg_rows_valid if seg_rows_valid is not None else rps,
             out_rows_per_seg if out_rows_per_seg is not None else rps, out_row_off, zero_invalid, self.st))
+        self.launches += 1
+
+    def _ln_ab(self, x, gb, rows, out_lp, ab):
+        Cdim = x.shape[1]
+        L.check(self.lib.cst_layernorm_ab(x.data_ptr(), Cdim, gb[0].data_ptr(), gb[1].data_ptr(), out_lp.data_ptr(),
+                                          L.DT[out_lp.dtype], Cdim, ab.data_ptr(), rows, Cdim, self.st))
+        self.launches += 1
+
+    def _skinny(self, A, W, b, out, rows, ln=None, residual=None, act=L.ACT_NONE):
+        """out[rows, N] = act(LN?(A) W^T + b) (+ residual) through the weight-streaming linear of the decoder kernels
+        (cst_dec_linear): LayerNorm fused into the A-row load, for the few (B*M) rows of the memory stage."""
+        N, K = W.shape
+        p = L.DecLinearParams()
+        p.A, p.W, p.bias, p.residual = A.data_ptr(), W.data_ptr(), L.ptr(b), L.ptr(residual)
+        p.ln_gamma, p.ln_beta = (ln[0].data_ptr(), ln[1].data_ptr()) if ln is not None else (0, 0)
+        p.lda, p.ldr = A.shape[1], (residual.shape[1] if residual is not None else 0)
+        p.out[0], p.out_dtype[0], p.ldo[0] = out.data_ptr(), L.DT[out.dtype], out.shape[1]
+        p.step = 0
+        p.a_dtype, p.w_dtype = L.DT[A.dtype], L.DT[W.dtype]
+        p.M, p.N, p.K, p.n_seg, p.act = rows, N, K, 1, act
+        L.check(self.lib.cst_dec_linear(C.byref(p), self.st))
         self.launches += 1
 
     def _attn(self, q, k, v, out, ldq, ldkv, H, n_q, q_rps, n_kv, kv_rps, kv_len, seg=None, totals=None):
@@ -291,8 +340,15 @@ class EncoderPlan:
         self.sub_mid.zero_()
         self.launches += 2
         es = self.qkv.element_size()
+        fuse = self.ln_fuse
+        st_cur, st_nxt = self.ln_stats0, self.ln_stats1      # statistics of the rows in y: read by consumers / written by producers
+        SL = 2 * (D // 256)                                   # statistics slots per row (one per 128-column slice)
         for i, lw in enumerate(P["w2v_layers"]):
-            self._linear(self.xa, lw["qkv_w"], lw["qkv_b"], self.qkv, R)
+            if fuse and i > 0:
+                # xa = bf16(y) of the previous layer's fc2: its LayerNorm (LN2 of layer i-1) is applied after the product
+                self._linear(self.xa, lw["qkvL_w"], lw["qkvL_b"], self.qkv, R, ln_in=(st_cur, lw["qkvL_cs"], SL), ln_dim=D)
+            else:
+                self._linear(self.xa, lw["qkv_w"], lw["qkv_b"], self.qkv, R)
             qp = self.qkv.data_ptr()
             # all allocated query rows are computed (rows >= T' are finite filler, never read as keys):
             # no buffer row is ever left stale, so masked keys always meet finite V rows
@@ -302,12 +358,38 @@ class EncoderPlan:
             else:
                 self._attn(qp, qp + D * es, qp + 2 * D * es, self.ctx, 3 * D, 3 * D, W2V_HEADS,
                            max_q, None, max_kv, None, self.w2v_valid, seg=self.seg_w2v, totals=(R, R))
-            self._linear(self.ctx, lw["o_w"], lw["o_b"], self.y, R, residual=self.x)
-            self._ln(self.y, (lw["ln1_g"], lw["ln1_b"]), R, out_f32=self.x, out_lp=self.xa)
-            self._linear(self.xa, lw["fc1_w"], lw["fc1_b"], self.ffn, R, act=L.ACT_GELU)
-            self._linear(self.ffn, lw["fc2_w"], lw["fc2_b"], self.y, R, residual=self.x)
+            if self.ln_light:
+                # light LayerNorm: y -> xa (bf16, normalised) + ab; the fp32 normalised row only ever exists inside the next
+                # residual GEMM's epilogue.  ab buffers alternate (the residual GEMM reads one while nothing writes it).
+                prev = P["w2v_layers"][i - 1] if i > 0 else None
+                self._linear(self.ctx, lw["o_w"], lw["o_b"], self.y, R, residual=self.x if i == 0 else self.y,
+                             res_ln=None if i == 0 else (self.ln_stats1, 0, prev["ln2_g"], prev["ln2_b"]), ln_dim=D)
+                self._ln_ab(self.y, (lw["ln1_g"], lw["ln1_b"]), R, self.xa, self.ln_stats0)
+                self._linear(self.xa, lw["fc1_w"], lw["fc1_b"], self.ffn, R, act=L.ACT_GELU)
+                self._linear(self.ffn, lw["fc2_w"], lw["fc2_b"], self.y, R, residual=self.y,
+                             res_ln=(self.ln_stats0, 0, lw["ln1_g"], lw["ln1_b"]), ln_dim=D)
+            elif fuse:
+                # y <- LN_prev(y) + ctx Wo^T + bo in place (layer 0: the explicit LayerNorm output x), bf16 copy -> xa,
+                # partial statistics of the new y -> st_nxt; then fc1 normalises lazily (LN1), fc2 closes the layer the same way
+                prev = P["w2v_layers"][i - 1] if i > 0 else None
+                self._linear(self.ctx, lw["o_w"], lw["o_b"], self.y, R, residual=self.x if i == 0 else self.y,
+                             res_ln=None if i == 0 else (st_cur, SL, prev["ln2_g"], prev["ln2_b"]),
+                             c2=self.xa, out_stats=st_nxt, ln_dim=D)
+                st_cur, st_nxt = st_nxt, st_cur
+                self._linear(self.xa, lw["fc1L_w"], lw["fc1L_b"], self.ffn, R, act=L.ACT_GELU, ln_in=(st_cur, lw["fc1L_cs"], SL), ln_dim=D)
+                self._linear(self.ffn, lw["fc2_w"], lw["fc2_b"], self.y, R, residual=self.y,
+                             res_ln=(st_cur, SL, lw["ln1_g"], lw["ln1_b"]), c2=self.xa, out_stats=st_nxt, ln_dim=D)
+                st_cur, st_nxt = st_nxt, st_cur
+            else:
+                self._linear(self.ctx, lw["o_w"], lw["o_b"], self.y, R, residual=self.x)
+                self._ln(self.y, (lw["ln1_g"], lw["ln1_b"]), R, out_f32=self.x, out_lp=self.xa)
+                self._linear(self.xa, lw["fc1_w"], lw["fc1_b"], self.ffn, R, act=L.ACT_GELU)
+                self._linear(self.ffn, lw["fc2_w"], lw["fc2_b"], self.y, R, residual=self.x)
             if i + 1 < len(P["w2v_layers"]):
-                self._ln(self.y, (lw["ln2_g"], lw["ln2_b"]), R, out_f32=self.x, out_lp=self.xa)
+                if self.ln_light:
+                    self._ln_ab(self.y, (lw["ln2_g"], lw["ln2_b"]), R, self.xa, self.ln_stats1)
+                elif not fuse:
+                    self._ln(self.y, (lw["ln2_g"], lw["ln2_b"]), R, out_f32=self.x, out_lp=self.xa)
             else:
                 # last layer: the LN output is (a) the wav2vec2 feature [B,T',768] and (b) the subsampler's
                 # zero-padded operand (2 leading zero frames, zeros from frame T' on)
@@ -344,9 +426,17 @@ class EncoderPlan:
         g0 = self.gs[0]
         max_q, max_kv = max(g.T2a for g in self.gs), max(g.T2 for g in self.gs)
         es = self.qkv2.element_size()
-        for lw in P["enc_layers"]:
-            self._ln(self.x2, (lw["ln1_g"], lw["ln1_b"]), R2, out_lp=self.x2a)
-            self._linear(self.x2a, lw["qkv_w"], lw["qkv_b"], self.qkv2, R2)
+        fuse = self.ln_fuse
+        if fuse:
+            st_cur, st_nxt = self.ln_stats0[:R2], self.ln_stats1[:R2]
+        SL = 2 * (D // 256)
+        for i, lw in enumerate(P["enc_layers"]):
+            if fuse and i > 0:
+                # pre-LN: x2a = bf16(x2) (un-normalised residual stream); LN1 is applied after the product
+                self._linear(self.x2a, lw["qkvL_w"], lw["qkvL_b"], self.qkv2, R2, ln_in=(st_cur, lw["qkvL_cs"], SL), ln_dim=D)
+            else:
+                self._ln(self.x2, (lw["ln1_g"], lw["ln1_b"]), R2, out_lp=self.x2a)
+                self._linear(self.x2a, lw["qkv_w"], lw["qkv_b"], self.qkv2, R2)
             qp = self.qkv2.data_ptr()
             if self.seg_enc is None:
                 self._attn(qp, qp + D * es, qp + 2 * D * es, self.ctx2, 3 * D, 3 * D, ENC_HEADS,
@@ -354,10 +444,17 @@ class EncoderPlan:
             else:
                 self._attn(qp, qp + D * es, qp + 2 * D * es, self.ctx2, 3 * D, 3 * D, ENC_HEADS,
                            max_q, None, max_kv, None, self.sub_valid, seg=self.seg_enc, totals=(R2, R2))
-            self._linear(self.ctx2, lw["o_w"], lw["o_b"], self.x2, R2, residual=self.x2)
-            self._ln(self.x2, (lw["ln2_g"], lw["ln2_b"]), R2, out_lp=self.x2a)
-            self._linear(self.x2a, lw["fc1_w"], lw["fc1_b"], self.ffn2, R2, act=L.ACT_RELU)
-            self._linear(self.ffn2, lw["fc2_w"], lw["fc2_b"], self.x2, R2, residual=self.x2)
+            if fuse:
+                self._linear(self.ctx2, lw["o_w"], lw["o_b"], self.x2, R2, residual=self.x2, c2=self.x2a, out_stats=st_nxt, ln_dim=D)
+                st_cur, st_nxt = st_nxt, st_cur
+                self._linear(self.x2a, lw["fc1L_w"], lw["fc1L_b"], self.ffn2, R2, act=L.ACT_RELU, ln_in=(st_cur, lw["fc1L_cs"], SL), ln_dim=D)
+                self._linear(self.ffn2, lw["fc2_w"], lw["fc2_b"], self.x2, R2, residual=self.x2, c2=self.x2a, out_stats=st_nxt, ln_dim=D)
+                st_cur, st_nxt = st_nxt, st_cur
+            else:
+                self._linear(self.ctx2, lw["o_w"], lw["o_b"], self.x2, R2, residual=self.x2)
+                self._ln(self.x2, (lw["ln2_g"], lw["ln2_b"]), R2, out_lp=self.x2a)
+                self._linear(self.x2a, lw["fc1_w"], lw["fc1_b"], self.ffn2, R2, act=L.ACT_RELU)
+                self._linear(self.ffn2, lw["fc2_w"], lw["fc2_b"], self.x2, R2, residual=self.x2)
         self._ln(self.x2, (P["ln_out_g"], P["ln_out_b"]), R2, out_f32=self.h_enc)
 
     def _stage_memory(self):
@@ -373,10 +470,14 @@ class EncoderPlan:
         nl = len(P["mem_layers"])
         self._ln(self.h_enc, (P["unit_g"], P["unit_b"]), R2, out_lp=self.kv_in)
         self._linear(self.kv_in, P["mem_kv_w"], P["mem_kv_b"], self.kv, R2)
+        fused = self.mem_fused
         for i, lw in enumerate(P["mem_layers"]):
             ln1 = (lw["ln1_g"], lw["ln1_b"])
-            self._ln(self.mem, ln1, RM, out_lp=self.mem_a)              # the layer's pre-LN on the M queries
-            self._linear(self.mem_a, lw["q_w"], lw["q_b"], self.mq, RM)
+            if fused:       # LN1 inside the q projection's row load (no LayerNorm launch, no normalised copy in HBM)
+                self._skinny(self.mem, lw["q_w"], lw["q_b"], self.mq, RM, ln=ln1)
+            else:
+                self._ln(self.mem, ln1, RM, out_lp=self.mem_a)          # the layer's pre-LN on the M queries
+                self._linear(self.mem_a, lw["q_w"], lw["q_b"], self.mq, RM)
             kp = self.kv.data_ptr() + i * 2 * D * es
             # memories attend ALL T2 frames: the reference passes an all-False key-padding mask here
             if self.seg_mem is None:
@@ -384,10 +485,15 @@ class EncoderPlan:
             else:
                 self._attn(self.mq.data_ptr(), kp, kp + D * es, self.mctx, D, 2 * D * nl, ENC_HEADS, M, None,
                            max(g.T2 for g in self.gs), None, None, seg=self.seg_mem, totals=(RM, R2))
-            self._linear(self.mctx, lw["o_w"], lw["o_b"], self.mem, RM, residual=self.mem)
-            self._ln(self.mem, (lw["ln2_g"], lw["ln2_b"]), RM, out_lp=self.mem_a)
-            self._linear(self.mem_a, lw["fc1_w"], lw["fc1_b"], self.mffn, RM, act=L.ACT_RELU)
-            self._linear(self.mffn, lw["fc2_w"], lw["fc2_b"], self.mem, RM, residual=self.mem)
+            if fused:
+                self._skinny(self.mctx, lw["o_w"], lw["o_b"], self.mem, RM, residual=self.mem)
+                self._skinny(self.mem, lw["fc1_w"], lw["fc1_b"], self.mffn, RM, ln=(lw["ln2_g"], lw["ln2_b"]), act=L.ACT_RELU)
+                self._skinny(self.mffn, lw["fc2_w"], lw["fc2_b"], self.mem, RM, residual=self.mem)
+            else:
+                self._linear(self.mctx, lw["o_w"], lw["o_b"], self.mem, RM, residual=self.mem)
+                self._ln(self.mem, (lw["ln2_g"], lw["ln2_b"]), RM, out_lp=self.mem_a)
+                self._linear(self.mem_a, lw["fc1_w"], lw["fc1_b"], self.mffn, RM, act=L.ACT_RELU)
+                self._linear(self.mffn, lw["fc2_w"], lw["fc2_b"], self.mem, RM, residual=self.mem)
 
     def _issue(self, upto="memory"):
         self.st = L.stream_ptr() if self.dev.type == "cuda" else 0
@@ -495,6 +601,8 @@ class TextPlan(EncoderPlan):
         self.gs, self.groups, self.Bt, self.M = [g], [(B, T)], B, M
         self.utt0, self.r2_0, self.R2 = [0], [0], B * g.T2a
         self.seg_w2v = self.seg_enc = self.seg_mem = None
+        self.ln_fuse = self.ln_light = False            # the text branch keeps the separate LayerNorm passes
+        self.mem_fused = os.environ.get("CST_MEM_FUSED", "1") != "0"
         self.dev = device or torch.device("cuda", torch.cuda.current_device())
         self.act = act_dtype
         self.act_code = L.DT[act_dtype]

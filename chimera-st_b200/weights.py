@@ -87,6 +87,8 @@ def prepare(state_dict, device, act_dtype, conv_dtype=None):
         wv, bv = sd[a + "v_proj.weight"].float(), sd[a + "v_proj.bias"].float()
         if fused_qkv:
             d["qkv_w"], d["qkv_b"] = op(torch.cat((wq, wk, wv), 0)), f32(torch.cat((bq, bk, bv), 0))
+            d["_qkv_raw"] = (torch.cat((wq, wk, wv), 0), torch.cat((bq, bk, bv), 0))       # fp32 masters for fold_ln, dropped below
+            d["_fc1_raw"] = (sd[prefix + "fc1.weight"].float(), sd[prefix + "fc1.bias"].float())
         else:
             d["q_w"], d["q_b"] = op(wq), f32(bq)
             d["kv_w"], d["kv_b"] = op(torch.cat((wk, wv), 0)), f32(torch.cat((bk, bv), 0))
@@ -97,6 +99,18 @@ def prepare(state_dict, device, act_dtype, conv_dtype=None):
         d["ln2_g"], d["ln2_b"] = f32(sd[prefix + "final_layer_norm.weight"]), f32(sd[prefix + "final_layer_norm.bias"])
         return d
 
+    def fold_ln(d, name, gamma, beta):
+        """LayerNorm folded around a projection for the fused-LayerNorm GEMM epilogue (cst_gemm_params.ln_in_stats):
+        LN(y; g, b) W^T + c = rstd * (y (W diag g)^T) - rstd*mean * colsum(W diag g) + (W b + c).  The GEMM multiplies
+        the bf16 copy of the UN-normalised rows by W' = W diag g; colsum is taken over the ROUNDED W' (what the tensor
+        cores really multiply), so the mean term cancels exactly what the product contains."""
+        w, c = (t.double().cpu() for t in d["_" + name + "_raw"])
+        g64, b64 = gamma.double().cpu(), beta.double().cpu()
+        wf = (w * g64[None, :]).float().to(act_dtype)
+        d[name + "L_w"] = wf.to(device).contiguous()
+        d[name + "L_cs"] = wf.double().sum(1).float().to(device).contiguous()
+        d[name + "L_b"] = (c + w @ b64).float().to(device).contiguous()
+
     P["w2v_layers"] = [layer(W + f"encoder.layers.{i}.") for i in range(W2V_LAYERS)]
     for i in range(2):
         w = sd[f"subsample.conv_layers.{i}.weight"].float()        # [1024, Cin, 5]
@@ -104,6 +118,20 @@ def prepare(state_dict, device, act_dtype, conv_dtype=None):
         P[f"sub{i}_w"] = op(_glu_interleave(w))
         P[f"sub{i}_b"] = f32(_glu_interleave(sd[f"subsample.conv_layers.{i}.bias"].float()))
     P["enc_layers"] = [layer(f"transformer_layers.{i}.") for i in range(ENC_LAYERS)]
+    if act_dtype != torch.float32:
+        # fused-LayerNorm variants (16-bit mode): post-LN wav2vec2 layers -- QKV of layer i consumes LN2 of layer i-1, fc1
+        # consumes LN1 of its own layer; pre-LN shared layers -- QKV consumes LN1, fc1 consumes LN2 of their own layer
+        for i, d in enumerate(P["w2v_layers"]):
+            if i > 0:
+                fold_ln(d, "qkv", P["w2v_layers"][i - 1]["ln2_g"], P["w2v_layers"][i - 1]["ln2_b"])
+            fold_ln(d, "fc1", d["ln1_g"], d["ln1_b"])
+        for i, d in enumerate(P["enc_layers"]):
+            if i > 0:
+                fold_ln(d, "qkv", d["ln1_g"], d["ln1_b"])
+            fold_ln(d, "fc1", d["ln2_g"], d["ln2_b"])
+    for d in P["w2v_layers"] + P["enc_layers"]:
+        d.pop("_qkv_raw", None)
+        d.pop("_fc1_raw", None)
     P["ln_out_g"], P["ln_out_b"] = f32(sd["layer_norm.weight"]), f32(sd["layer_norm.bias"])
     P["mem_embed"] = f32(sd["interlingua_embedding.weight"])
     if "text_embed_tokens.weight" in sd:                       # text (MT) branch input, interlingua:216

@@ -104,6 +104,24 @@ typedef struct cst_gemm_params {
   int bias_bs_inner;
   int rows_per_seg, seg_rows_valid; long long out_rows_per_seg; int out_row_off;
   const int32_t* seg_len; int segs_per_outer;
+  /* ---- LayerNorm fused AROUND the GEMM (tensor-core path, identity row mapping, unbatched; all NULL / 0 = plain GEMM).
+   * Replaces the separate LayerNorm passes of the post-LN wav2vec2 layers (wav2vec2.py:937-957) and of the pre-LN shared
+   * layers (transformer_layer.py:129-155).  Row statistics travel as PARTIAL sums: stats[row*8 + slot] = {sum, sum of
+   * squares} of one 128-column slice of an fp32 row (slot = 2 * n-tile + column half), written by the GEMM that produces
+   * the row (out_stats) and added up by the GEMMs that consume it; mean / rstd (eps 1e-5) are formed on the fly.
+   *   ln_in_stats : the A operand is the bf16 copy of UN-normalised rows; the epilogue applies their LayerNorm after the
+   *                 product: v = rstd*(acc - mean*ln_colsum[n]) + bias[n], with gamma folded into W and W.beta into bias
+   *                 by the caller (ln_colsum[n] = sum_k W'[n,k]).  Bulk-store epilogue only (no residual).
+   *   res_stats   : the residual rows are UN-normalised; the epilogue adds LayerNorm(residual)*res_gamma + res_beta.
+ *                 res_slots == 0: res_stats holds one finished {rstd, -mean*rstd} pair per row (cst_layernorm_ab).
+   *   C2          : second copy of the output in c2_dtype (the next GEMM's bf16 operand), row stride ldc2.
+   *   out_stats   : partial statistics of the fp32 output rows.  res_stats / C2 / out_stats need an fp32 C with a
+   *                 residual (which may be C itself: in-place update of the residual stream). */
+  const float* ln_in_stats; const float* ln_colsum; int ln_in_slots;
+  const float* res_stats; int res_slots; const float* res_gamma; const float* res_beta;
+  void* C2; int c2_dtype; long long ldc2;
+  float* out_stats;
+  int ln_dim;                    /* width of the normalised rows (K for ln_in_stats, N for res_stats / out_stats) */
 } cst_gemm_params;
 int cst_gemm(const cst_gemm_params* p, void* stream);
 
@@ -116,6 +134,13 @@ int cst_layernorm(const float* x, long long ldx, const float* gamma, const float
                   float* out_f32, void* out_lp, int lp_dtype, long long ldo,
                   int rows, int C, int rows_per_seg, int seg_rows_valid,
                   long long out_rows_per_seg, int out_row_off, int zero_invalid, void* stream);
+
+/* "Light" LayerNorm of the post-LN wav2vec2 layers (16-bit mode): writes only the bf16 operand copy of the normalised rows and
+ * ab_out[row] = {rstd, -mean*rstd}; the fp32 normalised rows are re-created by the next residual GEMM's epilogue
+ * (cst_gemm_params.res_stats, res_slots == 0) instead of making a round trip through HBM.  Same reference lines as
+ * cst_layernorm (wav2vec2.py:945,957). */
+int cst_layernorm_ab(const float* x, long long ldx, const float* gamma, const float* beta, void* out_lp, int lp_dtype,
+                     long long ldo, float* ab_out, int rows, int C, void* stream);
 
 /* Generic dtype/layout copy x[rows, C] -> y: used for (a) the pos-conv operand layout
  * [B, 16 groups, Tpad, 64] (48 channels + 16 zero lanes, 64 zero frames each side) and (b) broadcasting

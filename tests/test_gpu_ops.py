@@ -217,6 +217,78 @@ def test_attention(dtype, tol, B, H, Tq, Tk, masked):
     assert rel_l2(out.cpu().float(), ref) < tol, rel_l2(out.cpu().float(), ref)
 
 
+@pytest.mark.parametrize("M,N,K,lazy_res,inplace", [(300, 768, 768, True, True), (300, 768, 3072, True, True), (20000, 768, 768, True, True),
+                                                    (517, 512, 512, False, True), (130, 768, 768, False, False), (16500, 512, 2048, False, True)])
+def test_gemm_fused_layernorm_producer(M, N, K, lazy_res, inplace):
+    """out-proj / fc2 with the LayerNorm fused around the GEMM: y <- LN(y_prev)*g + b (from partial statistics, or the plain
+    residual) + A W^T + bias, in place; a bf16 copy; partial statistics of the new rows.  Checked against torch in fp64 on
+    the bf16-rounded operands (single-CTA and CTA-pair kernels: M on both sides of 16384)."""
+    g = torch.Generator().manual_seed(M + N + K)
+    A = (torch.randn(M, K, generator=g) * 0.7).to(torch.bfloat16)
+    W = (torch.randn(N, K, generator=g) * 0.03).to(torch.bfloat16)
+    bias = torch.randn(N, generator=g) * 0.1
+    yprev = torch.randn(M, N, generator=g) * 1.7 + 0.4
+    gamma, beta = 1 + 0.2 * torch.randn(N, generator=g), 0.1 * torch.randn(N, generator=g)
+    slots = 2 * (N // 256)
+    # partial statistics of yprev as a producer would have written them: per 128-column slice {sum, sum of squares}
+    st_in = torch.zeros(M, 8, 2)
+    for sidx in range(slots):
+        blk = yprev[:, 128 * sidx:128 * (sidx + 1)].double()
+        st_in[:, sidx, 0], st_in[:, sidx, 1] = blk.sum(1).float(), (blk * blk).sum(1).float()
+    res = torch.nn.functional.layer_norm(yprev.double(), (N,), gamma.double(), beta.double(), 1e-5) if lazy_res else yprev.double()
+    ref = A.float().double() @ W.float().double().T + bias.double() + res
+    yd = yprev.to(DEV).clone()
+    out = yd if inplace else torch.empty(M, N, device=DEV)
+    c2 = torch.zeros(M, N, dtype=torch.bfloat16, device=DEV)
+    st_out = torch.full((M, 8, 2), -1.0, device=DEV)
+    ops().gemm(A.to(DEV), W.to(DEV), out, M, N, K, lda=K, a_rows=M, bias=bias.to(DEV), residual=yd,
+               res_ln=(st_in.to(DEV), slots, gamma.to(DEV), beta.to(DEV)) if lazy_res else None, c2=c2, out_stats=st_out, ln_dim=N)
+    torch.cuda.synchronize()
+    got = out.cpu().double()
+    assert rel_l2(got, ref) < 5e-6, rel_l2(got, ref)
+    assert torch.equal(c2.cpu(), out.cpu().to(torch.bfloat16))
+    so = st_out.cpu().double()
+    assert float((so[:, :slots, 0].sum(1) - got.sum(1)).abs().max()) < 2e-3
+    assert float(((so[:, :slots, 1].sum(1) - (got * got).sum(1)) / (got * got).sum(1)).abs().max()) < 2e-6
+    for sidx in range(slots):                               # every slot is one 128-column slice
+        assert float((so[:, sidx, 0] - got[:, 128 * sidx:128 * (sidx + 1)].sum(1)).abs().max()) < 1e-3
+    assert bool((so[:, slots:] == -1.0).all())
+
+
+@pytest.mark.parametrize("M,N,K,act", [(300, 2304, 768, 0), (20000, 3072, 768, 1), (517, 1536, 512, 0), (130, 2048, 512, 2)])
+def test_gemm_fused_layernorm_consumer(M, N, K, act):
+    """QKV / fc1 on the bf16 copy of UN-normalised rows, LayerNorm applied after the product from the partial statistics:
+    rstd*(y W'^T) - rstd*mean*colsum(W') + c  ==  act(LN(y; g, b) W^T + bias)."""
+    g = torch.Generator().manual_seed(M + N)
+    y = torch.randn(M, K, generator=g) * 1.5 + 0.3
+    W = torch.randn(N, K, generator=g) * 0.04
+    bias = torch.randn(N, generator=g) * 0.1
+    gamma, beta = 1 + 0.2 * torch.randn(K, generator=g), 0.1 * torch.randn(K, generator=g)
+    slots = 2 * (K // 256)
+    st = torch.zeros(M, 8, 2)
+    for sidx in range(slots):
+        blk = y[:, 128 * sidx:128 * (sidx + 1)].double()
+        st[:, sidx, 0], st[:, sidx, 1] = blk.sum(1).float(), (blk * blk).sum(1).float()
+    Wf = (W.double() * gamma.double()[None, :]).float().to(torch.bfloat16)
+    cs = Wf.double().sum(1).float()
+    cb = (bias.double() + W.double() @ beta.double()).float()
+    ya = y.to(torch.bfloat16)
+    # what the kernel computes, in fp64, on the rounded operands
+    mean, var = y.double().mean(1, keepdim=True), y.double().var(1, unbiased=False, keepdim=True)
+    rstd = (var + 1e-5).rsqrt()
+    z = rstd * (ya.float().double() @ Wf.float().double().T) - rstd * mean * cs.double()[None, :] + cb.double()[None, :]
+    ref = {0: z, 1: torch.nn.functional.gelu(z), 2: torch.relu(z)}[act]
+    out = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    ops().gemm(ya.to(DEV), Wf.to(DEV), out, M, N, K, lda=K, a_rows=M, bias=cb.to(DEV), act=act,
+               ln_in=(st.to(DEV), cs.to(DEV), slots), ln_dim=K)
+    torch.cuda.synchronize()
+    assert rel_l2(out.cpu().float(), ref) < 3e-3, rel_l2(out.cpu().float(), ref)
+    # and it IS the LayerNorm'ed projection (up to bf16 rounding of operands / output)
+    true = torch.nn.functional.layer_norm(y.double(), (K,), gamma.double(), beta.double(), 1e-5) @ W.double().T + bias.double()
+    true = {0: true, 1: torch.nn.functional.gelu(true), 2: torch.relu(true)}[act]
+    assert rel_l2(out.cpu().float(), true) < 8e-3, rel_l2(out.cpu().float(), true)
+
+
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-6), (torch.bfloat16, 6e-3)])
 @pytest.mark.parametrize("H,segs,masked", [
     (12, [(749, 749), (300, 290), (1499, 1499), (128, 100), (257, 256)], True),      # wav2vec2 stage: q rows >= kv rows
