@@ -35,7 +35,7 @@ class GemmParams(C.Structure):
         ("ln_in_stats", C.c_void_p), ("ln_colsum", C.c_void_p), ("ln_in_slots", C.c_int),
         ("res_stats", C.c_void_p), ("res_slots", C.c_int), ("res_gamma", C.c_void_p), ("res_beta", C.c_void_p),
         ("C2", C.c_void_p), ("c2_dtype", C.c_int), ("ldc2", C.c_longlong),
-        ("out_stats", C.c_void_p), ("ln_dim", C.c_int),
+        ("out_stats", C.c_void_p), ("ln_dim", C.c_int), ("exact_act", C.c_int), ("acc_scale", C.c_float),
     ]
 
 
@@ -78,6 +78,7 @@ _SIGS = {
     "cst_layernorm": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                 C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_int,
                                 C.c_void_p]),
+    "cst_split_f16": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p]),
     "cst_layernorm_ab": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p,
                                    C.c_int, C.c_int, C.c_void_p]),
     "cst_posconv_pack": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),

@@ -22,6 +22,8 @@ struct GemmDev {          // device copy of cst_gemm_params (pointers already ty
   __nv_bfloat16* C2; long long ldc2;
   float2* out_stats;
   float ln_inv_dim;
+  int exact_act;
+  float acc_scale;
 };
 
 // {rstd, -mean * rstd} of one row from its partial sums (sum, sum of squares per 128-column slice), eps 1e-5

@@ -141,6 +141,9 @@ extern "C" int cst_gemm(const cst_gemm_params* hp, void* stream) {
   p.C2 = reinterpret_cast<__nv_bfloat16*>(hp->C2); p.ldc2 = hp->ldc2;
   p.out_stats = reinterpret_cast<float2*>(hp->out_stats);
   p.ln_inv_dim = hp->ln_dim > 0 ? 1.0f / (float)hp->ln_dim : 0.f;
+  p.exact_act = hp->exact_act;
+  p.acc_scale = hp->acc_scale == 0.f ? 1.0f : hp->acc_scale;
+  CST_REQUIRE(p.acc_scale == 1.0f || hp->ab_dtype != CST_F32, "cst_gemm: acc_scale is a tensor-core path parameter");
   const bool ln_fused = hp->ln_in_stats || hp->res_stats || hp->C2 || hp->out_stats;
   if (ln_fused) {
     CST_REQUIRE(hp->ab_dtype == CST_BF16 || hp->ab_dtype == CST_F16, "cst_gemm: fused LayerNorm needs the tensor-core path (16-bit operands)");

@@ -161,6 +161,7 @@ __device__ __forceinline__ void epi_tile_fast(const GemmDev& p, float* patch, ui
     }
     if (col_ok && !TC_DBG(2)) {
       const uint64_t b01 = pk2(b_cur.x, b_cur.y), b23 = pk2(b_cur.z, b_cur.w);
+      const uint64_t sc2 = pk2(p.acc_scale, p.acc_scale);
 #pragma unroll
       for (int i0 = 0; i0 < 8; i0 += 4) {
         float v[4][4];
@@ -168,12 +169,15 @@ __device__ __forceinline__ void epi_tile_fast(const GemmDev& p, float* patch, ui
         for (int u = 0; u < 4; ++u) {
           const int rr = (i0 + u) * 4 + lr;
           const float4 a4 = *reinterpret_cast<const float4*>(&patch[rr * TC_PATCH_LD + 4 * ((lc >> 2) ^ (rr & 7))]);
-          upk2(fadd2(pk2(a4.x, a4.y), b01), v[u][0], v[u][1]);
-          upk2(fadd2(pk2(a4.z, a4.w), b23), v[u][2], v[u][3]);
+          upk2(ffma2(pk2(a4.x, a4.y), sc2, b01), v[u][0], v[u][1]);
+          upk2(ffma2(pk2(a4.z, a4.w), sc2, b23), v[u][2], v[u][3]);
         }
         if (ACT == CST_ACT_GELU) {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) { gelu2(v[u][0], v[u][1]); gelu2(v[u][2], v[u][3]); }
+          for (int u = 0; u < 4; ++u) {
+            if (p.exact_act) { v[u][0] = gelu_erf(v[u][0]); v[u][1] = gelu_erf(v[u][1]); v[u][2] = gelu_erf(v[u][2]); v[u][3] = gelu_erf(v[u][3]); }
+            else { gelu2(v[u][0], v[u][1]); gelu2(v[u][2], v[u][3]); }
+          }
         } else if (ACT == CST_ACT_RELU) {
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
@@ -294,16 +298,24 @@ __device__ __forceinline__ void epi_tile_bulk(const GemmDev& p, const CUtensorMa
         upk2(ffma2(pk2(v[4 * i + 2], v[4 * i + 3]), ln_a2, ffma2(ln_b2, pk2(cs.z, cs.w), pk2(bv.z, bv.w))), v[4 * i + 2], v[4 * i + 3]);
       }
     } else if (bias) {                                         // same address in every lane: one broadcast transaction each
+      const uint64_t sc2 = pk2(p.acc_scale, p.acc_scale);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + n0) + i);
-        upk2(fadd2(pk2(v[4 * i], v[4 * i + 1]), pk2(bv.x, bv.y)), v[4 * i], v[4 * i + 1]);
-        upk2(fadd2(pk2(v[4 * i + 2], v[4 * i + 3]), pk2(bv.z, bv.w)), v[4 * i + 2], v[4 * i + 3]);
+        upk2(ffma2(pk2(v[4 * i], v[4 * i + 1]), sc2, pk2(bv.x, bv.y)), v[4 * i], v[4 * i + 1]);
+        upk2(ffma2(pk2(v[4 * i + 2], v[4 * i + 3]), sc2, pk2(bv.z, bv.w)), v[4 * i + 2], v[4 * i + 3]);
       }
+    } else if (p.acc_scale != 1.0f) {
+      const uint64_t sc2 = pk2(p.acc_scale, p.acc_scale);
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) upk2(fmul2(pk2(v[i], v[i + 1]), sc2), v[i], v[i + 1]);
     }
     if (ACT == CST_ACT_GELU) {
 #pragma unroll
-      for (int i = 0; i < 32; i += 2) gelu2(v[i], v[i + 1]);
+      for (int i = 0; i < 32; i += 2) {
+        if (p.exact_act) { v[i] = gelu_erf(v[i]); v[i + 1] = gelu_erf(v[i + 1]); }      // fp32 parity mode (split GEMMs)
+        else gelu2(v[i], v[i + 1]);
+      }
     } else if (ACT == CST_ACT_RELU) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
@@ -453,6 +465,7 @@ __device__ __forceinline__ void epi_tile(const GemmDev& p, const CUtensorMap* tm
     __syncwarp();
     if (col_ok) {
       const uint64_t b01 = pk2(b4.x, b4.y), b23 = pk2(b4.z, b4.w);
+      const uint64_t sc2 = pk2(p.acc_scale, p.acc_scale);
       // 4 rows per batch: the 16 element chains (bias, activation, alpha, residual) are independent, so the
       // two epilogue warps of an SM sub-partition keep the FMA/MUFU pipes busy instead of waiting on one chain
 #pragma unroll
@@ -462,20 +475,28 @@ __device__ __forceinline__ void epi_tile(const GemmDev& p, const CUtensorMap* tm
         for (int u = 0; u < 4; ++u) {
           const int rr = (i0 + u) * 4 + lr;
           const float4 a4 = *reinterpret_cast<const float4*>(&patch[rr * TC_PATCH_LD + 4 * ((lc >> 2) ^ (rr & 7))]);
-          upk2(fadd2(pk2(a4.x, a4.y), b01), v[u][0], v[u][1]);
-          upk2(fadd2(pk2(a4.z, a4.w), b23), v[u][2], v[u][3]);
+          upk2(ffma2(pk2(a4.x, a4.y), sc2, b01), v[u][0], v[u][1]);
+          upk2(ffma2(pk2(a4.z, a4.w), sc2, b23), v[u][2], v[u][3]);
         }
         if (ACT == CST_ACT_GLU) {
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            v[u][0] = v[u][0] * mufu_rcp(1.0f + mufu_ex2(-1.4426950408889634f * v[u][1])) * p.alpha;
-            v[u][1] = v[u][2] * mufu_rcp(1.0f + mufu_ex2(-1.4426950408889634f * v[u][3])) * p.alpha;
+            if (p.exact_act) {
+              v[u][0] = v[u][0] * sigmoidf_(v[u][1]) * p.alpha;
+              v[u][1] = v[u][2] * sigmoidf_(v[u][3]) * p.alpha;
+            } else {
+              v[u][0] = v[u][0] * mufu_rcp(1.0f + mufu_ex2(-1.4426950408889634f * v[u][1])) * p.alpha;
+              v[u][1] = v[u][2] * mufu_rcp(1.0f + mufu_ex2(-1.4426950408889634f * v[u][3])) * p.alpha;
+            }
             if (p.residual) { v[u][0] += res[i0 + u].x; v[u][1] += res[i0 + u].y; }
           }
         } else {
           if (ACT == CST_ACT_GELU) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) { gelu2(v[u][0], v[u][1]); gelu2(v[u][2], v[u][3]); }
+            for (int u = 0; u < 4; ++u) {
+              if (p.exact_act) { v[u][0] = gelu_erf(v[u][0]); v[u][1] = gelu_erf(v[u][1]); v[u][2] = gelu_erf(v[u][2]); v[u][3] = gelu_erf(v[u][3]); }
+              else { gelu2(v[u][0], v[u][1]); gelu2(v[u][2], v[u][3]); }
+            }
           } else if (ACT == CST_ACT_RELU) {
 #pragma unroll
             for (int u = 0; u < 4; ++u) {

@@ -104,6 +104,13 @@ class EncoderPlan:
         #       epilogue of the residual GEMMs has no headroom for a second output (profiles/SUMMARY_r02.md) -- kept as a lever.
         mode = int(os.environ.get("CST_LN_FUSE", "1")) if act_dtype == torch.bfloat16 else 0
         self.ln_fuse, self.ln_light = mode == 2, mode == 1
+        # fp32 mode, CST_F32_TC=1 ("fast fp32", opt-in): GEMMs on the tensor cores through a 3-term fp16 split of both operands
+        # (csrc/split.cu).  The split operands are exact to 7.6e-8, but tcgen05's fp32 accumulation in tensor memory is NOT
+        # round-to-nearest: its error grows linearly with K (4e-7 at K = 64, 1.6e-5 at K = 3072 against 1e-6 for FFMA;
+        # tools/dbg_split.py), so the whole path lands at 3.1e-5 rel-L2 -- 4.2x faster than the FFMA mode but outside the
+        # <= 1e-5 bar.  The default fp32 mode therefore stays on the CUDA-core FFMA GEMM (1.3e-6 .. 2.9e-6).
+        self.f32_tc = (act_dtype == torch.float32 and self.dev.type == "cuda" and "_s16" in params
+                       and os.environ.get("CST_F32_TC", "0") == "1")
         # memory stage (B*M rows): LayerNorm fused into weight-streaming linears (cst_dec_linear); CST_MEM_FUSED=0 keeps
         # LayerNorm + tensor-core / FFMA GEMM launches
         self.mem_fused = os.environ.get("CST_MEM_FUSED", "1") != "0"
@@ -138,6 +145,8 @@ class EncoderPlan:
             # ---- wav2vec2 encoder: fp32 residual stream x, pre-LN sums y, GEMM-operand copy xa
             ("x", R, W2V_DIM, f32), ("y", R, W2V_DIM, f32), ("xa", R, W2V_DIM, act_dtype),
             ("ln_stats0", R, 16, f32), ("ln_stats1", R, 16, f32),      # partial row statistics [row][8 slots]{sum, sum sq}
+            # fp32 mode on the tensor cores: [hi | lo | hi] fp16 copy of the current GEMM's A operand (largest: conv level 0)
+            ("split_buf", (self.crows[0] + SLACK) if self.f32_tc else 1, 1536, torch.float16),
             ("xg", XG + SLACK, 64, act_dtype), ("qkv", R, 3 * W2V_DIM, act_dtype),
             ("ctx", R, W2V_DIM, act_dtype), ("ffn", R, W2V_FFN, act_dtype), ("w2v_out", R, W2V_DIM, f32),
             # ---- subsampler operands (zero-padded: re-zeroed every run)
@@ -190,9 +199,20 @@ class EncoderPlan:
         beta): the residual rows are normalised on the fly; c2: bf16 copy of the output; out_stats: partial statistics of the
         output rows (cst_gemm_params, "LayerNorm fused around the GEMM")."""
         p = L.GemmParams()
+        exact, acc_scale = 0, 0.0
+        if self.f32_tc and A.dtype == torch.float32 and W.data_ptr() in self.P["_s16"]:
+            # 3-term fp16 split: A rows [hi | lo | hi] (this launch), W rows [hi | hi | lo] (prepared once), K' = 3K
+            w16, blk, acc_scale = self.P["_s16"][W.data_ptr()]
+            src_rows = (((nb_outer - 1) * a_bs[0] + (nb_inner - 1) * a_bs[1]) // lda + a_rows) * (lda // blk)
+            assert src_rows * 3 * blk <= self.split_buf.numel() and lda % blk == 0
+            L.check(self.lib.cst_split_f16(A.data_ptr(), blk, src_rows, blk, self.split_buf.data_ptr(), self.st))
+            self.launches += 1
+            A, W = self.split_buf, w16
+            K, lda, a_bs, w_bs, exact = 3 * K, 3 * lda, (3 * a_bs[0], 3 * a_bs[1]), 3 * w_bs, 1
         p.A, p.W, p.bias, p.residual, p.C = A.data_ptr(), W.data_ptr(), L.ptr(bias), L.ptr(residual), C_.data_ptr()
         p.ab_dtype, p.c_dtype = L.DT[A.dtype], L.DT[C_.dtype]
         assert A.dtype == W.dtype
+        p.exact_act, p.acc_scale = exact, acc_scale
         p.M, p.N, p.K = M, N, K
         p.lda = lda
         p.ldc = ldc if ldc is not None else C_.shape[1]
@@ -601,7 +621,7 @@ class TextPlan(EncoderPlan):
         self.gs, self.groups, self.Bt, self.M = [g], [(B, T)], B, M
         self.utt0, self.r2_0, self.R2 = [0], [0], B * g.T2a
         self.seg_w2v = self.seg_enc = self.seg_mem = None
-        self.ln_fuse = self.ln_light = False            # the text branch keeps the separate LayerNorm passes
+        self.ln_fuse = self.ln_light = self.f32_tc = False   # the text branch keeps separate LayerNorm passes and the FFMA fp32 GEMM
         self.mem_fused = os.environ.get("CST_MEM_FUSED", "1") != "0"
         self.dev = device or torch.device("cuda", torch.cuda.current_device())
         self.act = act_dtype

@@ -152,4 +152,46 @@ def prepare(state_dict, device, act_dtype, conv_dtype=None):
         bs.append(c + w @ b_)
     P["mem_kv_w"], P["mem_kv_b"] = op(torch.cat(ws, 0).float()), f32(torch.cat(bs, 0).float())
     P["unit_g"], P["unit_b"] = f32(torch.ones(sd["layer_norm.weight"].shape[0])), f32(torch.zeros(sd["layer_norm.weight"].shape[0]))
+    if act_dtype == torch.float32:
+        P["_s16"] = split_packs(P)
     return P
+
+
+def split_w(w, blk):
+    """fp32 [N, K] (K = n_blk * blk) -> (fp16 [N, 3K], 2^-s): per blk-wide block [hi | hi | lo], hi = fp16(w * 2^s),
+    lo = fp16(w * 2^s - hi) -- the weight side of the 3-term split (cst_split_f16 packs the activation rows as [hi | lo | hi]).
+    The power-of-two scale 2^s (exact) lifts the largest |w| to ~2^14: trained weights are ~1e-2, whose lo parts (~1e-5) would
+    otherwise fall into fp16's denormals and lose their mantissa; the GEMM epilogue multiplies the accumulator by 2^-s."""
+    import math
+    N, K = w.shape[-2], w.shape[-1]
+    amax = float(w.abs().max())
+    sh = max(0, min(24, int(math.floor(math.log2(16384.0 / amax))))) if amax > 0 else 0
+    w3 = (w.reshape(-1, N, K // blk, blk).float() * float(2.0 ** sh))
+    hi = w3.to(torch.float16)
+    lo = (w3 - hi.float()).to(torch.float16)
+    return torch.cat((hi, hi, lo), dim=-1).reshape(*w.shape[:-1], 3 * K).contiguous(), float(2.0 ** -sh)
+
+
+def split_packs(P):
+    """fp32 mode on the tensor cores: {data_ptr of the fp32 GEMM weight: (fp16 split pack, block width)}.  The block width is
+    the width of one SOURCE row of the A operand: K for a plain linear, the channel count for the implicit-GEMM convolutions
+    (a window spans several source rows), 64 for the packed pos-conv operand."""
+    out = {}
+
+    def add(w, blk):
+        w16, inv = split_w(w, blk)
+        out[w.data_ptr()] = (w16, blk, inv)
+    for i in range(1, len(CONV_LAYERS)):
+        add(P[f"conv{i}_w"], 512)
+    add(P["proj_w"], 512)
+    add(P["pos_w"], 64)
+    for d in P["w2v_layers"] + P["enc_layers"]:
+        for k in ("qkv_w", "o_w", "fc1_w", "fc2_w"):
+            add(d[k], d[k].shape[1])
+    add(P["sub0_w"], 768)
+    add(P["sub1_w"], 512)
+    add(P["mem_kv_w"], 512)
+    for d in P["mem_layers"]:
+        for k in ("q_w", "o_w", "fc1_w", "fc2_w"):
+            add(d[k], d[k].shape[1])
+    return out

@@ -122,8 +122,17 @@ typedef struct cst_gemm_params {
   void* C2; int c2_dtype; long long ldc2;
   float* out_stats;
   int ln_dim;                    /* width of the normalised rows (K for ln_in_stats, N for res_stats / out_stats) */
+  int exact_act;                 /* tensor-core path: 1 = erff GELU / exact sigmoid in the epilogue (the fp32 parity mode's split GEMMs) */
+  float acc_scale;               /* tensor-core path: the accumulator is multiplied by this before the bias (0 = 1): undoes the
+                                    power-of-two scale that keeps the lo parts of split fp16 weights out of the denormals */
 } cst_gemm_params;
 int cst_gemm(const cst_gemm_params* p, void* stream);
+
+/* fp32 mode on the tensor cores: 3-term fp16 split of a GEMM operand.  x [rows, C] f32 (row stride ldx) -> out fp16 [rows, 3C] =
+ * [hi | lo | hi] per row, hi = fp16(x), lo = fp16(x - hi).  With weight rows packed [whi | whi | wlo] per C-wide block, cst_gemm
+ * (CST_F16 operands, K' = 3K, fp32 accumulation, exact_act = 1) gives x.w to ~2^-22 relative: the <= 1e-5 parity mode without the
+ * CUDA-core FFMA GEMM.  Same reference lines as cst_gemm. */
+int cst_split_f16(const float* x, long long ldx, long long rows, int C, void* out, void* stream);
 
 /* ---- LayerNorm over the channel axis (eps 1e-5), one warp per row ----------------------------------
  * Replaces: LayerNorm of wav2vec2.py:539-540, 827-828, 945/957, transformer_layer.py:129-155,
