@@ -1,0 +1,337 @@
+// f.4 (BASELINE configs[4]): the pieces of the BACKWARD pass of the speech-encoding path that are not GEMMs.
+// The reference has no backward code of its own on this path -- torch autograd differentiates the modules of
+// fairseq/models/wav2vec/wav2vec2.py, fairseq/modules/transformer_layer.py, multihead_attention.py,
+// fairseq/models/speech_to_text/s2t_transformer.py:31-77 and fairseq/models/chimera/w2v2_transformer_interlingua.py:207-312;
+// these kernels are the hand-written derivatives of the forward kernels in this directory (parity: autograd through
+// oracle/chimera_oracle.py, tests/test_gpu_backward.py).  GEMM-shaped gradients (dgrad / wgrad) go through cst_gemm on
+// transposed copies made by cst_transpose.  All gradients are fp32.
+#include <cuda_fp16.h>
+#include "common.cuh"
+
+namespace cst {
+
+template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+
+// ---- transpose (+ cast): out[c * ldo + r] = x[r * ldx + c]; columns r in [rows, rows_pad) of out are zero-filled so that the
+// result can be the K-major operand of a GEMM whose reduction axis (rows) must be a multiple of 64.  ldx may be smaller than
+// cols (overlapping windows: the implicit-GEMM view of a strided convolution's input).
+template <typename OutT>
+__global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ x, long long ldx, int rows, int cols,
+                                                        OutT* __restrict__ out, long long ldo, int rows_pad) {
+  __shared__ float tile[32][33];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int r = r0 + ty + i, c = c0 + tx;
+    tile[ty + i][tx] = (r < rows && c < cols) ? x[(long long)r * ldx + c] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int c = c0 + ty + i, r = r0 + tx;
+    if (c < cols && r < rows_pad) out[(long long)c * ldo + r] = from_f32<OutT>(tile[tx][ty + i]);
+  }
+}
+template <typename OutT>
+__global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ x, long long n, OutT* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = from_f32<OutT>(x[i]);
+}
+
+// ---- column sums (bias / LayerNorm-parameter gradients), deterministic: grid.y row slabs write partials, a second launch of
+// the same kernel (one slab) adds the partials up.
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, long long ldx, int rows, int cols, int rows_per_slab,
+                                                     float* __restrict__ out, long long ldo, float scale) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= cols) return;
+  const int r0 = blockIdx.y * rows_per_slab;
+  const int r1 = min(rows, r0 + rows_per_slab);
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int r = r0;
+  for (; r + 3 < r1; r += 4) {
+    s0 += x[(long long)r * ldx + c]; s1 += x[(long long)(r + 1) * ldx + c];
+    s2 += x[(long long)(r + 2) * ldx + c]; s3 += x[(long long)(r + 3) * ldx + c];
+  }
+  for (; r < r1; ++r) s0 += x[(long long)r * ldx + c];
+  out[(long long)blockIdx.y * ldo + c] = ((s0 + s1) + (s2 + s3)) * scale;
+}
+
+// ---- activations as separate passes (the training forward keeps the pre-activation z for the backward pass)
+//   act 1 GELU (erf), 2 ReLU, 3 GLU on interleaved (value, gate) column pairs: y[:, i] = z[:, 2i] * sigmoid(z[:, 2i+1]) * alpha
+__global__ void __launch_bounds__(256) act_fwd_kernel(int act, const float* __restrict__ z, long long ldz, int rows, int cols_out,
+                                                      float* __restrict__ y, long long ldy, float alpha) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long total = (long long)rows * cols_out;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols_out;
+    const int c = (int)(i - r * cols_out);
+    float v;
+    if (act == CST_ACT_GLU) {
+      const float a = z[r * ldz + 2 * c], g = z[r * ldz + 2 * c + 1];
+      v = a * (1.0f / (1.0f + expf(-g)));
+    } else {
+      const float a = z[r * ldz + c];
+      v = act == CST_ACT_GELU ? gelu_erf(a) : (act == CST_ACT_RELU ? fmaxf(a, 0.f) : a);
+    }
+    y[r * ldy + c] = v * alpha;
+  }
+}
+__global__ void __launch_bounds__(256) act_bwd_kernel(int act, const float* __restrict__ z, long long ldz, const float* __restrict__ dy,
+                                                      long long ldy, int rows, int cols_out, float* __restrict__ dz, long long lddz,
+                                                      float alpha) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long total = (long long)rows * cols_out;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols_out;
+    const int c = (int)(i - r * cols_out);
+    const float g_out = dy[r * ldy + c] * alpha;
+    if (act == CST_ACT_GLU) {
+      const float a = z[r * ldz + 2 * c], g = z[r * ldz + 2 * c + 1];
+      const float s = 1.0f / (1.0f + expf(-g));
+      dz[r * lddz + 2 * c] = g_out * s;
+      dz[r * lddz + 2 * c + 1] = g_out * a * s * (1.0f - s);
+    } else if (act == CST_ACT_GELU) {
+      const float a = z[r * ldz + c];
+      // d/dx [x Phi(x)] = Phi(x) + x phi(x)
+      const float cdf = 0.5f * (1.0f + erff(a * 0.70710678118654752440f));
+      const float pdf = 0.3989422804014327f * expf(-0.5f * a * a);
+      dz[r * lddz + c] = g_out * (cdf + a * pdf);
+    } else if (act == CST_ACT_RELU) {
+      dz[r * lddz + c] = z[r * ldz + c] > 0.f ? g_out : 0.f;
+    } else {
+      dz[r * lddz + c] = g_out;
+    }
+  }
+}
+
+// ---- LayerNorm backward, one warp per row (statistics recomputed from x in fp32 registers, as the forward kernel):
+//   xhat = (x - mean) rstd;  g = dy * gamma;  dx = rstd * (g - mean_c(g) - xhat * mean_c(g * xhat))  (+ dx if accumulate)
+// Per-CTA partial sums of dgamma = sum_rows dy * xhat and dbeta = sum_rows dy go to part[blockIdx.x][2][C]; cst_colsum adds them.
+template <int NV>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ gamma,
+                                                            const float* __restrict__ dy, long long ldy, float* __restrict__ dx,
+                                                            long long lddx, float* __restrict__ part, int rows, int accumulate) {
+  constexpr int C = NV * 128;
+  __shared__ float red[2][C];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row = blockIdx.x * 8 + warp;
+  float4 dg[NV], db[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) dg[i] = db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (row < rows) {
+    float4 v[NV], g[NV];
+    const float* xr = x + (long long)row * ldx;
+    const float* dr = dy + (long long)row * ldy;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = load4(xr + (lane + 32 * i) * 4);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    const float mean = warp_sum(s) * (1.0f / C);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+      q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / C) + 1e-5f);
+    float sg = 0.f, sgx = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 d4 = load4(dr + (lane + 32 * i) * 4), gm = load4(gamma + (lane + 32 * i) * 4);
+      v[i].x *= rstd; v[i].y *= rstd; v[i].z *= rstd; v[i].w *= rstd;          // xhat
+      db[i] = d4;
+      dg[i] = make_float4(d4.x * v[i].x, d4.y * v[i].y, d4.z * v[i].z, d4.w * v[i].w);
+      g[i] = make_float4(d4.x * gm.x, d4.y * gm.y, d4.z * gm.z, d4.w * gm.w);
+      sg += (g[i].x + g[i].y) + (g[i].z + g[i].w);
+      sgx += (g[i].x * v[i].x + g[i].y * v[i].y) + (g[i].z * v[i].z + g[i].w * v[i].w);
+    }
+    const float mg = warp_sum(sg) * (1.0f / C), mgx = warp_sum(sgx) * (1.0f / C);
+    float* o = dx + (long long)row * lddx;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float4 r = make_float4(rstd * (g[i].x - mg - v[i].x * mgx), rstd * (g[i].y - mg - v[i].y * mgx),
+                             rstd * (g[i].z - mg - v[i].z * mgx), rstd * (g[i].w - mg - v[i].w * mgx));
+      if (accumulate) { const float4 p = load4(o + (lane + 32 * i) * 4); r.x += p.x; r.y += p.y; r.z += p.z; r.w += p.w; }
+      store4(o + (lane + 32 * i) * 4, r);
+    }
+  }
+  if (part != nullptr) {                                         // the 8 rows of the CTA, added in a fixed order
+    for (int w = 0; w < 8; ++w) {
+      if (warp == w) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          float4 a = dg[i], b = db[i];
+          if (w > 0) {
+            const float4 pa = load4(&red[0][(lane + 32 * i) * 4]), pb = load4(&red[1][(lane + 32 * i) * 4]);
+            a.x += pa.x; a.y += pa.y; a.z += pa.z; a.w += pa.w;
+            b.x += pb.x; b.y += pb.y; b.z += pb.z; b.w += pb.w;
+          }
+          store4(&red[0][(lane + 32 * i) * 4], a);
+          store4(&red[1][(lane + 32 * i) * 4], b);
+        }
+      }
+      __syncthreads();
+    }
+    for (int c = threadIdx.x; c < 2 * C; c += 256) part[(long long)blockIdx.x * 2 * C + c] = red[c / C][c % C];
+  }
+}
+
+// ---- col2im of a strided convolution's input gradient.  The forward conv is an implicit GEMM over a channels-last matrix
+// viewed with row pitch stride*C: output row m reads input rows stride*m .. stride*m + k - 1.  Its A-operand gradient
+// dcol [M, k*C] = dY W is scattered back: dx[r, c] = sum over taps t with (r - t) % stride == 0, m = (r - t) / stride in [0, M)
+// of dcol[m, t*C + c]   (gather form: deterministic).  Rows of filler / padding carry zero dY, so the flattened form is exact.
+__global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ dcol, long long M, int k, int stride, int C,
+                                                     float* __restrict__ dx, long long rows_in, int accumulate) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int c4n = C >> 2;
+  const long long total = rows_in * c4n;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / c4n;
+    const int c = (int)(i - r * c4n) * 4;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = 0; t < k; ++t) {
+      const long long d = r - t;
+      if (d < 0) break;
+      if (d % stride) continue;
+      const long long m = d / stride;
+      if (m >= M) continue;
+      const float4 v = load4(dcol + m * (long long)k * C + (long long)t * C + c);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    float* o = dx + r * C + c;
+    if (accumulate) { const float4 p = load4(o); s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w; }
+    store4(o, s);
+  }
+}
+
+// ---- row remap with masking: out[seg*out_rps + t + off] (+)= in[seg*in_rps + t + in_off] for t < valid (seg_len[seg] when given,
+// else seg_valid); rows t >= valid of the OUTPUT segment range [0, n_rows_out) are zeroed when zero_rest.  The transpose of the
+// forward row remaps (zero-padded subsampler operands, masked projection rows).
+__global__ void __launch_bounds__(256) rows_remap_kernel(const float* __restrict__ in, long long ldi, int in_rps, int in_off,
+                                                         float* __restrict__ out, long long ldo, int out_rps, int out_off,
+                                                         int n_seg, int n_rows, int C, int seg_valid, const int32_t* __restrict__ seg_len,
+                                                         int accumulate, float scale) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int c4n = C >> 2;
+  const long long total = (long long)n_seg * n_rows * c4n;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long rr = i / c4n;
+    const int c = (int)(i - rr * c4n) * 4;
+    const int seg = (int)(rr / n_rows), t = (int)(rr - (long long)seg * n_rows);
+    const int valid = seg_len ? min(seg_valid, seg_len[seg]) : seg_valid;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t < valid) {
+      v = load4(in + ((long long)seg * in_rps + t + in_off) * ldi + c);
+      v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+    }
+    float* o = out + ((long long)seg * out_rps + t + out_off) * ldo + c;
+    if (accumulate) { const float4 p = load4(o); v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w; }
+    store4(o, v);
+  }
+}
+
+}  // namespace cst
+
+using namespace cst;
+
+static inline unsigned grid_for(long long n, int per = 256) {
+  long long b = (n + per - 1) / per;
+  if (b < 1) b = 1;
+  if (b > 148 * 32) b = 148 * 32;
+  return (unsigned)b;
+}
+
+extern "C" int cst_transpose(const float* x, long long ldx, int rows, int cols, void* out, int out_dtype, long long ldo, int rows_pad,
+                             void* stream) {
+  CST_REQUIRE(x && out && rows > 0 && cols > 0 && rows_pad >= rows && ldo >= rows_pad, "cst_transpose: bad args rows=%d cols=%d", rows, cols);
+  dim3 grid(cdiv(rows_pad, 32), cdiv(cols, 32));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (out_dtype == CST_F32) CST_CHECK_CUDA(launch_k(transpose_kernel<float>, grid, dim3(256), 0, st, x, ldx, rows, cols, (float*)out, ldo, rows_pad));
+  else if (out_dtype == CST_BF16) CST_CHECK_CUDA(launch_k(transpose_kernel<__nv_bfloat16>, grid, dim3(256), 0, st, x, ldx, rows, cols, (__nv_bfloat16*)out, ldo, rows_pad));
+  else CST_CHECK_CUDA(launch_k(transpose_kernel<__half>, grid, dim3(256), 0, st, x, ldx, rows, cols, (__half*)out, ldo, rows_pad));
+  return CST_OK;
+}
+
+extern "C" int cst_cast(const float* x, long long n, void* out, int out_dtype, void* stream) {
+  CST_REQUIRE(x && out && n > 0 && (out_dtype == CST_BF16 || out_dtype == CST_F16), "cst_cast: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (out_dtype == CST_BF16) CST_CHECK_CUDA(launch_k(cast_kernel<__nv_bfloat16>, dim3(grid_for(n)), dim3(256), 0, st, x, n, (__nv_bfloat16*)out));
+  else CST_CHECK_CUDA(launch_k(cast_kernel<__half>, dim3(grid_for(n)), dim3(256), 0, st, x, n, (__half*)out));
+  return CST_OK;
+}
+
+// out[c] = scale * sum_r x[r, c]; ws: at least 64 * cols floats
+extern "C" int cst_colsum(const float* x, long long ldx, int rows, int cols, float* out, float* ws, float scale, void* stream) {
+  CST_REQUIRE(x && out && ws && rows > 0 && cols > 0, "cst_colsum: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  int slabs = rows >= 4096 ? 64 : (rows >= 256 ? 16 : 1);
+  const int per = cdiv(rows, slabs);
+  slabs = cdiv(rows, per);
+  if (slabs == 1) {
+    CST_CHECK_CUDA(launch_k(colsum_kernel, dim3(cdiv(cols, 256), 1), dim3(256), 0, st, x, ldx, rows, cols, rows, out, (long long)cols, scale));
+  } else {
+    CST_CHECK_CUDA(launch_k(colsum_kernel, dim3(cdiv(cols, 256), slabs), dim3(256), 0, st, x, ldx, rows, cols, per, ws, (long long)cols, 1.0f));
+    CST_CHECK_CUDA(launch_k(colsum_kernel, dim3(cdiv(cols, 256), 1), dim3(256), 0, st, (const float*)ws, (long long)cols, slabs, cols, slabs, out,
+                            (long long)cols, scale));
+  }
+  return CST_OK;
+}
+
+extern "C" int cst_act_fwd(int act, const float* z, long long ldz, int rows, int cols_out, float* y, long long ldy, float alpha, void* stream) {
+  CST_REQUIRE(z && y && rows > 0 && cols_out > 0 && act >= CST_ACT_NONE && act <= CST_ACT_GLU, "cst_act_fwd: bad args");
+  CST_CHECK_CUDA(launch_k(act_fwd_kernel, dim3(grid_for((long long)rows * cols_out)), dim3(256), 0, (cudaStream_t)stream, act, z, ldz, rows,
+                          cols_out, y, ldy, alpha));
+  return CST_OK;
+}
+
+extern "C" int cst_act_bwd(int act, const float* z, long long ldz, const float* dy, long long ldy, int rows, int cols_out, float* dz,
+                           long long lddz, float alpha, void* stream) {
+  CST_REQUIRE(z && dy && dz && rows > 0 && cols_out > 0 && act >= CST_ACT_NONE && act <= CST_ACT_GLU, "cst_act_bwd: bad args");
+  CST_CHECK_CUDA(launch_k(act_bwd_kernel, dim3(grid_for((long long)rows * cols_out)), dim3(256), 0, (cudaStream_t)stream, act, z, ldz, dy, ldy,
+                          rows, cols_out, dz, lddz, alpha));
+  return CST_OK;
+}
+
+// part: NULL (no parameter gradients) or cdiv(rows, 8) * 2 * C floats ([block][dgamma | dbeta][C]); reduce with cst_colsum (ldx = 2C).
+extern "C" int cst_layernorm_bwd(const float* x, long long ldx, const float* gamma, const float* dy, long long ldy, float* dx, long long lddx,
+                                 float* part, int rows, int C, int accumulate, void* stream) {
+  CST_REQUIRE(x && gamma && dy && dx && rows > 0 && (C == 512 || C == 768), "cst_layernorm_bwd: bad args rows=%d C=%d", rows, C);
+  CST_REQUIRE(ldx % 4 == 0 && ldy % 4 == 0 && lddx % 4 == 0, "cst_layernorm_bwd: leading dims must be multiples of 4");
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid(cdiv(rows, 8));
+  if (C == 512) {
+    CST_CHECK_CUDA(launch_k(layernorm_bwd_kernel<4>, grid, dim3(256), 0, st, x, ldx, gamma, dy, ldy, dx, lddx, part, rows, accumulate));
+  } else {
+    CST_CHECK_CUDA(launch_k(layernorm_bwd_kernel<6>, grid, dim3(256), 0, st, x, ldx, gamma, dy, ldy, dx, lddx, part, rows, accumulate));
+  }
+  return CST_OK;
+}
+
+extern "C" int cst_col2im(const float* dcol, long long M, int k, int stride, int C, float* dx, long long rows_in, int accumulate, void* stream) {
+  CST_REQUIRE(dcol && dx && M > 0 && k > 0 && stride > 0 && C % 4 == 0 && rows_in > 0, "cst_col2im: bad args");
+  CST_CHECK_CUDA(launch_k(col2im_kernel, dim3(grid_for(rows_in * (C / 4))), dim3(256), 0, (cudaStream_t)stream, dcol, M, k, stride, C, dx,
+                          rows_in, accumulate));
+  return CST_OK;
+}
+
+extern "C" int cst_rows_remap(const float* in, long long ldi, int in_rps, int in_off, float* out, long long ldo, int out_rps, int out_off,
+                              int n_seg, int n_rows, int C, int seg_valid, const int32_t* seg_len, int accumulate, float scale, void* stream) {
+  CST_REQUIRE(in && out && n_seg > 0 && n_rows > 0 && C % 4 == 0, "cst_rows_remap: bad args");
+  CST_CHECK_CUDA(launch_k(rows_remap_kernel, dim3(grid_for((long long)n_seg * n_rows * (C / 4))), dim3(256), 0, (cudaStream_t)stream, in, ldi,
+                          in_rps, in_off, out, ldo, out_rps, out_off, n_seg, n_rows, C, seg_valid, seg_len, accumulate, scale));
+  return CST_OK;
+}

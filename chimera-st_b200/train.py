@@ -1,0 +1,487 @@
+"""Forward + backward of the speech-encoding path (BASELINE configs[4]), first correct version.
+
+`EncoderTrainStep(state_dict, B, L, M).forward_backward(wave, lens, d_memories)` runs the audio branch of
+`S2T_W2V2_TransformerInterlinguaEncoder.forward` (fairseq/models/chimera/w2v2_transformer_interlingua.py:207-312) with every
+activation the backward pass needs kept in HBM, then the hand-written backward kernels (`csrc/backward.cu`,
+`csrc/attention_bwd.cu`, `csrc/conv0_bwd.cu`, dgrad / wgrad through `cst_gemm` on `cst_transpose`-d operands), and returns the
+gradient of every encoder parameter under its REFERENCE state-dict name (so that the reference's optimizer / DDP wrapper --
+`fairseq/legacy_distributed_data_parallel.py:94-178`, restated in `ddp.py` -- can consume them).
+
+Scope of this version: fp32 arithmetic (CUDA-core GEMM / attention; parity <= 1e-4 against autograd through the
+oracle), dropout = 0 and LayerDrop = 0 (the parity configuration of SURVEY §8(d) C5), one padded batch per step, unfused
+activations in the forward pass (the pre-activation is kept).  `GradMultiply(feature_grad_mult)` (wav2vec2.py:530-532) is applied
+to the feature-extractor gradients.  torch is used for buffers and for re-arranging WEIGHT tensors between the reference layout and
+the kernel layout; everything that touches an activation is a kernel behind the C ABI.
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib as L
+from . import weights as _weights
+from .plan import Geometry, SLACK
+from .synth import W2V_DIM, W2V_FFN, W2V_HEADS, W2V_LAYERS, ENC_DIM, ENC_FFN, ENC_HEADS, ENC_LAYERS, MEM_LAYERS, POS_K, POS_GROUPS
+
+F32 = torch.float32
+
+
+class _Ops:
+    """Thin launch helpers over the C ABI (device tensors in / out, current stream)."""
+
+    def __init__(self, device):
+        self.lib = L.load()
+        self.dev = device
+        self.ws = torch.empty(64 * 8192 + 1024, dtype=F32, device=device)       # cst_colsum scratch
+
+    def st(self):
+        return L.stream_ptr()
+
+    def new(self, *shape, zero=False):
+        return (torch.zeros if zero else torch.empty)(*shape, dtype=F32, device=self.dev)
+
+    def gemm(self, A, W, Cout, M, N, K, lda, a_rows, bias=None, residual=None, rows_per_seg=None, seg_len=None,
+             nb_outer=1, nb_inner=1, a_bs=(0, 0), w_bs=0, c_bs=(0, 0), bias_bs=0, ldc=None):
+        p = L.GemmParams()
+        p.A, p.W, p.bias, p.residual, p.C = A.data_ptr(), W.data_ptr(), L.ptr(bias), L.ptr(residual), Cout.data_ptr()
+        p.ab_dtype, p.c_dtype = L.F32, L.F32
+        p.M, p.N, p.K, p.lda = M, N, K, lda
+        p.ldc = ldc if ldc is not None else Cout.shape[-1]
+        p.ldr = p.ldc if residual is not None else 0
+        p.a_rows, p.act, p.alpha = a_rows, L.ACT_NONE, 1.0
+        p.nb_outer, p.nb_inner = nb_outer, nb_inner
+        p.a_bs_outer, p.a_bs_inner = a_bs
+        p.w_bs_inner = w_bs
+        p.c_bs_outer, p.c_bs_inner = c_bs
+        p.r_bs_outer, p.r_bs_inner = c_bs
+        p.bias_bs_inner = bias_bs
+        p.rows_per_seg = rows_per_seg if rows_per_seg is not None else M
+        p.seg_rows_valid = p.rows_per_seg
+        p.out_rows_per_seg = p.rows_per_seg
+        p.seg_len = L.ptr(seg_len)
+        p.segs_per_outer = 1
+        L.check(self.lib.cst_gemm(C.byref(p), self.st()))
+        return Cout
+
+    def linear(self, x, W, b=None, residual=None, rows=None):
+        rows = rows if rows is not None else x.shape[0]
+        N, K = W.shape
+        return self.gemm(x, W, self.new(rows, N), rows, N, K, lda=x.shape[1], a_rows=x.shape[0], bias=b, residual=residual)
+
+    def transpose(self, x, rows, cols, ldx=None, pad=64):
+        rp = (rows + pad - 1) // pad * pad
+        out = self.new(cols, rp)
+        L.check(self.lib.cst_transpose(x.data_ptr(), ldx if ldx is not None else x.shape[1], rows, cols, out.data_ptr(), L.F32, rp, rp,
+                                       self.st()))
+        return out
+
+    def colsum(self, x, rows, cols, ldx=None, scale=1.0):
+        out = self.new(cols)
+        L.check(self.lib.cst_colsum(x.data_ptr(), ldx if ldx is not None else x.shape[1], rows, cols, out.data_ptr(), self.ws.data_ptr(),
+                                    scale, self.st()))
+        return out
+
+    def linear_bwd(self, x, W, dy, rows, need_dx=True, dx_residual=None, bias=True):
+        """y = x W^T + b  ->  (dx = dy W (+ dx_residual), dW = dy^T x, db = colsum(dy))."""
+        N, K = W.shape
+        dx = None
+        if need_dx:
+            Wt = self.transpose(W, N, K)                         # [K, N] (N is a multiple of 64 on this path)
+            dx = self.gemm(dy, Wt, self.new(rows, K), rows, K, N, lda=dy.shape[1], a_rows=dy.shape[0], residual=dx_residual)
+        dyT = self.transpose(dy, rows, N)                        # [N, rows_pad]
+        xT = self.transpose(x, rows, K)                          # [K, rows_pad]
+        dW = self.gemm(dyT, xT, self.new(N, K), N, K, dyT.shape[1], lda=dyT.shape[1], a_rows=N)
+        db = self.colsum(dy, rows, N) if bias else None
+        return dx, dW, db
+
+    def act(self, kind, z, rows, cols_out, alpha=1.0):
+        y = self.new(rows, cols_out)
+        L.check(self.lib.cst_act_fwd(kind, z.data_ptr(), z.shape[1], rows, cols_out, y.data_ptr(), cols_out, alpha, self.st()))
+        return y
+
+    def act_bwd(self, kind, z, dy, rows, cols_out, alpha=1.0):
+        dz = self.new(rows, z.shape[1])
+        L.check(self.lib.cst_act_bwd(kind, z.data_ptr(), z.shape[1], dy.data_ptr(), dy.shape[1], rows, cols_out, dz.data_ptr(), z.shape[1],
+                                     alpha, self.st()))
+        return dz
+
+    def ln(self, x, g, b, rows):
+        out = self.new(rows, x.shape[1])
+        Cd = x.shape[1]
+        L.check(self.lib.cst_layernorm(x.data_ptr(), Cd, g.data_ptr(), b.data_ptr(), out.data_ptr(), 0, L.F32, Cd, rows, Cd, rows, rows, rows,
+                                       0, 0, self.st()))
+        return out
+
+    def ln_bwd(self, x, g, dy, rows, dx=None):
+        """-> (dx (accumulated into `dx` when given), dgamma, dbeta)"""
+        Cd = x.shape[1]
+        acc = dx is not None
+        dx = dx if acc else self.new(rows, Cd)
+        nblk = (rows + 7) // 8
+        part = self.new(nblk, 2 * Cd)
+        L.check(self.lib.cst_layernorm_bwd(x.data_ptr(), Cd, g.data_ptr(), dy.data_ptr(), dy.shape[1], dx.data_ptr(), Cd, part.data_ptr(), rows,
+                                           Cd, 1 if acc else 0, self.st()))
+        gb = self.colsum(part, nblk, 2 * Cd)
+        return dx, gb[:Cd], gb[Cd:]
+
+    def attention(self, q, k, v, ldq, ldkv, B, H, n_q, q_rps, n_kv, kv_rps, kv_len, out_rows, out_cols):
+        out = self.new(out_rows, out_cols, zero=True)
+        L.check(self.lib.cst_attention(q, k, v, out.data_ptr(), L.F32, ldq, ldkv, out_cols, B, H, n_q, q_rps, n_kv, kv_rps, L.ptr(kv_len),
+                                       self.st()))
+        return out
+
+    def attention_bwd(self, q, k, v, o, do, dq, dk, dv, ldq, ldkv, ldo, B, H, n_q, q_rps, n_kv, kv_rps, kv_len):
+        L.check(self.lib.cst_attention_bwd(q, k, v, o.data_ptr(), do.data_ptr(), dq, dk, dv, ldq, ldkv, ldo, B, H, n_q, q_rps, n_kv, kv_rps,
+                                           L.ptr(kv_len), self.st()))
+
+    def remap(self, src, in_rps, in_off, dst, out_rps, out_off, n_seg, n_rows, Cd, valid, seg_len=None, accumulate=False, scale=1.0):
+        L.check(self.lib.cst_rows_remap(src.data_ptr(), src.shape[1], in_rps, in_off, dst.data_ptr(), dst.shape[1], out_rps, out_off, n_seg,
+                                        n_rows, Cd, valid, L.ptr(seg_len), 1 if accumulate else 0, scale, self.st()))
+        return dst
+
+    def col2im(self, dcol, M, k, stride, Cd, rows_in):
+        dx = self.new(rows_in, Cd)
+        L.check(self.lib.cst_col2im(dcol.data_ptr(), M, k, stride, Cd, dx.data_ptr(), rows_in, 0, self.st()))
+        return dx
+
+
+def _attn_layer_grads(G, name, dqkv_w, dqkv_b, D, fused=True):
+    """Kernel layout -> reference names for an attention block's in-projection (q rows carry the folded 1/8)."""
+    if fused:
+        G[name + "q_proj.weight"], G[name + "k_proj.weight"], G[name + "v_proj.weight"] = dqkv_w[:D] * 0.125, dqkv_w[D:2 * D], dqkv_w[2 * D:]
+        G[name + "q_proj.bias"], G[name + "k_proj.bias"], G[name + "v_proj.bias"] = dqkv_b[:D] * 0.125, dqkv_b[D:2 * D], dqkv_b[2 * D:]
+
+
+class EncoderTrainStep:
+    def __init__(self, state_dict, B, Lw, M=None, device="cuda", feature_grad_mult=0.1):
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise L.CstError("EncoderTrainStep runs only on a CUDA device (no CPU fallback)")
+        sd = _weights._strip(state_dict)
+        self.sd = {k: v.detach().to(dev, F32) for k, v in sd.items() if v.is_floating_point()}
+        self.M = M or self.sd["interlingua_embedding.weight"].shape[0]
+        self.g = Geometry(B, Lw, self.M)
+        self.dev = dev
+        self.o = _Ops(dev)
+        self.fgm = float(feature_grad_mult)
+        self.P = _weights.prepare(self.sd, dev, F32)
+
+    # ------------------------------------------------------------------ forward (activations kept)
+    def forward(self, wave, lens):
+        o, g, P, lib = self.o, self.g, self.P, self.o.lib
+        B, st = g.B, self.o.st()
+        T = {}                                                     # the tape
+        self.T = T
+        wave = wave.to(self.dev, F32).contiguous()
+        src_len = lens.to(self.dev, torch.int64).contiguous()
+        T["wave"] = wave
+        i32 = dict(dtype=torch.int32, device=self.dev)
+        w2v_valid, sub_valid = torch.empty(B, **i32), torch.empty(B, **i32)
+        L.check(lib.cst_frame_lengths(src_len.data_ptr(), B, g.L, g.Tp, w2v_valid.data_ptr(), sub_valid.data_ptr(), 0, 0, st))
+        T["w2v_valid"], T["sub_valid"] = w2v_valid, sub_valid
+        # ---- conv feature extractor
+        ss = o.new(B * 512, 2)
+        stats_ws = torch.zeros(B * 72, dtype=torch.float64, device=self.dev)
+        L.check(lib.cst_conv0_stats(wave.data_ptr(), B, g.L, P["conv0_w"].data_ptr(), P["gn_g"].data_ptr(), P["gn_b"].data_ptr(),
+                                    ss.data_ptr(), stats_ws.data_ptr(), st))
+        c = o.new(B * g.Ta[0] + SLACK, 512, zero=True)
+        L.check(lib.cst_conv0_apply(wave.data_ptr(), B, g.L, P["conv0_w"].data_ptr(), ss.data_ptr(), c.data_ptr(), L.F32, g.Ta[0], st))
+        T["ss"] = ss
+        T["c"], T["cz"] = [c], [None]
+        for i in range(1, 7):
+            w = P[f"conv{i}_w"]
+            rows = B * g.Ta[i]
+            z = o.gemm(c, w, o.new(rows, 512), rows, 512, w.shape[1], lda=1024, a_rows=(B * g.Ta[i - 1] + SLACK) // 2)
+            cn = o.new(rows + SLACK, 512, zero=True)
+            L.check(lib.cst_act_fwd(L.ACT_GELU, z.data_ptr(), 512, rows, 512, cn.data_ptr(), 512, 1.0, st))
+            T["c"].append(cn)
+            T["cz"].append(z)
+            c = cn
+        R = B * g.T6a
+        feat = c
+        feat_ln = o.ln(feat, P["ln_feat_g"], P["ln_feat_b"], R)
+        xp = o.gemm(feat_ln, P["proj_w"], o.new(R, W2V_DIM), R, W2V_DIM, 512, lda=512, a_rows=R, bias=P["proj_b"], rows_per_seg=g.T6a,
+                    seg_len=w2v_valid)
+        T["feat_ln"], T["xp"] = feat_ln, xp
+        # ---- pos-conv (grouped implicit GEMM on the packed operand), GELU, residual
+        xg = torch.zeros(B * 16 * g.Tpp + SLACK, 64, dtype=F32, device=self.dev)
+        L.check(lib.cst_posconv_pack(xp.data_ptr(), B, g.T6a, g.Tp, xg.data_ptr(), L.F32, g.Tpp, st))
+        zpos = o.gemm(xg, P["pos_w"], o.new(R, W2V_DIM), g.T6a, 48, 128 * 64, lda=64, a_rows=g.Tpp, bias=P["pos_b"], nb_outer=B, nb_inner=16,
+                      a_bs=(16 * g.Tpp * 64, g.Tpp * 64), w_bs=48 * 128 * 64, c_bs=(g.T6a * W2V_DIM, 48), bias_bs=48, ldc=W2V_DIM)
+        y0 = xp.clone()
+        gp = o.act(L.ACT_GELU, zpos, R, W2V_DIM)
+        o.remap(gp, R, 0, y0, R, 0, 1, R, W2V_DIM, R, accumulate=True)
+        T["xg"], T["zpos"], T["y0"] = xg, zpos, y0
+        x = o.ln(y0, P["ln_enc_g"], P["ln_enc_b"], R)
+        # ---- 12 post-LN wav2vec2 layers
+        D = W2V_DIM
+        T["w2v"] = []
+        for lw in P["w2v_layers"]:
+            t = {"x": x}
+            qkv = o.linear(x, lw["qkv_w"], lw["qkv_b"])
+            qp = qkv.data_ptr()
+            ctx = o.attention(qp, qp + 4 * D, qp + 8 * D, 3 * D, 3 * D, B, W2V_HEADS, g.T6a, g.T6a, g.Tp, g.T6a, w2v_valid, R, D)
+            y1 = o.linear(ctx, lw["o_w"], lw["o_b"], residual=x)
+            x1 = o.ln(y1, lw["ln1_g"], lw["ln1_b"], R)
+            z = o.linear(x1, lw["fc1_w"], lw["fc1_b"])
+            h = o.act(L.ACT_GELU, z, R, W2V_FFN)
+            y2 = o.linear(h, lw["fc2_w"], lw["fc2_b"], residual=x1)
+            x = o.ln(y2, lw["ln2_g"], lw["ln2_b"], R)
+            t.update(qkv=qkv, ctx=ctx, y1=y1, x1=x1, z=z, h=h, y2=y2)
+            T["w2v"].append(t)
+        T["w2v_out"] = x
+        # ---- subsampler: zero-padded operands, conv + GLU twice
+        sub_in = torch.zeros(B * g.Tin1 + SLACK, D, dtype=F32, device=self.dev)
+        o.remap(x, g.T6a, 0, sub_in, g.Tin1, 2, B, g.Tp, D, g.Tp)
+        w0, w1 = P["sub0_w"], P["sub1_w"]
+        zs0 = o.gemm(sub_in, w0, o.new(B * g.T1a, w0.shape[0]), B * g.T1a, w0.shape[0], w0.shape[1], lda=2 * D, a_rows=(B * g.Tin1 + SLACK) // 2,
+                     bias=P["sub0_b"])
+        s0 = o.act(L.ACT_GLU, zs0, B * g.T1a, ENC_DIM)
+        sub_mid = torch.zeros(B * g.Tin2 + SLACK, ENC_DIM, dtype=F32, device=self.dev)
+        o.remap(s0, g.T1a, 0, sub_mid, g.Tin2, 2, B, g.T1, ENC_DIM, g.T1)
+        zs1 = o.gemm(sub_mid, w1, o.new(B * g.T2a, w1.shape[0]), B * g.T2a, w1.shape[0], w1.shape[1], lda=2 * ENC_DIM,
+                     a_rows=(B * g.Tin2 + SLACK) // 2, bias=P["sub1_b"])
+        R2 = B * g.T2a
+        x2 = o.act(L.ACT_GLU, zs1, R2, ENC_DIM, alpha=math.sqrt(ENC_DIM))
+        T.update(sub_in=sub_in, zs0=zs0, sub_mid=sub_mid, zs1=zs1)
+        # ---- 6 pre-LN shared layers
+        D2 = ENC_DIM
+        T["enc"] = []
+        for lw in P["enc_layers"]:
+            t = {"x_in": x2}
+            a = o.ln(x2, lw["ln1_g"], lw["ln1_b"], R2)
+            qkv = o.linear(a, lw["qkv_w"], lw["qkv_b"])
+            qp = qkv.data_ptr()
+            ctx = o.attention(qp, qp + 4 * D2, qp + 8 * D2, 3 * D2, 3 * D2, B, ENC_HEADS, g.T2a, g.T2a, g.T2, g.T2a, sub_valid, R2, D2)
+            xm = o.linear(ctx, lw["o_w"], lw["o_b"], residual=x2)
+            b_ = o.ln(xm, lw["ln2_g"], lw["ln2_b"], R2)
+            z = o.linear(b_, lw["fc1_w"], lw["fc1_b"])
+            h = o.act(L.ACT_RELU, z, R2, ENC_FFN)
+            x2 = o.linear(h, lw["fc2_w"], lw["fc2_b"], residual=xm)
+            t.update(a=a, qkv=qkv, ctx=ctx, xm=xm, b=b_, z=z, h=h)
+            T["enc"].append(t)
+        T["x2_out"] = x2
+        h_enc = o.ln(x2, P["ln_out_g"], P["ln_out_b"], R2)
+        T["h_enc"] = h_enc
+        # ---- memory stage: M learned queries over ALL T2 frames, per-layer affine LN1 of h_enc (un-folded: training form)
+        Mq, RM = self.M, B * self.M
+        mem = o.new(RM, D2)
+        L.check(lib.cst_broadcast_rows(P["mem_embed"].data_ptr(), Mq, D2, B, mem.data_ptr(), st))
+        T["mem"] = []
+        for lw in P["mem_layers"]:
+            t = {"m_in": mem}
+            a = o.ln(mem, lw["ln1_g"], lw["ln1_b"], RM)
+            kv_in = o.ln(h_enc, lw["ln1_g"], lw["ln1_b"], R2)
+            q = o.linear(a, lw["q_w"], lw["q_b"])
+            kv = o.linear(kv_in, lw["kv_w"], lw["kv_b"])
+            kp = kv.data_ptr()
+            ctx = o.attention(q.data_ptr(), kp, kp + 4 * D2, D2, 2 * D2, B, ENC_HEADS, Mq, Mq, g.T2, g.T2a, None, RM, D2)
+            mm = o.linear(ctx, lw["o_w"], lw["o_b"], residual=mem)
+            b_ = o.ln(mm, lw["ln2_g"], lw["ln2_b"], RM)
+            z = o.linear(b_, lw["fc1_w"], lw["fc1_b"])
+            h = o.act(L.ACT_RELU, z, RM, ENC_FFN)
+            mem = o.linear(h, lw["fc2_w"], lw["fc2_b"], residual=mm)
+            t.update(a=a, kv_in=kv_in, q=q, kv=kv, ctx=ctx, mm=mm, b=b_, z=z, h=h)
+            T["mem"].append(t)
+        self.mem_out = mem
+        return mem.view(B, Mq, D2).transpose(0, 1)                 # [M, B, 512] (view)
+
+    # ------------------------------------------------------------------ backward
+    def _ffn_bwd(self, G, name, lw, t, dy, rows, act, x_key, dx_acc=None):
+        """y = x_in + fc2(act(fc1(LNorm-ed input))) pieces shared by all three layer types: returns d(fc1 input)."""
+        o = self.o
+        dh, dW2, db2 = o.linear_bwd(t["h"], lw["fc2_w"], dy, rows)
+        G[name + "fc2.weight"], G[name + "fc2.bias"] = dW2, db2
+        dz = o.act_bwd(act, t["z"], dh, rows, t["z"].shape[1])
+        dxin, dW1, db1 = o.linear_bwd(t[x_key], lw["fc1_w"], dz, rows)
+        G[name + "fc1.weight"], G[name + "fc1.bias"] = dW1, db1
+        return dxin
+
+    def backward(self, d_mem):
+        """d_mem: [M, B, 512] gradient of the loss w.r.t. the memories.  -> {reference parameter name: gradient}."""
+        o, g, P, T = self.o, self.g, self.P, self.T
+        B, Mq, D2 = g.B, self.M, ENC_DIM
+        RM, R2, R = B * Mq, B * g.T2a, B * g.T6a
+        G = {}
+        dmem = d_mem.to(self.dev, F32).transpose(0, 1).contiguous().view(RM, D2)
+        dh_enc = o.new(R2, D2, zero=True)
+        # ---- memory stage
+        for li in reversed(range(MEM_LAYERS)):
+            lw, t, nm = P["mem_layers"][li], T["mem"][li], f"interlingua_layers.{li}."
+            db_in = self._ffn_bwd(G, nm, lw, t, dmem, RM, L.ACT_RELU, "b")
+            dmm, dg2, dbt2 = o.ln_bwd(t["mm"], lw["ln2_g"], db_in, RM, dx=dmem.clone())     # residual path + LN2 path
+            G[nm + "final_layer_norm.weight"], G[nm + "final_layer_norm.bias"] = dg2, dbt2
+            dctx, dWo, dbo = o.linear_bwd(t["ctx"], lw["o_w"], dmm, RM)
+            G[nm + "self_attn.out_proj.weight"], G[nm + "self_attn.out_proj.bias"] = dWo, dbo
+            dq = o.new(RM, D2, zero=True)
+            dkv = o.new(R2, 2 * D2, zero=True)
+            kp, dkp = t["kv"].data_ptr(), dkv.data_ptr()
+            o.attention_bwd(t["q"].data_ptr(), kp, kp + 4 * D2, t["ctx"], dctx, dq.data_ptr(), dkp, dkp + 4 * D2, D2, 2 * D2, D2, B, ENC_HEADS,
+                            Mq, Mq, g.T2, g.T2a, None)
+            da, dWq, dbq = o.linear_bwd(t["a"], lw["q_w"], dq, RM)
+            G[nm + "self_attn.q_proj.weight"], G[nm + "self_attn.q_proj.bias"] = dWq * 0.125, dbq * 0.125
+            dkv_in, dWkv, dbkv = o.linear_bwd(t["kv_in"], lw["kv_w"], dkv, R2)
+            G[nm + "self_attn.k_proj.weight"], G[nm + "self_attn.v_proj.weight"] = dWkv[:D2], dWkv[D2:]
+            G[nm + "self_attn.k_proj.bias"], G[nm + "self_attn.v_proj.bias"] = dbkv[:D2], dbkv[D2:]
+            dmem, dg1a, db1a = o.ln_bwd(t["m_in"], lw["ln1_g"], da, RM, dx=dmm)              # + residual
+            _, dg1b, db1b = o.ln_bwd(T["h_enc"], lw["ln1_g"], dkv_in, R2, dx=dh_enc)         # the SAME LN1 on the key/value side
+            G[nm + "self_attn_layer_norm.weight"], G[nm + "self_attn_layer_norm.bias"] = dg1a + dg1b, db1a + db1b
+        G["interlingua_embedding.weight"] = o.colsum(dmem.view(B, Mq * D2), B, Mq * D2).view(Mq, D2)
+        self.dbg = {"h_enc": dh_enc}
+        # ---- final LayerNorm + shared layers
+        dx2, dgo, dbo_ = o.ln_bwd(T["x2_out"], P["ln_out_g"], dh_enc, R2)
+        G["layer_norm.weight"], G["layer_norm.bias"] = dgo, dbo_
+        for li in reversed(range(ENC_LAYERS)):
+            lw, t, nm = P["enc_layers"][li], T["enc"][li], f"transformer_layers.{li}."
+            db_in = self._ffn_bwd(G, nm, lw, t, dx2, R2, L.ACT_RELU, "b")
+            dxm, dg2, dbt2 = o.ln_bwd(t["xm"], lw["ln2_g"], db_in, R2, dx=dx2)
+            G[nm + "final_layer_norm.weight"], G[nm + "final_layer_norm.bias"] = dg2, dbt2
+            dctx, dWo, dbo = o.linear_bwd(t["ctx"], lw["o_w"], dxm, R2)
+            G[nm + "self_attn.out_proj.weight"], G[nm + "self_attn.out_proj.bias"] = dWo, dbo
+            dqkv = o.new(R2, 3 * D2, zero=True)
+            qp, dqp = t["qkv"].data_ptr(), dqkv.data_ptr()
+            o.attention_bwd(qp, qp + 4 * D2, qp + 8 * D2, t["ctx"], dctx, dqp, dqp + 4 * D2, dqp + 8 * D2, 3 * D2, 3 * D2, D2, B, ENC_HEADS,
+                            g.T2a, g.T2a, g.T2, g.T2a, T["sub_valid"])
+            da, dWqkv, dbqkv = o.linear_bwd(t["a"], lw["qkv_w"], dqkv, R2)
+            _attn_layer_grads(G, nm + "self_attn.", dWqkv, dbqkv, D2)
+            dx2, dg1, db1 = o.ln_bwd(t["x_in"], lw["ln1_g"], da, R2, dx=dxm)
+            G[nm + "self_attn_layer_norm.weight"], G[nm + "self_attn_layer_norm.bias"] = dg1, db1
+        self.dbg["sub_out"] = dx2
+        # ---- subsampler (GLU -> conv dgrad / wgrad on the zero-padded operands)
+        D = W2V_DIM
+        w0, w1 = P["sub0_w"], P["sub1_w"]
+        dzs1 = o.act_bwd(L.ACT_GLU, T["zs1"], dx2, R2, D2, alpha=math.sqrt(D2))
+        dcol, dW1, db1 = self._conv_bwd(T["sub_mid"], w1, dzs1, R2, 2 * D2, (B * g.Tin2 + SLACK) // 2)
+        G["subsample.conv_layers.1.weight"], G["subsample.conv_layers.1.bias"] = self._glu_conv_w(dW1, D2), _glu_deinterleave(db1)
+        dmid = o.col2im(dcol, R2, 5, 2, D2, B * g.Tin2)
+        ds0 = o.new(B * g.T1a, D2, zero=True)
+        o.remap(dmid, g.Tin2, 2, ds0, g.T1a, 0, B, g.T1, D2, g.T1)
+        dzs0 = o.act_bwd(L.ACT_GLU, T["zs0"], ds0, B * g.T1a, D2)
+        dcol, dW0, db0 = self._conv_bwd(T["sub_in"], w0, dzs0, B * g.T1a, 2 * D, (B * g.Tin1 + SLACK) // 2)
+        G["subsample.conv_layers.0.weight"], G["subsample.conv_layers.0.bias"] = self._glu_conv_w(dW0, D), _glu_deinterleave(db0)
+        din = o.col2im(dcol, B * g.T1a, 5, 2, D, B * g.Tin1)
+        dx = o.new(R, D, zero=True)
+        o.remap(din, g.Tin1, 2, dx, g.T6a, 0, B, g.Tp, D, g.Tp)
+        self.dbg["w2v_out"] = dx
+        # ---- 12 post-LN wav2vec2 layers
+        for li in reversed(range(W2V_LAYERS)):
+            lw, t, nm = P["w2v_layers"][li], T["w2v"][li], f"wav2vec_model.encoder.layers.{li}."
+            dy2, dg2, dbt2 = o.ln_bwd(t["y2"], lw["ln2_g"], dx, R)
+            G[nm + "final_layer_norm.weight"], G[nm + "final_layer_norm.bias"] = dg2, dbt2
+            dx1_ffn = self._ffn_bwd(G, nm, lw, t, dy2, R, L.ACT_GELU, "x1")
+            dx1 = dx1_ffn
+            o.remap(dy2, R, 0, dx1, R, 0, 1, R, D, R, accumulate=True)                       # residual x1 -> y2
+            dy1, dg1, dbt1 = o.ln_bwd(t["y1"], lw["ln1_g"], dx1, R)
+            G[nm + "self_attn_layer_norm.weight"], G[nm + "self_attn_layer_norm.bias"] = dg1, dbt1
+            dctx, dWo, dbo = o.linear_bwd(t["ctx"], lw["o_w"], dy1, R)
+            G[nm + "self_attn.out_proj.weight"], G[nm + "self_attn.out_proj.bias"] = dWo, dbo
+            dqkv = o.new(R, 3 * D, zero=True)
+            qp, dqp = t["qkv"].data_ptr(), dqkv.data_ptr()
+            o.attention_bwd(qp, qp + 4 * D, qp + 8 * D, t["ctx"], dctx, dqp, dqp + 4 * D, dqp + 8 * D, 3 * D, 3 * D, D, B, W2V_HEADS,
+                            g.T6a, g.T6a, g.Tp, g.T6a, T["w2v_valid"])
+            dx, dWqkv, dbqkv = o.linear_bwd(t["x"], lw["qkv_w"], dqkv, R, dx_residual=dy1)   # + residual x -> y1
+            _attn_layer_grads(G, nm + "self_attn.", dWqkv, dbqkv, D)
+        self.dbg["w2v_in"] = dx
+        # ---- encoder LayerNorm, pos-conv, masked projection, feature LayerNorm
+        dy0, dge, dbe = o.ln_bwd(T["y0"], P["ln_enc_g"], dx, R)
+        G["wav2vec_model.encoder.layer_norm.weight"], G["wav2vec_model.encoder.layer_norm.bias"] = dge, dbe
+        dzpos = o.act_bwd(L.ACT_GELU, T["zpos"], dy0, R, D)
+        dxp = self._posconv_bwd(G, dzpos, dy0)
+        # x[padding_mask] = 0: rows t >= valid carry no gradient into the projection
+        dxp_m = o.new(R, D, zero=True)
+        o.remap(dxp, g.T6a, 0, dxp_m, g.T6a, 0, B, g.T6a, D, g.T6a, seg_len=T["w2v_valid"])
+        self.dbg["proj_masked"] = dxp
+        dfl, dWp, dbp = o.linear_bwd(T["feat_ln"], P["proj_w"], dxp_m, R)
+        G["wav2vec_model.post_extract_proj.weight"], G["wav2vec_model.post_extract_proj.bias"] = dWp, dbp
+        dfeat, dgf, dbf = o.ln_bwd(T["c"][6], P["ln_feat_g"], dfl, R)
+        G["wav2vec_model.layer_norm.weight"], G["wav2vec_model.layer_norm.bias"] = dgf, dbf
+        self.dbg["conv_feats"] = dfeat
+        # ---- conv feature extractor; GradMultiply(feature_grad_mult) scales everything that flows into it (wav2vec2.py:530-532)
+        dc = o.new(R, 512)
+        o.remap(dfeat, R, 0, dc, R, 0, 1, R, 512, R, scale=self.fgm)
+        fe = "wav2vec_model.feature_extractor.conv_layers."
+        for i in range(6, 0, -1):
+            w = P[f"conv{i}_w"]
+            rows = B * g.Ta[i]
+            k = w.shape[1] // 512
+            dz = o.act_bwd(L.ACT_GELU, T["cz"][i], dc, rows, 512)
+            dcol, dW, _ = self._conv_bwd(T["c"][i - 1], w, dz, rows, 1024, (B * g.Ta[i - 1] + SLACK) // 2, bias=False)
+            G[fe + f"{i}.0.weight"] = dW.view(512, k, 512).permute(0, 2, 1).contiguous()
+            dc = o.col2im(dcol, rows, k, 2, 512, B * g.Ta[i - 1])
+        nch = (g.T[0] + 127) // 128
+        ws = o.new(B * nch * 5120 + B * 1024 + 64 * 5120)
+        dw0, dgn, dbn = o.new(512, 10), o.new(512), o.new(512)
+        L.check(o.lib.cst_conv0_bwd(T["wave"].data_ptr(), B, g.L, P["conv0_w"].data_ptr(), P["gn_g"].data_ptr(), P["gn_b"].data_ptr(),
+                                    T["ss"].data_ptr(), dc.data_ptr(), g.Ta[0], dw0.data_ptr(), dgn.data_ptr(), dbn.data_ptr(), ws.data_ptr(),
+                                    1.0, o.st()))
+        G[fe + "0.0.weight"], G[fe + "0.2.weight"], G[fe + "0.2.bias"] = dw0.view(512, 1, 10), dgn, dbn
+        return G
+
+    def _conv_bwd(self, x_src, w, dz, rows, lda, a_rows, bias=True):
+        """Implicit-GEMM convolution z[m] = window_m(x_src) . w: -> (dcol [rows, K] = dz w, dW [N, K] = dz^T windows, db)."""
+        o = self.o
+        N, K = w.shape
+        Wt = o.transpose(w, N, K)
+        dcol = o.gemm(dz, Wt, o.new(rows, K), rows, K, N, lda=dz.shape[1], a_rows=dz.shape[0])
+        dzT = o.transpose(dz, rows, N)
+        winT = o.transpose(x_src, rows, K, ldx=lda)                 # transposed overlapping windows
+        dW = o.gemm(dzT, winT, o.new(N, K), N, K, dzT.shape[1], lda=dzT.shape[1], a_rows=N)
+        return dcol, dW, (o.colsum(dz, rows, N) if bias else None)
+
+    @staticmethod
+    def _glu_conv_w(dW, cin):
+        """[1024 interleaved (value_i, gate_i), 5*cin] -> reference Conv1d weight [1024, cin, 5]."""
+        n = dW.shape[0]
+        d = dW.view(n // 2, 2, 5, cin)
+        d = torch.cat((d[:, 0], d[:, 1]), 0)                       # de-interleave: values then gates
+        return d.permute(0, 2, 1).contiguous()
+
+    def _posconv_bwd(self, G, dz, dy0):
+        """y0 = xp + GELU(conv_g(xp) + b): -> d xp; parameter gradients of the weight-normed grouped conv (wav2vec2.py:773-786)."""
+        o, g, P = self.o, self.g, self.P
+        B, D, R = g.B, W2V_DIM, g.B * g.T6a
+        cg, Kc = D // POS_GROUPS, POS_K * 64
+        pc = "wav2vec_model.encoder.pos_conv.0."
+        G[pc + "bias"] = o.colsum(dz, R, D)
+        # weight gradient: per utterance, per group  dWp[g] [48, 128*64] += dz_g^T [48, T] . windows(xg)[T, 128*64]
+        dWp = o.new(POS_GROUPS, cg, Kc, zero=True)
+        Tpad = (g.T6a + 63) // 64 * 64
+        for b in range(B):
+            dzT = o.transpose(dz[b * g.T6a:], g.T6a, D)             # [768, Tpad] = [16 x 48, Tpad]
+            winT = o.new(POS_GROUPS, Kc, Tpad)
+            for gi in range(POS_GROUPS):
+                src = T_slice(self.T["xg"], (b * 16 + gi) * g.Tpp)
+                L.check(o.lib.cst_transpose(src.data_ptr(), 64, g.T6a, Kc, winT[gi].data_ptr(), L.F32, Tpad, Tpad, o.st()))
+            o.gemm(dzT, winT, dWp, cg, Kc, Tpad, lda=Tpad, a_rows=D, residual=dWp, nb_outer=1, nb_inner=POS_GROUPS,
+                   a_bs=(0, cg * Tpad), w_bs=Kc * Tpad, c_bs=(0, cg * Kc), ldc=Kc)
+        dw = dWp.view(POS_GROUPS, cg, POS_K, 64)[..., :cg].permute(0, 1, 3, 2).reshape(D, cg, POS_K)     # [co, ci, tap]
+        v, gg = self.sd[pc + "weight_v"], self.sd[pc + "weight_g"]
+        nrm = v.norm(dim=(0, 1), keepdim=True)
+        G[pc + "weight_g"] = (dw * v / nrm).sum(dim=(0, 1), keepdim=True)
+        G[pc + "weight_v"] = gg / nrm * (dw - v * (dw * v).sum(dim=(0, 1), keepdim=True) / (nrm * nrm))
+        # input gradient: the same grouped implicit GEMM on the packed dz with the flipped, transposed kernel
+        w = v * (gg / nrm)                                          # [768, 48, 128]
+        wg = w.view(POS_GROUPS, cg, cg, POS_K)                      # [g, co, ci, tap]
+        wd = torch.zeros(POS_GROUPS, cg, POS_K, 64, dtype=F32, device=self.dev)       # [g, ci, tap', co]
+        wd[..., :cg] = wg.flip(3).permute(0, 2, 3, 1)
+        wd = wd.reshape(POS_GROUPS, cg, Kc).contiguous()
+        dzg = torch.zeros(B * 16 * g.Tpp + SLACK + 1, 64, dtype=F32, device=self.dev)
+        L.check(o.lib.cst_posconv_pack(dz.data_ptr(), B, g.T6a, g.T6a, dzg.data_ptr(), L.F32, g.Tpp, o.st()))
+        dxp = dy0.clone()                                           # residual path
+        shifted = dzg[1:]                                           # window of frame s = packed rows s+1 .. s+128
+        o.gemm(shifted, wd, dxp, g.T6a, 48, Kc, lda=64, a_rows=g.Tpp - 1, residual=dxp, nb_outer=B, nb_inner=16,
+               a_bs=(16 * g.Tpp * 64, g.Tpp * 64), w_bs=48 * Kc, c_bs=(g.T6a * D, 48), ldc=D)
+        return dxp
+
+    def forward_backward(self, wave, lens, d_mem):
+        mem = self.forward(wave, lens)
+        return mem, self.backward(d_mem)
+
+
+def T_slice(t, row0):
+    return t[row0:]
+
+
+def _glu_deinterleave(db):
+    d = db.view(-1, 2)
+    return torch.cat((d[:, 0], d[:, 1]), 0).contiguous()

@@ -18,6 +18,8 @@ conv feature extractor (conv1..6) may use fp16 operands (`conv_dtype`): that sta
 layers, so operand rounding accumulates (bf16: 6.3e-3 rel-L2 at its output, fp16: 0.8e-3) -- same bytes, same tensor
 throughput, and fp16 is the half-precision format of the reference's own recipes (`--fp16`).
 """
+import os
+
 import torch
 
 from .synth import CONV_LAYERS, W2V_LAYERS, ENC_LAYERS, MEM_LAYERS, POS_GROUPS, POS_K
@@ -152,8 +154,8 @@ def prepare(state_dict, device, act_dtype, conv_dtype=None):
         bs.append(c + w @ b_)
     P["mem_kv_w"], P["mem_kv_b"] = op(torch.cat(ws, 0).float()), f32(torch.cat(bs, 0).float())
     P["unit_g"], P["unit_b"] = f32(torch.ones(sd["layer_norm.weight"].shape[0])), f32(torch.zeros(sd["layer_norm.weight"].shape[0]))
-    if act_dtype == torch.float32:
-        P["_s16"] = split_packs(P)
+    if act_dtype == torch.float32 and os.environ.get("CST_F32_TC", "0") == "1":
+        P["_s16"] = split_packs(P)          # only the opt-in "fast fp32" mode needs them (plan.py)
     return P
 
 

@@ -1,0 +1,64 @@
+"""Gradient all-reduce plumbing of the training configuration (C5) on CPU: world_size-2 gloo, bucketed + asynchronous, against
+the reference's rule (flat buffer, pre-divided by the world size, summed: legacy_distributed_data_parallel.py:94-178)."""
+import os
+import socket
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import chimera_st_b200  # noqa: F401
+from chimera_st_b200 import ddp
+
+SIZES = [("mem.fc2.weight", 2048 * 16), ("mem.fc2.bias", 512), ("big.weight", 40000), ("enc.ln.weight", 512), ("enc.qkv.weight", 9000),
+         ("missing.on.rank1", 77), ("conv0.weight", 5120)]
+
+
+def _worker(rank, world, port, q):
+    from conftest import ROOT
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(100 + rank)
+    grads = {n: torch.randn(sz, generator=g) for n, sz in SIZES}
+    if rank == 1:
+        del grads["missing.on.rank1"]                      # a parameter without a gradient on one rank counts as zeros
+    red = ddp.GradAllReducer(SIZES, bucket_bytes=64 * 1024)
+    # gradients arrive in backward order, a few at a time: complete buckets start reducing before the rest exists
+    names = [n for n, _ in SIZES if n in grads]
+    red.ready({n: grads[n] for n in names[:3]})
+    started_early = len(red.inflight)
+    red.ready({n: grads[n] for n in names[3:]})
+    out = red.finish(grads)
+    q.put((rank, started_early, len(red.buckets), {n: t.numpy().copy() for n, t in out.items()}))   # plain arrays: no fd passing
+    dist.destroy_process_group()
+
+
+def test_bucket_plan_keeps_backward_order_and_isolates_big_tensors():
+    b = ddp.plan_buckets(SIZES, bucket_bytes=64 * 1024)
+    assert [n for bk in b for n in bk] == [n for n, _ in SIZES]
+    assert ["mem.fc2.weight"] in b and ["big.weight"] in b            # >= one bucket (16384 elements): travel alone
+    assert all(sum(dict(SIZES)[n] for n in bk) <= 16384 or len(bk) == 1 for bk in b)
+
+
+def test_two_rank_gloo_all_reduce_matches_the_reference_rule():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, early0, nb, out0), (_, early1, _, out1) = res
+    assert early0 >= 1 and early1 >= 1 and nb >= 3                   # overlap: something was in flight before the last gradient
+    gens = [torch.Generator().manual_seed(100 + r) for r in range(2)]
+    ref = {n: [torch.randn(sz, generator=gens[r]) for r in range(2)] for n, sz in SIZES}
+    for n, sz in SIZES:
+        want = ref[n][0] / 2 + (ref[n][1] / 2 if n != "missing.on.rank1" else 0)
+        assert torch.allclose(torch.from_numpy(out0[n]), want, atol=1e-7) and (out0[n] == out1[n]).all(), n
