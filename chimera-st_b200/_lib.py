@@ -100,18 +100,21 @@ _SIGS = {
     "cst_label_smoothed_ce": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_longlong, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_longlong, C.c_float, C.c_void_p]),
     "cst_sum": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
-    "cst_transpose": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_void_p]),
+    "cst_transpose": (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                C.c_longlong, C.c_void_p]),
     "cst_cast": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_void_p]),
-    "cst_colsum": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]),
-    "cst_act_fwd": (C.c_int, [C.c_int, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_float, C.c_void_p]),
-    "cst_act_bwd": (C.c_int, [C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_longlong,
-                              C.c_float, C.c_void_p]),
+    "cst_colsum": (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]),
+    "cst_act_fwd": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_longlong, C.c_float,
+                              C.c_void_p]),
+    "cst_act_bwd": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_void_p,
+                              C.c_int, C.c_longlong, C.c_float, C.c_void_p]),
     "cst_layernorm_bwd": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p,
                                     C.c_int, C.c_int, C.c_int, C.c_void_p]),
-    "cst_attention_bwd": (C.c_int, [C.c_void_p] * 8 + [C.c_longlong] * 3 + [C.c_int] * 6 + [C.c_void_p, C.c_void_p]),
-    "cst_col2im": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
-    "cst_rows_remap": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int,
-                                 C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_void_p]),
+    "cst_attention_bwd": (C.c_int, [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 4 + [C.c_longlong] * 6 + [C.c_int] * 6 +
+                          [C.c_void_p, C.c_void_p]),
+    "cst_col2im": (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
+    "cst_rows_remap": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_int,
+                                 C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_void_p]),
     "cst_conv0_bwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]),
     "cst_dec_embed": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_int,

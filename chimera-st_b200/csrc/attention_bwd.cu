@@ -1,7 +1,7 @@
 // f.4: backward of softmax attention (head_dim 64), fp32 on the CUDA cores -- the derivative of cst_attention's arithmetic
 // (F.multi_head_attention_forward as called from fairseq/modules/multihead_attention.py:155-187; q pre-scaled, keys >= kv_len[b]
 // masked with -inf, all query rows live).  Flash-style: nothing of size Tq x Tk is stored by the forward pass; this kernel
-// recomputes S = Q K^T per 64 x 64 tile, first for the row statistics (max, sum) and D_i = dO_i . O_i, then for
+// recomputes S = Q K^T per 64 x 64 tile, first for the row statistics (max, sum) and D_i = sum_j P_ij dP_ij, then for
 //   P = exp(S - m) / l,  dP = dO V^T,  dS = P o (dP - D),  dQ += dS K,  dK += dS^T Q,  dV += P^T dO.
 // One CTA per (64-query tile, head, utterance); dK / dV are accumulated across query tiles with fp32 atomics (pre-zeroed by the
 // caller).  First correct version: FFMA tiles in shared memory; the tcgen05 version is future work.
@@ -29,10 +29,15 @@ __device__ __forceinline__ void tile_mm(const float* __restrict__ As, const floa
   }
 }
 
-__global__ void __launch_bounds__(256) attention_bwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
-                                                            const float* __restrict__ o, const float* __restrict__ d_o,
+__device__ __forceinline__ float ab_ld(const void* p, int dt, long long i) {
+  return dt == CST_F32 ? reinterpret_cast<const float*>(p)[i] : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
+}
+
+__global__ void __launch_bounds__(256) attention_bwd_kernel(const void* __restrict__ q, const void* __restrict__ k, const void* __restrict__ v,
+                                                            const void* __restrict__ o, int dt, const float* __restrict__ d_o,
                                                             float* __restrict__ dq, float* __restrict__ dk, float* __restrict__ dv,
-                                                            long long ldq, long long ldkv, long long ldo,
+                                                            long long ldq, long long ldkv, long long ldo_fwd, long long ldo,
+                                                            long long lddq, long long lddkv,
                                                             int n_q, int q_rows_per_seg, int n_kv, int kv_rows_per_seg,
                                                             const int32_t* __restrict__ kv_len) {
   extern __shared__ float sm[];
@@ -52,51 +57,57 @@ __global__ void __launch_bounds__(256) attention_bwd_kernel(const float* __restr
   int klen = kv_len ? kv_len[b] : n_kv;
   if (klen > n_kv) klen = n_kv;
   const long long qrow0 = (long long)b * q_rows_per_seg, krow0 = (long long)b * kv_rows_per_seg;
-  // Q, dO tiles; D_i = dO_i . O_i
+  // Q, dO tiles
   for (int e = tid; e < AB_T * AB_D; e += 256) {
     const int i = e >> 6, d = e & 63;
     const bool ok = q0 + i < n_q;
-    Qs[i * AB_LD + d] = ok ? q[(qrow0 + q0 + i) * ldq + h * AB_D + d] : 0.f;
+    Qs[i * AB_LD + d] = ok ? ab_ld(q, dt, (qrow0 + q0 + i) * ldq + h * AB_D + d) : 0.f;
     Gs[i * AB_LD + d] = ok ? d_o[(qrow0 + q0 + i) * ldo + h * AB_D + d] : 0.f;
   }
-  __syncthreads();
-  if (tid < AB_T) {
-    float s = 0.f;
-    if (q0 + tid < n_q)
-      for (int d = 0; d < AB_D; ++d) s = fmaf(Gs[tid * AB_LD + d], o[(qrow0 + q0 + tid) * ldo + h * AB_D + d], s);
-    row_d[tid] = s;
-    row_m[tid] = -INFINITY;
-    row_l[tid] = 0.f;
-  }
+  if (tid < AB_T) { row_d[tid] = 0.f; row_m[tid] = -INFINITY; row_l[tid] = 0.f; }
   __syncthreads();
   auto load_kv = [&](int k0, bool with_v) {
     for (int e = tid; e < AB_T * AB_D; e += 256) {
       const int j = e >> 6, d = e & 63;
       const bool ok = k0 + j < klen;
-      Ks[j * AB_LD + d] = ok ? k[(krow0 + k0 + j) * ldkv + h * AB_D + d] : 0.f;
-      if (with_v) Vs[j * AB_LD + d] = ok ? v[(krow0 + k0 + j) * ldkv + h * AB_D + d] : 0.f;
+      Ks[j * AB_LD + d] = ok ? ab_ld(k, dt, (krow0 + k0 + j) * ldkv + h * AB_D + d) : 0.f;
+      if (with_v) Vs[j * AB_LD + d] = ok ? ab_ld(v, dt, (krow0 + k0 + j) * ldkv + h * AB_D + d) : 0.f;
     }
   };
-  // ---- pass 1: row maximum and sum of exponentials over all keys
+  // ---- pass 1: row maximum, sum of exponentials and D_i = sum_j P_ij dP_ij over all keys.  D is accumulated from the recomputed
+  // probabilities (un-normalised, rescaled with the running maximum like l) instead of dO_i . O_i: the stored O of the 16-bit mode
+  // is bf16, and dS = P o (dP - D) cancels heavily when the values of a sequence are close to each other.
+  (void)o; (void)ldo_fwd;
   for (int k0 = 0; k0 < klen; k0 += AB_T) {
     __syncthreads();
-    load_kv(k0, false);
+    load_kv(k0, true);
     __syncthreads();
-    float s[4][4] = {};
+    float s[4][4] = {}, dp[4][4] = {};
     tile_mm<0>(Qs, Ks, ty, tx, s);
+    tile_mm<0>(Gs, Vs, ty, tx, dp);
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) Ps[(4 * ty + a) * AB_LD + 4 * tx + c] = (k0 + 4 * tx + c < klen) ? s[a][c] : -INFINITY;
+      for (int c = 0; c < 4; ++c) {
+        Ps[(4 * ty + a) * AB_LD + 4 * tx + c] = (k0 + 4 * tx + c < klen) ? s[a][c] : -INFINITY;
+        Ss[(4 * ty + a) * AB_LD + 4 * tx + c] = dp[a][c];
+      }
     __syncthreads();
     if (tid < AB_T) {
       float mx = row_m[tid];
       for (int j = 0; j < AB_T; ++j) mx = fmaxf(mx, Ps[tid * AB_LD + j]);
-      float l = row_l[tid] * expf(row_m[tid] - mx);
-      for (int j = 0; j < AB_T; ++j) l += expf(Ps[tid * AB_LD + j] - mx);
-      row_m[tid] = mx; row_l[tid] = l;
+      const float resc = expf(row_m[tid] - mx);
+      float l = row_l[tid] * resc, dacc = row_d[tid] * resc;
+      for (int j = 0; j < AB_T; ++j) {
+        const float e = expf(Ps[tid * AB_LD + j] - mx);
+        l += e;
+        dacc = fmaf(e, Ss[tid * AB_LD + j], dacc);
+      }
+      row_m[tid] = mx; row_l[tid] = l; row_d[tid] = dacc;
     }
   }
+  __syncthreads();
+  if (tid < AB_T) row_d[tid] = row_l[tid] > 0.f ? row_d[tid] / row_l[tid] : 0.f;
   __syncthreads();
   // ---- pass 2: gradients
   float dq_acc[4][4] = {};
@@ -141,8 +152,8 @@ __global__ void __launch_bounds__(256) attention_bwd_kernel(const float* __restr
       if (j < klen) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          atomicAdd(dv + (krow0 + j) * ldkv + h * AB_D + 4 * tx + c, gv[a][c]);
-          atomicAdd(dk + (krow0 + j) * ldkv + h * AB_D + 4 * tx + c, gk[a][c]);
+          atomicAdd(dv + (krow0 + j) * lddkv + h * AB_D + 4 * tx + c, gv[a][c]);
+          atomicAdd(dk + (krow0 + j) * lddkv + h * AB_D + 4 * tx + c, gk[a][c]);
         }
       }
     }
@@ -162,25 +173,28 @@ __global__ void __launch_bounds__(256) attention_bwd_kernel(const float* __restr
   for (int a = 0; a < 4; ++a) {
     const int i = q0 + 4 * ty + a;
     if (i < n_q)
-      *reinterpret_cast<float4*>(dq + (qrow0 + i) * ldq + h * AB_D + 4 * tx) = make_float4(dq_acc[a][0], dq_acc[a][1], dq_acc[a][2], dq_acc[a][3]);
+      *reinterpret_cast<float4*>(dq + (qrow0 + i) * lddq + h * AB_D + 4 * tx) = make_float4(dq_acc[a][0], dq_acc[a][1], dq_acc[a][2], dq_acc[a][3]);
   }
 }
 
 }  // namespace cst
 
-// q / dq [B*q_rows_per_seg, ldq]; k, v / dk, dv [B*kv_rows_per_seg, ldkv]; o, d_o [B*q_rows_per_seg, ldo]; head h at columns h*64.
-// dq rows >= n_q of a segment are left untouched; dk / dv must be ZERO on entry (they are accumulated atomically).
-extern "C" int cst_attention_bwd(const float* q, const float* k, const float* v, const float* o, const float* d_o,
-                                 float* dq, float* dk, float* dv, long long ldq, long long ldkv, long long ldo,
+// q [B*q_rows_per_seg, ldq], k / v [B*kv_rows_per_seg, ldkv], o [.., ldo_fwd] in `dtype` (CST_F32 / CST_BF16: the tape of the 16-bit mode);
+// d_o [.., ldo], dq [.., lddq], dk / dv [.., lddkv] fp32; head h at columns h*64.  dq rows >= n_q of a segment are left untouched;
+// dk / dv must be ZERO on entry (they are accumulated atomically).
+extern "C" int cst_attention_bwd(const void* q, const void* k, const void* v, const void* o, int dtype, const float* d_o,
+                                 float* dq, float* dk, float* dv, long long ldq, long long ldkv, long long ldo_fwd, long long ldo,
+                                 long long lddq, long long lddkv,
                                  int B, int H, int n_q, int q_rows_per_seg, int n_kv, int kv_rows_per_seg, const int32_t* kv_len,
                                  void* stream) {
   using namespace cst;
   CST_REQUIRE(q && k && v && o && d_o && dq && dk && dv && B > 0 && H > 0 && n_q > 0 && n_kv > 0, "cst_attention_bwd: bad args");
-  CST_REQUIRE(n_q <= q_rows_per_seg && n_kv <= kv_rows_per_seg && ldq % 4 == 0, "cst_attention_bwd: bad geometry");
+  CST_REQUIRE(dtype == CST_F32 || dtype == CST_BF16, "cst_attention_bwd: dtype must be CST_F32 or CST_BF16");
+  CST_REQUIRE(n_q <= q_rows_per_seg && n_kv <= kv_rows_per_seg && lddq % 4 == 0, "cst_attention_bwd: bad geometry");
   static bool attr = false;
   if (!attr) { CST_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM)); attr = true; }
   dim3 grid(cdiv(n_q, AB_T), H, B);
-  CST_CHECK_CUDA(launch_k(attention_bwd_kernel, grid, dim3(256), AB_SMEM, (cudaStream_t)stream, q, k, v, o, d_o, dq, dk, dv, ldq, ldkv, ldo,
-                          n_q, q_rows_per_seg, n_kv, kv_rows_per_seg, kv_len));
+  CST_CHECK_CUDA(launch_k(attention_bwd_kernel, grid, dim3(256), AB_SMEM, (cudaStream_t)stream, q, k, v, o, dtype, d_o, dq, dk, dv, ldq, ldkv,
+                          ldo_fwd, ldo, lddq, lddkv, n_q, q_rows_per_seg, n_kv, kv_rows_per_seg, kv_len));
   return CST_OK;
 }

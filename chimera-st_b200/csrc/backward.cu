@@ -10,14 +10,40 @@
 
 namespace cst {
 
-template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
 
-// ---- transpose (+ cast): out[c * ldo + r] = x[r * ldx + c]; columns r in [rows, rows_pad) of out are zero-filled so that the
-// result can be the K-major operand of a GEMM whose reduction axis (rows) must be a multiple of 64.  ldx may be smaller than
-// cols (overlapping windows: the implicit-GEMM view of a strided convolution's input).
-template <typename OutT>
-__global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ x, long long ldx, int rows, int cols,
-                                                        OutT* __restrict__ out, long long ldo, int rows_pad) {
+// ---- runtime-typed element access: the tape of the 16-bit training mode keeps GEMM operands / pre-activations in bf16 and
+// gradients in fp32; these passes are HBM-bound, the dtype branch is uniform per launch.
+__device__ __forceinline__ float ld_any(const void* p, int dt, long long i) {
+  if (dt == CST_F32) return reinterpret_cast<const float*>(p)[i];
+  if (dt == CST_BF16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
+  return __half2float(reinterpret_cast<const __half*>(p)[i]);
+}
+__device__ __forceinline__ void st_any(void* p, int dt, long long i, float v) {
+  if (dt == CST_F32) reinterpret_cast<float*>(p)[i] = v;
+  else if (dt == CST_BF16) reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
+  else reinterpret_cast<__half*>(p)[i] = __float2half_rn(v);
+}
+__device__ __forceinline__ float4 ld4_any(const void* p, int dt, long long i) {      // i % 4 == 0, row pitches % 4 == 0
+  if (dt == CST_F32) return load4(reinterpret_cast<const float*>(p) + i);
+  if (dt == CST_BF16) return load4(reinterpret_cast<const __nv_bfloat16*>(p) + i);
+  const __half* h = reinterpret_cast<const __half*>(p) + i;
+  return make_float4(__half2float(h[0]), __half2float(h[1]), __half2float(h[2]), __half2float(h[3]));
+}
+__device__ __forceinline__ void st4_any(void* p, int dt, long long i, float4 v) {
+  if (dt == CST_F32) store4(reinterpret_cast<float*>(p) + i, v);
+  else if (dt == CST_BF16) store4(reinterpret_cast<__nv_bfloat16*>(p) + i, v);
+  else store4(reinterpret_cast<__half*>(p) + i, v);
+}
+
+// ---- transpose (+ cast): outT[c][r] = x[r * ldx + c]; columns r in [rows, rows_pad) of outT are zero-filled so that the result
+// can be the K-major operand of a GEMM whose reduction axis (rows) must be a multiple of 64.  ldx may be smaller than cols
+// (overlapping windows: the implicit-GEMM view of a strided convolution's input).  outT is stored in `chunk`-column slabs,
+// element (c, r) at ((r / chunk) * cols + c) * chunk + r % chunk: chunk == rows_pad is the plain [cols, rows_pad] matrix, smaller
+// chunks lay the reduction axis out as a batch of GEMMs (split-K for the weight gradients of the conv stack, whose reduction
+// runs over >1e5 rows while the output has only a few dozen tiles).  `copy` (optional) receives the un-transposed cast copy.
+__global__ void __launch_bounds__(256) transpose_kernel(const void* __restrict__ x, int xdt, long long ldx, int rows, int cols,
+                                                        void* __restrict__ out, int odt, int rows_pad, int chunk,
+                                                        void* __restrict__ copy, long long ldcopy) {
   __shared__ float tile[32][33];
   pdl_launch_dependents();
   pdl_wait();
@@ -26,26 +52,31 @@ __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict_
 #pragma unroll
   for (int i = 0; i < 32; i += 8) {
     const int r = r0 + ty + i, c = c0 + tx;
-    tile[ty + i][tx] = (r < rows && c < cols) ? x[(long long)r * ldx + c] : 0.f;
+    const bool ok = r < rows && c < cols;
+    const float v = ok ? ld_any(x, xdt, (long long)r * ldx + c) : 0.f;
+    tile[ty + i][tx] = v;
+    if (copy != nullptr && ok) st_any(copy, odt, (long long)r * ldcopy + c, v);
   }
   __syncthreads();
 #pragma unroll
   for (int i = 0; i < 32; i += 8) {
     const int c = c0 + ty + i, r = r0 + tx;
-    if (c < cols && r < rows_pad) out[(long long)c * ldo + r] = from_f32<OutT>(tile[tx][ty + i]);
+    if (c < cols && r < rows_pad) {
+      const int s = r / chunk;
+      st_any(out, odt, ((long long)s * cols + c) * chunk + (r - s * chunk), tile[tx][ty + i]);
+    }
   }
 }
-template <typename OutT>
-__global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ x, long long n, OutT* __restrict__ out) {
+__global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ x, long long n, void* __restrict__ out, int odt) {
   pdl_launch_dependents();
   pdl_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    out[i] = from_f32<OutT>(x[i]);
+    st_any(out, odt, i, x[i]);
 }
 
 // ---- column sums (bias / LayerNorm-parameter gradients), deterministic: grid.y row slabs write partials, a second launch of
 // the same kernel (one slab) adds the partials up.
-__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, long long ldx, int rows, int cols, int rows_per_slab,
+__global__ void __launch_bounds__(256) colsum_kernel(const void* __restrict__ xv, int xdt, long long ldx, int rows, int cols, int rows_per_slab,
                                                      float* __restrict__ out, long long ldo, float scale) {
   pdl_launch_dependents();
   pdl_wait();
@@ -56,17 +87,17 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
   int r = r0;
   for (; r + 3 < r1; r += 4) {
-    s0 += x[(long long)r * ldx + c]; s1 += x[(long long)(r + 1) * ldx + c];
-    s2 += x[(long long)(r + 2) * ldx + c]; s3 += x[(long long)(r + 3) * ldx + c];
+    s0 += ld_any(xv, xdt, (long long)r * ldx + c); s1 += ld_any(xv, xdt, (long long)(r + 1) * ldx + c);
+    s2 += ld_any(xv, xdt, (long long)(r + 2) * ldx + c); s3 += ld_any(xv, xdt, (long long)(r + 3) * ldx + c);
   }
-  for (; r < r1; ++r) s0 += x[(long long)r * ldx + c];
+  for (; r < r1; ++r) s0 += ld_any(xv, xdt, (long long)r * ldx + c);
   out[(long long)blockIdx.y * ldo + c] = ((s0 + s1) + (s2 + s3)) * scale;
 }
 
 // ---- activations as separate passes (the training forward keeps the pre-activation z for the backward pass)
 //   act 1 GELU (erf), 2 ReLU, 3 GLU on interleaved (value, gate) column pairs: y[:, i] = z[:, 2i] * sigmoid(z[:, 2i+1]) * alpha
-__global__ void __launch_bounds__(256) act_fwd_kernel(int act, const float* __restrict__ z, long long ldz, int rows, int cols_out,
-                                                      float* __restrict__ y, long long ldy, float alpha) {
+__global__ void __launch_bounds__(256) act_fwd_kernel(int act, const void* __restrict__ z, int zdt, long long ldz, int rows, int cols_out,
+                                                      void* __restrict__ y, int ydt, long long ldy, float alpha) {
   pdl_launch_dependents();
   pdl_wait();
   const long long total = (long long)rows * cols_out;
@@ -75,40 +106,40 @@ __global__ void __launch_bounds__(256) act_fwd_kernel(int act, const float* __re
     const int c = (int)(i - r * cols_out);
     float v;
     if (act == CST_ACT_GLU) {
-      const float a = z[r * ldz + 2 * c], g = z[r * ldz + 2 * c + 1];
+      const float a = ld_any(z, zdt, r * ldz + 2 * c), g = ld_any(z, zdt, r * ldz + 2 * c + 1);
       v = a * (1.0f / (1.0f + expf(-g)));
     } else {
-      const float a = z[r * ldz + c];
+      const float a = ld_any(z, zdt, r * ldz + c);
       v = act == CST_ACT_GELU ? gelu_erf(a) : (act == CST_ACT_RELU ? fmaxf(a, 0.f) : a);
     }
-    y[r * ldy + c] = v * alpha;
+    st_any(y, ydt, r * ldy + c, v * alpha);
   }
 }
-__global__ void __launch_bounds__(256) act_bwd_kernel(int act, const float* __restrict__ z, long long ldz, const float* __restrict__ dy,
-                                                      long long ldy, int rows, int cols_out, float* __restrict__ dz, long long lddz,
-                                                      float alpha) {
+__global__ void __launch_bounds__(256) act_bwd_kernel(int act, const void* __restrict__ z, int zdt, long long ldz, const void* __restrict__ dy,
+                                                      int dydt, long long ldy, int rows, int cols_out, void* __restrict__ dz, int dzdt,
+                                                      long long lddz, float alpha) {
   pdl_launch_dependents();
   pdl_wait();
   const long long total = (long long)rows * cols_out;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / cols_out;
     const int c = (int)(i - r * cols_out);
-    const float g_out = dy[r * ldy + c] * alpha;
+    const float g_out = ld_any(dy, dydt, r * ldy + c) * alpha;
     if (act == CST_ACT_GLU) {
-      const float a = z[r * ldz + 2 * c], g = z[r * ldz + 2 * c + 1];
+      const float a = ld_any(z, zdt, r * ldz + 2 * c), g = ld_any(z, zdt, r * ldz + 2 * c + 1);
       const float s = 1.0f / (1.0f + expf(-g));
-      dz[r * lddz + 2 * c] = g_out * s;
-      dz[r * lddz + 2 * c + 1] = g_out * a * s * (1.0f - s);
+      st_any(dz, dzdt, r * lddz + 2 * c, g_out * s);
+      st_any(dz, dzdt, r * lddz + 2 * c + 1, g_out * a * s * (1.0f - s));
     } else if (act == CST_ACT_GELU) {
-      const float a = z[r * ldz + c];
+      const float a = ld_any(z, zdt, r * ldz + c);
       // d/dx [x Phi(x)] = Phi(x) + x phi(x)
       const float cdf = 0.5f * (1.0f + erff(a * 0.70710678118654752440f));
       const float pdf = 0.3989422804014327f * expf(-0.5f * a * a);
-      dz[r * lddz + c] = g_out * (cdf + a * pdf);
+      st_any(dz, dzdt, r * lddz + c, g_out * (cdf + a * pdf));
     } else if (act == CST_ACT_RELU) {
-      dz[r * lddz + c] = z[r * ldz + c] > 0.f ? g_out : 0.f;
+      st_any(dz, dzdt, r * lddz + c, ld_any(z, zdt, r * ldz + c) > 0.f ? g_out : 0.f);
     } else {
-      dz[r * lddz + c] = g_out;
+      st_any(dz, dzdt, r * lddz + c, g_out);
     }
   }
 }
@@ -192,7 +223,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
 // viewed with row pitch stride*C: output row m reads input rows stride*m .. stride*m + k - 1.  Its A-operand gradient
 // dcol [M, k*C] = dY W is scattered back: dx[r, c] = sum over taps t with (r - t) % stride == 0, m = (r - t) / stride in [0, M)
 // of dcol[m, t*C + c]   (gather form: deterministic).  Rows of filler / padding carry zero dY, so the flattened form is exact.
-__global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ dcol, long long M, int k, int stride, int C,
+__global__ void __launch_bounds__(256) col2im_kernel(const void* __restrict__ dcol, int cdt, long long M, int k, int stride, int C,
                                                      float* __restrict__ dx, long long rows_in, int accumulate) {
   pdl_launch_dependents();
   pdl_wait();
@@ -208,7 +239,7 @@ __global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ d
       if (d % stride) continue;
       const long long m = d / stride;
       if (m >= M) continue;
-      const float4 v = load4(dcol + m * (long long)k * C + (long long)t * C + c);
+      const float4 v = ld4_any(dcol, cdt, m * (long long)k * C + (long long)t * C + c);
       s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }
     float* o = dx + r * C + c;
@@ -221,7 +252,7 @@ __global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ d
 // else seg_valid); rows t >= valid of the OUTPUT segment range [0, n_rows_out) are zeroed when zero_rest.  The transpose of the
 // forward row remaps (zero-padded subsampler operands, masked projection rows).
 __global__ void __launch_bounds__(256) rows_remap_kernel(const float* __restrict__ in, long long ldi, int in_rps, int in_off,
-                                                         float* __restrict__ out, long long ldo, int out_rps, int out_off,
+                                                         void* __restrict__ out, int odt, long long ldo, int out_rps, int out_off,
                                                          int n_seg, int n_rows, int C, int seg_valid, const int32_t* __restrict__ seg_len,
                                                          int accumulate, float scale) {
   pdl_launch_dependents();
@@ -238,9 +269,9 @@ __global__ void __launch_bounds__(256) rows_remap_kernel(const float* __restrict
       v = load4(in + ((long long)seg * in_rps + t + in_off) * ldi + c);
       v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
     }
-    float* o = out + ((long long)seg * out_rps + t + out_off) * ldo + c;
-    if (accumulate) { const float4 p = load4(o); v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w; }
-    store4(o, v);
+    const long long oi = ((long long)seg * out_rps + t + out_off) * ldo + c;
+    if (accumulate) { const float4 p = ld4_any(out, odt, oi); v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w; }
+    st4_any(out, odt, oi, v);
   }
 }
 
@@ -255,54 +286,53 @@ static inline unsigned grid_for(long long n, int per = 256) {
   return (unsigned)b;
 }
 
-extern "C" int cst_transpose(const float* x, long long ldx, int rows, int cols, void* out, int out_dtype, long long ldo, int rows_pad,
-                             void* stream) {
-  CST_REQUIRE(x && out && rows > 0 && cols > 0 && rows_pad >= rows && ldo >= rows_pad, "cst_transpose: bad args rows=%d cols=%d", rows, cols);
+extern "C" int cst_transpose(const void* x, int x_dtype, long long ldx, int rows, int cols, void* out, int out_dtype, int rows_pad, int chunk,
+                             void* copy, long long ldcopy, void* stream) {
+  CST_REQUIRE(x && out && rows > 0 && cols > 0 && rows_pad >= rows, "cst_transpose: bad args rows=%d cols=%d", rows, cols);
+  if (chunk <= 0) chunk = rows_pad;
+  CST_REQUIRE(rows_pad % chunk == 0, "cst_transpose: rows_pad=%d must be a multiple of chunk=%d", rows_pad, chunk);
   dim3 grid(cdiv(rows_pad, 32), cdiv(cols, 32));
-  cudaStream_t st = (cudaStream_t)stream;
-  if (out_dtype == CST_F32) CST_CHECK_CUDA(launch_k(transpose_kernel<float>, grid, dim3(256), 0, st, x, ldx, rows, cols, (float*)out, ldo, rows_pad));
-  else if (out_dtype == CST_BF16) CST_CHECK_CUDA(launch_k(transpose_kernel<__nv_bfloat16>, grid, dim3(256), 0, st, x, ldx, rows, cols, (__nv_bfloat16*)out, ldo, rows_pad));
-  else CST_CHECK_CUDA(launch_k(transpose_kernel<__half>, grid, dim3(256), 0, st, x, ldx, rows, cols, (__half*)out, ldo, rows_pad));
+  CST_CHECK_CUDA(launch_k(transpose_kernel, grid, dim3(256), 0, (cudaStream_t)stream, x, x_dtype, ldx, rows, cols, out, out_dtype, rows_pad, chunk,
+                          copy, ldcopy));
   return CST_OK;
 }
 
 extern "C" int cst_cast(const float* x, long long n, void* out, int out_dtype, void* stream) {
   CST_REQUIRE(x && out && n > 0 && (out_dtype == CST_BF16 || out_dtype == CST_F16), "cst_cast: bad args");
-  cudaStream_t st = (cudaStream_t)stream;
-  if (out_dtype == CST_BF16) CST_CHECK_CUDA(launch_k(cast_kernel<__nv_bfloat16>, dim3(grid_for(n)), dim3(256), 0, st, x, n, (__nv_bfloat16*)out));
-  else CST_CHECK_CUDA(launch_k(cast_kernel<__half>, dim3(grid_for(n)), dim3(256), 0, st, x, n, (__half*)out));
+  CST_CHECK_CUDA(launch_k(cast_kernel, dim3(grid_for(n)), dim3(256), 0, (cudaStream_t)stream, x, n, out, out_dtype));
   return CST_OK;
 }
 
 // out[c] = scale * sum_r x[r, c]; ws: at least 64 * cols floats
-extern "C" int cst_colsum(const float* x, long long ldx, int rows, int cols, float* out, float* ws, float scale, void* stream) {
+extern "C" int cst_colsum(const void* x, int x_dtype, long long ldx, int rows, int cols, float* out, float* ws, float scale, void* stream) {
   CST_REQUIRE(x && out && ws && rows > 0 && cols > 0, "cst_colsum: bad args");
   cudaStream_t st = (cudaStream_t)stream;
   int slabs = rows >= 4096 ? 64 : (rows >= 256 ? 16 : 1);
   const int per = cdiv(rows, slabs);
   slabs = cdiv(rows, per);
   if (slabs == 1) {
-    CST_CHECK_CUDA(launch_k(colsum_kernel, dim3(cdiv(cols, 256), 1), dim3(256), 0, st, x, ldx, rows, cols, rows, out, (long long)cols, scale));
+    CST_CHECK_CUDA(launch_k(colsum_kernel, dim3(cdiv(cols, 256), 1), dim3(256), 0, st, x, x_dtype, ldx, rows, cols, rows, out, (long long)cols, scale));
   } else {
-    CST_CHECK_CUDA(launch_k(colsum_kernel, dim3(cdiv(cols, 256), slabs), dim3(256), 0, st, x, ldx, rows, cols, per, ws, (long long)cols, 1.0f));
-    CST_CHECK_CUDA(launch_k(colsum_kernel, dim3(cdiv(cols, 256), 1), dim3(256), 0, st, (const float*)ws, (long long)cols, slabs, cols, slabs, out,
-                            (long long)cols, scale));
+    CST_CHECK_CUDA(launch_k(colsum_kernel, dim3(cdiv(cols, 256), slabs), dim3(256), 0, st, x, x_dtype, ldx, rows, cols, per, ws, (long long)cols, 1.0f));
+    CST_CHECK_CUDA(launch_k(colsum_kernel, dim3(cdiv(cols, 256), 1), dim3(256), 0, st, (const void*)ws, (int)CST_F32, (long long)cols, slabs, cols, slabs,
+                            out, (long long)cols, scale));
   }
   return CST_OK;
 }
 
-extern "C" int cst_act_fwd(int act, const float* z, long long ldz, int rows, int cols_out, float* y, long long ldy, float alpha, void* stream) {
+extern "C" int cst_act_fwd(int act, const void* z, int z_dtype, long long ldz, int rows, int cols_out, void* y, int y_dtype, long long ldy,
+                           float alpha, void* stream) {
   CST_REQUIRE(z && y && rows > 0 && cols_out > 0 && act >= CST_ACT_NONE && act <= CST_ACT_GLU, "cst_act_fwd: bad args");
-  CST_CHECK_CUDA(launch_k(act_fwd_kernel, dim3(grid_for((long long)rows * cols_out)), dim3(256), 0, (cudaStream_t)stream, act, z, ldz, rows,
-                          cols_out, y, ldy, alpha));
+  CST_CHECK_CUDA(launch_k(act_fwd_kernel, dim3(grid_for((long long)rows * cols_out)), dim3(256), 0, (cudaStream_t)stream, act, z, z_dtype, ldz, rows,
+                          cols_out, y, y_dtype, ldy, alpha));
   return CST_OK;
 }
 
-extern "C" int cst_act_bwd(int act, const float* z, long long ldz, const float* dy, long long ldy, int rows, int cols_out, float* dz,
-                           long long lddz, float alpha, void* stream) {
+extern "C" int cst_act_bwd(int act, const void* z, int z_dtype, long long ldz, const void* dy, int dy_dtype, long long ldy, int rows, int cols_out,
+                           void* dz, int dz_dtype, long long lddz, float alpha, void* stream) {
   CST_REQUIRE(z && dy && dz && rows > 0 && cols_out > 0 && act >= CST_ACT_NONE && act <= CST_ACT_GLU, "cst_act_bwd: bad args");
-  CST_CHECK_CUDA(launch_k(act_bwd_kernel, dim3(grid_for((long long)rows * cols_out)), dim3(256), 0, (cudaStream_t)stream, act, z, ldz, dy, ldy,
-                          rows, cols_out, dz, lddz, alpha));
+  CST_CHECK_CUDA(launch_k(act_bwd_kernel, dim3(grid_for((long long)rows * cols_out)), dim3(256), 0, (cudaStream_t)stream, act, z, z_dtype, ldz, dy,
+                          dy_dtype, ldy, rows, cols_out, dz, dz_dtype, lddz, alpha));
   return CST_OK;
 }
 
@@ -321,17 +351,19 @@ extern "C" int cst_layernorm_bwd(const float* x, long long ldx, const float* gam
   return CST_OK;
 }
 
-extern "C" int cst_col2im(const float* dcol, long long M, int k, int stride, int C, float* dx, long long rows_in, int accumulate, void* stream) {
+extern "C" int cst_col2im(const void* dcol, int dcol_dtype, long long M, int k, int stride, int C, float* dx, long long rows_in, int accumulate,
+                          void* stream) {
   CST_REQUIRE(dcol && dx && M > 0 && k > 0 && stride > 0 && C % 4 == 0 && rows_in > 0, "cst_col2im: bad args");
-  CST_CHECK_CUDA(launch_k(col2im_kernel, dim3(grid_for(rows_in * (C / 4))), dim3(256), 0, (cudaStream_t)stream, dcol, M, k, stride, C, dx,
+  CST_CHECK_CUDA(launch_k(col2im_kernel, dim3(grid_for(rows_in * (C / 4))), dim3(256), 0, (cudaStream_t)stream, dcol, dcol_dtype, M, k, stride, C, dx,
                           rows_in, accumulate));
   return CST_OK;
 }
 
-extern "C" int cst_rows_remap(const float* in, long long ldi, int in_rps, int in_off, float* out, long long ldo, int out_rps, int out_off,
-                              int n_seg, int n_rows, int C, int seg_valid, const int32_t* seg_len, int accumulate, float scale, void* stream) {
-  CST_REQUIRE(in && out && n_seg > 0 && n_rows > 0 && C % 4 == 0, "cst_rows_remap: bad args");
+extern "C" int cst_rows_remap(const float* in, long long ldi, int in_rps, int in_off, void* out, int out_dtype, long long ldo, int out_rps,
+                              int out_off, int n_seg, int n_rows, int C, int seg_valid, const int32_t* seg_len, int accumulate, float scale,
+                              void* stream) {
+  CST_REQUIRE(in && out && n_seg > 0 && n_rows > 0 && C % 4 == 0 && ldo % 4 == 0, "cst_rows_remap: bad args");
   CST_CHECK_CUDA(launch_k(rows_remap_kernel, dim3(grid_for((long long)n_seg * n_rows * (C / 4))), dim3(256), 0, (cudaStream_t)stream, in, ldi,
-                          in_rps, in_off, out, ldo, out_rps, out_off, n_seg, n_rows, C, seg_valid, seg_len, accumulate, scale));
+                          in_rps, in_off, out, out_dtype, ldo, out_rps, out_off, n_seg, n_rows, C, seg_valid, seg_len, accumulate, scale));
   return CST_OK;
 }

@@ -79,7 +79,6 @@ __global__ void __launch_bounds__(CB_C) conv0_bwd_kernel(const float* __restrict
 extern "C" int cst_conv0_bwd(const float* wave, int B, int L, const float* w, const float* gamma, const float* beta,
                              const float* scale_shift, const float* dout, int rows_per_seg, float* dw, float* dgamma, float* dbeta,
                              float* ws, float grad_scale, void* stream);
-extern "C" int cst_colsum(const float* x, long long ldx, int rows, int cols, float* out, float* ws, float scale, void* stream);
 
 extern "C" int cst_conv0_bwd(const float* wave, int B, int L, const float* w, const float* gamma, const float* beta,
                              const float* scale_shift, const float* dout, int rows_per_seg, float* dw, float* dgamma, float* dbeta,
@@ -98,15 +97,15 @@ extern "C" int cst_conv0_bwd(const float* wave, int B, int L, const float* w, co
   CST_CHECK_CUDA(launch_k(conv0_bwd_kernel<0>, dim3(n_chunks, B), dim3(CB_C), 0, st, wave, L, T0, rows_per_seg, w, gamma, beta, ss, dout,
                           (const float*)nullptr, part, n_chunks));
   for (int b = 0; b < B; ++b) {
-    int rc = cst_colsum(part + (size_t)b * n_chunks * 2 * CB_C, 2 * CB_C, n_chunks, 2 * CB_C, sums + (size_t)b * 2 * CB_C, red_ws, 1.0f, stream);
+    int rc = cst_colsum(part + (size_t)b * n_chunks * 2 * CB_C, CST_F32, 2 * CB_C, n_chunks, 2 * CB_C, sums + (size_t)b * 2 * CB_C, red_ws, 1.0f, stream);
     if (rc) return rc;
   }
   // dbeta = sum_b S1, dgamma = sum_b S2 (rows of `sums` are [b][S1 | S2])
-  int rc = cst_colsum(sums, 2 * CB_C, B, CB_C, dbeta, red_ws, grad_scale, stream);
+  int rc = cst_colsum(sums, CST_F32, 2 * CB_C, B, CB_C, dbeta, red_ws, grad_scale, stream);
   if (rc) return rc;
-  rc = cst_colsum(sums + CB_C, 2 * CB_C, B, CB_C, dgamma, red_ws, grad_scale, stream);
+  rc = cst_colsum(sums + CB_C, CST_F32, 2 * CB_C, B, CB_C, dgamma, red_ws, grad_scale, stream);
   if (rc) return rc;
   CST_CHECK_CUDA(launch_k(conv0_bwd_kernel<1>, dim3(n_chunks, B), dim3(CB_C), 0, st, wave, L, T0, rows_per_seg, w, gamma, beta, ss, dout,
                           (const float*)sums, part, n_chunks));
-  return cst_colsum(part, CB_C * CB_K, B * n_chunks, CB_C * CB_K, dw, red_ws, grad_scale, stream);
+  return cst_colsum(part, CST_F32, CB_C * CB_K, B * n_chunks, CB_C * CB_K, dw, red_ws, grad_scale, stream);
 }

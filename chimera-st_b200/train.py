@@ -26,25 +26,34 @@ from .synth import W2V_DIM, W2V_FFN, W2V_HEADS, W2V_LAYERS, ENC_DIM, ENC_FFN, EN
 F32 = torch.float32
 
 
-class _Ops:
-    """Thin launch helpers over the C ABI (device tensors in / out, current stream)."""
+_CODE = {torch.float32: L.F32, torch.bfloat16: L.BF16, torch.float16: L.F16}
+SM_COUNT = 148
 
-    def __init__(self, device):
+
+class _Ops:
+    """Thin launch helpers over the C ABI (device tensors in / out, current stream).  `op` is the dtype of GEMM operands and of the
+    pre-activations kept on the tape (fp32: the parity mode; bf16: BASELINE configs[4]); gradients of activations are always fp32."""
+
+    def __init__(self, device, op=F32):
         self.lib = L.load()
         self.dev = device
-        self.ws = torch.empty(64 * 8192 + 1024, dtype=F32, device=device)       # cst_colsum scratch
+        self.op = op
+        self.opc = _CODE[op]
+        self.esz = 4 if op == F32 else 2
+        self.ws = torch.empty(64 * 8192 + 1024, dtype=F32, device=device)       # cst_colsum scratch (<= 8192 columns per call)
 
     def st(self):
         return L.stream_ptr()
 
-    def new(self, *shape, zero=False):
-        return (torch.zeros if zero else torch.empty)(*shape, dtype=F32, device=self.dev)
+    def new(self, *shape, zero=False, dtype=F32):
+        return (torch.zeros if zero else torch.empty)(*shape, dtype=dtype, device=self.dev)
 
     def gemm(self, A, W, Cout, M, N, K, lda, a_rows, bias=None, residual=None, rows_per_seg=None, seg_len=None,
              nb_outer=1, nb_inner=1, a_bs=(0, 0), w_bs=0, c_bs=(0, 0), bias_bs=0, ldc=None):
+        assert A.dtype == W.dtype, (A.dtype, W.dtype)
         p = L.GemmParams()
         p.A, p.W, p.bias, p.residual, p.C = A.data_ptr(), W.data_ptr(), L.ptr(bias), L.ptr(residual), Cout.data_ptr()
-        p.ab_dtype, p.c_dtype = L.F32, L.F32
+        p.ab_dtype, p.c_dtype = _CODE[A.dtype], _CODE[Cout.dtype]
         p.M, p.N, p.K, p.lda = M, N, K, lda
         p.ldc = ldc if ldc is not None else Cout.shape[-1]
         p.ldr = p.ldc if residual is not None else 0
@@ -63,54 +72,85 @@ class _Ops:
         L.check(self.lib.cst_gemm(C.byref(p), self.st()))
         return Cout
 
-    def linear(self, x, W, b=None, residual=None, rows=None):
+    def linear(self, x, W, b=None, residual=None, rows=None, out_dtype=F32):
         rows = rows if rows is not None else x.shape[0]
         N, K = W.shape
-        return self.gemm(x, W, self.new(rows, N), rows, N, K, lda=x.shape[1], a_rows=x.shape[0], bias=b, residual=residual)
+        return self.gemm(x, W, self.new(rows, N, dtype=out_dtype), rows, N, K, lda=x.shape[1], a_rows=x.shape[0], bias=b, residual=residual)
 
-    def transpose(self, x, rows, cols, ldx=None, pad=64):
-        rp = (rows + pad - 1) // pad * pad
-        out = self.new(cols, rp)
-        L.check(self.lib.cst_transpose(x.data_ptr(), ldx if ldx is not None else x.shape[1], rows, cols, out.data_ptr(), L.F32, rp, rp,
-                                       self.st()))
-        return out
+    def transpose(self, x, rows, cols, ldx=None, pad=64, chunks=1, copy=False, out_dtype=None):
+        """-> x^T [chunks, cols, rows_pad / chunks] in `out_dtype` (default: the operand dtype), zero-filled beyond `rows`
+        (+ the un-transposed cast copy [rows, cols] when copy=True)."""
+        od = out_dtype or self.op
+        per = ((rows + chunks - 1) // chunks + pad - 1) // pad * pad
+        rp = per * chunks
+        out = self.new(chunks, cols, per, dtype=od)
+        cp = self.new(rows, cols, dtype=od) if copy else None
+        L.check(self.lib.cst_transpose(x.data_ptr(), _CODE[x.dtype], ldx if ldx is not None else x.shape[1], rows, cols, out.data_ptr(), _CODE[od],
+                                       rp, per, L.ptr(cp), cols, self.st()))
+        return (out, cp) if copy else out
 
     def colsum(self, x, rows, cols, ldx=None, scale=1.0):
         out = self.new(cols)
-        L.check(self.lib.cst_colsum(x.data_ptr(), ldx if ldx is not None else x.shape[1], rows, cols, out.data_ptr(), self.ws.data_ptr(),
-                                    scale, self.st()))
+        for c0 in range(0, cols, 8192):                            # the scratch buffer bounds the columns of one call
+            n = min(8192, cols - c0)
+            L.check(self.lib.cst_colsum(x.data_ptr() + c0 * x.element_size(), _CODE[x.dtype], ldx if ldx is not None else x.shape[1], rows, n,
+                                        out.data_ptr() + 4 * c0, self.ws.data_ptr(), scale, self.st()))
         return out
 
-    def linear_bwd(self, x, W, dy, rows, need_dx=True, dx_residual=None, bias=True):
-        """y = x W^T + b  ->  (dx = dy W (+ dx_residual), dW = dy^T x, db = colsum(dy))."""
+    def wgrad(self, dy, x, rows, N, K, ldx=None):
+        """dW [N, K] = dy[:rows]^T x[:rows] (fp32), dy fp32 [rows, N], x operand dtype (row pitch ldx: < K for the overlapping windows
+        of an implicit-GEMM convolution).  Also returns the operand-dtype copy of dy for the dgrad GEMM.  When the output has few
+        tiles and the reduction is long (the conv stack: 24 tiles, > 1e5 rows) the row axis is split into a GEMM batch (split-K) and
+        the partial products are added by cst_colsum in a fixed order."""
+        tiles = ((N + 127) // 128) * ((K + 255) // 256)
+        S = max(1, min(SM_COUNT // tiles, rows // 1024))
+        if self.op == F32:
+            dyT, dy_op = self.transpose(dy, rows, N, chunks=S), dy
+        else:
+            dyT, dy_op = self.transpose(dy, rows, N, chunks=S, copy=True)
+        xT = self.transpose(x, rows, K, ldx=ldx, chunks=S)
+        per = dyT.shape[2]
+        if S == 1:
+            dW = self.gemm(dyT, xT, self.new(N, K), N, K, per, lda=per, a_rows=N)
+        else:
+            part = self.gemm(dyT, xT, self.new(S, N * K), N, K, per, lda=per, a_rows=N, nb_inner=S, a_bs=(0, N * per), w_bs=K * per,
+                             c_bs=(0, N * K), ldc=K)
+            dW = self.colsum(part, S, N * K).view(N, K)
+        return dW, dy_op
+
+    def linear_bwd(self, x, W, dy, rows, need_dx=True, dx_residual=None, bias=True, ldx=None, dx_dtype=F32):
+        """y = x W^T + b  ->  (dx = dy W (+ dx_residual), dW = dy^T x, db = colsum(dy)); x / W in the operand dtype, dy fp32."""
         N, K = W.shape
+        dW, dy_op = self.wgrad(dy, x, rows, N, K, ldx=ldx)
         dx = None
         if need_dx:
-            Wt = self.transpose(W, N, K)                         # [K, N] (N is a multiple of 64 on this path)
-            dx = self.gemm(dy, Wt, self.new(rows, K), rows, K, N, lda=dy.shape[1], a_rows=dy.shape[0], residual=dx_residual)
-        dyT = self.transpose(dy, rows, N)                        # [N, rows_pad]
-        xT = self.transpose(x, rows, K)                          # [K, rows_pad]
-        dW = self.gemm(dyT, xT, self.new(N, K), N, K, dyT.shape[1], lda=dyT.shape[1], a_rows=N)
+            Wt = self.transpose(W, N, K)[0]                        # [K, N] (N is a multiple of 64 on this path)
+            dx = self.gemm(dy_op, Wt, self.new(rows, K, dtype=dx_dtype), rows, K, N, lda=dy_op.shape[1], a_rows=dy_op.shape[0],
+                           residual=dx_residual)
         db = self.colsum(dy, rows, N) if bias else None
         return dx, dW, db
 
-    def act(self, kind, z, rows, cols_out, alpha=1.0):
-        y = self.new(rows, cols_out)
-        L.check(self.lib.cst_act_fwd(kind, z.data_ptr(), z.shape[1], rows, cols_out, y.data_ptr(), cols_out, alpha, self.st()))
+    def act(self, kind, z, rows, cols_out, alpha=1.0, out_dtype=None, out=None):
+        y = out if out is not None else self.new(rows, cols_out, dtype=out_dtype or self.op)
+        L.check(self.lib.cst_act_fwd(kind, z.data_ptr(), _CODE[z.dtype], z.shape[1], rows, cols_out, y.data_ptr(), _CODE[y.dtype], y.shape[1],
+                                     alpha, self.st()))
         return y
 
     def act_bwd(self, kind, z, dy, rows, cols_out, alpha=1.0):
         dz = self.new(rows, z.shape[1])
-        L.check(self.lib.cst_act_bwd(kind, z.data_ptr(), z.shape[1], dy.data_ptr(), dy.shape[1], rows, cols_out, dz.data_ptr(), z.shape[1],
-                                     alpha, self.st()))
+        L.check(self.lib.cst_act_bwd(kind, z.data_ptr(), _CODE[z.dtype], z.shape[1], dy.data_ptr(), _CODE[dy.dtype], dy.shape[1], rows, cols_out,
+                                     dz.data_ptr(), L.F32, z.shape[1], alpha, self.st()))
         return dz
 
-    def ln(self, x, g, b, rows):
-        out = self.new(rows, x.shape[1])
+    def ln(self, x, g, b, rows, f32=True):
+        """-> (fp32 normalised rows or None, operand-dtype copy); in the fp32 mode both are the same tensor."""
         Cd = x.shape[1]
-        L.check(self.lib.cst_layernorm(x.data_ptr(), Cd, g.data_ptr(), b.data_ptr(), out.data_ptr(), 0, L.F32, Cd, rows, Cd, rows, rows, rows,
-                                       0, 0, self.st()))
-        return out
+        lowp = self.op != F32
+        out = self.new(rows, Cd) if (f32 or not lowp) else None
+        lp = self.new(rows, Cd, dtype=self.op) if lowp else None
+        L.check(self.lib.cst_layernorm(x.data_ptr(), Cd, g.data_ptr(), b.data_ptr(), L.ptr(out), L.ptr(lp), self.opc if lowp else L.F32, Cd, rows,
+                                       Cd, rows, rows, rows, 0, 0, self.st()))
+        return out, (lp if lowp else out)
 
     def ln_bwd(self, x, g, dy, rows, dx=None):
         """-> (dx (accumulated into `dx` when given), dgamma, dbeta)"""
@@ -125,23 +165,24 @@ class _Ops:
         return dx, gb[:Cd], gb[Cd:]
 
     def attention(self, q, k, v, ldq, ldkv, B, H, n_q, q_rps, n_kv, kv_rps, kv_len, out_rows, out_cols):
-        out = self.new(out_rows, out_cols, zero=True)
-        L.check(self.lib.cst_attention(q, k, v, out.data_ptr(), L.F32, ldq, ldkv, out_cols, B, H, n_q, q_rps, n_kv, kv_rps, L.ptr(kv_len),
+        out = self.new(out_rows, out_cols, zero=True, dtype=self.op)
+        L.check(self.lib.cst_attention(q, k, v, out.data_ptr(), self.opc, ldq, ldkv, out_cols, B, H, n_q, q_rps, n_kv, kv_rps, L.ptr(kv_len),
                                        self.st()))
         return out
 
-    def attention_bwd(self, q, k, v, o, do, dq, dk, dv, ldq, ldkv, ldo, B, H, n_q, q_rps, n_kv, kv_rps, kv_len):
-        L.check(self.lib.cst_attention_bwd(q, k, v, o.data_ptr(), do.data_ptr(), dq, dk, dv, ldq, ldkv, ldo, B, H, n_q, q_rps, n_kv, kv_rps,
-                                           L.ptr(kv_len), self.st()))
+    def attention_bwd(self, q, k, v, o, do, dq, dk, dv, ldq, ldkv, ldo, B, H, n_q, q_rps, n_kv, kv_rps, kv_len, dtype=None):
+        """q / k / v / o: forward tensors (operand dtype, row strides ldq / ldkv / ldo); do, dq, dk, dv fp32 with the SAME row strides."""
+        L.check(self.lib.cst_attention_bwd(q, k, v, o.data_ptr(), _CODE[o.dtype] if dtype is None else dtype, do.data_ptr(), dq, dk, dv,
+                                           ldq, ldkv, ldo, ldo, ldq, ldkv, B, H, n_q, q_rps, n_kv, kv_rps, L.ptr(kv_len), self.st()))
 
     def remap(self, src, in_rps, in_off, dst, out_rps, out_off, n_seg, n_rows, Cd, valid, seg_len=None, accumulate=False, scale=1.0):
-        L.check(self.lib.cst_rows_remap(src.data_ptr(), src.shape[1], in_rps, in_off, dst.data_ptr(), dst.shape[1], out_rps, out_off, n_seg,
-                                        n_rows, Cd, valid, L.ptr(seg_len), 1 if accumulate else 0, scale, self.st()))
+        L.check(self.lib.cst_rows_remap(src.data_ptr(), src.shape[1], in_rps, in_off, dst.data_ptr(), _CODE[dst.dtype], dst.shape[1], out_rps,
+                                        out_off, n_seg, n_rows, Cd, valid, L.ptr(seg_len), 1 if accumulate else 0, scale, self.st()))
         return dst
 
     def col2im(self, dcol, M, k, stride, Cd, rows_in):
         dx = self.new(rows_in, Cd)
-        L.check(self.lib.cst_col2im(dcol.data_ptr(), M, k, stride, Cd, dx.data_ptr(), rows_in, 0, self.st()))
+        L.check(self.lib.cst_col2im(dcol.data_ptr(), _CODE[dcol.dtype], M, k, stride, Cd, dx.data_ptr(), rows_in, 0, self.st()))
         return dx
 
 
@@ -153,23 +194,30 @@ def _attn_layer_grads(G, name, dqkv_w, dqkv_b, D, fused=True):
 
 
 class EncoderTrainStep:
-    def __init__(self, state_dict, B, Lw, M=None, device="cuda", feature_grad_mult=0.1):
+    def __init__(self, state_dict, B, Lw, M=None, device="cuda", feature_grad_mult=0.1, dtype=F32):
         dev = torch.device(device)
         if dev.type != "cuda":
             raise L.CstError("EncoderTrainStep runs only on a CUDA device (no CPU fallback)")
+        if dtype not in (F32, torch.bfloat16):
+            raise L.CstError("EncoderTrainStep: dtype must be torch.float32 or torch.bfloat16")
         sd = _weights._strip(state_dict)
         self.sd = {k: v.detach().to(dev, F32) for k, v in sd.items() if v.is_floating_point()}
         self.M = M or self.sd["interlingua_embedding.weight"].shape[0]
         self.g = Geometry(B, Lw, self.M)
         self.dev = dev
-        self.o = _Ops(dev)
+        self.op = dtype
+        self.o = _Ops(dev, dtype)
         self.fgm = float(feature_grad_mult)
-        self.P = _weights.prepare(self.sd, dev, F32)
+        # 16-bit mode: the normalisation-free conv stack runs its FORWARD GEMMs on fp16 operands like the inference path (DESIGN.md §2:
+        # bf16 there costs 6e-3 of the 1e-2 budget); every backward operand (transposed copies of weights, activations, gradients)
+        # is bf16 -- gradients need the range, and cst_transpose converts on the fly.
+        self.cdt = dtype if dtype == F32 else torch.float16
+        self.P = _weights.prepare(self.sd, dev, dtype, conv_dtype=self.cdt)
 
     # ------------------------------------------------------------------ forward (activations kept)
     def forward(self, wave, lens):
         o, g, P, lib = self.o, self.g, self.P, self.o.lib
-        B, st = g.B, self.o.st()
+        B, st, op, opc, esz = g.B, self.o.st(), self.op, self.o.opc, self.o.esz
         T = {}                                                     # the tape
         self.T = T
         wave = wave.to(self.dev, F32).contiguous()
@@ -184,84 +232,85 @@ class EncoderTrainStep:
         stats_ws = torch.zeros(B * 72, dtype=torch.float64, device=self.dev)
         L.check(lib.cst_conv0_stats(wave.data_ptr(), B, g.L, P["conv0_w"].data_ptr(), P["gn_g"].data_ptr(), P["gn_b"].data_ptr(),
                                     ss.data_ptr(), stats_ws.data_ptr(), st))
-        c = o.new(B * g.Ta[0] + SLACK, 512, zero=True)
-        L.check(lib.cst_conv0_apply(wave.data_ptr(), B, g.L, P["conv0_w"].data_ptr(), ss.data_ptr(), c.data_ptr(), L.F32, g.Ta[0], st))
+        cdt = self.cdt
+        c = o.new(B * g.Ta[0] + SLACK, 512, zero=True, dtype=cdt)
+        L.check(lib.cst_conv0_apply(wave.data_ptr(), B, g.L, P["conv0_w"].data_ptr(), ss.data_ptr(), c.data_ptr(), _CODE[cdt], g.Ta[0], st))
         T["ss"] = ss
         T["c"], T["cz"] = [c], [None]
         for i in range(1, 7):
             w = P[f"conv{i}_w"]
             rows = B * g.Ta[i]
-            z = o.gemm(c, w, o.new(rows, 512), rows, 512, w.shape[1], lda=1024, a_rows=(B * g.Ta[i - 1] + SLACK) // 2)
-            cn = o.new(rows + SLACK, 512, zero=True)
-            L.check(lib.cst_act_fwd(L.ACT_GELU, z.data_ptr(), 512, rows, 512, cn.data_ptr(), 512, 1.0, st))
+            z = o.gemm(c, w, o.new(rows, 512, dtype=cdt), rows, 512, w.shape[1], lda=1024, a_rows=(B * g.Ta[i - 1] + SLACK) // 2)
+            cn = o.new(rows + SLACK, 512, zero=True, dtype=(cdt if i < 6 else F32))     # the last block feeds a LayerNorm: fp32
+            o.act(L.ACT_GELU, z, rows, 512, out=cn)
             T["c"].append(cn)
             T["cz"].append(z)
             c = cn
         R = B * g.T6a
         feat = c
-        feat_ln = o.ln(feat, P["ln_feat_g"], P["ln_feat_b"], R)
+        _, feat_ln = o.ln(feat, P["ln_feat_g"], P["ln_feat_b"], R, f32=False)
         xp = o.gemm(feat_ln, P["proj_w"], o.new(R, W2V_DIM), R, W2V_DIM, 512, lda=512, a_rows=R, bias=P["proj_b"], rows_per_seg=g.T6a,
                     seg_len=w2v_valid)
         T["feat_ln"], T["xp"] = feat_ln, xp
         # ---- pos-conv (grouped implicit GEMM on the packed operand), GELU, residual
-        xg = torch.zeros(B * 16 * g.Tpp + SLACK, 64, dtype=F32, device=self.dev)
-        L.check(lib.cst_posconv_pack(xp.data_ptr(), B, g.T6a, g.Tp, xg.data_ptr(), L.F32, g.Tpp, st))
-        zpos = o.gemm(xg, P["pos_w"], o.new(R, W2V_DIM), g.T6a, 48, 128 * 64, lda=64, a_rows=g.Tpp, bias=P["pos_b"], nb_outer=B, nb_inner=16,
-                      a_bs=(16 * g.Tpp * 64, g.Tpp * 64), w_bs=48 * 128 * 64, c_bs=(g.T6a * W2V_DIM, 48), bias_bs=48, ldc=W2V_DIM)
+        xg = torch.zeros(B * 16 * g.Tpp + SLACK, 64, dtype=op, device=self.dev)
+        L.check(lib.cst_posconv_pack(xp.data_ptr(), B, g.T6a, g.Tp, xg.data_ptr(), opc, g.Tpp, st))
+        zpos = o.gemm(xg, P["pos_w"], o.new(R, W2V_DIM), g.T6a, 48, 128 * 64, lda=64, a_rows=g.Tpp, bias=P["pos_b"], nb_outer=B,
+                      nb_inner=16, a_bs=(16 * g.Tpp * 64, g.Tpp * 64), w_bs=48 * 128 * 64, c_bs=(g.T6a * W2V_DIM, 48), bias_bs=48, ldc=W2V_DIM)
         y0 = xp.clone()
-        gp = o.act(L.ACT_GELU, zpos, R, W2V_DIM)
+        gp = o.act(L.ACT_GELU, zpos, R, W2V_DIM, out_dtype=F32)
         o.remap(gp, R, 0, y0, R, 0, 1, R, W2V_DIM, R, accumulate=True)
         T["xg"], T["zpos"], T["y0"] = xg, zpos, y0
-        x = o.ln(y0, P["ln_enc_g"], P["ln_enc_b"], R)
+        x, x_op = o.ln(y0, P["ln_enc_g"], P["ln_enc_b"], R)
         # ---- 12 post-LN wav2vec2 layers
         D = W2V_DIM
         T["w2v"] = []
         for lw in P["w2v_layers"]:
-            t = {"x": x}
-            qkv = o.linear(x, lw["qkv_w"], lw["qkv_b"])
+            t = {"x_op": x_op}
+            qkv = o.linear(x_op, lw["qkv_w"], lw["qkv_b"], out_dtype=op)
             qp = qkv.data_ptr()
-            ctx = o.attention(qp, qp + 4 * D, qp + 8 * D, 3 * D, 3 * D, B, W2V_HEADS, g.T6a, g.T6a, g.Tp, g.T6a, w2v_valid, R, D)
+            ctx = o.attention(qp, qp + esz * D, qp + 2 * esz * D, 3 * D, 3 * D, B, W2V_HEADS, g.T6a, g.T6a, g.Tp, g.T6a, w2v_valid, R, D)
             y1 = o.linear(ctx, lw["o_w"], lw["o_b"], residual=x)
-            x1 = o.ln(y1, lw["ln1_g"], lw["ln1_b"], R)
-            z = o.linear(x1, lw["fc1_w"], lw["fc1_b"])
+            x1, x1_op = o.ln(y1, lw["ln1_g"], lw["ln1_b"], R)
+            z = o.linear(x1_op, lw["fc1_w"], lw["fc1_b"])           # fp32 pre-activation: h is rounded once, as in the fused epilogue
             h = o.act(L.ACT_GELU, z, R, W2V_FFN)
             y2 = o.linear(h, lw["fc2_w"], lw["fc2_b"], residual=x1)
-            x = o.ln(y2, lw["ln2_g"], lw["ln2_b"], R)
-            t.update(qkv=qkv, ctx=ctx, y1=y1, x1=x1, z=z, h=h, y2=y2)
+            x, x_op = o.ln(y2, lw["ln2_g"], lw["ln2_b"], R)
+            t.update(qkv=qkv, ctx=ctx, y1=y1, x1_op=x1_op, z=z, h=h, y2=y2)
             T["w2v"].append(t)
         T["w2v_out"] = x
         # ---- subsampler: zero-padded operands, conv + GLU twice
-        sub_in = torch.zeros(B * g.Tin1 + SLACK, D, dtype=F32, device=self.dev)
+        sub_in = torch.zeros(B * g.Tin1 + SLACK, D, dtype=op, device=self.dev)
         o.remap(x, g.T6a, 0, sub_in, g.Tin1, 2, B, g.Tp, D, g.Tp)
         w0, w1 = P["sub0_w"], P["sub1_w"]
-        zs0 = o.gemm(sub_in, w0, o.new(B * g.T1a, w0.shape[0]), B * g.T1a, w0.shape[0], w0.shape[1], lda=2 * D, a_rows=(B * g.Tin1 + SLACK) // 2,
-                     bias=P["sub0_b"])
-        s0 = o.act(L.ACT_GLU, zs0, B * g.T1a, ENC_DIM)
-        sub_mid = torch.zeros(B * g.Tin2 + SLACK, ENC_DIM, dtype=F32, device=self.dev)
+        zs0 = o.gemm(sub_in, w0, o.new(B * g.T1a, w0.shape[0]), B * g.T1a, w0.shape[0], w0.shape[1], lda=2 * D,
+                     a_rows=(B * g.Tin1 + SLACK) // 2, bias=P["sub0_b"])
+        s0 = o.act(L.ACT_GLU, zs0, B * g.T1a, ENC_DIM, out_dtype=F32)
+        sub_mid = torch.zeros(B * g.Tin2 + SLACK, ENC_DIM, dtype=op, device=self.dev)
         o.remap(s0, g.T1a, 0, sub_mid, g.Tin2, 2, B, g.T1, ENC_DIM, g.T1)
         zs1 = o.gemm(sub_mid, w1, o.new(B * g.T2a, w1.shape[0]), B * g.T2a, w1.shape[0], w1.shape[1], lda=2 * ENC_DIM,
                      a_rows=(B * g.Tin2 + SLACK) // 2, bias=P["sub1_b"])
         R2 = B * g.T2a
-        x2 = o.act(L.ACT_GLU, zs1, R2, ENC_DIM, alpha=math.sqrt(ENC_DIM))
+        x2 = o.act(L.ACT_GLU, zs1, R2, ENC_DIM, alpha=math.sqrt(ENC_DIM), out_dtype=F32)
         T.update(sub_in=sub_in, zs0=zs0, sub_mid=sub_mid, zs1=zs1)
         # ---- 6 pre-LN shared layers
         D2 = ENC_DIM
         T["enc"] = []
         for lw in P["enc_layers"]:
             t = {"x_in": x2}
-            a = o.ln(x2, lw["ln1_g"], lw["ln1_b"], R2)
-            qkv = o.linear(a, lw["qkv_w"], lw["qkv_b"])
+            _, a = o.ln(x2, lw["ln1_g"], lw["ln1_b"], R2, f32=False)
+            qkv = o.linear(a, lw["qkv_w"], lw["qkv_b"], out_dtype=op)
             qp = qkv.data_ptr()
-            ctx = o.attention(qp, qp + 4 * D2, qp + 8 * D2, 3 * D2, 3 * D2, B, ENC_HEADS, g.T2a, g.T2a, g.T2, g.T2a, sub_valid, R2, D2)
+            ctx = o.attention(qp, qp + esz * D2, qp + 2 * esz * D2, 3 * D2, 3 * D2, B, ENC_HEADS, g.T2a, g.T2a, g.T2, g.T2a, sub_valid, R2, D2)
             xm = o.linear(ctx, lw["o_w"], lw["o_b"], residual=x2)
-            b_ = o.ln(xm, lw["ln2_g"], lw["ln2_b"], R2)
+            _, b_ = o.ln(xm, lw["ln2_g"], lw["ln2_b"], R2, f32=False)
             z = o.linear(b_, lw["fc1_w"], lw["fc1_b"])
             h = o.act(L.ACT_RELU, z, R2, ENC_FFN)
             x2 = o.linear(h, lw["fc2_w"], lw["fc2_b"], residual=xm)
             t.update(a=a, qkv=qkv, ctx=ctx, xm=xm, b=b_, z=z, h=h)
             T["enc"].append(t)
         T["x2_out"] = x2
-        h_enc = o.ln(x2, P["ln_out_g"], P["ln_out_b"], R2)
+        h_enc, _ = o.ln(x2, P["ln_out_g"], P["ln_out_b"], R2)
         T["h_enc"] = h_enc
         # ---- memory stage: M learned queries over ALL T2 frames, per-layer affine LN1 of h_enc (un-folded: training form)
         Mq, RM = self.M, B * self.M
@@ -270,14 +319,14 @@ class EncoderTrainStep:
         T["mem"] = []
         for lw in P["mem_layers"]:
             t = {"m_in": mem}
-            a = o.ln(mem, lw["ln1_g"], lw["ln1_b"], RM)
-            kv_in = o.ln(h_enc, lw["ln1_g"], lw["ln1_b"], R2)
-            q = o.linear(a, lw["q_w"], lw["q_b"])
-            kv = o.linear(kv_in, lw["kv_w"], lw["kv_b"])
+            _, a = o.ln(mem, lw["ln1_g"], lw["ln1_b"], RM, f32=False)
+            _, kv_in = o.ln(h_enc, lw["ln1_g"], lw["ln1_b"], R2, f32=False)
+            q = o.linear(a, lw["q_w"], lw["q_b"], out_dtype=op)
+            kv = o.linear(kv_in, lw["kv_w"], lw["kv_b"], out_dtype=op)
             kp = kv.data_ptr()
-            ctx = o.attention(q.data_ptr(), kp, kp + 4 * D2, D2, 2 * D2, B, ENC_HEADS, Mq, Mq, g.T2, g.T2a, None, RM, D2)
+            ctx = o.attention(q.data_ptr(), kp, kp + esz * D2, D2, 2 * D2, B, ENC_HEADS, Mq, Mq, g.T2, g.T2a, None, RM, D2)
             mm = o.linear(ctx, lw["o_w"], lw["o_b"], residual=mem)
-            b_ = o.ln(mm, lw["ln2_g"], lw["ln2_b"], RM)
+            _, b_ = o.ln(mm, lw["ln2_g"], lw["ln2_b"], RM, f32=False)
             z = o.linear(b_, lw["fc1_w"], lw["fc1_b"])
             h = o.act(L.ACT_RELU, z, RM, ENC_FFN)
             mem = o.linear(h, lw["fc2_w"], lw["fc2_b"], residual=mm)
@@ -287,20 +336,20 @@ class EncoderTrainStep:
         return mem.view(B, Mq, D2).transpose(0, 1)                 # [M, B, 512] (view)
 
     # ------------------------------------------------------------------ backward
-    def _ffn_bwd(self, G, name, lw, t, dy, rows, act, x_key, dx_acc=None):
-        """y = x_in + fc2(act(fc1(LNorm-ed input))) pieces shared by all three layer types: returns d(fc1 input)."""
+    def _ffn_bwd(self, G, name, lw, t, dy, rows, act, x_key, dx_residual=None):
+        """y = x_in + fc2(act(fc1(LNorm-ed input))) pieces shared by all three layer types: returns d(fc1 input) (+ dx_residual)."""
         o = self.o
         dh, dW2, db2 = o.linear_bwd(t["h"], lw["fc2_w"], dy, rows)
         G[name + "fc2.weight"], G[name + "fc2.bias"] = dW2, db2
         dz = o.act_bwd(act, t["z"], dh, rows, t["z"].shape[1])
-        dxin, dW1, db1 = o.linear_bwd(t[x_key], lw["fc1_w"], dz, rows)
+        dxin, dW1, db1 = o.linear_bwd(t[x_key], lw["fc1_w"], dz, rows, dx_residual=dx_residual)
         G[name + "fc1.weight"], G[name + "fc1.bias"] = dW1, db1
         return dxin
 
     def backward(self, d_mem):
         """d_mem: [M, B, 512] gradient of the loss w.r.t. the memories.  -> {reference parameter name: gradient}."""
         o, g, P, T = self.o, self.g, self.P, self.T
-        B, Mq, D2 = g.B, self.M, ENC_DIM
+        B, Mq, D2, esz = g.B, self.M, ENC_DIM, self.o.esz
         RM, R2, R = B * Mq, B * g.T2a, B * g.T6a
         G = {}
         dmem = d_mem.to(self.dev, F32).transpose(0, 1).contiguous().view(RM, D2)
@@ -316,7 +365,7 @@ class EncoderTrainStep:
             dq = o.new(RM, D2, zero=True)
             dkv = o.new(R2, 2 * D2, zero=True)
             kp, dkp = t["kv"].data_ptr(), dkv.data_ptr()
-            o.attention_bwd(t["q"].data_ptr(), kp, kp + 4 * D2, t["ctx"], dctx, dq.data_ptr(), dkp, dkp + 4 * D2, D2, 2 * D2, D2, B, ENC_HEADS,
+            o.attention_bwd(t["q"].data_ptr(), kp, kp + esz * D2, t["ctx"], dctx, dq.data_ptr(), dkp, dkp + 4 * D2, D2, 2 * D2, D2, B, ENC_HEADS,
                             Mq, Mq, g.T2, g.T2a, None)
             da, dWq, dbq = o.linear_bwd(t["a"], lw["q_w"], dq, RM)
             G[nm + "self_attn.q_proj.weight"], G[nm + "self_attn.q_proj.bias"] = dWq * 0.125, dbq * 0.125
@@ -340,8 +389,8 @@ class EncoderTrainStep:
             G[nm + "self_attn.out_proj.weight"], G[nm + "self_attn.out_proj.bias"] = dWo, dbo
             dqkv = o.new(R2, 3 * D2, zero=True)
             qp, dqp = t["qkv"].data_ptr(), dqkv.data_ptr()
-            o.attention_bwd(qp, qp + 4 * D2, qp + 8 * D2, t["ctx"], dctx, dqp, dqp + 4 * D2, dqp + 8 * D2, 3 * D2, 3 * D2, D2, B, ENC_HEADS,
-                            g.T2a, g.T2a, g.T2, g.T2a, T["sub_valid"])
+            o.attention_bwd(qp, qp + esz * D2, qp + 2 * esz * D2, t["ctx"], dctx, dqp, dqp + 4 * D2, dqp + 8 * D2, 3 * D2, 3 * D2, D2, B,
+                            ENC_HEADS, g.T2a, g.T2a, g.T2, g.T2a, T["sub_valid"])
             da, dWqkv, dbqkv = o.linear_bwd(t["a"], lw["qkv_w"], dqkv, R2)
             _attn_layer_grads(G, nm + "self_attn.", dWqkv, dbqkv, D2)
             dx2, dg1, db1 = o.ln_bwd(t["x_in"], lw["ln1_g"], da, R2, dx=dxm)
@@ -368,18 +417,16 @@ class EncoderTrainStep:
             lw, t, nm = P["w2v_layers"][li], T["w2v"][li], f"wav2vec_model.encoder.layers.{li}."
             dy2, dg2, dbt2 = o.ln_bwd(t["y2"], lw["ln2_g"], dx, R)
             G[nm + "final_layer_norm.weight"], G[nm + "final_layer_norm.bias"] = dg2, dbt2
-            dx1_ffn = self._ffn_bwd(G, nm, lw, t, dy2, R, L.ACT_GELU, "x1")
-            dx1 = dx1_ffn
-            o.remap(dy2, R, 0, dx1, R, 0, 1, R, D, R, accumulate=True)                       # residual x1 -> y2
+            dx1 = self._ffn_bwd(G, nm, lw, t, dy2, R, L.ACT_GELU, "x1_op", dx_residual=dy2)  # + residual x1 -> y2
             dy1, dg1, dbt1 = o.ln_bwd(t["y1"], lw["ln1_g"], dx1, R)
             G[nm + "self_attn_layer_norm.weight"], G[nm + "self_attn_layer_norm.bias"] = dg1, dbt1
             dctx, dWo, dbo = o.linear_bwd(t["ctx"], lw["o_w"], dy1, R)
             G[nm + "self_attn.out_proj.weight"], G[nm + "self_attn.out_proj.bias"] = dWo, dbo
             dqkv = o.new(R, 3 * D, zero=True)
             qp, dqp = t["qkv"].data_ptr(), dqkv.data_ptr()
-            o.attention_bwd(qp, qp + 4 * D, qp + 8 * D, t["ctx"], dctx, dqp, dqp + 4 * D, dqp + 8 * D, 3 * D, 3 * D, D, B, W2V_HEADS,
+            o.attention_bwd(qp, qp + esz * D, qp + 2 * esz * D, t["ctx"], dctx, dqp, dqp + 4 * D, dqp + 8 * D, 3 * D, 3 * D, D, B, W2V_HEADS,
                             g.T6a, g.T6a, g.Tp, g.T6a, T["w2v_valid"])
-            dx, dWqkv, dbqkv = o.linear_bwd(t["x"], lw["qkv_w"], dqkv, R, dx_residual=dy1)   # + residual x -> y1
+            dx, dWqkv, dbqkv = o.linear_bwd(t["x_op"], lw["qkv_w"], dqkv, R, dx_residual=dy1)   # + residual x -> y1
             _attn_layer_grads(G, nm + "self_attn.", dWqkv, dbqkv, D)
         self.dbg["w2v_in"] = dx
         # ---- encoder LayerNorm, pos-conv, masked projection, feature LayerNorm
@@ -418,15 +465,11 @@ class EncoderTrainStep:
         return G
 
     def _conv_bwd(self, x_src, w, dz, rows, lda, a_rows, bias=True):
-        """Implicit-GEMM convolution z[m] = window_m(x_src) . w: -> (dcol [rows, K] = dz w, dW [N, K] = dz^T windows, db)."""
+        """Implicit-GEMM convolution z[m] = window_m(x_src) . w: -> (dcol [rows, K] = dz w (operand dtype), dW [N, K] = dz^T windows, db)."""
         o = self.o
         N, K = w.shape
-        Wt = o.transpose(w, N, K)
-        dcol = o.gemm(dz, Wt, o.new(rows, K), rows, K, N, lda=dz.shape[1], a_rows=dz.shape[0])
-        dzT = o.transpose(dz, rows, N)
-        winT = o.transpose(x_src, rows, K, ldx=lda)                 # transposed overlapping windows
-        dW = o.gemm(dzT, winT, o.new(N, K), N, K, dzT.shape[1], lda=dzT.shape[1], a_rows=N)
-        return dcol, dW, (o.colsum(dz, rows, N) if bias else None)
+        dcol, dW, db = o.linear_bwd(x_src, w, dz, rows, bias=bias, ldx=lda, dx_dtype=o.op)
+        return dcol, dW, db
 
     @staticmethod
     def _glu_conv_w(dW, cin):
@@ -447,11 +490,11 @@ class EncoderTrainStep:
         dWp = o.new(POS_GROUPS, cg, Kc, zero=True)
         Tpad = (g.T6a + 63) // 64 * 64
         for b in range(B):
-            dzT = o.transpose(dz[b * g.T6a:], g.T6a, D)             # [768, Tpad] = [16 x 48, Tpad]
-            winT = o.new(POS_GROUPS, Kc, Tpad)
+            dzT = o.transpose(dz[b * g.T6a:], g.T6a, D)[0]          # [768, Tpad] = [16 x 48, Tpad]
+            winT = o.new(POS_GROUPS, Kc, Tpad, dtype=o.op)
             for gi in range(POS_GROUPS):
-                src = T_slice(self.T["xg"], (b * 16 + gi) * g.Tpp)
-                L.check(o.lib.cst_transpose(src.data_ptr(), 64, g.T6a, Kc, winT[gi].data_ptr(), L.F32, Tpad, Tpad, o.st()))
+                src = self.T["xg"][(b * 16 + gi) * g.Tpp:]
+                L.check(o.lib.cst_transpose(src.data_ptr(), o.opc, 64, g.T6a, Kc, winT[gi].data_ptr(), o.opc, Tpad, Tpad, 0, 0, o.st()))
             o.gemm(dzT, winT, dWp, cg, Kc, Tpad, lda=Tpad, a_rows=D, residual=dWp, nb_outer=1, nb_inner=POS_GROUPS,
                    a_bs=(0, cg * Tpad), w_bs=Kc * Tpad, c_bs=(0, cg * Kc), ldc=Kc)
         dw = dWp.view(POS_GROUPS, cg, POS_K, 64)[..., :cg].permute(0, 1, 3, 2).reshape(D, cg, POS_K)     # [co, ci, tap]
@@ -464,9 +507,9 @@ class EncoderTrainStep:
         wg = w.view(POS_GROUPS, cg, cg, POS_K)                      # [g, co, ci, tap]
         wd = torch.zeros(POS_GROUPS, cg, POS_K, 64, dtype=F32, device=self.dev)       # [g, ci, tap', co]
         wd[..., :cg] = wg.flip(3).permute(0, 2, 3, 1)
-        wd = wd.reshape(POS_GROUPS, cg, Kc).contiguous()
-        dzg = torch.zeros(B * 16 * g.Tpp + SLACK + 1, 64, dtype=F32, device=self.dev)
-        L.check(o.lib.cst_posconv_pack(dz.data_ptr(), B, g.T6a, g.T6a, dzg.data_ptr(), L.F32, g.Tpp, o.st()))
+        wd = wd.reshape(POS_GROUPS, cg, Kc).to(o.op).contiguous()
+        dzg = torch.zeros(B * 16 * g.Tpp + SLACK + 8, 64, dtype=o.op, device=self.dev)
+        L.check(o.lib.cst_posconv_pack(dz.data_ptr(), B, g.T6a, g.T6a, dzg.data_ptr(), o.opc, g.Tpp, o.st()))
         dxp = dy0.clone()                                           # residual path
         shifted = dzg[1:]                                           # window of frame s = packed rows s+1 .. s+128
         o.gemm(shifted, wd, dxp, g.T6a, 48, Kc, lda=64, a_rows=g.Tpp - 1, residual=dxp, nb_outer=B, nb_inner=16,
@@ -476,10 +519,6 @@ class EncoderTrainStep:
     def forward_backward(self, wave, lens, d_mem):
         mem = self.forward(wave, lens)
         return mem, self.backward(d_mem)
-
-
-def T_slice(t, row0):
-    return t[row0:]
 
 
 def _glu_deinterleave(db):

@@ -233,29 +233,39 @@ int cst_sum(const float* x, long long n, float* out, void* stream);
  *   dW [N,K] = dY^T [N,M] X [M,K]    -> cst_gemm(A = dY^T, W = X^T)      (both from cst_transpose, M zero-padded to 64)
  * All gradient tensors are fp32. */
 
-/* out[c*ldo + r] = x[r*ldx + c] (out_dtype CST_F32 / CST_BF16 / CST_F16); columns r in [rows, rows_pad) are zero-filled.  ldx may be
- * smaller than cols: the implicit-GEMM window view of a strided convolution's input. */
-int cst_transpose(const float* x, long long ldx, int rows, int cols, void* out, int out_dtype, long long ldo, int rows_pad, void* stream);
+/* Tensors named `x_dtype` etc. take CST_F32 / CST_BF16 / CST_F16: the fp32 parity mode keeps the whole tape in fp32, the 16-bit mode
+ * keeps GEMM operands and pre-activations in bf16 and every gradient of an activation in fp32.
+ *
+ * cst_transpose: outT(c, r) = x[r*ldx + c] cast to out_dtype; columns r in [rows, rows_pad) are zero-filled.  ldx may be smaller than
+ * cols: the implicit-GEMM window view of a strided convolution's input.  outT is laid out in `chunk`-column slabs, element (c, r) at
+ * ((r / chunk)*cols + c)*chunk + r % chunk (chunk <= 0 or == rows_pad: the plain [cols, rows_pad] matrix; smaller chunks make the
+ * reduction axis a GEMM batch = split-K for weight gradients).  copy (optional): the un-transposed cast copy, row stride ldcopy. */
+int cst_transpose(const void* x, int x_dtype, long long ldx, int rows, int cols, void* outT, int out_dtype, int rows_pad, int chunk,
+                  void* copy, long long ldcopy, void* stream);
 int cst_cast(const float* x, long long n, void* out, int out_dtype, void* stream);
 /* out[c] = scale * sum_r x[r*ldx + c], fixed summation order; ws >= 64*cols floats. */
-int cst_colsum(const float* x, long long ldx, int rows, int cols, float* out, float* ws, float scale, void* stream);
+int cst_colsum(const void* x, int x_dtype, long long ldx, int rows, int cols, float* out, float* ws, float scale, void* stream);
 /* Activations as separate passes (the training forward keeps the pre-activation z): y = act(z) * alpha; GLU reads interleaved
  * (value, gate) column pairs of z [rows, 2*cols_out].  cst_act_bwd: dz from z and dy. */
-int cst_act_fwd(int act, const float* z, long long ldz, int rows, int cols_out, float* y, long long ldy, float alpha, void* stream);
-int cst_act_bwd(int act, const float* z, long long ldz, const float* dy, long long ldy, int rows, int cols_out, float* dz, long long lddz,
-                float alpha, void* stream);
+int cst_act_fwd(int act, const void* z, int z_dtype, long long ldz, int rows, int cols_out, void* y, int y_dtype, long long ldy, float alpha,
+                void* stream);
+int cst_act_bwd(int act, const void* z, int z_dtype, long long ldz, const void* dy, int dy_dtype, long long ldy, int rows, int cols_out,
+                void* dz, int dz_dtype, long long lddz, float alpha, void* stream);
 /* LayerNorm backward (eps 1e-5, C in {512, 768}): dx (+)= d LN(x; gamma, beta) / dx . dy; part (optional) receives per-CTA partial
  * sums [cdiv(rows,8)][dgamma | dbeta][C] to be reduced with cst_colsum(ldx = 2C). */
 int cst_layernorm_bwd(const float* x, long long ldx, const float* gamma, const float* dy, long long ldy, float* dx, long long lddx,
                       float* part, int rows, int C, int accumulate, void* stream);
-/* Attention backward (head_dim 64, fp32): recomputes the probabilities tile by tile.  dk / dv must be zero on entry. */
-int cst_attention_bwd(const float* q, const float* k, const float* v, const float* o, const float* d_o,
-                      float* dq, float* dk, float* dv, long long ldq, long long ldkv, long long ldo,
+/* Attention backward (head_dim 64): recomputes the probabilities tile by tile in fp32.  q / k / v / o: the forward tensors in `dtype`
+ * (row strides ldq, ldkv, ldo_fwd); d_o, dq, dk, dv fp32 (row strides ldo, lddq, lddkv).  dk / dv must be zero on entry. */
+int cst_attention_bwd(const void* q, const void* k, const void* v, const void* o, int dtype, const float* d_o,
+                      float* dq, float* dk, float* dv, long long ldq, long long ldkv, long long ldo_fwd, long long ldo,
+                      long long lddq, long long lddkv,
                       int B, int H, int n_q, int q_rows_per_seg, int n_kv, int kv_rows_per_seg, const int32_t* kv_len, void* stream);
 /* Input gradient of an implicit-GEMM strided convolution from its A-operand gradient dcol [M, k*C] (gather form). */
-int cst_col2im(const float* dcol, long long M, int k, int stride, int C, float* dx, long long rows_in, int accumulate, void* stream);
+int cst_col2im(const void* dcol, int dcol_dtype, long long M, int k, int stride, int C, float* dx, long long rows_in, int accumulate,
+               void* stream);
 /* out[seg*out_rps + t + out_off] (+)= scale * in[seg*in_rps + t + in_off] for t < min(seg_valid, seg_len[seg]), else 0 (t < n_rows). */
-int cst_rows_remap(const float* in, long long ldi, int in_rps, int in_off, float* out, long long ldo, int out_rps, int out_off,
+int cst_rows_remap(const float* in, long long ldi, int in_rps, int in_off, void* out, int out_dtype, long long ldo, int out_rps, int out_off,
                    int n_seg, int n_rows, int C, int seg_valid, const int32_t* seg_len, int accumulate, float scale, void* stream);
 /* conv0 + GroupNorm + GELU backward (recomputes the convolution from the waveform); see csrc/conv0_bwd.cu for the workspace size. */
 int cst_conv0_bwd(const float* wave, int B, int L, const float* w, const float* gamma, const float* beta,
