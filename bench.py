@@ -244,6 +244,198 @@ def eager_gpu_rate(fn, wave, tl, steps, warmup, autocast=False):
     return times
 
 
+
+# --------------------------------------------------------------------------------------- c5: training step
+C5_B, C5_L, C5_M = 8, 150000, 16            # ~1.2 M samples per GPU, T' = 468 frames per utterance
+
+
+def run_c5(args, rank, world, local_rank, cores):
+    """BASELINE configs[4]: Chimera-16 ST training forward + backward of the encoder / memory path, ~1.2 M audio samples per GPU
+    (B = 8 x 150 000), data-parallel over the ranks with a bucketed NCCL all-reduce of the gradients overlapped with the backward
+    segments (`chimera_st_b200.ddp`, replacing LegacyDistributedDataParallel).  The loss is the contrastive (InfoNCE) head over the
+    memories against fixed synthetic text-pass memories (triplet_st_mt_contrastive.py:154-169); dropout = LayerDrop = 0.
+    step = forward + loss + backward + gradient all-reduce;  value: waveforms resident in HBM;  e2e: pinned host waveforms -> H2D ->
+    step -> D2H of the loss."""
+    B, Lw, M = C5_B, C5_L, C5_M
+    audio_per_step = B * Lw / SR
+    dt_name = args.dtype
+    cfg = {"workload": "c5: Chimera-16 encoder+memory TRAINING step (forward + contrastive head + backward + gradient all-reduce), "
+                       "B=%d x %d samples (%.1f M samples, %.1f audio-s) per GPU" % (B, Lw, B * Lw / 1e6, audio_per_step),
+           "interlingua_length": M, "parallelism": "data-parallel dp%d, bucketed gradient all-reduce (%s buckets of %d MB) overlapped with "
+                                                   "the backward segments" % (world, args.comm_dtype, args.bucket_mb),
+           "dropout": 0.0, "layerdrop": 0.0, "feature_grad_mult": 0.1,
+           "l2": "tape (> 4 GB of activations per step) exceeds the 126 MB L2; no explicit flush",
+           "precision": ("bf16 GEMM operands (fp16 in the conv-stack forward), fp32 accumulation / gradients / norms / softmax"
+                         if dt_name == "bf16" else "fp32 FFMA")}
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        # the reference differentiates its modules with autograd; its own forward cannot be differentiated under torch 2.11 (in-place
+        # masking on a view, DESIGN.md §8a), so the CPU arm is autograd through the oracle restatement of the same modules
+        from oracle import chimera_oracle as O
+        torch.set_num_threads(cores)
+        sd = synth.make_state_dict(seed=0, interlingua_length=M, dead_heads=False)
+        rows = 2                                               # bounded sample: 2 of the 8 utterances per step
+        wave, tl = host_batch([Lw] * rows, seed=0)
+        R = torch.randn(M, rows, 512, generator=torch.Generator().manual_seed(1))
+        times = []
+        for it in range(args.warmup + args.steps):
+            sdg = {k: (v.clone().requires_grad_() if v.is_floating_point() else v) for k, v in sd.items()}
+            t = time.perf_counter()
+            mem, _ = O.encoder_forward(sdg, wave, tl)
+            (mem * R).sum().backward()
+            dtm = time.perf_counter() - t
+            if it >= args.warmup:
+                times.append(dtm)
+        rate = rows * Lw / SR * len(times) / sum(times)
+        sample = "%d of the %d utterances of the step (L=%d), forward + backward by autograd, fp32, torch CPU %d threads" % (rows, B, Lw, cores)
+        print(json.dumps({"impl": "reference", "metric": "encoded audio-sec/sec", "value": round(rate, 3), "unit": "audio-s/s",
+                          "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * sum(times) / len(times), 2),
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+                          "cpu_baseline": {"value": round(rate, 3), "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
+                          "e2e": {"value": round(rate, 3), "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    assert torch.cuda.is_available(), "bench.py --impl b200 needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    D.init("nccl")
+    from chimera_st_b200.train import EncoderTrainStep, GraphedTrainStep
+    from chimera_st_b200 import ddp, losses
+    dtype = torch.bfloat16 if dt_name == "bf16" else torch.float32
+    sd = synth.make_state_dict(seed=0, interlingua_length=M, dead_heads=False)
+    step = EncoderTrainStep(sd, B, Lw, device="cuda", feature_grad_mult=0.1, dtype=dtype)
+    host_w, host_l = host_batch([Lw] * B, seed=1000 * rank)
+    wave, lens = host_w.cuda(), host_l.cuda()
+    text_mem = torch.randn(M, B, 512, generator=torch.Generator().manual_seed(7 + rank)).cuda()
+
+    def loss_fn(mem):
+        _, loss, da, _ = losses.contrastive_loss(mem.contiguous(), text_mem, temp=0.1, grad_scale=1.0)
+        return loss, da
+
+    gs = GraphedTrainStep(step, wave, lens, loss_fn)
+    comm = torch.bfloat16 if args.comm_dtype == "bf16" else None
+    gs.reducer = ddp.GradAllReducer(gs.names, world_size=world, bucket_bytes=args.bucket_mb << 20, comm_dtype=comm)
+    n_params = sum(n for _, n in gs.names)
+    loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+
+    def barrier():
+        torch.cuda.synchronize()
+        D.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        return gs.run()
+
+    def step_e2e():
+        wave.copy_(host_w, non_blocking=True)
+        lens.copy_(host_l, non_blocking=True)
+        loss = gs.run()
+        loss_host.copy_(loss.reshape(1), non_blocking=True)
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step_resident()
+    e1.record()
+    barrier()
+    t_res = D.reduce_max(e0.elapsed_time(e1) * 1e-3, "cuda")
+    clocks = sampler.stop() if rank == 0 else None
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    e1.record()
+    barrier()
+    t_e2e = D.reduce_max(e0.elapsed_time(e1) * 1e-3, "cuda")
+    # local compute only (no all-reduce): what the collective costs on top
+    red, gs.reducer = gs.reducer, None
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        gs.run()
+    e1.record()
+    barrier()
+    t_local = D.reduce_max(e0.elapsed_time(e1) * 1e-3, "cuda")
+    gs.reducer = red
+    # replicas agree after the all-reduce (every rank holds the same averaged gradient)
+    gs.run()
+    torch.cuda.synchronize()
+    probe = gs.reduced["wav2vec_model.encoder.layers.0.fc1.weight"].float()
+    csum = float(probe.double().sum())
+    agree = abs(D.reduce_max(csum, "cuda") + D.reduce_max(-csum, "cuda")) <= 1e-6 * max(1.0, abs(csum))
+    total_audio = D.reduce_sum(audio_per_step, "cuda")
+
+    # ---- instrumented eager pass: per-kernel CUDA-event timing for the roofline object
+    prof = LaunchProfiler(step.o.lib)
+    step.o.lib = prof
+    torch.cuda._sleep(int(2e8))
+    loss, dmem = loss_fn(step.forward(wave, lens))
+    step.backward(dmem)
+    step.o.lib = prof.lib
+    ksum = prof.summary()
+    launches_per_step = sum(v["launches"] for v in ksum.values())
+    if rank != 0:
+        D.finalize()
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    dom = "gemm_tc_bf16" if "gemm_tc_bf16" in ksum else "gemm_ffma_f32"
+    kd = ksum[dom]
+    ach = kd["flops"] / kd["seconds"] / 1e12
+    peak = peaks.get("bf16_tflops_sustained", 1400.0) if dom == "gemm_tc_bf16" else 72.0
+    step_kernel_s = sum(v["seconds"] for v in ksum.values())
+    roofline = {"bound": "tensor", "kernel": dom, "achieved": round(ach, 2), "peak": peak, "unit": "TFLOP/s", "frac": round(ach / peak, 4),
+                "traffic": None, "peak_source": "measured (sustained)" if peaks and dom == "gemm_tc_bf16" else "nominal",
+                "launches_per_step": kd["launches"], "share_of_kernel_time": round(kd["seconds"] / step_kernel_s, 3),
+                "algorithmic_flop_per_step": kd["flops"],
+                "by_kernel": {k: {"launches": v["launches"], "ms": round(v["seconds"] * 1e3, 3),
+                                  "tflops": round(v["flops"] / v["seconds"] / 1e12, 2) if v["flops"] > 0 else None}
+                              for k, v in sorted(ksum.items(), key=lambda kv: -kv[1]["seconds"])}}
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import chimera_oracle as O
+        torch.set_num_threads(cores)
+        rows = 2
+        w2, l2 = host_w[:rows].clone(), host_l[:rows].clone()
+        R = torch.randn(M, rows, 512, generator=torch.Generator().manual_seed(1))
+        sdg = {k: (v.clone().requires_grad_() if v.is_floating_point() else v) for k, v in sd.items()}
+        t = time.perf_counter()
+        mem, _ = O.encoder_forward(sdg, w2, l2)
+        (mem * R).sum().backward()
+        t_cpu = time.perf_counter() - t
+        cpu = {"value": round(rows * Lw / SR / t_cpu, 3), "unit": "audio-s/s", "cores": cores, "kind": "port",
+               "sample": "%d of the %d utterances (L=%d), forward + backward by autograd through the oracle, fp32, torch CPU %d threads, "
+                         "one pass" % (rows, B, Lw, cores)}
+    grad_bytes = n_params * (2 if comm is not None else 4)
+    line = {"metric": "encoded audio-sec/sec", "value": round(total_audio * args.steps / t_res, 1), "unit": "audio-s/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": round(1e3 * t_res / args.steps, 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if dtype == torch.bfloat16 else "f32",
+            "data": "synthetic", "config": cfg,
+            "e2e": {"value": round(total_audio * args.steps / t_e2e, 1), "unit": "audio-s/s",
+                    "h2d_bytes_per_step": host_w.numel() * 4 + host_l.numel() * 8, "d2h_bytes_per_step": 4},
+            "gpu_launches": launches_per_step * args.steps, "cuda_graph": True,
+            "train": {"loss": float(gs.loss), "parameters": n_params, "gradient_tensors": len(gs.names),
+                      "backward_segments": len(gs.seg_grads), "buckets": len(red.buckets),
+                      "allreduce_bytes_per_step": grad_bytes, "ms_per_step_without_allreduce": round(1e3 * t_local / args.steps, 3),
+                      "allreduce_exposed_ms": round(1e3 * (t_res - t_local) / args.steps, 3), "replicas_agree": bool(agree)},
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line))
+    D.finalize()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -251,7 +443,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--workload", default="c3", choices=["c3", "c1", "c2", "c4"])
+    ap.add_argument("--workload", default="c3", choices=["c3", "c1", "c2", "c4", "c5"],
+                    help="c5 = BASELINE configs[4]: training forward + backward of the path with the DDP gradient all-reduce")
+    ap.add_argument("--comm-dtype", default="bf16", choices=["bf16", "fp32"], help="c5: dtype of the gradient buckets on the wire")
+    ap.add_argument("--bucket-mb", type=int, default=32, help="c5: gradient bucket size")
     ap.add_argument("--utts", type=int, default=512)
     ap.add_argument("--max-tokens", type=int, default=2000000,
                     help="c3 token budget per batch in samples (default: the reference's --max-tokens 2000000, "
@@ -278,6 +473,8 @@ def main():
 
     rank, world, local_rank = D.env_rank_world()
     cores = os.cpu_count() or 1
+    if args.workload == "c5":
+        return run_c5(args, rank, world, local_rank, cores)
     M = 64 if args.workload == "c4" else 16          # configs[3] is Chimera-64
     scaling = args.scaling if args.workload == "c3" else "weak"
     batches = make_workload(args.workload, rank, world, args.utts, args.max_tokens, strong=scaling == "strong")

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libchimera_st_b200.so")
-SOURCES = ["api.cu", "lengths.cu", "wave.cu", "conv0.cu", "conv0_tc.cu", "norm.cu", "split.cu", "gemm_f32.cu", "gemm_tc.cu", "attention.cu", "attention_tc.cu", "attention_tc2.cu", "posconv_tc.cu", "posconv_tc2.cu", "decoder.cu", "text.cu", "loss.cu", "backward.cu", "attention_bwd.cu", "conv0_bwd.cu", "decoder_beam.cu"]
+SOURCES = ["api.cu", "lengths.cu", "wave.cu", "conv0.cu", "conv0_tc.cu", "norm.cu", "split.cu", "gemm_f32.cu", "gemm_tc.cu", "attention.cu", "attention_tc.cu", "attention_tc2.cu", "posconv_tc.cu", "posconv_tc2.cu", "decoder.cu", "text.cu", "loss.cu", "backward.cu", "attention_bwd.cu", "attention_bwd_tc.cu", "conv0_bwd.cu", "decoder_beam.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-DCST_BUILD"] + os.environ.get("CST_EXTRA_NVCC_FLAGS", "").split()
 

@@ -93,17 +93,31 @@ __global__ void __launch_bounds__(256) attention_bwd_kernel(const void* __restri
         Ss[(4 * ty + a) * AB_LD + 4 * tx + c] = dp[a][c];
       }
     __syncthreads();
-    if (tid < AB_T) {
-      float mx = row_m[tid];
-      for (int j = 0; j < AB_T; ++j) mx = fmaxf(mx, Ps[tid * AB_LD + j]);
-      const float resc = expf(row_m[tid] - mx);
-      float l = row_l[tid] * resc, dacc = row_d[tid] * resc;
-      for (int j = 0; j < AB_T; ++j) {
-        const float e = expf(Ps[tid * AB_LD + j] - mx);
+    {
+      // 4 threads per query row (16 keys each), combined with two butterfly steps inside the quad
+      const int row = tid >> 2, part = tid & 3;
+      const float* ps = Ps + row * AB_LD + part * 16;
+      const float* ds = Ss + row * AB_LD + part * 16;
+      float mx = row_m[row];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) mx = fmaxf(mx, ps[j]);
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      float l = 0.f, dacc = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float e = expf(ps[j] - mx);
         l += e;
-        dacc = fmaf(e, Ss[tid * AB_LD + j], dacc);
+        dacc = fmaf(e, ds[j], dacc);
       }
-      row_m[tid] = mx; row_l[tid] = l; row_d[tid] = dacc;
+      l += __shfl_xor_sync(0xffffffffu, l, 1); l += __shfl_xor_sync(0xffffffffu, l, 2);
+      dacc += __shfl_xor_sync(0xffffffffu, dacc, 1); dacc += __shfl_xor_sync(0xffffffffu, dacc, 2);
+      if (part == 0) {
+        const float resc = expf(row_m[row] - mx);
+        row_l[row] = row_l[row] * resc + l;
+        row_d[row] = row_d[row] * resc + dacc;
+        row_m[row] = mx;
+      }
     }
   }
   __syncthreads();

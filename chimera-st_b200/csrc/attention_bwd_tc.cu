@@ -1,0 +1,216 @@
+// f.4 (16-bit mode): attention backward on the tensor cores as five batched tcgen05 GEMMs around one softmax-backward kernel.
+// Training shapes are short (T' <= 1499 frames), so the T x T score matrices of one layer are a transient of a few hundred MB and
+// every step below is HBM- or tensor-bound instead of the CUDA-core FFMA loop of attention_bwd.cu (which stays as the fp32 parity
+// kernel).  Arithmetic: the derivative of cst_attention (F.multi_head_attention_forward as called from
+// fairseq/modules/multihead_attention.py:155-187; q pre-scaled, keys >= kv_len[b] masked, all query rows live):
+//   S = Q K^T, dP = dO V^T                                  (2 GEMMs, K = 64, fp32 out)
+//   P = softmax(S + mask), D = rowsum(P o dP), dS = P o (dP - D)      (one kernel; writes dS, dS^T, P^T in bf16)
+//   dQ = dS K, dK = dS^T Q, dV = P^T dO                      (3 GEMMs, N = 64, reduction over the padded key / query axis)
+// Operands are re-laid per (utterance, head) as dense [T, 64] / [64, T] bf16 panels by head_pack_kernel; the three dense fp32
+// results are scattered back into the strided dq / dk / dv buffers by head_unpack_kernel.
+#include "common.cuh"
+
+namespace cst {
+
+__device__ __forceinline__ float hb_ld(const void* p, int dt, long long i) {
+  return dt == CST_F32 ? reinterpret_cast<const float*>(p)[i] : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
+}
+
+// src [B*rows_per_seg, ld] (dtype sdt), head h at columns h*64 .. h*64+63  ->  dst [B*H][Tp][64] bf16 (rows t >= valid zero) and
+// dstT [B*H][64][Tp] (optional).  valid = min(n, len[b]).  grid (Tp/64, H, B), 256 threads.
+__global__ void __launch_bounds__(256) head_pack_kernel(const void* __restrict__ src, int sdt, long long ld, int rows_per_seg, int n,
+                                                        const int32_t* __restrict__ len, int H, int Tp,
+                                                        __nv_bfloat16* __restrict__ dst, __nv_bfloat16* __restrict__ dstT) {
+  __shared__ float tile[64][65];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int t0 = blockIdx.x * 64, h = blockIdx.y, b = blockIdx.z;
+  int valid = n;
+  if (len != nullptr) valid = min(valid, len[b]);
+  const long long bh = (long long)b * H + h;
+  for (int e = threadIdx.x; e < 64 * 64; e += 256) {
+    const int i = e >> 6, d = e & 63;
+    const int t = t0 + i;
+    const float v = t < valid ? hb_ld(src, sdt, ((long long)b * rows_per_seg + t) * ld + h * 64 + d) : 0.f;
+    tile[i][d] = v;
+    dst[(bh * Tp + t) * 64 + d] = __float2bfloat16_rn(v);
+  }
+  if (dstT == nullptr) return;
+  __syncthreads();
+  for (int e = threadIdx.x; e < 64 * 64; e += 256) {
+    const int d = e >> 6, i = e & 63;
+    dstT[(bh * 64 + d) * Tp + t0 + i] = __float2bfloat16_rn(tile[i][d]);
+  }
+}
+
+// dense [B*H][Tp][64] fp32 -> out[(b*rows_per_seg + t)*ld + h*64 + d] for t < n.  grid (cdiv(n, 16), H, B), 256 threads.
+__global__ void __launch_bounds__(256) head_unpack_kernel(const float* __restrict__ src, int Tp, int n, int H, float* __restrict__ out,
+                                                          long long ld, int rows_per_seg) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int t = blockIdx.x * 16 + (threadIdx.x >> 4), d = (threadIdx.x & 15) * 4;
+  if (t >= n) return;
+  const float4 v = load4(src + (((long long)b * H + h) * Tp + t) * 64 + d);
+  store4(out + ((long long)b * rows_per_seg + t) * ld + h * 64 + d, v);
+}
+
+// One CTA = 32 query rows of one (utterance, head).  Phase A: a warp owns 4 rows and computes max, sum of exponentials and
+// D = sum_j P_ij dP_ij (two sweeps over the row; the rows just came out of the GEMMs and are re-read through L1/L2).  Phase B: per
+// 64-key chunk all threads form P and dS, store dS row-major and stage both tiles in shared memory for the transposed stores
+// (32 consecutive query rows per key = 64-byte segments).
+__global__ void __launch_bounds__(256) attn_bwd_softmax_kernel(const float* __restrict__ S, const float* __restrict__ dP, int Tqp, int Tkp,
+                                                               int n_q, int n_kv, const int32_t* __restrict__ kv_len, int H,
+                                                               __nv_bfloat16* __restrict__ dS, __nv_bfloat16* __restrict__ dST,
+                                                               __nv_bfloat16* __restrict__ PT) {
+  __shared__ float st_m[32], st_il[32], st_d[32];
+  __shared__ float tp[32][65], tds[32][65];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int r0 = blockIdx.x * 32;
+  const long long bh = blockIdx.y;
+  const int b = (int)(bh / H);
+  int klen = n_kv;
+  if (kv_len != nullptr) klen = min(klen, kv_len[b]);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* Sb = S + bh * (long long)Tqp * Tkp;
+  const float* Pb = dP + bh * (long long)Tqp * Tkp;
+  for (int rr = 0; rr < 4; ++rr) {
+    const int r = warp * 4 + rr;
+    const float* srow = Sb + (long long)(r0 + r) * Tkp;
+    const float* prow = Pb + (long long)(r0 + r) * Tkp;
+    float mx = -INFINITY;
+    for (int c = lane; c < klen; c += 32) mx = fmaxf(mx, srow[c]);
+    mx = warp_max(mx);
+    float l = 0.f, dacc = 0.f;
+    for (int c = lane; c < klen; c += 32) {
+      const float e = expf(srow[c] - mx);
+      l += e;
+      dacc = fmaf(e, prow[c], dacc);
+    }
+    l = warp_sum(l); dacc = warp_sum(dacc);
+    if (lane == 0) {
+      const bool live = (r0 + r) < n_q && l > 0.f;
+      st_m[r] = mx; st_il[r] = live ? 1.0f / l : 0.f; st_d[r] = live ? dacc / l : 0.f;
+    }
+  }
+  __syncthreads();
+  __nv_bfloat16* dSb = dS + bh * (long long)Tqp * Tkp;
+  __nv_bfloat16* dSTb = dST + bh * (long long)Tkp * Tqp;
+  __nv_bfloat16* PTb = PT + bh * (long long)Tkp * Tqp;
+  for (int c0 = 0; c0 < Tkp; c0 += 64) {
+    // 32 x 64 tile: thread -> row (tid / 8), 8 consecutive columns
+    {
+      const int r = threadIdx.x >> 3, cc = (threadIdx.x & 7) * 8;
+      const float m = st_m[r], il = st_il[r], dd = st_d[r];
+      const float* srow = Sb + (long long)(r0 + r) * Tkp + c0 + cc;
+      const float* prow = Pb + (long long)(r0 + r) * Tkp + c0 + cc;
+      const float4 s0 = load4(srow), s1 = load4(srow + 4), g0 = load4(prow), g1 = load4(prow + 4);
+      const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+      const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      float pv[8], dv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float p = (c0 + cc + i < klen) ? expf(sv[i] - m) * il : 0.f;
+        pv[i] = p;
+        dv[i] = p * (gv[i] - dd);
+        tp[r][cc + i] = p;
+        tds[r][cc + i] = dv[i];
+      }
+      uint4 u;
+      u.x = pack_bf16x2(dv[0], dv[1]); u.y = pack_bf16x2(dv[2], dv[3]); u.z = pack_bf16x2(dv[4], dv[5]); u.w = pack_bf16x2(dv[6], dv[7]);
+      *reinterpret_cast<uint4*>(dSb + (long long)(r0 + r) * Tkp + c0 + cc) = u;
+    }
+    __syncthreads();
+    {
+      const int c = threadIdx.x >> 2, rg = (threadIdx.x & 3) * 8;          // key column, 8 consecutive query rows
+      uint4 u, w;
+      u.x = pack_bf16x2(tp[rg][c], tp[rg + 1][c]); u.y = pack_bf16x2(tp[rg + 2][c], tp[rg + 3][c]);
+      u.z = pack_bf16x2(tp[rg + 4][c], tp[rg + 5][c]); u.w = pack_bf16x2(tp[rg + 6][c], tp[rg + 7][c]);
+      w.x = pack_bf16x2(tds[rg][c], tds[rg + 1][c]); w.y = pack_bf16x2(tds[rg + 2][c], tds[rg + 3][c]);
+      w.z = pack_bf16x2(tds[rg + 4][c], tds[rg + 5][c]); w.w = pack_bf16x2(tds[rg + 6][c], tds[rg + 7][c]);
+      *reinterpret_cast<uint4*>(PTb + (long long)(c0 + c) * Tqp + r0 + rg) = u;
+      *reinterpret_cast<uint4*>(dSTb + (long long)(c0 + c) * Tqp + r0 + rg) = w;
+    }
+    __syncthreads();
+  }
+}
+
+static inline long long up64(long long x) { return (x + 63) / 64 * 64; }
+
+}  // namespace cst
+
+using namespace cst;
+
+extern "C" long long cst_attention_bwd_tc_ws_bytes(int B, int H, int n_q, int n_kv) {
+  const long long BH = (long long)B * H, Tqp = up64(n_q), Tkp = up64(n_kv);
+  return BH * (Tqp * 64 * 2 * 4 + Tkp * 64 * 2 * 3          // Qh QhT Gh GhT | Kh KhT Vh
+               + Tqp * Tkp * (4 + 4 + 2 + 2 + 2)           // S dP | dS dST PT
+               + Tqp * 64 * 4 + Tkp * 64 * 4 * 2) + 4096;  // dQd | dKd dVd
+}
+
+static int batched_gemm(const void* A, const void* W, void* Cout, int c_dtype, int M, int N, int K, long long a_rows, int nz, void* stream) {
+  cst_gemm_params p;
+  memset(&p, 0, sizeof(p));
+  p.A = A; p.W = W; p.C = Cout;
+  p.ab_dtype = CST_BF16; p.c_dtype = c_dtype;
+  p.M = M; p.N = N; p.K = K; p.lda = K; p.ldc = N; p.a_rows = a_rows;
+  p.act = CST_ACT_NONE; p.alpha = 1.0f;
+  p.nb_outer = 1; p.nb_inner = nz;
+  p.a_bs_inner = (long long)M * K; p.w_bs_inner = (long long)N * K; p.c_bs_inner = (long long)M * N;
+  p.rows_per_seg = M; p.seg_rows_valid = M; p.out_rows_per_seg = M; p.segs_per_outer = 1;
+  return cst_gemm(&p, stream);
+}
+
+// q / k / v: bf16 forward tensors (row strides ldq / ldkv); d_o fp32 (ldo); dq / dk / dv fp32 (lddq / lddkv), rows t < n_q / n_kv of
+// every utterance are written.  ws: cst_attention_bwd_tc_ws_bytes(B, H, n_q, n_kv) bytes, 256-byte aligned.
+extern "C" int cst_attention_bwd_tc(const void* q, const void* k, const void* v, const float* d_o, float* dq, float* dk, float* dv,
+                                    long long ldq, long long ldkv, long long ldo, long long lddq, long long lddkv,
+                                    int B, int H, int n_q, int q_rows_per_seg, int n_kv, int kv_rows_per_seg, const int32_t* kv_len,
+                                    void* ws, void* stream) {
+  CST_REQUIRE(q && k && v && d_o && dq && dk && dv && ws && B > 0 && H > 0 && n_q > 0 && n_kv > 0, "cst_attention_bwd_tc: bad args");
+  CST_REQUIRE(n_q <= q_rows_per_seg && n_kv <= kv_rows_per_seg && ((uintptr_t)ws % 256) == 0 && lddq % 4 == 0 && lddkv % 4 == 0,
+              "cst_attention_bwd_tc: bad geometry");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long BH = (long long)B * H;
+  const int Tqp = (int)up64(n_q), Tkp = (int)up64(n_kv);
+  uint8_t* w = reinterpret_cast<uint8_t*>(ws);
+  auto take = [&](long long bytes) { uint8_t* p = w; w += (bytes + 255) / 256 * 256; return p; };
+  auto* Qh = (__nv_bfloat16*)take(BH * Tqp * 64 * 2); auto* QhT = (__nv_bfloat16*)take(BH * Tqp * 64 * 2);
+  auto* Gh = (__nv_bfloat16*)take(BH * Tqp * 64 * 2); auto* GhT = (__nv_bfloat16*)take(BH * Tqp * 64 * 2);
+  auto* Kh = (__nv_bfloat16*)take(BH * Tkp * 64 * 2); auto* KhT = (__nv_bfloat16*)take(BH * Tkp * 64 * 2);
+  auto* Vh = (__nv_bfloat16*)take(BH * Tkp * 64 * 2);
+  auto* S = (float*)take(BH * Tqp * Tkp * 4); auto* dP = (float*)take(BH * Tqp * Tkp * 4);
+  auto* dS = (__nv_bfloat16*)take(BH * Tqp * Tkp * 2); auto* dST = (__nv_bfloat16*)take(BH * Tqp * Tkp * 2);
+  auto* PT = (__nv_bfloat16*)take(BH * Tqp * Tkp * 2);
+  auto* dQd = (float*)take(BH * Tqp * 64 * 4); auto* dKd = (float*)take(BH * Tkp * 64 * 4); auto* dVd = (float*)take(BH * Tkp * 64 * 4);
+  CST_REQUIRE((long long)(w - reinterpret_cast<uint8_t*>(ws)) <= cst_attention_bwd_tc_ws_bytes(B, H, n_q, n_kv) + 16 * 256,
+              "cst_attention_bwd_tc: workspace accounting");
+  CST_CHECK_CUDA(launch_k(head_pack_kernel, dim3(Tqp / 64, H, B), dim3(256), 0, st, q, (int)CST_BF16, ldq, q_rows_per_seg, n_q,
+                          (const int32_t*)nullptr, H, Tqp, Qh, QhT));
+  CST_CHECK_CUDA(launch_k(head_pack_kernel, dim3(Tqp / 64, H, B), dim3(256), 0, st, (const void*)d_o, (int)CST_F32, ldo, q_rows_per_seg, n_q,
+                          (const int32_t*)nullptr, H, Tqp, Gh, GhT));
+  CST_CHECK_CUDA(launch_k(head_pack_kernel, dim3(Tkp / 64, H, B), dim3(256), 0, st, k, (int)CST_BF16, ldkv, kv_rows_per_seg, n_kv, kv_len, H,
+                          Tkp, Kh, KhT));
+  CST_CHECK_CUDA(launch_k(head_pack_kernel, dim3(Tkp / 64, H, B), dim3(256), 0, st, v, (int)CST_BF16, ldkv, kv_rows_per_seg, n_kv, kv_len, H,
+                          Tkp, Vh, (__nv_bfloat16*)nullptr));
+  int rc = batched_gemm(Qh, Kh, S, CST_F32, Tqp, Tkp, 64, Tqp, (int)BH, stream);
+  if (rc) return rc;
+  rc = batched_gemm(Gh, Vh, dP, CST_F32, Tqp, Tkp, 64, Tqp, (int)BH, stream);
+  if (rc) return rc;
+  CST_CHECK_CUDA(launch_k(attn_bwd_softmax_kernel, dim3(Tqp / 32, (unsigned)BH), dim3(256), 0, st, (const float*)S, (const float*)dP, Tqp, Tkp,
+                          n_q, n_kv, kv_len, H, dS, dST, PT));
+  rc = batched_gemm(dS, KhT, dQd, CST_F32, Tqp, 64, Tkp, Tqp, (int)BH, stream);
+  if (rc) return rc;
+  rc = batched_gemm(dST, QhT, dKd, CST_F32, Tkp, 64, Tqp, Tkp, (int)BH, stream);
+  if (rc) return rc;
+  rc = batched_gemm(PT, GhT, dVd, CST_F32, Tkp, 64, Tqp, Tkp, (int)BH, stream);
+  if (rc) return rc;
+  CST_CHECK_CUDA(launch_k(head_unpack_kernel, dim3(cdiv(n_q, 16), H, B), dim3(256), 0, st, (const float*)dQd, Tqp, n_q, H, dq, lddq,
+                          q_rows_per_seg));
+  CST_CHECK_CUDA(launch_k(head_unpack_kernel, dim3(cdiv(n_kv, 16), H, B), dim3(256), 0, st, (const float*)dKd, Tkp, n_kv, H, dk, lddkv,
+                          kv_rows_per_seg));
+  CST_CHECK_CUDA(launch_k(head_unpack_kernel, dim3(cdiv(n_kv, 16), H, B), dim3(256), 0, st, (const float*)dVd, Tkp, n_kv, H, dv, lddkv,
+                          kv_rows_per_seg));
+  return CST_OK;
+}

@@ -42,7 +42,10 @@ def plan_buckets(named_sizes, bucket_bytes=32 << 20, elem_bytes=4):
 
 
 class GradAllReducer:
-    def __init__(self, named_sizes, world_size=None, process_group=None, bucket_bytes=32 << 20):
+    def __init__(self, named_sizes, world_size=None, process_group=None, bucket_bytes=32 << 20, comm_dtype=None):
+        """comm_dtype: dtype of the flat buffers on the wire (None: the gradients' own fp32; torch.bfloat16 halves the bytes, the
+        reference's --fp16 runs reduce fp16 gradients the same way)."""
+        self.comm_dtype = comm_dtype
         self.group = process_group
         self.world = world_size if world_size is not None else (dist.get_world_size(process_group) if dist.is_initialized() else 1)
         self.sizes = OrderedDict(named_sizes)
@@ -71,6 +74,8 @@ class GradAllReducer:
         names = self.buckets[bi]
         flat = torch.cat([self.have[bi][n].reshape(-1) for n in names]) if len(names) > 1 else self.have[bi][names[0]].reshape(-1).clone()
         flat.div_(self.world)                                       # pre-divided, as the reference (:126-127)
+        if self.comm_dtype is not None and flat.dtype != self.comm_dtype:
+            flat = flat.to(self.comm_dtype)
         work = None
         if self.world > 1:
             work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)

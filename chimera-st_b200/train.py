@@ -15,6 +15,7 @@ the kernel layout; everything that touches an activation is a kernel behind the 
 """
 import ctypes as C
 import math
+import os
 
 import torch
 
@@ -40,6 +41,7 @@ class _Ops:
         self.op = op
         self.opc = _CODE[op]
         self.esz = 4 if op == F32 else 2
+        self.tc_attn_bwd = os.environ.get("CST_ATTN_BWD_TC", "1") != "0"        # A/B lever: 0 = FFMA attention backward in the 16-bit mode too
         self.ws = torch.empty(64 * 8192 + 1024, dtype=F32, device=device)       # cst_colsum scratch (<= 8192 columns per call)
 
     def st(self):
@@ -91,8 +93,9 @@ class _Ops:
 
     def colsum(self, x, rows, cols, ldx=None, scale=1.0):
         out = self.new(cols)
-        for c0 in range(0, cols, 8192):                            # the scratch buffer bounds the columns of one call
-            n = min(8192, cols - c0)
+        step = 8192 if rows >= 256 else cols                       # only the two-level reduction of tall inputs uses the scratch buffer
+        for c0 in range(0, cols, step):
+            n = min(step, cols - c0)
             L.check(self.lib.cst_colsum(x.data_ptr() + c0 * x.element_size(), _CODE[x.dtype], ldx if ldx is not None else x.shape[1], rows, n,
                                         out.data_ptr() + 4 * c0, self.ws.data_ptr(), scale, self.st()))
         return out
@@ -171,7 +174,13 @@ class _Ops:
         return out
 
     def attention_bwd(self, q, k, v, o, do, dq, dk, dv, ldq, ldkv, ldo, B, H, n_q, q_rps, n_kv, kv_rps, kv_len, dtype=None):
-        """q / k / v / o: forward tensors (operand dtype, row strides ldq / ldkv / ldo); do, dq, dk, dv fp32 with the SAME row strides."""
+        """q / k / v / o: forward tensors (operand dtype, row strides ldq / ldkv / ldo); do, dq, dk, dv fp32 with the SAME row strides.
+        16-bit mode: batched tcgen05 GEMMs + one softmax-backward kernel (csrc/attention_bwd_tc.cu); fp32: the FFMA parity kernel."""
+        if self.op == torch.bfloat16 and dtype is None and self.tc_attn_bwd:
+            ws = torch.empty(int(self.lib.cst_attention_bwd_tc_ws_bytes(B, H, n_q, n_kv)), dtype=torch.uint8, device=self.dev)
+            L.check(self.lib.cst_attention_bwd_tc(q, k, v, do.data_ptr(), dq, dk, dv, ldq, ldkv, ldo, ldq, ldkv, B, H, n_q, q_rps, n_kv, kv_rps,
+                                                  L.ptr(kv_len), ws.data_ptr(), self.st()))
+            return
         L.check(self.lib.cst_attention_bwd(q, k, v, o.data_ptr(), _CODE[o.dtype] if dtype is None else dtype, do.data_ptr(), dq, dk, dv,
                                            ldq, ldkv, ldo, ldo, ldq, ldkv, B, H, n_q, q_rps, n_kv, kv_rps, L.ptr(kv_len), self.st()))
 
@@ -348,6 +357,19 @@ class EncoderTrainStep:
 
     def backward(self, d_mem):
         """d_mem: [M, B, 512] gradient of the loss w.r.t. the memories.  -> {reference parameter name: gradient}."""
+        G = {}
+        for part in self.backward_iter(d_mem):
+            G.update(part)
+        return G
+
+    # the order in which `backward_iter` hands gradients over (the DDP bucket order, ddp.GradAllReducer)
+    SEGMENTS = ("memory stage + shared layers + subsampler", "wav2vec2 layers 11..6", "wav2vec2 layers 5..0 + pos-conv + projection",
+                "conv feature extractor")
+
+    def backward_iter(self, d_mem):
+        """Generator form of `backward`: yields {name: gradient} of each finished SEGMENT in backward order, so that the caller can
+        start the gradient all-reduce of a segment (NCCL, its own stream) while the kernels of the next one run -- the overlap
+        `LegacyDistributedDataParallel` does not have (legacy_distributed_data_parallel.py:94-178 reduces after the whole backward)."""
         o, g, P, T = self.o, self.g, self.P, self.T
         B, Mq, D2, esz = g.B, self.M, ENC_DIM, self.o.esz
         RM, R2, R = B * Mq, B * g.T2a, B * g.T6a
@@ -412,8 +434,13 @@ class EncoderTrainStep:
         dx = o.new(R, D, zero=True)
         o.remap(din, g.Tin1, 2, dx, g.T6a, 0, B, g.Tp, D, g.Tp)
         self.dbg["w2v_out"] = dx
+        yield G
+        G = {}
         # ---- 12 post-LN wav2vec2 layers
         for li in reversed(range(W2V_LAYERS)):
+            if li == W2V_LAYERS // 2 - 1:
+                yield G
+                G = {}
             lw, t, nm = P["w2v_layers"][li], T["w2v"][li], f"wav2vec_model.encoder.layers.{li}."
             dy2, dg2, dbt2 = o.ln_bwd(t["y2"], lw["ln2_g"], dx, R)
             G[nm + "final_layer_norm.weight"], G[nm + "final_layer_norm.bias"] = dg2, dbt2
@@ -443,6 +470,8 @@ class EncoderTrainStep:
         dfeat, dgf, dbf = o.ln_bwd(T["c"][6], P["ln_feat_g"], dfl, R)
         G["wav2vec_model.layer_norm.weight"], G["wav2vec_model.layer_norm.bias"] = dgf, dbf
         self.dbg["conv_feats"] = dfeat
+        yield G
+        G = {}
         # ---- conv feature extractor; GradMultiply(feature_grad_mult) scales everything that flows into it (wav2vec2.py:530-532)
         dc = o.new(R, 512)
         o.remap(dfeat, R, 0, dc, R, 0, 1, R, 512, R, scale=self.fgm)
@@ -462,7 +491,7 @@ class EncoderTrainStep:
                                     T["ss"].data_ptr(), dc.data_ptr(), g.Ta[0], dw0.data_ptr(), dgn.data_ptr(), dbn.data_ptr(), ws.data_ptr(),
                                     1.0, o.st()))
         G[fe + "0.0.weight"], G[fe + "0.2.weight"], G[fe + "0.2.bias"] = dw0.view(512, 1, 10), dgn, dbn
-        return G
+        yield G
 
     def _conv_bwd(self, x_src, w, dz, rows, lda, a_rows, bias=True):
         """Implicit-GEMM convolution z[m] = window_m(x_src) . w: -> (dcol [rows, K] = dz w (operand dtype), dW [N, K] = dz^T windows, db)."""
@@ -495,7 +524,7 @@ class EncoderTrainStep:
             for gi in range(POS_GROUPS):
                 src = self.T["xg"][(b * 16 + gi) * g.Tpp:]
                 L.check(o.lib.cst_transpose(src.data_ptr(), o.opc, 64, g.T6a, Kc, winT[gi].data_ptr(), o.opc, Tpad, Tpad, 0, 0, o.st()))
-            o.gemm(dzT, winT, dWp, cg, Kc, Tpad, lda=Tpad, a_rows=D, residual=dWp, nb_outer=1, nb_inner=POS_GROUPS,
+            o.gemm(dzT, winT, dWp, cg, Kc, Tpad, lda=Tpad, a_rows=cg, residual=dWp, nb_outer=1, nb_inner=POS_GROUPS,
                    a_bs=(0, cg * Tpad), w_bs=Kc * Tpad, c_bs=(0, cg * Kc), ldc=Kc)
         dw = dWp.view(POS_GROUPS, cg, POS_K, 64)[..., :cg].permute(0, 1, 3, 2).reshape(D, cg, POS_K)     # [co, ci, tap]
         v, gg = self.sd[pc + "weight_v"], self.sd[pc + "weight_g"]
@@ -519,6 +548,58 @@ class EncoderTrainStep:
     def forward_backward(self, wave, lens, d_mem):
         mem = self.forward(wave, lens)
         return mem, self.backward(d_mem)
+
+
+class GraphedTrainStep:
+    """One training step of the path as CUDA graphs: forward + loss in one graph, the backward pass in one graph per segment of
+    `EncoderTrainStep.backward_iter`; between the segment replays the finished gradients are handed to the bucketed all-reduce
+    (`ddp.GradAllReducer`), whose NCCL kernels run on the communicator's stream underneath the next segment.  Inputs are static
+    device buffers (`wave`, `lens`); `loss_fn(memories [M, B, 512]) -> (loss scalar tensor, d_memories)` is captured with the
+    forward pass.  Every activation / gradient lives in the graphs' shared memory pool, so replays allocate nothing."""
+
+    def __init__(self, step, wave, lens, loss_fn, reducer=None, warmup=2):
+        self.step, self.wave, self.lens, self.reducer = step, wave, lens, reducer
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                              # eager warm-up (one-time attribute / descriptor setup)
+            for _ in range(warmup):
+                loss, dmem = loss_fn(step.forward(wave, lens))
+                step.backward(dmem)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        pool = torch.cuda.graph_pool_handle()
+        self.graphs, self.seg_grads = [], []
+        g0 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g0, pool=pool):
+            self.loss, dmem = loss_fn(step.forward(wave, lens))
+        self.graphs.append(g0)
+        it = step.backward_iter(dmem)
+        while True:
+            gi = torch.cuda.CUDAGraph()
+            done = False
+            with torch.cuda.graph(gi, pool=pool):
+                try:
+                    part = next(it)
+                except StopIteration:
+                    done = True
+            if done:
+                break
+            self.graphs.append(gi)
+            self.seg_grads.append(part)
+        self.grads = {k: v for part in self.seg_grads for k, v in part.items()}
+        self.names = [(k, v.numel()) for part in self.seg_grads for k, v in part.items()]
+        self.reduced = None
+
+    def run(self):
+        """-> loss (device scalar).  `self.grads`: local gradients; `self.reduced`: all-reduced ones when a reducer is attached."""
+        self.graphs[0].replay()
+        for gi, part in zip(self.graphs[1:], self.seg_grads):
+            gi.replay()
+            if self.reducer is not None:
+                self.reducer.ready(part)
+        if self.reducer is not None:
+            self.reduced = self.reducer.finish(self.grads)
+        return self.loss
 
 
 def _glu_deinterleave(db):

@@ -261,6 +261,14 @@ int cst_attention_bwd(const void* q, const void* k, const void* v, const void* o
                       float* dq, float* dk, float* dv, long long ldq, long long ldkv, long long ldo_fwd, long long ldo,
                       long long lddq, long long lddkv,
                       int B, int H, int n_q, int q_rows_per_seg, int n_kv, int kv_rows_per_seg, const int32_t* kv_len, void* stream);
+/* The same derivative for the 16-bit mode on the tensor cores (csrc/attention_bwd_tc.cu): S = Q K^T and dP = dO V^T as batched
+ * tcgen05 GEMMs, one softmax-backward kernel, dQ / dK / dV as three more batched GEMMs.  q / k / v bf16, d_o / dq / dk / dv fp32;
+ * rows t < n_q (dq) and t < n_kv (dk, dv) of every utterance are written.  ws: cst_attention_bwd_tc_ws_bytes(...) bytes, 256-byte aligned. */
+long long cst_attention_bwd_tc_ws_bytes(int B, int H, int n_q, int n_kv);
+int cst_attention_bwd_tc(const void* q, const void* k, const void* v, const float* d_o, float* dq, float* dk, float* dv,
+                         long long ldq, long long ldkv, long long ldo, long long lddq, long long lddkv,
+                         int B, int H, int n_q, int q_rows_per_seg, int n_kv, int kv_rows_per_seg, const int32_t* kv_len,
+                         void* ws, void* stream);
 /* Input gradient of an implicit-GEMM strided convolution from its A-operand gradient dcol [M, k*C] (gather form). */
 int cst_col2im(const void* dcol, int dcol_dtype, long long M, int k, int stride, int C, float* dx, long long rows_in, int accumulate,
                void* stream);

@@ -240,3 +240,33 @@ def test_encoder_forward_backward_matches_autograd_through_the_oracle(lens):
     assert rel_l2(G2[k0].cpu(), 0.1 * G[k0].cpu()) < 1e-5          # two runs differ by the order of the dK / dV atomics
     k1 = "wav2vec_model.post_extract_proj.weight"
     assert rel_l2(G2[k1].cpu(), G[k1].cpu()) < 1e-5
+
+
+@pytest.mark.parametrize("B,H,Tq,Tk,masked", [(2, 8, 16, 117, False), (3, 12, 150, 150, True), (2, 12, 468, 468, True), (1, 8, 129, 257, False)])
+def test_attention_backward_tensor_core_path(B, H, Tq, Tk, masked):
+    """cst_attention_bwd_tc (batched tcgen05 GEMMs + softmax-backward kernel) against fp64 autograd on the bf16-rounded inputs."""
+    o = _Ops(torch.device(DEV), torch.bfloat16)
+    g = torch.Generator().manual_seed(Tq * 7 + Tk)
+    Cd = H * 64
+    bf = lambda t: t.to(torch.bfloat16).float()                     # noqa: E731
+    q = bf(torch.randn(B, Tq, Cd, generator=g) * 0.4).double().requires_grad_()
+    k = bf(torch.randn(B, Tk, Cd, generator=g)).double().requires_grad_()
+    v = bf(torch.randn(B, Tk, Cd, generator=g)).double().requires_grad_()
+    kl = torch.tensor([Tk, max(1, Tk // 2), 3][:B], dtype=torch.int32) if masked else None
+    qh, kh, vh = (t.view(B, -1, H, 64).transpose(1, 2) for t in (q, k, v))
+    s = qh @ kh.transpose(-1, -2)
+    if masked:
+        s = s.masked_fill(torch.arange(Tk)[None, None, None, :] >= kl.long()[:, None, None, None], float("-inf"))
+    out = (torch.softmax(s, -1) @ vh).transpose(1, 2).reshape(B, Tq, Cd)
+    do = torch.randn(B, Tq, Cd, generator=g)
+    out.backward(do.double())
+    qd, kd, vd = (t.detach().to(DEV, torch.bfloat16).reshape(-1, Cd) for t in (q, k, v))
+    od = out.detach().to(DEV, torch.bfloat16).view(B * Tq, Cd)
+    dq, dk, dv = (torch.zeros(t.shape, device=DEV) for t in (qd, kd, vd))
+    o.attention_bwd(qd.data_ptr(), kd.data_ptr(), vd.data_ptr(), od, do.to(DEV).view(B * Tq, Cd), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(),
+                    Cd, Cd, Cd, B, H, Tq, Tq, Tk, Tk, kl.to(DEV) if masked else None)
+    torch.cuda.synchronize()
+    # bf16 operands inside the five GEMMs (dO, P, dS are rounded): 2^-9 per product term
+    assert rel_l2(dq.cpu().view(B, Tq, Cd), q.grad.float()) < 8e-3
+    assert rel_l2(dk.cpu().view(B, Tk, Cd), k.grad.float()) < 8e-3
+    assert rel_l2(dv.cpu().view(B, Tk, Cd), v.grad.float()) < 8e-3
