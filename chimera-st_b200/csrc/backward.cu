@@ -67,6 +67,72 @@ __global__ void __launch_bounds__(256) transpose_kernel(const void* __restrict__
     }
   }
 }
+// 64 x 64 tiles, 8 elements (16 bytes of bf16) per access on both sides; needs cols % 8 == 0, ldx % 8 == 0, 16-byte aligned bases.
+__device__ __forceinline__ void ld8_any(const void* p, int dt, long long i, float (&v)[8]) {
+  if (dt == CST_F32) {
+    const float4 a = load4(reinterpret_cast<const float*>(p) + i), b = load4(reinterpret_cast<const float*>(p) + i + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+    const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p) + i);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (dt == CST_BF16) {
+        const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
+        v[2 * j] = __low2float(h); v[2 * j + 1] = __high2float(h);
+      } else {
+        const __half2 h = *reinterpret_cast<const __half2*>(&w[j]);
+        v[2 * j] = __low2float(h); v[2 * j + 1] = __high2float(h);
+      }
+    }
+  }
+}
+__device__ __forceinline__ void st8_any(void* p, int dt, long long i, const float (&v)[8]) {
+  if (dt == CST_F32) {
+    store4(reinterpret_cast<float*>(p) + i, make_float4(v[0], v[1], v[2], v[3]));
+    store4(reinterpret_cast<float*>(p) + i + 4, make_float4(v[4], v[5], v[6], v[7]));
+  } else {
+    uint4 u;
+    if (dt == CST_BF16) { u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]); u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]); }
+    else { u.x = pack_f16x2(v[0], v[1]); u.y = pack_f16x2(v[2], v[3]); u.z = pack_f16x2(v[4], v[5]); u.w = pack_f16x2(v[6], v[7]); }
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p) + i) = u;
+  }
+}
+__global__ void __launch_bounds__(256) transpose64_kernel(const void* __restrict__ x, int xdt, long long ldx, int rows, int cols,
+                                                          void* __restrict__ out, int odt, int rows_pad, int chunk,
+                                                          void* __restrict__ copy, long long ldcopy) {
+  __shared__ float tile[64][65];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int r0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int idx = threadIdx.x + it * 256;
+    const int row = idx >> 3, cs = (idx & 7) * 8;
+    const int r = r0 + row, c = c0 + cs;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (r < rows && c < cols) {
+      ld8_any(x, xdt, (long long)r * ldx + c, v);
+      if (copy != nullptr) st8_any(copy, odt, (long long)r * ldcopy + c, v);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) tile[row][cs + j] = v[j];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int idx = threadIdx.x + it * 256;
+    const int cc = idx >> 3, rs = (idx & 7) * 8;
+    const int c = c0 + cc, r = r0 + rs;
+    if (c < cols && r < rows_pad) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = tile[rs + j][cc];
+      const int s = r / chunk;
+      st8_any(out, odt, ((long long)s * cols + c) * chunk + (r - s * chunk), v);
+    }
+  }
+}
 __global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ x, long long n, void* __restrict__ out, int odt) {
   pdl_launch_dependents();
   pdl_wait();
@@ -96,23 +162,32 @@ __global__ void __launch_bounds__(256) colsum_kernel(const void* __restrict__ xv
 
 // ---- activations as separate passes (the training forward keeps the pre-activation z for the backward pass)
 //   act 1 GELU (erf), 2 ReLU, 3 GLU on interleaved (value, gate) column pairs: y[:, i] = z[:, 2i] * sigmoid(z[:, 2i+1]) * alpha
+__device__ __forceinline__ float gelu_grad_erf(float a) {         // d/dx [x Phi(x)] = Phi(x) + x phi(x)
+  const float cdf = 0.5f * (1.0f + erff(a * 0.70710678118654752440f));
+  return cdf + a * 0.3989422804014327f * expf(-0.5f * a * a);
+}
+// 4 output columns per thread (cols_out % 4 == 0, row pitches % 4 == 0): 16-byte accesses on the fp32 side, 8-byte on the 16-bit side
 __global__ void __launch_bounds__(256) act_fwd_kernel(int act, const void* __restrict__ z, int zdt, long long ldz, int rows, int cols_out,
                                                       void* __restrict__ y, int ydt, long long ldy, float alpha) {
   pdl_launch_dependents();
   pdl_wait();
-  const long long total = (long long)rows * cols_out;
+  const int c4n = cols_out >> 2;
+  const long long total = (long long)rows * c4n;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / cols_out;
-    const int c = (int)(i - r * cols_out);
-    float v;
+    const long long r = i / c4n;
+    const int c = (int)(i - r * c4n) * 4;
+    float4 v;
     if (act == CST_ACT_GLU) {
-      const float a = ld_any(z, zdt, r * ldz + 2 * c), g = ld_any(z, zdt, r * ldz + 2 * c + 1);
-      v = a * (1.0f / (1.0f + expf(-g)));
+      const float4 a = ld4_any(z, zdt, r * ldz + 2 * c), b = ld4_any(z, zdt, r * ldz + 2 * c + 4);      // (v0 g0 v1 g1) (v2 g2 v3 g3)
+      v = make_float4(a.x / (1.0f + expf(-a.y)), a.z / (1.0f + expf(-a.w)), b.x / (1.0f + expf(-b.y)), b.z / (1.0f + expf(-b.w)));
     } else {
-      const float a = ld_any(z, zdt, r * ldz + c);
-      v = act == CST_ACT_GELU ? gelu_erf(a) : (act == CST_ACT_RELU ? fmaxf(a, 0.f) : a);
+      const float4 a = ld4_any(z, zdt, r * ldz + c);
+      if (act == CST_ACT_GELU) v = make_float4(gelu_erf(a.x), gelu_erf(a.y), gelu_erf(a.z), gelu_erf(a.w));
+      else if (act == CST_ACT_RELU) v = make_float4(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f), fmaxf(a.z, 0.f), fmaxf(a.w, 0.f));
+      else v = a;
     }
-    st_any(y, ydt, r * ldy + c, v * alpha);
+    v.x *= alpha; v.y *= alpha; v.z *= alpha; v.w *= alpha;
+    st4_any(y, ydt, r * ldy + c, v);
   }
 }
 __global__ void __launch_bounds__(256) act_bwd_kernel(int act, const void* __restrict__ z, int zdt, long long ldz, const void* __restrict__ dy,
@@ -120,26 +195,28 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(int act, const void* __res
                                                       long long lddz, float alpha) {
   pdl_launch_dependents();
   pdl_wait();
-  const long long total = (long long)rows * cols_out;
+  const int c4n = cols_out >> 2;
+  const long long total = (long long)rows * c4n;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / cols_out;
-    const int c = (int)(i - r * cols_out);
-    const float g_out = ld_any(dy, dydt, r * ldy + c) * alpha;
+    const long long r = i / c4n;
+    const int c = (int)(i - r * c4n) * 4;
+    float4 g = ld4_any(dy, dydt, r * ldy + c);
+    g.x *= alpha; g.y *= alpha; g.z *= alpha; g.w *= alpha;
     if (act == CST_ACT_GLU) {
-      const float a = ld_any(z, zdt, r * ldz + 2 * c), g = ld_any(z, zdt, r * ldz + 2 * c + 1);
-      const float s = 1.0f / (1.0f + expf(-g));
-      st_any(dz, dzdt, r * lddz + 2 * c, g_out * s);
-      st_any(dz, dzdt, r * lddz + 2 * c + 1, g_out * a * s * (1.0f - s));
-    } else if (act == CST_ACT_GELU) {
-      const float a = ld_any(z, zdt, r * ldz + c);
-      // d/dx [x Phi(x)] = Phi(x) + x phi(x)
-      const float cdf = 0.5f * (1.0f + erff(a * 0.70710678118654752440f));
-      const float pdf = 0.3989422804014327f * expf(-0.5f * a * a);
-      st_any(dz, dzdt, r * lddz + c, g_out * (cdf + a * pdf));
-    } else if (act == CST_ACT_RELU) {
-      st_any(dz, dzdt, r * lddz + c, ld_any(z, zdt, r * ldz + c) > 0.f ? g_out : 0.f);
+      const float4 a = ld4_any(z, zdt, r * ldz + 2 * c), b = ld4_any(z, zdt, r * ldz + 2 * c + 4);
+      const float s0 = 1.0f / (1.0f + expf(-a.y)), s1 = 1.0f / (1.0f + expf(-a.w)), s2 = 1.0f / (1.0f + expf(-b.y)), s3 = 1.0f / (1.0f + expf(-b.w));
+      st4_any(dz, dzdt, r * lddz + 2 * c, make_float4(g.x * s0, g.x * a.x * s0 * (1.0f - s0), g.y * s1, g.y * a.z * s1 * (1.0f - s1)));
+      st4_any(dz, dzdt, r * lddz + 2 * c + 4, make_float4(g.z * s2, g.z * b.x * s2 * (1.0f - s2), g.w * s3, g.w * b.z * s3 * (1.0f - s3)));
     } else {
-      st_any(dz, dzdt, r * lddz + c, g_out);
+      float4 o = g;
+      if (act == CST_ACT_GELU) {
+        const float4 a = ld4_any(z, zdt, r * ldz + c);
+        o = make_float4(g.x * gelu_grad_erf(a.x), g.y * gelu_grad_erf(a.y), g.z * gelu_grad_erf(a.z), g.w * gelu_grad_erf(a.w));
+      } else if (act == CST_ACT_RELU) {
+        const float4 a = ld4_any(z, zdt, r * ldz + c);
+        o = make_float4(a.x > 0.f ? g.x : 0.f, a.y > 0.f ? g.y : 0.f, a.z > 0.f ? g.z : 0.f, a.w > 0.f ? g.w : 0.f);
+      }
+      st4_any(dz, dzdt, r * lddz + c, o);
     }
   }
 }
@@ -291,6 +368,15 @@ extern "C" int cst_transpose(const void* x, int x_dtype, long long ldx, int rows
   CST_REQUIRE(x && out && rows > 0 && cols > 0 && rows_pad >= rows, "cst_transpose: bad args rows=%d cols=%d", rows, cols);
   if (chunk <= 0) chunk = rows_pad;
   CST_REQUIRE(rows_pad % chunk == 0, "cst_transpose: rows_pad=%d must be a multiple of chunk=%d", rows_pad, chunk);
+  const int xes = x_dtype == CST_F32 ? 4 : 2, oes = out_dtype == CST_F32 ? 4 : 2;
+  const bool vec = cols % 8 == 0 && ldx % 8 == 0 && rows_pad % 8 == 0 && chunk % 8 == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)out % 16) == 0 &&
+                   (copy == nullptr || (((uintptr_t)copy % 16) == 0 && ldcopy % 8 == 0)) && (ldx * xes) % 16 == 0 && ((long long)chunk * oes) % 16 == 0;
+  if (vec) {
+    dim3 grid(cdiv(rows_pad, 64), cdiv(cols, 64));
+    CST_CHECK_CUDA(launch_k(transpose64_kernel, grid, dim3(256), 0, (cudaStream_t)stream, x, x_dtype, ldx, rows, cols, out, out_dtype, rows_pad,
+                            chunk, copy, ldcopy));
+    return CST_OK;
+  }
   dim3 grid(cdiv(rows_pad, 32), cdiv(cols, 32));
   CST_CHECK_CUDA(launch_k(transpose_kernel, grid, dim3(256), 0, (cudaStream_t)stream, x, x_dtype, ldx, rows, cols, out, out_dtype, rows_pad, chunk,
                           copy, ldcopy));
@@ -303,11 +389,18 @@ extern "C" int cst_cast(const float* x, long long n, void* out, int out_dtype, v
   return CST_OK;
 }
 
-// out[c] = scale * sum_r x[r, c]; ws: at least 64 * cols floats
+// out[c] = scale * sum_r x[r, c]; ws: CST_COLSUM_WS_FLOATS floats of scratch (inputs of >= 256 rows need cols <= that / 64)
 extern "C" int cst_colsum(const void* x, int x_dtype, long long ldx, int rows, int cols, float* out, float* ws, float scale, void* stream) {
   CST_REQUIRE(x && out && ws && rows > 0 && cols > 0, "cst_colsum: bad args");
+  CST_REQUIRE(rows < 256 || (long long)cols * 64 <= CST_COLSUM_WS_FLOATS, "cst_colsum: cols=%d too wide for the scratch buffer", cols);
   cudaStream_t st = (cudaStream_t)stream;
-  int slabs = rows >= 4096 ? 64 : (rows >= 256 ? 16 : 1);
+  // enough row slabs to fill the machine: the kernel is a latency-bound stream of row reads per thread
+  int slabs = 1;
+  if (rows >= 256) {
+    const int want = cdiv(4 * 148, cdiv(cols, 256));                       // ~4 CTAs per SM
+    slabs = min(min(want, rows / 32), (int)(CST_COLSUM_WS_FLOATS / cols));
+    if (slabs < 1) slabs = 1;
+  }
   const int per = cdiv(rows, slabs);
   slabs = cdiv(rows, per);
   if (slabs == 1) {
@@ -323,7 +416,8 @@ extern "C" int cst_colsum(const void* x, int x_dtype, long long ldx, int rows, i
 extern "C" int cst_act_fwd(int act, const void* z, int z_dtype, long long ldz, int rows, int cols_out, void* y, int y_dtype, long long ldy,
                            float alpha, void* stream) {
   CST_REQUIRE(z && y && rows > 0 && cols_out > 0 && act >= CST_ACT_NONE && act <= CST_ACT_GLU, "cst_act_fwd: bad args");
-  CST_CHECK_CUDA(launch_k(act_fwd_kernel, dim3(grid_for((long long)rows * cols_out)), dim3(256), 0, (cudaStream_t)stream, act, z, z_dtype, ldz, rows,
+  CST_REQUIRE(cols_out % 4 == 0 && ldz % 4 == 0 && ldy % 4 == 0, "cst_act_fwd: cols_out / ldz / ldy must be multiples of 4");
+  CST_CHECK_CUDA(launch_k(act_fwd_kernel, dim3(grid_for((long long)rows * cols_out / 4)), dim3(256), 0, (cudaStream_t)stream, act, z, z_dtype, ldz, rows,
                           cols_out, y, y_dtype, ldy, alpha));
   return CST_OK;
 }
@@ -331,7 +425,8 @@ extern "C" int cst_act_fwd(int act, const void* z, int z_dtype, long long ldz, i
 extern "C" int cst_act_bwd(int act, const void* z, int z_dtype, long long ldz, const void* dy, int dy_dtype, long long ldy, int rows, int cols_out,
                            void* dz, int dz_dtype, long long lddz, float alpha, void* stream) {
   CST_REQUIRE(z && dy && dz && rows > 0 && cols_out > 0 && act >= CST_ACT_NONE && act <= CST_ACT_GLU, "cst_act_bwd: bad args");
-  CST_CHECK_CUDA(launch_k(act_bwd_kernel, dim3(grid_for((long long)rows * cols_out)), dim3(256), 0, (cudaStream_t)stream, act, z, z_dtype, ldz, dy,
+  CST_REQUIRE(cols_out % 4 == 0 && ldz % 4 == 0 && ldy % 4 == 0 && lddz % 4 == 0, "cst_act_bwd: cols_out / ld* must be multiples of 4");
+  CST_CHECK_CUDA(launch_k(act_bwd_kernel, dim3(grid_for((long long)rows * cols_out / 4)), dim3(256), 0, (cudaStream_t)stream, act, z, z_dtype, ldz, dy,
                           dy_dtype, ldy, rows, cols_out, dz, dz_dtype, lddz, alpha));
   return CST_OK;
 }

@@ -42,7 +42,7 @@ class _Ops:
         self.opc = _CODE[op]
         self.esz = 4 if op == F32 else 2
         self.tc_attn_bwd = os.environ.get("CST_ATTN_BWD_TC", "1") != "0"        # A/B lever: 0 = FFMA attention backward in the 16-bit mode too
-        self.ws = torch.empty(64 * 8192 + 1024, dtype=F32, device=device)       # cst_colsum scratch (<= 8192 columns per call)
+        self.ws = torch.empty(512 * 1024, dtype=F32, device=device)             # cst_colsum scratch (CST_COLSUM_WS_FLOATS)
 
     def st(self):
         return L.stream_ptr()

@@ -243,7 +243,8 @@ int cst_sum(const float* x, long long n, float* out, void* stream);
 int cst_transpose(const void* x, int x_dtype, long long ldx, int rows, int cols, void* outT, int out_dtype, int rows_pad, int chunk,
                   void* copy, long long ldcopy, void* stream);
 int cst_cast(const float* x, long long n, void* out, int out_dtype, void* stream);
-/* out[c] = scale * sum_r x[r*ldx + c], fixed summation order; ws >= 64*cols floats. */
+/* out[c] = scale * sum_r x[r*ldx + c], fixed summation order; ws: CST_COLSUM_WS_FLOATS floats of scratch. */
+#define CST_COLSUM_WS_FLOATS (512 * 1024)
 int cst_colsum(const void* x, int x_dtype, long long ldx, int rows, int cols, float* out, float* ws, float scale, void* stream);
 /* Activations as separate passes (the training forward keeps the pre-activation z): y = act(z) * alpha; GLU reads interleaved
  * (value, gate) column pairs of z [rows, 2*cols_out].  cst_act_bwd: dz from z and dy. */
