@@ -143,7 +143,7 @@ def _oracle_grads(sd, wave, lens, R, relu_masks=None):
     """Autograd through the oracle.  `relu_masks` (one bool tensor per ReLU call, in call order) pins the sign pattern of the nine ReLU
     layers to the one OUR forward pass saw: with ~5e4 pre-activations per layer a few always lie within 1e-6 of zero, where two fp32
     forward passes legitimately disagree on the sign; one flipped element changes that layer's fc1 gradient by ~1e-3 and everything
-    upstream by ~3e-4 (measured, tools/dbg_grads3.py), which says nothing about the backward kernels."""
+    upstream by ~3e-4 (measured, tools/dbg_grads2.py, tools/relu_margin.py), which says nothing about the backward kernels."""
     sdg = {k: (v.clone().requires_grad_() if v.is_floating_point() else v) for k, v in sd.items()}
     calls = []
     orig = torch.relu
