@@ -245,6 +245,80 @@ def eager_gpu_rate(fn, wave, tl, steps, warmup, autocast=False):
 
 
 
+# --------------------------------------------------------------------------------------- secondary configurations in the default line
+def c5_quick(rank, world, steps=5, dtype=torch.bfloat16, comm_dtype=torch.bfloat16, bucket_mb=32):
+    """BASELINE configs[4] in brief (all ranks call it): the CUDA-graphed training step of `run_c5` (B = 8 x 150 000 samples per GPU,
+    contrastive head, bucketed gradient all-reduce overlapped with the backward segments), timed with CUDA events, max over ranks."""
+    from chimera_st_b200.train import EncoderTrainStep, GraphedTrainStep
+    from chimera_st_b200 import ddp, losses
+    B, Lw, M = C5_B, C5_L, C5_M
+    sd = synth.make_state_dict(seed=0, interlingua_length=M, dead_heads=False)
+    step = EncoderTrainStep(sd, B, Lw, device="cuda", feature_grad_mult=0.1, dtype=dtype)
+    host_w, host_l = host_batch([Lw] * B, seed=1000 * rank)
+    wave, lens = host_w.cuda(), host_l.cuda()
+    text_mem = torch.randn(M, B, 512, generator=torch.Generator().manual_seed(7 + rank)).cuda()
+
+    def loss_fn(mem):
+        _, loss, da, _ = losses.contrastive_loss(mem.contiguous(), text_mem, temp=0.1, grad_scale=1.0)
+        return loss, da
+    gs = GraphedTrainStep(step, wave, lens, loss_fn)
+    red = ddp.GradAllReducer(gs.names, world_size=world, bucket_bytes=bucket_mb << 20, comm_dtype=comm_dtype)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    out = {}
+    for key, reducer in (("ms_per_step", red), ("ms_per_step_without_allreduce", None)):
+        gs.reducer = reducer
+        for _ in range(3):
+            gs.run()
+        torch.cuda.synchronize(); D.barrier(); torch.cuda.synchronize()
+        e0.record()
+        for _ in range(steps):
+            gs.run()
+        e1.record()
+        torch.cuda.synchronize(); D.barrier()
+        out[key] = round(D.reduce_max(e0.elapsed_time(e1), "cuda") / steps, 3)
+    total_audio = D.reduce_sum(B * Lw / SR, "cuda")
+    out.update({"workload": "c5: training step (forward + contrastive head + backward + gradient all-reduce), B=%d x %d samples per GPU, bf16" % (B, Lw),
+                "audio_s_per_s": round(total_audio / (out["ms_per_step"] * 1e-3), 1), "n_gpus": world,
+                "allreduce_bytes_per_step": sum(n for _, n in gs.names) * (2 if comm_dtype is not None else 4),
+                "allreduce_exposed_ms": round(out["ms_per_step"] - out["ms_per_step_without_allreduce"], 3), "loss": float(gs.loss)})
+    del gs, step
+    torch.cuda.empty_cache()
+    return out
+
+
+def c4_decode_quick(rank, world, dtype=torch.bfloat16, beam=1):
+    """BASELINE configs[3] in brief (all ranks, one batch each): Chimera-64, 64 utterances x 20 s, encode + greedy decode
+    (SequenceGenerator beam 1, max_len_b 200), CUDA events, max over ranks."""
+    from chimera_st_b200.encoder import build_encoder_from_state_dict
+    from chimera_st_b200.decoder import B200GreedyDecoder, B200BeamDecoder
+    M, lens_ = 64, [320000] * 64
+    enc = build_encoder_from_state_dict(synth.make_state_dict(seed=0, interlingua_length=M), dtype=dtype, device="cuda", use_graph=True)
+    dsd = synth.make_decoder_state_dict(seed=1)
+    dec = B200GreedyDecoder(dsd, dtype=dtype, device="cuda") if beam == 1 else B200BeamDecoder(dsd, beam=beam, dtype=dtype, device="cuda")
+    w, l = host_batch(lens_, seed=77 + rank)
+    w, l = w.cuda(), l.cuda()
+    for _ in range(2):
+        dec.generate(enc(w, l).encoder_out, max_len=200)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    torch.cuda.synchronize(); D.barrier(); torch.cuda.synchronize()
+    ev[0].record()
+    mem0 = enc(w, l).encoder_out
+    ev[1].record()
+    dec.generate(mem0, max_len=200)
+    ev[2].record()
+    torch.cuda.synchronize()
+    t_enc, t_dec = D.reduce_max(ev[0].elapsed_time(ev[1]), "cuda"), D.reduce_max(ev[1].elapsed_time(ev[2]), "cuda")
+    audio = D.reduce_sum(sum(lens_) / SR, "cuda")
+    out = {"workload": "c4: Chimera-64 encode + %s decode, 64 utterances x 20 s per GPU, bf16" % ("greedy" if beam == 1 else "beam-%d" % beam),
+           "n_gpus": world, "encode_ms": round(t_enc, 3), "decode_ms": round(t_dec, 3), "decode_steps": dec.last_steps,
+           "us_per_decode_step": round(1e3 * t_dec / max(1, dec.last_steps), 1),
+           "encode_decode_audio_s_per_s": round(audio / ((t_enc + t_dec) * 1e-3), 1),
+           "encode_only_audio_s_per_s": round(audio / (t_enc * 1e-3), 1)}
+    del enc, dec
+    torch.cuda.empty_cache()
+    return out
+
+
 # --------------------------------------------------------------------------------------- c5: training step
 C5_B, C5_L, C5_M = 8, 150000, 16            # SURVEY.md §8: ~1.2 M samples per GPU, T' = 468 frames per utterance
 
@@ -460,6 +534,8 @@ def main():
                     help="wav2vec2 frame rows per super-batch (several reference batches, each with its own padded width, in one "
                          "row space / one CUDA graph); -1 = the encoder's default (24576), 0 = one plan per reference batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="c3 only: skip the brief secondary measurements (c4 encode + greedy decode, c5 training step) appended to the line")
     ap.add_argument("--profile-json", default="")
     ap.add_argument("--beam", type=int, default=1, help="--decode only: beam width (1 = greedy, 2..8 = B200BeamDecoder)")
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
@@ -626,6 +702,18 @@ def main():
         p.lib = real
     ksum = prof.summary()
 
+    # ---- secondary configurations (all ranks take part: c5 has the gradient all-reduce); never allowed to break the headline
+    extras = None
+    if args.workload == "c3" and not args.no_extras and dtype == torch.bfloat16:
+        extras = {}
+        enc.invalidate()
+        torch.cuda.empty_cache()
+        for name, fn in (("c4_encode_decode", lambda: c4_decode_quick(rank, world)), ("c5_train", lambda: c5_quick(rank, world))):
+            try:
+                extras[name] = fn()
+            except Exception as e:                                    # noqa: BLE001
+                extras[name] = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}   # same code on every rank: ranks stay in step
+
     if rank != 0:
         D.finalize()
         return
@@ -762,6 +850,8 @@ def main():
             "roofline": roofline, "roofline_hbm_kernel": hbm_roof, "cpu_baseline": cpu, "parity": parity}
     if decode is not None:
         line["decode"] = decode
+    if extras is not None:
+        line["secondary"] = extras
     print(json.dumps(line))
     D.finalize()
 

@@ -16,6 +16,8 @@
 //                 the S half-row, exact key mask (keys >= kv_len[b] get zero probability), running max / sum in
 //                 fp32, P = exp2 in bf16 -> shared memory (manual 128B swizzle); the output accumulator stays
 //                 in registers: O = O * alpha_j + PV_j.
+// Measured and rejected (round 2): delaying the second resident CTA of the first wave by 800 / 1600 / 2400 cycles to de-phase the two
+// CTAs of an SM changes nothing (399 -> 401 TFLOP/s at B32 H12 T749, tools/attn_rate.py).
 // Every query row of the tile is computed (padded query rows are live in the reference).  V rows of masked
 // keys must be finite (the plan guarantees it: no activation row is ever left unwritten).
 #include <cuda_fp16.h>

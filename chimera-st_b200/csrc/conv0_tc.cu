@@ -11,9 +11,13 @@
 // through swizzled shared memory and written by the TMA engine (3-D map [B, rows_per_seg, 512]: the frame axis clips
 // the last tile, frames T0 <= t < rows_per_seg are written as zeros, like conv0.cu).
 //
-// Warps: 0-3 build the A tile (one frame per thread, two stages), 4-11 epilogue (TMEM lane quarter = warp % 4, two
-// warps per quarter split the 256 columns of a stage), 12 = MMA issuer + TMEM owner.  Persistent: each CTA owns a
-// contiguous range of frame tiles, so the per-utterance scale/shift table (4 KB) is reloaded only at utterance changes.
+// Warps: 0-3 build the A tile (one frame per thread, two stages), 4..4+CT_EPI-1 epilogue (TMEM lane quarter = warp % 4,
+// CT_EPI/4 warps per quarter split the 256 columns of a stage), the last warp = MMA issuer + TMEM owner.  Persistent: each CTA
+// owns a contiguous range of frame tiles, so the per-utterance scale/shift table (4 KB) is reloaded only at utterance changes.
+// CT_EPI = 16 (round 2; 8 in round 1): the epilogue is a latency chain (tcgen05.ld -> FFMA2 -> MUFU GELU -> pack -> STS ->
+// async-proxy fence -> bulk store) and with two epilogue warps per scheduler ncu showed issue-active 53 %, XU 43 %, DRAM 39 %:
+// 0.52 -> 0.43 ms on the C2 batch (3.07 -> 3.71 TB/s).  Measured and rejected: one 64-column block (128B swizzle) and one bulk
+// store per stage instead of two 32-column blocks -- same time (3.69 TB/s), the stores are not what the warps wait for.
 #include "tc_common.cuh"
 
 namespace cst {
@@ -21,10 +25,15 @@ namespace cst {
 constexpr int CT_BM = 128, CT_C = 512;
 constexpr int CT_W_BYTES = CT_C * 128;              // 512 rows x 64 fp16 (only the first 32 columns are read)
 constexpr int CT_A_BYTES = CT_BM * 128;             // per stage
-constexpr int CT_STG_BYTES = 8 * 4096;              // per-epilogue-warp staging, 2 x 2 KB each
+#ifndef CT_EPI
+#define CT_EPI 16
+#endif
+constexpr int CT_CPW = 1024 / CT_EPI;               // accumulator columns per epilogue warp and stage (128 or 64)
+constexpr int CT_STG_BYTES = CT_EPI * 4096;         // per-epilogue-warp staging, 2 x 2 KB each
 constexpr int CT_SS_BYTES = 4096;                   // 256 channel pairs x {sc0, sc1, sh0, sh1}
 constexpr int CT_SMEM = CT_W_BYTES + 2 * CT_A_BYTES + CT_STG_BYTES + CT_SS_BYTES + 256 + 1024;
-constexpr int CT_THREADS = 13 * 32;
+constexpr int CT_THREADS = (5 + CT_EPI) * 32;
+constexpr int CT_MMA_WARP = 4 + CT_EPI;
 
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
@@ -56,12 +65,12 @@ conv0_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     mbar_init(w_full, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(a_full + 8 * s, 4); mbar_init(a_empty + 8 * s, 1);
-      mbar_init(t_full + 8 * s, 1); mbar_init(t_empty + 8 * s, 8);
+      mbar_init(t_full + 8 * s, 1); mbar_init(t_empty + 8 * s, CT_EPI);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_async_smem();
   }
-  if (warp == 12) {
+  if (warp == CT_MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -102,7 +111,7 @@ conv0_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
       __syncwarp();
       if (lane == 0) mbar_arrive(a_full + 8 * s);
     }
-  } else if (warp == 12) {
+  } else if (warp == CT_MMA_WARP) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       mbar_expect_tx(w_full, CT_W_BYTES);
@@ -130,19 +139,21 @@ conv0_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     }
     __syncwarp();
   } else {
-    // ===================== epilogue (warps 4..11) =====================
-    const int ew = warp - 4, q = warp & 3, chalf = ew >> 2;
-    const int et = threadIdx.x - 128;                              // 0..255
+    // ===================== epilogue (warps 4 .. 4+CT_EPI-1) =====================
+    const int ew = warp - 4, q = warp & 3, cpart = ew >> 2;
+    const int et = threadIdx.x - 128;                              // 0 .. 32*CT_EPI-1
     const uint32_t stage_s = sStg + ew * 4096;
     uint32_t seq = 0;
     int cur_b = -1, i = 0;
     for (int tile = tile_begin; tile < tile_end; ++tile, ++i) {
       const int b = tile / tiles_per_utt, t0 = (tile - b * tiles_per_utt) * CT_BM;
       if (b != cur_b) {                                            // new utterance: reload {scale, shift}, pair-interleaved
-        named_bar_sync(1, 256);
-        const float4 v = __ldg(reinterpret_cast<const float4*>(scale_shift + (size_t)b * CT_C) + et);   // sc0 sh0 sc1 sh1
-        ss_tab[et] = make_float4(v.x, v.z, v.y, v.w);
-        named_bar_sync(1, 256);
+        named_bar_sync(1, 32 * CT_EPI);
+        if (et < 256) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(scale_shift + (size_t)b * CT_C) + et);   // sc0 sh0 sc1 sh1
+          ss_tab[et] = make_float4(v.x, v.z, v.y, v.w);
+        }
+        named_bar_sync(1, 32 * CT_EPI);
         cur_b = b;
       }
       const bool live = t0 + q * 32 + lane < T0;
@@ -151,21 +162,21 @@ conv0_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
       for (int h = 0; h < 2; ++h) {
         mbar_wait(t_full + 8 * h, (uint32_t)(i & 1));
         tc_fence_after();
-        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + h * 256 + chalf * 128;
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + h * 256 + cpart * CT_CPW;
         float acc[2][32];
         tmem_ld32(t_row, acc[0]);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < CT_CPW / 32; ++j) {
           float (&v)[32] = acc[j & 1];
           tmem_ld_wait();
-          if (j + 1 < 4) {
+          if (j + 1 < CT_CPW / 32) {
             tmem_ld32(t_row + (j + 1) * 32, acc[(j + 1) & 1]);
           } else {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(t_empty + 8 * h);
           }
-          const int c0 = h * 256 + chalf * 128 + j * 32;           // first channel of the chunk
+          const int c0 = h * 256 + cpart * CT_CPW + j * 32;        // first channel of the chunk
 #pragma unroll
           for (int pr = 0; pr < 16; ++pr) {
             const float4 ss = ss_tab[(c0 >> 1) + pr];              // broadcast read
@@ -202,7 +213,7 @@ conv0_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 12) {
+  if (warp == CT_MMA_WARP) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }

@@ -210,6 +210,21 @@ def test_fast_fp32_mode_on_tensor_cores(monkeypatch):
     assert 1e-7 < err < 1e-4, err
 
 
+@pytest.mark.parametrize("lever", ["CST_MEM_FUSED=1", "CST_LN_FUSE=0", "CST_LN_FUSE=2"])
+def test_epilogue_levers_keep_parity_bf16(monkeypatch, lever):
+    """The non-default forms of the LayerNorm / memory-stage plumbing (A/B levers) give the same memories within the
+    16-bit tolerance: LN-fused weight-streaming linears in the memory stage, separate LayerNorm passes, LayerNorm fully fused around
+    the GEMMs (the variant instantiations of the tcgen05 GEMM)."""
+    from chimera_st_b200.encoder import build_encoder_from_state_dict
+    k, v = lever.split("=")
+    monkeypatch.setenv(k, v)
+    g, wave, lens = _golden("c1mix")
+    sd = synth.make_state_dict(seed=0, interlingua_length=16)
+    enc = build_encoder_from_state_dict(sd, dtype=torch.bfloat16, device="cuda", use_graph=False)
+    out = enc(wave.cuda(), lens.cuda()).encoder_out.float().cpu()
+    assert rel_l2(out, torch.from_numpy(g["memories"])) < 1e-2
+
+
 def test_single_utterance_output_does_not_alias_the_arena():
     """B == 1: [1,M,512].transpose(0,1) is 'contiguous' to torch, so the result must be cloned explicitly."""
     enc = encoder(16, torch.float32, use_graph=True)
