@@ -309,7 +309,36 @@ def c4_decode_quick(rank, world, dtype=torch.bfloat16, beam=1):
     torch.cuda.synchronize()
     t_enc, t_dec = D.reduce_max(ev[0].elapsed_time(ev[1]), "cuda"), D.reduce_max(ev[1].elapsed_time(ev[2]), "cuda")
     audio = D.reduce_sum(sum(lens_) / SR, "cuda")
+    pipe = None
+    if beam == 1:
+        # throughput form over a stream of batches: the latency-bound decode of batch i runs on its own stream underneath the
+        # encoder pass of batch i+1 and the decodes of batches i-1, i-2 (decoder.generate_async); same kernels, same hypotheses
+        n_lanes = int(os.environ.get("CST_C4_LANES", "3"))
+        n_batches = 3 * n_lanes
+        pending = [None] * n_lanes
+
+        def run_pipeline(k):
+            for i in range(k):
+                ln = i % n_lanes
+                if pending[ln] is not None:
+                    dec.collect(pending[ln])
+                pending[ln] = dec.generate_async(enc(w, l).encoder_out, max_len=200, lane=ln)
+            for ln in range(n_lanes):
+                if pending[ln] is not None:
+                    dec.collect(pending[ln])
+                    pending[ln] = None
+        run_pipeline(n_lanes)                                    # graph capture / warm-up of every lane
+        torch.cuda.synchronize(); D.barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ev[0].record()
+        run_pipeline(n_batches)
+        ev[1].record()
+        torch.cuda.synchronize()
+        t_pipe = D.reduce_max(ev[0].elapsed_time(ev[1]), "cuda")
+        pipe = {"lanes": n_lanes, "batches": n_batches, "ms_per_batch": round(t_pipe / n_batches, 3),
+                "encode_decode_audio_s_per_s": round(audio * n_batches / (t_pipe * 1e-3), 1), "wall_s": round(time.perf_counter() - t0, 3)}
     out = {"workload": "c4: Chimera-64 encode + %s decode, 64 utterances x 20 s per GPU, bf16" % ("greedy" if beam == 1 else "beam-%d" % beam),
+           "pipelined": pipe,
            "n_gpus": world, "encode_ms": round(t_enc, 3), "decode_ms": round(t_dec, 3), "decode_steps": dec.last_steps,
            "us_per_decode_step": round(1e3 * t_dec / max(1, dec.last_steps), 1),
            "encode_decode_audio_s_per_s": round(audio / ((t_enc + t_dec) * 1e-3), 1),

@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(DA_THREADS) dec_attention_kernel(const float* 
                                                                    const KVT* __restrict__ k, const KVT* __restrict__ v,
                                                                    long long kv_bs, long long kv_rs, float* __restrict__ out,
                                                                    long long ldo, int H, int n_keys, int n_max,
-                                                                   const int* __restrict__ step) {
+                                                                   const int* __restrict__ step, int kv_group) {
   extern __shared__ __align__(16) float da_smem[];            // [64 q][8*64 partial o][16 red][n_max scores]
   float* sq = da_smem;
   float* po = da_smem + 64;
@@ -460,8 +460,8 @@ __global__ void __launch_bounds__(DA_THREADS) dec_attention_kernel(const float* 
   const int n = step ? min(*step + 1, n_max) : n_keys;
   if (tid < 64) sq[tid] = q[(size_t)b * ldq + h * 64 + tid];
   __syncthreads();
-  const KVT* kb = k + (size_t)b * kv_bs + h * 64;
-  const KVT* vb = v + (size_t)b * kv_bs + h * 64;
+  const KVT* kb = k + (size_t)(b / kv_group) * kv_bs + h * 64;      // kv_group rows share one K / V set (the K beams of a sentence)
+  const KVT* vb = v + (size_t)(b / kv_group) * kv_bs + h * 64;
   const int sub = lane & 3;                                    // which 16-dim quarter of the head this lane covers
   float4 qq[4];
 #pragma unroll
@@ -747,18 +747,24 @@ extern "C" int cst_dec_linear(const cst_dec_linear_params* p, void* stream) {
 extern "C" int cst_dec_attention(const float* q, long long ldq, const void* k, const void* v, int kv_dtype,
                                  long long kv_batch_stride, long long kv_row_stride, float* out, long long ldo, int B, int H,
                                  int n_keys, int n_keys_max, const int32_t* step, void* stream) {
-  CST_REQUIRE(q && k && v && out, "cst_dec_attention: null pointer");
+  return cst_dec_attention_grouped(q, ldq, k, v, kv_dtype, kv_batch_stride, kv_row_stride, out, ldo, B, H, n_keys, n_keys_max, step, 1, stream);
+}
+
+extern "C" int cst_dec_attention_grouped(const float* q, long long ldq, const void* k, const void* v, int kv_dtype,
+                                         long long kv_batch_stride, long long kv_row_stride, float* out, long long ldo, int B, int H,
+                                         int n_keys, int n_keys_max, const int32_t* step, int kv_group, void* stream) {
+  CST_REQUIRE(q && k && v && out && kv_group >= 1, "cst_dec_attention: null pointer / bad kv_group");
   CST_REQUIRE(B > 0 && H > 0 && n_keys_max > 0 && (step || (n_keys > 0 && n_keys <= n_keys_max)), "cst_dec_attention: bad sizes");
   CST_REQUIRE(kv_row_stride % 8 == 0 && kv_batch_stride % 8 == 0 && ldo % 2 == 0, "cst_dec_attention: strides must keep 16-byte rows");
   const size_t smem = (size_t)(64 + 8 * 64 + 16 + n_keys_max) * sizeof(float);
   CST_REQUIRE(smem <= 48 * 1024, "cst_dec_attention: n_keys_max=%d too large", n_keys_max);
   if (kv_dtype == CST_F32)
     CST_CHECK_CUDA(launch_dec(dec_attention_kernel<float>, dim3(B * H), dim3(DA_THREADS), smem, (cudaStream_t)stream, q, ldq,
-                              (const float*)k, (const float*)v, kv_batch_stride, kv_row_stride, out, ldo, H, n_keys, n_keys_max, step));
+                              (const float*)k, (const float*)v, kv_batch_stride, kv_row_stride, out, ldo, H, n_keys, n_keys_max, step, kv_group));
   else if (kv_dtype == CST_BF16)
     CST_CHECK_CUDA(launch_dec(dec_attention_kernel<__nv_bfloat16>, dim3(B * H), dim3(DA_THREADS), smem, (cudaStream_t)stream, q, ldq,
                               (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, kv_batch_stride, kv_row_stride, out, ldo, H, n_keys,
-                              n_keys_max, step));
+                              n_keys_max, step, kv_group));
   else
     CST_REQUIRE(false, "cst_dec_attention: kv_dtype %d unsupported", kv_dtype);
   return CST_OK;

@@ -129,6 +129,7 @@ class _DecodePlan:
         self.out_len = torch.zeros(B, device=device, dtype=torch.int32)
         self.counters = torch.zeros(4, device=device, dtype=torch.int32)
         self.graph = None
+        self.graph_chunk = None                               # CHUNK steps in one graph (run_async)
         self.min_len = 1
         self.launches_per_step = 0
         self.total_launches = 0
@@ -215,7 +216,7 @@ class _DecodePlan:
     def prepare(self, memories, min_len=1):
         """Reset the device state for a new batch (and capture the step graph on first use), on the current stream."""
         if self.graph is not None and min_len != self.min_len:
-            self.graph = None                                  # min_len is a kernel argument baked into the graph
+            self.graph = self.graph_chunk = None               # min_len is a kernel argument baked into the graph
         self.min_len = min_len
         self.begin(memories)
         if self.use_graph and self.graph is None:
@@ -229,6 +230,33 @@ class _DecodePlan:
             self.graph = g
             self.begin(memories)
         self.n_begin = self.n_launch
+
+    CHUNK = int(os.environ.get("CST_DEC_CHUNK", "8"))     # decoding steps per graph of run_async
+
+    def run_async(self, memories, min_len=1):
+        """Enqueue a WHOLE decode (max_len + 1 steps, rounded up to CHUNK; steps past the last one are no-ops of the select kernel)
+        on the current stream without any host synchronisation: ceil((max_len + 1) / CHUNK) replays of a CHUNK-step graph.  Used to
+        run the latency-bound decode of one batch underneath the encoder / the decodes of other batches (decoder.generate_async).
+        -> number of steps enqueued."""
+        self.prepare(memories, min_len)
+        if self.use_graph and self.graph_chunk is None:
+            torch.cuda.current_stream().synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for _ in range(self.CHUNK):
+                    self._step()
+            self.graph_chunk = g
+            self.begin(memories)
+            self.n_begin = self.n_launch
+        n = -(-(self.max_len + 1) // self.CHUNK)
+        for _ in range(n):
+            if self.graph_chunk is not None:
+                self.graph_chunk.replay()
+            else:
+                for _ in range(self.CHUNK):
+                    self._step()
+        self.total_launches = self.n_begin + n * self.CHUNK * self.launches_per_step
+        return n * self.CHUNK
 
     def run(self, memories, min_len=1, poll=8):
         """-> number of steps issued."""
@@ -311,6 +339,10 @@ class B200GreedyDecoder:
         else:
             plans = self._run_lanes(memories, split, M, max_len, min_len, poll)
         self.last_launches = sum(p.total_launches for p in plans)
+        return self._hypotheses(plans)
+
+    @staticmethod
+    def _hypotheses(plans):
         out = []
         for plan in plans:
             toks, lens, ps = plan.tokens.cpu(), plan.out_len.cpu(), plan.pos_scores.cpu()
@@ -320,6 +352,33 @@ class B200GreedyDecoder:
                 out.append({"tokens": toks[b, 1:n + 1].long(), "score": float(sc.sum() / max(n, 1)), "attention": None,
                             "alignment": torch.empty(0), "positional_scores": sc})
         return out
+
+    @torch.no_grad()
+    def generate_async(self, memories, max_len=200, min_len=1, lane=0):
+        """Throughput form: enqueue the whole greedy decode of `memories` on lane `lane`'s own stream and return at once (no host
+        synchronisation; `collect(handle)` waits and returns the hypotheses of `generate`).  A decoding step is a latency chain of 51
+        short kernels that leaves most SMs idle, so the decodes of several batches -- and the encoder pass of the next batch on the
+        caller's stream -- overlap almost for free; one lane holds one batch at a time (collect before reusing it)."""
+        if memories.device.type != self.device.type or self.device.type != "cuda":
+            raise L.CstError("generate_async needs CUDA memories (no CPU fallback)")
+        if memories.dtype == torch.float16:
+            memories = memories.float()
+        M, B = memories.shape[0], memories.shape[1]
+        while len(self._streams) <= lane:
+            self._streams.append(torch.cuda.Stream(device=self.device))
+        st = self._streams[lane]
+        plan = self._plan(B, M, int(max_len), memories.dtype, lane=("async", lane))
+        st.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(st):
+            steps = plan.run_async(memories.contiguous(), min_len=min_len)
+        memories.record_stream(st)
+        return plan, st, steps
+
+    def collect(self, handle):
+        plan, st, steps = handle
+        st.synchronize()
+        self.last_steps, self.last_launches, self.last_lanes = steps, plan.total_launches, 1
+        return self._hypotheses([plan])
 
     def _run_lanes(self, memories, split, M, max_len, min_len, poll):
         while len(self._streams) < len(split):
@@ -360,6 +419,12 @@ class _BeamPlan(_DecodePlan):
         super().__init__(P, B * K, M, max_len, mem_dtype, device, lib, use_graph)
         self.nsent, self.K, self.R = B, K, B * K
         R, T = self.R, self.T
+        # the K beams of a sentence attend the same memories: K / V are projected and kept once per SENTENCE and the memory
+        # attention maps decoder row r to set r / K (cst_dec_attention_grouped) -- 1/K of the memory, no repeat_interleave copy
+        nl = len(P["layers"])
+        self.mem = torch.zeros(M * B, DIM, device=device, dtype=mem_dtype)
+        self.xk = torch.zeros(nl, M * B, DIM, device=device, dtype=P["embed"].dtype)
+        self.xv = torch.zeros(nl, M * B, DIM, device=device, dtype=P["embed"].dtype)
         zi = dict(device=device, dtype=torch.int32)
         zf = dict(device=device, dtype=torch.float32)
         self.tok = [torch.zeros(R, T, **zi) for _ in range(2)]
@@ -377,8 +442,13 @@ class _BeamPlan(_DecodePlan):
     def begin_beam(self, memories):
         """memories [M, B, 512]: every sentence's memories are repeated for its K beams (reorder_encoder_out with
         new_order = arange(B).repeat_interleave(K), sequence_generator.py:239-243)."""
-        M, B, K = self.M, self.nsent, self.K
-        self.begin(memories.reshape(M, B, 1, DIM).expand(M, B, K, DIM).reshape(M * B * K, DIM))
+        M, B, P = self.M, self.nsent, self.P
+        self.n_launch = 0
+        self.mem.copy_(memories.reshape(M * B, DIM))
+        for t in (self.tokens, self.pos_scores, self.done, self.out_len, self.counters):
+            t.zero_()
+        for i, lay in enumerate(P["layers"]):
+            self._linear(self.mem, lay["xkv_w"], lay["xkv_b"], [self.xk[i], self.xv[i]], M * B, 2 * DIM, DIM)
         for t in self.tok:
             t.fill_(PAD)
             t[:, 0] = EOS
@@ -404,7 +474,10 @@ class _BeamPlan(_DecodePlan):
             self.n_launch += 1
             self._linear(self.a, lay["so_w"], lay["so_b"], [self.x], R, DIM, DIM, residual=self.x)
             self._linear(self.x, lay["xq_w"], lay["xq_b"], [self.q], R, DIM, DIM, ln=(lay["ln2_g"], lay["ln2_b"]))
-            self._attention(self.xk[i], self.xv[i], DIM, R * DIM, M, M, False)
+            L.check(self.lib.cst_dec_attention_grouped(self.q.data_ptr(), DIM, self.xk[i].data_ptr(), self.xv[i].data_ptr(),
+                                                       L.DT[self.xk.dtype], DIM, self.nsent * DIM, self.a.data_ptr(), DIM, R, HEADS, M, M,
+                                                       0, self.K, self._st()))
+            self.n_launch += 1
             self._linear(self.a, lay["xo_w"], lay["xo_b"], [self.x], R, DIM, DIM, residual=self.x)
             self._linear(self.x, lay["fc1_w"], lay["fc1_b"], [self.h], R, FFN, DIM, ln=(lay["ln3_g"], lay["ln3_b"]),
                          act=L.ACT_RELU)

@@ -15,8 +15,9 @@ pre-training heads and `embed_positions._float_tensor`), so a reference checkpoi
 Integer (int32 / int64) `src_tokens` take the text (MT) branch (embedding + sinusoidal positions -> the same shared layers
 and memory stage).  `torch.int16` src_tokens are 16-bit PCM samples "on the wire" (SURVEY §8 f.3): copied as int16 and
 scaled by 2^-15 on the device, bit-identical to the reference's float32 waveform read at half the PCIe bytes.
-Not reproduced (out of scope): training-time dropout / LayerDrop,
-`modal_embedding` debug option, `non_shared_encoder_layers`.  They raise NotImplementedError.
+`modal_embedding=True` (the reference's `interlingua_debug_options`) and `non_shared_encoder_layers=n` register the reference's extra
+parameters (`modal_embedding.weight`, `audio_exclusive_layers.*`) and follow its forward (:239-249, :272-282).
+Not reproduced (out of scope): training-time dropout / LayerDrop in `forward` (the training step lives in train.py).
 """
 import os
 from collections import OrderedDict
@@ -61,7 +62,7 @@ class B200InterlinguaEncoder(nn.Module):
     MAX_PLANS = 256         # cached (B, L) shapes (geometry + CUDA graph); activations overlay one shared arena
 
     def __init__(self, interlingua_length=16, dtype=torch.float32, use_graph=True, dead_heads=True,
-                 text_vocab=0, encoder_out_dtype=None, conv_fp16=None):
+                 text_vocab=0, encoder_out_dtype=None, conv_fp16=None, modal_embedding=False, non_shared_encoder_layers=0):
         nn.Module.__init__(self)          # explicit: the fairseq plugin mixes this class with FairseqEncoder
         if dtype not in (torch.float32, torch.bfloat16):
             raise ValueError("compute dtype must be float32 or bfloat16")
@@ -74,7 +75,7 @@ class B200InterlinguaEncoder(nn.Module):
         self.use_graph = use_graph
         self.encoder_out_dtype = encoder_out_dtype
         self.no_interlingua = False
-        for name, shape, _, _ in encoder_param_spec(interlingua_length, dead_heads, text_vocab):
+        for name, shape, _, _ in encoder_param_spec(interlingua_length, dead_heads, text_vocab, modal_embedding, non_shared_encoder_layers):
             _register(self, name, torch.zeros(shape), buffer=name.endswith("_float_tensor"))
         self._prepared = None
         self._plans = OrderedDict()
@@ -281,6 +282,10 @@ def build_encoder_from_state_dict(state_dict, interlingua_length=None, dtype=tor
     M = interlingua_length or sd["interlingua_embedding.weight"].shape[0]
     dead = "wav2vec_model.mask_emb" in sd
     vocab = sd["text_embed_tokens.weight"].shape[0] if "text_embed_tokens.weight" in sd else 0
-    enc = B200InterlinguaEncoder(M, dtype=dtype, use_graph=use_graph, dead_heads=dead, text_vocab=vocab, conv_fp16=conv_fp16)
+    n_excl = 0
+    while f"audio_exclusive_layers.{n_excl}.fc1.weight" in sd:
+        n_excl += 1
+    enc = B200InterlinguaEncoder(M, dtype=dtype, use_graph=use_graph, dead_heads=dead, text_vocab=vocab, conv_fp16=conv_fp16,
+                                 modal_embedding="modal_embedding.weight" in sd, non_shared_encoder_layers=n_excl)
     enc.load_state_dict(sd, strict=True)
     return enc.to(device).eval()

@@ -46,11 +46,13 @@ class B200FairseqEncoder(B200InterlinguaEncoder, FairseqEncoder):
     """B200InterlinguaEncoder with the FairseqEncoder mix-in (forward_torchscript, set_num_updates, ...)."""
 
     def __init__(self, args, src_dict=None, embed_tokens=None):
-        if getattr(args, "non_shared_encoder_layers", 0) or getattr(args, "interlingua_debug_options", []):
-            raise NotImplementedError("non_shared_encoder_layers / interlingua_debug_options are not supported by the B200 path")
+        dbg = list(getattr(args, "interlingua_debug_options", []) or [])
+        if [o for o in dbg if o != "modal_embedding"]:
+            raise NotImplementedError("interlingua_debug_options %s are not supported by the B200 path" % dbg)
         vocab = embed_tokens.num_embeddings if embed_tokens is not None else 0
         B200InterlinguaEncoder.__init__(self, interlingua_length=args.interlingua_length, dtype=_compute_dtype(args),
-                                        use_graph=True, dead_heads=True, text_vocab=vocab)
+                                        use_graph=True, dead_heads=True, text_vocab=vocab, modal_embedding="modal_embedding" in dbg,
+                                        non_shared_encoder_layers=int(getattr(args, "non_shared_encoder_layers", 0) or 0))
         self.dictionary = src_dict
         self.no_interlingua = getattr(args, "no_interlingua", False)
 

@@ -617,13 +617,19 @@ class TextPlan(EncoderPlan):
         if "text_embed" not in params:
             raise RuntimeError("the checkpoint has no text_embed_tokens.weight: the text branch is unavailable")
         self.lib = lib if lib is not None else L.load()
+        # the text branch always runs the SHARED transformer layers (non_shared_encoder_layers replaces the first ones for audio only,
+        # w2v2_transformer_interlingua.py:239-249) and adds modal_embedding row 1 to the memory queries (:272-282)
+        if "enc_layers_text" in params or "mem_embed_text" in params:
+            params = dict(params)
+            params["enc_layers"] = params.get("enc_layers_text", params["enc_layers"])
+            params["mem_embed"] = params.get("mem_embed_text", params["mem_embed"])
         self.P = params
         self.g = g = TextGeometry(B, T, M)
         self.gs, self.groups, self.Bt, self.M = [g], [(B, T)], B, M
         self.utt0, self.r2_0, self.R2 = [0], [0], B * g.T2a
         self.seg_w2v = self.seg_enc = self.seg_mem = None
         self.ln_fuse = self.ln_light = self.f32_tc = False   # the text branch keeps separate LayerNorm passes and the FFMA fp32 GEMM
-        self.mem_fused = os.environ.get("CST_MEM_FUSED", "1") != "0"
+        self.mem_fused = os.environ.get("CST_MEM_FUSED", "0") != "0"
         self.dev = device or torch.device("cuda", torch.cuda.current_device())
         self.act = act_dtype
         self.act_code = L.DT[act_dtype]

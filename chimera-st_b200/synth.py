@@ -30,7 +30,7 @@ SUB_MID = 1024
 SAMPLE_RATE = 16000
 
 
-def encoder_param_spec(interlingua_length=16, dead_heads=True, text_vocab=0):
+def encoder_param_spec(interlingua_length=16, dead_heads=True, text_vocab=0, modal_embedding=False, non_shared_encoder_layers=0):
     """[(name, shape, kind, scale)] in the reference's state_dict order."""
     s = []
     W = "wav2vec_model."
@@ -96,15 +96,21 @@ def encoder_param_spec(interlingua_length=16, dead_heads=True, text_vocab=0):
     s.append(("interlingua_embedding.weight", (interlingua_length, ENC_DIM), "embed0", ENC_DIM ** -0.5))
     for i in range(MEM_LAYERS):
         layer(f"interlingua_layers.{i}.", ENC_DIM, ENC_FFN, 0.03125, 0.0442, 0.0255, 0.01275, 2.0)
+    if modal_embedding:                      # 'modal_embedding' in interlingua_debug_options: Embedding(3, 512, padding_idx 2), :179-180
+        s.append(("modal_embedding.weight", (3, ENC_DIM), "normal", ENC_DIM ** -0.5))
+    for i in range(non_shared_encoder_layers):      # :183-187
+        layer(f"audio_exclusive_layers.{i}.", ENC_DIM, ENC_FFN, 0.03125, 0.0442, 0.0255, 0.01275, 2.0)
     return s
 
 
-def make_state_dict(seed=0, interlingua_length=16, dead_heads=True, text_vocab=0, prefix=""):
+def make_state_dict(seed=0, interlingua_length=16, dead_heads=True, text_vocab=0, prefix="", modal_embedding=False,
+                    non_shared_encoder_layers=0):
     """Seeded fp32 CPU state dict with the reference encoder's keys/shapes."""
     g = torch.Generator().manual_seed(seed)
     sd = OrderedDict()
     pending_g = None
-    for name, shape, kind, scale in encoder_param_spec(interlingua_length, dead_heads, text_vocab):
+    for name, shape, kind, scale in encoder_param_spec(interlingua_length, dead_heads, text_vocab, modal_embedding,
+                                                       non_shared_encoder_layers):
         if kind == "normal":
             t = torch.randn(shape, generator=g) * scale
         elif kind == "gain":

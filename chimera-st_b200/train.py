@@ -210,6 +210,8 @@ class EncoderTrainStep:
         if dtype not in (F32, torch.bfloat16):
             raise L.CstError("EncoderTrainStep: dtype must be torch.float32 or torch.bfloat16")
         sd = _weights._strip(state_dict)
+        if any(k.startswith(("audio_exclusive_layers.", "modal_embedding.")) for k in sd):
+            raise NotImplementedError("EncoderTrainStep: modal_embedding / non_shared_encoder_layers checkpoints are inference-only here")
         self.sd = {k: v.detach().to(dev, F32) for k, v in sd.items() if v.is_floating_point()}
         self.M = M or self.sd["interlingua_embedding.weight"].shape[0]
         self.g = Geometry(B, Lw, self.M)

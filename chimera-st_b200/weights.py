@@ -120,6 +120,14 @@ def prepare(state_dict, device, act_dtype, conv_dtype=None):
         P[f"sub{i}_w"] = op(_glu_interleave(w))
         P[f"sub{i}_b"] = f32(_glu_interleave(sd[f"subsample.conv_layers.{i}.bias"].float()))
     P["enc_layers"] = [layer(f"transformer_layers.{i}.") for i in range(ENC_LAYERS)]
+    # non_shared_encoder_layers = n (w2v2_transformer_interlingua.py:183-187,239-249): the AUDIO branch runs audio_exclusive_layers[0..n)
+    # in place of transformer_layers[0..n); the text branch keeps all shared layers
+    n_excl = 0
+    while f"audio_exclusive_layers.{n_excl}.fc1.weight" in sd:
+        n_excl += 1
+    if n_excl:
+        P["enc_layers_text"] = P["enc_layers"]
+        P["enc_layers"] = [layer(f"audio_exclusive_layers.{i}.") for i in range(n_excl)] + P["enc_layers_text"][n_excl:]
     if act_dtype != torch.float32:
         # fused-LayerNorm variants (16-bit mode): post-LN wav2vec2 layers -- QKV of layer i consumes LN2 of layer i-1, fc1
         # consumes LN1 of its own layer; pre-LN shared layers -- QKV consumes LN1, fc1 consumes LN2 of their own layer
@@ -131,11 +139,17 @@ def prepare(state_dict, device, act_dtype, conv_dtype=None):
             if i > 0:
                 fold_ln(d, "qkv", d["ln1_g"], d["ln1_b"])
             fold_ln(d, "fc1", d["ln2_g"], d["ln2_b"])
-    for d in P["w2v_layers"] + P["enc_layers"]:
+    for d in P["w2v_layers"] + P["enc_layers"] + P.get("enc_layers_text", []):
         d.pop("_qkv_raw", None)
         d.pop("_fc1_raw", None)
     P["ln_out_g"], P["ln_out_b"] = f32(sd["layer_norm.weight"]), f32(sd["layer_norm.bias"])
     P["mem_embed"] = f32(sd["interlingua_embedding.weight"])
+    if "modal_embedding.weight" in sd:
+        # 'modal_embedding' debug option (w2v2_transformer_interlingua.py:179-182,272-282): row 0 (audio) / row 1 (text) of a 3-row
+        # embedding is added to every memory query before the memory stage
+        me = sd["modal_embedding.weight"].float()
+        P["mem_embed_text"] = f32(sd["interlingua_embedding.weight"].float() + me[1])
+        P["mem_embed"] = f32(sd["interlingua_embedding.weight"].float() + me[0])
     if "text_embed_tokens.weight" in sd:                       # text (MT) branch input, interlingua:216
         P["text_embed"] = f32(sd["text_embed_tokens.weight"])
     P["mem_layers"] = [layer(f"interlingua_layers.{i}.", fused_qkv=False) for i in range(MEM_LAYERS)]

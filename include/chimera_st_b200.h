@@ -320,6 +320,12 @@ int cst_dec_linear(const cst_dec_linear_params* p, void* stream);
 int cst_dec_attention(const float* q, long long ldq, const void* k, const void* v, int kv_dtype,
                       long long kv_batch_stride, long long kv_row_stride, float* out, long long ldo, int B, int H,
                       int n_keys, int n_keys_max, const int32_t* step, void* stream);
+/* Same, with kv_group consecutive decoder rows sharing ONE K / V set (row b reads set b / kv_group): the K beams of a sentence
+ * attend the same memories, whose K / V are projected and stored once per sentence instead of once per beam row (the reference
+ * repeats encoder_out K times: reorder_encoder_out with new_order = arange(B).repeat_interleave(K), sequence_generator.py:239-243). */
+int cst_dec_attention_grouped(const float* q, long long ldq, const void* k, const void* v, int kv_dtype,
+                              long long kv_batch_stride, long long kv_row_stride, float* out, long long ldo, int B, int H,
+                              int n_keys, int n_keys_max, const int32_t* step, int kv_group, void* stream);
 
 /* One step of SequenceGenerator._generate for beam_size = 1 (fairseq/sequence_generator.py:294-540):
  * lp = log_softmax(logits[b]); lp[pad] = -inf; step >= max_len: only EOS; step < min_len: no EOS; next = argmax.

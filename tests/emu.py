@@ -246,13 +246,14 @@ def _dec_linear(self, pref, stream):
     return 0
 
 
-def _dec_attention(self, q, ldq, k, v, kv_dtype, kv_bs, kv_rs, out, ldo, B, H, n_keys, n_max, step, stream):
+def _dec_attention(self, q, ldq, k, v, kv_dtype, kv_bs, kv_rs, out, ldo, B, H, n_keys, n_max, step, stream, kv_group=1):
     assert kv_dtype == F32
     n = min(int(_mem(step, 1, np.int32)[0]) + 1, n_max) if step else n_keys
     for b in range(B):
+        s_ = b // kv_group
         qb = torch.from_numpy(_mem(q + 4 * b * ldq, H * 64).copy()).view(H, 64).double()
-        K = torch.from_numpy(np.stack([_mem(k + 4 * (b * kv_bs + j * kv_rs), H * 64).copy() for j in range(n)])).view(n, H, 64).double()
-        Vv = torch.from_numpy(np.stack([_mem(v + 4 * (b * kv_bs + j * kv_rs), H * 64).copy() for j in range(n)])).view(n, H, 64).double()
+        K = torch.from_numpy(np.stack([_mem(k + 4 * (s_ * kv_bs + j * kv_rs), H * 64).copy() for j in range(n)])).view(n, H, 64).double()
+        Vv = torch.from_numpy(np.stack([_mem(v + 4 * (s_ * kv_bs + j * kv_rs), H * 64).copy() for j in range(n)])).view(n, H, 64).double()
         s = torch.einsum("hd,nhd->hn", qb, K)
         o = torch.einsum("hn,nhd->hd", torch.softmax(s, -1), Vv)
         _mem(out + 4 * b * ldo, H * 64)[:] = o.reshape(-1).float().numpy()
@@ -293,6 +294,13 @@ def _dec_select(self, logits, V, B, tokens, ld_tok, pos_scores, ld_ps, done, out
 EmuLib.cst_dec_embed = _dec_embed
 EmuLib.cst_dec_linear = _dec_linear
 EmuLib.cst_dec_attention = _dec_attention
+
+
+def _dec_attention_grouped(self, q, ldq, k, v, kv_dtype, kv_bs, kv_rs, out, ldo, B, H, n_keys, n_max, step, kv_group, stream):
+    return _dec_attention(self, q, ldq, k, v, kv_dtype, kv_bs, kv_rs, out, ldo, B, H, n_keys, n_max, step, stream, kv_group=kv_group)
+
+
+EmuLib.cst_dec_attention_grouped = _dec_attention_grouped
 EmuLib.cst_dec_select = _dec_select
 
 

@@ -279,3 +279,24 @@ def test_decoder_rejects_host_tensors():
     dec = B200GreedyDecoder(synth.make_decoder_state_dict(seed=1), device="cuda")
     with pytest.raises(L.CstError):
         dec.generate(torch.zeros(16, 2, 512))
+
+
+def test_generate_async_lanes_give_the_hypotheses_of_generate():
+    """Three batches decoded concurrently on three stream lanes (whole decodes enqueued as chunk graphs, no host polling) while the
+    caller's stream keeps working: token IDs and per-token log-probabilities identical to one-at-a-time generate()."""
+    from chimera_st_b200.decoder import B200GreedyDecoder
+    dsd = synth.make_decoder_state_dict(seed=1)
+    dec = B200GreedyDecoder(dsd, dtype=torch.float32, device="cuda")
+    mems = [_r(16, b, 512, seed=40 + i).cuda() for i, b in enumerate((8, 5, 8, 8))]
+    ref = [dec.generate(m, max_len=21) for m in mems]
+    busy = torch.randn(2048, 2048, device="cuda")
+    handles = []
+    for i, m in enumerate(mems[:3]):
+        handles.append(dec.generate_async(m, max_len=21, lane=i))
+        busy = busy @ busy * 1e-3                                  # unrelated work on the caller's stream
+    got = [dec.collect(h) for h in handles]
+    got.append(dec.collect(dec.generate_async(mems[3], max_len=21, lane=0)))      # lane re-used after its collect
+    for a, b in zip(ref, got):
+        assert [h["tokens"].tolist() for h in a] == [h["tokens"].tolist() for h in b]
+        for ha, hb in zip(a, b):
+            assert torch.equal(ha["positional_scores"], hb["positional_scores"])

@@ -225,6 +225,34 @@ def test_epilogue_levers_keep_parity_bf16(monkeypatch, lever):
     assert rel_l2(out, torch.from_numpy(g["memories"])) < 1e-2
 
 
+def test_modal_embedding_and_non_shared_encoder_layers_follow_the_reference_forward():
+    """`modal_embedding` (row 0 for audio, row 1 for text, added to the memory queries; w2v2_transformer_interlingua.py:272-282) and
+    `non_shared_encoder_layers` (audio runs audio_exclusive_layers[0..n) in place of transformer_layers[0..n), text keeps the shared
+    ones; :239-249).  Checked against the oracle on state dicts rewritten to the equivalent plain model."""
+    from chimera_st_b200.encoder import build_encoder_from_state_dict
+    sd = synth.make_state_dict(seed=3, interlingua_length=16, text_vocab=50, modal_embedding=True, non_shared_encoder_layers=2)
+    assert "modal_embedding.weight" in sd and "audio_exclusive_layers.1.fc2.bias" in sd
+    enc = build_encoder_from_state_dict(sd, dtype=torch.float32, device="cuda", use_graph=False)
+    assert set(enc.state_dict().keys()) == set(sd.keys())
+    plain = {k: v for k, v in sd.items() if not k.startswith(("modal_embedding.", "audio_exclusive_layers."))}
+    audio_eq, text_eq = dict(plain), dict(plain)
+    audio_eq["interlingua_embedding.weight"] = sd["interlingua_embedding.weight"] + sd["modal_embedding.weight"][0]
+    text_eq["interlingua_embedding.weight"] = sd["interlingua_embedding.weight"] + sd["modal_embedding.weight"][1]
+    for k, v in sd.items():
+        if k.startswith("audio_exclusive_layers."):
+            audio_eq["transformer_layers." + k[len("audio_exclusive_layers."):]] = v
+    wave, lens = synth.make_waveforms([12000, 7000], seed=4)
+    tok = torch.randint(4, 50, (2, 9))
+    tl = torch.tensor([9, 6])
+    with torch.no_grad():
+        ref_a, _ = O.encoder_forward(audio_eq, wave, lens)
+        ref_t, _ = O.encoder_forward_text(text_eq, tok, tl)
+    got_a = enc(wave.cuda(), lens.cuda()).encoder_out.cpu()
+    got_t = enc(tok.cuda(), tl.cuda()).encoder_out.cpu()
+    assert rel_l2(got_a, ref_a) < 1e-5 and rel_l2(got_t, ref_t) < 1e-5
+    assert rel_l2(got_a, O.encoder_forward(plain, wave, lens)[0]) > 1e-3      # the options really change the result
+
+
 def test_single_utterance_output_does_not_alias_the_arena():
     """B == 1: [1,M,512].transpose(0,1) is 'contiguous' to torch, so the result must be cloned explicitly."""
     enc = encoder(16, torch.float32, use_graph=True)

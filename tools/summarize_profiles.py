@@ -21,6 +21,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "profiles")
 SRC = os.path.join(ROOT, "gpurun_out")
 METRICS = [
+    "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+    "l1tex__data_bank_conflicts_pipe_lsu.sum", "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct",
     "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
     "launch__occupancy_limit_shared_mem", "launch__waves_per_multiprocessor",
     "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
@@ -31,8 +33,8 @@ METRICS = [
 ]
 
 
-def launch_list(tag):
-    path = os.path.join(SRC, "launches_c2.csv")
+def launch_list(tag, src="launches_c2.csv", suffix=""):
+    path = os.path.join(SRC, src)
     if not os.path.exists(path):
         return
     with open(path) as f:
@@ -52,20 +54,25 @@ def launch_list(tag):
         a[0] += 1
         a[1] += val
     tot = sum(v[1] for v in agg.values())
-    with open(os.path.join(OUT, "launches_%s.csv" % tag), "w") as f:
+    with open(os.path.join(OUT, "launches_%s%s.csv" % (tag, suffix)), "w") as f:
         w = csv.writer(f)
         w.writerow(["kernel", "launches", "total_us", "share_of_step"])
         for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             w.writerow([k, v[0], "%.1f" % v[1], "%.4f" % (v[1] / tot)])
         w.writerow(["TOTAL", sum(v[0] for v in agg.values()), "%.1f" % tot, "1.0"])
-    print("wrote launches_%s.csv (%d kernels, %.2f ms)" % (tag, len(agg), tot / 1e3))
+    print("wrote launches_%s%s.csv (%d kernels, %.2f ms)" % (tag, suffix, len(agg), tot / 1e3))
 
 
 def ncu_raw(tag, name):
+    """prof_<name>.ncu-rep, or its raw-page CSV export prof_<tag>_<name>_raw.csv made on the GPU box (gpurun copies back <= 64 MiB)."""
     rep = os.path.join(SRC, "prof_%s.ncu-rep" % name)
-    if not os.path.exists(rep):
+    raw = os.path.join(SRC, "prof_%s_%s_raw.csv" % (tag, name))
+    if os.path.exists(raw):
+        out = open(raw).read()
+    elif os.path.exists(rep):
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    else:
         return
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units, data = rows[0], rows[1], rows[2:]
     cols = [(m, hdr.index(m)) for m in ["Kernel Name"] + METRICS if m in hdr]
@@ -85,7 +92,9 @@ CLASSES = [("gemm_tc", "gemm_tc_bf16"), ("layernorm_kernel", "layernorm"), ("con
 def traffic(tag):
     """gpurun_out/traffic_c3.csv (tools/gpu_traffic.sh) -> profiles/traffic_<tag>.json: DRAM bytes per launch per kernel class."""
     import json
-    path = os.path.join(SRC, "traffic_c3.csv")
+    path = os.path.join(SRC, "traffic_%s_c3.csv" % tag)
+    if not os.path.exists(path):
+        path = os.path.join(SRC, "traffic_c3.csv")
     if not os.path.exists(path):
         return
     with open(path) as f:
@@ -125,6 +134,9 @@ if __name__ == "__main__":
     tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
     os.makedirs(OUT, exist_ok=True)
     launch_list(tag)
-    for n in ("gemm", "attn", "conv0", "posconv", "ln"):
+    launch_list(tag, "launches_%s_default.csv" % tag, "_default")      # the default bench command (c3, graphs)
+    launch_list(tag, "launches_%s_c5.csv" % tag, "_c5")                # the training step
+    launch_list(tag, "launches_%s_beam.csv" % tag, "_beam")
+    for n in ("gemm", "attn", "conv0", "posconv", "ln", "c5"):
         ncu_raw(tag, n)
     traffic(tag)
