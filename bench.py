@@ -735,6 +735,29 @@ def main():
     extras = None
     if args.workload == "c3" and not args.no_extras and dtype == torch.bfloat16:
         extras = {}
+        if world > 1 and scaling == "weak":
+            # strong-scaling probe next to the weak-scaling headline: ONE fixed global set of `--utts` utterances dealt over the
+            # ranks (shows tail imbalance and per-rank launch floors the weak form hides); resident inputs, max over ranks
+            try:
+                sb = make_workload("c3", rank, world, args.utts, args.max_tokens, strong=True)
+                sdev = [tuple(t.cuda() for t in host_batch(b, seed=5000 + 1000 * rank + i)) for i, b in enumerate(sb)]
+                for _ in range(2):
+                    enc.forward_many(sdev, n_lanes=lanes, super_rows=super_rows)
+                barrier()
+                e0.record()
+                for _ in range(args.steps):
+                    enc.forward_many(sdev, n_lanes=lanes, super_rows=super_rows)
+                e1.record()
+                barrier()
+                t_s = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+                a_s = D.reduce_sum(sum(sum(b) for b in sb) / SR, "cuda")
+                extras["c3_strong_scaling"] = {"workload": "c3, FIXED global set of %d utterances dealt round-robin over %d ranks" % (args.utts, world),
+                                               "scaling": "strong", "n_gpus": world, "batches_on_rank0": len(sb),
+                                               "ms_per_step": round(1e3 * t_s / args.steps, 3),
+                                               "audio_s_per_s": round(a_s * args.steps / t_s, 1)}
+                del sdev
+            except Exception as e:                                    # noqa: BLE001
+                extras["c3_strong_scaling"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
         enc.invalidate()
         torch.cuda.empty_cache()
         for name, fn in (("c4_encode_decode", lambda: c4_decode_quick(rank, world)), ("c5_train", lambda: c5_quick(rank, world))):
