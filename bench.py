@@ -783,14 +783,14 @@ def main():
     else:
         peak, peak_src = 72.0, "nominal fp32 FFMA 148 SM x 128 lanes x 2 x 1.9 GHz (no measured fp32 peak)"
     step_kernel_s = sum(v["seconds"] for v in ksum.values())
-    # DRAM traffic per launch of the dominant kernel from the committed ncu capture (profiles/traffic_r01.json,
+    # DRAM traffic per launch of the dominant kernel from the committed ncu capture (profiles/traffic_r02.json,
     # same workload family: c3 batches); null for other workloads
     traffic, traffic_src = None, None
     try:
         if args.workload == "c3":
-            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01.json")))
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_r02.json")))
             traffic = round(tj["kernels"][dom]["traffic_bytes_per_launch"])
-            traffic_src = "profiles/traffic_r01.json: " + tj["workload"]
+            traffic_src = "profiles/traffic_r02.json: " + tj["workload"]
     except Exception:
         pass
     roofline = {"bound": "tensor", "kernel": dom, "achieved": round(ach, 2), "peak": peak, "unit": "TFLOP/s",
@@ -813,9 +813,9 @@ def main():
                     "algorithmic_bytes_per_launch": round(k1["bytes"] / max(1, k1["launches"])), "traffic": None}
         try:
             if args.workload == "c3":
-                tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01.json")))
+                tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_r02.json")))
                 hbm_roof["traffic"] = round(tj["kernels"]["conv0_gn_gelu"]["traffic_bytes_per_launch"])
-                hbm_roof["traffic_source"] = "profiles/traffic_r01.json: " + tj["workload"]
+                hbm_roof["traffic_source"] = "profiles/traffic_r02.json: " + tj["workload"]
         except Exception:
             pass
     if args.profile_json:
