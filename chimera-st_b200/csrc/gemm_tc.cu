@@ -591,6 +591,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // ===================== TMA producer =====================
+    // Measured and rejected (round 2): letting this warp pull each tile's fp32 residual rows into L2 a k-loop ahead
+    // (cp.async.bulk.prefetch.L2, 128 x 1 KB per tile) for the HBM-bound residual GEMMs (out-proj: 372 TFLOP/s, ~0.55 of the HBM
+    // bound) made c3 SLOWER: 191.8 - 192.4 -> 196.7 - 196.8 ms per step.
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
