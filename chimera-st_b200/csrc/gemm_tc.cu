@@ -593,7 +593,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== TMA producer =====================
     // Measured and rejected (round 2): letting this warp pull each tile's fp32 residual rows into L2 a k-loop ahead
     // (cp.async.bulk.prefetch.L2, 128 x 1 KB per tile) for the HBM-bound residual GEMMs (out-proj: 372 TFLOP/s, ~0.55 of the HBM
-    // bound) made c3 SLOWER: 191.8 - 192.4 -> 196.7 - 196.8 ms per step.
+    // bound) made c3 SLOWER: 191.8 - 192.4 -> 196.7 - 196.8 ms per step; the same prefetch issued by the
+    // epilogue warps for their slice of the NEXT tile (one lane per row, 512 B) was also slower (187.9 - 189.2 -> 189.4 - 189.9 ms):
+    // those rows were written by the kernel before and mostly sit in the 126 MB L2 already.
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
