@@ -313,7 +313,7 @@ def c4_decode_quick(rank, world, dtype=torch.bfloat16, beam=1):
     if beam == 1:
         # throughput form over a stream of batches: the latency-bound decode of batch i runs on its own stream underneath the
         # encoder pass of batch i+1 and the decodes of batches i-1, i-2 (decoder.generate_async); same kernels, same hypotheses
-        n_lanes = int(os.environ.get("CST_C4_LANES", "3"))
+        n_lanes = int(os.environ.get("CST_C4_LANES", "6"))
         n_batches = 3 * n_lanes
         pending = [None] * n_lanes
 

@@ -671,6 +671,9 @@ static int dec_linear_init() {
   int dev = 0;
   CST_CHECK_CUDA(cudaGetDevice(&dev));
   CST_CHECK_CUDA(cudaDeviceGetAttribute(&g_dl_sms, cudaDevAttrMultiProcessorCount, dev));
+  // CST_DEC_SMS: SM count the K = 512 linears size their persistent grids for (lever for concurrent decode lanes: smaller grids
+  // leave room for the kernels of the other lanes)
+  if (const char* e = getenv("CST_DEC_SMS")) { if (atoi(e) > 0) g_dl_sms = atoi(e); }
   return CST_OK;
 }
 
