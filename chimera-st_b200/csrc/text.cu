@@ -30,7 +30,31 @@ __global__ void __launch_bounds__(128) text_embed_kernel(const long long* __rest
   }
 }
 
+// x[b, t] += pos[t < valid[b] ? t + 2 : 1] for t < T: the sinusoidal positions the NON-memory base encoder adds to the sub-sampled
+// audio frames (S2T_W2V2_TransformerEncoder.forward, fairseq/models/chimera/w2v2_transformer.py:353-357; same position rule as
+// the text branch: make_positions over the padding mask, row 1 = padding_idx is zero).
+__global__ void __launch_bounds__(128) add_positions_kernel(float* __restrict__ x, const int* __restrict__ valid,
+                                                            const float* __restrict__ pos, int T, int rows_per_seg, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.x / T, t = blockIdx.x - b * T;
+  if (t >= valid[b]) return;                                   // padded frames get the zero row
+  float* dst = x + ((size_t)b * rows_per_seg + t) * C;
+  const float* q = pos + (size_t)(t + 2) * C;
+  for (int c = 4 * threadIdx.x; c < C; c += 4 * blockDim.x) {
+    const float4 a = load4(dst + c), p4 = load4(q + c);
+    store4(dst + c, make_float4(a.x + p4.x, a.y + p4.y, a.z + p4.z, a.w + p4.w));
+  }
+}
+
 }  // namespace cst
+
+extern "C" int cst_add_positions(float* x, const int32_t* valid, const float* pos_table, int B, int T, int rows_per_seg, int C, void* stream) {
+  CST_REQUIRE(x && valid && pos_table && B > 0 && T > 0 && rows_per_seg >= T && C > 0 && C % 4 == 0, "cst_add_positions: bad args");
+  CST_CHECK_CUDA(cst::launch_k(cst::add_positions_kernel, dim3(B * T), dim3(128), 0, (cudaStream_t)stream, x, (const int*)valid, pos_table, T,
+                               rows_per_seg, C));
+  return CST_OK;
+}
 
 extern "C" int cst_text_embed(const int64_t* tokens, const int64_t* lengths, const float* embed, const float* pos_table,
                               float scale, float* x, int32_t* valid, int B, int T, int rows_per_seg, int C, int V,

@@ -75,6 +75,10 @@ class B200InterlinguaEncoder(nn.Module):
         self.use_graph = use_graph
         self.encoder_out_dtype = encoder_out_dtype
         self.no_interlingua = False
+        # base_encoder = True: the arithmetic of the reference's NON-memory encoder (S2T_W2V2_TransformerEncoder.forward,
+        # fairseq/models/chimera/w2v2_transformer.py:338-386) on the same parameters: sinusoidal positions after the subsampler,
+        # encoder_out = LayerNorm-ed states [T2, B, 512], the real key-padding mask (None when nothing is padded)
+        self.base_encoder = False
         for name, shape, _, _ in encoder_param_spec(interlingua_length, dead_heads, text_vocab, modal_embedding, non_shared_encoder_layers):
             _register(self, name, torch.zeros(shape), buffer=name.endswith("_float_tensor"))
         self._prepared = None
@@ -125,7 +129,8 @@ class B200InterlinguaEncoder(nn.Module):
             plans, arena = self._plans, self._arena
         else:
             plans, arena = lane["plans"], lane["arena"]
-        key = (B, L, text) if groups is None else tuple(groups)
+        base = bool(self.base_encoder) and not text
+        key = (B, L, text, base) if groups is None else tuple(groups) + (base,)
         plan = plans.get(key)
         if plan is None:
             while len(plans) >= self.MAX_PLANS:
@@ -136,7 +141,7 @@ class B200InterlinguaEncoder(nn.Module):
                                 arena=arena)
             else:
                 plan = EncoderPlan(self._prepared, B, L, self.interlingua_length, self.compute_dtype, dev, self.use_graph,
-                                   arena=arena, conv_dtype=self.conv_dtype, groups=groups)
+                                   arena=arena, conv_dtype=self.conv_dtype, groups=groups, audio_positions=base)
             if arena.generation != gen:                # arena grew: older plans (and their graphs) point at freed memory
                 plans.clear()
             plans[key] = plan
@@ -263,6 +268,12 @@ class B200InterlinguaEncoder(nn.Module):
         plan = self._plan(B, L)
         plan.load_inputs(src_tokens if src_tokens.dtype == torch.int16 else src_tokens.float(), src_lengths)
         self.last_launches = plan.run()
+        if self.base_encoder:                                      # w2v2_transformer.py:364-386
+            out = plan.view("h_enc").transpose(0, 1)
+            out = out.to(self.encoder_out_dtype or self._out_dtype(src_tokens)).clone(memory_format=torch.contiguous_format)
+            T2 = out.shape[0]
+            pad = torch.arange(T2, device=out.device)[None, :] >= plan.sub_valid[:B, None]
+            return EncoderOut(out, pad if bool(pad.any()) else None, None, None, None, None)
         if self.no_interlingua:                                    # interlingua:260-262
             out = plan.view("h_enc").transpose(0, 1)
         else:

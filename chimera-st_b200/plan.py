@@ -75,11 +75,14 @@ class EncoderPlan:
     offsets.  Results are those of running each group alone (tests/test_gpu_encoder.py::test_super_batch_*)."""
 
     def __init__(self, params, B, Lw, M, act_dtype=torch.float32, device=None, use_graph=False, lib=None,
-                 arena=None, conv_dtype=None, groups=None):
+                 arena=None, conv_dtype=None, groups=None, audio_positions=False):
         # `lib` is injectable so tests can drive the plan against a host emulator of the C ABI
         # (tests/emu.py); the product never passes it and always loads the CUDA library.
         self.lib = lib if lib is not None else L.load()
         self.P = params
+        # the NON-memory base encoder adds sinusoidal positions to the sub-sampled frames (w2v2_transformer.py:353-357)
+        self.audio_positions = bool(audio_positions)
+        self._pos_dev = None
         self.groups = [(int(b), int(l)) for b, l in groups] if groups is not None else [(int(B), int(Lw))]
         self.gs = gs = [Geometry(b, l, M) for b, l in self.groups]
         self.g = gs[0]                                  # single-batch plans: the geometry (kept for callers / tests)
@@ -526,6 +529,13 @@ class EncoderPlan:
         if upto == "w2v":
             return
         self._stage_subsample()
+        if self.audio_positions:
+            if self._pos_dev is None:                           # static plan data, kept outside the (shared) arena
+                self._pos_dev = sinusoidal_table(max(g.T2 for g in self.gs) + 2).to(self.dev)
+            for k, g in enumerate(self.gs):
+                L.check(self.lib.cst_add_positions(self.x2[self.r2_0[k]:].data_ptr(), self.sub_valid[self.utt0[k]:].data_ptr(),
+                                                   self._pos_dev.data_ptr(), g.B, g.T2, g.T2a, ENC_DIM, self.st))
+                self.launches += 1
         self._stage_shared_layers()
         self._stage_memory()
 

@@ -203,6 +203,10 @@ int cst_attention_segs(const void* q, const void* k, const void* v, void* out, i
  * x f32 [B*rows_per_seg, C] (rows t >= T of a segment are zero-filled); valid int32 [B] = lengths (may be NULL). */
 int cst_text_embed(const int64_t* tokens, const int64_t* lengths, const float* embed, const float* pos_table,
                    float scale, float* x, int32_t* valid, int B, int T, int rows_per_seg, int C, int V, void* stream);
+/* Sinusoidal positions of the NON-memory base encoder (S2T_W2V2_TransformerEncoder.forward, fairseq/models/chimera/
+ * w2v2_transformer.py:353-357): x[b, t, :] += pos_table[t + 2] for t < valid[b] (padded frames get the zero padding row); same table
+ * as cst_text_embed, T + 2 rows.  x f32 [B*rows_per_seg, C]. */
+int cst_add_positions(float* x, const int32_t* valid, const float* pos_table, int B, int T, int rows_per_seg, int C, void* stream);
 
 /* ==== training heads over the path's outputs =====================================================
  * Contrastive (InfoNCE) loss over the M shared semantic memories of the audio and the text pass.

@@ -240,6 +240,27 @@ def encoder_forward(sd, wave, src_lengths, stages=None, literal_memory=False):
     return out, torch.zeros(wave.shape[0], out.shape[0], dtype=torch.bool)        # :301-312
 
 
+def base_encoder_forward(sd, wave, src_lengths):
+    """S2T_W2V2_TransformerEncoder.forward (the NON-memory base encoder, fairseq/models/chimera/w2v2_transformer.py:338-386):
+    wav2vec2 features -> subsampler -> x = sqrt(512) x + embed_positions(padding mask) (:353-357; positions 2, 3, ... on the valid
+    frames, the zero padding row elsewhere, as in the text branch) -> 6 shared layers -> LayerNorm.
+    Returns (encoder_out [T2,B,512], encoder_padding_mask bool [B,T2] or None when nothing is padded (:366-367))."""
+    assert int(src_lengths.max()) == wave.shape[1], "collater guarantees max(len)==L"
+    x, fmask, lens = wav2vec_extract_features(sd, wave, src_lengths)
+    x, lens2 = conv1d_subsampler(sd, x, lens)
+    x = math.sqrt(512) * x
+    pad = lengths_to_padding_mask(lens2)
+    if pad.shape[1] < x.shape[1]:
+        pad = F.pad(pad, (0, x.shape[1] - pad.shape[1]), value=True)
+    valid = ~pad
+    positions = torch.cumsum(valid.long(), dim=1) * valid.long() + 1
+    x = x + sinusoidal_table(x.shape[1] + 2)[positions].to(x.dtype)
+    for i in range(6):
+        x = encoder_layer(sd, f"transformer_layers.{i}.", x, pad)
+    x = _ln(x, sd, "layer_norm")
+    return x.transpose(0, 1).contiguous(), (pad if bool(pad.any()) else None)
+
+
 def sinusoidal_table(n, dim=512, padding_idx=1):
     """SinusoidalPositionalEmbedding.get_embedding, fairseq/modules/sinusoidal_positional_embedding.py:38-59."""
     half = dim // 2

@@ -253,6 +253,30 @@ def test_modal_embedding_and_non_shared_encoder_layers_follow_the_reference_forw
     assert rel_l2(got_a, O.encoder_forward(plain, wave, lens)[0]) > 1e-3      # the options really change the result
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_base_encoder_mode_matches_the_reference_base_class(dtype):
+    """enc.base_encoder = True: S2T_W2V2_TransformerEncoder.forward (w2v2_transformer.py:338-386) -- sinusoidal positions after
+    the subsampler, LayerNorm-ed states as encoder_out, the real padding mask or None -- against goldens of the UNMODIFIED
+    reference base-class forward (oracle/gen_golden_base.py)."""
+    from chimera_st_b200.encoder import build_encoder_from_state_dict
+    g = np.load(os.path.join(GOLDEN, "base_encoder.npz"))
+    enc = build_encoder_from_state_dict(synth.make_state_dict(seed=0, interlingua_length=16), dtype=dtype, device="cuda", use_graph=False)
+    enc.base_encoder = True
+    for name in ("tiny", "full"):
+        wave, lens = synth.make_waveforms(g[name + "_lens"].tolist(), seed=int(g[name + "_seed"]))
+        out = enc(wave.cuda(), lens.cuda())
+        ref = torch.from_numpy(g[name + "_encoder_out"])
+        assert out.encoder_out.shape == ref.shape
+        assert rel_l2(out.encoder_out.float().cpu(), ref) < TOL[dtype]
+        if bool(g[name + "_has_mask"]):
+            assert torch.equal(out.encoder_padding_mask.cpu(), torch.from_numpy(g[name + "_padding_mask"]))
+        else:
+            assert out.encoder_padding_mask is None
+    enc.base_encoder = False
+    mem = enc(wave.cuda(), lens.cuda())                      # back to the memory encoder: separate plan, [M, B, 512]
+    assert mem.encoder_out.shape == (16, len(g["full_lens"]), 512)
+
+
 def test_single_utterance_output_does_not_alias_the_arena():
     """B == 1: [1,M,512].transpose(0,1) is 'contiguous' to torch, so the result must be cloned explicitly."""
     enc = encoder(16, torch.float32, use_graph=True)

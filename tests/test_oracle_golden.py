@@ -116,3 +116,18 @@ def test_integer_rules_exhaustive():
         fm = O.frame_padding_mask(torch.tensor(ns), T)
         assert (~fm).sum(1).tolist() == got
         assert O.subsampler_lengths(torch.tensor(got)).tolist() == [s for *_, s in items]
+
+
+def test_base_encoder_restatement_matches_the_reference_base_class():
+    """oracle.base_encoder_forward (S2T_W2V2_TransformerEncoder.forward, w2v2_transformer.py:338-386) against the unmodified
+    reference (tests/golden/base_encoder.npz, oracle/gen_golden_base.py)."""
+    g = np.load(os.path.join(GOLDEN, "base_encoder.npz"))
+    sd = synth.make_state_dict(seed=0, interlingua_length=16)
+    for name in ("tiny", "full"):
+        wave, lens = synth.make_waveforms(g[name + "_lens"].tolist(), seed=int(g[name + "_seed"]))
+        with torch.no_grad():
+            out, pad = O.base_encoder_forward(sd, wave, lens)
+        assert rel_l2(out, torch.from_numpy(g[name + "_encoder_out"])) < 5e-6
+        assert (pad is not None) == bool(g[name + "_has_mask"])
+        if pad is not None:
+            assert np.array_equal(pad.numpy(), g[name + "_padding_mask"])
