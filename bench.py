@@ -277,6 +277,22 @@ def c5_quick(rank, world, steps=5, dtype=torch.bfloat16, comm_dtype=torch.bfloat
         torch.cuda.synchronize(); D.barrier()
         out[key] = round(D.reduce_max(e0.elapsed_time(e1), "cuda") / steps, 3)
     total_audio = D.reduce_sum(B * Lw / SR, "cuda")
+    # ... and with the parameter update (fused Adam on the reduced gradients + operand refresh, one more CUDA graph)
+    from chimera_st_b200.train import FusedAdam
+    gs.reducer = ddp.GradAllReducer(gs.names, world_size=world, bucket_bytes=bucket_mb << 20, comm_dtype=comm_dtype, persistent=True)
+    gs.optimizer = FusedAdam({n: step.sd[n] for n, _ in gs.names}, lr=1e-5, betas=(0.9, 0.98), eps=1e-8)
+    loss0 = float(gs.loss)
+    for _ in range(3):
+        gs.run()
+    torch.cuda.synchronize(); D.barrier(); torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        gs.run()
+    e1.record()
+    torch.cuda.synchronize(); D.barrier()
+    t_opt = D.reduce_max(e0.elapsed_time(e1), "cuda") / steps
+    out["with_adam_update"] = {"ms_per_step": round(t_opt, 3), "audio_s_per_s": round(total_audio / (t_opt * 1e-3), 1),
+                               "loss_before": loss0, "loss_after_%d_updates" % (3 + steps): float(gs.loss)}
     out.update({"workload": "c5: training step (forward + contrastive head + backward + gradient all-reduce), B=%d x %d samples per GPU, bf16" % (B, Lw),
                 "audio_s_per_s": round(total_audio / (out["ms_per_step"] * 1e-3), 1), "n_gpus": world,
                 "allreduce_bytes_per_step": sum(n for _, n in gs.names) * (2 if comm_dtype is not None else 4),
@@ -477,6 +493,25 @@ def run_c5(args, rank, world, local_rank, cores):
     csum = float(probe.double().sum())
     agree = abs(D.reduce_max(csum, "cuda") + D.reduce_max(-csum, "cuda")) <= 1e-6 * max(1.0, abs(csum))
     total_audio = D.reduce_sum(audio_per_step, "cuda")
+    # the same step with the parameter update: fused Adam on the reduced gradients + refresh of the kernel-layout operands, one more
+    # CUDA graph (the reference: FP16Optimizer + Adam, fairseq/optim/fp16_optimizer.py, adam.py)
+    from chimera_st_b200.train import FusedAdam
+    gs.reducer = ddp.GradAllReducer(gs.names, world_size=world, bucket_bytes=args.bucket_mb << 20, comm_dtype=comm, persistent=True)
+    gs.optimizer = FusedAdam({n: step.sd[n] for n, _ in gs.names}, lr=1e-5, betas=(0.9, 0.98), eps=1e-8, weight_decay=0.0)
+    loss0 = float(gs.loss)
+    for _ in range(3):
+        gs.run()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        gs.run()
+    e1.record()
+    barrier()
+    t_opt = D.reduce_max(e0.elapsed_time(e1) * 1e-3, "cuda")
+    loss1 = float(gs.loss)
+    psum = float(step.sd["wav2vec_model.encoder.layers.0.fc1.weight"].double().sum())
+    params_agree = abs(D.reduce_max(psum, "cuda") + D.reduce_max(-psum, "cuda")) <= 1e-9 * max(1.0, abs(psum))
+    gs.optimizer = None
 
     # ---- instrumented eager pass: per-kernel CUDA-event timing for the roofline object
     prof = LaunchProfiler(step.o.lib)
@@ -533,7 +568,11 @@ def run_c5(args, rank, world, local_rank, cores):
             "train": {"loss": float(gs.loss), "parameters": n_params, "gradient_tensors": len(gs.names),
                       "backward_segments": len(gs.seg_grads), "buckets": len(red.buckets),
                       "allreduce_bytes_per_step": grad_bytes, "ms_per_step_without_allreduce": round(1e3 * t_local / args.steps, 3),
-                      "allreduce_exposed_ms": round(1e3 * (t_res - t_local) / args.steps, 3), "replicas_agree": bool(agree)},
+                      "allreduce_exposed_ms": round(1e3 * (t_res - t_local) / args.steps, 3), "replicas_agree": bool(agree),
+                      "with_adam_update": {"ms_per_step": round(1e3 * t_opt / args.steps, 3),
+                                           "audio_s_per_s": round(total_audio * args.steps / t_opt, 1),
+                                           "loss_before": loss0, "loss_after_%d_updates" % (3 + args.steps): loss1,
+                                           "parameters_agree_across_ranks": bool(params_agree)}},
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(line))
     D.finalize()

@@ -462,3 +462,36 @@ extern "C" int cst_rows_remap(const float* in, long long ldi, int in_rps, int in
                           in_rps, in_off, out, out_dtype, ldo, out_rps, out_off, n_seg, n_rows, C, seg_valid, seg_len, accumulate, scale));
   return CST_OK;
 }
+
+// ---- fused Adam update of one parameter tensor ("optimizer fusion").
+// Replaces: fairseq/optim/adam.py:157-224 (the fp32 path FP16Optimizer drives, fairseq/optim/fp16_optimizer.py):
+//   g' = g * grad_scale;  m = b1 m + (1-b1) g';  v = b2 v + (1-b2) g'^2;  denom = sqrt(v) + eps
+//   p -= weight_decay * lr * p;  p -= step_size * m / denom,   step_size = lr sqrt(1 - b2^t) / (1 - b1^t) (formed by the caller)
+// One pass over p / m / v (fp32) and the all-reduced gradient (fp32 or the bf16 wire format of ddp.GradAllReducer) instead of the ~10
+// elementwise torch kernels of the reference's step.
+namespace cst {
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const void* __restrict__ g, int gdt, float* __restrict__ m,
+                                                   float* __restrict__ v, long long n, float lr, float b1, float b2, float eps, float wd,
+                                                   float step_size, float gscale, const float* __restrict__ dyn) {
+  pdl_launch_dependents();
+  pdl_wait();
+  if (dyn != nullptr) { lr = dyn[0]; step_size = dyn[1]; gscale = dyn[2]; }     // per-step values from the device: one CUDA graph for all steps
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = ld_any(g, gdt, i) * gscale;
+    const float mi = b1 * m[i] + (1.0f - b1) * gi;
+    const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+    float pi = p[i];
+    pi -= wd * lr * pi;
+    pi -= step_size * mi / (sqrtf(vi) + eps);
+    m[i] = mi; v[i] = vi; p[i] = pi;
+  }
+}
+}  // namespace cst
+
+extern "C" int cst_adam_step(float* p, const void* g, int g_dtype, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                             float eps, float weight_decay, float step_size, float grad_scale, const float* dyn, void* stream) {
+  CST_REQUIRE(p && g && m && v && n > 0 && (g_dtype == CST_F32 || g_dtype == CST_BF16), "cst_adam_step: bad args");
+  CST_CHECK_CUDA(launch_k(cst::adam_kernel, dim3(grid_for(n)), dim3(256), 0, (cudaStream_t)stream, p, g, g_dtype, m, v, n, lr, beta1, beta2, eps,
+                          weight_decay, step_size, grad_scale, dyn));
+  return CST_OK;
+}

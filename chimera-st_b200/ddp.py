@@ -42,10 +42,13 @@ def plan_buckets(named_sizes, bucket_bytes=32 << 20, elem_bytes=4):
 
 
 class GradAllReducer:
-    def __init__(self, named_sizes, world_size=None, process_group=None, bucket_bytes=32 << 20, comm_dtype=None):
+    def __init__(self, named_sizes, world_size=None, process_group=None, bucket_bytes=32 << 20, comm_dtype=None, persistent=False):
         """comm_dtype: dtype of the flat buffers on the wire (None: the gradients' own fp32; torch.bfloat16 halves the bytes, the
-        reference's --fp16 runs reduce fp16 gradients the same way)."""
+        reference's --fp16 runs reduce fp16 gradients the same way).  persistent: the flat buffers are allocated once and reused, so
+        the reduced gradients keep their addresses from step to step (a CUDA-graphed optimizer update can read them)."""
         self.comm_dtype = comm_dtype
+        self.persistent = persistent
+        self._stage, self._comm = {}, {}
         self.group = process_group
         self.world = world_size if world_size is not None else (dist.get_world_size(process_group) if dist.is_initialized() else 1)
         self.sizes = OrderedDict(named_sizes)
@@ -72,10 +75,23 @@ class GradAllReducer:
 
     def _launch(self, bi):
         names = self.buckets[bi]
-        flat = torch.cat([self.have[bi][n].reshape(-1) for n in names]) if len(names) > 1 else self.have[bi][names[0]].reshape(-1).clone()
-        flat.div_(self.world)                                       # pre-divided, as the reference (:126-127)
-        if self.comm_dtype is not None and flat.dtype != self.comm_dtype:
-            flat = flat.to(self.comm_dtype)
+        parts = [self.have[bi][n].reshape(-1) for n in names]
+        if self.persistent:
+            if bi not in self._stage:
+                self._stage[bi] = torch.empty(sum(p.numel() for p in parts), dtype=parts[0].dtype, device=parts[0].device)
+                if self.comm_dtype is not None and self.comm_dtype != parts[0].dtype:
+                    self._comm[bi] = torch.empty_like(self._stage[bi], dtype=self.comm_dtype)
+            flat = self._stage[bi]
+            torch.cat(parts, out=flat)
+            flat.div_(self.world)
+            if bi in self._comm:
+                self._comm[bi].copy_(flat)
+                flat = self._comm[bi]
+        else:
+            flat = torch.cat(parts) if len(names) > 1 else parts[0].clone()
+            flat.div_(self.world)                                   # pre-divided, as the reference (:126-127)
+            if self.comm_dtype is not None and flat.dtype != self.comm_dtype:
+                flat = flat.to(self.comm_dtype)
         work = None
         if self.world > 1:
             work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)

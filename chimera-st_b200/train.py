@@ -223,7 +223,7 @@ class EncoderTrainStep:
         # bf16 there costs 6e-3 of the 1e-2 budget); every backward operand (transposed copies of weights, activations, gradients)
         # is bf16 -- gradients need the range, and cst_transpose converts on the fly.
         self.cdt = dtype if dtype == F32 else torch.float16
-        self.P = _weights.prepare(self.sd, dev, dtype, conv_dtype=self.cdt)
+        self.P = _weights.prepare(self.sd, dev, dtype, conv_dtype=self.cdt, training=True)
 
     # ------------------------------------------------------------------ forward (activations kept)
     def forward(self, wave, lens):
@@ -551,6 +551,64 @@ class EncoderTrainStep:
         mem = self.forward(wave, lens)
         return mem, self.backward(d_mem)
 
+    def refresh_weights(self):
+        """After the fp32 master parameters (`self.sd`, reference layout) changed in place: rebuild the kernel-layout operands and copy
+        them INTO the existing device tensors (captured CUDA graphs keep their weight pointers) -- the counterpart of the fp32 -> fp16
+        parameter sync of the reference's FP16Optimizer (fairseq/optim/fp16_optimizer.py)."""
+        new = _weights.prepare(self.sd, self.dev, self.op, conv_dtype=self.cdt, training=True)
+
+        def copy_tree(dst, src):
+            if torch.is_tensor(dst):
+                dst.copy_(src)
+            elif isinstance(dst, dict):
+                for k in dst:
+                    copy_tree(dst[k], src[k])
+            elif isinstance(dst, (list, tuple)):
+                for a, b in zip(dst, src):
+                    copy_tree(a, b)
+        copy_tree(self.P, new)
+
+
+class FusedAdam:
+    """Adam over the encoder's fp32 master parameters, one fused kernel per tensor (`cst_adam_step`), the arithmetic of
+    fairseq/optim/adam.py:157-224 (decoupled weight decay `p -= wd * lr * p`, eps added to sqrt(v), bias corrections in the step size).
+    Gradients may be fp32 or the bf16 wire format of the all-reduce.  The per-step scalars (lr, step size, gradient scale) are read from
+    a device buffer, so `step` can be captured into a CUDA graph once and replayed every step after `advance()`."""
+
+    def __init__(self, params, lr=1e-4, betas=(0.9, 0.98), eps=1e-8, weight_decay=0.0):
+        self.params = params                                       # {reference name: fp32 device tensor}, updated in place
+        self.lr, self.betas, self.eps, self.wd = float(lr), (float(betas[0]), float(betas[1])), float(eps), float(weight_decay)
+        dev = next(iter(params.values())).device
+        self.m = {k: torch.zeros_like(v) for k, v in params.items()}
+        self.v = {k: torch.zeros_like(v) for k, v in params.items()}
+        self.t = 0
+        self.dyn = torch.zeros(4, dtype=F32, device=dev)
+        self._dyn_host = torch.zeros(4, dtype=F32).pin_memory() if dev.type == "cuda" else torch.zeros(4, dtype=F32)
+        self.lib = L.load()
+
+    def advance(self, lr=None, grad_scale=1.0):
+        """Next step number: refresh {lr, step_size, grad_scale} on the device (asynchronous copy on the current stream)."""
+        self.t += 1
+        if lr is not None:
+            self.lr = float(lr)
+        b1, b2 = self.betas
+        self._dyn_host[0] = self.lr
+        self._dyn_host[1] = self.lr * math.sqrt(1.0 - b2 ** self.t) / (1.0 - b1 ** self.t)
+        self._dyn_host[2] = float(grad_scale)
+        self.dyn.copy_(self._dyn_host, non_blocking=True)
+
+    def step(self, grads):
+        """Launch the updates (reads the scalars written by the last `advance()`); parameters without a gradient are left alone."""
+        b1, b2 = self.betas
+        st = L.stream_ptr()
+        for name, p in self.params.items():
+            g = grads.get(name)
+            if g is None:
+                continue
+            assert g.numel() == p.numel() and g.is_contiguous() and p.is_contiguous(), name
+            L.check(self.lib.cst_adam_step(p.data_ptr(), g.data_ptr(), _CODE[g.dtype], self.m[name].data_ptr(), self.v[name].data_ptr(), p.numel(),
+                                           self.lr, b1, b2, self.eps, self.wd, 0.0, 1.0, self.dyn.data_ptr(), st))
+
 
 class GraphedTrainStep:
     """One training step of the path as CUDA graphs: forward + loss in one graph, the backward pass in one graph per segment of
@@ -559,8 +617,9 @@ class GraphedTrainStep:
     device buffers (`wave`, `lens`); `loss_fn(memories [M, B, 512]) -> (loss scalar tensor, d_memories)` is captured with the
     forward pass.  Every activation / gradient lives in the graphs' shared memory pool, so replays allocate nothing."""
 
-    def __init__(self, step, wave, lens, loss_fn, reducer=None, warmup=2):
+    def __init__(self, step, wave, lens, loss_fn, reducer=None, warmup=2, optimizer=None):
         self.step, self.wave, self.lens, self.reducer = step, wave, lens, reducer
+        self.optimizer, self.g_update = optimizer, None
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):                              # eager warm-up (one-time attribute / descriptor setup)
@@ -569,7 +628,7 @@ class GraphedTrainStep:
                 step.backward(dmem)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        pool = torch.cuda.graph_pool_handle()
+        pool = self.pool = torch.cuda.graph_pool_handle()
         self.graphs, self.seg_grads = [], []
         g0 = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g0, pool=pool):
@@ -601,6 +660,20 @@ class GraphedTrainStep:
                 self.reducer.ready(part)
         if self.reducer is not None:
             self.reduced = self.reducer.finish(self.grads)
+        if self.optimizer is not None:
+            # parameter update + refresh of the kernel-layout operands as one more CUDA graph (captured on the first step, when the
+            # reduced gradients exist; a persistent reducer keeps their addresses)
+            grads = self.reduced if self.reducer is not None else self.grads
+            self.optimizer.advance()
+            if self.g_update is None:
+                assert self.reducer is None or self.reducer.persistent, "a graphed optimizer needs GradAllReducer(persistent=True)"
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=self.pool):
+                    self.optimizer.step(grads)
+                    self.step.refresh_weights()
+                self.g_update = g
+            self.g_update.replay()
         return self.loss
 
 

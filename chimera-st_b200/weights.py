@@ -36,8 +36,10 @@ def _glu_interleave(w):
     return torch.stack((w[:half], w[half:]), dim=1).reshape(w.shape)
 
 
-def prepare(state_dict, device, act_dtype, conv_dtype=None):
-    """conv_dtype: operand dtype of the conv feature extractor GEMMs (conv1..6); defaults to act_dtype."""
+def prepare(state_dict, device, act_dtype, conv_dtype=None, training=False):
+    """conv_dtype: operand dtype of the conv feature extractor GEMMs (conv1..6); defaults to act_dtype.
+    training=True (train.py): only the operands the training step uses, built with device-side ops only (no host round trip), so
+    that the refresh after an optimizer update can be captured into a CUDA graph."""
     sd = _strip(state_dict)
     conv_dtype = conv_dtype or act_dtype
     f32 = lambda t: t.detach().to(device=device, dtype=torch.float32).contiguous()   # noqa: E731
@@ -46,7 +48,7 @@ def prepare(state_dict, device, act_dtype, conv_dtype=None):
     P = {}
     fe = W + "feature_extractor.conv_layers."
     P["conv0_w"] = f32(sd[fe + "0.0.weight"].reshape(512, 10))
-    if act_dtype != torch.float32:
+    if act_dtype != torch.float32 and not training:
         # tcgen05 conv0 (cst_conv0_apply_tc): fp16 [512, 64] rows [hi | hi | lo | 0...], hi = fp16(w), lo = fp16(w - hi)
         w0 = P["conv0_w"]
         hi = w0.to(torch.float16)
@@ -69,12 +71,12 @@ def prepare(state_dict, device, act_dtype, conv_dtype=None):
         w = v * (g / v.norm(dim=(0, 1), keepdim=True))
     cg = w.shape[1]                                        # 48 channels per group
     wg = w.view(POS_GROUPS, cg, cg, POS_K).permute(0, 1, 3, 2)      # [g, co, tap, ci]
-    wp = torch.zeros(POS_GROUPS, cg, POS_K, 64, dtype=torch.float32)
+    wp = torch.zeros(POS_GROUPS, cg, POS_K, 64, dtype=torch.float32, device=w.device)
     wp[..., :cg] = wg
     P["pos_w"] = op(wp.reshape(POS_GROUPS, cg, POS_K * 64))
-    if act_dtype != torch.float32:
+    if act_dtype != torch.float32 and not training:
         # cst_posconv_stacked: [group, tap pair, 128 rows, 64 lanes]; rows 0..47 even tap, rows 64..111 odd tap
-        w2 = torch.zeros(POS_GROUPS, POS_K // 2, 128, 64, dtype=torch.float32)
+        w2 = torch.zeros(POS_GROUPS, POS_K // 2, 128, 64, dtype=torch.float32, device=w.device)
         w2[:, :, 0:cg, :] = wp[:, :, 0::2, :].permute(0, 2, 1, 3)
         w2[:, :, 64:64 + cg, :] = wp[:, :, 1::2, :].permute(0, 2, 1, 3)
         P["pos_w2"] = op(w2)
@@ -128,7 +130,7 @@ def prepare(state_dict, device, act_dtype, conv_dtype=None):
     if n_excl:
         P["enc_layers_text"] = P["enc_layers"]
         P["enc_layers"] = [layer(f"audio_exclusive_layers.{i}.") for i in range(n_excl)] + P["enc_layers_text"][n_excl:]
-    if act_dtype != torch.float32:
+    if act_dtype != torch.float32 and not training:
         # fused-LayerNorm variants (16-bit mode): post-LN wav2vec2 layers -- QKV of layer i consumes LN2 of layer i-1, fc1
         # consumes LN1 of its own layer; pre-LN shared layers -- QKV consumes LN1, fc1 consumes LN2 of their own layer
         for i, d in enumerate(P["w2v_layers"]):
@@ -167,7 +169,8 @@ def prepare(state_dict, device, act_dtype, conv_dtype=None):
         ws.append(w * g_[None, :])
         bs.append(c + w @ b_)
     P["mem_kv_w"], P["mem_kv_b"] = op(torch.cat(ws, 0).float()), f32(torch.cat(bs, 0).float())
-    P["unit_g"], P["unit_b"] = f32(torch.ones(sd["layer_norm.weight"].shape[0])), f32(torch.zeros(sd["layer_norm.weight"].shape[0]))
+    P["unit_g"] = torch.ones(sd["layer_norm.weight"].shape[0], dtype=torch.float32, device=device)
+    P["unit_b"] = torch.zeros(sd["layer_norm.weight"].shape[0], dtype=torch.float32, device=device)
     if act_dtype == torch.float32 and os.environ.get("CST_F32_TC", "0") == "1":
         P["_s16"] = split_packs(P)          # only the opt-in "fast fp32" mode needs them (plan.py)
     return P

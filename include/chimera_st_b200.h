@@ -280,6 +280,12 @@ int cst_col2im(const void* dcol, int dcol_dtype, long long M, int k, int stride,
 /* out[seg*out_rps + t + out_off] (+)= scale * in[seg*in_rps + t + in_off] for t < min(seg_valid, seg_len[seg]), else 0 (t < n_rows). */
 int cst_rows_remap(const float* in, long long ldi, int in_rps, int in_off, void* out, int out_dtype, long long ldo, int out_rps, int out_off,
                    int n_seg, int n_rows, int C, int seg_valid, const int32_t* seg_len, int accumulate, float scale, void* stream);
+/* Fused Adam update of one tensor.  Replaces fairseq/optim/adam.py:157-224 (fp32 parameters and moments; the gradient is fp32 or the bf16
+ * wire format of the all-reduce): m = b1 m + (1-b1) g', v = b2 v + (1-b2) g'^2 with g' = grad_scale * g; p -= weight_decay*lr*p;
+ * p -= step_size * m / (sqrt(v) + eps), step_size = lr * sqrt(1 - b2^t) / (1 - b1^t) formed by the caller.  dyn (optional, device
+ * float[3] = {lr, step_size, grad_scale}) overrides the by-value arguments, so that one captured CUDA graph serves every step. */
+int cst_adam_step(float* p, const void* g, int g_dtype, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                  float weight_decay, float step_size, float grad_scale, const float* dyn, void* stream);
 /* conv0 + GroupNorm + GELU backward (recomputes the convolution from the waveform); see csrc/conv0_bwd.cu for the workspace size. */
 int cst_conv0_bwd(const float* wave, int B, int L, const float* w, const float* gamma, const float* beta,
                   const float* scale_shift, const float* dout, int rows_per_seg, float* dw, float* dgamma, float* dbeta,
