@@ -112,6 +112,7 @@ __global__ void __launch_bounds__(256) attention_bwd_kernel(const void* __restri
       }
       l += __shfl_xor_sync(0xffffffffu, l, 1); l += __shfl_xor_sync(0xffffffffu, l, 2);
       dacc += __shfl_xor_sync(0xffffffffu, dacc, 1); dacc += __shfl_xor_sync(0xffffffffu, dacc, 2);
+      __syncwarp();                                              // the quad's reads of row_m[row] above are ordered before the update
       if (part == 0) {
         const float resc = expf(row_m[row] - mx);
         row_l[row] = row_l[row] * resc + l;
