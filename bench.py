@@ -512,6 +512,37 @@ def run_c5(args, rank, world, local_rank, cores):
     psum = float(step.sd["wav2vec_model.encoder.layers.0.fc1.weight"].double().sum())
     params_agree = abs(D.reduce_max(psum, "cuda") + D.reduce_max(-psum, "cuda")) <= 1e-9 * max(1.0, abs(psum))
     gs.optimizer = None
+    # the ST + MT + contrastive form of the step (criterions/triplet_st_mt_contrastive.py): a text pass of the SAME encoder (8 x 40
+    # tokens) inside the forward graph, InfoNCE between the audio and the text memories, both backward passes into one gradient set
+    joint = None
+    try:
+        from chimera_st_b200.train import TextTrainPass
+        sd_t = synth.make_state_dict(seed=0, interlingua_length=M, dead_heads=False, text_vocab=10000)
+        step_t = EncoderTrainStep(sd_t, B, Lw, device="cuda", feature_grad_mult=0.1, dtype=dtype)
+        tp = TextTrainPass(step_t, B, 40)
+        tok = torch.randint(4, 10000, (B, 40), generator=torch.Generator().manual_seed(11 + rank)).cuda()
+        tlen = torch.full((B,), 40, dtype=torch.int64).cuda()
+
+        def joint_loss(mem):
+            tmem = tp.forward(tok, tlen)
+            _, loss, da, dt_ = losses.contrastive_loss(mem.contiguous(), tmem.contiguous(), temp=0.1, grad_scale=1.0)
+            return loss, da, tp.backward(dt_)
+        gj = GraphedTrainStep(step_t, wave, lens, joint_loss)
+        gj.reducer = ddp.GradAllReducer(gj.names, world_size=world, bucket_bytes=args.bucket_mb << 20, comm_dtype=comm)
+        for _ in range(3):
+            gj.run()
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            gj.run()
+        e1.record()
+        barrier()
+        t_j = D.reduce_max(e0.elapsed_time(e1) * 1e-3, "cuda")
+        joint = {"ms_per_step": round(1e3 * t_j / args.steps, 3), "text_tokens_per_gpu": B * 40, "loss": float(gj.loss),
+                 "gradient_tensors": len(gj.names), "parameters": sum(n for _, n in gj.names)}
+        del gj, tp, step_t
+    except Exception as e:                                            # noqa: BLE001
+        joint = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
 
     # ---- instrumented eager pass: per-kernel CUDA-event timing for the roofline object
     prof = LaunchProfiler(step.o.lib)
@@ -572,7 +603,8 @@ def run_c5(args, rank, world, local_rank, cores):
                       "with_adam_update": {"ms_per_step": round(1e3 * t_opt / args.steps, 3),
                                            "audio_s_per_s": round(total_audio * args.steps / t_opt, 1),
                                            "loss_before": loss0, "loss_after_%d_updates" % (3 + args.steps): loss1,
-                                           "parameters_agree_across_ranks": bool(params_agree)}},
+                                           "parameters_agree_across_ranks": bool(params_agree)},
+                      "st_mt_contrastive_step": joint},
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(line))
     D.finalize()

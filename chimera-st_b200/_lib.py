@@ -120,6 +120,7 @@ _SIGS = {
     "cst_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_longlong] + [C.c_float] * 7 + [C.c_void_p, C.c_void_p]),
     "cst_conv0_bwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]),
+    "cst_embed_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p]),
     "cst_add_positions": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "cst_dec_embed": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_int,
                                 C.c_int, C.c_void_p, C.c_void_p]),

@@ -47,7 +47,29 @@ __global__ void __launch_bounds__(128) add_positions_kernel(float* __restrict__ 
   }
 }
 
+// dE[tok, :] += scale * dx[b, t, :] for every token of the batch except the padding index (nn.Embedding(padding_idx) keeps that row's
+// gradient at zero): the backward of the gather in text_embed_kernel.  fp32 atomics (a token may occur many times).
+__global__ void __launch_bounds__(128) embed_bwd_kernel(const long long* __restrict__ tokens, const float* __restrict__ dx, float scale,
+                                                        float* __restrict__ dE, int T, int rows_per_seg, int C, int V, int pad) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.x / T, t = blockIdx.x - b * T;
+  long long tok = tokens[(size_t)b * T + t];
+  tok = min((long long)V - 1, max(0ll, tok));
+  if (tok == pad) return;
+  const float* src = dx + ((size_t)b * rows_per_seg + t) * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(dE + (size_t)tok * C + c, scale * src[c]);
+}
+
 }  // namespace cst
+
+extern "C" int cst_embed_bwd(const int64_t* tokens, const float* dx, float scale, float* dE, int B, int T, int rows_per_seg, int C, int V,
+                             int pad_idx, void* stream) {
+  CST_REQUIRE(tokens && dx && dE && B > 0 && T > 0 && rows_per_seg >= T && C > 0 && V > 0, "cst_embed_bwd: bad args");
+  CST_CHECK_CUDA(cst::launch_k(cst::embed_bwd_kernel, dim3(B * T), dim3(128), 0, (cudaStream_t)stream, (const long long*)tokens, dx, scale, dE, T,
+                               rows_per_seg, C, V, pad_idx));
+  return CST_OK;
+}
 
 extern "C" int cst_add_positions(float* x, const int32_t* valid, const float* pos_table, int B, int T, int rows_per_seg, int C, void* stream) {
   CST_REQUIRE(x && valid && pos_table && B > 0 && T > 0 && rows_per_seg >= T && C > 0 && C % 4 == 0, "cst_add_positions: bad args");

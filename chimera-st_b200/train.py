@@ -304,10 +304,19 @@ class EncoderTrainStep:
         R2 = B * g.T2a
         x2 = o.act(L.ACT_GLU, zs1, R2, ENC_DIM, alpha=math.sqrt(ENC_DIM), out_dtype=F32)
         T.update(sub_in=sub_in, zs0=zs0, sub_mid=sub_mid, zs1=zs1)
+        return self._shared_memory_fwd(g, T, x2, sub_valid)
+
+    def _shared_memory_fwd(self, g, T, x2, sub_valid):
+        """6 pre-LN shared layers -> LayerNorm -> memory stage on the rows of `x2` [B*T2a, 512] fp32 (audio: sub-sampled frames; text:
+        embedded tokens): the part of the forward both branches of the encoder run (w2v2_transformer_interlingua.py:238-298)."""
+        o, P, lib = self.o, self.P, self.o.lib
+        B, st, op, esz = g.B, self.o.st(), self.op, self.o.esz
+        R2 = B * g.T2a
+        T["sub_valid"] = sub_valid
         # ---- 6 pre-LN shared layers
         D2 = ENC_DIM
         T["enc"] = []
-        for lw in P["enc_layers"]:
+        for lw in self._enc_layers(T):
             t = {"x_in": x2}
             _, a = o.ln(x2, lw["ln1_g"], lw["ln1_b"], R2, f32=False)
             qkv = o.linear(a, lw["qkv_w"], lw["qkv_b"], out_dtype=op)
@@ -357,10 +366,11 @@ class EncoderTrainStep:
         G[name + "fc1.weight"], G[name + "fc1.bias"] = dW1, db1
         return dxin
 
-    def backward(self, d_mem):
-        """d_mem: [M, B, 512] gradient of the loss w.r.t. the memories.  -> {reference parameter name: gradient}."""
+    def backward(self, d_mem, G0=None):
+        """d_mem: [M, B, 512] gradient of the loss w.r.t. the memories.  -> {reference parameter name: gradient}.
+        G0: gradients to start from (the text pass of the same step, TextTrainPass.backward): shared parameters are summed."""
         G = {}
-        for part in self.backward_iter(d_mem):
+        for part in self.backward_iter(d_mem, G0):
             G.update(part)
         return G
 
@@ -368,57 +378,15 @@ class EncoderTrainStep:
     SEGMENTS = ("memory stage + shared layers + subsampler", "wav2vec2 layers 11..6", "wav2vec2 layers 5..0 + pos-conv + projection",
                 "conv feature extractor")
 
-    def backward_iter(self, d_mem):
+    def backward_iter(self, d_mem, G0=None):
         """Generator form of `backward`: yields {name: gradient} of each finished SEGMENT in backward order, so that the caller can
         start the gradient all-reduce of a segment (NCCL, its own stream) while the kernels of the next one run -- the overlap
         `LegacyDistributedDataParallel` does not have (legacy_distributed_data_parallel.py:94-178 reduces after the whole backward)."""
         o, g, P, T = self.o, self.g, self.P, self.T
         B, Mq, D2, esz = g.B, self.M, ENC_DIM, self.o.esz
         RM, R2, R = B * Mq, B * g.T2a, B * g.T6a
-        G = {}
-        dmem = d_mem.to(self.dev, F32).transpose(0, 1).contiguous().view(RM, D2)
-        dh_enc = o.new(R2, D2, zero=True)
-        # ---- memory stage
-        for li in reversed(range(MEM_LAYERS)):
-            lw, t, nm = P["mem_layers"][li], T["mem"][li], f"interlingua_layers.{li}."
-            db_in = self._ffn_bwd(G, nm, lw, t, dmem, RM, L.ACT_RELU, "b")
-            dmm, dg2, dbt2 = o.ln_bwd(t["mm"], lw["ln2_g"], db_in, RM, dx=dmem.clone())     # residual path + LN2 path
-            G[nm + "final_layer_norm.weight"], G[nm + "final_layer_norm.bias"] = dg2, dbt2
-            dctx, dWo, dbo = o.linear_bwd(t["ctx"], lw["o_w"], dmm, RM)
-            G[nm + "self_attn.out_proj.weight"], G[nm + "self_attn.out_proj.bias"] = dWo, dbo
-            dq = o.new(RM, D2, zero=True)
-            dkv = o.new(R2, 2 * D2, zero=True)
-            kp, dkp = t["kv"].data_ptr(), dkv.data_ptr()
-            o.attention_bwd(t["q"].data_ptr(), kp, kp + esz * D2, t["ctx"], dctx, dq.data_ptr(), dkp, dkp + 4 * D2, D2, 2 * D2, D2, B, ENC_HEADS,
-                            Mq, Mq, g.T2, g.T2a, None)
-            da, dWq, dbq = o.linear_bwd(t["a"], lw["q_w"], dq, RM)
-            G[nm + "self_attn.q_proj.weight"], G[nm + "self_attn.q_proj.bias"] = dWq * 0.125, dbq * 0.125
-            dkv_in, dWkv, dbkv = o.linear_bwd(t["kv_in"], lw["kv_w"], dkv, R2)
-            G[nm + "self_attn.k_proj.weight"], G[nm + "self_attn.v_proj.weight"] = dWkv[:D2], dWkv[D2:]
-            G[nm + "self_attn.k_proj.bias"], G[nm + "self_attn.v_proj.bias"] = dbkv[:D2], dbkv[D2:]
-            dmem, dg1a, db1a = o.ln_bwd(t["m_in"], lw["ln1_g"], da, RM, dx=dmm)              # + residual
-            _, dg1b, db1b = o.ln_bwd(T["h_enc"], lw["ln1_g"], dkv_in, R2, dx=dh_enc)         # the SAME LN1 on the key/value side
-            G[nm + "self_attn_layer_norm.weight"], G[nm + "self_attn_layer_norm.bias"] = dg1a + dg1b, db1a + db1b
-        G["interlingua_embedding.weight"] = o.colsum(dmem.view(B, Mq * D2), B, Mq * D2).view(Mq, D2)
-        self.dbg = {"h_enc": dh_enc}
-        # ---- final LayerNorm + shared layers
-        dx2, dgo, dbo_ = o.ln_bwd(T["x2_out"], P["ln_out_g"], dh_enc, R2)
-        G["layer_norm.weight"], G["layer_norm.bias"] = dgo, dbo_
-        for li in reversed(range(ENC_LAYERS)):
-            lw, t, nm = P["enc_layers"][li], T["enc"][li], f"transformer_layers.{li}."
-            db_in = self._ffn_bwd(G, nm, lw, t, dx2, R2, L.ACT_RELU, "b")
-            dxm, dg2, dbt2 = o.ln_bwd(t["xm"], lw["ln2_g"], db_in, R2, dx=dx2)
-            G[nm + "final_layer_norm.weight"], G[nm + "final_layer_norm.bias"] = dg2, dbt2
-            dctx, dWo, dbo = o.linear_bwd(t["ctx"], lw["o_w"], dxm, R2)
-            G[nm + "self_attn.out_proj.weight"], G[nm + "self_attn.out_proj.bias"] = dWo, dbo
-            dqkv = o.new(R2, 3 * D2, zero=True)
-            qp, dqp = t["qkv"].data_ptr(), dqkv.data_ptr()
-            o.attention_bwd(qp, qp + esz * D2, qp + 2 * esz * D2, t["ctx"], dctx, dqp, dqp + 4 * D2, dqp + 8 * D2, 3 * D2, 3 * D2, D2, B,
-                            ENC_HEADS, g.T2a, g.T2a, g.T2, g.T2a, T["sub_valid"])
-            da, dWqkv, dbqkv = o.linear_bwd(t["a"], lw["qkv_w"], dqkv, R2)
-            _attn_layer_grads(G, nm + "self_attn.", dWqkv, dbqkv, D2)
-            dx2, dg1, db1 = o.ln_bwd(t["x_in"], lw["ln1_g"], da, R2, dx=dxm)
-            G[nm + "self_attn_layer_norm.weight"], G[nm + "self_attn_layer_norm.bias"] = dg1, db1
+        G = dict(G0) if G0 else {}
+        dx2 = self._shared_memory_bwd(g, T, G, d_mem)
         self.dbg["sub_out"] = dx2
         # ---- subsampler (GLU -> conv dgrad / wgrad on the zero-padded operands)
         D = W2V_DIM
@@ -495,6 +463,67 @@ class EncoderTrainStep:
         G[fe + "0.0.weight"], G[fe + "0.2.weight"], G[fe + "0.2.bias"] = dw0.view(512, 1, 10), dgn, dbn
         yield G
 
+    def _shared_memory_bwd(self, g, T, G, d_mem):
+        """Backward of `_shared_memory_fwd`: fills G with the gradients of the memory stage, the final LayerNorm and the shared layers
+        (ADDING to entries that already exist: the audio and the text pass of one training step share these parameters) and returns
+        d x2 [B*T2a, 512]."""
+        o, P = self.o, self.P
+        B, Mq, D2, esz = g.B, self.M, ENC_DIM, self.o.esz
+        RM, R2 = B * Mq, B * g.T2a
+        G0, G = G, {}
+        dmem = d_mem.to(self.dev, F32).transpose(0, 1).contiguous().view(RM, D2)
+        dh_enc = o.new(R2, D2, zero=True)
+        # ---- memory stage
+        for li in reversed(range(MEM_LAYERS)):
+            lw, t, nm = P["mem_layers"][li], T["mem"][li], f"interlingua_layers.{li}."
+            db_in = self._ffn_bwd(G, nm, lw, t, dmem, RM, L.ACT_RELU, "b")
+            dmm, dg2, dbt2 = o.ln_bwd(t["mm"], lw["ln2_g"], db_in, RM, dx=dmem.clone())     # residual path + LN2 path
+            G[nm + "final_layer_norm.weight"], G[nm + "final_layer_norm.bias"] = dg2, dbt2
+            dctx, dWo, dbo = o.linear_bwd(t["ctx"], lw["o_w"], dmm, RM)
+            G[nm + "self_attn.out_proj.weight"], G[nm + "self_attn.out_proj.bias"] = dWo, dbo
+            dq = o.new(RM, D2, zero=True)
+            dkv = o.new(R2, 2 * D2, zero=True)
+            kp, dkp = t["kv"].data_ptr(), dkv.data_ptr()
+            o.attention_bwd(t["q"].data_ptr(), kp, kp + esz * D2, t["ctx"], dctx, dq.data_ptr(), dkp, dkp + 4 * D2, D2, 2 * D2, D2, B, ENC_HEADS,
+                            Mq, Mq, g.T2, g.T2a, None)
+            da, dWq, dbq = o.linear_bwd(t["a"], lw["q_w"], dq, RM)
+            G[nm + "self_attn.q_proj.weight"], G[nm + "self_attn.q_proj.bias"] = dWq * 0.125, dbq * 0.125
+            dkv_in, dWkv, dbkv = o.linear_bwd(t["kv_in"], lw["kv_w"], dkv, R2)
+            G[nm + "self_attn.k_proj.weight"], G[nm + "self_attn.v_proj.weight"] = dWkv[:D2], dWkv[D2:]
+            G[nm + "self_attn.k_proj.bias"], G[nm + "self_attn.v_proj.bias"] = dbkv[:D2], dbkv[D2:]
+            dmem, dg1a, db1a = o.ln_bwd(t["m_in"], lw["ln1_g"], da, RM, dx=dmm)              # + residual
+            _, dg1b, db1b = o.ln_bwd(T["h_enc"], lw["ln1_g"], dkv_in, R2, dx=dh_enc)         # the SAME LN1 on the key/value side
+            G[nm + "self_attn_layer_norm.weight"], G[nm + "self_attn_layer_norm.bias"] = dg1a + dg1b, db1a + db1b
+        G["interlingua_embedding.weight"] = o.colsum(dmem.view(B, Mq * D2), B, Mq * D2).view(Mq, D2)
+        self.dbg = {"h_enc": dh_enc}
+        # ---- final LayerNorm + shared layers
+        dx2, dgo, dbo_ = o.ln_bwd(T["x2_out"], P["ln_out_g"], dh_enc, R2)
+        G["layer_norm.weight"], G["layer_norm.bias"] = dgo, dbo_
+        for li in reversed(range(ENC_LAYERS)):
+            lw, t, nm = self._enc_layers(T)[li], T["enc"][li], self._enc_names(T)[li]
+            db_in = self._ffn_bwd(G, nm, lw, t, dx2, R2, L.ACT_RELU, "b")
+            dxm, dg2, dbt2 = o.ln_bwd(t["xm"], lw["ln2_g"], db_in, R2, dx=dx2)
+            G[nm + "final_layer_norm.weight"], G[nm + "final_layer_norm.bias"] = dg2, dbt2
+            dctx, dWo, dbo = o.linear_bwd(t["ctx"], lw["o_w"], dxm, R2)
+            G[nm + "self_attn.out_proj.weight"], G[nm + "self_attn.out_proj.bias"] = dWo, dbo
+            dqkv = o.new(R2, 3 * D2, zero=True)
+            qp, dqp = t["qkv"].data_ptr(), dqkv.data_ptr()
+            o.attention_bwd(qp, qp + esz * D2, qp + 2 * esz * D2, t["ctx"], dctx, dqp, dqp + 4 * D2, dqp + 8 * D2, 3 * D2, 3 * D2, D2, B,
+                            ENC_HEADS, g.T2a, g.T2a, g.T2, g.T2a, T["sub_valid"])
+            da, dWqkv, dbqkv = o.linear_bwd(t["a"], lw["qkv_w"], dqkv, R2)
+            _attn_layer_grads(G, nm + "self_attn.", dWqkv, dbqkv, D2)
+            dx2, dg1, db1 = o.ln_bwd(t["x_in"], lw["ln1_g"], da, R2, dx=dxm)
+            G[nm + "self_attn_layer_norm.weight"], G[nm + "self_attn_layer_norm.bias"] = dg1, db1
+        for k, v in G.items():
+            G0[k] = v if k not in G0 else G0[k] + v
+        return dx2
+
+    def _enc_layers(self, T):
+        return self.P["enc_layers"]
+
+    def _enc_names(self, T):
+        return [f"transformer_layers.{i}." for i in range(ENC_LAYERS)]
+
     def _conv_bwd(self, x_src, w, dz, rows, lda, a_rows, bias=True):
         """Implicit-GEMM convolution z[m] = window_m(x_src) . w: -> (dcol [rows, K] = dz w (operand dtype), dW [N, K] = dz^T windows, db)."""
         o = self.o
@@ -569,6 +598,48 @@ class EncoderTrainStep:
         copy_tree(self.P, new)
 
 
+class TextTrainPass:
+    """The text (MT) pass of the training step: integer tokens -> sqrt(512) * embedding + sinusoidal positions -> the SAME shared layers
+    and memory stage as the audio pass (w2v2_transformer_interlingua.py:212-217,230-298), with the tape kept for its backward.  It shares
+    the kernels, operands and master parameters of an `EncoderTrainStep`; `backward(d_mem, G)` ADDS its gradients of the shared
+    parameters to the audio pass's in `G` and adds `text_embed_tokens.weight` -- what the reference's ST + MT + contrastive criterion
+    (criterions/triplet_st_mt_contrastive.py) obtains from autograd over both passes."""
+
+    def __init__(self, step, B, T):
+        from .plan import TextGeometry, sinusoidal_table
+        if "text_embed" not in step.P:
+            raise L.CstError("the checkpoint has no text_embed_tokens.weight: the text pass is unavailable")
+        self.s = step
+        self.g = TextGeometry(B, T, step.M)
+        self.pos = sinusoidal_table(T + 2).to(step.dev)
+        self.T = None
+
+    def forward(self, tokens, lengths):
+        s, g, o = self.s, self.g, self.s.o
+        B, Tn = g.B, g.L
+        tokens = tokens.to(s.dev, torch.int64).contiguous()
+        lengths = lengths.to(s.dev, torch.int64).contiguous()
+        E = s.P["text_embed"]
+        x2 = o.new(B * Tn, ENC_DIM)
+        valid = torch.empty(B, dtype=torch.int32, device=s.dev)
+        L.check(o.lib.cst_text_embed(tokens.data_ptr(), lengths.data_ptr(), E.data_ptr(), self.pos.data_ptr(), math.sqrt(ENC_DIM), x2.data_ptr(),
+                                     valid.data_ptr(), B, Tn, Tn, ENC_DIM, E.shape[0], o.st()))
+        self.T = {"tokens": tokens}
+        return s._shared_memory_fwd(g, self.T, x2, valid)
+
+    def backward(self, d_mem, G=None):
+        s, g, o = self.s, self.g, self.s.o
+        G = {} if G is None else G
+        dx2 = s._shared_memory_bwd(g, self.T, G, d_mem)
+        E = s.P["text_embed"]
+        dE = o.new(E.shape[0], ENC_DIM, zero=True)
+        L.check(o.lib.cst_embed_bwd(self.T["tokens"].data_ptr(), dx2.data_ptr(), math.sqrt(ENC_DIM), dE.data_ptr(), g.B, g.L, g.L, ENC_DIM,
+                                    E.shape[0], 1, o.st()))
+        k = "text_embed_tokens.weight"
+        G[k] = dE if k not in G else G[k] + dE
+        return G
+
+
 class FusedAdam:
     """Adam over the encoder's fp32 master parameters, one fused kernel per tensor (`cst_adam_step`), the arithmetic of
     fairseq/optim/adam.py:157-224 (decoupled weight decay `p -= wd * lr * p`, eps added to sqrt(v), bias corrections in the step size).
@@ -614,8 +685,8 @@ class GraphedTrainStep:
     """One training step of the path as CUDA graphs: forward + loss in one graph, the backward pass in one graph per segment of
     `EncoderTrainStep.backward_iter`; between the segment replays the finished gradients are handed to the bucketed all-reduce
     (`ddp.GradAllReducer`), whose NCCL kernels run on the communicator's stream underneath the next segment.  Inputs are static
-    device buffers (`wave`, `lens`); `loss_fn(memories [M, B, 512]) -> (loss scalar tensor, d_memories)` is captured with the
-    forward pass.  Every activation / gradient lives in the graphs' shared memory pool, so replays allocate nothing."""
+    device buffers (`wave`, `lens`); `loss_fn(memories [M, B, 512]) -> (loss scalar tensor, d_memories[, G0])` is captured with the
+    forward pass (G0: gradients of a text pass run inside loss_fn, merged into the first backward segment).  Every activation / gradient lives in the graphs' shared memory pool, so replays allocate nothing."""
 
     def __init__(self, step, wave, lens, loss_fn, reducer=None, warmup=2, optimizer=None):
         self.step, self.wave, self.lens, self.reducer = step, wave, lens, reducer
@@ -624,17 +695,18 @@ class GraphedTrainStep:
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):                              # eager warm-up (one-time attribute / descriptor setup)
             for _ in range(warmup):
-                loss, dmem = loss_fn(step.forward(wave, lens))
-                step.backward(dmem)
+                res = loss_fn(step.forward(wave, lens))
+                step.backward(res[1], res[2] if len(res) > 2 else None)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         pool = self.pool = torch.cuda.graph_pool_handle()
         self.graphs, self.seg_grads = [], []
         g0 = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g0, pool=pool):
-            self.loss, dmem = loss_fn(step.forward(wave, lens))
+            res = loss_fn(step.forward(wave, lens))
+        self.loss, dmem = res[0], res[1]
         self.graphs.append(g0)
-        it = step.backward_iter(dmem)
+        it = step.backward_iter(dmem, res[2] if len(res) > 2 else None)
         while True:
             gi = torch.cuda.CUDAGraph()
             done = False

@@ -203,6 +203,10 @@ int cst_attention_segs(const void* q, const void* k, const void* v, void* out, i
  * x f32 [B*rows_per_seg, C] (rows t >= T of a segment are zero-filled); valid int32 [B] = lengths (may be NULL). */
 int cst_text_embed(const int64_t* tokens, const int64_t* lengths, const float* embed, const float* pos_table,
                    float scale, float* x, int32_t* valid, int B, int T, int rows_per_seg, int C, int V, void* stream);
+/* Backward of cst_text_embed's gather (training step, text pass): dE[tokens[b,t], :] += scale * dx[b, t, :] for tokens != pad_idx
+ * (nn.Embedding(padding_idx): that row gets no gradient); dE f32 [V, C] is accumulated with fp32 atomics (zero it first). */
+int cst_embed_bwd(const int64_t* tokens, const float* dx, float scale, float* dE, int B, int T, int rows_per_seg, int C, int V,
+                  int pad_idx, void* stream);
 /* Sinusoidal positions of the NON-memory base encoder (S2T_W2V2_TransformerEncoder.forward, fairseq/models/chimera/
  * w2v2_transformer.py:353-357): x[b, t, :] += pos_table[t + 2] for t < valid[b] (padded frames get the zero padding row); same table
  * as cst_text_embed, T + 2 rows.  x f32 [B*rows_per_seg, C]. */

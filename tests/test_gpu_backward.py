@@ -270,3 +270,62 @@ def test_attention_backward_tensor_core_path(B, H, Tq, Tk, masked):
     assert rel_l2(dq.cpu().view(B, Tq, Cd), q.grad.float()) < 8e-3
     assert rel_l2(dk.cpu().view(B, Tk, Cd), k.grad.float()) < 8e-3
     assert rel_l2(dv.cpu().view(B, Tk, Cd), v.grad.float()) < 8e-3
+
+
+def test_text_pass_backward_and_gradient_accumulation_over_both_passes():
+    """TextTrainPass (tokens -> shared layers -> memory stage): every gradient <= 1e-4 against autograd through the oracle's text
+    branch (ReLU sign pattern pinned as above; the padding row of the embedding gets no gradient, nn.Embedding(padding_idx)); then
+    one audio pass + one text pass into the same G: shared parameters hold the SUM of both passes' gradients."""
+    from chimera_st_b200.train import TextTrainPass
+    torch.set_num_threads(8)
+    V = 60
+    sd = synth.make_state_dict(seed=0, interlingua_length=16, dead_heads=False, text_vocab=V)
+    g = torch.Generator().manual_seed(5)
+    tok = torch.randint(4, V, (3, 9), generator=g)
+    tl = torch.tensor([9, 6, 4])
+    for b in range(3):
+        tok[b, int(tl[b]):] = 1
+    R = torch.randn(16, 3, 512, generator=g)
+    step = EncoderTrainStep(sd, 2, 6000, device=DEV, feature_grad_mult=1.0)
+    tp = TextTrainPass(step, 3, 9)
+    mem = tp.forward(tok, tl)
+    Gt = tp.backward(R.to(DEV))
+    torch.cuda.synchronize()
+    T = tp.T
+    masks = [t["z"].view(3, 9, -1).cpu() > 0 for t in T["enc"]] + [t["z"].view(3, 16, -1).cpu() > 0 for t in T["mem"]]
+    sdg = {k: (v.clone().requires_grad_() if v.is_floating_point() else v) for k, v in sd.items()}
+    calls, orig = [], torch.relu
+
+    def pinned(z):
+        calls.append(1)
+        return z * masks[len(calls) - 1].to(z.dtype)
+    torch.relu = pinned
+    try:
+        ref_mem, _ = O.encoder_forward_text(sdg, tok, tl)
+    finally:
+        torch.relu = orig
+    (ref_mem * R).sum().backward()
+    assert rel_l2(mem.cpu(), ref_mem.detach()) < 1e-5
+    ref = {k: v.grad for k, v in sdg.items() if v.is_floating_point() and v.grad is not None}
+    ref["text_embed_tokens.weight"][1] = 0                                   # padding_idx row
+    bad = {}
+    for k, v in Gt.items():
+        if k.endswith("k_proj.bias"):
+            continue
+        e = rel_l2(v.cpu().reshape(ref[k].shape), ref[k])
+        if not e < 1e-4:
+            bad[k] = e
+    assert not bad, bad
+    assert "text_embed_tokens.weight" in Gt and not any(k.startswith("wav2vec_model.") for k in Gt)
+    # both passes into one G
+    wave, wl = synth.make_waveforms([6000, 4500], seed=31)
+    Ra = torch.randn(16, 2, 512, generator=g)
+    step.forward(wave, wl)
+    Ga = step.backward(Ra.to(DEV))
+    both = {k: v.clone() for k, v in Ga.items()}
+    tp.forward(tok, tl)
+    tp.backward(R.to(DEV), both)
+    k = "transformer_layers.2.fc1.weight"
+    assert rel_l2(both[k].cpu(), (Ga[k] + Gt[k]).cpu()) < 1e-5
+    k = "wav2vec_model.encoder.layers.3.fc2.weight"
+    assert torch.equal(both[k], Ga[k])
