@@ -64,7 +64,9 @@ __device__ int tc_dbg_flags;      // timing experiments: 1 skip global stores, 2
 // LNF (fp32 output with residual): LayerNorm fused around the GEMM (cst_gemm_params: res_stats / C2 / out_stats) -- the
 // residual rows are normalised on the fly from their partial statistics, a bf16 copy of the output is stored next to the
 // fp32 one, and this warp's partial statistics of the output rows (its 128-column slice) are written for the consumers.
-template <int BN, int ACT, int CD, bool RES, bool BST, bool LNF, bool VAR, typename WaitF>
+// LNS: the fused-LayerNorm epilogue also emits output statistics / the bf16 copy (full fusion); false = only the lazily normalised
+// residual of the default "light LayerNorm" mode, which then needs neither the 16 statistics registers nor their arithmetic.
+template <int BN, int ACT, int CD, bool RES, bool BST, bool LNF, bool VAR, bool LNS, typename WaitF>
 __device__ __forceinline__ void epi_tile_fast(const GemmDev& p, float* patch, uint32_t t_row, int nb, int lane, int chalf,
                                               const float* bias, uint8_t* c_base, const float* r_base, const int (&orow)[8],
                                               uint32_t st_mask, WaitF wait_acc, const CUtensorMap* tmC = nullptr, int row0 = 0) {
@@ -115,7 +117,7 @@ __device__ __forceinline__ void epi_tile_fast(const GemmDev& p, float* patch, ui
   // fused LayerNorm state: per-row {rstd, -mean*rstd} of the lazily normalised residual, gamma / beta of the current and
   // next chunk, running partial statistics of the output rows
   const bool lazy_res = LNF && p.res_stats != nullptr;
-  float ra[LNF ? 8 : 1], rb[LNF ? 8 : 1], s1[LNF ? 8 : 1], s2[LNF ? 8 : 1];
+  float ra[LNF ? 8 : 1], rb[LNF ? 8 : 1], s1[LNS ? 8 : 1], s2[LNS ? 8 : 1];
   float4 g_cur = make_float4(1.f, 1.f, 1.f, 1.f), t_cur = make_float4(0.f, 0.f, 0.f, 0.f), g_nxt = g_cur, t_nxt = t_cur;
   auto load_gamma = [&](int ch) {
     return (lazy_res && col_ok_of(ch)) ? __ldg(reinterpret_cast<const float4*>(p.res_gamma + col_of(ch))) : make_float4(1.f, 1.f, 1.f, 1.f);
@@ -126,7 +128,8 @@ __device__ __forceinline__ void epi_tile_fast(const GemmDev& p, float* patch, ui
   if (LNF) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      ra[i] = 1.f; rb[i] = 0.f; s1[i] = 0.f; s2[i] = 0.f;
+      ra[i] = 1.f; rb[i] = 0.f;
+      if (LNS) { s1[i] = 0.f; s2[i] = 0.f; }
       if (lazy_res && ((st_mask >> i) & 1)) {
         const float2 ab = ln_ab_from_partials(p.res_stats, orow[i], p.res_slots, p.ln_inv_dim);
         ra[i] = ab.x; rb[i] = ab.y;
@@ -204,7 +207,7 @@ __device__ __forceinline__ void epi_tile_fast(const GemmDev& p, float* patch, ui
           }
           if (has_next) load_res(ch + 1, i0, r_cur);           // these four registers are free again: refill for chunk c+1
         }
-        if (LNF) {
+        if (LNS) {
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const int i = i0 + u;
@@ -245,7 +248,7 @@ __device__ __forceinline__ void epi_tile_fast(const GemmDev& p, float* patch, ui
     b_cur = b_nxt;
     if (LNF) { g_cur = g_nxt; t_cur = t_nxt; }
   }
-  if (LNF) {
+  if (LNS) {
     if (p.out_stats != nullptr) {                              // the 8 lanes of a row group hold 4 columns each of the row's chunks
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -425,22 +428,27 @@ __device__ __forceinline__ void epi_tile(const GemmDev& p, const CUtensorMap* tm
         if constexpr (BN % 64 == 0) {
           if (lnf) {
             if constexpr (VAR && ACT == CST_ACT_NONE) {        // out-proj / fc2: the only users of the fused LayerNorm epilogue
-              if (bulk == 2) epi_tile_fast<BN, ACT, 0, true, true, true, true>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc, tmC, row_base);
-              else epi_tile_fast<BN, ACT, 0, true, false, true, true>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc);
+              if (p.C2 != nullptr || p.out_stats != nullptr) {
+                if (bulk == 2) epi_tile_fast<BN, ACT, 0, true, true, true, true, true>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc, tmC, row_base);
+                else epi_tile_fast<BN, ACT, 0, true, false, true, true, true>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc);
+              } else {
+                if (bulk == 2) epi_tile_fast<BN, ACT, 0, true, true, true, true, false>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc, tmC, row_base);
+                else epi_tile_fast<BN, ACT, 0, true, false, true, true, false>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc);
+              }
             }
           }
-          else if (bulk == 2) epi_tile_fast<BN, ACT, 0, true, true, false, VAR>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc, tmC, row_base);
-          else epi_tile_fast<BN, ACT, 0, true, false, false, VAR>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc);
+          else if (bulk == 2) epi_tile_fast<BN, ACT, 0, true, true, false, VAR, false>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc, tmC, row_base);
+          else epi_tile_fast<BN, ACT, 0, true, false, false, VAR, false>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc);
         } else {
-          epi_tile_fast<BN, ACT, 0, true, false, false, VAR>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc);
+          epi_tile_fast<BN, ACT, 0, true, false, false, VAR, false>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc);
         }
       }
-      else if (!c_f16) epi_tile_fast<BN, ACT, 1, true, false, false, VAR>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc);
-      else epi_tile_fast<BN, ACT, 2, true, false, false, VAR>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc);
+      else if (!c_f16) epi_tile_fast<BN, ACT, 1, true, false, false, VAR, false>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc);
+      else epi_tile_fast<BN, ACT, 2, true, false, false, VAR, false>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc);
     } else {
-      if (!c_16) epi_tile_fast<BN, ACT, 0, false, false, false, VAR>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc);
-      else if (!c_f16) epi_tile_fast<BN, ACT, 1, false, false, false, VAR>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc);
-      else epi_tile_fast<BN, ACT, 2, false, false, false, VAR>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc);
+      if (!c_16) epi_tile_fast<BN, ACT, 0, false, false, false, VAR, false>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc);
+      else if (!c_f16) epi_tile_fast<BN, ACT, 1, false, false, false, VAR, false>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc);
+      else epi_tile_fast<BN, ACT, 2, false, false, false, VAR, false>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc);
     }
   } else {
   wait_acc();
