@@ -66,7 +66,7 @@ __device__ int tc_dbg_flags;      // timing experiments: 1 skip global stores, 2
 // fp32 one, and this warp's partial statistics of the output rows (its 128-column slice) are written for the consumers.
 // LNS: the fused-LayerNorm epilogue also emits output statistics / the bf16 copy (full fusion); false = only the lazily normalised
 // residual of the default "light LayerNorm" mode, which then needs neither the 16 statistics registers nor their arithmetic.
-template <int BN, int ACT, int CD, bool RES, bool BST, bool LNF, bool VAR, bool LNS, typename WaitF>
+template <int BN, int ACT, int CD, bool RES, bool BST, bool LNF, int VAR, bool LNS, typename WaitF>
 __device__ __forceinline__ void epi_tile_fast(const GemmDev& p, float* patch, uint32_t t_row, int nb, int lane, int chalf,
                                               const float* bias, uint8_t* c_base, const float* r_base, const int (&orow)[8],
                                               uint32_t st_mask, WaitF wait_acc, const CUtensorMap* tmC = nullptr, int row0 = 0) {
@@ -164,7 +164,7 @@ __device__ __forceinline__ void epi_tile_fast(const GemmDev& p, float* patch, ui
     }
     if (col_ok && !TC_DBG(2)) {
       const uint64_t b01 = pk2(b_cur.x, b_cur.y), b23 = pk2(b_cur.z, b_cur.w);
-      const uint64_t sc2 = VAR ? pk2(p.acc_scale, p.acc_scale) : 0ull;
+      const uint64_t sc2 = VAR == 2 ? pk2(p.acc_scale, p.acc_scale) : 0ull;
 #pragma unroll
       for (int i0 = 0; i0 < 8; i0 += 4) {
         float v[4][4];
@@ -172,7 +172,7 @@ __device__ __forceinline__ void epi_tile_fast(const GemmDev& p, float* patch, ui
         for (int u = 0; u < 4; ++u) {
           const int rr = (i0 + u) * 4 + lr;
           const float4 a4 = *reinterpret_cast<const float4*>(&patch[rr * TC_PATCH_LD + 4 * ((lc >> 2) ^ (rr & 7))]);
-          if constexpr (VAR) {
+          if constexpr (VAR == 2) {
             upk2(ffma2(pk2(a4.x, a4.y), sc2, b01), v[u][0], v[u][1]);
             upk2(ffma2(pk2(a4.z, a4.w), sc2, b23), v[u][2], v[u][3]);
           } else {
@@ -183,7 +183,7 @@ __device__ __forceinline__ void epi_tile_fast(const GemmDev& p, float* patch, ui
         if (ACT == CST_ACT_GELU) {
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            if (VAR && p.exact_act) { v[u][0] = gelu_erf(v[u][0]); v[u][1] = gelu_erf(v[u][1]); v[u][2] = gelu_erf(v[u][2]); v[u][3] = gelu_erf(v[u][3]); }
+            if (VAR == 2 && p.exact_act) { v[u][0] = gelu_erf(v[u][0]); v[u][1] = gelu_erf(v[u][1]); v[u][2] = gelu_erf(v[u][2]); v[u][3] = gelu_erf(v[u][3]); }
             else { gelu2(v[u][0], v[u][1]); gelu2(v[u][2], v[u][3]); }
           }
         } else if (ACT == CST_ACT_RELU) {
@@ -274,7 +274,7 @@ __device__ __forceinline__ void epi_tile_fast(const GemmDev& p, float* patch, ui
 // accumulator stage is released as soon as its last chunk is in registers.
 // LNI: the A operand was the bf16 copy of UN-normalised rows; their LayerNorm is applied after the product (lane = row, so
 // mean / rstd are per-lane scalars): v = rstd*acc + (-mean*rstd)*colsum[n] + bias[n]  (cst_gemm_params: ln_in_stats).
-template <int BN, int ACT, int CD, bool LNI, bool VAR, typename WaitF, typename ReleaseF>
+template <int BN, int ACT, int CD, bool LNI, int VAR, typename WaitF, typename ReleaseF>
 __device__ __forceinline__ void epi_tile_bulk(const GemmDev& p, const CUtensorMap* tmC, uint32_t stage_s, uint32_t& seq, uint32_t t_row,
                                               int row0, int nb, int lane, int chalf, const float* bias, WaitF wait_acc, ReleaseF release_acc) {
   static_assert(BN % 64 == 0, "bulk epilogue: whole 32-column chunks per warp half");
@@ -306,11 +306,11 @@ __device__ __forceinline__ void epi_tile_bulk(const GemmDev& p, const CUtensorMa
         upk2(ffma2(pk2(v[4 * i + 2], v[4 * i + 3]), ln_a2, ffma2(ln_b2, pk2(cs.z, cs.w), pk2(bv.z, bv.w))), v[4 * i + 2], v[4 * i + 3]);
       }
     } else if (bias) {                                         // same address in every lane: one broadcast transaction each
-      const uint64_t sc2 = VAR ? pk2(p.acc_scale, p.acc_scale) : 0ull;
+      const uint64_t sc2 = VAR == 2 ? pk2(p.acc_scale, p.acc_scale) : 0ull;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + n0) + i);
-        if constexpr (VAR) {
+        if constexpr (VAR == 2) {
           upk2(ffma2(pk2(v[4 * i], v[4 * i + 1]), sc2, pk2(bv.x, bv.y)), v[4 * i], v[4 * i + 1]);
           upk2(ffma2(pk2(v[4 * i + 2], v[4 * i + 3]), sc2, pk2(bv.z, bv.w)), v[4 * i + 2], v[4 * i + 3]);
         } else {
@@ -318,7 +318,7 @@ __device__ __forceinline__ void epi_tile_bulk(const GemmDev& p, const CUtensorMa
           upk2(fadd2(pk2(v[4 * i + 2], v[4 * i + 3]), pk2(bv.z, bv.w)), v[4 * i + 2], v[4 * i + 3]);
         }
       }
-    } else if (VAR && p.acc_scale != 1.0f) {
+    } else if (VAR == 2 && p.acc_scale != 1.0f) {
       const uint64_t sc2 = pk2(p.acc_scale, p.acc_scale);
 #pragma unroll
       for (int i = 0; i < 32; i += 2) upk2(fmul2(pk2(v[i], v[i + 1]), sc2), v[i], v[i + 1]);
@@ -326,7 +326,7 @@ __device__ __forceinline__ void epi_tile_bulk(const GemmDev& p, const CUtensorMa
     if (ACT == CST_ACT_GELU) {
 #pragma unroll
       for (int i = 0; i < 32; i += 2) {
-        if (VAR && p.exact_act) { v[i] = gelu_erf(v[i]); v[i + 1] = gelu_erf(v[i + 1]); }      // fp32 parity mode (split GEMMs)
+        if (VAR == 2 && p.exact_act) { v[i] = gelu_erf(v[i]); v[i + 1] = gelu_erf(v[i + 1]); }      // fp32 parity mode (split GEMMs)
         else gelu2(v[i], v[i + 1]);
       }
     } else if (ACT == CST_ACT_RELU) {
@@ -368,13 +368,13 @@ __device__ __forceinline__ void epi_tile_bulk(const GemmDev& p, const CUtensorMa
 // VAR: the rarely used epilogue variants (LayerNorm fused around the GEMM, exact activations and the accumulator scale of the split
 // fp32 mode) live in their own kernel instantiations -- compiled into the default kernels they cost registers (272 bytes of spills
 // in the BN = 256 / 128 no-activation kernels) and ~15 % of the c3 GEMM time (measured: 113 -> 133 ms per step).
-template <int BN, int ACT, bool VAR, typename WaitF, typename ReleaseF>
+template <int BN, int ACT, int VAR, typename WaitF, typename ReleaseF>
 __device__ __forceinline__ void epi_tile(const GemmDev& p, const CUtensorMap* tmC, int bulk, uint32_t& seq, float* patch, uint32_t t_row,
                                          int row_base, int nb, int zo, int zi, int lane, int chalf, WaitF wait_acc, ReleaseF release_acc) {
   if constexpr (BN % 64 == 0 && ACT != CST_ACT_GLU) {
     if (bulk == 1) {
       const uint32_t stage_s = smem_u32(patch);
-      if constexpr (VAR) {
+      if constexpr (VAR == 2) {
         if (p.ln_in_stats != nullptr) {                          // LayerNorm of the input applied after the product (bf16 outputs)
           if constexpr (ACT == CST_ACT_NONE || ACT == CST_ACT_GELU || ACT == CST_ACT_RELU)
             epi_tile_bulk<BN, ACT, 1, true, true>(p, tmC, stage_s, seq, t_row, row_base, nb, lane, chalf, p.bias, wait_acc, release_acc);
@@ -422,19 +422,17 @@ __device__ __forceinline__ void epi_tile(const GemmDev& p, const CUtensorMap* tm
   if (fast) {
     uint8_t* c_base = reinterpret_cast<uint8_t*>(p.C) + c_off * esz;
     const float* r_base = p.residual + r_off;
-    const bool lnf = VAR && (p.res_stats != nullptr || p.C2 != nullptr || p.out_stats != nullptr);
+    const bool lnf = VAR != 0 && (p.res_stats != nullptr || p.C2 != nullptr || p.out_stats != nullptr);
     if (p.residual) {
       if (!c_16) {
         if constexpr (BN % 64 == 0) {
           if (lnf) {
-            if constexpr (VAR && ACT == CST_ACT_NONE) {        // out-proj / fc2: the only users of the fused LayerNorm epilogue
-              if (p.C2 != nullptr || p.out_stats != nullptr) {
-                if (bulk == 2) epi_tile_fast<BN, ACT, 0, true, true, true, true, true>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc, tmC, row_base);
-                else epi_tile_fast<BN, ACT, 0, true, false, true, true, true>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc);
-              } else {
-                if (bulk == 2) epi_tile_fast<BN, ACT, 0, true, true, true, true, false>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc, tmC, row_base);
-                else epi_tile_fast<BN, ACT, 0, true, false, true, true, false>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc);
-              }
+            if constexpr (VAR == 2 && ACT == CST_ACT_NONE) {   // out-proj / fc2 of the full fusion: statistics + bf16 copy as well
+              if (bulk == 2) epi_tile_fast<BN, ACT, 0, true, true, true, 2, true>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc, tmC, row_base);
+              else epi_tile_fast<BN, ACT, 0, true, false, true, 2, true>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc);
+            } else if constexpr (VAR == 1 && ACT == CST_ACT_NONE) {   // light LayerNorm mode: lazily normalised residual only
+              if (bulk == 2) epi_tile_fast<BN, ACT, 0, true, true, true, 1, false>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc, tmC, row_base);
+              else epi_tile_fast<BN, ACT, 0, true, false, true, 1, false>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc);
             }
           }
           else if (bulk == 2) epi_tile_fast<BN, ACT, 0, true, true, false, VAR, false>(p, patch, t_row, nb, lane, chalf, bias, c_base, r_base, orow, st_mask, wait_acc, tmC, row_base);
@@ -488,7 +486,7 @@ __device__ __forceinline__ void epi_tile(const GemmDev& p, const CUtensorMap* tm
     __syncwarp();
     if (col_ok) {
       const uint64_t b01 = pk2(b4.x, b4.y), b23 = pk2(b4.z, b4.w);
-      const uint64_t sc2 = VAR ? pk2(p.acc_scale, p.acc_scale) : pk2(1.0f, 1.0f);
+      const uint64_t sc2 = VAR == 2 ? pk2(p.acc_scale, p.acc_scale) : pk2(1.0f, 1.0f);
       // 4 rows per batch: the 16 element chains (bias, activation, alpha, residual) are independent, so the
       // two epilogue warps of an SM sub-partition keep the FMA/MUFU pipes busy instead of waiting on one chain
 #pragma unroll
@@ -504,7 +502,7 @@ __device__ __forceinline__ void epi_tile(const GemmDev& p, const CUtensorMap* tm
         if (ACT == CST_ACT_GLU) {
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            if (VAR && p.exact_act) {
+            if (VAR == 2 && p.exact_act) {
               v[u][0] = v[u][0] * sigmoidf_(v[u][1]) * p.alpha;
               v[u][1] = v[u][2] * sigmoidf_(v[u][3]) * p.alpha;
             } else {
@@ -517,7 +515,7 @@ __device__ __forceinline__ void epi_tile(const GemmDev& p, const CUtensorMap* tm
           if (ACT == CST_ACT_GELU) {
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-              if (VAR && p.exact_act) { v[u][0] = gelu_erf(v[u][0]); v[u][1] = gelu_erf(v[u][1]); v[u][2] = gelu_erf(v[u][2]); v[u][3] = gelu_erf(v[u][3]); }
+              if (VAR == 2 && p.exact_act) { v[u][0] = gelu_erf(v[u][0]); v[u][1] = gelu_erf(v[u][1]); v[u][2] = gelu_erf(v[u][2]); v[u][3] = gelu_erf(v[u][3]); }
               else { gelu2(v[u][0], v[u][1]); gelu2(v[u][2], v[u][3]); }
             }
           } else if (ACT == CST_ACT_RELU) {
@@ -560,7 +558,7 @@ __device__ __forceinline__ void epi_tile(const GemmDev& p, const CUtensorMap* tm
   TC_EPI_ADD(0, pt0, pt1); TC_EPI_ADD(1, pt1, pt2); TC_EPI_ADD(2, pt2, pt3); TC_EPI_ADD(3, 0, 1);
 }
 
-template <int BN, int ACT, bool VAR>
+template <int BN, int ACT, int VAR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
                const GemmDev p, int m_tiles, int n_tiles, int total_tiles, int a_wrap, int ab_f16, int bulk) {
@@ -718,11 +716,14 @@ static int make_c_map(CUtensorMap* tmC, const cst_gemm_params& hp, int bulk) {
   return make_map_2d(tmC, hp.C, hp.N, hp.M, hp.ldc, 32, 32, esz, esz == 4 ? 128 : 64);
 }
 
-static inline bool needs_variant_kernel(const cst_gemm_params& hp, const GemmDev& p) {
-  return hp.ln_in_stats || hp.res_stats || hp.C2 || hp.out_stats || hp.exact_act || p.acc_scale != 1.0f;
+// 0: default kernels; 1: only the lazily normalised residual of the light LayerNorm mode (out-proj / fc2); 2: every variant
+static inline int needs_variant_kernel(const cst_gemm_params& hp, const GemmDev& p) {
+  if (hp.ln_in_stats || hp.C2 || hp.out_stats || hp.exact_act || p.acc_scale != 1.0f) return 2;
+  if (hp.res_stats) return hp.act == CST_ACT_NONE ? 1 : 2;
+  return 0;
 }
 
-template <int BN, int ACT, bool VAR>
+template <int BN, int ACT, int VAR>
 static int launch_tc_act(const cst_gemm_params& hp, const GemmDev& p, int nz, cudaStream_t st) {
   using Cfg = TcCfg<BN>;
   static bool attr_set = false;
@@ -778,7 +779,7 @@ constexpr int TC2_HALF_BYTES = 128 * TC_BK * 2;                 // 16 KB: 128 A 
 constexpr int TC2_STAGE_BYTES = 2 * TC2_HALF_BYTES;
 constexpr int TC2_SMEM_BYTES = TC2_STAGES * TC2_STAGE_BYTES + TC_EPI_WARPS * TC_PATCH_BYTES + 1024 + 256;
 
-template <int ACT, bool VAR>
+template <int ACT, int VAR>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
                     const GemmDev p, int m_tiles, int n_tiles, int total_tiles, int a_wrap, int ab_f16, int bulk) {
@@ -935,7 +936,7 @@ extern "C" int cst_debug_tc_trace(unsigned long long* host) {
 namespace cst {
 #endif
 
-template <int ACT, bool VAR>
+template <int ACT, int VAR>
 static int launch_tc_pair_act(const cst_gemm_params& hp, const GemmDev& p, int nz, cudaStream_t st) {
   static bool attr_set = false;
   static int max_pairs = 0;
@@ -990,37 +991,41 @@ static int launch_tc_pair_act(const cst_gemm_params& hp, const GemmDev& p, int n
 }
 
 static int launch_tc_pair(const cst_gemm_params& hp, const GemmDev& p, int nz, cudaStream_t st) {
-  if (needs_variant_kernel(hp, p)) {
+  const int var = needs_variant_kernel(hp, p);
+  if (var == 1) return launch_tc_pair_act<CST_ACT_NONE, 1>(hp, p, nz, st);
+  if (var == 2) {
     switch (hp.act) {
-      case CST_ACT_NONE: return launch_tc_pair_act<CST_ACT_NONE, true>(hp, p, nz, st);
-      case CST_ACT_GELU: return launch_tc_pair_act<CST_ACT_GELU, true>(hp, p, nz, st);
-      case CST_ACT_RELU: return launch_tc_pair_act<CST_ACT_RELU, true>(hp, p, nz, st);
-      default: return launch_tc_pair_act<CST_ACT_GLU, true>(hp, p, nz, st);
+      case CST_ACT_NONE: return launch_tc_pair_act<CST_ACT_NONE, 2>(hp, p, nz, st);
+      case CST_ACT_GELU: return launch_tc_pair_act<CST_ACT_GELU, 2>(hp, p, nz, st);
+      case CST_ACT_RELU: return launch_tc_pair_act<CST_ACT_RELU, 2>(hp, p, nz, st);
+      default: return launch_tc_pair_act<CST_ACT_GLU, 2>(hp, p, nz, st);
     }
   }
   switch (hp.act) {
-    case CST_ACT_NONE: return launch_tc_pair_act<CST_ACT_NONE, false>(hp, p, nz, st);
-    case CST_ACT_GELU: return launch_tc_pair_act<CST_ACT_GELU, false>(hp, p, nz, st);
-    case CST_ACT_RELU: return launch_tc_pair_act<CST_ACT_RELU, false>(hp, p, nz, st);
-    default: return launch_tc_pair_act<CST_ACT_GLU, false>(hp, p, nz, st);
+    case CST_ACT_NONE: return launch_tc_pair_act<CST_ACT_NONE, 0>(hp, p, nz, st);
+    case CST_ACT_GELU: return launch_tc_pair_act<CST_ACT_GELU, 0>(hp, p, nz, st);
+    case CST_ACT_RELU: return launch_tc_pair_act<CST_ACT_RELU, 0>(hp, p, nz, st);
+    default: return launch_tc_pair_act<CST_ACT_GLU, 0>(hp, p, nz, st);
   }
 }
 
 template <int BN>
 static int launch_tc(const cst_gemm_params& hp, const GemmDev& p, int nz, cudaStream_t st) {
-  if (needs_variant_kernel(hp, p)) {
+  const int var = needs_variant_kernel(hp, p);
+  if (var == 1) return launch_tc_act<BN, CST_ACT_NONE, 1>(hp, p, nz, st);
+  if (var == 2) {
     switch (hp.act) {
-      case CST_ACT_NONE: return launch_tc_act<BN, CST_ACT_NONE, true>(hp, p, nz, st);
-      case CST_ACT_GELU: return launch_tc_act<BN, CST_ACT_GELU, true>(hp, p, nz, st);
-      case CST_ACT_RELU: return launch_tc_act<BN, CST_ACT_RELU, true>(hp, p, nz, st);
-      default: return launch_tc_act<BN, CST_ACT_GLU, true>(hp, p, nz, st);
+      case CST_ACT_NONE: return launch_tc_act<BN, CST_ACT_NONE, 2>(hp, p, nz, st);
+      case CST_ACT_GELU: return launch_tc_act<BN, CST_ACT_GELU, 2>(hp, p, nz, st);
+      case CST_ACT_RELU: return launch_tc_act<BN, CST_ACT_RELU, 2>(hp, p, nz, st);
+      default: return launch_tc_act<BN, CST_ACT_GLU, 2>(hp, p, nz, st);
     }
   }
   switch (hp.act) {
-    case CST_ACT_NONE: return launch_tc_act<BN, CST_ACT_NONE, false>(hp, p, nz, st);
-    case CST_ACT_GELU: return launch_tc_act<BN, CST_ACT_GELU, false>(hp, p, nz, st);
-    case CST_ACT_RELU: return launch_tc_act<BN, CST_ACT_RELU, false>(hp, p, nz, st);
-    default: return launch_tc_act<BN, CST_ACT_GLU, false>(hp, p, nz, st);
+    case CST_ACT_NONE: return launch_tc_act<BN, CST_ACT_NONE, 0>(hp, p, nz, st);
+    case CST_ACT_GELU: return launch_tc_act<BN, CST_ACT_GELU, 0>(hp, p, nz, st);
+    case CST_ACT_RELU: return launch_tc_act<BN, CST_ACT_RELU, 0>(hp, p, nz, st);
+    default: return launch_tc_act<BN, CST_ACT_GLU, 0>(hp, p, nz, st);
   }
 }
 
