@@ -632,7 +632,7 @@ def main():
     ap.add_argument("--lanes", type=int, default=2, help="concurrent CUDA-stream lanes for independent super-batches")
     ap.add_argument("--super-rows", type=int, default=-1,
                     help="wav2vec2 frame rows per super-batch (several reference batches, each with its own padded width, in one "
-                         "row space / one CUDA graph); -1 = the encoder's default (24576), 0 = one plan per reference batch")
+                         "row space / one CUDA graph); -1 = the encoder's default (49152), 0 = one plan per reference batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true",
                     help="c3 only: skip the brief secondary measurements (c4 encode + greedy decode, c5 training step) appended to the line")

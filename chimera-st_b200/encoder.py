@@ -156,7 +156,7 @@ class B200InterlinguaEncoder(nn.Module):
                            for _ in range(n)]
         return self._lanes
 
-    SUPER_ROWS = 24576      # forward_many: wav2vec2 frame rows per super-batch; 0 = one plan per batch
+    SUPER_ROWS = 49152      # forward_many: wav2vec2 frame rows per super-batch (measured sweet spot on c3: 24576 / 36864 / 49152 / 65536 / 98304 rows = 188.0 / 187.6 / 181.9-183.8 / 184.4 / 183.9 ms per step); 0 = one plan per batch
     SUPER_MAX_GROUPS = 16
 
     @staticmethod
