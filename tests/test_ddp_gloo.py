@@ -62,3 +62,22 @@ def test_two_rank_gloo_all_reduce_matches_the_reference_rule():
     for n, sz in SIZES:
         want = ref[n][0] / 2 + (ref[n][1] / 2 if n != "missing.on.rank1" else 0)
         assert torch.allclose(torch.from_numpy(out0[n]), want, atol=1e-7) and (out0[n] == out1[n]).all(), n
+
+
+def test_persistent_buffers_keep_their_addresses_and_bf16_wire_format():
+    """GradAllReducer(persistent=True): the flat buffers (and therefore the reduced-gradient views a CUDA-graphed optimizer update reads)
+    are allocated once; comm_dtype=bfloat16 rounds the pre-divided gradients to the wire format (single process: no collective)."""
+    sizes = [("a", 300), ("b", 40000), ("c", 7)]
+    red = ddp.GradAllReducer(sizes, world_size=1, bucket_bytes=64 * 1024, comm_dtype=torch.bfloat16, persistent=True)
+    g = torch.Generator().manual_seed(3)
+    ptrs = None
+    for step in range(3):
+        grads = {n: torch.randn(sz, generator=g) for n, sz in sizes}
+        red.ready(grads)
+        out = red.finish(grads)
+        for n, sz in sizes:
+            assert out[n].dtype == torch.bfloat16 and out[n].numel() == sz
+            assert torch.equal(out[n].float(), grads[n].to(torch.bfloat16).float())
+        now = {n: out[n].data_ptr() for n, _ in sizes}
+        assert ptrs is None or now == ptrs
+        ptrs = now
