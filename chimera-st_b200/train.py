@@ -226,7 +226,18 @@ class EncoderTrainStep:
         self.P = _weights.prepare(self.sd, dev, dtype, conv_dtype=self.cdt, training=True)
 
     # ------------------------------------------------------------------ forward (activations kept)
-    def forward(self, wave, lens):
+    @staticmethod
+    def sample_layerdrop(p, rng=None):
+        """The reference's LayerDrop draw for one step (TransformerEncoder.extract_features, wav2vec2.py:835-838): one host-side uniform
+        number per wav2vec2 layer, the layer runs iff it exceeds `p` (encoder_layerdrop, 0.05 in the base recipe).  -> set of skipped
+        layer indices for `forward(..., skip_w2v_layers=...)`."""
+        import numpy as np
+        draw = (rng or np.random).random
+        return frozenset(i for i in range(W2V_LAYERS) if not draw() > p)
+
+    def forward(self, wave, lens, skip_w2v_layers=()):
+        """skip_w2v_layers: wav2vec2 layers LayerDrop removed for this step (`sample_layerdrop`): they are not run, their parameters get
+        no gradient (absent from the result; the all-reduce counts them as zeros, legacy_distributed_data_parallel.py:141-143)."""
         o, g, P, lib = self.o, self.g, self.P, self.o.lib
         B, st, op, opc, esz = g.B, self.o.st(), self.op, self.o.opc, self.o.esz
         T = {}                                                     # the tape
@@ -276,7 +287,10 @@ class EncoderTrainStep:
         # ---- 12 post-LN wav2vec2 layers
         D = W2V_DIM
         T["w2v"] = []
-        for lw in P["w2v_layers"]:
+        for li, lw in enumerate(P["w2v_layers"]):
+            if li in skip_w2v_layers:
+                T["w2v"].append(None)
+                continue
             t = {"x_op": x_op}
             qkv = o.linear(x_op, lw["qkv_w"], lw["qkv_b"], out_dtype=op)
             qp = qkv.data_ptr()
@@ -412,6 +426,8 @@ class EncoderTrainStep:
                 yield G
                 G = {}
             lw, t, nm = P["w2v_layers"][li], T["w2v"][li], f"wav2vec_model.encoder.layers.{li}."
+            if t is None:                                           # dropped by LayerDrop in this step
+                continue
             dy2, dg2, dbt2 = o.ln_bwd(t["y2"], lw["ln2_g"], dx, R)
             G[nm + "final_layer_norm.weight"], G[nm + "final_layer_norm.bias"] = dg2, dbt2
             dx1 = self._ffn_bwd(G, nm, lw, t, dy2, R, L.ACT_GELU, "x1_op", dx_residual=dy2)  # + residual x1 -> y2

@@ -329,3 +329,35 @@ def test_text_pass_backward_and_gradient_accumulation_over_both_passes():
     assert rel_l2(both[k].cpu(), (Ga[k] + Gt[k]).cpu()) < 1e-5
     k = "wav2vec_model.encoder.layers.3.fc2.weight"
     assert torch.equal(both[k], Ga[k])
+
+
+def test_layerdrop_skips_layers_like_the_reference():
+    """LayerDrop (wav2vec2.py:835-838): with layers {2, 7} dropped the memories and every gradient match autograd through the oracle
+    with those layers replaced by the identity; the dropped layers' parameters get no gradient.  `sample_layerdrop` draws like the
+    reference (one uniform number per layer, run iff > p)."""
+    import numpy as np
+    torch.set_num_threads(8)
+    lens = [6000, 4500]
+    skip = frozenset({2, 7})
+    sd = synth.make_state_dict(seed=0, interlingua_length=16, dead_heads=False)
+    wave, tl = synth.make_waveforms(lens, seed=31)
+    R = torch.randn(16, 2, 512, generator=torch.Generator().manual_seed(1))
+    step = EncoderTrainStep(sd, 2, wave.shape[1], device=DEV, feature_grad_mult=1.0)
+    mem = step.forward(wave, tl, skip_w2v_layers=skip)
+    G = step.backward(R.to(DEV))
+    torch.cuda.synchronize()
+    masks = _relu_masks_of(step)
+    orig_layer = O.w2v_layer
+    O.w2v_layer = lambda sd_, i, x, m: x if i in skip else orig_layer(sd_, i, x, m)
+    try:
+        ref_mem, ref, _ = _oracle_grads(sd, wave, tl, R, masks)
+    finally:
+        O.w2v_layer = orig_layer
+    assert rel_l2(mem.cpu(), ref_mem) < 1e-5
+    assert not any(k.startswith(("wav2vec_model.encoder.layers.2.", "wav2vec_model.encoder.layers.7.")) for k in G)
+    bad = {k: rel_l2(v.cpu().reshape(ref[k].shape), ref[k]) for k, v in G.items() if not k.endswith("k_proj.bias")}
+    bad = {k: e for k, e in bad.items() if not e < 1e-4}
+    assert not bad, bad
+    rng = np.random.RandomState(0)
+    want = frozenset(i for i, u in enumerate(np.random.RandomState(0).random_sample(12)) if not u > 0.3)
+    assert EncoderTrainStep.sample_layerdrop(0.3, rng) == want and EncoderTrainStep.sample_layerdrop(0.0, rng) == frozenset()
