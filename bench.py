@@ -15,6 +15,11 @@ encoder.forward -> D2H of the memories, through the public module API), roofline
 encoder -- `oracle/_ref/src`, the bundle `oracle/make_ref_bundle.py` ships -- on this box's cores, one batch per length
 decile of the workload), parity (the B200 memories of those same batches against the reference's, every row), clocks
 sampled during the timed region.
+Also in the line: `roofline.large_m` (the GEMM on the M >= 16 384 shapes), `roofline_hbm_kernel` (conv0 + GroupNorm + GELU), `e2e.int16_wire`
+(the same end-to-end loop with 16-bit PCM on the wire) and, for the default workload, `secondary`: brief measurements of BASELINE configs[3]
+(`c4_encode_decode`: Chimera-64, 64 x 20 s, encode + greedy decode, serial and pipelined over stream lanes), configs[4] (`c5_train`: the
+CUDA-graphed training step with the bucketed gradient all-reduce, with and without the fused Adam update) and, for N > 1, a strong-scaling
+probe (`c3_strong_scaling`).  `--workload c5` prints the training step as its own line (per-kernel split, ST + MT + contrastive form).
 `--impl reference`: the reference arm = the reference's own modules (kind "reference"; only if the bundle is missing the
 oracle port, kind "port", with a warning) on the host cores, same metric/config; step i times decile batch i mod 10.
 """
