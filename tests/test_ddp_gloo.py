@@ -81,3 +81,14 @@ def test_persistent_buffers_keep_their_addresses_and_bf16_wire_format():
         now = {n: out[n].data_ptr() for n, _ in sizes}
         assert ptrs is None or now == ptrs
         ptrs = now
+
+
+def test_layerdrop_draw_follows_the_reference_rule():
+    """One uniform number per wav2vec2 layer, the layer runs iff the number exceeds p (wav2vec2.py:835-838)."""
+    import numpy as np
+    from chimera_st_b200.train import EncoderTrainStep
+    for seed, p in ((0, 0.3), (5, 0.05), (9, 0.9)):
+        u = np.random.RandomState(seed).random_sample(12)
+        want = frozenset(i for i in range(12) if not u[i] > p)
+        assert EncoderTrainStep.sample_layerdrop(p, np.random.RandomState(seed)) == want
+    assert EncoderTrainStep.sample_layerdrop(0.0, np.random.RandomState(1)) == frozenset()
