@@ -35,8 +35,10 @@ class _Ops:
     """Thin launch helpers over the C ABI (device tensors in / out, current stream).  `op` is the dtype of GEMM operands and of the
     pre-activations kept on the tape (fp32: the parity mode; bf16: BASELINE configs[4]); gradients of activations are always fp32."""
 
-    def __init__(self, device, op=F32):
-        self.lib = L.load()
+    def __init__(self, device, op=F32, lib=None):
+        # `lib` is injectable so tests can drive the launch sequence against the host emulator of the C ABI (tests/emu.py); the product
+        # never passes it and always loads the CUDA library.
+        self.lib = lib if lib is not None else L.load()
         self.dev = device
         self.op = op
         self.opc = _CODE[op]
@@ -45,7 +47,7 @@ class _Ops:
         self.ws = torch.empty(512 * 1024, dtype=F32, device=device)             # cst_colsum scratch (CST_COLSUM_WS_FLOATS)
 
     def st(self):
-        return L.stream_ptr()
+        return L.stream_ptr() if self.dev.type == "cuda" else 0
 
     def new(self, *shape, zero=False, dtype=F32):
         return (torch.zeros if zero else torch.empty)(*shape, dtype=dtype, device=self.dev)
@@ -203,9 +205,9 @@ def _attn_layer_grads(G, name, dqkv_w, dqkv_b, D, fused=True):
 
 
 class EncoderTrainStep:
-    def __init__(self, state_dict, B, Lw, M=None, device="cuda", feature_grad_mult=0.1, dtype=F32):
+    def __init__(self, state_dict, B, Lw, M=None, device="cuda", feature_grad_mult=0.1, dtype=F32, lib=None):
         dev = torch.device(device)
-        if dev.type != "cuda":
+        if dev.type != "cuda" and lib is None:
             raise L.CstError("EncoderTrainStep runs only on a CUDA device (no CPU fallback)")
         if dtype not in (F32, torch.bfloat16):
             raise L.CstError("EncoderTrainStep: dtype must be torch.float32 or torch.bfloat16")
@@ -217,7 +219,7 @@ class EncoderTrainStep:
         self.g = Geometry(B, Lw, self.M)
         self.dev = dev
         self.op = dtype
-        self.o = _Ops(dev, dtype)
+        self.o = _Ops(dev, dtype, lib=lib)
         self.fgm = float(feature_grad_mult)
         # 16-bit mode: the normalisation-free conv stack runs its FORWARD GEMMs on fp16 operands like the inference path (DESIGN.md §2:
         # bf16 there costs 6e-3 of the 1e-2 budget); every backward operand (transposed copies of weights, activations, gradients)
@@ -662,7 +664,7 @@ class FusedAdam:
     Gradients may be fp32 or the bf16 wire format of the all-reduce.  The per-step scalars (lr, step size, gradient scale) are read from
     a device buffer, so `step` can be captured into a CUDA graph once and replayed every step after `advance()`."""
 
-    def __init__(self, params, lr=1e-4, betas=(0.9, 0.98), eps=1e-8, weight_decay=0.0):
+    def __init__(self, params, lr=1e-4, betas=(0.9, 0.98), eps=1e-8, weight_decay=0.0, lib=None):
         self.params = params                                       # {reference name: fp32 device tensor}, updated in place
         self.lr, self.betas, self.eps, self.wd = float(lr), (float(betas[0]), float(betas[1])), float(eps), float(weight_decay)
         dev = next(iter(params.values())).device
@@ -671,7 +673,10 @@ class FusedAdam:
         self.t = 0
         self.dyn = torch.zeros(4, dtype=F32, device=dev)
         self._dyn_host = torch.zeros(4, dtype=F32).pin_memory() if dev.type == "cuda" else torch.zeros(4, dtype=F32)
-        self.lib = L.load()
+        if dev.type != "cuda" and lib is None:
+            raise L.CstError("FusedAdam runs only on CUDA tensors (no CPU fallback)")
+        self.dev = dev
+        self.lib = lib if lib is not None else L.load()                 # injectable for the host emulator (tests/emu.py), like _Ops
 
     def advance(self, lr=None, grad_scale=1.0):
         """Next step number: refresh {lr, step_size, grad_scale} on the device (asynchronous copy on the current stream)."""
@@ -687,7 +692,7 @@ class FusedAdam:
     def step(self, grads):
         """Launch the updates (reads the scalars written by the last `advance()`); parameters without a gradient are left alone."""
         b1, b2 = self.betas
-        st = L.stream_ptr()
+        st = L.stream_ptr() if self.dev.type == "cuda" else 0
         for name, p in self.params.items():
             g = grads.get(name)
             if g is None:

@@ -412,3 +412,190 @@ def _dec_beam_select(self, pref, stream):
 
 EmuLib.cst_dec_attention_beam = _dec_attention_beam
 EmuLib.cst_dec_beam_select = _dec_beam_select
+
+
+# ---- backward pass (cst_transpose .. cst_conv0_bwd): the derivative entry points of the training step (train.py), fp32, on host memory.
+# Where a derivative is not a plain index shuffle it is obtained from torch autograd of the forward expression, so the emulator states
+# WHAT the kernel computes independently of how csrc/backward.cu computes it. ------------------------------------------------------------
+def _view(ptr, rows, cols, ld, copy=True):
+    if rows <= 0:
+        return torch.zeros(0, cols)
+    t = torch.from_numpy(_mem(ptr, (rows - 1) * ld + cols))
+    t = t.as_strided((rows, cols), (ld, 1))
+    return t.clone() if copy else t
+
+
+def _transpose(self, x, x_dtype, ldx, rows, cols, outT, out_dtype, rows_pad, chunk, copy, ldcopy, stream):
+    assert x_dtype == F32 and out_dtype == F32 and rows_pad >= rows
+    chunk = rows_pad if chunk <= 0 else chunk
+    assert rows_pad % chunk == 0
+    X = _view(x, rows, cols, ldx)                                  # ldx < cols: overlapping windows of a strided convolution's input
+    Xp = torch.zeros(rows_pad, cols)
+    Xp[:rows] = X
+    out = Xp.view(rows_pad // chunk, chunk, cols).permute(0, 2, 1).contiguous()       # [(r / chunk), c, r % chunk]
+    _mem(outT, out.numel())[:] = out.reshape(-1).numpy()
+    if copy:
+        _view(copy, rows, cols, ldcopy, copy=False)[:] = X
+    self.calls.append("transpose")
+    return 0
+
+
+def _colsum(self, x, x_dtype, ldx, rows, cols, out, ws, scale, stream):
+    assert x_dtype == F32
+    _mem(out, cols)[:] = (_view(x, rows, cols, ldx).double().sum(0) * scale).float().numpy()
+    self.calls.append("colsum")
+    return 0
+
+
+def _act(kind, z, alpha):
+    if kind == 1:
+        y = 0.5 * z * (1 + torch.erf(z / math.sqrt(2.0)))
+    elif kind == 2:
+        y = torch.relu(z)
+    else:
+        assert kind == 3
+        y = z[:, 0::2] * torch.sigmoid(z[:, 1::2])               # interleaved (value, gate) pairs
+    return y * alpha
+
+
+def _act_fwd(self, act, z, z_dtype, ldz, rows, cols_out, y, y_dtype, ldy, alpha, stream):
+    assert z_dtype == F32 and y_dtype == F32
+    Z = _view(z, rows, cols_out * (2 if act == 3 else 1), ldz).double()
+    _view(y, rows, cols_out, ldy, copy=False)[:] = _act(act, Z, alpha).float()
+    self.calls.append("act_fwd")
+    return 0
+
+
+def _act_bwd(self, act, z, z_dtype, ldz, dy, dy_dtype, ldy, rows, cols_out, dz, dz_dtype, lddz, alpha, stream):
+    assert z_dtype == F32 and dy_dtype == F32 and dz_dtype == F32
+    cin = cols_out * (2 if act == 3 else 1)
+    Z = _view(z, rows, cin, ldz).double().requires_grad_()
+    _act(act, Z, alpha).backward(_view(dy, rows, cols_out, ldy).double())
+    _view(dz, rows, cin, lddz, copy=False)[:] = Z.grad.float()
+    self.calls.append("act_bwd")
+    return 0
+
+
+def _layernorm_bwd(self, x, ldx, gamma, dy, ldy, dx, lddx, part, rows, Cd, accumulate, stream):
+    X = _view(x, rows, Cd, ldx).double().requires_grad_()
+    g = torch.from_numpy(_mem(gamma, Cd).copy()).double()
+    DY = _view(dy, rows, Cd, ldy).double()
+    torch.nn.functional.layer_norm(X, (Cd,), g, None, 1e-5).backward(DY)
+    out = _view(dx, rows, Cd, lddx, copy=False)
+    out[:] = (out.double() + X.grad if accumulate else X.grad).float()
+    if part:
+        xd = X.detach()
+        xhat = (xd - xd.mean(1, keepdim=True)) / torch.sqrt(xd.var(1, unbiased=False, keepdim=True) + 1e-5)
+        nblk = (rows + 7) // 8
+        both = torch.zeros(nblk * 8, 2 * Cd, dtype=torch.float64)
+        both[:rows, :Cd], both[:rows, Cd:] = DY * xhat, DY
+        _mem(part, nblk * 2 * Cd)[:] = both.view(nblk, 8, 2 * Cd).sum(1).float().reshape(-1).numpy()      # [block][dgamma | dbeta]
+    self.calls.append("layernorm_bwd")
+    return 0
+
+
+def _attention_bwd(self, q, k, v, o, dtype, d_o, dq, dk, dv, ldq, ldkv, ldo_fwd, ldo, lddq, lddkv, B, H, n_q, q_rps, n_kv, kv_rps, kv_len,
+                   stream):
+    assert dtype == F32
+
+    def heads(ptr, n, rps, ld, copy=True):
+        t = torch.from_numpy(_mem(ptr, ((B - 1) * rps + n - 1) * ld + H * 64)).as_strided((B, n, H, 64), (rps * ld, ld, 64, 1))
+        return t.clone() if copy else t
+    Q, K, V = (heads(p_, n, r, ld).double().requires_grad_() for p_, n, r, ld in ((q, n_q, q_rps, ldq), (k, n_kv, kv_rps, ldkv),
+                                                                                   (v, n_kv, kv_rps, ldkv)))
+    s = torch.einsum("bqhd,bkhd->bhqk", Q, K)
+    if kv_len:
+        kl = torch.from_numpy(_mem(kv_len, B, np.int32).copy()).long()
+        s = s.masked_fill(torch.arange(n_kv)[None, None, None, :] >= kl[:, None, None, None], float("-inf"))
+    out = torch.einsum("bhqk,bkhd->bqhd", torch.softmax(s, -1), V)
+    out.backward(heads(d_o, n_q, q_rps, ldo).double())
+    heads(dq, n_q, q_rps, lddq, copy=False)[:] = Q.grad.float()
+    for dst, grad in ((dk, K.grad), (dv, V.grad)):                # "must be zero on entry": the kernel accumulates with atomics
+        view = heads(dst, n_kv, kv_rps, lddkv, copy=False)
+        view[:] = view + grad.float()
+    self.calls.append("attention_bwd")
+    return 0
+
+
+def _col2im(self, dcol, dcol_dtype, M, k, stride, Cd, dx, rows_in, accumulate, stream):
+    assert dcol_dtype == F32
+    D = torch.from_numpy(_mem(dcol, M * k * Cd).copy()).view(M, k, Cd).double()
+    acc = torch.zeros(rows_in, Cd, dtype=torch.float64)
+    for t in range(k):                                             # window m covers input rows m*stride .. m*stride + k - 1
+        r = torch.arange(M) * stride + t
+        ok = r < rows_in
+        acc.index_add_(0, r[ok], D[ok, t])
+    out = _view(dx, rows_in, Cd, Cd, copy=False)
+    out[:] = (out.double() + acc if accumulate else acc).float()
+    self.calls.append("col2im")
+    return 0
+
+
+def _rows_remap(self, inp, ldi, in_rps, in_off, out, out_dtype, ldo, out_rps, out_off, n_seg, n_rows, Cd, seg_valid, seg_len, accumulate,
+                scale, stream):
+    assert out_dtype == F32
+    sl = _mem(seg_len, n_seg, np.int32) if seg_len else None
+    for s in range(n_seg):
+        valid = min(seg_valid, int(sl[s])) if sl is not None else seg_valid
+        valid = max(0, min(valid, n_rows))
+        val = torch.zeros(n_rows, Cd)
+        if valid:
+            val[:valid] = _view(inp + 4 * (s * in_rps + in_off) * ldi, valid, Cd, ldi) * scale
+        dst = _view(out + 4 * (s * out_rps + out_off) * ldo, n_rows, Cd, ldo, copy=False)
+        dst[:] = dst + val if accumulate else val
+    self.calls.append("rows_remap")
+    return 0
+
+
+def _conv0_bwd(self, wave, B, L, w, gamma, beta, scale_shift, dout, rows_per_seg, dw, dgamma, dbeta, ws, grad_scale, stream):
+    x = torch.from_numpy(_mem(wave, B * L).reshape(B, L).copy()).double()
+    W = torch.from_numpy(_mem(w, 5120).reshape(512, 1, 10).copy()).double().requires_grad_()
+    g = torch.from_numpy(_mem(gamma, 512).copy()).double().requires_grad_()
+    b = torch.from_numpy(_mem(beta, 512).copy()).double().requires_grad_()
+    y = torch.nn.functional.conv1d(x.unsqueeze(1), W, stride=5)
+    y = torch.nn.functional.group_norm(y, 512, g, b, 1e-5)
+    y = 0.5 * y * (1 + torch.erf(y / math.sqrt(2.0)))
+    T0 = y.shape[2]
+    D = torch.from_numpy(_mem(dout, B * rows_per_seg * 512).copy()).view(B, rows_per_seg, 512)[:, :T0].double()
+    y.backward(D.transpose(1, 2))
+    for dst, t in ((dw, W.grad), (dgamma, g.grad), (dbeta, b.grad)):
+        _mem(dst, t.numel())[:] = (t * grad_scale).float().reshape(-1).numpy()      # GradMultiply folded into the three outputs
+    self.calls.append("conv0_bwd")
+    return 0
+
+
+def _embed_bwd(self, tokens, dx, scale, dE, B, T, rows_per_seg, Cd, V, pad_idx, stream):
+    tok = torch.from_numpy(_mem(tokens, B * T, np.int64).copy()).view(B, T)
+    D = torch.from_numpy(_mem(dx, B * rows_per_seg * Cd).copy()).view(B, rows_per_seg, Cd)[:, :T]
+    E = torch.from_numpy(_mem(dE, V * Cd)).view(V, Cd)
+    keep = tok != pad_idx
+    E.index_add_(0, tok[keep], D[keep] * scale)
+    self.calls.append("embed_bwd")
+    return 0
+
+
+def _adam_step(self, p, g, g_dtype, m, v, n, lr, b1, b2, eps, wd, step_size, grad_scale, dyn, stream):
+    assert g_dtype == F32
+    if dyn:
+        lr, step_size, grad_scale = (float(t) for t in _mem(dyn, 3))
+    P, G, M_, V_ = (torch.from_numpy(_mem(t, n)) for t in (p, g, m, v))
+    gi = G * grad_scale
+    M_.mul_(b1).add_(gi, alpha=1 - b1)
+    V_.mul_(b2).addcmul_(gi, gi, value=1 - b2)
+    P.mul_(1 - wd * lr)
+    P.addcdiv_(M_, V_.sqrt() + eps, value=-step_size)
+    self.calls.append("adam_step")
+    return 0
+
+
+EmuLib.cst_transpose = _transpose
+EmuLib.cst_colsum = _colsum
+EmuLib.cst_act_fwd = _act_fwd
+EmuLib.cst_act_bwd = _act_bwd
+EmuLib.cst_layernorm_bwd = _layernorm_bwd
+EmuLib.cst_attention_bwd = _attention_bwd
+EmuLib.cst_col2im = _col2im
+EmuLib.cst_rows_remap = _rows_remap
+EmuLib.cst_conv0_bwd = _conv0_bwd
+EmuLib.cst_embed_bwd = _embed_bwd
+EmuLib.cst_adam_step = _adam_step
