@@ -7,6 +7,7 @@
 // transposed copies made by cst_transpose.  All gradients are fp32.
 #include <cuda_fp16.h>
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace cst {
 
@@ -325,6 +326,35 @@ __global__ void __launch_bounds__(256) col2im_kernel(const void* __restrict__ dc
   }
 }
 
+// ---- dropout (training step; fairseq_dropout.py:16-27 = F.dropout): out = add + x * keep / (1 - p), masks regenerated from
+// (seed, site, element index) -- see philox.cuh.  The SAME kernel is the derivative: the gradient of the dropped tensor is
+// dropout(dy) with the same seed and site.  Optional `add` (fp32) is the residual the reference adds right after the dropout
+// (x = residual + dropout(x), wav2vec2.py TransformerSentenceEncoderLayer / transformer_layer.py:~160-190); optional second output =
+// the GEMM-operand copy.  One thread = 4 consecutive columns = one Philox counter.
+__global__ void __launch_bounds__(256) dropout_kernel(const void* __restrict__ x, int xdt, long long ldx, const float* __restrict__ add,
+                                                      long long ldadd, void* __restrict__ out, int odt, long long ldo,
+                                                      void* __restrict__ out2, int o2dt, long long ldo2, int rows, int cols, uint32_t thresh,
+                                                      float scale, const unsigned long long* __restrict__ seed_dev, uint32_t site) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const unsigned long long seed = seed_dev[0];
+  const int c4n = cols >> 2;
+  const long long total = (long long)rows * c4n;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / c4n;
+    const int c = (int)(i - r * c4n) * 4;
+    const Philox4 rnd = philox4x32_10(seed, (unsigned long long)i, site);           // group = (r * cols + c) / 4 = i
+    float4 v = ld4_any(x, xdt, r * ldx + c);
+    v.x = rnd.x >= thresh ? v.x * scale : 0.f;
+    v.y = rnd.y >= thresh ? v.y * scale : 0.f;
+    v.z = rnd.z >= thresh ? v.z * scale : 0.f;
+    v.w = rnd.w >= thresh ? v.w * scale : 0.f;
+    if (add != nullptr) { const float4 a = load4(add + r * ldadd + c); v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w; }
+    st4_any(out, odt, r * ldo + c, v);
+    if (out2 != nullptr) st4_any(out2, o2dt, r * ldo2 + c, v);
+  }
+}
+
 // ---- row remap with masking: out[seg*out_rps + t + off] (+)= in[seg*in_rps + t + in_off] for t < valid (seg_len[seg] when given,
 // else seg_valid); rows t >= valid of the OUTPUT segment range [0, n_rows_out) are zeroed when zero_rest.  The transpose of the
 // forward row remaps (zero-padded subsampler operands, masked projection rows).
@@ -460,6 +490,18 @@ extern "C" int cst_rows_remap(const float* in, long long ldi, int in_rps, int in
   CST_REQUIRE(in && out && n_seg > 0 && n_rows > 0 && C % 4 == 0 && ldo % 4 == 0, "cst_rows_remap: bad args");
   CST_CHECK_CUDA(launch_k(rows_remap_kernel, dim3(grid_for((long long)n_seg * n_rows * (C / 4))), dim3(256), 0, (cudaStream_t)stream, in, ldi,
                           in_rps, in_off, out, out_dtype, ldo, out_rps, out_off, n_seg, n_rows, C, seg_valid, seg_len, accumulate, scale));
+  return CST_OK;
+}
+
+extern "C" int cst_dropout(const void* x, int x_dtype, long long ldx, const float* add, long long ldadd, void* out, int out_dtype, long long ldo,
+                           void* out2, int out2_dtype, long long ldo2, int rows, int cols, float p, const unsigned long long* seed,
+                           unsigned int site, void* stream) {
+  CST_REQUIRE(x && out && seed && rows > 0 && cols > 0 && p >= 0.f && p < 1.f, "cst_dropout: bad args");
+  CST_REQUIRE(cols % 4 == 0 && ldx % 4 == 0 && ldo % 4 == 0 && (!add || ldadd % 4 == 0) && (!out2 || ldo2 % 4 == 0),
+              "cst_dropout: cols / row pitches must be multiples of 4");
+  CST_CHECK_CUDA(launch_k(dropout_kernel, dim3(grid_for((long long)rows * cols / 4)), dim3(256), 0, (cudaStream_t)stream, x, x_dtype, ldx, add,
+                          ldadd, out, out_dtype, ldo, out2, out2_dtype, ldo2, rows, cols, dropout_threshold(p), 1.0f / (1.0f - p), seed,
+                          (uint32_t)site));
   return CST_OK;
 }
 

@@ -147,6 +147,16 @@ class _Ops:
                                      dz.data_ptr(), L.F32, z.shape[1], alpha, self.st()))
         return dz
 
+    def dropout(self, x, rows, cols, p, seed, site, add=None, out_dtype=F32, lp_dtype=None):
+        """-> add + x * keep / (1 - p) (and its `lp_dtype` copy); the mask is a function of (*seed, site, element index): calling this on a
+        gradient with the same seed / site is the derivative (csrc/philox.cuh)."""
+        out = self.new(rows, cols, dtype=out_dtype)
+        lp = self.new(rows, cols, dtype=lp_dtype) if lp_dtype is not None else None
+        L.check(self.lib.cst_dropout(x.data_ptr(), _CODE[x.dtype], x.shape[1], L.ptr(add), add.shape[1] if add is not None else 0,
+                                     out.data_ptr(), _CODE[out_dtype], cols, L.ptr(lp), _CODE[lp_dtype] if lp is not None else 0, cols,
+                                     rows, cols, float(p), seed.data_ptr(), int(site), self.st()))
+        return out if lp is None else (out, lp)
+
     def ln(self, x, g, b, rows, f32=True):
         """-> (fp32 normalised rows or None, operand-dtype copy); in the fp32 mode both are the same tensor."""
         Cd = x.shape[1]
@@ -205,7 +215,8 @@ def _attn_layer_grads(G, name, dqkv_w, dqkv_b, D, fused=True):
 
 
 class EncoderTrainStep:
-    def __init__(self, state_dict, B, Lw, M=None, device="cuda", feature_grad_mult=0.1, dtype=F32, lib=None):
+    def __init__(self, state_dict, B, Lw, M=None, device="cuda", feature_grad_mult=0.1, dtype=F32, lib=None, dropout=0.0,
+                 activation_dropout=None, w2v_dropout=0.0, w2v_dropout_input=0.0, seed=1):
         dev = torch.device(device)
         if dev.type != "cuda" and lib is None:
             raise L.CstError("EncoderTrainStep runs only on a CUDA device (no CPU fallback)")
@@ -226,6 +237,29 @@ class EncoderTrainStep:
         # is bf16 -- gradients need the range, and cst_transpose converts on the fly.
         self.cdt = dtype if dtype == F32 else torch.float16
         self.P = _weights.prepare(self.sd, dev, dtype, conv_dtype=self.cdt, training=True)
+        # Dropout of the training recipe (train-en2any-ST.sh:45 --dropout 0.1; wav2vec2 base: dropout 0.1, dropout_input 0.1,
+        # activation_dropout 0): `dropout` = the shared / memory layers' dropout_module + the dropout after the embedding scale
+        # (w2v2_transformer_interlingua.py:237), `activation_dropout` their activation_dropout_module (defaults to `dropout`,
+        # w2v2_transformer.py:460), `w2v_dropout` = wav2vec2's encoder dropout (wav2vec2.py:830) and dropout1 / dropout3 of its layers,
+        # `w2v_dropout_input` = wav2vec2.py:553.  0 everywhere = the parity configuration.  Masks are regenerated from (seed, site) in the
+        # backward pass, never stored; `seed_dev` lives on the device so CUDA-graph replays draw fresh masks (`next_dropout_seed`).
+        # Dropout of the attention probabilities (attention_dropout) is NOT built.
+        self.pd = {"shared": float(dropout), "act": float(dropout if activation_dropout is None else activation_dropout),
+                   "w2v": float(w2v_dropout), "w2v_input": float(w2v_dropout_input)}
+        self._sites = {}
+        self._seed_host = torch.tensor([int(seed)], dtype=torch.int64)
+        if dev.type == "cuda":
+            self._seed_host = self._seed_host.pin_memory()
+        self.seed_dev = self._seed_host.to(dev).clone()
+
+    def next_dropout_seed(self):
+        """New masks for the next step (asynchronous copy on the current stream; graph replays read the device value)."""
+        self._seed_host[0] += 1
+        self.seed_dev.copy_(self._seed_host, non_blocking=True)
+
+    def _drop(self, T, tag, p, x, rows, cols, **kw):
+        site = self._sites.setdefault((T.get("pass", 0), tag), len(self._sites))
+        return self.o.dropout(x, rows, cols, p, self.seed_dev, site, **kw)
 
     # ------------------------------------------------------------------ forward (activations kept)
     @staticmethod
@@ -275,6 +309,8 @@ class EncoderTrainStep:
         _, feat_ln = o.ln(feat, P["ln_feat_g"], P["ln_feat_b"], R, f32=False)
         xp = o.gemm(feat_ln, P["proj_w"], o.new(R, W2V_DIM), R, W2V_DIM, 512, lda=512, a_rows=R, bias=P["proj_b"], rows_per_seg=g.T6a,
                     seg_len=w2v_valid)
+        if self.pd["w2v_input"] > 0:                               # dropout_input (wav2vec2.py:553); padded rows stay zero
+            xp = self._drop(T, "w2v.input", self.pd["w2v_input"], xp, R, W2V_DIM)
         T["feat_ln"], T["xp"] = feat_ln, xp
         # ---- pos-conv (grouped implicit GEMM on the packed operand), GELU, residual
         xg = torch.zeros(B * 16 * g.Tpp + SLACK, 64, dtype=op, device=self.dev)
@@ -286,6 +322,10 @@ class EncoderTrainStep:
         o.remap(gp, R, 0, y0, R, 0, 1, R, W2V_DIM, R, accumulate=True)
         T["xg"], T["zpos"], T["y0"] = xg, zpos, y0
         x, x_op = o.ln(y0, P["ln_enc_g"], P["ln_enc_b"], R)
+        pw = self.pd["w2v"]
+        if pw > 0:                                                 # F.dropout after the encoder LayerNorm (wav2vec2.py:830)
+            x = self._drop(T, "w2v.enc", pw, x, R, W2V_DIM, lp_dtype=None if op == F32 else op)
+            x, x_op = (x, x) if op == F32 else x
         # ---- 12 post-LN wav2vec2 layers
         D = W2V_DIM
         T["w2v"] = []
@@ -297,11 +337,17 @@ class EncoderTrainStep:
             qkv = o.linear(x_op, lw["qkv_w"], lw["qkv_b"], out_dtype=op)
             qp = qkv.data_ptr()
             ctx = o.attention(qp, qp + esz * D, qp + 2 * esz * D, 3 * D, 3 * D, B, W2V_HEADS, g.T6a, g.T6a, g.Tp, g.T6a, w2v_valid, R, D)
-            y1 = o.linear(ctx, lw["o_w"], lw["o_b"], residual=x)
+            if pw > 0:                                             # x = residual + dropout1(attention output)
+                y1 = self._drop(T, f"w2v{li}.attn", pw, o.linear(ctx, lw["o_w"], lw["o_b"]), R, D, add=x)
+            else:
+                y1 = o.linear(ctx, lw["o_w"], lw["o_b"], residual=x)
             x1, x1_op = o.ln(y1, lw["ln1_g"], lw["ln1_b"], R)
             z = o.linear(x1_op, lw["fc1_w"], lw["fc1_b"])           # fp32 pre-activation: h is rounded once, as in the fused epilogue
             h = o.act(L.ACT_GELU, z, R, W2V_FFN)
-            y2 = o.linear(h, lw["fc2_w"], lw["fc2_b"], residual=x1)
+            if pw > 0:                                             # x = residual + dropout3(fc2 output); activation_dropout is 0 in wav2vec2 base
+                y2 = self._drop(T, f"w2v{li}.ffn", pw, o.linear(h, lw["fc2_w"], lw["fc2_b"]), R, D, add=x1)
+            else:
+                y2 = o.linear(h, lw["fc2_w"], lw["fc2_b"], residual=x1)
             x, x_op = o.ln(y2, lw["ln2_g"], lw["ln2_b"], R)
             t.update(qkv=qkv, ctx=ctx, y1=y1, x1_op=x1_op, z=z, h=h, y2=y2)
             T["w2v"].append(t)
@@ -329,20 +375,31 @@ class EncoderTrainStep:
         B, st, op, esz = g.B, self.o.st(), self.op, self.o.esz
         R2 = B * g.T2a
         T["sub_valid"] = sub_valid
+        ps, pa = self.pd["shared"], self.pd["act"]
+        if ps > 0:                                                 # dropout_module after embed_scale (+ positions) (interlingua.py:237)
+            x2 = self._drop(T, "embed", ps, x2, R2, ENC_DIM)
         # ---- 6 pre-LN shared layers
         D2 = ENC_DIM
         T["enc"] = []
-        for lw in self._enc_layers(T):
+        for li, lw in enumerate(self._enc_layers(T)):
             t = {"x_in": x2}
             _, a = o.ln(x2, lw["ln1_g"], lw["ln1_b"], R2, f32=False)
             qkv = o.linear(a, lw["qkv_w"], lw["qkv_b"], out_dtype=op)
             qp = qkv.data_ptr()
             ctx = o.attention(qp, qp + esz * D2, qp + 2 * esz * D2, 3 * D2, 3 * D2, B, ENC_HEADS, g.T2a, g.T2a, g.T2, g.T2a, sub_valid, R2, D2)
-            xm = o.linear(ctx, lw["o_w"], lw["o_b"], residual=x2)
+            if ps > 0:
+                xm = self._drop(T, f"enc{li}.attn", ps, o.linear(ctx, lw["o_w"], lw["o_b"]), R2, D2, add=x2)
+            else:
+                xm = o.linear(ctx, lw["o_w"], lw["o_b"], residual=x2)
             _, b_ = o.ln(xm, lw["ln2_g"], lw["ln2_b"], R2, f32=False)
             z = o.linear(b_, lw["fc1_w"], lw["fc1_b"])
             h = o.act(L.ACT_RELU, z, R2, ENC_FFN)
-            x2 = o.linear(h, lw["fc2_w"], lw["fc2_b"], residual=xm)
+            if pa > 0:                                             # activation_dropout_module (transformer_layer.py); h = the fc2 operand
+                h = self._drop(T, f"enc{li}.act", pa, h, R2, ENC_FFN, out_dtype=op)
+            if ps > 0:
+                x2 = self._drop(T, f"enc{li}.ffn", ps, o.linear(h, lw["fc2_w"], lw["fc2_b"]), R2, D2, add=xm)
+            else:
+                x2 = o.linear(h, lw["fc2_w"], lw["fc2_b"], residual=xm)
             t.update(a=a, qkv=qkv, ctx=ctx, xm=xm, b=b_, z=z, h=h)
             T["enc"].append(t)
         T["x2_out"] = x2
@@ -353,7 +410,7 @@ class EncoderTrainStep:
         mem = o.new(RM, D2)
         L.check(lib.cst_broadcast_rows(P["mem_embed"].data_ptr(), Mq, D2, B, mem.data_ptr(), st))
         T["mem"] = []
-        for lw in P["mem_layers"]:
+        for li, lw in enumerate(P["mem_layers"]):
             t = {"m_in": mem}
             _, a = o.ln(mem, lw["ln1_g"], lw["ln1_b"], RM, f32=False)
             _, kv_in = o.ln(h_enc, lw["ln1_g"], lw["ln1_b"], R2, f32=False)
@@ -361,22 +418,35 @@ class EncoderTrainStep:
             kv = o.linear(kv_in, lw["kv_w"], lw["kv_b"], out_dtype=op)
             kp = kv.data_ptr()
             ctx = o.attention(q.data_ptr(), kp, kp + esz * D2, D2, 2 * D2, B, ENC_HEADS, Mq, Mq, g.T2, g.T2a, None, RM, D2)
-            mm = o.linear(ctx, lw["o_w"], lw["o_b"], residual=mem)
+            if ps > 0:                                             # only the M memory rows of cat(h_enc, memories) survive the layer
+                mm = self._drop(T, f"mem{li}.attn", ps, o.linear(ctx, lw["o_w"], lw["o_b"]), RM, D2, add=mem)
+            else:
+                mm = o.linear(ctx, lw["o_w"], lw["o_b"], residual=mem)
             _, b_ = o.ln(mm, lw["ln2_g"], lw["ln2_b"], RM, f32=False)
             z = o.linear(b_, lw["fc1_w"], lw["fc1_b"])
             h = o.act(L.ACT_RELU, z, RM, ENC_FFN)
-            mem = o.linear(h, lw["fc2_w"], lw["fc2_b"], residual=mm)
+            if pa > 0:
+                h = self._drop(T, f"mem{li}.act", pa, h, RM, ENC_FFN, out_dtype=op)
+            if ps > 0:
+                mem = self._drop(T, f"mem{li}.ffn", ps, o.linear(h, lw["fc2_w"], lw["fc2_b"]), RM, D2, add=mm)
+            else:
+                mem = o.linear(h, lw["fc2_w"], lw["fc2_b"], residual=mm)
             t.update(a=a, kv_in=kv_in, q=q, kv=kv, ctx=ctx, mm=mm, b=b_, z=z, h=h)
             T["mem"].append(t)
         self.mem_out = mem
         return mem.view(B, Mq, D2).transpose(0, 1)                 # [M, B, 512] (view)
 
     # ------------------------------------------------------------------ backward
-    def _ffn_bwd(self, G, name, lw, t, dy, rows, act, x_key, dx_residual=None):
-        """y = x_in + fc2(act(fc1(LNorm-ed input))) pieces shared by all three layer types: returns d(fc1 input) (+ dx_residual)."""
+    def _ffn_bwd(self, G, name, lw, t, dy, rows, act, x_key, dx_residual=None, T=None, tag=None, p_out=0.0, p_act=0.0):
+        """y = x_in + drop(fc2(drop_act(act(fc1(LNorm-ed input))))) pieces shared by all three layer types: returns d(fc1 input)
+        (+ dx_residual).  t["h"] is the fc2 operand (after the activation dropout)."""
         o = self.o
+        if p_out > 0:
+            dy = self._drop(T, tag + ".ffn", p_out, dy, rows, dy.shape[1])
         dh, dW2, db2 = o.linear_bwd(t["h"], lw["fc2_w"], dy, rows)
         G[name + "fc2.weight"], G[name + "fc2.bias"] = dW2, db2
+        if p_act > 0:
+            dh = self._drop(T, tag + ".act", p_act, dh, rows, dh.shape[1])
         dz = o.act_bwd(act, t["z"], dh, rows, t["z"].shape[1])
         dxin, dW1, db1 = o.linear_bwd(t[x_key], lw["fc1_w"], dz, rows, dx_residual=dx_residual)
         G[name + "fc1.weight"], G[name + "fc1.bias"] = dW1, db1
@@ -423,6 +493,7 @@ class EncoderTrainStep:
         yield G
         G = {}
         # ---- 12 post-LN wav2vec2 layers
+        pw = self.pd["w2v"]
         for li in reversed(range(W2V_LAYERS)):
             if li == W2V_LAYERS // 2 - 1:
                 yield G
@@ -432,10 +503,10 @@ class EncoderTrainStep:
                 continue
             dy2, dg2, dbt2 = o.ln_bwd(t["y2"], lw["ln2_g"], dx, R)
             G[nm + "final_layer_norm.weight"], G[nm + "final_layer_norm.bias"] = dg2, dbt2
-            dx1 = self._ffn_bwd(G, nm, lw, t, dy2, R, L.ACT_GELU, "x1_op", dx_residual=dy2)  # + residual x1 -> y2
+            dx1 = self._ffn_bwd(G, nm, lw, t, dy2, R, L.ACT_GELU, "x1_op", dx_residual=dy2, T=T, tag=f"w2v{li}", p_out=pw)  # + residual x1 -> y2
             dy1, dg1, dbt1 = o.ln_bwd(t["y1"], lw["ln1_g"], dx1, R)
             G[nm + "self_attn_layer_norm.weight"], G[nm + "self_attn_layer_norm.bias"] = dg1, dbt1
-            dctx, dWo, dbo = o.linear_bwd(t["ctx"], lw["o_w"], dy1, R)
+            dctx, dWo, dbo = o.linear_bwd(t["ctx"], lw["o_w"], self._drop(T, f"w2v{li}.attn", pw, dy1, R, D) if pw > 0 else dy1, R)
             G[nm + "self_attn.out_proj.weight"], G[nm + "self_attn.out_proj.bias"] = dWo, dbo
             dqkv = o.new(R, 3 * D, zero=True)
             qp, dqp = t["qkv"].data_ptr(), dqkv.data_ptr()
@@ -445,6 +516,8 @@ class EncoderTrainStep:
             _attn_layer_grads(G, nm + "self_attn.", dWqkv, dbqkv, D)
         self.dbg["w2v_in"] = dx
         # ---- encoder LayerNorm, pos-conv, masked projection, feature LayerNorm
+        if pw > 0:
+            dx = self._drop(T, "w2v.enc", pw, dx, R, D)
         dy0, dge, dbe = o.ln_bwd(T["y0"], P["ln_enc_g"], dx, R)
         G["wav2vec_model.encoder.layer_norm.weight"], G["wav2vec_model.encoder.layer_norm.bias"] = dge, dbe
         dzpos = o.act_bwd(L.ACT_GELU, T["zpos"], dy0, R, D)
@@ -453,6 +526,8 @@ class EncoderTrainStep:
         dxp_m = o.new(R, D, zero=True)
         o.remap(dxp, g.T6a, 0, dxp_m, g.T6a, 0, B, g.T6a, D, g.T6a, seg_len=T["w2v_valid"])
         self.dbg["proj_masked"] = dxp
+        if self.pd["w2v_input"] > 0:
+            dxp_m = self._drop(T, "w2v.input", self.pd["w2v_input"], dxp_m, R, D)
         dfl, dWp, dbp = o.linear_bwd(T["feat_ln"], P["proj_w"], dxp_m, R)
         G["wav2vec_model.post_extract_proj.weight"], G["wav2vec_model.post_extract_proj.bias"] = dWp, dbp
         dfeat, dgf, dbf = o.ln_bwd(T["c"][6], P["ln_feat_g"], dfl, R)
@@ -489,15 +564,16 @@ class EncoderTrainStep:
         B, Mq, D2, esz = g.B, self.M, ENC_DIM, self.o.esz
         RM, R2 = B * Mq, B * g.T2a
         G0, G = G, {}
+        ps, pa = self.pd["shared"], self.pd["act"]
         dmem = d_mem.to(self.dev, F32).transpose(0, 1).contiguous().view(RM, D2)
         dh_enc = o.new(R2, D2, zero=True)
         # ---- memory stage
         for li in reversed(range(MEM_LAYERS)):
             lw, t, nm = P["mem_layers"][li], T["mem"][li], f"interlingua_layers.{li}."
-            db_in = self._ffn_bwd(G, nm, lw, t, dmem, RM, L.ACT_RELU, "b")
+            db_in = self._ffn_bwd(G, nm, lw, t, dmem, RM, L.ACT_RELU, "b", T=T, tag=f"mem{li}", p_out=ps, p_act=pa)
             dmm, dg2, dbt2 = o.ln_bwd(t["mm"], lw["ln2_g"], db_in, RM, dx=dmem.clone())     # residual path + LN2 path
             G[nm + "final_layer_norm.weight"], G[nm + "final_layer_norm.bias"] = dg2, dbt2
-            dctx, dWo, dbo = o.linear_bwd(t["ctx"], lw["o_w"], dmm, RM)
+            dctx, dWo, dbo = o.linear_bwd(t["ctx"], lw["o_w"], self._drop(T, f"mem{li}.attn", ps, dmm, RM, D2) if ps > 0 else dmm, RM)
             G[nm + "self_attn.out_proj.weight"], G[nm + "self_attn.out_proj.bias"] = dWo, dbo
             dq = o.new(RM, D2, zero=True)
             dkv = o.new(R2, 2 * D2, zero=True)
@@ -519,10 +595,10 @@ class EncoderTrainStep:
         G["layer_norm.weight"], G["layer_norm.bias"] = dgo, dbo_
         for li in reversed(range(ENC_LAYERS)):
             lw, t, nm = self._enc_layers(T)[li], T["enc"][li], self._enc_names(T)[li]
-            db_in = self._ffn_bwd(G, nm, lw, t, dx2, R2, L.ACT_RELU, "b")
+            db_in = self._ffn_bwd(G, nm, lw, t, dx2, R2, L.ACT_RELU, "b", T=T, tag=f"enc{li}", p_out=ps, p_act=pa)
             dxm, dg2, dbt2 = o.ln_bwd(t["xm"], lw["ln2_g"], db_in, R2, dx=dx2)
             G[nm + "final_layer_norm.weight"], G[nm + "final_layer_norm.bias"] = dg2, dbt2
-            dctx, dWo, dbo = o.linear_bwd(t["ctx"], lw["o_w"], dxm, R2)
+            dctx, dWo, dbo = o.linear_bwd(t["ctx"], lw["o_w"], self._drop(T, f"enc{li}.attn", ps, dxm, R2, D2) if ps > 0 else dxm, R2)
             G[nm + "self_attn.out_proj.weight"], G[nm + "self_attn.out_proj.bias"] = dWo, dbo
             dqkv = o.new(R2, 3 * D2, zero=True)
             qp, dqp = t["qkv"].data_ptr(), dqkv.data_ptr()
@@ -534,6 +610,8 @@ class EncoderTrainStep:
             G[nm + "self_attn_layer_norm.weight"], G[nm + "self_attn_layer_norm.bias"] = dg1, db1
         for k, v in G.items():
             G0[k] = v if k not in G0 else G0[k] + v
+        if ps > 0:
+            dx2 = self._drop(T, "embed", ps, dx2, R2, D2)
         return dx2
 
     def _enc_layers(self, T):
@@ -642,7 +720,7 @@ class TextTrainPass:
         valid = torch.empty(B, dtype=torch.int32, device=s.dev)
         L.check(o.lib.cst_text_embed(tokens.data_ptr(), lengths.data_ptr(), E.data_ptr(), self.pos.data_ptr(), math.sqrt(ENC_DIM), x2.data_ptr(),
                                      valid.data_ptr(), B, Tn, Tn, ENC_DIM, E.shape[0], o.st()))
-        self.T = {"tokens": tokens}
+        self.T = {"tokens": tokens, "pass": 1}                     # pass 1: its dropout sites draw masks of their own
         return s._shared_memory_fwd(g, self.T, x2, valid)
 
     def backward(self, d_mem, G=None):

@@ -284,6 +284,17 @@ int cst_col2im(const void* dcol, int dcol_dtype, long long M, int k, int stride,
 /* out[seg*out_rps + t + out_off] (+)= scale * in[seg*in_rps + t + in_off] for t < min(seg_valid, seg_len[seg]), else 0 (t < n_rows). */
 int cst_rows_remap(const float* in, long long ldi, int in_rps, int in_off, void* out, int out_dtype, long long ldo, int out_rps, int out_off,
                    int n_seg, int n_rows, int C, int seg_valid, const int32_t* seg_len, int accumulate, float scale, void* stream);
+/* Dropout of the training step.  Replaces F.dropout as called by FairseqDropout (fairseq/modules/fairseq_dropout.py:16-27) at the
+ * elementwise sites of the path (wav2vec2.py:553,830 and the three per-layer dropouts of TransformerSentenceEncoderLayer;
+ * w2v2_transformer_interlingua.py:237; transformer_layer.py dropout_module / activation_dropout_module):
+ *   out[r, c] = (add ? add[r, c] : 0) + x[r, c] * keep(r, c) / (1 - p),  keep = Philox4x32-10(key = *seed, counter = {(r*cols + c)/4, site})
+ *   word (r*cols + c) % 4 >= floor(p * 2^32)   (csrc/philox.cuh; tests/emu.py restates it in numpy, compared bit for bit).
+ * Masks are never stored: the derivative is the same call on the gradient with the same *seed and site.  `seed` is a DEVICE pointer (one
+ * 64-bit value per step) so that a captured CUDA graph draws fresh masks on every replay.  add: fp32 residual (optional); out2: optional
+ * second copy (the GEMM-operand dtype); cols and all row pitches multiples of 4. */
+int cst_dropout(const void* x, int x_dtype, long long ldx, const float* add, long long ldadd, void* out, int out_dtype, long long ldo,
+                void* out2, int out2_dtype, long long ldo2, int rows, int cols, float p, const unsigned long long* seed,
+                unsigned int site, void* stream);
 /* Fused Adam update of one tensor.  Replaces fairseq/optim/adam.py:157-224 (fp32 parameters and moments; the gradient is fp32 or the bf16
  * wire format of the all-reduce): m = b1 m + (1-b1) g', v = b2 v + (1-b2) g'^2 with g' = grad_scale * g; p -= weight_decay*lr*p;
  * p -= step_size * m / (sqrt(v) + eps), step_size = lr * sqrt(1 - b2^t) / (1 - b1^t) formed by the caller.  dyn (optional, device

@@ -121,13 +121,24 @@ def pos_conv_weight(sd):
     return v * (g / v.norm(dim=(0, 1), keepdim=True))
 
 
+DROPOUT_HOOK = None
+
+
+def _dropout(tag, x):
+    """A dropout site of the training-mode forward (FairseqDropout / F.dropout, fairseq/modules/fairseq_dropout.py:16-27).  The oracle is
+    the eval-mode restatement: the identity unless a test installs DROPOUT_HOOK(tag, x) -> x * mask / (1 - p) to replay the masks the
+    CUDA path drew (tests/test_train_emulated.py, tests/test_gpu_backward.py)."""
+    return x if DROPOUT_HOOK is None else DROPOUT_HOOK(tag, x)
+
+
 def w2v_layer(sd, i, x, pad_mask):
-    """TransformerSentenceEncoderLayer.forward post-LN branch, wav2vec2.py:937-957. x [B,T,768]."""
+    """TransformerSentenceEncoderLayer.forward post-LN branch, wav2vec2.py:937-957. x [B,T,768].
+    Dropout sites: dropout1 after the attention, dropout3 after fc2 (dropout2 = activation_dropout is 0 in wav2vec2 base)."""
     P = f"wav2vec_model.encoder.layers.{i}."
-    a = mha(sd, P + "self_attn.", x, x, 12, key_padding_mask=pad_mask)
+    a = _dropout(f"w2v{i}.attn", mha(sd, P + "self_attn.", x, x, 12, key_padding_mask=pad_mask))
     x = _ln(x + a, sd, P + "self_attn_layer_norm")
     h = _gelu(F.linear(x, sd[P + "fc1.weight"], sd[P + "fc1.bias"]))
-    h = F.linear(h, sd[P + "fc2.weight"], sd[P + "fc2.bias"])
+    h = _dropout(f"w2v{i}.ffn", F.linear(h, sd[P + "fc2.weight"], sd[P + "fc2.bias"]))
     return _ln(x + h, sd, P + "final_layer_norm")
 
 
@@ -143,6 +154,7 @@ def wav2vec_extract_features(sd, wave, src_lengths, stages=None):
     x = _ln(feats.transpose(1, 2), sd, W + "layer_norm")            # :539-540
     fmask = frame_padding_mask(src_lengths, x.size(1))             # :543-548
     x = F.linear(x, sd[W + "post_extract_proj.weight"], sd[W + "post_extract_proj.bias"])  # :550-551
+    x = _dropout("w2v.input", x)                                    # dropout_input :553
     x = x.masked_fill(fmask.unsqueeze(-1), 0.0)                     # :820-821
     if stages is not None:
         stages["proj_masked"] = x
@@ -151,6 +163,7 @@ def wav2vec_extract_features(sd, wave, src_lengths, stages=None):
                   padding=128 // 2, groups=16)[:, :, :-1]           # SamePad same_pad.py:10-18
     x = x + _gelu(pc).transpose(1, 2)                               # :823-825
     x = _ln(x, sd, W + "encoder.layer_norm")                        # :827-828 (layer_norm_first=False)
+    x = _dropout("w2v.enc", x)                                      # F.dropout :830
     if stages is not None:
         stages["w2v_in"] = x
     for i in range(12):
@@ -174,14 +187,20 @@ def conv1d_subsampler(sd, x, lens):
     return y.transpose(1, 2), subsampler_lengths(lens)
 
 
+def _layer_tag(P):
+    kind, idx = P.rstrip(".").rsplit(".", 1)
+    return {"transformer_layers": "enc", "interlingua_layers": "mem", "audio_exclusive_layers": "aenc"}[kind] + idx
+
+
 def encoder_layer(sd, P, x, pad_mask, attn_bias=None):
     """TransformerEncoderLayer.forward pre-LN (normalize_before=True), ReLU,
     fairseq/modules/transformer_layer.py:105-155. x [B,T,512]."""
+    tag = _layer_tag(P)
     h = _ln(x, sd, P + "self_attn_layer_norm")
-    x = x + mha(sd, P + "self_attn.", h, h, 8, key_padding_mask=pad_mask, attn_bias=attn_bias)
+    x = x + _dropout(tag + ".attn", mha(sd, P + "self_attn.", h, h, 8, key_padding_mask=pad_mask, attn_bias=attn_bias))   # dropout_module
     h = _ln(x, sd, P + "final_layer_norm")
-    h = torch.relu(F.linear(h, sd[P + "fc1.weight"], sd[P + "fc1.bias"]))
-    return x + F.linear(h, sd[P + "fc2.weight"], sd[P + "fc2.bias"])
+    h = _dropout(tag + ".act", torch.relu(F.linear(h, sd[P + "fc1.weight"], sd[P + "fc1.bias"])))     # activation_dropout_module
+    return x + _dropout(tag + ".ffn", F.linear(h, sd[P + "fc2.weight"], sd[P + "fc2.bias"]))          # dropout_module
 
 
 def memory_stage_literal(sd, h_enc):
@@ -209,10 +228,10 @@ def memory_stage(sd, h_enc):
         P = f"interlingua_layers.{l}."
         q_in = _ln(mem, sd, P + "self_attn_layer_norm")
         kv_in = _ln(h_enc, sd, P + "self_attn_layer_norm")
-        y = mem + mha(sd, P + "self_attn.", q_in, kv_in, 8)
+        y = mem + _dropout(f"mem{l}.attn", mha(sd, P + "self_attn.", q_in, kv_in, 8))
         h = _ln(y, sd, P + "final_layer_norm")
-        h = torch.relu(F.linear(h, sd[P + "fc1.weight"], sd[P + "fc1.bias"]))
-        mem = y + F.linear(h, sd[P + "fc2.weight"], sd[P + "fc2.bias"])
+        h = _dropout(f"mem{l}.act", torch.relu(F.linear(h, sd[P + "fc1.weight"], sd[P + "fc1.bias"])))
+        mem = y + _dropout(f"mem{l}.ffn", F.linear(h, sd[P + "fc2.weight"], sd[P + "fc2.bias"]))
     return mem
 
 
@@ -230,6 +249,7 @@ def encoder_forward(sd, wave, src_lengths, stages=None, literal_memory=False):
     if stages is not None:
         stages["sub_out"] = x
         stages["frame_mask"], stages["w2v_len"], stages["sub_len"] = fmask, lens, lens2
+    x = _dropout("embed", x)                                                      # dropout_module :237
     for i in range(6):
         x = encoder_layer(sd, f"transformer_layers.{i}.", x, pad)                 # :240-242
     h_enc = _ln(x, sd, "layer_norm")                                              # :254-255
@@ -286,6 +306,7 @@ def encoder_forward_text(sd, src_tokens, src_lengths, stages=None):
     x = math.sqrt(512) * sd["text_embed_tokens.weight"][src_tokens] + sinusoidal_table(T + 2)[positions]
     if stages is not None:
         stages["text_in"] = x
+    x = _dropout("embed", x)                                                      # dropout_module :237
     for i in range(6):
         x = encoder_layer(sd, f"transformer_layers.{i}.", x, pad)
     h_enc = _ln(x, sd, "layer_norm")

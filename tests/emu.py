@@ -25,6 +25,7 @@ def _mem(ptr, n, dtype=np.float32):
 class EmuLib:
     def __init__(self):
         self.calls = []
+        self.dropout_log = []
 
     def cst_wave_i16_to_f32(self, src, dst, n, stream):
         _mem(dst, n)[:] = _mem(src, n, np.int16).astype(np.float32) * np.float32(1.0 / 32768.0)
@@ -599,3 +600,64 @@ EmuLib.cst_rows_remap = _rows_remap
 EmuLib.cst_conv0_bwd = _conv0_bwd
 EmuLib.cst_embed_bwd = _embed_bwd
 EmuLib.cst_adam_step = _adam_step
+
+
+# ---- dropout: the numpy statement of csrc/philox.cuh (Philox4x32-10, key = seed, counter = {group lo, group hi, site, 0}) -------------
+def philox4x32_10(seed, group, site):
+    """group: uint64 array -> uint32 array [..., 4]"""
+    group = np.asarray(group, dtype=np.uint64)
+    m32 = np.uint64(0xFFFFFFFF)
+    c0, c1 = group & m32, group >> np.uint64(32)
+    c2, c3 = np.full_like(c0, np.uint64(site)), np.zeros_like(c0)
+    k0, k1 = np.uint64(seed & 0xFFFFFFFF), np.uint64((seed >> 32) & 0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = np.uint64(0xD2511F53) * c0, np.uint64(0xCD9E8D57) * c2
+        c0, c1, c2, c3 = (p1 >> np.uint64(32)) ^ c1 ^ k0, p1 & m32, (p0 >> np.uint64(32)) ^ c3 ^ k1, p0 & m32
+        k0, k1 = (k0 + np.uint64(0x9E3779B9)) & m32, (k1 + np.uint64(0xBB67AE85)) & m32
+    return np.stack((c0, c1, c2, c3), -1).astype(np.uint32)
+
+
+def dropout_keep(seed, site, n_elements, p):
+    """keep mask (bool [n_elements]) of elements 0 .. n-1 of one dropout site; n_elements % 4 == 0"""
+    assert n_elements % 4 == 0
+    words = philox4x32_10(seed, np.arange(n_elements // 4, dtype=np.uint64), site).reshape(-1)
+    return words >= np.uint32(min(int(float(np.float32(p)) * 4294967296.0), 0xFFFFFFFF))
+
+
+def _dropout(self, x, x_dtype, ldx, add, ldadd, out, out_dtype, ldo, out2, out2_dtype, ldo2, rows, cols, p, seed, site, stream):
+    assert x_dtype == F32 and out_dtype == F32 and (not out2 or out2_dtype == F32) and cols % 4 == 0
+    sd = int(_mem(seed, 1, np.uint64)[0])
+    keep = torch.from_numpy(dropout_keep(sd, site, rows * cols, p)).view(rows, cols)
+    scale = np.float32(1.0) / (np.float32(1.0) - np.float32(p))
+    val = torch.where(keep, _view(x, rows, cols, ldx) * float(scale), torch.zeros(()))
+    if add:
+        val = val + _view(add, rows, cols, ldadd)
+    _view(out, rows, cols, ldo, copy=False)[:] = val
+    if out2:
+        _view(out2, rows, cols, ldo2, copy=False)[:] = val
+    self.calls.append("dropout")
+    self.dropout_log.append((sd, site, rows, cols, float(p)))
+    return 0
+
+
+EmuLib.cst_dropout = _dropout
+
+
+def oracle_dropout_hook(step, pass_id, geom, p_of):
+    """DROPOUT_HOOK for oracle/chimera_oracle.py: the masks an `EncoderTrainStep` drew, re-created from (seed, site) with the numpy
+    Philox above and mapped from the kernel's padded row space [B * rows_per_seg, C] onto the oracle's [B, T, C] tensors.
+    geom(tag) -> rows_per_seg of that site, p_of(tag) -> its probability.  -> (hook, list of tags it was called with)."""
+    seed = int(step.seed_dev.item())
+    used = []
+
+    def hook(tag, x):
+        p = p_of(tag)
+        if p <= 0:
+            return x
+        B, Tn, Cd = x.shape
+        rps = geom(tag)
+        site = step._sites[(pass_id, tag)]
+        keep = torch.from_numpy(dropout_keep(seed, site, B * rps * Cd, p)).view(B, rps, Cd)[:, :Tn]
+        used.append(tag)
+        return x * keep.to(x.dtype) * float(np.float32(1.0) / (np.float32(1.0) - np.float32(p)))
+    return hook, used

@@ -361,3 +361,70 @@ def test_layerdrop_skips_layers_like_the_reference():
     rng = np.random.RandomState(0)
     want = frozenset(i for i, u in enumerate(np.random.RandomState(0).random_sample(12)) if not u > 0.3)
     assert EncoderTrainStep.sample_layerdrop(0.3, rng) == want and EncoderTrainStep.sample_layerdrop(0.0, rng) == frozenset()
+
+
+def test_dropout_kernel_matches_the_numpy_philox_bit_for_bit():
+    """cst_dropout: keep mask = Philox4x32-10(seed, site, element) >= p * 2^32 exactly as tests/emu.py states it; out = add + x * keep /
+    (1 - p) in fp32 and from / to bf16, second (operand) copy, and the same call on a gradient is the derivative."""
+    from emu import dropout_keep
+    o = _Ops(torch.device(DEV))
+    g = torch.Generator().manual_seed(3)
+    seed = torch.tensor([0x1234567ABCDEF], dtype=torch.int64, device=DEV)
+    for rows, cols, p, site in ((37, 512, 0.1, 0), (300, 768, 0.25, 41), (5, 2048, 0.5, 7)):
+        x, add = torch.randn(rows, cols, generator=g), torch.randn(rows, cols, generator=g)
+        keep = torch.from_numpy(dropout_keep(int(seed.item()), site, rows * cols, p)).view(rows, cols)
+        scale = 1.0 / (1.0 - p)
+        out, lp = o.dropout(x.to(DEV), rows, cols, p, seed, site, add=add.to(DEV), lp_dtype=torch.bfloat16)
+        want = add + torch.where(keep, x * torch.tensor(scale, dtype=torch.float32), torch.zeros(()))
+        ones = o.dropout(torch.ones(rows, cols, device=DEV), rows, cols, p, seed, site)
+        assert torch.equal(ones.cpu() != 0, keep)                                     # the mask, bit for bit
+        assert rel_l2(out.cpu(), want) < 1e-6 and torch.equal(lp.cpu(), out.cpu().to(torch.bfloat16))
+        xb = x.to(torch.bfloat16)
+        outb = o.dropout(xb.to(DEV), rows, cols, p, seed, site, out_dtype=torch.bfloat16)
+        assert torch.equal(outb.cpu() != 0, keep & (xb != 0))
+        assert rel_l2(outb.cpu().float(), torch.where(keep, xb.float() * scale, torch.zeros(()))) < 5e-3
+        assert abs(float(keep.float().mean()) - (1 - p)) < 0.02
+    # another seed / another site: other masks
+    a = o.dropout(torch.ones(64, 512, device=DEV), 64, 512, 0.5, seed, 1)
+    b = o.dropout(torch.ones(64, 512, device=DEV), 64, 512, 0.5, seed, 2)
+    c = o.dropout(torch.ones(64, 512, device=DEV), 64, 512, 0.5, seed + 1, 1)
+    assert not torch.equal(a, b) and not torch.equal(a, c)
+
+
+def test_encoder_step_with_dropout_matches_autograd_with_the_same_masks():
+    """The training recipe's elementwise dropout (p = 0.1 everywhere, dropout_input 0.1): forward masks are regenerated in the backward
+    pass; autograd through the oracle with the same masks installed at the reference's dropout sites agrees <= 1e-4 per tensor (fp32);
+    the bf16 mode runs the same sites (whole-gradient error at its usual level)."""
+    from emu import oracle_dropout_hook
+    torch.set_num_threads(8)
+    lens = [6000, 4500]
+    sd = synth.make_state_dict(seed=0, interlingua_length=16, dead_heads=False)
+    wave, tl = synth.make_waveforms(lens, seed=31)
+    R = torch.randn(16, 2, 512, generator=torch.Generator().manual_seed(1))
+    kw = dict(dropout=0.1, w2v_dropout=0.1, w2v_dropout_input=0.1, seed=5)
+    for dtype, tol_mem, tol in ((torch.float32, 1e-5, 1e-4), (torch.bfloat16, 1.5e-2, None)):
+        step = EncoderTrainStep(sd, 2, wave.shape[1], device=DEV, feature_grad_mult=1.0, dtype=dtype, **kw)
+        g = step.g
+        mem, G = step.forward_backward(wave, tl, R)
+        torch.cuda.synchronize()
+        hook, used = oracle_dropout_hook(step, 0, lambda tag: g.T6a if tag.startswith("w2v") else 16 if tag.startswith("mem") else g.T2a,
+                                         lambda tag: 0.1)
+        O.DROPOUT_HOOK = hook
+        try:
+            ref_mem, ref, _ = _oracle_grads(sd, wave, tl, R, _relu_masks_of(step))
+        finally:
+            O.DROPOUT_HOOK = None
+        assert len(set(used)) == 2 + 24 + 1 + 18 + 9
+        assert rel_l2(mem.cpu().float(), ref_mem) < tol_mem
+        num = den = 0.0
+        bad = {}
+        for k, v in G.items():
+            if k.endswith("k_proj.bias"):
+                continue
+            d = (v.cpu().float().reshape(ref[k].shape) - ref[k]).double()
+            num += float((d * d).sum()); den += float((ref[k].double() ** 2).sum())
+            e = rel_l2(v.cpu().float().reshape(ref[k].shape), ref[k])
+            if tol is not None and not e < tol:
+                bad[k] = e
+        assert not bad, bad
+        assert (num / den) ** 0.5 < (1e-4 if tol is not None else 2.5e-2), (num / den) ** 0.5

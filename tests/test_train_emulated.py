@@ -14,7 +14,7 @@ from chimera_st_b200 import synth, _lib as L
 from chimera_st_b200.train import EncoderTrainStep, TextTrainPass, FusedAdam
 from oracle import chimera_oracle as O, adam_oracle
 from conftest import GOLDEN, rel_l2
-from emu import EmuLib
+from emu import EmuLib, oracle_dropout_hook
 import pytest
 
 
@@ -175,3 +175,43 @@ def test_split_k_weight_gradient_and_strided_window_operand():
     W, res = torch.randn(N, K, generator=g), torch.randn(rows, K, generator=g)
     dx, dW2, db = o.linear_bwd(x, W, dy, rows, dx_residual=res)
     assert rel_l2(dx, dy @ W + res) < 1e-6 and rel_l2(dW2, dy.T @ x) < 1e-6 and rel_l2(db, dy.sum(0)) < 1e-6
+
+
+def test_emulated_dropout_replays_in_the_backward_pass():
+    """Elementwise dropout of the training recipe: the forward's masks are regenerated (never stored) in the backward pass.  Autograd
+    through the oracle with THE SAME masks installed at the reference's dropout sites gives the same memories and gradients."""
+    torch.set_num_threads(8)
+    lens = [4700, 3300]
+    sd = synth.make_state_dict(seed=0, interlingua_length=8, dead_heads=False)
+    wave, tl = synth.make_waveforms(lens, seed=31)
+    R = torch.randn(8, 2, 512, generator=torch.Generator().manual_seed(1))
+    emu = EmuLib()
+    step = EncoderTrainStep(sd, 2, wave.shape[1], device="cpu", feature_grad_mult=1.0, lib=emu, dropout=0.1, activation_dropout=0.2,
+                            w2v_dropout=0.1, w2v_dropout_input=0.15, seed=77)
+    g = step.g
+    mem, G = step.forward_backward(wave, tl, R)
+    n_sites = 2 + 2 * 12 + 1 + 3 * 6 + 3 * 3
+    assert len(step._sites) == n_sites and emu.calls.count("dropout") == 2 * n_sites          # every site once forward, once backward
+    fwd, bwd = emu.dropout_log[:n_sites], emu.dropout_log[n_sites:]
+    assert sorted(fwd) == sorted(bwd)                                                         # same (seed, site, shape, p) both ways
+
+    def p_of(tag):
+        return 0.15 if tag == "w2v.input" else 0.2 if tag.endswith(".act") else 0.1
+
+    def geom(tag):
+        return g.T6a if tag.startswith("w2v") else 8 if tag.startswith("mem") else g.T2a
+    hook, used = oracle_dropout_hook(step, 0, geom, p_of)
+    O.DROPOUT_HOOK = hook
+    try:
+        ref_mem, ref = _autograd(sd, lambda s: O.encoder_forward(s, wave, tl)[0], R, _masks(step.T, g.B, g.T2a, g.T2, 8))
+    finally:
+        O.DROPOUT_HOOK = None
+    assert len(set(used)) == n_sites
+    assert rel_l2(mem, ref_mem) < 1e-5
+    _compare(G, ref)
+    # it IS dropout: the memories differ from the dropout-free ones, and a new seed draws new masks
+    mem0 = EncoderTrainStep(sd, 2, wave.shape[1], device="cpu", lib=EmuLib()).forward(wave, tl)
+    assert rel_l2(mem, mem0) > 1e-2
+    step.next_dropout_seed()
+    assert int(step.seed_dev.item()) == 78
+    assert rel_l2(step.forward(wave, tl), mem) > 1e-2
