@@ -298,10 +298,32 @@ def c5_quick(rank, world, steps=5, dtype=torch.bfloat16, comm_dtype=torch.bfloat
     t_opt = D.reduce_max(e0.elapsed_time(e1), "cuda") / steps
     out["with_adam_update"] = {"ms_per_step": round(t_opt, 3), "audio_s_per_s": round(total_audio / (t_opt * 1e-3), 1),
                                "loss_before": loss0, "loss_after_%d_updates" % (3 + steps): float(gs.loss)}
+    # ... and the same step with the recipe's elementwise dropout (p = 0.1 at every site; masks regenerated, not stored)
+    final_loss, n_grad = float(gs.loss), sum(n for _, n in gs.names)
+    try:
+        gs = None
+        step_d = EncoderTrainStep(sd, B, Lw, device="cuda", feature_grad_mult=0.1, dtype=dtype, dropout=0.1, w2v_dropout=0.1,
+                                  w2v_dropout_input=0.1)
+        gs = GraphedTrainStep(step_d, wave, lens, loss_fn)
+        gs.reducer = ddp.GradAllReducer(gs.names, world_size=world, bucket_bytes=bucket_mb << 20, comm_dtype=comm_dtype)
+        for _ in range(3):
+            gs.run()
+        torch.cuda.synchronize(); D.barrier(); torch.cuda.synchronize()
+        e0.record()
+        for _ in range(steps):
+            gs.run()
+        e1.record()
+        torch.cuda.synchronize(); D.barrier()
+        t_d = D.reduce_max(e0.elapsed_time(e1), "cuda") / steps
+        out["with_dropout_0.1"] = {"ms_per_step": round(t_d, 3), "audio_s_per_s": round(total_audio / (t_d * 1e-3), 1),
+                                   "sites": len(step_d._sites), "note": "elementwise sites; attention-probability dropout not built"}
+        del step_d
+    except Exception as e:                                         # a secondary figure must not take the headline line down
+        out["with_dropout_0.1"] = {"error": repr(e)[:200]}
     out.update({"workload": "c5: training step (forward + contrastive head + backward + gradient all-reduce), B=%d x %d samples per GPU, bf16" % (B, Lw),
                 "audio_s_per_s": round(total_audio / (out["ms_per_step"] * 1e-3), 1), "n_gpus": world,
-                "allreduce_bytes_per_step": sum(n for _, n in gs.names) * (2 if comm_dtype is not None else 4),
-                "allreduce_exposed_ms": round(out["ms_per_step"] - out["ms_per_step_without_allreduce"], 3), "loss": float(gs.loss)})
+                "allreduce_bytes_per_step": n_grad * (2 if comm_dtype is not None else 4),
+                "allreduce_exposed_ms": round(out["ms_per_step"] - out["ms_per_step_without_allreduce"], 3), "loss": final_loss})
     del gs, step
     torch.cuda.empty_cache()
     return out
@@ -387,7 +409,10 @@ def run_c5(args, rank, world, local_rank, cores):
                        "B=%d x %d samples (%.1f M samples, %.1f audio-s) per GPU" % (B, Lw, B * Lw / 1e6, audio_per_step),
            "interlingua_length": M, "parallelism": "data-parallel dp%d, bucketed gradient all-reduce (%s buckets of %d MB) overlapped with "
                                                    "the backward segments" % (world, args.comm_dtype, args.bucket_mb),
-           "dropout": 0.0, "layerdrop": 0.0, "feature_grad_mult": 0.1,
+           "dropout": (0.0 if not getattr(args, "dropout", 0.0) else
+                       "%.2f at every elementwise site of the recipe (Philox masks regenerated in the backward pass); dropout of the "
+                       "attention probabilities is not built" % args.dropout),
+           "layerdrop": 0.0, "feature_grad_mult": 0.1,
            "l2": "tape (> 4 GB of activations per step) exceeds the 126 MB L2; no explicit flush",
            "precision": ("bf16 GEMM operands (fp16 in the conv-stack forward), fp32 accumulation / gradients / norms / softmax"
                          if dt_name == "bf16" else "fp32 FFMA")}
@@ -427,7 +452,9 @@ def run_c5(args, rank, world, local_rank, cores):
     from chimera_st_b200 import ddp, losses
     dtype = torch.bfloat16 if dt_name == "bf16" else torch.float32
     sd = synth.make_state_dict(seed=0, interlingua_length=M, dead_heads=False)
-    step = EncoderTrainStep(sd, B, Lw, device="cuda", feature_grad_mult=0.1, dtype=dtype)
+    pdrop = float(getattr(args, "dropout", 0.0))
+    step = EncoderTrainStep(sd, B, Lw, device="cuda", feature_grad_mult=0.1, dtype=dtype, dropout=pdrop, w2v_dropout=pdrop,
+                            w2v_dropout_input=pdrop)
     host_w, host_l = host_batch([Lw] * B, seed=1000 * rank)
     wave, lens = host_w.cuda(), host_l.cuda()
     text_mem = torch.randn(M, B, 512, generator=torch.Generator().manual_seed(7 + rank)).cuda()
@@ -626,6 +653,8 @@ def main():
                     help="c5 = BASELINE configs[4]: training forward + backward of the path with the DDP gradient all-reduce")
     ap.add_argument("--comm-dtype", default="bf16", choices=["bf16", "fp32"], help="c5: dtype of the gradient buckets on the wire")
     ap.add_argument("--bucket-mb", type=int, default=32, help="c5: gradient bucket size")
+    ap.add_argument("--dropout", type=float, default=0.0,
+                    help="c5: probability of the recipe's elementwise dropouts (train-en2any-ST.sh uses 0.1); 0 = the parity configuration")
     ap.add_argument("--utts", type=int, default=512)
     ap.add_argument("--max-tokens", type=int, default=2000000,
                     help="c3 token budget per batch in samples (default: the reference's --max-tokens 2000000, "

@@ -824,6 +824,8 @@ class GraphedTrainStep:
 
     def run(self):
         """-> loss (device scalar).  `self.grads`: local gradients; `self.reduced`: all-reduced ones when a reducer is attached."""
+        if any(p > 0 for p in self.step.pd.values()):
+            self.step.next_dropout_seed()                          # the captured kernels read the seed from the device: fresh masks per replay
         self.graphs[0].replay()
         for gi, part in zip(self.graphs[1:], self.seg_grads):
             gi.replay()
