@@ -298,7 +298,7 @@ def c5_quick(rank, world, steps=5, dtype=torch.bfloat16, comm_dtype=torch.bfloat
     t_opt = D.reduce_max(e0.elapsed_time(e1), "cuda") / steps
     out["with_adam_update"] = {"ms_per_step": round(t_opt, 3), "audio_s_per_s": round(total_audio / (t_opt * 1e-3), 1),
                                "loss_before": loss0, "loss_after_%d_updates" % (3 + steps): float(gs.loss)}
-    # ... and the same step with the recipe's elementwise dropout (p = 0.1 at every site; masks regenerated, not stored)
+    # ... and the same step with the recipe's dropout (p = 0.1 at every site incl. the attention probabilities; masks regenerated, not stored)
     final_loss, n_grad = float(gs.loss), sum(n for _, n in gs.names)
     try:
         gs = None
@@ -316,7 +316,7 @@ def c5_quick(rank, world, steps=5, dtype=torch.bfloat16, comm_dtype=torch.bfloat
         torch.cuda.synchronize(); D.barrier()
         t_d = D.reduce_max(e0.elapsed_time(e1), "cuda") / steps
         out["with_dropout_0.1"] = {"ms_per_step": round(t_d, 3), "audio_s_per_s": round(total_audio / (t_d * 1e-3), 1),
-                                   "sites": len(step_d._sites), "note": "elementwise sites; attention-probability dropout not built"}
+                                   "sites": len(step_d._sites), "note": "elementwise sites + attention probabilities (materialised attention forward)"}
         del step_d
     except Exception as e:                                         # a secondary figure must not take the headline line down
         out["with_dropout_0.1"] = {"error": repr(e)[:200]}
@@ -410,8 +410,9 @@ def run_c5(args, rank, world, local_rank, cores):
            "interlingua_length": M, "parallelism": "data-parallel dp%d, bucketed gradient all-reduce (%s buckets of %d MB) overlapped with "
                                                    "the backward segments" % (world, args.comm_dtype, args.bucket_mb),
            "dropout": (0.0 if not getattr(args, "dropout", 0.0) else
-                       "%.2f at every elementwise site of the recipe (Philox masks regenerated in the backward pass); dropout of the "
-                       "attention probabilities is not built" % args.dropout),
+                       "%.2f at every site of the recipe: elementwise dropouts, dropout_input and the attention probabilities (Philox masks "
+                       "regenerated in the backward pass, never stored; layers with attention dropout run the materialised attention on "
+                       "batched tcgen05 GEMMs instead of the flash kernel)" % args.dropout),
            "layerdrop": 0.0, "feature_grad_mult": 0.1,
            "l2": "tape (> 4 GB of activations per step) exceeds the 126 MB L2; no explicit flush",
            "precision": ("bf16 GEMM operands (fp16 in the conv-stack forward), fp32 accumulation / gradients / norms / softmax"
@@ -654,7 +655,7 @@ def main():
     ap.add_argument("--comm-dtype", default="bf16", choices=["bf16", "fp32"], help="c5: dtype of the gradient buckets on the wire")
     ap.add_argument("--bucket-mb", type=int, default=32, help="c5: gradient bucket size")
     ap.add_argument("--dropout", type=float, default=0.0,
-                    help="c5: probability of the recipe's elementwise dropouts (train-en2any-ST.sh uses 0.1); 0 = the parity configuration")
+                    help="c5: probability of the recipe's dropouts (train-en2any-ST.sh uses 0.1); 0 = the parity configuration")
     ap.add_argument("--utts", type=int, default=512)
     ap.add_argument("--max-tokens", type=int, default=2000000,
                     help="c3 token budget per batch in samples (default: the reference's --max-tokens 2000000, "

@@ -114,6 +114,11 @@ _SIGS = {
                           [C.c_void_p, C.c_void_p]),
     "cst_attention_bwd_tc_ws_bytes": (C.c_longlong, [C.c_int] * 4),
     "cst_attention_bwd_tc": (C.c_int, [C.c_void_p] * 7 + [C.c_longlong] * 5 + [C.c_int] * 6 + [C.c_void_p] * 3),
+    "cst_attention_dropout_fwd_ws_bytes": (C.c_longlong, [C.c_int] * 4),
+    "cst_attention_dropout_fwd": (C.c_int, [C.c_void_p] * 3 + [C.c_int, C.c_void_p, C.c_int] + [C.c_longlong] * 3 + [C.c_int] * 6
+                                  + [C.c_void_p, C.c_float, C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p]),
+    "cst_attention_bwd_tc_dropout": (C.c_int, [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 4 + [C.c_longlong] * 5 + [C.c_int] * 6
+                                     + [C.c_void_p, C.c_float, C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p]),
     "cst_col2im": (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
     "cst_rows_remap": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_int,
                                  C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_void_p]),

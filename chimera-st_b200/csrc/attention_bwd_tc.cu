@@ -8,7 +8,14 @@
 //   dQ = dS K, dK = dS^T Q, dV = P^T dO                      (3 GEMMs, N = 64, reduction over the padded key / query axis)
 // Operands are re-laid per (utterance, head) as dense [T, 64] / [64, T] bf16 panels by head_pack_kernel; the three dense fp32
 // results are scattered back into the strided dq / dk / dv buffers by head_unpack_kernel.
+//
+// Dropout of the attention probabilities (the training recipe's attention_dropout; F.multi_head_attention_forward applies F.dropout
+// to softmax(S) before the product with V): with p > 0 the FORWARD runs here too (cst_attention_dropout_fwd: S GEMM, one
+// softmax + dropout kernel writing Pd = P o keep / (1 - p), Pd V GEMM) and the backward uses the same masks:
+//   dV = Pd^T dO,   dP = (dO V^T) o keep / (1 - p),   D = rowsum(P o dP),   dS = P o (dP - D)
+// keep(b, h, i, j) = Philox word of element ((b*H + h)*Tqp + i)*Tkp + j (philox.cuh), regenerated, never stored.
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace cst {
 
@@ -54,6 +61,83 @@ __global__ void __launch_bounds__(256) head_unpack_kernel(const float* __restric
   const float4 v = load4(src + (((long long)b * H + h) * Tp + t) * 64 + d);
   store4(out + ((long long)b * rows_per_seg + t) * ld + h * 64 + d, v);
 }
+// the same scatter into a bf16 tensor (the attention output of the 16-bit training forward)
+__global__ void __launch_bounds__(256) head_unpack_bf16_kernel(const float* __restrict__ src, int Tp, int n, int H,
+                                                               __nv_bfloat16* __restrict__ out, long long ld, int rows_per_seg) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int t = blockIdx.x * 16 + (threadIdx.x >> 4), d = (threadIdx.x & 15) * 4;
+  if (t >= n) return;
+  const float4 v = load4(src + (((long long)b * H + h) * Tp + t) * 64 + d);
+  store4(out + ((long long)b * rows_per_seg + t) * ld + h * 64 + d, v);
+}
+
+// keep / (1 - p) factors of 4 consecutive score elements e .. e+3 (e % 4 == 0); seed == nullptr: no dropout
+struct Keep4 { float x, y, z, w; };
+__device__ __forceinline__ Keep4 keep4(const unsigned long long* seed, uint32_t site, long long e, uint32_t thresh, float scale) {
+  if (seed == nullptr) return Keep4{1.f, 1.f, 1.f, 1.f};
+  const Philox4 r = philox4x32_10(*seed, (unsigned long long)e >> 2, site);
+  return Keep4{r.x >= thresh ? scale : 0.f, r.y >= thresh ? scale : 0.f, r.z >= thresh ? scale : 0.f, r.w >= thresh ? scale : 0.f};
+}
+__device__ __forceinline__ float keep1(const unsigned long long* seed, uint32_t site, long long e, uint32_t thresh, float scale) {
+  if (seed == nullptr) return 1.f;
+  const Philox4 r = philox4x32_10(*seed, (unsigned long long)e >> 2, site);
+  const int w = (int)(e & 3);
+  const uint32_t v = w == 0 ? r.x : w == 1 ? r.y : w == 2 ? r.z : r.w;
+  return v >= thresh ? scale : 0.f;
+}
+
+// Forward softmax + dropout: Pd[bh][r][c] = softmax_c(S[bh][r][c]) * keep / (1 - p) in bf16 (columns >= klen and rows >= n_q: 0).
+// One CTA = 32 query rows of one (utterance, head); a warp computes max and sum of 4 rows, then every thread forms 8 columns.
+__global__ void __launch_bounds__(256) attn_fwd_softmax_dropout_kernel(const float* __restrict__ S, int Tqp, int Tkp, int n_q, int n_kv,
+                                                                       const int32_t* __restrict__ kv_len, int H,
+                                                                       __nv_bfloat16* __restrict__ Pd,
+                                                                       const unsigned long long* __restrict__ seed, uint32_t site,
+                                                                       uint32_t thresh, float scale) {
+  __shared__ float st_m[32], st_il[32];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int r0 = blockIdx.x * 32;
+  const long long bh = blockIdx.y;
+  const int b = (int)(bh / H);
+  int klen = n_kv;
+  if (kv_len != nullptr) klen = min(klen, kv_len[b]);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* Sb = S + bh * (long long)Tqp * Tkp;
+  for (int rr = 0; rr < 4; ++rr) {
+    const int r = warp * 4 + rr;
+    const float* srow = Sb + (long long)(r0 + r) * Tkp;
+    float mx = -INFINITY;
+    for (int c = lane; c < klen; c += 32) mx = fmaxf(mx, srow[c]);
+    mx = warp_max(mx);
+    float l = 0.f;
+    for (int c = lane; c < klen; c += 32) l += expf(srow[c] - mx);
+    l = warp_sum(l);
+    if (lane == 0) {
+      const bool live = (r0 + r) < n_q && l > 0.f;
+      st_m[r] = mx; st_il[r] = live ? 1.0f / l : 0.f;
+    }
+  }
+  __syncthreads();
+  __nv_bfloat16* Pb = Pd + bh * (long long)Tqp * Tkp;
+  const int r = threadIdx.x >> 3, cc = (threadIdx.x & 7) * 8;
+  const float m = st_m[r], il = st_il[r];
+  for (int c0 = 0; c0 < Tkp; c0 += 64) {
+    const long long e = (bh * Tqp + r0 + r) * (long long)Tkp + c0 + cc;
+    const float* srow = Sb + (long long)(r0 + r) * Tkp + c0 + cc;
+    const float4 s0 = load4(srow), s1 = load4(srow + 4);
+    const Keep4 k0 = keep4(seed, site, e, thresh, scale), k1 = keep4(seed, site, e + 4, thresh, scale);
+    const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    const float kv[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+    float pv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) pv[i] = (c0 + cc + i < klen) ? expf(sv[i] - m) * il * kv[i] : 0.f;
+    uint4 u;
+    u.x = pack_bf16x2(pv[0], pv[1]); u.y = pack_bf16x2(pv[2], pv[3]); u.z = pack_bf16x2(pv[4], pv[5]); u.w = pack_bf16x2(pv[6], pv[7]);
+    *reinterpret_cast<uint4*>(Pb + (long long)(r0 + r) * Tkp + c0 + cc) = u;
+  }
+}
 
 // One CTA = 32 query rows of one (utterance, head).  Phase A: a warp owns 4 rows and computes max, sum of exponentials and
 // D = sum_j P_ij dP_ij (two sweeps over the row; the rows just came out of the GEMMs and are re-read through L1/L2).  Phase B: per
@@ -62,7 +146,10 @@ __global__ void __launch_bounds__(256) head_unpack_kernel(const float* __restric
 __global__ void __launch_bounds__(256) attn_bwd_softmax_kernel(const float* __restrict__ S, const float* __restrict__ dP, int Tqp, int Tkp,
                                                                int n_q, int n_kv, const int32_t* __restrict__ kv_len, int H,
                                                                __nv_bfloat16* __restrict__ dS, __nv_bfloat16* __restrict__ dST,
-                                                               __nv_bfloat16* __restrict__ PT) {
+                                                               __nv_bfloat16* __restrict__ PT,
+                                                               const unsigned long long* __restrict__ seed, uint32_t site, uint32_t thresh,
+                                                               float scale) {
+  // with dropout (seed != nullptr): `dP` holds d(Pd) = dO V^T; dP = d(Pd) o keep/(1-p); PT receives Pd^T (the dV operand)
   __shared__ float st_m[32], st_il[32], st_d[32];
   __shared__ float tp[32][65], tds[32][65];
   pdl_launch_dependents();
@@ -83,10 +170,11 @@ __global__ void __launch_bounds__(256) attn_bwd_softmax_kernel(const float* __re
     for (int c = lane; c < klen; c += 32) mx = fmaxf(mx, srow[c]);
     mx = warp_max(mx);
     float l = 0.f, dacc = 0.f;
+    const long long e_row = (bh * Tqp + r0 + r) * (long long)Tkp;
     for (int c = lane; c < klen; c += 32) {
       const float e = expf(srow[c] - mx);
       l += e;
-      dacc = fmaf(e, prow[c], dacc);
+      dacc = fmaf(e, prow[c] * keep1(seed, site, e_row + c, thresh, scale), dacc);
     }
     l = warp_sum(l); dacc = warp_sum(dacc);
     if (lane == 0) {
@@ -106,15 +194,18 @@ __global__ void __launch_bounds__(256) attn_bwd_softmax_kernel(const float* __re
       const float* srow = Sb + (long long)(r0 + r) * Tkp + c0 + cc;
       const float* prow = Pb + (long long)(r0 + r) * Tkp + c0 + cc;
       const float4 s0 = load4(srow), s1 = load4(srow + 4), g0 = load4(prow), g1 = load4(prow + 4);
+      const long long e = (bh * Tqp + r0 + r) * (long long)Tkp + c0 + cc;
+      const Keep4 k0 = keep4(seed, site, e, thresh, scale), k1 = keep4(seed, site, e + 4, thresh, scale);
       const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
       const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float kv[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
       float pv[8], dv[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float p = (c0 + cc + i < klen) ? expf(sv[i] - m) * il : 0.f;
         pv[i] = p;
-        dv[i] = p * (gv[i] - dd);
-        tp[r][cc + i] = p;
+        dv[i] = p * (gv[i] * kv[i] - dd);
+        tp[r][cc + i] = p * kv[i];
         tds[r][cc + i] = dv[i];
       }
       uint4 u;
@@ -162,13 +253,33 @@ static int batched_gemm(const void* A, const void* W, void* Cout, int c_dtype, i
   return cst_gemm(&p, stream);
 }
 
+extern "C" int cst_attention_bwd_tc_dropout(const void* q, const void* k, const void* v, int qkv_dtype, const float* d_o, float* dq, float* dk,
+                                            float* dv, long long ldq, long long ldkv, long long ldo, long long lddq, long long lddkv,
+                                            int B, int H, int n_q, int q_rows_per_seg, int n_kv, int kv_rows_per_seg, const int32_t* kv_len,
+                                            float p, const unsigned long long* seed, unsigned int site, void* ws, void* stream);
+
 // q / k / v: bf16 forward tensors (row strides ldq / ldkv); d_o fp32 (ldo); dq / dk / dv fp32 (lddq / lddkv), rows t < n_q / n_kv of
 // every utterance are written.  ws: cst_attention_bwd_tc_ws_bytes(B, H, n_q, n_kv) bytes, 256-byte aligned.
 extern "C" int cst_attention_bwd_tc(const void* q, const void* k, const void* v, const float* d_o, float* dq, float* dk, float* dv,
                                     long long ldq, long long ldkv, long long ldo, long long lddq, long long lddkv,
                                     int B, int H, int n_q, int q_rows_per_seg, int n_kv, int kv_rows_per_seg, const int32_t* kv_len,
                                     void* ws, void* stream) {
+  return cst_attention_bwd_tc_dropout(q, k, v, CST_BF16, d_o, dq, dk, dv, ldq, ldkv, ldo, lddq, lddkv, B, H, n_q, q_rows_per_seg, n_kv,
+                                      kv_rows_per_seg, kv_len, 0.f, nullptr, 0u, ws, stream);
+}
+
+// The same with dropout of the attention probabilities (p > 0: masks of (*seed, site), see the header of this file) and q / k / v in
+// `qkv_dtype` (CST_BF16 or CST_F32: the panels are bf16 either way).
+extern "C" int cst_attention_bwd_tc_dropout(const void* q, const void* k, const void* v, int qkv_dtype, const float* d_o, float* dq, float* dk,
+                                            float* dv, long long ldq, long long ldkv, long long ldo, long long lddq, long long lddkv,
+                                            int B, int H, int n_q, int q_rows_per_seg, int n_kv, int kv_rows_per_seg, const int32_t* kv_len,
+                                            float p, const unsigned long long* seed, unsigned int site, void* ws, void* stream) {
   CST_REQUIRE(q && k && v && d_o && dq && dk && dv && ws && B > 0 && H > 0 && n_q > 0 && n_kv > 0, "cst_attention_bwd_tc: bad args");
+  CST_REQUIRE((qkv_dtype == CST_BF16 || qkv_dtype == CST_F32) && p >= 0.f && p < 1.f && (p == 0.f || seed != nullptr),
+              "cst_attention_bwd_tc: bad dtype / dropout arguments");
+  const unsigned long long* sd = p > 0.f ? seed : nullptr;
+  const uint32_t thresh = dropout_threshold(p);
+  const float kscale = 1.0f / (1.0f - p);
   CST_REQUIRE(n_q <= q_rows_per_seg && n_kv <= kv_rows_per_seg && ((uintptr_t)ws % 256) == 0 && lddq % 4 == 0 && lddkv % 4 == 0,
               "cst_attention_bwd_tc: bad geometry");
   cudaStream_t st = (cudaStream_t)stream;
@@ -186,20 +297,20 @@ extern "C" int cst_attention_bwd_tc(const void* q, const void* k, const void* v,
   auto* dQd = (float*)take(BH * Tqp * 64 * 4); auto* dKd = (float*)take(BH * Tkp * 64 * 4); auto* dVd = (float*)take(BH * Tkp * 64 * 4);
   CST_REQUIRE((long long)(w - reinterpret_cast<uint8_t*>(ws)) <= cst_attention_bwd_tc_ws_bytes(B, H, n_q, n_kv) + 16 * 256,
               "cst_attention_bwd_tc: workspace accounting");
-  CST_CHECK_CUDA(launch_k(head_pack_kernel, dim3(Tqp / 64, H, B), dim3(256), 0, st, q, (int)CST_BF16, ldq, q_rows_per_seg, n_q,
+  CST_CHECK_CUDA(launch_k(head_pack_kernel, dim3(Tqp / 64, H, B), dim3(256), 0, st, q, qkv_dtype, ldq, q_rows_per_seg, n_q,
                           (const int32_t*)nullptr, H, Tqp, Qh, QhT));
   CST_CHECK_CUDA(launch_k(head_pack_kernel, dim3(Tqp / 64, H, B), dim3(256), 0, st, (const void*)d_o, (int)CST_F32, ldo, q_rows_per_seg, n_q,
                           (const int32_t*)nullptr, H, Tqp, Gh, GhT));
-  CST_CHECK_CUDA(launch_k(head_pack_kernel, dim3(Tkp / 64, H, B), dim3(256), 0, st, k, (int)CST_BF16, ldkv, kv_rows_per_seg, n_kv, kv_len, H,
+  CST_CHECK_CUDA(launch_k(head_pack_kernel, dim3(Tkp / 64, H, B), dim3(256), 0, st, k, qkv_dtype, ldkv, kv_rows_per_seg, n_kv, kv_len, H,
                           Tkp, Kh, KhT));
-  CST_CHECK_CUDA(launch_k(head_pack_kernel, dim3(Tkp / 64, H, B), dim3(256), 0, st, v, (int)CST_BF16, ldkv, kv_rows_per_seg, n_kv, kv_len, H,
+  CST_CHECK_CUDA(launch_k(head_pack_kernel, dim3(Tkp / 64, H, B), dim3(256), 0, st, v, qkv_dtype, ldkv, kv_rows_per_seg, n_kv, kv_len, H,
                           Tkp, Vh, (__nv_bfloat16*)nullptr));
   int rc = batched_gemm(Qh, Kh, S, CST_F32, Tqp, Tkp, 64, Tqp, (int)BH, stream);
   if (rc) return rc;
   rc = batched_gemm(Gh, Vh, dP, CST_F32, Tqp, Tkp, 64, Tqp, (int)BH, stream);
   if (rc) return rc;
   CST_CHECK_CUDA(launch_k(attn_bwd_softmax_kernel, dim3(Tqp / 32, (unsigned)BH), dim3(256), 0, st, (const float*)S, (const float*)dP, Tqp, Tkp,
-                          n_q, n_kv, kv_len, H, dS, dST, PT));
+                          n_q, n_kv, kv_len, H, dS, dST, PT, sd, (uint32_t)site, thresh, kscale));
   rc = batched_gemm(dS, KhT, dQd, CST_F32, Tqp, 64, Tkp, Tqp, (int)BH, stream);
   if (rc) return rc;
   rc = batched_gemm(dST, QhT, dKd, CST_F32, Tkp, 64, Tqp, Tkp, (int)BH, stream);
@@ -212,5 +323,59 @@ extern "C" int cst_attention_bwd_tc(const void* q, const void* k, const void* v,
                           kv_rows_per_seg));
   CST_CHECK_CUDA(launch_k(head_unpack_kernel, dim3(cdiv(n_kv, 16), H, B), dim3(256), 0, st, (const float*)dVd, Tkp, n_kv, H, dv, lddkv,
                           kv_rows_per_seg));
+  return CST_OK;
+}
+
+// ---- forward with dropout of the attention probabilities (training step, attention_dropout > 0)
+extern "C" long long cst_attention_dropout_fwd_ws_bytes(int B, int H, int n_q, int n_kv) {
+  const long long BH = (long long)B * H, Tqp = up64(n_q), Tkp = up64(n_kv);
+  return BH * (Tqp * 64 * 2 + Tkp * 64 * 2 * 3             // Qh | Kh Vh VhT
+               + Tqp * Tkp * (4 + 2)                       // S | Pd
+               + Tqp * 64 * 4) + 4096;                     // Od
+}
+
+// out[(b*q_rows_per_seg + t)*ldo + h*64 + d] = sum_j Pd[b,h,t,j] v[b,j,h,d] for t < n_q, Pd = softmax(q k^T + key mask) o keep / (1 - p).
+// q / k / v in `qkv_dtype` (CST_BF16 / CST_F32; panels and products bf16 on tcgen05, fp32 accumulation), out in `out_dtype`.
+extern "C" int cst_attention_dropout_fwd(const void* q, const void* k, const void* v, int qkv_dtype, void* out, int out_dtype,
+                                         long long ldq, long long ldkv, long long ldo, int B, int H, int n_q, int q_rows_per_seg, int n_kv,
+                                         int kv_rows_per_seg, const int32_t* kv_len, float p, const unsigned long long* seed,
+                                         unsigned int site, void* ws, void* stream) {
+  CST_REQUIRE(q && k && v && out && ws && seed && B > 0 && H > 0 && n_q > 0 && n_kv > 0, "cst_attention_dropout_fwd: bad args");
+  CST_REQUIRE((qkv_dtype == CST_BF16 || qkv_dtype == CST_F32) && (out_dtype == CST_BF16 || out_dtype == CST_F32) && p >= 0.f && p < 1.f,
+              "cst_attention_dropout_fwd: bad dtype / p");
+  CST_REQUIRE(n_q <= q_rows_per_seg && n_kv <= kv_rows_per_seg && ((uintptr_t)ws % 256) == 0 && ldo % 4 == 0,
+              "cst_attention_dropout_fwd: bad geometry");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long BH = (long long)B * H;
+  const int Tqp = (int)up64(n_q), Tkp = (int)up64(n_kv);
+  uint8_t* w = reinterpret_cast<uint8_t*>(ws);
+  auto take = [&](long long bytes) { uint8_t* p_ = w; w += (bytes + 255) / 256 * 256; return p_; };
+  auto* Qh = (__nv_bfloat16*)take(BH * Tqp * 64 * 2);
+  auto* Kh = (__nv_bfloat16*)take(BH * Tkp * 64 * 2);
+  auto* Vh = (__nv_bfloat16*)take(BH * Tkp * 64 * 2); auto* VhT = (__nv_bfloat16*)take(BH * Tkp * 64 * 2);
+  auto* S = (float*)take(BH * Tqp * Tkp * 4);
+  auto* Pd = (__nv_bfloat16*)take(BH * Tqp * Tkp * 2);
+  auto* Od = (float*)take(BH * Tqp * 64 * 4);
+  CST_REQUIRE((long long)(w - reinterpret_cast<uint8_t*>(ws)) <= cst_attention_dropout_fwd_ws_bytes(B, H, n_q, n_kv) + 8 * 256,
+              "cst_attention_dropout_fwd: workspace accounting");
+  CST_CHECK_CUDA(launch_k(head_pack_kernel, dim3(Tqp / 64, H, B), dim3(256), 0, st, q, qkv_dtype, ldq, q_rows_per_seg, n_q,
+                          (const int32_t*)nullptr, H, Tqp, Qh, (__nv_bfloat16*)nullptr));
+  CST_CHECK_CUDA(launch_k(head_pack_kernel, dim3(Tkp / 64, H, B), dim3(256), 0, st, k, qkv_dtype, ldkv, kv_rows_per_seg, n_kv, kv_len, H, Tkp,
+                          Kh, (__nv_bfloat16*)nullptr));
+  CST_CHECK_CUDA(launch_k(head_pack_kernel, dim3(Tkp / 64, H, B), dim3(256), 0, st, v, qkv_dtype, ldkv, kv_rows_per_seg, n_kv, kv_len, H, Tkp,
+                          Vh, VhT));
+  int rc = batched_gemm(Qh, Kh, S, CST_F32, Tqp, Tkp, 64, Tqp, (int)BH, stream);
+  if (rc) return rc;
+  CST_CHECK_CUDA(launch_k(attn_fwd_softmax_dropout_kernel, dim3(Tqp / 32, (unsigned)BH), dim3(256), 0, st, (const float*)S, Tqp, Tkp, n_q, n_kv,
+                          kv_len, H, Pd, p > 0.f ? seed : (const unsigned long long*)nullptr, (uint32_t)site, dropout_threshold(p),
+                          1.0f / (1.0f - p)));
+  rc = batched_gemm(Pd, VhT, Od, CST_F32, Tqp, 64, Tkp, Tqp, (int)BH, stream);
+  if (rc) return rc;
+  if (out_dtype == CST_F32)
+    CST_CHECK_CUDA(launch_k(head_unpack_kernel, dim3(cdiv(n_q, 16), H, B), dim3(256), 0, st, (const float*)Od, Tqp, n_q, H, (float*)out, ldo,
+                            q_rows_per_seg));
+  else
+    CST_CHECK_CUDA(launch_k(head_unpack_bf16_kernel, dim3(cdiv(n_q, 16), H, B), dim3(256), 0, st, (const float*)Od, Tqp, n_q, H,
+                            (__nv_bfloat16*)out, ldo, q_rows_per_seg));
   return CST_OK;
 }

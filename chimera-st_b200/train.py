@@ -179,15 +179,32 @@ class _Ops:
         gb = self.colsum(part, nblk, 2 * Cd)
         return dx, gb[:Cd], gb[Cd:]
 
-    def attention(self, q, k, v, ldq, ldkv, B, H, n_q, q_rps, n_kv, kv_rps, kv_len, out_rows, out_cols):
+    def _ws(self, nbytes):
+        return torch.empty(int(nbytes), dtype=torch.uint8, device=self.dev)
+
+    def attention(self, q, k, v, ldq, ldkv, B, H, n_q, q_rps, n_kv, kv_rps, kv_len, out_rows, out_cols, drop=None):
+        """drop = (p, seed tensor, site): dropout of the attention probabilities -- the materialised form on batched tcgen05 GEMMs
+        (csrc/attention_bwd_tc.cu; bf16 panels in both modes) instead of the flash kernel."""
         out = self.new(out_rows, out_cols, zero=True, dtype=self.op)
+        if drop is not None and drop[0] > 0:
+            ws = self._ws(self.lib.cst_attention_dropout_fwd_ws_bytes(B, H, n_q, n_kv))
+            L.check(self.lib.cst_attention_dropout_fwd(q, k, v, self.opc, out.data_ptr(), self.opc, ldq, ldkv, out_cols, B, H, n_q, q_rps, n_kv,
+                                                       kv_rps, L.ptr(kv_len), float(drop[0]), drop[1].data_ptr(), int(drop[2]),
+                                                       ws.data_ptr(), self.st()))
+            return out
         L.check(self.lib.cst_attention(q, k, v, out.data_ptr(), self.opc, ldq, ldkv, out_cols, B, H, n_q, q_rps, n_kv, kv_rps, L.ptr(kv_len),
                                        self.st()))
         return out
 
-    def attention_bwd(self, q, k, v, o, do, dq, dk, dv, ldq, ldkv, ldo, B, H, n_q, q_rps, n_kv, kv_rps, kv_len, dtype=None):
+    def attention_bwd(self, q, k, v, o, do, dq, dk, dv, ldq, ldkv, ldo, B, H, n_q, q_rps, n_kv, kv_rps, kv_len, dtype=None, drop=None):
         """q / k / v / o: forward tensors (operand dtype, row strides ldq / ldkv / ldo); do, dq, dk, dv fp32 with the SAME row strides.
         16-bit mode: batched tcgen05 GEMMs + one softmax-backward kernel (csrc/attention_bwd_tc.cu); fp32: the FFMA parity kernel."""
+        if drop is not None and drop[0] > 0:                       # same masks as the forward (regenerated from seed / site)
+            ws = self._ws(self.lib.cst_attention_bwd_tc_ws_bytes(B, H, n_q, n_kv))
+            L.check(self.lib.cst_attention_bwd_tc_dropout(q, k, v, self.opc, do.data_ptr(), dq, dk, dv, ldq, ldkv, ldo, ldq, ldkv, B, H, n_q,
+                                                          q_rps, n_kv, kv_rps, L.ptr(kv_len), float(drop[0]), drop[1].data_ptr(), int(drop[2]),
+                                                          ws.data_ptr(), self.st()))
+            return
         if self.op == torch.bfloat16 and dtype is None and self.tc_attn_bwd:
             ws = torch.empty(int(self.lib.cst_attention_bwd_tc_ws_bytes(B, H, n_q, n_kv)), dtype=torch.uint8, device=self.dev)
             L.check(self.lib.cst_attention_bwd_tc(q, k, v, do.data_ptr(), dq, dk, dv, ldq, ldkv, ldo, ldq, ldkv, B, H, n_q, q_rps, n_kv, kv_rps,
@@ -216,7 +233,7 @@ def _attn_layer_grads(G, name, dqkv_w, dqkv_b, D, fused=True):
 
 class EncoderTrainStep:
     def __init__(self, state_dict, B, Lw, M=None, device="cuda", feature_grad_mult=0.1, dtype=F32, lib=None, dropout=0.0,
-                 activation_dropout=None, w2v_dropout=0.0, w2v_dropout_input=0.0, seed=1):
+                 activation_dropout=None, attention_dropout=None, w2v_dropout=0.0, w2v_attention_dropout=None, w2v_dropout_input=0.0, seed=1):
         dev = torch.device(device)
         if dev.type != "cuda" and lib is None:
             raise L.CstError("EncoderTrainStep runs only on a CUDA device (no CPU fallback)")
@@ -243,9 +260,12 @@ class EncoderTrainStep:
         # w2v2_transformer.py:460), `w2v_dropout` = wav2vec2's encoder dropout (wav2vec2.py:830) and dropout1 / dropout3 of its layers,
         # `w2v_dropout_input` = wav2vec2.py:553.  0 everywhere = the parity configuration.  Masks are regenerated from (seed, site) in the
         # backward pass, never stored; `seed_dev` lives on the device so CUDA-graph replays draw fresh masks (`next_dropout_seed`).
-        # Dropout of the attention probabilities (attention_dropout) is NOT built.
+        # `attention_dropout` (defaults to `dropout`, w2v2_transformer.py:459) / `w2v_attention_dropout` (defaults to `w2v_dropout`; 0.1
+        # in wav2vec2 base) drop the attention probabilities: those layers run the materialised attention of csrc/attention_bwd_tc.cu.
         self.pd = {"shared": float(dropout), "act": float(dropout if activation_dropout is None else activation_dropout),
-                   "w2v": float(w2v_dropout), "w2v_input": float(w2v_dropout_input)}
+                   "attn": float(dropout if attention_dropout is None else attention_dropout),
+                   "w2v": float(w2v_dropout), "w2v_attn": float(w2v_dropout if w2v_attention_dropout is None else w2v_attention_dropout),
+                   "w2v_input": float(w2v_dropout_input)}
         self._sites = {}
         self._seed_host = torch.tensor([int(seed)], dtype=torch.int64)
         if dev.type == "cuda":
@@ -257,9 +277,14 @@ class EncoderTrainStep:
         self._seed_host[0] += 1
         self.seed_dev.copy_(self._seed_host, non_blocking=True)
 
+    def _site(self, T, tag):
+        return self._sites.setdefault((T.get("pass", 0), tag), len(self._sites))
+
     def _drop(self, T, tag, p, x, rows, cols, **kw):
-        site = self._sites.setdefault((T.get("pass", 0), tag), len(self._sites))
-        return self.o.dropout(x, rows, cols, p, self.seed_dev, site, **kw)
+        return self.o.dropout(x, rows, cols, p, self.seed_dev, self._site(T, tag), **kw)
+
+    def _adrop(self, T, tag, p):
+        return (p, self.seed_dev, self._site(T, tag)) if p > 0 else None
 
     # ------------------------------------------------------------------ forward (activations kept)
     @staticmethod
@@ -336,7 +361,8 @@ class EncoderTrainStep:
             t = {"x_op": x_op}
             qkv = o.linear(x_op, lw["qkv_w"], lw["qkv_b"], out_dtype=op)
             qp = qkv.data_ptr()
-            ctx = o.attention(qp, qp + esz * D, qp + 2 * esz * D, 3 * D, 3 * D, B, W2V_HEADS, g.T6a, g.T6a, g.Tp, g.T6a, w2v_valid, R, D)
+            ctx = o.attention(qp, qp + esz * D, qp + 2 * esz * D, 3 * D, 3 * D, B, W2V_HEADS, g.T6a, g.T6a, g.Tp, g.T6a, w2v_valid, R, D,
+                              drop=self._adrop(T, f"w2v{li}.prob", self.pd["w2v_attn"]))
             if pw > 0:                                             # x = residual + dropout1(attention output)
                 y1 = self._drop(T, f"w2v{li}.attn", pw, o.linear(ctx, lw["o_w"], lw["o_b"]), R, D, add=x)
             else:
@@ -386,7 +412,8 @@ class EncoderTrainStep:
             _, a = o.ln(x2, lw["ln1_g"], lw["ln1_b"], R2, f32=False)
             qkv = o.linear(a, lw["qkv_w"], lw["qkv_b"], out_dtype=op)
             qp = qkv.data_ptr()
-            ctx = o.attention(qp, qp + esz * D2, qp + 2 * esz * D2, 3 * D2, 3 * D2, B, ENC_HEADS, g.T2a, g.T2a, g.T2, g.T2a, sub_valid, R2, D2)
+            ctx = o.attention(qp, qp + esz * D2, qp + 2 * esz * D2, 3 * D2, 3 * D2, B, ENC_HEADS, g.T2a, g.T2a, g.T2, g.T2a, sub_valid, R2, D2,
+                              drop=self._adrop(T, f"enc{li}.prob", self.pd["attn"]))
             if ps > 0:
                 xm = self._drop(T, f"enc{li}.attn", ps, o.linear(ctx, lw["o_w"], lw["o_b"]), R2, D2, add=x2)
             else:
@@ -417,7 +444,8 @@ class EncoderTrainStep:
             q = o.linear(a, lw["q_w"], lw["q_b"], out_dtype=op)
             kv = o.linear(kv_in, lw["kv_w"], lw["kv_b"], out_dtype=op)
             kp = kv.data_ptr()
-            ctx = o.attention(q.data_ptr(), kp, kp + esz * D2, D2, 2 * D2, B, ENC_HEADS, Mq, Mq, g.T2, g.T2a, None, RM, D2)
+            ctx = o.attention(q.data_ptr(), kp, kp + esz * D2, D2, 2 * D2, B, ENC_HEADS, Mq, Mq, g.T2, g.T2a, None, RM, D2,
+                              drop=self._adrop(T, f"mem{li}.prob", self.pd["attn"]))
             if ps > 0:                                             # only the M memory rows of cat(h_enc, memories) survive the layer
                 mm = self._drop(T, f"mem{li}.attn", ps, o.linear(ctx, lw["o_w"], lw["o_b"]), RM, D2, add=mem)
             else:
@@ -511,7 +539,7 @@ class EncoderTrainStep:
             dqkv = o.new(R, 3 * D, zero=True)
             qp, dqp = t["qkv"].data_ptr(), dqkv.data_ptr()
             o.attention_bwd(qp, qp + esz * D, qp + 2 * esz * D, t["ctx"], dctx, dqp, dqp + 4 * D, dqp + 8 * D, 3 * D, 3 * D, D, B, W2V_HEADS,
-                            g.T6a, g.T6a, g.Tp, g.T6a, T["w2v_valid"])
+                            g.T6a, g.T6a, g.Tp, g.T6a, T["w2v_valid"], drop=self._adrop(T, f"w2v{li}.prob", self.pd["w2v_attn"]))
             dx, dWqkv, dbqkv = o.linear_bwd(t["x_op"], lw["qkv_w"], dqkv, R, dx_residual=dy1)   # + residual x -> y1
             _attn_layer_grads(G, nm + "self_attn.", dWqkv, dbqkv, D)
         self.dbg["w2v_in"] = dx
@@ -579,7 +607,7 @@ class EncoderTrainStep:
             dkv = o.new(R2, 2 * D2, zero=True)
             kp, dkp = t["kv"].data_ptr(), dkv.data_ptr()
             o.attention_bwd(t["q"].data_ptr(), kp, kp + esz * D2, t["ctx"], dctx, dq.data_ptr(), dkp, dkp + 4 * D2, D2, 2 * D2, D2, B, ENC_HEADS,
-                            Mq, Mq, g.T2, g.T2a, None)
+                            Mq, Mq, g.T2, g.T2a, None, drop=self._adrop(T, f"mem{li}.prob", self.pd["attn"]))
             da, dWq, dbq = o.linear_bwd(t["a"], lw["q_w"], dq, RM)
             G[nm + "self_attn.q_proj.weight"], G[nm + "self_attn.q_proj.bias"] = dWq * 0.125, dbq * 0.125
             dkv_in, dWkv, dbkv = o.linear_bwd(t["kv_in"], lw["kv_w"], dkv, R2)
@@ -603,7 +631,7 @@ class EncoderTrainStep:
             dqkv = o.new(R2, 3 * D2, zero=True)
             qp, dqp = t["qkv"].data_ptr(), dqkv.data_ptr()
             o.attention_bwd(qp, qp + esz * D2, qp + 2 * esz * D2, t["ctx"], dctx, dqp, dqp + 4 * D2, dqp + 8 * D2, 3 * D2, 3 * D2, D2, B,
-                            ENC_HEADS, g.T2a, g.T2a, g.T2, g.T2a, T["sub_valid"])
+                            ENC_HEADS, g.T2a, g.T2a, g.T2, g.T2a, T["sub_valid"], drop=self._adrop(T, f"enc{li}.prob", self.pd["attn"]))
             da, dWqkv, dbqkv = o.linear_bwd(t["a"], lw["qkv_w"], dqkv, R2)
             _attn_layer_grads(G, nm + "self_attn.", dWqkv, dbqkv, D2)
             dx2, dg1, db1 = o.ln_bwd(t["x_in"], lw["ln1_g"], da, R2, dx=dxm)

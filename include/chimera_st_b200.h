@@ -278,6 +278,21 @@ int cst_attention_bwd_tc(const void* q, const void* k, const void* v, const floa
                          long long ldq, long long ldkv, long long ldo, long long lddq, long long lddkv,
                          int B, int H, int n_q, int q_rows_per_seg, int n_kv, int kv_rows_per_seg, const int32_t* kv_len,
                          void* ws, void* stream);
+/* Dropout of the attention probabilities (attention_dropout of the training recipe: F.multi_head_attention_forward drops softmax(S)
+ * before the product with V; fairseq/modules/multihead_attention.py:155-187).  With p > 0 the training forward runs as
+ * S = Q K^T (batched tcgen05 GEMM) -> softmax + dropout kernel -> Pd V (GEMM), and the backward pass regenerates the same masks:
+ * keep(b, h, i, j) = Philox word of element ((b*H + h)*up64(n_q) + i)*up64(n_kv) + j under (*seed, site) (csrc/philox.cuh).
+ * q / k / v in qkv_dtype (CST_BF16 / CST_F32; the per-head panels are bf16 either way), out in out_dtype; other arguments as
+ * cst_attention / cst_attention_bwd_tc.  ws: the *_ws_bytes figure, 256-byte aligned. */
+long long cst_attention_dropout_fwd_ws_bytes(int B, int H, int n_q, int n_kv);
+int cst_attention_dropout_fwd(const void* q, const void* k, const void* v, int qkv_dtype, void* out, int out_dtype,
+                              long long ldq, long long ldkv, long long ldo, int B, int H, int n_q, int q_rows_per_seg, int n_kv,
+                              int kv_rows_per_seg, const int32_t* kv_len, float p, const unsigned long long* seed,
+                              unsigned int site, void* ws, void* stream);
+int cst_attention_bwd_tc_dropout(const void* q, const void* k, const void* v, int qkv_dtype, const float* d_o, float* dq, float* dk,
+                                 float* dv, long long ldq, long long ldkv, long long ldo, long long lddq, long long lddkv,
+                                 int B, int H, int n_q, int q_rows_per_seg, int n_kv, int kv_rows_per_seg, const int32_t* kv_len,
+                                 float p, const unsigned long long* seed, unsigned int site, void* ws, void* stream);
 /* Input gradient of an implicit-GEMM strided convolution from its A-operand gradient dcol [M, k*C] (gather form). */
 int cst_col2im(const void* dcol, int dcol_dtype, long long M, int k, int stride, int C, float* dx, long long rows_in, int accumulate,
                void* stream);

@@ -68,7 +68,7 @@ def _gelu(x):
     return 0.5 * x * (1.0 + torch.erf(x * (1.0 / math.sqrt(2.0))))
 
 
-def mha(sd, prefix, q_in, kv_in, n_heads, key_padding_mask=None, attn_bias=None):
+def mha(sd, prefix, q_in, kv_in, n_heads, key_padding_mask=None, attn_bias=None, drop_tag=None):
     """softmax(((xWq+bq)*d^-0.5)(xWk+bk)^T + mask)(xWv+bv) Wo + bo, batch-first.
     q_in [B,Tq,C], kv_in [B,Tk,C]; key_padding_mask bool [B,Tk] (True = pad -> -inf);
     attn_bias additive [Tq,Tk].  Follows torch multi_head_attention_forward as called
@@ -88,6 +88,8 @@ def mha(sd, prefix, q_in, kv_in, n_heads, key_padding_mask=None, attn_bias=None)
     if key_padding_mask is not None:
         s = s.masked_fill(key_padding_mask[:, None, None, :], float("-inf"))
     p = torch.softmax(s, dim=-1)
+    if drop_tag is not None and attn_bias is None:                  # attention_dropout: F.dropout on the probabilities [B,H,Tq,Tk]
+        p = _dropout(drop_tag, p)
     o = (p @ v).transpose(1, 2).reshape(B, Tq, C)
     return F.linear(o, sd[prefix + "out_proj.weight"], sd[prefix + "out_proj.bias"])
 
@@ -135,7 +137,7 @@ def w2v_layer(sd, i, x, pad_mask):
     """TransformerSentenceEncoderLayer.forward post-LN branch, wav2vec2.py:937-957. x [B,T,768].
     Dropout sites: dropout1 after the attention, dropout3 after fc2 (dropout2 = activation_dropout is 0 in wav2vec2 base)."""
     P = f"wav2vec_model.encoder.layers.{i}."
-    a = _dropout(f"w2v{i}.attn", mha(sd, P + "self_attn.", x, x, 12, key_padding_mask=pad_mask))
+    a = _dropout(f"w2v{i}.attn", mha(sd, P + "self_attn.", x, x, 12, key_padding_mask=pad_mask, drop_tag=f"w2v{i}.prob"))
     x = _ln(x + a, sd, P + "self_attn_layer_norm")
     h = _gelu(F.linear(x, sd[P + "fc1.weight"], sd[P + "fc1.bias"]))
     h = _dropout(f"w2v{i}.ffn", F.linear(h, sd[P + "fc2.weight"], sd[P + "fc2.bias"]))
@@ -197,7 +199,8 @@ def encoder_layer(sd, P, x, pad_mask, attn_bias=None):
     fairseq/modules/transformer_layer.py:105-155. x [B,T,512]."""
     tag = _layer_tag(P)
     h = _ln(x, sd, P + "self_attn_layer_norm")
-    x = x + _dropout(tag + ".attn", mha(sd, P + "self_attn.", h, h, 8, key_padding_mask=pad_mask, attn_bias=attn_bias))   # dropout_module
+    x = x + _dropout(tag + ".attn", mha(sd, P + "self_attn.", h, h, 8, key_padding_mask=pad_mask, attn_bias=attn_bias,
+                                        drop_tag=tag + ".prob"))                                      # dropout_module
     h = _ln(x, sd, P + "final_layer_norm")
     h = _dropout(tag + ".act", torch.relu(F.linear(h, sd[P + "fc1.weight"], sd[P + "fc1.bias"])))     # activation_dropout_module
     return x + _dropout(tag + ".ffn", F.linear(h, sd[P + "fc2.weight"], sd[P + "fc2.bias"]))          # dropout_module
@@ -228,7 +231,7 @@ def memory_stage(sd, h_enc):
         P = f"interlingua_layers.{l}."
         q_in = _ln(mem, sd, P + "self_attn_layer_norm")
         kv_in = _ln(h_enc, sd, P + "self_attn_layer_norm")
-        y = mem + _dropout(f"mem{l}.attn", mha(sd, P + "self_attn.", q_in, kv_in, 8))
+        y = mem + _dropout(f"mem{l}.attn", mha(sd, P + "self_attn.", q_in, kv_in, 8, drop_tag=f"mem{l}.prob"))
         h = _ln(y, sd, P + "final_layer_norm")
         h = _dropout(f"mem{l}.act", torch.relu(F.linear(h, sd[P + "fc1.weight"], sd[P + "fc1.bias"])))
         mem = y + _dropout(f"mem{l}.ffn", F.linear(h, sd[P + "fc2.weight"], sd[P + "fc2.bias"]))

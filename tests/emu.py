@@ -654,10 +654,74 @@ def oracle_dropout_hook(step, pass_id, geom, p_of):
         p = p_of(tag)
         if p <= 0:
             return x
+        site = step._sites[(pass_id, tag)]
+        used.append(tag)
+        scale = float(np.float32(1.0) / (np.float32(1.0) - np.float32(p)))
+        if x.dim() == 4:                                            # attention probabilities [B, H, Tq, Tk]; geom -> (n_q, n_kv) of our call
+            B, H, Tq, Tk = x.shape
+            n_q, n_kv = geom(tag)
+            keep = torch.from_numpy(dropout_keep(seed, site, B * H * _up64(n_q) * _up64(n_kv), p))
+            return x * keep.view(B, H, _up64(n_q), _up64(n_kv))[:, :, :Tq, :Tk].to(x.dtype) * scale
         B, Tn, Cd = x.shape
         rps = geom(tag)
-        site = step._sites[(pass_id, tag)]
         keep = torch.from_numpy(dropout_keep(seed, site, B * rps * Cd, p)).view(B, rps, Cd)[:, :Tn]
-        used.append(tag)
-        return x * keep.to(x.dtype) * float(np.float32(1.0) / (np.float32(1.0) - np.float32(p)))
+        return x * keep.to(x.dtype) * scale
     return hook, used
+
+
+# ---- attention with dropout of the probabilities (cst_attention_dropout_fwd / cst_attention_bwd_tc_dropout), fp32 on the host ----------
+def _up64(n):
+    return (n + 63) // 64 * 64
+
+
+def _attn_prob_keep(seed_ptr, site, B, H, n_q, n_kv, p):
+    """keep / (1 - p) factors [B, H, n_q, n_kv]: element ((b*H + h)*up64(n_q) + i)*up64(n_kv) + j of the site"""
+    Tqp, Tkp = _up64(n_q), _up64(n_kv)
+    if p <= 0:
+        return torch.ones(B, H, n_q, n_kv, dtype=torch.float64)
+    sd = int(_mem(seed_ptr, 1, np.uint64)[0])
+    keep = torch.from_numpy(dropout_keep(sd, site, B * H * Tqp * Tkp, p)).view(B, H, Tqp, Tkp)[:, :, :n_q, :n_kv]
+    return keep.double() * float(np.float32(1.0) / (np.float32(1.0) - np.float32(p)))
+
+
+def _heads(ptr, B, H, n, rps, ld, copy=True):
+    t = torch.from_numpy(_mem(ptr, ((B - 1) * rps + n - 1) * ld + H * 64)).as_strided((B, n, H, 64), (rps * ld, ld, 64, 1))
+    return t.clone() if copy else t
+
+
+def _attn_dropout_graph(self, q, k, v, ldq, ldkv, B, H, n_q, q_rps, n_kv, kv_rps, kv_len, p, seed, site):
+    Q, K, V = (_heads(p_, B, H, n, r, ld).double().requires_grad_() for p_, n, r, ld in ((q, n_q, q_rps, ldq), (k, n_kv, kv_rps, ldkv),
+                                                                                         (v, n_kv, kv_rps, ldkv)))
+    s = torch.einsum("bqhd,bkhd->bhqk", Q, K)
+    if kv_len:
+        kl = torch.from_numpy(_mem(kv_len, B, np.int32).copy()).long()
+        s = s.masked_fill(torch.arange(n_kv)[None, None, None, :] >= kl[:, None, None, None], float("-inf"))
+    pd = torch.softmax(s, -1) * _attn_prob_keep(seed, site, B, H, n_q, n_kv, p)
+    return Q, K, V, torch.einsum("bhqk,bkhd->bqhd", pd, V)
+
+
+def _attention_dropout_fwd(self, q, k, v, qkv_dtype, out, out_dtype, ldq, ldkv, ldo, B, H, n_q, q_rps, n_kv, kv_rps, kv_len, p, seed, site,
+                           ws, stream):
+    assert qkv_dtype == F32 and out_dtype == F32
+    _, _, _, o = _attn_dropout_graph(self, q, k, v, ldq, ldkv, B, H, n_q, q_rps, n_kv, kv_rps, kv_len, p, seed, site)
+    _heads(out, B, H, n_q, q_rps, ldo, copy=False)[:] = o.detach().float()
+    self.calls.append("attention_dropout_fwd")
+    return 0
+
+
+def _attention_bwd_tc_dropout(self, q, k, v, qkv_dtype, d_o, dq, dk, dv, ldq, ldkv, ldo, lddq, lddkv, B, H, n_q, q_rps, n_kv, kv_rps, kv_len,
+                              p, seed, site, ws, stream):
+    assert qkv_dtype == F32
+    Q, K, V, o = _attn_dropout_graph(self, q, k, v, ldq, ldkv, B, H, n_q, q_rps, n_kv, kv_rps, kv_len, p, seed, site)
+    o.backward(_heads(d_o, B, H, n_q, q_rps, ldo).double())
+    _heads(dq, B, H, n_q, q_rps, lddq, copy=False)[:] = Q.grad.float()
+    _heads(dk, B, H, n_kv, kv_rps, lddkv, copy=False)[:] = K.grad.float()            # written, not accumulated
+    _heads(dv, B, H, n_kv, kv_rps, lddkv, copy=False)[:] = V.grad.float()
+    self.calls.append("attention_bwd_tc_dropout")
+    return 0
+
+
+EmuLib.cst_attention_dropout_fwd_ws_bytes = lambda self, B, H, n_q, n_kv: 256
+EmuLib.cst_attention_bwd_tc_ws_bytes = lambda self, B, H, n_q, n_kv: 256
+EmuLib.cst_attention_dropout_fwd = _attention_dropout_fwd
+EmuLib.cst_attention_bwd_tc_dropout = _attention_bwd_tc_dropout

@@ -401,7 +401,7 @@ def test_encoder_step_with_dropout_matches_autograd_with_the_same_masks():
     sd = synth.make_state_dict(seed=0, interlingua_length=16, dead_heads=False)
     wave, tl = synth.make_waveforms(lens, seed=31)
     R = torch.randn(16, 2, 512, generator=torch.Generator().manual_seed(1))
-    kw = dict(dropout=0.1, w2v_dropout=0.1, w2v_dropout_input=0.1, seed=5)
+    kw = dict(dropout=0.1, w2v_dropout=0.1, w2v_dropout_input=0.1, attention_dropout=0.0, w2v_attention_dropout=0.0, seed=5)
     for dtype, tol_mem, tol in ((torch.float32, 1e-5, 1e-4), (torch.bfloat16, 1.5e-2, None)):
         step = EncoderTrainStep(sd, 2, wave.shape[1], device=DEV, feature_grad_mult=1.0, dtype=dtype, **kw)
         g = step.g
@@ -428,3 +428,77 @@ def test_encoder_step_with_dropout_matches_autograd_with_the_same_masks():
                 bad[k] = e
         assert not bad, bad
         assert (num / den) ** 0.5 < (1e-4 if tol is not None else 2.5e-2), (num / den) ** 0.5
+
+
+@pytest.mark.parametrize("B,H,Tq,Tk,masked", [(2, 8, 16, 117, False), (3, 12, 150, 150, True), (1, 8, 129, 257, False)])
+def test_attention_with_dropout_of_the_probabilities(B, H, Tq, Tk, masked):
+    """cst_attention_dropout_fwd / cst_attention_bwd_tc_dropout: softmax(QK^T) o keep/(1-p) V and its derivative against torch autograd
+    with the mask re-created by the numpy Philox (element ((b*H + h)*up64(Tq) + i)*up64(Tk) + j); bf16 panels, fp32 accumulation."""
+    from emu import dropout_keep
+    o = _Ops(torch.device(DEV), torch.bfloat16)
+    g = torch.Generator().manual_seed(Tq * 7 + Tk)
+    Cd, p, site = H * 64, 0.1, 13
+    seed = torch.tensor([991], dtype=torch.int64, device=DEV)
+    bf = lambda t: t.to(torch.bfloat16).float()                                            # noqa: E731
+    q, k, v = (bf(torch.randn(B, T_, Cd, generator=g) * s_).requires_grad_() for T_, s_ in ((Tq, 0.4), (Tk, 1.0), (Tk, 1.0)))
+    do = torch.randn(B, Tq, Cd, generator=g)
+    kl = torch.tensor([Tk - 11 * b for b in range(B)], dtype=torch.int32) if masked else None
+    Tqp, Tkp = (Tq + 63) // 64 * 64, (Tk + 63) // 64 * 64
+    keep = torch.from_numpy(dropout_keep(991, site, B * H * Tqp * Tkp, p)).view(B, H, Tqp, Tkp)[:, :, :Tq, :Tk]
+    s = torch.einsum("bqhd,bkhd->bhqk", q.view(B, Tq, H, 64), k.view(B, Tk, H, 64))
+    if masked:
+        s = s.masked_fill(torch.arange(Tk)[None, None, None, :] >= kl[:, None, None, None].long(), float("-inf"))
+    pd = torch.softmax(s, -1) * keep / (1 - p)
+    ref = torch.einsum("bhqk,bkhd->bqhd", pd, v.view(B, Tk, H, 64)).reshape(B, Tq, Cd)
+    ref.backward(do)
+    dev = lambda t: t.detach().to(DEV, torch.bfloat16).reshape(-1, Cd).contiguous()         # noqa: E731
+    qd, kd, vd = dev(q), dev(k), dev(v)
+    kld = kl.to(DEV) if masked else None
+    drop = (p, seed, site)
+    out = o.attention(qd.data_ptr(), kd.data_ptr(), vd.data_ptr(), Cd, Cd, B, H, Tq, Tq, Tk, Tk, kld, B * Tq, Cd, drop=drop)
+    assert rel_l2(out.float().cpu().view(B, Tq, Cd), ref.detach()) < 1.2e-2
+    dq, dk, dv = (torch.zeros(B * T_, Cd, device=DEV) for T_ in (Tq, Tk, Tk))
+    o.attention_bwd(qd.data_ptr(), kd.data_ptr(), vd.data_ptr(), out, do.to(DEV).reshape(-1, Cd).contiguous(), dq.data_ptr(), dk.data_ptr(),
+                    dv.data_ptr(), Cd, Cd, Cd, B, H, Tq, Tq, Tk, Tk, kld, drop=drop)
+    for got, want, T_ in ((dq, q.grad, Tq), (dk, k.grad, Tk), (dv, v.grad, Tk)):
+        assert rel_l2(got.cpu().view(B, T_, Cd), want) < 2e-2
+    # p = 0 through the same entry points = plain attention
+    out0 = o.attention(qd.data_ptr(), kd.data_ptr(), vd.data_ptr(), Cd, Cd, B, H, Tq, Tq, Tk, Tk, kld, B * Tq, Cd)
+    assert rel_l2(out.float().cpu(), out0.float().cpu()) > 5e-2
+
+
+def test_bf16_step_with_the_full_dropout_recipe():
+    """p = 0.1 at every site INCLUDING the attention probabilities (bf16, the C5 arithmetic): memories and the whole gradient vector
+    against autograd through the oracle with the same masks."""
+    from emu import oracle_dropout_hook
+    torch.set_num_threads(8)
+    lens = [6000, 4500]
+    sd = synth.make_state_dict(seed=0, interlingua_length=16, dead_heads=False)
+    wave, tl = synth.make_waveforms(lens, seed=31)
+    R = torch.randn(16, 2, 512, generator=torch.Generator().manual_seed(1))
+    step = EncoderTrainStep(sd, 2, wave.shape[1], device=DEV, feature_grad_mult=1.0, dtype=torch.bfloat16, dropout=0.1, w2v_dropout=0.1,
+                            w2v_dropout_input=0.1, seed=9)
+    g = step.g
+    mem, G = step.forward_backward(wave, tl, R)
+    torch.cuda.synchronize()
+    assert len(step._sites) == 54 + 21
+
+    def geom(tag):
+        if tag.endswith(".prob"):
+            return (g.T6a, g.Tp) if tag.startswith("w2v") else (16, g.T2) if tag.startswith("mem") else (g.T2a, g.T2)
+        return g.T6a if tag.startswith("w2v") else 16 if tag.startswith("mem") else g.T2a
+    hook, used = oracle_dropout_hook(step, 0, geom, lambda tag: 0.1)
+    O.DROPOUT_HOOK = hook
+    try:
+        ref_mem, ref, _ = _oracle_grads(sd, wave, tl, R, _relu_masks_of(step))
+    finally:
+        O.DROPOUT_HOOK = None
+    assert len(set(used)) == 75
+    assert rel_l2(mem.cpu().float(), ref_mem) < 1.5e-2
+    num = den = 0.0
+    for k, v in G.items():
+        if k.endswith("k_proj.bias"):
+            continue
+        d = (v.cpu().float().reshape(ref[k].shape) - ref[k]).double()
+        num += float((d * d).sum()); den += float((ref[k].double() ** 2).sum())
+    assert (num / den) ** 0.5 < 2.5e-2, (num / den) ** 0.5

@@ -178,8 +178,9 @@ def test_split_k_weight_gradient_and_strided_window_operand():
 
 
 def test_emulated_dropout_replays_in_the_backward_pass():
-    """Elementwise dropout of the training recipe: the forward's masks are regenerated (never stored) in the backward pass.  Autograd
-    through the oracle with THE SAME masks installed at the reference's dropout sites gives the same memories and gradients."""
+    """Dropout of the training recipe (elementwise sites + attention probabilities): the forward's masks are regenerated (never stored)
+    in the backward pass.  Autograd through the oracle with THE SAME masks installed at the reference's dropout sites gives the same
+    memories and gradients."""
     torch.set_num_threads(8)
     lens = [4700, 3300]
     sd = synth.make_state_dict(seed=0, interlingua_length=8, dead_heads=False)
@@ -187,18 +188,25 @@ def test_emulated_dropout_replays_in_the_backward_pass():
     R = torch.randn(8, 2, 512, generator=torch.Generator().manual_seed(1))
     emu = EmuLib()
     step = EncoderTrainStep(sd, 2, wave.shape[1], device="cpu", feature_grad_mult=1.0, lib=emu, dropout=0.1, activation_dropout=0.2,
-                            w2v_dropout=0.1, w2v_dropout_input=0.15, seed=77)
+                            attention_dropout=0.3, w2v_dropout=0.1, w2v_dropout_input=0.15, seed=77)
     g = step.g
     mem, G = step.forward_backward(wave, tl, R)
-    n_sites = 2 + 2 * 12 + 1 + 3 * 6 + 3 * 3
-    assert len(step._sites) == n_sites and emu.calls.count("dropout") == 2 * n_sites          # every site once forward, once backward
-    fwd, bwd = emu.dropout_log[:n_sites], emu.dropout_log[n_sites:]
+    n_elem, n_prob = 2 + 2 * 12 + 1 + 3 * 6 + 3 * 3, 12 + 6 + 3
+    n_sites = n_elem + n_prob
+    assert len(step._sites) == n_sites and emu.calls.count("dropout") == 2 * n_elem           # every site once forward, once backward
+    assert emu.calls.count("attention_dropout_fwd") == n_prob == emu.calls.count("attention_bwd_tc_dropout")
+    assert "attention" not in emu.calls and "attention_bwd" not in emu.calls
+    fwd, bwd = emu.dropout_log[:n_elem], emu.dropout_log[n_elem:]
     assert sorted(fwd) == sorted(bwd)                                                         # same (seed, site, shape, p) both ways
 
     def p_of(tag):
+        if tag.endswith(".prob"):
+            return 0.1 if tag.startswith("w2v") else 0.3
         return 0.15 if tag == "w2v.input" else 0.2 if tag.endswith(".act") else 0.1
 
     def geom(tag):
+        if tag.endswith(".prob"):
+            return (g.T6a, g.Tp) if tag.startswith("w2v") else (8, g.T2) if tag.startswith("mem") else (g.T2a, g.T2)
         return g.T6a if tag.startswith("w2v") else 8 if tag.startswith("mem") else g.T2a
     hook, used = oracle_dropout_hook(step, 0, geom, p_of)
     O.DROPOUT_HOOK = hook
