@@ -134,7 +134,7 @@ class LaunchProfiler:
 
     def __getattr__(self, name):
         fn = getattr(self.lib, name)
-        if not name.startswith("cst_") or name in ("cst_last_error", "cst_abi_version", "cst_device_info"):
+        if not name.startswith("cst_") or name.endswith("_ws_bytes") or name in ("cst_last_error", "cst_abi_version", "cst_device_info"):
             return fn
 
         def timed(*a):
