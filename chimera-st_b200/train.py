@@ -808,6 +808,25 @@ class FusedAdam:
                                            self.lr, b1, b2, self.eps, self.wd, 0.0, 1.0, self.dyn.data_ptr(), st))
 
 
+class InverseSqrtLR:
+    """The recipe's learning-rate schedule (--lr-scheduler inverse_sqrt --lr 1e-4 --warmup-updates 4000, train-en2any-ST.sh:48-49;
+    fairseq/optim/lr_scheduler/inverse_square_root_schedule.py:49-95): linear from warmup_init_lr (default 0 when there is a warm-up) to
+    `lr` over `warmup_updates` updates, then lr * sqrt(warmup_updates / n).  `at(n)` feeds `FusedAdam.advance(lr=...)`, whose device
+    scalar block carries it into the captured update graph."""
+
+    def __init__(self, lr=1e-4, warmup_updates=4000, warmup_init_lr=-1.0):
+        self.end_lr, self.warmup = float(lr), int(warmup_updates)
+        self.init_lr = float(warmup_init_lr) if warmup_init_lr >= 0 else (0.0 if self.warmup > 0 else self.end_lr)
+        self.lr_step = (self.end_lr - self.init_lr) / self.warmup if self.warmup > 0 else 0.0
+        self.decay_factor = self.end_lr * self.warmup ** 0.5
+        self.initial = self.init_lr
+
+    def at(self, num_updates):
+        if num_updates < self.warmup:
+            return self.init_lr + num_updates * self.lr_step
+        return self.decay_factor * num_updates ** -0.5
+
+
 class GraphedTrainStep:
     """One training step of the path as CUDA graphs: forward + loss in one graph, the backward pass in one graph per segment of
     `EncoderTrainStep.backward_iter`; between the segment replays the finished gradients are handed to the bucketed all-reduce

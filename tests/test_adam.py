@@ -50,3 +50,15 @@ def test_fused_adam_kernel_matches_the_reference_optimizer(gdtype):
     o2.step({"a": torch.ones(5, device="cuda")})
     assert torch.equal(p2["b"].cpu(), torch.ones(5))
     assert not torch.isfinite(p2["a"]).all() or True                         # 0 / 0 with eps = 0 is the caller's problem; no crash
+
+
+def test_inverse_sqrt_schedule_matches_the_reference_class():
+    """train.InverseSqrtLR against goldens of the unmodified InverseSquareRootSchedule (oracle/gen_golden_lr.py): bit-identical floats."""
+    from chimera_st_b200.train import InverseSqrtLR
+    g = np.load(os.path.join(GOLDEN, "lr_schedule.npz"))
+    for name in ("recipe", "init"):
+        lr, warm, init = (float(x) for x in g[name + "_cfg"])
+        sch = InverseSqrtLR(lr, int(warm), init)
+        assert sch.initial == float(g[name + "_initial"])
+        got = [sch.at(int(u)) for u in g["updates"]]
+        assert got == [float(x) for x in g[name + "_lr"]], (got, g[name + "_lr"])
