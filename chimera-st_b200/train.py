@@ -267,15 +267,12 @@ class EncoderTrainStep:
                    "w2v": float(w2v_dropout), "w2v_attn": float(w2v_dropout if w2v_attention_dropout is None else w2v_attention_dropout),
                    "w2v_input": float(w2v_dropout_input)}
         self._sites = {}
-        self._seed_host = torch.tensor([int(seed)], dtype=torch.int64)
-        if dev.type == "cuda":
-            self._seed_host = self._seed_host.pin_memory()
-        self.seed_dev = self._seed_host.to(dev).clone()
+        self.seed_dev = torch.tensor([int(seed)], dtype=torch.int64).to(dev)
 
     def next_dropout_seed(self):
-        """New masks for the next step (asynchronous copy on the current stream; graph replays read the device value)."""
-        self._seed_host[0] += 1
-        self.seed_dev.copy_(self._seed_host, non_blocking=True)
+        """New masks for the next step: the seed is incremented ON the device, in stream order (graph replays read the device value; a
+        host-side counter copied asynchronously could be overwritten before an earlier copy ran when the host runs ahead)."""
+        self.seed_dev.add_(1)
 
     def _site(self, T, tag):
         return self._sites.setdefault((T.get("pass", 0), tag), len(self._sites))
@@ -778,7 +775,8 @@ class FusedAdam:
         self.v = {k: torch.zeros_like(v) for k, v in params.items()}
         self.t = 0
         self.dyn = torch.zeros(4, dtype=F32, device=dev)
-        self._dyn_host = torch.zeros(4, dtype=F32).pin_memory() if dev.type == "cuda" else torch.zeros(4, dtype=F32)
+        # a ring of pinned staging rows: the asynchronous copy of step t must not see the values the host wrote for step t + 1
+        self._dyn_ring = torch.zeros(64, 4, dtype=F32).pin_memory() if dev.type == "cuda" else torch.zeros(64, 4, dtype=F32)
         if dev.type != "cuda" and lib is None:
             raise L.CstError("FusedAdam runs only on CUDA tensors (no CPU fallback)")
         self.dev = dev
@@ -790,10 +788,11 @@ class FusedAdam:
         if lr is not None:
             self.lr = float(lr)
         b1, b2 = self.betas
-        self._dyn_host[0] = self.lr
-        self._dyn_host[1] = self.lr * math.sqrt(1.0 - b2 ** self.t) / (1.0 - b1 ** self.t)
-        self._dyn_host[2] = float(grad_scale)
-        self.dyn.copy_(self._dyn_host, non_blocking=True)
+        row = self._dyn_ring[self.t % self._dyn_ring.shape[0]]
+        row[0] = self.lr
+        row[1] = self.lr * math.sqrt(1.0 - b2 ** self.t) / (1.0 - b1 ** self.t)
+        row[2] = float(grad_scale)
+        self.dyn.copy_(row, non_blocking=True)
 
     def step(self, grads):
         """Launch the updates (reads the scalars written by the last `advance()`); parameters without a gradient are left alone."""
