@@ -35,18 +35,23 @@ __global__ void __launch_bounds__(256) head_pack_kernel(const void* __restrict__
   int valid = n;
   if (len != nullptr) valid = min(valid, len[b]);
   const long long bh = (long long)b * H + h;
-  for (int e = threadIdx.x; e < 64 * 64; e += 256) {
-    const int i = e >> 6, d = e & 63;
+  // 4 consecutive head columns per thread: 8-byte (bf16) / 16-byte (fp32) loads, 8-byte stores (ld and the head offset are multiples of 64)
+  for (int e = threadIdx.x; e < 64 * 16; e += 256) {
+    const int i = e >> 4, d = (e & 15) * 4;
     const int t = t0 + i;
-    const float v = t < valid ? hb_ld(src, sdt, ((long long)b * rows_per_seg + t) * ld + h * 64 + d) : 0.f;
-    tile[i][d] = v;
-    dst[(bh * Tp + t) * 64 + d] = __float2bfloat16_rn(v);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t < valid) {
+      const long long off = ((long long)b * rows_per_seg + t) * ld + h * 64 + d;
+      v = sdt == CST_F32 ? load4(reinterpret_cast<const float*>(src) + off) : load4(reinterpret_cast<const __nv_bfloat16*>(src) + off);
+    }
+    tile[i][d] = v.x; tile[i][d + 1] = v.y; tile[i][d + 2] = v.z; tile[i][d + 3] = v.w;
+    store4(dst + (bh * Tp + t) * 64 + d, v);
   }
   if (dstT == nullptr) return;
   __syncthreads();
-  for (int e = threadIdx.x; e < 64 * 64; e += 256) {
-    const int d = e >> 6, i = e & 63;
-    dstT[(bh * 64 + d) * Tp + t0 + i] = __float2bfloat16_rn(tile[i][d]);
+  for (int e = threadIdx.x; e < 64 * 16; e += 256) {               // transposed panel: 4 consecutive rows t of one head column
+    const int d = e >> 4, i = (e & 15) * 4;
+    store4(dstT + (bh * 64 + d) * Tp + t0 + i, make_float4(tile[i][d], tile[i + 1][d], tile[i + 2][d], tile[i + 3][d]));
   }
 }
 
