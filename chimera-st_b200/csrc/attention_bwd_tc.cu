@@ -85,13 +85,6 @@ __device__ __forceinline__ Keep4 keep4(const unsigned long long* seed, uint32_t 
   const Philox4 r = philox4x32_10(*seed, (unsigned long long)e >> 2, site);
   return Keep4{r.x >= thresh ? scale : 0.f, r.y >= thresh ? scale : 0.f, r.z >= thresh ? scale : 0.f, r.w >= thresh ? scale : 0.f};
 }
-__device__ __forceinline__ float keep1(const unsigned long long* seed, uint32_t site, long long e, uint32_t thresh, float scale) {
-  if (seed == nullptr) return 1.f;
-  const Philox4 r = philox4x32_10(*seed, (unsigned long long)e >> 2, site);
-  const int w = (int)(e & 3);
-  const uint32_t v = w == 0 ? r.x : w == 1 ? r.y : w == 2 ? r.z : r.w;
-  return v >= thresh ? scale : 0.f;
-}
 
 // Forward softmax + dropout: Pd[bh][r][c] = softmax_c(S[bh][r][c]) * keep / (1 - p) in bf16 (columns >= klen and rows >= n_q: 0).
 // One CTA = 32 query rows of one (utterance, head); a warp computes max and sum of 4 rows, then every thread forms 8 columns.
@@ -114,10 +107,19 @@ __global__ void __launch_bounds__(256) attn_fwd_softmax_dropout_kernel(const flo
     const int r = warp * 4 + rr;
     const float* srow = Sb + (long long)(r0 + r) * Tkp;
     float mx = -INFINITY;
-    for (int c = lane; c < klen; c += 32) mx = fmaxf(mx, srow[c]);
+    for (int c = lane * 4; c < klen; c += 128) {
+      const float4 s4 = load4(srow + c);
+      mx = fmaxf(mx, s4.x);
+      if (c + 1 < klen) mx = fmaxf(mx, s4.y);
+      if (c + 2 < klen) mx = fmaxf(mx, s4.z);
+      if (c + 3 < klen) mx = fmaxf(mx, s4.w);
+    }
     mx = warp_max(mx);
     float l = 0.f;
-    for (int c = lane; c < klen; c += 32) l += expf(srow[c] - mx);
+    for (int c = lane * 4; c < klen; c += 128) {
+      const float4 s4 = load4(srow + c);
+      l += (expf(s4.x - mx) + (c + 1 < klen ? expf(s4.y - mx) : 0.f)) + ((c + 2 < klen ? expf(s4.z - mx) : 0.f) + (c + 3 < klen ? expf(s4.w - mx) : 0.f));
+    }
     l = warp_sum(l);
     if (lane == 0) {
       const bool live = (r0 + r) < n_q && l > 0.f;
@@ -171,15 +173,26 @@ __global__ void __launch_bounds__(256) attn_bwd_softmax_kernel(const float* __re
     const int r = warp * 4 + rr;
     const float* srow = Sb + (long long)(r0 + r) * Tkp;
     const float* prow = Pb + (long long)(r0 + r) * Tkp;
+    // 4 consecutive columns per lane (16-byte loads, one Philox counter per quad); rows are padded to Tkp >= klen (multiple of 64)
     float mx = -INFINITY;
-    for (int c = lane; c < klen; c += 32) mx = fmaxf(mx, srow[c]);
+    for (int c = lane * 4; c < klen; c += 128) {
+      const float4 s4 = load4(srow + c);
+      mx = fmaxf(mx, s4.x);
+      if (c + 1 < klen) mx = fmaxf(mx, s4.y);
+      if (c + 2 < klen) mx = fmaxf(mx, s4.z);
+      if (c + 3 < klen) mx = fmaxf(mx, s4.w);
+    }
     mx = warp_max(mx);
     float l = 0.f, dacc = 0.f;
     const long long e_row = (bh * Tqp + r0 + r) * (long long)Tkp;
-    for (int c = lane; c < klen; c += 32) {
-      const float e = expf(srow[c] - mx);
-      l += e;
-      dacc = fmaf(e, prow[c] * keep1(seed, site, e_row + c, thresh, scale), dacc);
+    for (int c = lane * 4; c < klen; c += 128) {
+      const float4 s4 = load4(srow + c), g4 = load4(prow + c);
+      const Keep4 k4 = keep4(seed, site, e_row + c, thresh, scale);
+      const float e0 = expf(s4.x - mx), e1 = c + 1 < klen ? expf(s4.y - mx) : 0.f, e2 = c + 2 < klen ? expf(s4.z - mx) : 0.f,
+                  e3 = c + 3 < klen ? expf(s4.w - mx) : 0.f;
+      l += (e0 + e1) + (e2 + e3);
+      dacc = fmaf(e0, g4.x * k4.x, dacc); dacc = fmaf(e1, g4.y * k4.y, dacc);
+      dacc = fmaf(e2, g4.z * k4.z, dacc); dacc = fmaf(e3, g4.w * k4.w, dacc);
     }
     l = warp_sum(l); dacc = warp_sum(dacc);
     if (lane == 0) {
