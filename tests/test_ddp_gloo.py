@@ -92,3 +92,79 @@ def test_layerdrop_draw_follows_the_reference_rule():
         want = frozenset(i for i in range(12) if not u[i] > p)
         assert EncoderTrainStep.sample_layerdrop(p, np.random.RandomState(seed)) == want
     assert EncoderTrainStep.sample_layerdrop(0.0, np.random.RandomState(1)) == frozenset()
+
+
+_PROBE = ("interlingua_layers.2.fc2.weight", "transformer_layers.0.self_attn.q_proj.weight", "wav2vec_model.encoder.layers.11.fc1.bias",
+          "wav2vec_model.encoder.layers.3.self_attn.out_proj.weight", "wav2vec_model.post_extract_proj.weight",
+          "wav2vec_model.feature_extractor.conv_layers.0.0.weight")
+
+
+def _rank_inputs(rank):
+    from chimera_st_b200 import synth
+    sd = synth.make_state_dict(seed=0, interlingua_length=8, dead_heads=False)
+    wave, tl = synth.make_waveforms([4100, 3300], seed=40 + rank)            # same shapes, different audio per rank (data parallel)
+    R = torch.randn(8, 2, 512, generator=torch.Generator().manual_seed(5))
+    return sd, wave, tl, R
+
+
+def _train_worker(rank, world, port, q):
+    from conftest import ROOT
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from emu import EmuLib
+    from chimera_st_b200.train import EncoderTrainStep
+    torch.set_num_threads(4)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sd, wave, tl, R = _rank_inputs(rank)
+    step = EncoderTrainStep(sd, 2, wave.shape[1], device="cpu", lib=EmuLib())
+    step.forward(wave, tl)
+    names = [(k, v.numel()) for part in step.backward_iter(R) for k, v in part.items()]       # backward order = bucket order
+    red = ddp.GradAllReducer(names, bucket_bytes=8 << 20)
+    step.forward(wave, tl)
+    grads, early = {}, []
+    for part in step.backward_iter(R):                              # the four segments: finished buckets reduce while the next segment runs
+        red.ready(part)
+        grads.update(part)
+        early.append(len(red.inflight))
+    out = red.finish(grads)
+    q.put((rank, early, len(red.buckets), len(names), {n: out[n].reshape(-1)[:4096].numpy().copy() for n in _PROBE},
+           float(sum(float(v.double().sum()) for v in out.values()))))
+    dist.destroy_process_group()
+
+
+def test_two_rank_emulated_training_step_with_overlapped_all_reduce():
+    """The N > 1 training path end to end on CPU: two gloo ranks run the real `EncoderTrainStep` launch sequence (ABI emulator) on
+    different audio, hand the gradients of each backward segment to `GradAllReducer` as they finish, and end with the average of the two
+    ranks' gradients (legacy_distributed_data_parallel.py:94-178: pre-divide by the world size, sum), identical on both ranks."""
+    from conftest import ROOT
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from emu import EmuLib
+    from chimera_st_b200.train import EncoderTrainStep
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    # the expected result, serially, while the ranks work
+    want = None
+    for r in range(2):
+        sd, wave, tl, R = _rank_inputs(r)
+        _, G = EncoderTrainStep(sd, 2, wave.shape[1], device="cpu", lib=EmuLib()).forward_backward(wave, tl, R)
+        want = {k: v / 2 for k, v in G.items()} if want is None else {k: want[k] + G[k] / 2 for k in want}
+    res = sorted([q.get(timeout=600) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, early0, nb, nn, probe0, tot0), (_, early1, _, _, probe1, tot1) = res
+    assert nn == 361 and nb >= 8
+    assert early0[0] >= 1 and early0 == sorted(early0) and early1[0] >= 1    # buckets in flight after the FIRST segment already
+    assert tot0 == tot1                                                      # bit-identical on both ranks
+    for n in _PROBE:
+        assert (probe0[n] == probe1[n]).all(), n
+        ref = want[n].reshape(-1)[:4096]
+        err = float((torch.from_numpy(probe0[n]) - ref).norm() / ref.norm())
+        assert err < 1e-5, (n, err)
