@@ -223,3 +223,45 @@ def test_emulated_dropout_replays_in_the_backward_pass():
     step.next_dropout_seed()
     assert int(step.seed_dev.item()) == 78
     assert rel_l2(step.forward(wave, tl), mem) > 1e-2
+
+
+def test_emulated_text_pass_draws_its_own_dropout_masks():
+    """The text pass of a step shares the layers with the audio pass but not the masks: its sites are numbered separately (pass 1), and
+    replaying them in the oracle's text branch reproduces memories and gradients."""
+    torch.set_num_threads(8)
+    V = 60
+    sd = synth.make_state_dict(seed=2, interlingua_length=8, dead_heads=False, text_vocab=V)
+    gen = torch.Generator().manual_seed(9)
+    tok_len = torch.tensor([7, 4])
+    tokens = torch.randint(4, V, (2, 7), generator=gen)
+    tokens[1, 4:] = 1
+    Rt = torch.randn(8, 2, 512, generator=gen)
+    wave, tl = synth.make_waveforms([4100], seed=5)
+    emu = EmuLib()
+    step = EncoderTrainStep(sd, 1, wave.shape[1], device="cpu", feature_grad_mult=1.0, lib=emu, dropout=0.2, seed=3)
+    text = TextTrainPass(step, 2, 7)
+    step.forward(wave, tl)                                          # audio pass first: registers the pass-0 sites
+    n_audio = len(step._sites)
+    mem_t = text.forward(tokens, tok_len)
+    G = text.backward(Rt)
+    n_text = 1 + 4 * 6 + 4 * 3                                      # embed + (attn, prob, act, ffn) x (6 shared + 3 memory layers)
+    assert len(step._sites) == n_audio + n_text
+    assert all(step._sites[(1, t)] != step._sites[(0, t)] for t in ("embed", "enc0.attn", "mem2.prob"))
+
+    def geom(tag):
+        if tag.endswith(".prob"):
+            return (8, 7) if tag.startswith("mem") else (7, 7)
+        return 8 if tag.startswith("mem") else 7
+    hook, used = oracle_dropout_hook(step, 1, geom, lambda tag: 0.2)
+    sdg = {k: (v.clone().requires_grad_() if v.is_floating_point() else v) for k, v in sd.items()}
+    O.DROPOUT_HOOK = hook
+    try:
+        mt = _pinned(_masks(text.T, 2, 7, 7, 8), lambda: O.encoder_forward_text(sdg, tokens, tok_len)[0])
+    finally:
+        O.DROPOUT_HOOK = None
+    (mt * Rt).sum().backward()
+    ref = {k: v.grad for k, v in sdg.items() if v.is_floating_point() and v.grad is not None}
+    ref["text_embed_tokens.weight"][1] = 0
+    assert len(set(used)) == n_text
+    assert rel_l2(mem_t, mt.detach()) < 1e-5
+    _compare(G, ref)
