@@ -303,7 +303,7 @@ def c5_quick(rank, world, steps=5, dtype=torch.bfloat16, comm_dtype=torch.bfloat
     try:
         gs = None
         step_d = EncoderTrainStep(sd, B, Lw, device="cuda", feature_grad_mult=0.1, dtype=dtype, dropout=0.1, w2v_dropout=0.1,
-                                  w2v_dropout_input=0.1)
+                                  w2v_dropout_input=0.1, seed=1 + rank)
         gs = GraphedTrainStep(step_d, wave, lens, loss_fn)
         gs.reducer = ddp.GradAllReducer(gs.names, world_size=world, bucket_bytes=bucket_mb << 20, comm_dtype=comm_dtype)
         for _ in range(3):
@@ -455,7 +455,7 @@ def run_c5(args, rank, world, local_rank, cores):
     sd = synth.make_state_dict(seed=0, interlingua_length=M, dead_heads=False)
     pdrop = float(getattr(args, "dropout", 0.0))
     step = EncoderTrainStep(sd, B, Lw, device="cuda", feature_grad_mult=0.1, dtype=dtype, dropout=pdrop, w2v_dropout=pdrop,
-                            w2v_dropout_input=pdrop)
+                            w2v_dropout_input=pdrop, seed=1 + rank)          # every rank draws its own masks
     host_w, host_l = host_batch([Lw] * B, seed=1000 * rank)
     wave, lens = host_w.cuda(), host_l.cuda()
     text_mem = torch.randn(M, B, 512, generator=torch.Generator().manual_seed(7 + rank)).cuda()
