@@ -14,7 +14,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "chimera-st_b200", "libchimera_st_b200.so")
 FAMILIES = {"gemm_tc": r"gemm_tc", "attention_tc": r"attention_tc", "conv0_tc": r"conv0_tc", "posconv": r"posconv",
-            "layernorm": r"layernorm", "decoder": r"dec_", "train": r"(_bwd|_grad|loss|adam)"}
+            "layernorm": r"layernorm", "decoder": r"dec_", "train": r"(_bwd|_grad|loss|adam|dropout|colsum|head_pack|transpose)"}
 KEY = ("UTCHMMA", "UTCQMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTCBAR", "UTCCP", "SYNCS", "MUFU", "HMMA", "FFMA2", "FFMA")
 
 
