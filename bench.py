@@ -399,7 +399,8 @@ def run_c5(args, rank, world, local_rank, cores):
     """BASELINE configs[4]: Chimera-16 ST training forward + backward of the encoder / memory path, ~1.2 M audio samples per GPU
     (B = 8 x 150 000), data-parallel over the ranks with a bucketed NCCL all-reduce of the gradients overlapped with the backward
     segments (`chimera_st_b200.ddp`, replacing LegacyDistributedDataParallel).  The loss is the contrastive (InfoNCE) head over the
-    memories against fixed synthetic text-pass memories (triplet_st_mt_contrastive.py:154-169); dropout = LayerDrop = 0.
+    memories against fixed synthetic text-pass memories (triplet_st_mt_contrastive.py:154-169); dropout 0.1 at every site of the recipe
+    (--dropout 0 = the parity configuration), LayerDrop 0 (it needs one CUDA graph per pattern: eager path only).
     step = forward + loss + backward + gradient all-reduce;  value: waveforms resident in HBM;  e2e: pinned host waveforms -> H2D ->
     step -> D2H of the loss."""
     B, Lw, M = C5_B, C5_L, C5_M
@@ -654,8 +655,9 @@ def main():
                     help="c5 = BASELINE configs[4]: training forward + backward of the path with the DDP gradient all-reduce")
     ap.add_argument("--comm-dtype", default="bf16", choices=["bf16", "fp32"], help="c5: dtype of the gradient buckets on the wire")
     ap.add_argument("--bucket-mb", type=int, default=32, help="c5: gradient bucket size")
-    ap.add_argument("--dropout", type=float, default=0.0,
-                    help="c5: probability of the recipe's dropouts (train-en2any-ST.sh uses 0.1); 0 = the parity configuration")
+    ap.add_argument("--dropout", type=float, default=0.1,
+                    help="c5: probability of the recipe's dropouts (train-en2any-ST.sh:45 uses 0.1 = the timing configuration, SURVEY.md §7); "
+                         "0 = the parity configuration")
     ap.add_argument("--utts", type=int, default=512)
     ap.add_argument("--max-tokens", type=int, default=2000000,
                     help="c3 token budget per batch in samples (default: the reference's --max-tokens 2000000, "
