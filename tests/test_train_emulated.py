@@ -265,3 +265,47 @@ def test_emulated_text_pass_draws_its_own_dropout_masks():
     assert len(set(used)) == n_text
     assert rel_l2(mem_t, mt.detach()) < 1e-5
     _compare(G, ref)
+
+
+def test_emulated_training_update_end_to_end():
+    """One whole update on CPU: gradients (emulated launch sequence) -> FusedAdam at the schedule's learning rate -> refresh of the
+    kernel-layout operands -> next forward.  Reference: autograd through the oracle -> the oracle restatement of fairseq's Adam (pinned
+    bit-exactly to the reference class, tests/test_adam.py) -> oracle forward with the updated state dict."""
+    from chimera_st_b200.train import InverseSqrtLR
+    torch.set_num_threads(8)
+    sd = synth.make_state_dict(seed=0, interlingua_length=8, dead_heads=False)
+    wave, tl = synth.make_waveforms([4300, 3100], seed=12)
+    R = torch.randn(8, 2, 512, generator=torch.Generator().manual_seed(2))
+    emu = EmuLib()
+    # the step keeps the master parameters it is given (no copy on the same device): hand it its own tensors
+    step = EncoderTrainStep({k: v.clone() for k, v in sd.items()}, 2, wave.shape[1], device="cpu", feature_grad_mult=0.1, lib=emu)
+    g = step.g
+    step.forward(wave, tl)
+    G = step.backward(R)
+    masks = _masks(step.T, g.B, g.T2a, g.T2, 8)
+    lr = InverseSqrtLR(1e-2, 10).at(5)                              # mid warm-up: 5e-3
+    hp = dict(betas=(0.9, 0.98), eps=1e-8, weight_decay=1e-4)
+    opt = FusedAdam({k: step.sd[k] for k in G}, lr=1.0, lib=emu, **hp)
+    opt.advance(lr=lr)
+    opt.step({k: v.contiguous() for k, v in G.items()})
+    step.refresh_weights()
+    mem1 = step.forward(wave, tl)
+    # reference update
+    _, ref = _autograd(sd, lambda s: O.encoder_forward(s, wave, tl)[0], R, masks)
+    sd_ref = {k: v.clone() for k, v in sd.items()}
+    flips = total = 0
+    for k, gr in ref.items():
+        if float(gr.abs().max()) == 0 and k not in G:
+            continue
+        gr = gr * (0.1 if ".feature_extractor." in k else 1.0)     # GradMultiply(0.1) (wav2vec2.py:530-532)
+        p = sd_ref[k]
+        adam_oracle.adam_step(p, gr, torch.zeros_like(p), torch.zeros_like(p), 1, lr=lr, **hp)
+        # the first Adam step moves every element by ~lr * sign(g): elements whose gradient is rounding noise may go either way
+        d = (step.sd[k].reshape(p.shape) - p).abs() > 0.5 * lr
+        flips += int(d.sum()); total += p.numel()
+    assert flips < 5e-4 * total, (flips, total)                     # measured 5.7e-5
+    mem1_ref, _ = O.encoder_forward(sd_ref, wave, tl)
+    # the updated operands reached the kernels: the new memories follow the reference's (far from the old ones, close to the new)
+    mem0_ref, _ = O.encoder_forward(sd, wave, tl)
+    assert rel_l2(mem1, mem0_ref) > 20 * rel_l2(mem1, mem1_ref)
+    assert rel_l2(mem1, mem1_ref) < 1e-3                            # measured 5.9e-5 (against 5.06 to the old memories)
