@@ -242,6 +242,8 @@ class EncoderTrainStep:
         sd = _weights._strip(state_dict)
         if any(k.startswith(("audio_exclusive_layers.", "modal_embedding.")) for k in sd):
             raise NotImplementedError("EncoderTrainStep: modal_embedding / non_shared_encoder_layers checkpoints are inference-only here")
+        # fp32 master parameters under the reference names; tensors that already are fp32 on `dev` are NOT copied: an optimizer updating
+        # `self.sd` in place (FusedAdam) then updates the caller's tensors too -- pass clones to keep the originals
         self.sd = {k: v.detach().to(dev, F32) for k, v in sd.items() if v.is_floating_point()}
         self.M = M or self.sd["interlingua_embedding.weight"].shape[0]
         self.g = Geometry(B, Lw, self.M)
