@@ -102,7 +102,7 @@ _PROBE = ("interlingua_layers.2.fc2.weight", "transformer_layers.0.self_attn.q_p
 def _rank_inputs(rank):
     from chimera_st_b200 import synth
     sd = synth.make_state_dict(seed=0, interlingua_length=8, dead_heads=False)
-    wave, tl = synth.make_waveforms([4100, 3300], seed=40 + rank)            # same shapes, different audio per rank (data parallel)
+    wave, tl = synth.make_waveforms([3000, 2400], seed=40 + rank)            # same shapes, different audio per rank (data parallel)
     R = torch.randn(8, 2, 512, generator=torch.Generator().manual_seed(5))
     return sd, wave, tl, R
 
@@ -119,11 +119,11 @@ def _train_worker(rank, world, port, q):
     sd, wave, tl, R = _rank_inputs(rank)
     step = EncoderTrainStep(sd, 2, wave.shape[1], device="cpu", lib=EmuLib())
     step.forward(wave, tl)
-    names = [(k, v.numel()) for part in step.backward_iter(R) for k, v in part.items()]       # backward order = bucket order
+    parts = list(step.backward_iter(R))                             # the four backward segments, in the order they finish
+    names = [(k, v.numel()) for part in parts for k, v in part.items()]                        # backward order = bucket order
     red = ddp.GradAllReducer(names, bucket_bytes=8 << 20)
-    step.forward(wave, tl)
     grads, early = {}, []
-    for part in step.backward_iter(R):                              # the four segments: finished buckets reduce while the next segment runs
+    for part in parts:                                              # hand-over per segment: finished buckets reduce before the rest arrives
         red.ready(part)
         grads.update(part)
         early.append(len(red.inflight))
