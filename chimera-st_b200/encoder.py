@@ -231,7 +231,8 @@ class B200InterlinguaEncoder(nn.Module):
         if not src_tokens.dtype.is_floating_point and src_tokens.dtype != torch.int16 and not allow_text:
             raise NotImplementedError("integer (text) tokens are only accepted by forward()")
         if self.training:
-            raise NotImplementedError("training-mode forward (dropout / LayerDrop) is not implemented; call .eval()")
+            raise NotImplementedError("the module's forward is the eval() path; the training step (dropout, LayerDrop, backward) is "
+                                      "chimera_st_b200.train.EncoderTrainStep")
         if src_tokens.dim() != 2 or src_lengths.shape != (src_tokens.shape[0],):
             raise ValueError("expected src_tokens [B,L], src_lengths [B]")
         # Precondition of the frame-mask rule (a4): the batch is padded exactly to its longest utterance, as the
