@@ -144,3 +144,51 @@ def test_gemm_rejects_bad_arguments_without_touching_the_device():
     p = _lib.GemmParams()
     assert lib.cst_gemm(C.byref(p), None) != 0
     assert b"null pointer" in lib.cst_last_error()
+
+
+def test_ctypes_signatures_agree_with_the_header_prototypes():
+    """Every prototype in include/chimera_st_b200.h against the ctypes signature the host side binds (_lib._SIGS): same number of
+    arguments, and per argument the same class (pointer / float / 64-bit integer / 32-bit integer) -- ABI drift between the header, the
+    library and the binding shows up here, without a GPU."""
+    import ctypes as C
+    hdr = open(os.path.join(ROOT, "include", "chimera_st_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    hdr = re.sub(r"//[^\n]*", "", hdr)
+    protos = re.findall(r"\b(?:int|long long|const char\*|void)\s+(cst_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S)
+    assert len(protos) >= 40
+
+    def klass_c(arg):
+        arg = " ".join(arg.split())
+        if "*" in arg:
+            return "ptr"
+        base = arg.rsplit(" ", 1)[0] if " " in arg else arg
+        if base in ("float",):
+            return "f32"
+        if base in ("long long", "int64_t", "unsigned long long", "size_t"):
+            return "i64"
+        if base in ("int", "unsigned int", "unsigned", "int32_t", "uint32_t"):
+            return "i32"
+        raise AssertionError("unclassified header argument: %r" % arg)
+
+    def klass_py(t):
+        if t in (C.c_void_p, C.c_char_p) or hasattr(t, "contents") or getattr(t, "_type_", None) is not None and issubclass(t, C._Pointer):
+            return "ptr"
+        if t is C.c_float:
+            return "f32"
+        if t in (C.c_longlong, C.c_ulonglong, C.c_int64, C.c_uint64, C.c_size_t):
+            return "i64"
+        if t in (C.c_int, C.c_uint, C.c_int32, C.c_uint32):
+            return "i32"
+        raise AssertionError("unclassified ctypes argument: %r" % (t,))
+    checked = 0
+    for name, args in protos:
+        if name not in _lib._SIGS:
+            continue
+        _, argtypes = _lib._SIGS[name]
+        cargs = [a for a in (x.strip() for x in args.split(",")) if a and a != "void"]
+        assert len(cargs) == len(argtypes), (name, len(cargs), len(argtypes))
+        got = [klass_py(t) for t in argtypes]
+        want = [klass_c(a) for a in cargs]
+        assert got == want, (name, [(i, w, g) for i, (w, g) in enumerate(zip(want, got)) if w != g])
+        checked += 1
+    assert checked == len(_lib._SIGS) == len(protos), (checked, len(_lib._SIGS), len(protos))
